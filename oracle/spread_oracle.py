@@ -1,0 +1,463 @@
+"""CPU oracle (numpy) for the Wannier.jl spread / gradient hot path.
+
+TEST INFRASTRUCTURE ONLY.  This module is a CPU restatement of the reference
+algorithm; it is the *checker* for the CUDA path.  Only ``tests/``,
+``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl
+reference`` legs may import it.  Nothing under ``wannier.jl_b200/`` imports it.
+
+Parity pin: the reference is Julia and cannot run here; the restatement is
+pinned against the reference's own in-tree known answers (see
+``tests/golden/make_golden.py`` and ``tests/test_oracle_golden.py``):
+W90 ``m_matrix`` in ``test/fixtures/silicon/silicon.chk.fmt``, the ``.wout``
+final state, the constants in ``test/localization/max_localize.jl:52-55`` and
+the finite-difference protocol of ``test/localization/max_localize.jl:11-43`` /
+``test/localization/disentangle.jl:27-54``.
+
+Array conventions (math indexing, numpy C order):
+    M[k, b]      nb x nb complex   overlap  M_kb[m, l]
+    U[k]         nb x nw complex   gauge    U_k[m, n]
+    kpb_k[k, b]  0-based index of the k+b neighbour
+    bvec[k, b]   Cartesian b-vector (1/Angstrom)
+    wb[b]        b-vector weight (Angstrom^2), indexed by POSITION b
+All citations are relative to /root/reference.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+# --------------------------------------------------------------------------
+# small helpers
+# --------------------------------------------------------------------------
+def imaglog(z):
+    """Im ln z.  src/utils/linalg.jl:15  (atan(imag z, real z))."""
+    return np.arctan2(np.imag(z), np.real(z))
+
+
+def orthonorm_lowdin(A):
+    """Lowdin orthonormalisation A -> W V^H from svd.  src/utils/linalg.jl:25-29.
+    Works on a single matrix or a stack [..., m, n]."""
+    W, _, Vh = np.linalg.svd(A, full_matrices=False)
+    return W @ Vh
+
+
+def reciprocal_lattice(lattice):
+    """Columns of ``lattice`` are the lattice vectors (Angstrom); returns the matrix
+    whose columns are the reciprocal vectors, 2*pi*inv(lattice)^T
+    (WannierIO get_recip_lattice, used at src/io/w90/model.jl:21)."""
+    return 2.0 * np.pi * np.linalg.inv(lattice).T
+
+
+def bvectors_cart(recip_lattice, kpoints, kpb_k, kpb_G):
+    """b for every pair: recip_lattice * (kpoints[kpb_k] + kpb_G - kpoints[k]).
+    src/spread.jl:293 (same expression at :434, :580)."""
+    kpoints = np.asarray(kpoints, dtype=np.float64)
+    d = kpoints[kpb_k] + np.asarray(kpb_G, dtype=np.float64) - kpoints[:, None, :]
+    return d @ np.asarray(recip_lattice).T  # [k, b, 3]
+
+
+def compute_bweights(bvectors, atol=1e-6, sigma_atol=1e-5):
+    """B1 weights (MV1997 Eq. B1) for an already-complete flat list of b-vectors.
+    src/kpoints/kstencil.jl:132-170 + kstencil_shell.jl:341-391.
+    Shells = groups of equal |b|; solve  sum_shell w_s * triu(sum_b b b^T) = triu(I)
+    shell by shell via SVD, dropping shells that make the system singular.
+    Note: the reference's final remap (kstencil.jl:167-169) indexes
+    ``mappings[perm[i]]``; for one shell, or input already sorted by norm, that equals
+    the intended ``w[shell_of(b_i)]`` which is what is returned here."""
+    bvectors = np.asarray(bvectors, dtype=np.float64)
+    norms = np.linalg.norm(bvectors, axis=1)
+    perm = np.argsort(norms, kind="stable")
+    sorted_norms = norms[perm]
+    shells = []
+    i = 0
+    while i < len(perm):
+        idx = np.nonzero(np.abs(sorted_norms - sorted_norms[i]) <= atol)[0]
+        shells.append(idx)
+        i += len(idx)
+    iu = np.triu_indices(3)
+    # column-by-column upper triangle like Julia's m[triu!(trues)] : (1,1),(1,2),(2,2),(1,3),(2,3),(3,3)
+    order = sorted(range(6), key=lambda t: (iu[1][t], iu[0][t]))
+    tri = lambda m: m[iu][order]
+    target = tri(np.eye(3))
+    B = np.zeros((6, len(shells)))
+    W = np.zeros(len(shells))
+    keep = []
+    done = False
+    for ish, idx in enumerate(shells):
+        keep.append(ish)
+        b = bvectors[perm[idx]].T  # 3 x ndegen
+        B[:, ish] = tri(b @ b.T)
+        Um, S, Vh = np.linalg.svd(B[:, keep], full_matrices=False)
+        if np.all(S > sigma_atol):
+            W[keep] = Vh.T @ ((Um.T @ target) / S)
+            if np.allclose(B[:, keep] @ W[keep], target, rtol=0, atol=atol):
+                done = True
+                break
+        else:
+            keep.pop()
+    if not done:
+        raise ValueError("not enough shells to satisfy B1 condition")
+    w = np.zeros(len(bvectors))
+    for ish, idx in enumerate(shells):
+        w[perm[idx]] = W[ish]
+    return w
+
+
+# --------------------------------------------------------------------------
+# rotation of overlaps
+# --------------------------------------------------------------------------
+def compute_MU_UtMU(M, kpb_k, U):
+    """MU_kb = M_kb U_{k+b};  N_kb = U_k^H MU_kb.   src/spread.jl:164-195."""
+    Ukpb = U[kpb_k]                       # [k, b, nb, nw]
+    MU = M @ Ukpb                         # [k, b, nb, nw]
+    N = np.conj(np.swapaxes(U, -1, -2))[:, None] @ MU  # [k, b, nw, nw]
+    return MU, N
+
+
+def transform_gauge(M, kpb_k, U):
+    """All N_kb = U_k^H M_kb U_{k+b}.  src/localization/gauge.jl:83-98."""
+    return compute_MU_UtMU(M, kpb_k, U)[1]
+
+
+# --------------------------------------------------------------------------
+# spread, centres
+# --------------------------------------------------------------------------
+def center_from_N(N, bvec, wb):
+    """r_n = -(1/nk) sum_{k,b} w_b b Im ln N_nn.  src/spread.jl:565-594."""
+    nk = N.shape[0]
+    phi = imaglog(np.diagonal(N, axis1=-2, axis2=-1))        # [k, b, n]
+    r = -np.einsum("b,kbx,kbn->nx", wb, bvec, phi)
+    return r / nk
+
+
+def omega_from_N(N, bvec, wb):
+    """Spread decomposition from the rotated overlaps.  src/spread.jl:254-360.
+    Returns dict(Omega, OmegaI, OmegaOD, OmegaD, OmegaTilde, omega[nw], r[nw,3])."""
+    nk, nn, nw, _ = N.shape
+    a2 = np.abs(N) ** 2                                        # :304
+    ts = a2.sum(axis=(-1, -2))                                 # :305  ||N||_F^2
+    dN = np.diagonal(N, axis1=-2, axis2=-1)                    # [k,b,n]
+    phi = imaglog(dN)                                          # :308
+    a2d = np.abs(dN) ** 2
+    r = -np.einsum("b,kbx,kbn->nx", wb, bvec, phi) / nk        # :310, :324
+    r2 = np.einsum("b,kbn->n", wb, 1.0 - a2d + phi ** 2) / nk  # :311, :325
+    OmegaI = np.einsum("b,kb->", wb, nw - ts) / nk             # :318, :326
+    OmegaOD = np.einsum("b,kb->", wb, ts - a2d.sum(-1)) / nk   # :313, :320, :327
+    omega = r2 - (r ** 2).sum(axis=1)                          # :351
+    Omega = omega.sum()                                        # :353
+    OmegaTilde = Omega - OmegaI                                # :355
+    OmegaD = OmegaTilde - OmegaOD                              # :356
+    return dict(Omega=Omega, OmegaI=OmegaI, OmegaOD=OmegaOD, OmegaD=OmegaD,
+                OmegaTilde=OmegaTilde, omega=omega, r=r)
+
+
+def omega(M, kpb_k, bvec, wb, U):
+    """omega(stencil, M, U).  src/spread.jl:377-381."""
+    _, N = compute_MU_UtMU(M, kpb_k, U)
+    return omega_from_N(N, bvec, wb)
+
+
+def center(M, kpb_k, bvec, wb, U):
+    """center(stencil, M, U).  src/spread.jl:560-564."""
+    _, N = compute_MU_UtMU(M, kpb_k, U)
+    return center_from_N(N, bvec, wb)
+
+
+def omega_center(sp, r0, lam):
+    """Centre-penalty totals.  src/spread.jl:246-252."""
+    omegac = lam * ((sp["r"] - r0) ** 2).sum(axis=1)
+    out = dict(sp)
+    out.update(omegac=omegac, omegat=sp["omega"] + omegac,
+               Omegac=omegac.sum(), Omegat=sp["Omega"] + omegac.sum())
+    return out
+
+
+def omega_local(M, kpb_k, wb, U):
+    """Per-k local contribution to <r^2>.  src/spread.jl:522-548."""
+    _, N = compute_MU_UtMU(M, kpb_k, U)
+    dN = np.diagonal(N, axis1=-2, axis2=-1)
+    return np.einsum("b,kbn->k", wb, 1.0 - np.abs(dN) ** 2 + imaglog(dN) ** 2)
+
+
+# --------------------------------------------------------------------------
+# gradient
+# --------------------------------------------------------------------------
+def penalty_r(r, r0=None, lam=0.0):
+    """SpreadPenalty: identity; CenterSpreadPenalty: r - lam (r - r0).
+    src/spread.jl:203-227."""
+    if r0 is None:
+        return r
+    return r - lam * (r - r0)
+
+
+def omega_grad_from_MU_N(MU, N, bvec, wb, r0=None, lam=0.0):
+    """G_k = (4/nk) sum_b w_b MU_kb diag(t_n - conj N_nn),
+    t_n = -i q_n / N_nn, q_n = Im ln N_nn + penalty(r_n) . b.   src/spread.jl:398-481."""
+    nk = MU.shape[0]
+    r = center_from_N(N, bvec, wb)                             # :411
+    rt = penalty_r(r, r0, lam)
+    dN = np.diagonal(N, axis1=-2, axis2=-1)                    # [k,b,n]
+    q = imaglog(dN) + np.einsum("nx,kbx->kbn", rt, bvec)       # :459
+    t = -1j * q / dN                                           # :461
+    c = t - np.conj(dN)                                        # :470
+    G = 4.0 * np.einsum("b,kbmn,kbn->kmn", wb, MU, c)          # :474
+    return G / nk                                              # :478
+
+
+def omega_grad(M, kpb_k, bvec, wb, U, r0=None, lam=0.0):
+    """omega_grad([penalty,] stencil, M, U).  src/spread.jl:496-501."""
+    MU, N = compute_MU_UtMU(M, kpb_k, U)
+    return omega_grad_from_MU_N(MU, N, bvec, wb, r0, lam)
+
+
+def fg_maxloc(M, kpb_k, bvec, wb, U, r0=None, lam=0.0):
+    """One fg!(F, G, U) of src/localization/max_localize.jl:13-23: returns (Omega, G)."""
+    MU, N = compute_MU_UtMU(M, kpb_k, U)
+    G = omega_grad_from_MU_N(MU, N, bvec, wb, r0, lam)
+    sp = omega_from_N(N, bvec, wb)
+    f = sp["Omega"] if r0 is None else omega_center(sp, r0, lam)["Omegat"]   # spread.jl:220
+    return f, G
+
+
+# --------------------------------------------------------------------------
+# Stiefel manifold pieces (Optim.jl Stiefel_SVD used at max_localize.jl:62-63)
+# --------------------------------------------------------------------------
+def stiefel_retract(X):
+    """retract!: X <- polar factor of X (U V^H from svd), per k."""
+    return orthonorm_lowdin(X)
+
+
+def stiefel_project_tangent(G, X):
+    """project_tangent!: G <- G - X (X^H G + G^H X)/2, per k."""
+    XG = np.conj(np.swapaxes(X, -1, -2)) @ G
+    return G - X @ ((XG + np.conj(np.swapaxes(XG, -1, -2))) / 2)
+
+
+# --------------------------------------------------------------------------
+# (X, Y) parametrisation for disentanglement
+# --------------------------------------------------------------------------
+def X_Y_to_U(X, Y):
+    """U_k = Y_k X_k.  src/localization/disentangle.jl:351-356."""
+    return Y @ X
+
+
+def XY_to_X_Y(XY, nb, nw):
+    """Column k of XY = [vec(X_k); vec(Y_k)], column-major vec.
+    src/localization/disentangle.jl:424-435.  XY has shape [nk, nw*nw + nb*nw]
+    (numpy row k == Julia column k)."""
+    nk = XY.shape[0]
+    X = XY[:, : nw * nw].reshape(nk, nw, nw).transpose(0, 2, 1)
+    Y = XY[:, nw * nw:].reshape(nk, nw, nb).transpose(0, 2, 1)
+    return np.ascontiguousarray(X), np.ascontiguousarray(Y)
+
+
+def X_Y_to_XY(X, Y):
+    """Inverse packing.  src/localization/disentangle.jl:454-466."""
+    nk = X.shape[0]
+    return np.concatenate([X.transpose(0, 2, 1).reshape(nk, -1),
+                           Y.transpose(0, 2, 1).reshape(nk, -1)], axis=1)
+
+
+def GU_to_GX_GY(G, X, Y, frozen):
+    """G_X = Y^H G, G_Y = G X^H, zero G_Y[frozen rows, :] and G_Y[:, :n_froz].
+    src/localization/disentangle.jl:481-501."""
+    GX = np.conj(np.swapaxes(Y, -1, -2)) @ G
+    GY = G @ np.conj(np.swapaxes(X, -1, -2))
+    GY = GY.copy()
+    for k in range(G.shape[0]):
+        nf = int(frozen[k].sum())
+        GY[k][frozen[k], :] = 0
+        GY[k][:, :nf] = 0
+    return GX, GY
+
+
+def fg_disentangle(M, kpb_k, bvec, wb, XY, nb, nw, frozen, r0=None, lam=0.0):
+    """fg!(Omega, G, XY) of src/localization/disentangle.jl:586-614."""
+    X, Y = XY_to_X_Y(XY, nb, nw)
+    U = X_Y_to_U(X, Y)
+    f, GU = fg_maxloc(M, kpb_k, bvec, wb, U, r0, lam)
+    GX, GY = GU_to_GX_GY(GU, X, Y, frozen)
+    return f, X_Y_to_XY(GX, GY)
+
+
+def orthonorm_freeze(U, frozen, atol=1e-10):
+    """src/localization/disentangle.jl:223-281 (one k-point)."""
+    nb, nw = U.shape
+    nonf = ~frozen
+    Uf = U[frozen, :]
+    if Uf.shape[0] > 0:
+        Uf = orthonorm_lowdin(Uf)
+    Ur = U[nonf, :]
+    Ur = Ur - Ur @ np.conj(Uf.T) @ Uf
+    A, S, Bh = np.linalg.svd(Ur, full_matrices=False)
+    assert int((S > atol).sum()) == nw - int(frozen.sum()), S
+    S = (S > atol).astype(np.float64)
+    Ur = (A * S) @ Bh
+    V = np.empty_like(U)
+    V[frozen, :] = Uf
+    V[nonf, :] = Ur
+    return V
+
+
+def U_to_X_Y(U, frozen):
+    """src/localization/disentangle.jl:369-402."""
+    nk, nb, nw = U.shape
+    X = np.zeros((nk, nw, nw), dtype=U.dtype)
+    Y = np.zeros((nk, nb, nw), dtype=U.dtype)
+    for k in range(nk):
+        f = frozen[k]
+        nf = int(f.sum())
+        Af = orthonorm_freeze(U[k], f)
+        Ur = Af[~f, :]
+        Yk = Y[k]
+        rows_f = np.nonzero(f)[0]
+        Yk[rows_f, np.arange(nf)] = 1.0
+        if nf != nw:
+            Pr = Ur @ np.conj(Ur.T)
+            Pr = (Pr + np.conj(Pr.T)) / 2
+            _, V = np.linalg.eigh(Pr)
+            rows_nf = np.nonzero(~f)[0]
+            Yk[np.ix_(rows_nf, np.arange(nf, nw))] = V[:, V.shape[1] - (nw - nf):]
+        X[k] = orthonorm_lowdin(np.conj(Yk.T) @ Af)
+    return X, Y
+
+
+def zero_froz_grad(Gxy, frozen, nb, nw):
+    """src/localization/disentangle.jl:563-579 (test helper)."""
+    GX, GY = XY_to_X_Y(Gxy, nb, nw)
+    GY = GY.copy()
+    for k in range(GY.shape[0]):
+        nf = int(frozen[k].sum())
+        GY[k][frozen[k], :] = 0
+        GY[k][:, :nf] = 0
+    return X_Y_to_XY(GX, GY)
+
+
+# --------------------------------------------------------------------------
+# k-space position operator / Berry connection ("next" rows)
+# --------------------------------------------------------------------------
+def berry_connection_kspace(M, kpb_k, bvec, wb, U, imlog_diag=True, force_hermiticity=True):
+    """A^W_k[m,n,alpha].  src/spread.jl:747-793."""
+    _, N = compute_MU_UtMU(M, kpb_k, U)
+    nk, nn, nw, _ = N.shape
+    eye = np.eye(nw)
+    Nn = 1j * (N - eye)
+    if imlog_diag:
+        idx = np.arange(nw)
+        Nn[..., idx, idx] = -imaglog(N[..., idx, idx])
+    A = np.einsum("b,kbx,kbmn->kmnx", wb, bvec, Nn)
+    if force_hermiticity:
+        A = (A + np.conj(A.transpose(0, 2, 1, 3))) / 2
+    return A
+
+
+def position_op(M, kpb_k, bvec, wb, U):
+    """R[m,n,alpha].  src/spread.jl:674-716."""
+    _, N = compute_MU_UtMU(M, kpb_k, U)
+    nk, nn, nw, _ = N.shape
+    R = np.einsum("b,kbx,kbmn->mnx", wb, bvec, N - np.eye(nw))
+    return R / (-1j * nk)
+
+
+# --------------------------------------------------------------------------
+# Riemannian L-BFGS driver (stands in for Optim.jl at max_localize.jl:73-84)
+# --------------------------------------------------------------------------
+def _rdot(a, b):
+    return float(np.real(np.vdot(a, b)))
+
+
+def lbfgs_stiefel(fg, x0, retract, project, f_tol=1e-7, g_tol=1e-5, max_iter=200, m=3,
+                  verbose=False):
+    """Manifold L-BFGS with a strong-Wolfe bracketing line search.
+
+    Optim.jl's exact LBFGS/HagerZhang trajectory is third-party code that is not in
+    /root/reference (Project.toml compat Optim = "1.7"); only the converged optimum is
+    pinnable (test/localization/max_localize.jl:52-55).  Same stopping rules as
+    Optim.Options at max_localize.jl:77-83: |f - f_prev| <= f_tol*|f| or max|g| <= g_tol.
+    The CUDA driver (csrc/optimizer.cu) implements this same algorithm."""
+    x = retract(x0)
+    f, g = fg(x)
+    g = project(g, x)
+    S, Yh, rho = [], [], []
+    it = 0
+    hist = [f]
+    while it < max_iter:
+        if np.max(np.abs(g)) <= g_tol:
+            break
+        # two-loop recursion
+        q = g.copy()
+        al = []
+        for s, y, r_ in zip(reversed(S), reversed(Yh), reversed(rho)):
+            a = r_ * _rdot(s, q)
+            al.append(a)
+            q -= a * y
+        if S:
+            q *= _rdot(S[-1], Yh[-1]) / _rdot(Yh[-1], Yh[-1])
+        for (s, y, r_), a in zip(zip(S, Yh, rho), reversed(al)):
+            b = r_ * _rdot(y, q)
+            q += (a - b) * s
+        d = project(-q, x)
+        dphi0 = _rdot(g, d)
+        if dphi0 >= 0:
+            d = -g
+            dphi0 = _rdot(g, d)
+            S, Yh, rho = [], [], []
+        alpha = 1.0 if S else min(1.0, 1.0 / max(np.sqrt(_rdot(g, g)), 1e-300))
+
+        def phi(a_):
+            xn = retract(x + a_ * d)
+            fn, gn = fg(xn)
+            gn = project(gn, xn)
+            return fn, gn, xn, _rdot(gn, project(d, xn))
+
+        c1, c2 = 1e-4, 0.9
+        lo, hi = 0.0, None
+        f_lo, d_lo = f, dphi0
+        best = None
+        for _ in range(30):
+            fn, gn, xn, dn = phi(alpha)
+            if fn > f + c1 * alpha * dphi0 or (best is not None and fn >= f_lo and lo > 0):
+                hi = alpha
+            elif abs(dn) <= -c2 * dphi0:
+                best = (fn, gn, xn)
+                break
+            elif dn >= 0:
+                hi = alpha
+            else:
+                lo, f_lo, d_lo = alpha, fn, dn
+                best = (fn, gn, xn)
+            if hi is None:
+                alpha *= 2.0
+            else:
+                alpha = 0.5 * (lo + hi)
+        if best is None:
+            break
+        fn, gn, xn = best
+        s = project(xn - x, xn)
+        y = gn - project(g, xn)
+        sy = _rdot(s, y)
+        if sy > 1e-14 * np.sqrt(_rdot(s, s) * _rdot(y, y)):
+            S.append(s); Yh.append(y); rho.append(1.0 / sy)
+            if len(S) > m:
+                S.pop(0); Yh.pop(0); rho.pop(0)
+        # transport history to the new tangent space by projection
+        S = [project(v, xn) for v in S]
+        Yh = [project(v, xn) for v in Yh]
+        df = abs(fn - f)
+        x, f_prev, f, g = xn, f, fn, gn
+        hist.append(f)
+        it += 1
+        if verbose:
+            print(f"iter {it:4d} f={f:.12f} |g|inf={np.max(np.abs(g)):.3e}")
+        if df <= f_tol * abs(f):
+            break
+    return x, f, it, hist
+
+
+def max_localize(M, kpb_k, bvec, wb, U0, r0=None, lam=0.0, f_tol=1e-7, g_tol=1e-5,
+                 max_iter=200, m=3, verbose=False):
+    """max_localize(model).  src/localization/max_localize.jl:44-101."""
+    assert U0.shape[1] == U0.shape[2], "n_bands != n_wann, run instead disentanglement?"
+    fg = lambda U: fg_maxloc(M, kpb_k, bvec, wb, U, r0, lam)
+    return lbfgs_stiefel(fg, U0, stiefel_retract, stiefel_project_tangent,
+                         f_tol, g_tol, max_iter, m, verbose)
