@@ -1,0 +1,155 @@
+/* wannier_b200.h — C-ABI of libwannier_b200.so
+ *
+ * B200 (sm_100a) implementation of the Marzari-Vanderbilt spread / gradient hot path of
+ * Wannier.jl.  The reference has NO FFI for this path (it is plain Julia generic functions),
+ * so every entry point below names the Julia function (file:line under the reference tree) it
+ * replaces; INTEGRATION.md shows the `ccall` wrapper a maintainer adds on the Julia side.
+ *
+ * Conventions
+ *   - complex = double[2] interleaved (re, im), matrices column-major: byte-identical to
+ *     Julia `Array{ComplexF64}` / `Matrix{ComplexF64}`.
+ *   - U    : [nk_total][nw][nb]   (Julia U[:, :, ik], nb x nw col-major, k slowest)
+ *   - M    : [nk][nn][nb][nb]     (Julia M[ik][ib], nb x nb col-major) for the k-slab of the ctx
+ *   - G    : [nk][nw][nb]         gradient for the k-slab of the ctx
+ *   - indices are 0-based int32; `kpb_k` holds GLOBAL k indices (0 <= idx < nk_total)
+ *   - every function returns 0 on success and a negative wb200_status otherwise; the message is
+ *     available from wb200_last_error().  There is no CPU fallback: wb200_create fails without
+ *     an sm_100 device.
+ *   - a ctx is bound to ONE device and is not thread-safe (same contract as the reference's
+ *     `Cache`, src/spread.jl:127-162, which is captured mutably by the fg! closure).
+ *   - "host" entry points take host pointers, copy in/out and block until done.
+ *     "_dev" entry points take device pointers valid on the ctx's device, enqueue on the ctx's
+ *     stream (wb200_set_stream) and do not synchronise unless documented.
+ */
+#ifndef WANNIER_B200_H
+#define WANNIER_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct wb200_ctx wb200_ctx;
+
+enum wb200_status {
+    WB200_OK = 0,
+    WB200_ERR_ARG = -1,       /* bad argument (shape, null pointer, index out of range) */
+    WB200_ERR_CUDA = -2,      /* CUDA runtime error; see wb200_last_error */
+    WB200_ERR_NODEVICE = -3,  /* no sm_100 device */
+    WB200_ERR_NOCONV = -4,    /* iterative routine (polar factor, line search) did not converge */
+    WB200_ERR_SINGULAR = -5   /* |N_nn| < 1e-10: the reference's "N^kb too small" (opt_rotate.jl:60-62) */
+};
+
+/* flags for wb200_create */
+#define WB200_FLAG_DEFAULT 0u
+#define WB200_FLAG_NO_TENSOR 1u   /* force the CUDA-core FP64 rotation kernel even where DMMA applies */
+#define WB200_FLAG_FORCE_TENSOR 2u /* fail instead of falling back when the DMMA kernel cannot be used */
+
+/* ---- context --------------------------------------------------------------------------------
+ * Replaces `Cache(model)` (src/spread.jl:139-162) + the stencil fields read by the hot loops
+ * (src/kpoints/kstencil.jl:19-60).  Uploads M once (it is never written by the optimiser,
+ * src/localization/max_localize.jl:10-26) and owns all work buffers.
+ *   device     CUDA device ordinal
+ *   nb nw      n_bands, n_wann          nk_total  number of k-points of the model
+ *   k_begin,nk the contiguous k-slab [k_begin, k_begin+nk) this ctx owns (single GPU: 0, nk_total)
+ *   nn         number of b-vectors per k-point
+ *   kpb_k      [nk][nn]  global index of k+b                      (stencil.kpb_k, 0-based)
+ *   bvec_cart  [nk][nn][3] recip_lattice*(k[kpb]+G-k[ik]) in 1/A  (src/spread.jl:293)
+ *   bweights   [nn] w_b in A^2, indexed by position ib             (stencil.bweights)
+ *   M          [nk][nn][nb*nb] complex                             (model.overlaps)
+ *              M alone may also be a DEVICE pointer (unified addressing decides; a 13 GB overlap
+ *              set produced on the GPU need not bounce through the host).                        */
+int wb200_create(wb200_ctx** out, int device, int nb, int nw, int nk_total, int k_begin, int nk,
+                 int nn, const int32_t* kpb_k, const double* bvec_cart, const double* bweights,
+                 const double* M, unsigned flags);
+void wb200_destroy(wb200_ctx* ctx);
+const char* wb200_last_error(const wb200_ctx* ctx); /* ctx may be NULL: last create error */
+const char* wb200_version(void);
+/* use the given cudaStream_t (e.g. torch's current stream) for all subsequent work; NULL = the
+ * ctx's own stream */
+int wb200_set_stream(wb200_ctx* ctx, void* cuda_stream);
+int wb200_synchronize(wb200_ctx* ctx);
+/* which rotation kernel the ctx selected: 0 = CUDA-core FP64, 1 = FP64 DMMA tensor path */
+int wb200_rotation_kernel(const wb200_ctx* ctx);
+/* number of kernel launches issued by this ctx since creation (bench.py's gpu_launches) */
+long long wb200_launch_count(const wb200_ctx* ctx);
+
+/* CenterSpreadPenalty(r0, lambda) (src/spread.jl:214-227); r0 = NULL restores SpreadPenalty. */
+int wb200_set_penalty(wb200_ctx* ctx, const double* r0 /*[nw][3]*/, double lambda);
+/* frozen_bands of the disentanglement (src/localization/disentangle.jl:481-501), [nk][nb] 0/1 */
+int wb200_set_frozen(wb200_ctx* ctx, const uint8_t* frozen);
+
+/* ---- host-pointer entry points (the drop-in calls) -------------------------------------------
+ * wb200_fg      = fg!(F, G, U) of get_fg!_maxloc (src/localization/max_localize.jl:13-23):
+ *                 compute_MU_UtMU! (spread.jl:164-195) -> omega_grad! (398-481) -> omega! (254-360).
+ *                 f and/or G may be NULL (Optim's only_fg! convention).  f receives Omega, or
+ *                 Omega_t when a centre penalty is set (spread.jl:220).
+ * wb200_spread  = omega(stencil, M, U) (spread.jl:377-381): out5 = {Omega, OmegaI, OmegaOD,
+ *                 OmegaD, OmegaTilde}; omega_n [nw]; r [nw][3]; min_abs_Nnn = min |N_nn| (the
+ *                 guard the reference has commented out, spread.jl:452-457).  Always forms the
+ *                 full N = U^H M U, so the split is exact for any U (rectangular, non-unitary).
+ * wb200_center  = center(stencil, M, U) (spread.jl:560-594).
+ * wb200_rotate_overlaps = transform_gauge(M, kpb_k, U) (src/localization/gauge.jl:83-98) and
+ *                 compute_MU_UtMU! (spread.jl:164-195): N [nk][nn][nw*nw]; MU [nk][nn][nb*nw]
+ *                 (either may be NULL).
+ * wb200_fg_xy   = fg!(Omega, G, XY) of get_fg!_disentangle (disentangle.jl:586-614); XY and G_XY
+ *                 are (nw*nw + nb*nw) x nk column-major, column ik = [vec(X_k); vec(Y_k)].
+ *                 Single-slab ctx only (k_begin = 0, nk = nk_total).                            */
+int wb200_fg(wb200_ctx* ctx, const double* U, double* f, double* G);
+int wb200_spread(wb200_ctx* ctx, const double* U, double out5[5], double* omega_n, double* r,
+                 double* min_abs_Nnn);
+int wb200_center(wb200_ctx* ctx, const double* U, double* r);
+int wb200_rotate_overlaps(wb200_ctx* ctx, const double* U, double* N, double* MU);
+int wb200_fg_xy(wb200_ctx* ctx, const double* XY, double* f, double* G_XY);
+
+/* Optim.Stiefel_SVD (third-party; call sites max_localize.jl:62-63, disentangle.jl:687-690):
+ *   project_tangent!: G <- G - X (X^H G + G^H X)/2      per matrix
+ *   retract!:         X <- polar factor of X (= U V^H of svd(X)), computed GEMM-only
+ * X, G: [count][ncol][nrow] complex, nrow x ncol column-major.                                   */
+int wb200_project_tangent(wb200_ctx* ctx, const double* X, double* G, int nrow, int ncol, int count);
+int wb200_retract(wb200_ctx* ctx, double* X, int nrow, int ncol, int count);
+
+/* max_localize(model; f_tol, g_tol, max_iter, history_size) (max_localize.jl:44-101) with the
+ * optimiser loop device-resident (L-BFGS on the power Stiefel manifold, strong-Wolfe line search,
+ * Optim's stopping rules |df| <= f_tol |f| or |g|_inf <= g_tol).  U_inout [nk][nw][nb], nb == nw.
+ * Single-slab ctx only.  iters / n_fg may be NULL.                                               */
+int wb200_max_localize(wb200_ctx* ctx, double* U_inout, double f_tol, double g_tol, int max_iter,
+                       int history, double* f_final, int* iters, int* n_fg);
+/* disentangle(model; ...) (disentangle.jl:631-728) on the product manifold (X, Y); frozen set by
+ * wb200_set_frozen; XY_inout as in wb200_fg_xy (initial point from U_to_X_Y on the host).       */
+int wb200_disentangle(wb200_ctx* ctx, double* XY_inout, double f_tol, double g_tol, int max_iter,
+                      int history, double* f_final, int* iters, int* n_fg);
+
+/* ---- device-pointer entry points (resident data, k-sharding across processes) ----------------
+ * One evaluation on a k-slab is split where the reference has its global dependency
+ * (omega_grad! needs r from center! over ALL k, spread.jl:411):
+ *   phase1: rotation of the slab's overlaps + per-slab partial sums  -> sums [wb200_nsums]
+ *           (caller all-reduces `sums` over the ranks: ncclAllReduce(sum) / torch.distributed)
+ *   phase2: spread scalars from the reduced sums and the slab's gradient.
+ *   dU    device, [nk_total][nw][nb] (all k: neighbours k+b may live in other slabs)
+ *   dsums device, wb200_nsums(ctx) doubles (layout: sum w b phi [nw][3], sum w(1-|N|^2+phi^2)
+ *         [nw], sum w ||N||_F^2, sum w sum_n |N_nn|^2)
+ *   dres  device, wb200_nres(ctx) doubles: {Omega, OmegaI, OmegaOD, OmegaD, OmegaTilde, f,
+ *         0, 0, omega_n[nw], r[nw][3]}
+ *   dG    device, [nk][nw][nb] or NULL
+ * `exact_split` != 0 forms the full N (second GEMM) so OmegaI/OmegaOD are exact for any U;
+ * 0 uses ||N||_F = ||M U_{k+b}||_F, valid for square unitary U_k (max_localize); Omega, r, omega_n
+ * and G never depend on this choice.                                                            */
+int wb200_nsums(const wb200_ctx* ctx);
+int wb200_nres(const wb200_ctx* ctx);
+int wb200_fg_phase1_dev(wb200_ctx* ctx, const double* dU, double* dsums, int exact_split);
+int wb200_fg_phase2_dev(wb200_ctx* ctx, const double* dsums, double* dres, double* dG);
+/* phase1 + phase2 for a single-slab ctx, no host synchronisation */
+int wb200_fg_dev(wb200_ctx* ctx, const double* dU, double* dres, double* dG, int exact_split);
+/* min over the slab of |N_nn| from the last phase1 (synchronises) */
+int wb200_min_abs_diag(wb200_ctx* ctx, double* out);
+int wb200_project_tangent_dev(wb200_ctx* ctx, const double* dX, double* dG, int nrow, int ncol,
+                              int count);
+int wb200_retract_dev(wb200_ctx* ctx, double* dX, int nrow, int ncol, int count, int* iters);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WANNIER_B200_H */

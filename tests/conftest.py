@@ -33,3 +33,20 @@ def silicon():
 @pytest.fixture(scope="session")
 def silicon_split():
     return load_golden("silicon_split.npz")
+
+
+@pytest.fixture(scope="session")
+def w():
+    """the product package (wannier.jl_b200/, loaded by path because of the dot in its name)"""
+    import __graft_entry__ as ge
+    return ge.load_package()
+
+
+def make_ctx(w, st, M, nw, **kw):
+    """Context from oracle-layout arrays."""
+    nk, nn, nb, _ = M.shape
+    return w.Context(nb, nw, nk, nn, st["kpb_k"], st["bvec"], st["wb"], w.api.to_abi_M(M), **kw)
+
+
+def fixture_stencil(d):
+    return dict(kpb_k=d["kpb_k"], bvec=d["bvec"], wb=d["wb"])

@@ -1,0 +1,96 @@
+"""CPU-only checks: the C-ABI library builds/loads and exports every symbol the header declares,
+the host-side layout helpers agree with the oracle, the synthetic generators are well formed.
+No compute call is made (there is no GPU here and the library has no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import spread_oracle as so
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(w):
+    import __graft_entry__ as ge
+    if not os.path.exists(w.lib.LIB_PATH):
+        ge.build()
+    hdr = open(os.path.join(ROOT, "include", "wannier_b200.h")).read()
+    declared = set(re.findall(r"\b(wb200_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(w.lib.SYMBOLS)
+    lib = ctypes.CDLL(w.lib.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(lib, name), name
+    assert b"sm_100a" in w.lib.load().wb200_version()
+
+
+def test_no_cpu_fallback_create_fails_without_device(w):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    st, M, U = w.synthetic.make_model_arrays("cubic", (2, 2, 2), 4, 4)
+    with pytest.raises(w.WB200Error) as e:
+        w.Context(4, 4, 8, 6, st["kpb_k"], st["bvec"], st["wb"], w.api.to_abi_M(M))
+    assert e.value.status == -3
+
+
+def test_product_never_imports_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "wannier.jl_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in txt and "from oracle" not in txt, f
+
+
+@pytest.mark.parametrize("lat,grid,nn", [("bcc", (4, 4, 4), 12), ("fcc", (3, 3, 3), 8),
+                                         ("cubic", (3, 2, 2), 6), ("tetragonal", (10, 10, 1), 6)])
+def test_synthetic_stencil(w, lat, grid, nn):
+    st = w.synthetic.make_stencil(w.synthetic.LATTICES[lat](), grid)
+    assert st["kpb_k"].shape == (np.prod(grid), nn)
+    b = st["bvec"][0]
+    assert np.allclose(np.einsum("b,bx,by->xy", st["wb"], b, b), np.eye(3), atol=1e-10)   # B1
+    # same b through the reference formula (src/spread.jl:293)
+    b2 = so.bvectors_cart(st["recip"], st["kpoints"], st["kpb_k"], st["kpb_G"])
+    assert np.allclose(b2, st["bvec"], atol=1e-12)
+    # every b has its -b partner at the neighbour: kpb(kpb(k, b), -b) == k
+    for ib in range(nn):
+        jb = int(np.argmin(np.abs(b + b[ib]).sum(axis=1)))
+        assert np.allclose(b[jb], -b[ib])
+        assert np.array_equal(st["kpb_k"][st["kpb_k"][:, ib], jb], np.arange(len(st["kpoints"])))
+    if lat == "tetragonal":
+        assert (st["kpb_k"][:, 4:] == np.arange(100)[:, None]).all()      # self-neighbours, G != 0
+        assert np.abs(st["kpb_G"][:, 4:, 2]).min() == 1
+
+
+def test_synthetic_overlaps_are_consistent(w):
+    st, M, U = w.synthetic.make_model_arrays("bcc", (3, 3, 3), 6, 6)
+    b = st["bvec"][0]
+    for ib in range(12):
+        jb = int(np.argmin(np.abs(b + b[ib]).sum(axis=1)))
+        assert np.allclose(M[st["kpb_k"][:, ib], jb], np.conj(M[:, ib].transpose(0, 2, 1)), atol=1e-12)
+    assert np.linalg.norm(M, ord=2, axis=(-2, -1)).max() <= 1 + 1e-12
+    assert np.abs(np.conj(U.transpose(0, 2, 1)) @ U - np.eye(6)).max() < 1e-12
+    sp = so.omega(M, st["kpb_k"], st["bvec"], st["wb"], U)
+    assert sp["OmegaI"] > 1e-3 and np.isfinite(sp["Omega"])
+
+
+def test_host_layout_helpers_match_oracle(w, silicon):
+    nb, nw = 12, 8
+    fro = silicon["frozen"]
+    X, Y = w.api.U_to_X_Y(silicon["U"], fro)
+    Xo, Yo = so.U_to_X_Y(silicon["U"], fro)
+    assert np.allclose(w.api.X_Y_to_U(X, Y), so.X_Y_to_U(Xo, Yo), atol=1e-12)
+    XY = w.api.X_Y_to_XY(X, Y)
+    assert np.array_equal(XY, so.X_Y_to_XY(X, Y))
+    X2, Y2 = w.api.XY_to_X_Y(XY, nb, nw)
+    assert np.array_equal(X, X2) and np.array_equal(Y, Y2)
+    U = silicon["U"]
+    assert np.array_equal(w.api.from_abi_U(w.api.to_abi_U(U)), U)
+    # Julia column-major image: element (m, n) of U_k at n*nb + m
+    assert w.api.to_abi_U(U).reshape(len(U), -1)[3, 2 * nb + 5] == U[3, 5, 2]
+    st = w.KspaceStencil(silicon["recip"], silicon["kpoints"], silicon["wb"], silicon["kpb_k"], silicon["kpb_G"])
+    assert np.allclose(st.bvectors_cart(), silicon["bvec"], atol=1e-12)
+    m = w.Model(silicon["lattice"], st, silicon["M"], U, fro)
+    assert (m.n_bands, m.n_wannier, m.n_kpoints, m.n_bvectors) == (12, 8, 64, 8)

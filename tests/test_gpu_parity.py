@@ -1,0 +1,306 @@
+"""GPU parity tests (-m gpu): every call goes through the C-ABI of libwannier_b200.so and is
+compared with the CPU oracle on identical inputs.  Tolerances: 1e-10 relative for FP64 results
+(BASELINE north_star); OmegaD, a difference of near-equal numbers, uses 1e-10 * Omega absolute;
+max_localize must reach the reference optimum within 1e-8 A^2."""
+import numpy as np
+import pytest
+
+from oracle import spread_oracle as so
+from conftest import make_ctx, fixture_stencil
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-10
+
+
+def rel(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+def check_spread(got, ref):
+    out5, om, r, _ = got
+    scale = abs(ref["Omega"])
+    for i, key in enumerate(["Omega", "OmegaI", "OmegaOD", "OmegaD", "OmegaTilde"]):
+        assert abs(out5[i] - ref[key]) <= RTOL * scale, (key, out5[i], ref[key])
+    assert rel(om, ref["omega"]) < RTOL
+    assert np.abs(r - ref["r"]).max() <= RTOL * max(1.0, np.abs(ref["r"]).max())
+
+
+def oracle_args(d):
+    return d["M"], d["kpb_k"], d["bvec"], d["wb"]
+
+
+# ---------------------------------------------------------------------------------------------
+# reference fixtures (BASELINE config 1 and the 12 -> 8 silicon model)
+# ---------------------------------------------------------------------------------------------
+def test_valence_spread_and_known_answers(w, valence):
+    ctx = make_ctx(w, fixture_stencil(valence), valence["M"], 4)
+    assert ctx.rotation_kernel == "cuda-core-fp64"
+    for U in (valence["U"], valence["U_ptg"], valence["U"] @ valence["W1"]):
+        got = ctx.spread(w.api.to_abi_U(U))
+        check_spread(got, so.omega(*oracle_args(valence), U))
+    # reference constant: test/localization/max_localize.jl:53 (OmegaI is gauge invariant)
+    assert abs(ctx.spread(w.api.to_abi_U(valence["U_ptg"]))[0][1] - valence["ref_maxloc"][1]) < 1e-11
+    r = ctx.center(w.api.to_abi_U(valence["U"]))
+    assert np.abs(r - so.center(*oracle_args(valence), valence["U"])).max() < 1e-10
+    ctx.close()
+
+
+def test_valence_fg_matches_oracle_and_finite_differences(w, valence):
+    # test/localization/max_localize.jl:11-43
+    ctx = make_ctx(w, fixture_stencil(valence), valence["M"], 4)
+    rng = np.random.default_rng(1)
+    for U in (valence["U"], valence["U"] @ valence["W1"]):
+        G = np.empty((64, 4, 4), dtype=np.complex128)
+        f = ctx.fg(w.api.to_abi_U(U), G=G)
+        G = w.api.from_abi_U(G)
+        f_ref, G_ref = so.fg_maxloc(*oracle_args(valence), U)
+        assert abs(f - f_ref) < RTOL * abs(f_ref)
+        assert rel(G, G_ref) < RTOL
+        d = rng.standard_normal(U.shape) + 1j * rng.standard_normal(U.shape)
+        h = 1e-5
+        fd = (ctx.fg(w.api.to_abi_U(U + h * d)) - ctx.fg(w.api.to_abi_U(U - h * d))) / (2 * h)
+        assert abs(fd - np.real(np.vdot(G, d))) < 1e-6 * max(1.0, abs(fd))
+    # only_fg! convention: F or G may be skipped
+    assert ctx.fg(w.api.to_abi_U(valence["U"]), want_f=False, G=np.empty((64, 4, 4), dtype=np.complex128)) is None
+    ctx.close()
+
+
+def test_center_penalty(w, valence):
+    # test/localization/constrain_center/max_localize.jl: CenterSpreadPenalty(r0, lambda = 10)
+    ctx = make_ctx(w, fixture_stencil(valence), valence["M"], 4)
+    rng = np.random.default_rng(5)
+    r0 = rng.standard_normal((4, 3))
+    lam = 10.0
+    ctx.set_penalty(r0, lam)
+    U = valence["U"]
+    G = np.empty((64, 4, 4), dtype=np.complex128)
+    f = ctx.fg(w.api.to_abi_U(U), G=G)
+    f_ref, G_ref = so.fg_maxloc(*oracle_args(valence), U, r0, lam)
+    assert abs(f - f_ref) < RTOL * abs(f_ref)
+    assert rel(w.api.from_abi_U(G), G_ref) < RTOL
+    ctx.set_penalty(None, 0.0)
+    assert abs(ctx.fg(w.api.to_abi_U(U)) - so.fg_maxloc(*oracle_args(valence), U)[0]) < 1e-9
+    ctx.close()
+    # host mirror: omega(CenterSpreadPenalty, ...) -> SpreadCenter (src/spread.jl:221, 246-252)
+    st = w.KspaceStencil(valence["recip"], valence["kpoints"], valence["wb"], valence["kpb_k"], valence["kpb_G"])
+    sc = w.omega(w.CenterSpreadPenalty(r0, lam), st, valence["M"], U)
+    ref = so.omega_center(so.omega(*oracle_args(valence), U), r0, lam)
+    assert abs(sc.Omegat - ref["Omegat"]) < RTOL * abs(ref["Omegat"])
+    assert rel(sc.omegat, ref["omegat"]) < RTOL
+
+
+def test_silicon_rotation_matches_w90_chk(w, silicon):
+    # test/io/model.jl:38-75 analogue: U^H M U == chk.m_matrix (rectangular U: 12 -> 8)
+    ctx = make_ctx(w, fixture_stencil(silicon), silicon["M"], 8)
+    N, MU = ctx.rotate_overlaps(w.api.to_abi_U(silicon["U_chk"]), want_N=True, want_MU=True)
+    N = N.transpose(0, 1, 3, 2)
+    assert np.abs(N - silicon["chk_m_matrix"]).max() < 1e-13
+    MU_ref, N_ref = so.compute_MU_UtMU(silicon["M"], silicon["kpb_k"], silicon["U_chk"])
+    assert rel(MU.transpose(0, 1, 3, 2), MU_ref) < 1e-13
+    assert rel(N, N_ref) < 1e-13
+    got = ctx.spread(w.api.to_abi_U(silicon["U_chk"]))
+    check_spread(got, so.omega(*oracle_args(silicon), silicon["U_chk"]))
+    ref = silicon["wout_final"]       # W90's own numbers (slightly different Bohr): 3e-8 relative
+    assert np.allclose(got[0][:4], ref, rtol=3e-8, atol=0)
+    ctx.close()
+
+
+def test_split_overlaps(w, silicon, silicon_split):
+    # test/localization/split.jl:17-47
+    for V, ref in ((silicon_split["Vv"], silicon_split["Mv_ref"]), (silicon_split["Vc"], silicon_split["Mc_ref"])):
+        N = w.transform_gauge(silicon["M"], silicon["kpb_k"], silicon["U_chk"] @ V)
+        assert np.abs(N - ref).max() < 1e-7
+
+
+def test_silicon_rectangular_fg_and_disentangle_chain(w, silicon):
+    # test/localization/disentangle.jl:27-54
+    nb, nw = 12, 8
+    ctx = make_ctx(w, fixture_stencil(silicon), silicon["M"], nw)
+    U = silicon["U"]
+    G = np.empty((64, nw, nb), dtype=np.complex128)
+    f = ctx.fg(w.api.to_abi_U(U), G=G)
+    f_ref, G_ref = so.fg_maxloc(*oracle_args(silicon), U)
+    assert abs(f - f_ref) < RTOL * abs(f_ref)
+    assert rel(w.api.from_abi_U(G), G_ref) < RTOL
+    fro = silicon["frozen"]
+    ctx.set_frozen(fro)
+    X, Y = so.U_to_X_Y(U, fro)
+    XY = so.X_Y_to_XY(X, Y)
+    Gxy = np.empty_like(XY)
+    f = ctx.fg_xy(np.ascontiguousarray(XY), G=Gxy)
+    f_ref, G_ref = so.fg_disentangle(*oracle_args(silicon), XY, nb, nw, fro)
+    assert abs(f - f_ref) < RTOL * abs(f_ref)
+    assert rel(Gxy, G_ref) < RTOL
+    ctx.close()
+
+
+def test_stiefel_project_and_retract(w, valence, silicon):
+    ctx = make_ctx(w, fixture_stencil(valence), valence["M"], 4)
+    rng = np.random.default_rng(7)
+    for (nrow, ncol, count) in ((4, 4, 64), (12, 8, 17), (128, 128, 3), (40, 24, 5)):
+        X = so.stiefel_retract(rng.standard_normal((count, nrow, ncol)) + 1j * rng.standard_normal((count, nrow, ncol)))
+        G = rng.standard_normal(X.shape) + 1j * rng.standard_normal(X.shape)
+        Gc = w.api.to_abi_U(G)
+        ctx.project_tangent(w.api.to_abi_U(X), Gc, nrow, ncol)
+        assert rel(w.api.from_abi_U(Gc), so.stiefel_project_tangent(G, X)) < 1e-12
+        Xp = X + 0.1 * G
+        Xc = w.api.to_abi_U(Xp)
+        ctx.retract(Xc, nrow, ncol)
+        assert np.abs(w.api.from_abi_U(Xc) - so.stiefel_retract(Xp)).max() < 1e-12
+    # far-from-unitary input (projections from an .amn): polar factor == Lowdin (src/utils/linalg.jl:25-29)
+    A = silicon["U"] * 3.0 + 0.3 * (rng.standard_normal(silicon["U"].shape))
+    Ac = w.api.to_abi_U(A)
+    ctx.retract(Ac, 12, 8)
+    assert np.abs(w.api.from_abi_U(Ac) - so.orthonorm_lowdin(A)).max() < 1e-11
+    ctx.close()
+
+
+def test_max_localize_reaches_reference_optimum(w, valence):
+    # test/localization/max_localize.jl:45-56: Omega = 6.374823673444644 etc. (atol 1e-7 there;
+    # north_star: within 1e-8 A^2)
+    ref = valence["ref_maxloc"]
+    st = w.KspaceStencil(valence["recip"], valence["kpoints"], valence["wb"], valence["kpb_k"], valence["kpb_G"])
+    model = w.Model(valence["lattice"], st, valence["M"], valence["U_ptg"])
+    U, info = w.max_localize(model, return_info=True)             # reference default tolerances
+    assert abs(so.omega(*oracle_args(valence), U)["Omega"] - ref[0]) < 2e-6
+    U, info = w.max_localize(model, f_tol=1e-13, g_tol=1e-8, max_iter=500, return_info=True)
+    sp = so.omega(*oracle_args(valence), U)
+    assert abs(sp["Omega"] - ref[0]) < 1e-8
+    assert abs(sp["OmegaI"] - ref[1]) < 1e-8
+    assert abs(sp["OmegaOD"] - ref[2]) < 1e-8
+    assert abs(info["f"] - sp["Omega"]) < 1e-10
+    assert np.abs(np.conj(U.transpose(0, 2, 1)) @ U - np.eye(4)).max() < 1e-12
+    # same algorithm as the oracle's driver: same iteration count and optimum
+    Uo, fo, ito, _ = so.max_localize(*oracle_args(valence), valence["U_ptg"], f_tol=1e-13, g_tol=1e-8, max_iter=500)
+    assert abs(fo - info["f"]) < 1e-9
+    with pytest.raises(ValueError):   # max_localize.jl:52-53
+        w.max_localize(w.Model(valence["lattice"], st, np.zeros((64, 8, 5, 5), complex), np.zeros((64, 5, 4), complex)))
+
+
+def test_disentangle_driver(w, silicon):
+    # test/localization/disentangle.jl:56-97 pins Optim's 4-step trajectory (unpinnable without
+    # Optim.jl); here: the device driver decreases Omega, keeps frozen states, agrees with the oracle's fg
+    st = w.KspaceStencil(silicon["recip"], silicon["kpoints"], silicon["wb"], silicon["kpb_k"], silicon["kpb_G"])
+    model = w.Model(silicon["lattice"], st, silicon["M"], silicon["U"], silicon["frozen"])
+    X0, Y0 = so.U_to_X_Y(silicon["U"], silicon["frozen"])
+    f0 = so.omega(*oracle_args(silicon), so.X_Y_to_U(X0, Y0))["Omega"]
+    U, info = w.disentangle(model, max_iter=30, return_info=True)
+    sp = so.omega(*oracle_args(silicon), U)
+    assert abs(sp["Omega"] - info["f"]) < 1e-9
+    assert info["f"] < f0 - 1.0
+    assert np.abs(np.conj(U.transpose(0, 2, 1)) @ U - np.eye(8)).max() < 1e-11
+    # frozen states stay inside the span of U:  sum_n |U[m, n]|^2 == 1 for frozen m
+    w2 = (np.abs(U) ** 2).sum(axis=2)
+    assert np.abs(w2[silicon["frozen"]] - 1).max() < 1e-10
+
+
+# ---------------------------------------------------------------------------------------------
+# synthetic shapes: both rotation kernels against the oracle, padding and edge cases
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("lat,grid,nb,nw", [
+    ("bcc", (2, 2, 2), 128, 128),     # north-star tile shape (DMMA 128 x 32 CTA tiles)
+    ("bcc", (2, 2, 1), 128, 96),      # rectangular, nw not a multiple of... 32 (it is) but < nb
+    ("cubic", (2, 2, 2), 100, 70),    # padded rows / columns / k-chunks
+    ("fcc", (2, 2, 2), 64, 64),
+    ("fcc", (2, 1, 2), 40, 33),
+    ("tetragonal", (3, 3, 1), 256, 256),   # self-neighbours with G != 0 (config 5 shape)
+    ("cubic", (2, 1, 1), 200, 130),
+    ("fcc", (3, 3, 3), 18, 9),        # config 2 shape (CUDA-core kernel)
+    ("bcc", (3, 3, 3), 32, 32),       # config 3 shape
+    ("cubic", (1, 1, 1), 5, 3),       # single k-point, all neighbours are the point itself
+])
+def test_synthetic_both_kernels(w, lat, grid, nb, nw):
+    st, M, U = w.synthetic.make_model_arrays(lat, grid, nb, nw)
+    nk = len(U)
+    f_ref, G_ref = so.fg_maxloc(M, st["kpb_k"], st["bvec"], st["wb"], U)
+    sp_ref = so.omega(M, st["kpb_k"], st["bvec"], st["wb"], U)
+    kernels = set()
+    for flags in (w.lib.FLAG_DEFAULT, w.lib.FLAG_NO_TENSOR):
+        ctx = make_ctx(w, st, M, nw, flags=flags)
+        kernels.add(ctx.rotation_kernel)
+        G = np.empty((nk, nw, nb), dtype=np.complex128)
+        f = ctx.fg(w.api.to_abi_U(U), G=G)
+        assert abs(f - f_ref) < RTOL * abs(f_ref), ctx.rotation_kernel
+        assert rel(w.api.from_abi_U(G), G_ref) < RTOL, ctx.rotation_kernel
+        check_spread(ctx.spread(w.api.to_abi_U(U)), sp_ref)
+        N, MU = ctx.rotate_overlaps(w.api.to_abi_U(U), want_N=True, want_MU=True)
+        MU_ref, N_ref = so.compute_MU_UtMU(M, st["kpb_k"], U)
+        assert rel(MU.transpose(0, 1, 3, 2), MU_ref) < 1e-12
+        assert rel(N.transpose(0, 1, 3, 2), N_ref) < 1e-12
+        # determinism: bitwise identical on a second call
+        G2 = np.empty_like(G)
+        f2 = ctx.fg(w.api.to_abi_U(U), G=G2)
+        assert f2 == f and np.array_equal(G, G2)
+        ctx.close()
+    assert kernels == ({"cuda-core-fp64", "dmma-fp64"} if 32 < nb <= 256 else {"cuda-core-fp64"})
+
+
+def test_unitary_shortcut_vs_exact_split(w):
+    # fg (one GEMM, ||N||_F = ||MU||_F for square unitary U) and spread (full N) agree on all
+    # five scalars when nb == nw
+    import torch
+    st, M, U = w.synthetic.make_model_arrays("bcc", (2, 2, 2), 64, 64)
+    ctx = make_ctx(w, st, M, 64)
+    dU = torch.from_numpy(w.api.to_abi_U(U)).cuda()
+    res = torch.zeros(ctx.nres, dtype=torch.float64, device="cuda")
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    ctx.fg_dev(dU.data_ptr(), res.data_ptr(), None, exact_split=False)
+    a = res.cpu().numpy().copy()
+    ctx.fg_dev(dU.data_ptr(), res.data_ptr(), None, exact_split=True)
+    b = res.cpu().numpy()
+    assert np.abs(a[:5] - b[:5]).max() < 1e-11 * abs(b[0])
+    sp = so.omega(M, st["kpb_k"], st["bvec"], st["wb"], U)
+    assert abs(a[1] - sp["OmegaI"]) < 1e-10 * sp["Omega"] and abs(a[2] - sp["OmegaOD"]) < 1e-10 * sp["Omega"]
+    ctx.close()
+
+
+def test_k_slab_sharding_on_one_gpu(w):
+    """Multi-GPU path emulated on one device: two slab contexts, phase1 each, sums added (what the
+    NCCL all-reduce does), phase2 each; equals the single-slab result."""
+    import torch
+    st, M, U = w.synthetic.make_model_arrays("bcc", (4, 2, 2), 64, 48)
+    nk, nb, nw = len(U), 64, 48
+    f_ref, G_ref = so.fg_maxloc(M, st["kpb_k"], st["bvec"], st["wb"], U)
+    dU = torch.from_numpy(w.api.to_abi_U(U)).cuda()
+    stream = torch.cuda.current_stream().cuda_stream
+    ctxs, sums = [], []
+    for (k0, k1) in ((0, 6), (6, 16)):
+        c = w.Context(nb, nw, nk, 12, st["kpb_k"][k0:k1], st["bvec"][k0:k1], st["wb"],
+                      w.api.to_abi_M(M[k0:k1]), k_begin=k0, nk=k1 - k0)
+        c.set_stream(stream)
+        s = torch.zeros(c.nsums, dtype=torch.float64, device="cuda")
+        c.fg_phase1_dev(dU.data_ptr(), s.data_ptr())
+        ctxs.append((c, k0, k1))
+        sums.append(s)
+    total = sums[0] + sums[1]
+    G = torch.zeros((nk, nw, nb), dtype=torch.complex128, device="cuda")
+    res = torch.zeros(ctxs[0][0].nres, dtype=torch.float64, device="cuda")
+    for c, k0, k1 in ctxs:
+        c.fg_phase2_dev(total.data_ptr(), res.data_ptr(), G[k0:k1].data_ptr())
+    torch.cuda.synchronize()
+    assert abs(res[5].item() - f_ref) < RTOL * abs(f_ref)
+    assert rel(G.cpu().numpy().transpose(0, 2, 1), G_ref) < RTOL
+    for c, _, _ in ctxs:
+        c.close()
+
+
+def test_error_behaviour(w, valence):
+    st = fixture_stencil(valence)
+    bad = st["kpb_k"].copy()
+    bad[3, 2] = 64
+    with pytest.raises(w.WB200Error) as e:
+        w.Context(4, 4, 64, 8, bad, st["bvec"], st["wb"], w.api.to_abi_M(valence["M"]))
+    assert e.value.status == -1
+    with pytest.raises(w.WB200Error):
+        w.Context(4, 5, 64, 8, st["kpb_k"], st["bvec"], st["wb"], w.api.to_abi_M(valence["M"]))
+    ctx = make_ctx(w, st, valence["M"], 4)
+    with pytest.raises(ValueError):
+        ctx.fg(np.zeros((3, 4, 4), dtype=np.complex128))
+    # a singular gauge gives |N_nn| ~ 0: reported through min_abs_Nnn instead of silent NaN
+    U = valence["U"].copy()
+    U[:, :, 0] = 0
+    mn = ctx.spread(w.api.to_abi_U(U))[3]
+    assert mn < 1e-10
+    ctx.close()

@@ -1,0 +1,12 @@
+"""wannier.jl_b200 — B200-native (sm_100a) implementation of Wannier.jl's spread / gradient hot
+path behind the reference's own function API.  See DESIGN.md / INTEGRATION.md.
+
+The directory name contains a dot, so the package is loaded by path (see
+``__graft_entry__.load_package``) under the module name ``wannier_jl_b200``.
+"""
+from . import lib, api, synthetic  # noqa: F401
+from .api import (KspaceStencil, Model, Spread, SpreadCenter, SpreadPenalty, CenterSpreadPenalty,  # noqa: F401
+                  Cache, omega, omega_grad, omega_center, center, compute_MU_UtMU, transform_gauge,
+                  get_fg_maxloc, max_localize, get_fg_disentangle, disentangle, X_Y_to_U, X_Y_to_XY,
+                  XY_to_X_Y, U_to_X_Y)
+from .lib import Context, WB200Error  # noqa: F401

@@ -1,0 +1,420 @@
+"""Host-side mirror of the reference's Julia API for the spread / gradient hot path.
+
+Julia is not available in the build or GPU images, so the host layer above the C-ABI is this
+Python module; names, argument meaning and error behaviour follow the reference
+(paths below are under the reference tree):
+
+    KspaceStencil, Model                      src/kpoints/kstencil.jl:19-60, src/model.jl:26-66
+    Spread, SpreadCenter                      src/spread.jl:30-54, 62-97
+    SpreadPenalty, CenterSpreadPenalty        src/spread.jl:203-227
+    Cache, compute_MU_UtMU                    src/spread.jl:127-198
+    omega, omega_grad, center, omega_center   src/spread.jl:241-252, 370-381, 496-510, 560-564
+    transform_gauge                           src/localization/gauge.jl:83-98
+    get_fg_maxloc, max_localize               src/localization/max_localize.jl:10-101
+    X_Y_to_XY, XY_to_X_Y, X_Y_to_U, U_to_X_Y  src/localization/disentangle.jl:351-466
+    get_fg_disentangle, disentangle           src/localization/disentangle.jl:586-728
+
+Arrays use math indexing in numpy C order: M[k, b, m, l], U[k, m, n], G[k, m, n]; they are
+converted to the C-ABI's column-major (Julia) memory image at this boundary.  All arithmetic of
+the hot path runs in libwannier_b200.so on the GPU; nothing here falls back to the CPU.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import lib as _lib
+
+
+# ------------------------------------------------------------------------------------------
+# data model
+# ------------------------------------------------------------------------------------------
+@dataclass
+class KspaceStencil:
+    """src/kpoints/kstencil.jl:19-60.  recip_lattice columns are the reciprocal vectors (1/A);
+    kpoints fractional [nk, 3]; bweights [nn]; kpb_k [nk, nn] 0-based; kpb_G [nk, nn, 3]."""
+    recip_lattice: np.ndarray
+    kpoints: np.ndarray
+    bweights: np.ndarray
+    kpb_k: np.ndarray
+    kpb_G: np.ndarray
+
+    @property
+    def n_kpoints(self):
+        return self.kpb_k.shape[0]
+
+    @property
+    def n_bvectors(self):
+        return self.kpb_k.shape[1]
+
+    def bvectors_cart(self):
+        """b = recip_lattice * (kpoints[kpb_k] + kpb_G - kpoints[k])   (src/spread.jl:293)"""
+        kp = np.asarray(self.kpoints, dtype=np.float64)
+        d = kp[self.kpb_k] + np.asarray(self.kpb_G, dtype=np.float64) - kp[:, None, :]
+        return d @ np.asarray(self.recip_lattice, dtype=np.float64).T
+
+
+@dataclass
+class Model:
+    """src/model.jl:26-66 (the fields the hot path reads)."""
+    lattice: np.ndarray
+    kstencil: KspaceStencil
+    overlaps: np.ndarray                 # M[k, b, m, l]
+    gauges: np.ndarray                   # U[k, m, n]
+    frozen_bands: np.ndarray | None = None   # [nk, nb] bool
+    eigenvalues: np.ndarray | None = None
+
+    def __post_init__(self):
+        nk, nn, nb, nb2 = self.overlaps.shape
+        if nb != nb2:
+            raise ValueError("overlaps must be n_bands x n_bands")
+        if self.gauges.shape[0] != nk or self.gauges.shape[1] != nb:
+            raise ValueError("gauges must be [n_kpts, n_bands, n_wann]")
+        if self.kstencil.kpb_k.shape != (nk, nn):
+            raise ValueError("kstencil does not match overlaps")
+        if self.gauges.shape[2] > nb:
+            raise ValueError("n_wann > n_bands")
+
+    n_bands = property(lambda self: self.overlaps.shape[2])
+    n_wannier = property(lambda self: self.gauges.shape[2])
+    n_kpoints = property(lambda self: self.overlaps.shape[0])
+    n_bvectors = property(lambda self: self.overlaps.shape[1])
+
+
+@dataclass
+class Spread:
+    """src/spread.jl:30-54 (ASCII field names; unicode aliases below)."""
+    Omega: float
+    OmegaI: float
+    OmegaOD: float
+    OmegaD: float
+    OmegaTilde: float
+    omega: np.ndarray
+    r: np.ndarray
+    min_abs_Nnn: float = float("nan")
+
+    Ω = property(lambda s: s.Omega)
+    ΩI = property(lambda s: s.OmegaI)
+    ΩOD = property(lambda s: s.OmegaOD)
+    ΩD = property(lambda s: s.OmegaD)
+    Ω̃ = property(lambda s: s.OmegaTilde)
+    ω = property(lambda s: s.omega)
+
+
+@dataclass
+class SpreadCenter(Spread):
+    """src/spread.jl:62-97"""
+    Omegac: float = 0.0
+    Omegat: float = 0.0
+    omegac: np.ndarray = field(default_factory=lambda: np.zeros(0))
+    omegat: np.ndarray = field(default_factory=lambda: np.zeros(0))
+
+
+class SpreadPenalty:
+    """src/spread.jl:203"""
+
+
+@dataclass
+class CenterSpreadPenalty:
+    """src/spread.jl:214-217: r0 [nw, 3] (Cartesian A), lam."""
+    r0: np.ndarray
+    lam: float
+
+
+# ------------------------------------------------------------------------------------------
+# layout conversion at the C-ABI boundary
+# ------------------------------------------------------------------------------------------
+def to_abi_U(U):
+    """U[k, m, n] -> [k][n][m] contiguous (Julia nb x nw col-major per k)."""
+    return np.ascontiguousarray(np.asarray(U, dtype=np.complex128).transpose(0, 2, 1))
+
+
+def from_abi_U(Uc):
+    return np.ascontiguousarray(Uc.transpose(0, 2, 1))
+
+
+def to_abi_M(M):
+    return np.ascontiguousarray(np.asarray(M, dtype=np.complex128).transpose(0, 1, 3, 2))
+
+
+# ------------------------------------------------------------------------------------------
+# Cache = device context for one (stencil, M)
+# ------------------------------------------------------------------------------------------
+class Cache:
+    """Cache(model) / Cache(stencil, M, U) (src/spread.jl:139-162): here it owns the device
+    context — M resident in HBM, all work buffers — instead of host MU/UtMU arrays."""
+
+    def __init__(self, kstencil, M, n_wann, *, device=0, flags=_lib.FLAG_DEFAULT):
+        nk, nn, nb, _ = M.shape
+        self.nb, self.nw, self.nk, self.nn = nb, n_wann, nk, nn
+        self.ctx = _lib.Context(nb, n_wann, nk, nn, kstencil.kpb_k, kstencil.bvectors_cart(),
+                                kstencil.bweights, to_abi_M(M), device=device, flags=flags)
+        self._penalty = None
+
+    @classmethod
+    def from_model(cls, model, **kw):
+        c = cls(model.kstencil, model.overlaps, model.n_wannier, **kw)
+        if model.frozen_bands is not None:
+            c.ctx.set_frozen(np.asarray(model.frozen_bands, dtype=np.uint8))
+        return c
+
+    def set_penalty(self, p):
+        if p is None or isinstance(p, SpreadPenalty):
+            self.ctx.set_penalty(None, 0.0)
+            self._penalty = None
+        elif isinstance(p, CenterSpreadPenalty):
+            self.ctx.set_penalty(np.asarray(p.r0, dtype=np.float64), p.lam)
+            self._penalty = p
+        else:
+            raise TypeError("penalty must be SpreadPenalty or CenterSpreadPenalty")
+
+    def close(self):
+        self.ctx.close()
+
+
+def _split_args(args):
+    """([penalty,] model[, U])  or  ([penalty,] stencil, M, U)"""
+    args = list(args)
+    p = None
+    if args and isinstance(args[0], (SpreadPenalty, CenterSpreadPenalty)):
+        p = args.pop(0)
+    if isinstance(args[0], Model):
+        model = args[0]
+        U = args[1] if len(args) > 1 else model.gauges
+        return p, model.kstencil, model.overlaps, U
+    st, M, U = args
+    return p, st, M, U
+
+
+def _with_cache(args, cache):
+    p, st, M, U = _split_args(args)
+    own = cache is None
+    if own:
+        cache = Cache(st, M, U.shape[2])
+    cache.set_penalty(p)
+    return p, cache, U, own
+
+
+def omega(*args, cache=None):
+    """omega([penalty,] model[, U]) / omega([penalty,] stencil, M, U)  (src/spread.jl:370-381;
+    with CenterSpreadPenalty -> omega_center, :221)."""
+    p, cache, U, own = _with_cache(args, cache)
+    try:
+        out5, om, r, mn = cache.ctx.spread(to_abi_U(U))
+    finally:
+        if own:
+            cache.close()
+    sp = Spread(*[float(x) for x in out5], om, r, mn)
+    if isinstance(p, CenterSpreadPenalty):
+        return omega_center(sp, p.r0, p.lam)
+    return sp
+
+
+def omega_center(sp, r0, lam):
+    """src/spread.jl:246-252"""
+    omegac = lam * ((sp.r - np.asarray(r0)) ** 2).sum(axis=1)
+    return SpreadCenter(sp.Omega, sp.OmegaI, sp.OmegaOD, sp.OmegaD, sp.OmegaTilde, sp.omega, sp.r,
+                        sp.min_abs_Nnn, float(omegac.sum()), float(sp.Omega + omegac.sum()), omegac,
+                        sp.omega + omegac)
+
+
+def omega_grad(*args, cache=None):
+    """omega_grad([penalty,] stencil, M, U) -> G[k, m, n]   (src/spread.jl:496-510)"""
+    p, cache, U, own = _with_cache(args, cache)
+    try:
+        G = np.empty((cache.nk, cache.nw, cache.nb), dtype=np.complex128)
+        cache.ctx.fg(to_abi_U(U), want_f=False, G=G)
+    finally:
+        if own:
+            cache.close()
+    return from_abi_U(G)
+
+
+def center(*args, cache=None):
+    """center(model[, U]) / center(stencil, M, U) -> r[nw, 3]   (src/spread.jl:560-564)"""
+    p, cache, U, own = _with_cache(args, cache)
+    try:
+        return cache.ctx.center(to_abi_U(U))
+    finally:
+        if own:
+            cache.close()
+
+
+def compute_MU_UtMU(cache, U):
+    """compute_MU_UtMU!(cache, stencil, M, U) (src/spread.jl:164-198): returns (MU, UtMU) with
+    MU[k, b, m, n], UtMU[k, b, j, n]."""
+    N, MU = cache.ctx.rotate_overlaps(to_abi_U(U), want_N=True, want_MU=True)
+    return MU.transpose(0, 1, 3, 2), N.transpose(0, 1, 3, 2)
+
+
+def transform_gauge(M, kstencil_or_kpb, U, cache=None):
+    """transform_gauge(M, kpb_k, U) -> N[k, b, j, n] = U_k^H M_kb U_{k+b}  (gauge.jl:83-98)"""
+    own = cache is None
+    if own:
+        if isinstance(kstencil_or_kpb, KspaceStencil):
+            st = kstencil_or_kpb
+        else:  # only kpb_k matters for the rotation
+            kpb = np.asarray(kstencil_or_kpb)
+            st = KspaceStencil(np.eye(3), np.zeros((kpb.shape[0], 3)), np.ones(kpb.shape[1]), kpb,
+                               np.zeros(kpb.shape + (3,), dtype=np.int64))
+        cache = Cache(st, M, U.shape[2])
+    try:
+        N, _ = cache.ctx.rotate_overlaps(to_abi_U(U), want_N=True, want_MU=False)
+    finally:
+        if own:
+            cache.close()
+    return np.ascontiguousarray(N.transpose(0, 1, 3, 2))
+
+
+# ------------------------------------------------------------------------------------------
+# max_localize
+# ------------------------------------------------------------------------------------------
+def get_fg_maxloc(p, model, cache=None):
+    """get_fg!_maxloc (src/localization/max_localize.jl:10-28).  Returns fg(F, G, U) with
+    Optim's only_fg! convention: F / G may be None to skip; G[k, m, n] is written in place;
+    returns Omega (or None)."""
+    cache = cache or Cache.from_model(model)
+    cache.set_penalty(p)
+    Gbuf = np.empty((cache.nk, cache.nw, cache.nb), dtype=np.complex128)
+
+    def fg(F, G, U):
+        f = cache.ctx.fg(to_abi_U(U), want_f=F is not None, G=Gbuf if G is not None else None)
+        if G is not None:
+            G[...] = Gbuf.transpose(0, 2, 1)
+        return f
+
+    fg.cache = cache
+    return fg
+
+
+def max_localize(*args, f_tol=1e-7, g_tol=1e-5, max_iter=200, history_size=3, cache=None,
+                 return_info=False):
+    """max_localize([p,] model; f_tol, g_tol, max_iter, history_size) -> gauges U[k, m, n]
+    (src/localization/max_localize.jl:44-101).  The whole optimiser loop is device-resident."""
+    args = list(args)
+    p = SpreadPenalty()
+    if isinstance(args[0], (SpreadPenalty, CenterSpreadPenalty)):
+        p = args.pop(0)
+    model = args[0]
+    if model.n_bands != model.n_wannier:
+        raise ValueError("n_bands != n_wann, run instead disentanglement?")   # max_localize.jl:52-53
+    own = cache is None
+    cache = cache or Cache.from_model(model)
+    cache.set_penalty(p)
+    try:
+        Uc = to_abi_U(model.gauges)
+        f, iters, nfg = cache.ctx.max_localize(Uc, f_tol, g_tol, max_iter, history_size)
+    finally:
+        if own:
+            cache.close()
+    U = from_abi_U(Uc)
+    return (U, dict(f=f, iterations=iters, n_fg=nfg)) if return_info else U
+
+
+# ------------------------------------------------------------------------------------------
+# disentangle: (X, Y) parametrisation
+# ------------------------------------------------------------------------------------------
+def X_Y_to_U(X, Y):
+    """U_k = Y_k X_k   (disentangle.jl:351-356).  Host helper (layout/setup only)."""
+    return Y @ X
+
+
+def X_Y_to_XY(X, Y):
+    """row k of the result = Julia column k = [vec(X_k); vec(Y_k)]  (disentangle.jl:454-466)"""
+    nk = X.shape[0]
+    return np.ascontiguousarray(np.concatenate(
+        [X.transpose(0, 2, 1).reshape(nk, -1), Y.transpose(0, 2, 1).reshape(nk, -1)], axis=1))
+
+
+def XY_to_X_Y(XY, nb, nw):
+    """disentangle.jl:424-435"""
+    nk = XY.shape[0]
+    X = XY[:, :nw * nw].reshape(nk, nw, nw).transpose(0, 2, 1)
+    Y = XY[:, nw * nw:].reshape(nk, nw, nb).transpose(0, 2, 1)
+    return np.ascontiguousarray(X), np.ascontiguousarray(Y)
+
+
+def _lowdin(A):
+    W, _, Vh = np.linalg.svd(A, full_matrices=False)
+    return W @ Vh
+
+
+def orthonorm_freeze(U, frozen, atol=1e-10):
+    """disentangle.jl:223-281 (one k-point; one-off host setup, not on the iterated path)."""
+    nb, nw = U.shape
+    Uf = U[frozen, :]
+    if Uf.shape[0] > 0:
+        Uf = _lowdin(Uf)
+    Ur = U[~frozen, :]
+    Ur = Ur - Ur @ np.conj(Uf.T) @ Uf
+    A, S, Bh = np.linalg.svd(Ur, full_matrices=False)
+    if int((S > atol).sum()) != nw - int(frozen.sum()):
+        raise ValueError("orthonorm_freeze: wrong number of non-zero singular values")
+    Ur = (A * (S > atol)) @ Bh
+    V = np.empty_like(U)
+    V[frozen, :] = Uf
+    V[~frozen, :] = Ur
+    return V
+
+
+def U_to_X_Y(U, frozen):
+    """disentangle.jl:369-402 (one-off host setup)."""
+    nk, nb, nw = U.shape
+    X = np.zeros((nk, nw, nw), dtype=np.complex128)
+    Y = np.zeros((nk, nb, nw), dtype=np.complex128)
+    for k in range(nk):
+        f = np.asarray(frozen[k], dtype=bool)
+        nf = int(f.sum())
+        Af = orthonorm_freeze(U[k], f)
+        Ur = Af[~f, :]
+        Y[k][np.nonzero(f)[0], np.arange(nf)] = 1.0
+        if nf != nw:
+            Pr = Ur @ np.conj(Ur.T)
+            Pr = (Pr + np.conj(Pr.T)) / 2
+            _, V = np.linalg.eigh(Pr)
+            Y[k][np.ix_(np.nonzero(~f)[0], np.arange(nf, nw))] = V[:, V.shape[1] - (nw - nf):]
+        X[k] = _lowdin(np.conj(Y[k].T) @ Af)
+    return X, Y
+
+
+def get_fg_disentangle(p, model, cache=None):
+    """get_fg!_disentangle (disentangle.jl:586-614): fg(F, G, XY) with XY [nk, nw*nw + nb*nw]."""
+    cache = cache or Cache.from_model(model)
+    cache.set_penalty(p)
+
+    def fg(F, G, XY):
+        XY = np.ascontiguousarray(XY, dtype=np.complex128)
+        Gb = np.empty_like(XY) if G is not None else None
+        f = cache.ctx.fg_xy(XY, want_f=F is not None, G=Gb)
+        if G is not None:
+            G[...] = Gb
+        return f
+
+    fg.cache = cache
+    return fg
+
+
+def disentangle(*args, f_tol=1e-7, g_tol=1e-5, max_iter=200, history_size=3, cache=None,
+                return_info=False):
+    """disentangle([p,] model; ...) -> gauges U[k, m, n]   (disentangle.jl:631-728)"""
+    args = list(args)
+    p = SpreadPenalty()
+    if isinstance(args[0], (SpreadPenalty, CenterSpreadPenalty)):
+        p = args.pop(0)
+    model = args[0]
+    if model.frozen_bands is None:
+        raise ValueError("disentangle needs model.frozen_bands")
+    own = cache is None
+    cache = cache or Cache.from_model(model)
+    cache.set_penalty(p)
+    try:
+        X0, Y0 = U_to_X_Y(model.gauges, model.frozen_bands)     # disentangle.jl:666
+        XY = X_Y_to_XY(X0, Y0)                                  # :670
+        f, iters, nfg = cache.ctx.disentangle(XY, f_tol, g_tol, max_iter, history_size)
+    finally:
+        if own:
+            cache.close()
+    X, Y = XY_to_X_Y(XY, model.n_bands, model.n_wannier)
+    U = X_Y_to_U(X, Y)
+    return (U, dict(f=f, iterations=iters, n_fg=nfg)) if return_info else U

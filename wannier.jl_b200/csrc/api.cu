@@ -1,0 +1,433 @@
+// api.cu — the C-ABI of libwannier_b200.so (see include/wannier_b200.h for the contract and the
+// reference functions each entry point replaces).
+#include "common.cuh"
+
+#include <algorithm>
+#include <cmath>
+
+static thread_local std::string g_create_error;
+
+extern "C" const char* wb200_version(void) { return "wannier_b200 0.1 (sm_100a)"; }
+
+extern "C" const char* wb200_last_error(const wb200_ctx* ctx) {
+    return ctx ? ctx->err.c_str() : g_create_error.c_str();
+}
+
+extern "C" void wb200_destroy(wb200_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    wb_dmma_plan_destroy(ctx);
+    void* ptrs[] = {ctx->d_kpb, ctx->d_kself, ctx->d_bvec, ctx->d_wb, ctx->d_M, ctx->d_r0,
+                    ctx->d_frozen, ctx->d_nfrozen, ctx->d_U, ctx->d_G, ctx->d_MU, ctx->d_N,
+                    ctx->d_dN, ctx->d_fro, ctx->d_part, ctx->d_pmin, ctx->d_sums, ctx->d_res,
+                    ctx->d_min, ctx->d_scal, ctx->d_tmp1, ctx->d_tmp2, ctx->d_XY, ctx->d_GXY};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+#define CREATE_FAIL(code, msg)        \
+    do {                              \
+        g_create_error = (msg);       \
+        if (ctx) wb200_destroy(ctx);  \
+        return (code);                \
+    } while (0)
+#define CREATE_CUDA(call)                                                              \
+    do {                                                                               \
+        cudaError_t e_ = (call);                                                       \
+        if (e_ != cudaSuccess)                                                         \
+            CREATE_FAIL(WB200_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+extern "C" int wb200_create(wb200_ctx** out, int device, int nb, int nw, int nk_total, int k_begin,
+                            int nk, int nn, const int32_t* kpb_k, const double* bvec_cart,
+                            const double* bweights, const double* M, unsigned flags) {
+    wb200_ctx* ctx = nullptr;
+    if (!out) CREATE_FAIL(WB200_ERR_ARG, "wb200_create: out is NULL");
+    *out = nullptr;
+    if (nb <= 0 || nw <= 0 || nw > nb || nk_total <= 0 || nn <= 0 || nk <= 0 || k_begin < 0 ||
+        k_begin + nk > nk_total)
+        CREATE_FAIL(WB200_ERR_ARG, "wb200_create: bad sizes (need 0 < nw <= nb, 0 <= k_begin, k_begin + nk <= nk_total)");
+    if (!kpb_k || !bvec_cart || !bweights || !M)
+        CREATE_FAIL(WB200_ERR_ARG, "wb200_create: NULL input array");
+    for (long long i = 0; i < (long long)nk * nn; i++)
+        if (kpb_k[i] < 0 || kpb_k[i] >= nk_total)
+            CREATE_FAIL(WB200_ERR_ARG, "wb200_create: kpb_k index out of range at pair " + std::to_string(i));
+
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev)
+        CREATE_FAIL(WB200_ERR_NODEVICE, "wb200_create: no CUDA device " + std::to_string(device) +
+                                            " (this library has no CPU fallback)");
+    cudaDeviceProp prop;
+    CREATE_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        CREATE_FAIL(WB200_ERR_NODEVICE, std::string("wb200_create: device is ") + prop.name +
+                                            " (sm_" + std::to_string(prop.major) + std::to_string(prop.minor) +
+                                            "); this library is built for sm_100a only");
+    CREATE_CUDA(cudaSetDevice(device));
+
+    ctx = new wb200_ctx();
+    ctx->device = device;
+    ctx->nb = nb; ctx->nw = nw; ctx->nk_total = nk_total; ctx->k_begin = k_begin; ctx->nk = nk;
+    ctx->nn = nn; ctx->flags = flags;
+    CREATE_CUDA(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+    ctx->stream = ctx->own_stream;
+
+    const size_t pairs = (size_t)nk * nn;
+    const size_t mat = (size_t)nb * nw;
+    CREATE_CUDA(cudaMalloc(&ctx->d_kpb, sizeof(int32_t) * pairs));
+    CREATE_CUDA(cudaMalloc(&ctx->d_kself, sizeof(int32_t) * pairs));
+    CREATE_CUDA(cudaMalloc(&ctx->d_bvec, sizeof(double) * pairs * 3));
+    CREATE_CUDA(cudaMalloc(&ctx->d_wb, sizeof(double) * nn));
+    CREATE_CUDA(cudaMalloc(&ctx->d_M, sizeof(cplx) * pairs * nb * nb));
+    CREATE_CUDA(cudaMalloc(&ctx->d_r0, sizeof(double) * 3 * nw));
+    CREATE_CUDA(cudaMalloc(&ctx->d_U, sizeof(cplx) * (size_t)nk_total * mat));
+    CREATE_CUDA(cudaMalloc(&ctx->d_G, sizeof(cplx) * (size_t)nk * mat));
+    CREATE_CUDA(cudaMalloc(&ctx->d_MU, sizeof(cplx) * pairs * mat));
+    CREATE_CUDA(cudaMalloc(&ctx->d_dN, sizeof(cplx) * pairs * nw));
+    CREATE_CUDA(cudaMalloc(&ctx->d_fro, sizeof(double) * pairs));
+    CREATE_CUDA(cudaMalloc(&ctx->d_part, sizeof(double) * (size_t)nk * ctx->nsums()));
+    CREATE_CUDA(cudaMalloc(&ctx->d_pmin, sizeof(double) * nk));
+    CREATE_CUDA(cudaMalloc(&ctx->d_sums, sizeof(double) * ctx->nsums()));
+    CREATE_CUDA(cudaMalloc(&ctx->d_res, sizeof(double) * ctx->nres()));
+    CREATE_CUDA(cudaMalloc(&ctx->d_min, sizeof(double)));
+    CREATE_CUDA(cudaMalloc(&ctx->d_scal, sizeof(double) * 2048));
+    CREATE_CUDA(cudaMallocHost(&ctx->h_pinned, sizeof(double) * (ctx->nres() + 64)));
+    CREATE_CUDA(cudaMemset(ctx->d_r0, 0, sizeof(double) * 3 * nw));
+
+    std::vector<int32_t> kself(pairs);
+    for (size_t p = 0; p < pairs; p++) kself[p] = k_begin + (int32_t)(p / nn);
+    CREATE_CUDA(cudaMemcpy(ctx->d_kpb, kpb_k, sizeof(int32_t) * pairs, cudaMemcpyHostToDevice));
+    CREATE_CUDA(cudaMemcpy(ctx->d_kself, kself.data(), sizeof(int32_t) * pairs, cudaMemcpyHostToDevice));
+    CREATE_CUDA(cudaMemcpy(ctx->d_bvec, bvec_cart, sizeof(double) * pairs * 3, cudaMemcpyHostToDevice));
+    CREATE_CUDA(cudaMemcpy(ctx->d_wb, bweights, sizeof(double) * nn, cudaMemcpyHostToDevice));
+    CREATE_CUDA(cudaMemcpy(ctx->d_M, M, sizeof(cplx) * pairs * nb * nb, cudaMemcpyDefault));  // host or device
+    ctx->h_wb.assign(bweights, bweights + nn);
+    ctx->wsum = 0.0;
+    for (int b = 0; b < nn; b++) ctx->wsum += bweights[b];
+
+    if (!(flags & WB200_FLAG_NO_TENSOR)) {
+        int s = wb_dmma_plan_create(ctx, M);
+        if (s != WB200_OK) CREATE_FAIL(s, "wb200_create: tensor plan: " + ctx->err);
+    }
+    if ((flags & WB200_FLAG_FORCE_TENSOR) && !ctx->dmma)
+        CREATE_FAIL(WB200_ERR_ARG, "wb200_create: WB200_FLAG_FORCE_TENSOR but the DMMA rotation kernel does not support this shape");
+    ctx->rotation_kernel = ctx->dmma ? 1 : 0;
+    CREATE_CUDA(cudaDeviceSynchronize());
+    *out = ctx;
+    return WB200_OK;
+}
+
+extern "C" int wb200_set_stream(wb200_ctx* ctx, void* s) {
+    if (!ctx) return WB200_ERR_ARG;
+    ctx->stream = s ? (cudaStream_t)s : ctx->own_stream;
+    return WB200_OK;
+}
+extern "C" int wb200_synchronize(wb200_ctx* ctx) {
+    if (!ctx) return WB200_ERR_ARG;
+    WB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return WB200_OK;
+}
+extern "C" int wb200_rotation_kernel(const wb200_ctx* ctx) { return ctx ? ctx->rotation_kernel : -1; }
+extern "C" long long wb200_launch_count(const wb200_ctx* ctx) { return ctx ? ctx->launches : -1; }
+extern "C" int wb200_nsums(const wb200_ctx* ctx) { return ctx ? ctx->nsums() : -1; }
+extern "C" int wb200_nres(const wb200_ctx* ctx) { return ctx ? ctx->nres() : -1; }
+
+extern "C" int wb200_set_penalty(wb200_ctx* ctx, const double* r0, double lambda) {
+    if (!ctx) return WB200_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    if (!r0) {
+        ctx->has_penalty = 0;
+        ctx->lambda = 0.0;
+        return WB200_OK;
+    }
+    WB_CUDA(ctx, cudaMemcpy(ctx->d_r0, r0, sizeof(double) * 3 * ctx->nw, cudaMemcpyHostToDevice));
+    ctx->has_penalty = 1;
+    ctx->lambda = lambda;
+    return WB200_OK;
+}
+
+extern "C" int wb200_set_frozen(wb200_ctx* ctx, const uint8_t* frozen) {
+    if (!ctx) return WB200_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    if (!frozen) {
+        if (ctx->d_frozen) { cudaFree(ctx->d_frozen); ctx->d_frozen = nullptr; }
+        if (ctx->d_nfrozen) { cudaFree(ctx->d_nfrozen); ctx->d_nfrozen = nullptr; }
+        return WB200_OK;
+    }
+    const size_t n = (size_t)ctx->nk * ctx->nb;
+    if (!ctx->d_frozen) WB_CUDA(ctx, cudaMalloc(&ctx->d_frozen, n));
+    if (!ctx->d_nfrozen) WB_CUDA(ctx, cudaMalloc(&ctx->d_nfrozen, sizeof(int32_t) * ctx->nk));
+    std::vector<int32_t> nf(ctx->nk, 0);
+    for (int k = 0; k < ctx->nk; k++)
+        for (int m = 0; m < ctx->nb; m++) nf[k] += frozen[(size_t)k * ctx->nb + m] ? 1 : 0;
+    WB_CUDA(ctx, cudaMemcpy(ctx->d_frozen, frozen, n, cudaMemcpyHostToDevice));
+    WB_CUDA(ctx, cudaMemcpy(ctx->d_nfrozen, nf.data(), sizeof(int32_t) * ctx->nk, cudaMemcpyHostToDevice));
+    return WB200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// device pipeline
+// ---------------------------------------------------------------------------------------------
+static int rotate(wb200_ctx* ctx, const cplx* dU) {
+    if (ctx->dmma) return wb_rotate_dmma(ctx, dU);
+    return wb_rotate_generic(ctx, dU);
+}
+
+extern "C" int wb200_fg_phase1_dev(wb200_ctx* ctx, const double* dU, double* dsums, int exact_split) {
+    if (!ctx || !dU || !dsums) return WB200_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    WB_TRY(rotate(ctx, (const cplx*)dU));
+    if (exact_split) WB_TRY(wb_form_N(ctx, (const cplx*)dU));
+    WB_TRY(wb_pair_reduce(ctx, dsums));
+    return WB200_OK;
+}
+
+extern "C" int wb200_fg_phase2_dev(wb200_ctx* ctx, const double* dsums, double* dres, double* dG) {
+    if (!ctx || !dsums) return WB200_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    if (dres) WB_TRY(wb_finalize(ctx, dsums, dres));
+    if (dG) WB_TRY(wb_grad(ctx, dsums, (cplx*)dG));
+    return WB200_OK;
+}
+
+int wb_fg_device(wb200_ctx* ctx, const cplx* dU, double* dres, cplx* dG, int exact_split) {
+    WB_TRY(wb200_fg_phase1_dev(ctx, (const double*)dU, ctx->d_sums, exact_split));
+    WB_TRY(wb200_fg_phase2_dev(ctx, ctx->d_sums, dres, (double*)dG));
+    return WB200_OK;
+}
+
+extern "C" int wb200_fg_dev(wb200_ctx* ctx, const double* dU, double* dres, double* dG,
+                            int exact_split) {
+    if (!ctx || !dU) return WB200_ERR_ARG;
+    if (ctx->nk != ctx->nk_total) {
+        ctx->err = "wb200_fg_dev: single-slab ctx only; use phase1/phase2 with an all-reduce of sums";
+        return WB200_ERR_ARG;
+    }
+    return wb_fg_device(ctx, (const cplx*)dU, dres, (cplx*)dG, exact_split);
+}
+
+extern "C" int wb200_min_abs_diag(wb200_ctx* ctx, double* out) {
+    if (!ctx || !out) return WB200_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    WB_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, ctx->d_min, sizeof(double), cudaMemcpyDeviceToHost,
+                                 ctx->stream));
+    WB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *out = ctx->h_pinned[0];
+    return WB200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host entry points
+// ---------------------------------------------------------------------------------------------
+static int require_single_slab(wb200_ctx* ctx, const char* who) {
+    if (ctx->nk != ctx->nk_total || ctx->k_begin != 0) {
+        ctx->err = std::string(who) + ": host entry points need a single-slab ctx (k_begin = 0, nk = nk_total)";
+        return WB200_ERR_ARG;
+    }
+    return WB200_OK;
+}
+
+static int upload_U(wb200_ctx* ctx, const double* U) {
+    WB_CUDA(ctx, cudaMemcpyAsync(ctx->d_U, U, sizeof(cplx) * (size_t)ctx->nk_total * ctx->nb * ctx->nw,
+                                 cudaMemcpyHostToDevice, ctx->stream));
+    return WB200_OK;
+}
+
+extern "C" int wb200_fg(wb200_ctx* ctx, const double* U, double* f, double* G) {
+    if (!ctx || !U) return WB200_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    WB_TRY(require_single_slab(ctx, "wb200_fg"));
+    WB_TRY(upload_U(ctx, U));
+    WB_TRY(wb_fg_device(ctx, ctx->d_U, ctx->d_res, G ? ctx->d_G : nullptr, 0));
+    if (G)
+        WB_CUDA(ctx, cudaMemcpyAsync(G, ctx->d_G, sizeof(cplx) * (size_t)ctx->nk * ctx->nb * ctx->nw,
+                                     cudaMemcpyDeviceToHost, ctx->stream));
+    WB_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, ctx->d_res, sizeof(double) * 8, cudaMemcpyDeviceToHost,
+                                 ctx->stream));
+    WB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (f) *f = ctx->h_pinned[5];
+    return WB200_OK;
+}
+
+extern "C" int wb200_spread(wb200_ctx* ctx, const double* U, double out5[5], double* omega_n,
+                            double* r, double* min_abs_Nnn) {
+    if (!ctx || !U) return WB200_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    WB_TRY(require_single_slab(ctx, "wb200_spread"));
+    WB_TRY(upload_U(ctx, U));
+    WB_TRY(wb_fg_device(ctx, ctx->d_U, ctx->d_res, nullptr, 1));
+    WB_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, ctx->d_res, sizeof(double) * ctx->nres(),
+                                 cudaMemcpyDeviceToHost, ctx->stream));
+    WB_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned + ctx->nres(), ctx->d_min, sizeof(double),
+                                 cudaMemcpyDeviceToHost, ctx->stream));
+    WB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const double* h = ctx->h_pinned;
+    if (out5) for (int i = 0; i < 5; i++) out5[i] = h[i];
+    if (omega_n) for (int n = 0; n < ctx->nw; n++) omega_n[n] = h[8 + n];
+    if (r) for (int i = 0; i < 3 * ctx->nw; i++) r[i] = h[8 + ctx->nw + i];
+    if (min_abs_Nnn) *min_abs_Nnn = h[ctx->nres()];
+    return WB200_OK;
+}
+
+extern "C" int wb200_center(wb200_ctx* ctx, const double* U, double* r) {
+    if (!ctx || !U || !r) return WB200_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    WB_TRY(require_single_slab(ctx, "wb200_center"));
+    WB_TRY(upload_U(ctx, U));
+    WB_TRY(wb_fg_device(ctx, ctx->d_U, ctx->d_res, nullptr, 0));
+    WB_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, ctx->d_res, sizeof(double) * ctx->nres(),
+                                 cudaMemcpyDeviceToHost, ctx->stream));
+    WB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < 3 * ctx->nw; i++) r[i] = ctx->h_pinned[8 + ctx->nw + i];
+    return WB200_OK;
+}
+
+extern "C" int wb200_rotate_overlaps(wb200_ctx* ctx, const double* U, double* N, double* MU) {
+    if (!ctx || !U) return WB200_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    WB_TRY(require_single_slab(ctx, "wb200_rotate_overlaps"));
+    WB_TRY(upload_U(ctx, U));
+    WB_TRY(rotate(ctx, ctx->d_U));
+    const size_t pairs = (size_t)ctx->nk * ctx->nn;
+    if (N) {
+        WB_TRY(wb_form_N(ctx, ctx->d_U));
+        WB_CUDA(ctx, cudaMemcpyAsync(N, ctx->d_N, sizeof(cplx) * pairs * ctx->nw * ctx->nw,
+                                     cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (MU)
+        WB_CUDA(ctx, cudaMemcpyAsync(MU, ctx->d_MU, sizeof(cplx) * pairs * ctx->nb * ctx->nw,
+                                     cudaMemcpyDeviceToHost, ctx->stream));
+    WB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return WB200_OK;
+}
+
+static int ensure_xy(wb200_ctx* ctx) {
+    const size_t st = (size_t)ctx->nw * ctx->nw + (size_t)ctx->nb * ctx->nw;
+    if (!ctx->d_XY) WB_CUDA(ctx, cudaMalloc(&ctx->d_XY, sizeof(cplx) * st * ctx->nk));
+    if (!ctx->d_GXY) WB_CUDA(ctx, cudaMalloc(&ctx->d_GXY, sizeof(cplx) * st * ctx->nk));
+    return WB200_OK;
+}
+
+extern "C" int wb200_fg_xy(wb200_ctx* ctx, const double* XY, double* f, double* G_XY) {
+    if (!ctx || !XY) return WB200_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    WB_TRY(require_single_slab(ctx, "wb200_fg_xy"));
+    WB_TRY(ensure_xy(ctx));
+    const size_t st = (size_t)ctx->nw * ctx->nw + (size_t)ctx->nb * ctx->nw;
+    WB_CUDA(ctx, cudaMemcpyAsync(ctx->d_XY, XY, sizeof(cplx) * st * ctx->nk, cudaMemcpyHostToDevice,
+                                 ctx->stream));
+    WB_TRY(wb_xy_to_u(ctx, ctx->d_XY, ctx->d_U));
+    WB_TRY(wb_fg_device(ctx, ctx->d_U, ctx->d_res, G_XY ? ctx->d_G : nullptr, 0));
+    if (G_XY) {
+        WB_TRY(wb_gu_to_gxy(ctx, ctx->d_XY, ctx->d_G, ctx->d_GXY));
+        WB_CUDA(ctx, cudaMemcpyAsync(G_XY, ctx->d_GXY, sizeof(cplx) * st * ctx->nk,
+                                     cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    WB_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, ctx->d_res, sizeof(double) * 8, cudaMemcpyDeviceToHost,
+                                 ctx->stream));
+    WB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (f) *f = ctx->h_pinned[5];
+    return WB200_OK;
+}
+
+extern "C" int wb200_project_tangent_dev(wb200_ctx* ctx, const double* dX, double* dG, int nrow,
+                                         int ncol, int count) {
+    if (!ctx || !dX || !dG || nrow <= 0 || ncol <= 0 || ncol > nrow || count <= 0) return WB200_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    return wb_project_tangent_dev(ctx, (const cplx*)dX, (cplx*)dG, nrow, ncol, count);
+}
+extern "C" int wb200_retract_dev(wb200_ctx* ctx, double* dX, int nrow, int ncol, int count, int* iters) {
+    if (!ctx || !dX || nrow <= 0 || ncol <= 0 || ncol > nrow || count <= 0) return WB200_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    return wb_retract_dev(ctx, (cplx*)dX, nrow, ncol, count, iters);
+}
+
+extern "C" int wb200_project_tangent(wb200_ctx* ctx, const double* X, double* G, int nrow, int ncol,
+                                     int count) {
+    if (!ctx || !X || !G || nrow <= 0 || ncol <= 0 || ncol > nrow || count <= 0) return WB200_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    const size_t e = (size_t)nrow * ncol * count;
+    cplx *dX = nullptr, *dG = nullptr;
+    WB_CUDA(ctx, cudaMalloc(&dX, sizeof(cplx) * e));
+    if (cudaMalloc(&dG, sizeof(cplx) * e) != cudaSuccess) { cudaFree(dX); ctx->err = "cudaMalloc"; return WB200_ERR_CUDA; }
+    int s = WB200_OK;
+    if (cudaMemcpyAsync(dX, X, sizeof(cplx) * e, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess ||
+        cudaMemcpyAsync(dG, G, sizeof(cplx) * e, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) {
+        ctx->err = "H2D copy failed"; s = WB200_ERR_CUDA;
+    }
+    if (s == WB200_OK) s = wb_project_tangent_dev(ctx, dX, dG, nrow, ncol, count);
+    if (s == WB200_OK && (cudaMemcpyAsync(G, dG, sizeof(cplx) * e, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+                          cudaStreamSynchronize(ctx->stream) != cudaSuccess)) {
+        ctx->err = "D2H copy failed"; s = WB200_ERR_CUDA;
+    }
+    cudaFree(dX); cudaFree(dG);
+    return s;
+}
+
+extern "C" int wb200_retract(wb200_ctx* ctx, double* X, int nrow, int ncol, int count) {
+    if (!ctx || !X || nrow <= 0 || ncol <= 0 || ncol > nrow || count <= 0) return WB200_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    const size_t e = (size_t)nrow * ncol * count;
+    cplx* dX = nullptr;
+    WB_CUDA(ctx, cudaMalloc(&dX, sizeof(cplx) * e));
+    int s = WB200_OK;
+    if (cudaMemcpyAsync(dX, X, sizeof(cplx) * e, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) {
+        ctx->err = "H2D copy failed"; s = WB200_ERR_CUDA;
+    }
+    if (s == WB200_OK) s = wb_retract_dev(ctx, dX, nrow, ncol, count, nullptr);
+    if (s == WB200_OK && (cudaMemcpyAsync(X, dX, sizeof(cplx) * e, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+                          cudaStreamSynchronize(ctx->stream) != cudaSuccess)) {
+        ctx->err = "D2H copy failed"; s = WB200_ERR_CUDA;
+    }
+    cudaFree(dX);
+    return s;
+}
+
+extern "C" int wb200_max_localize(wb200_ctx* ctx, double* U, double f_tol, double g_tol, int max_iter,
+                                  int history, double* f_final, int* iters, int* n_fg) {
+    if (!ctx || !U) return WB200_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    WB_TRY(require_single_slab(ctx, "wb200_max_localize"));
+    if (ctx->nb != ctx->nw) {  // max_localize.jl:52-53
+        ctx->err = "n_bands != n_wann, run instead disentanglement?";
+        return WB200_ERR_ARG;
+    }
+    const size_t e = (size_t)ctx->nk * ctx->nb * ctx->nw;
+    cplx* dx = nullptr;
+    WB_CUDA(ctx, cudaMalloc(&dx, sizeof(cplx) * e));
+    int s = WB200_OK;
+    if (cudaMemcpyAsync(dx, U, sizeof(cplx) * e, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) {
+        ctx->err = "H2D copy failed"; s = WB200_ERR_CUDA;
+    }
+    if (s == WB200_OK) s = wb_lbfgs(ctx, 0, dx, f_tol, g_tol, max_iter, history, f_final, iters, n_fg);
+    if (s == WB200_OK && (cudaMemcpyAsync(U, dx, sizeof(cplx) * e, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+                          cudaStreamSynchronize(ctx->stream) != cudaSuccess)) {
+        ctx->err = "D2H copy failed"; s = WB200_ERR_CUDA;
+    }
+    cudaFree(dx);
+    return s;
+}
+
+extern "C" int wb200_disentangle(wb200_ctx* ctx, double* XY, double f_tol, double g_tol, int max_iter,
+                                 int history, double* f_final, int* iters, int* n_fg) {
+    if (!ctx || !XY) return WB200_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    WB_TRY(require_single_slab(ctx, "wb200_disentangle"));
+    const size_t e = (size_t)ctx->nk * ((size_t)ctx->nw * ctx->nw + (size_t)ctx->nb * ctx->nw);
+    cplx* dx = nullptr;
+    WB_CUDA(ctx, cudaMalloc(&dx, sizeof(cplx) * e));
+    int s = WB200_OK;
+    if (cudaMemcpyAsync(dx, XY, sizeof(cplx) * e, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) {
+        ctx->err = "H2D copy failed"; s = WB200_ERR_CUDA;
+    }
+    if (s == WB200_OK) s = wb_lbfgs(ctx, 1, dx, f_tol, g_tol, max_iter, history, f_final, iters, n_fg);
+    if (s == WB200_OK && (cudaMemcpyAsync(XY, dx, sizeof(cplx) * e, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+                          cudaStreamSynchronize(ctx->stream) != cudaSuccess)) {
+        ctx->err = "D2H copy failed"; s = WB200_ERR_CUDA;
+    }
+    cudaFree(dx);
+    return s;
+}

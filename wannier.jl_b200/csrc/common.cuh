@@ -1,0 +1,179 @@
+// common.cuh — shared declarations of libwannier_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/wannier_b200.h"
+
+typedef double2 cplx;  // (x = re, y = im) == Julia ComplexF64
+
+__host__ __device__ __forceinline__ cplx cmul(cplx a, cplx b) {
+    return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__host__ __device__ __forceinline__ cplx cconj(cplx a) { return make_double2(a.x, -a.y); }
+// c += a*b
+__device__ __forceinline__ void cfma(cplx& c, cplx a, cplx b) {
+    c.x = fma(a.x, b.x, c.x);
+    c.x = fma(-a.y, b.y, c.x);
+    c.y = fma(a.x, b.y, c.y);
+    c.y = fma(a.y, b.x, c.y);
+}
+// c += conj(a)*b
+__device__ __forceinline__ void cfma_conj(cplx& c, cplx a, cplx b) {
+    c.x = fma(a.x, b.x, c.x);
+    c.x = fma(a.y, b.y, c.x);
+    c.y = fma(a.x, b.y, c.y);
+    c.y = fma(-a.y, b.x, c.y);
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_min(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// generic batched complex GEMM   C[b] = alpha * op(A[ia(b)]) * op(B[ib(b)]) + beta * C[b]
+// ---------------------------------------------------------------------------------------------
+struct ZgemmArgs {
+    int m, n, k;             // op(A): m x k, op(B): k x n, C: m x n
+    const cplx* A;
+    long long strideA;       // in complex elements
+    int lda;
+    const int32_t* idxA;     // optional batch -> matrix index
+    const cplx* B;
+    long long strideB;
+    int ldb;
+    const int32_t* idxB;
+    cplx* C;
+    long long strideC;
+    int ldc;
+    double alpha, beta;
+    int batch;
+    int transA, transB;      // 0 = N, 1 = conjugate transpose
+};
+
+// ---------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------
+struct DmmaPlan;  // rotate_dmma.cu
+
+struct wb200_ctx {
+    int device = 0;
+    int nb = 0, nw = 0, nk_total = 0, k_begin = 0, nk = 0, nn = 0;
+    unsigned flags = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    long long launches = 0;
+    std::string err;
+
+    // constant data (uploaded once)
+    int32_t* d_kpb = nullptr;    // [nk][nn] global index of k+b
+    int32_t* d_kself = nullptr;  // [nk*nn] global index of k for every pair
+    double* d_bvec = nullptr;    // [nk][nn][3]
+    double* d_wb = nullptr;      // [nn]
+    cplx* d_M = nullptr;         // [nk][nn][nb*nb] col-major (generic path / exact N)
+    double wsum = 0.0;           // sum_b w_b
+    std::vector<double> h_wb;
+
+    // penalty / frozen
+    int has_penalty = 0;
+    double lambda = 0.0;
+    double* d_r0 = nullptr;       // [nw][3]
+    uint8_t* d_frozen = nullptr;  // [nk][nb]
+    int32_t* d_nfrozen = nullptr; // [nk]
+
+    // work buffers
+    cplx* d_U = nullptr;     // [nk_total][nb*nw] staging copy for host entry points
+    cplx* d_G = nullptr;     // [nk][nb*nw]
+    cplx* d_MU = nullptr;    // [nk][nn][nb*nw]
+    cplx* d_N = nullptr;     // [nk][nn][nw*nw]   (lazy; exact split / rotate_overlaps)
+    cplx* d_dN = nullptr;    // [nk][nn][nw]      diag N
+    double* d_fro = nullptr; // [nk][nn]          ||N||_F^2 (or ||MU||_F^2)
+    double* d_part = nullptr;   // [nk][nsums]
+    double* d_pmin = nullptr;   // [nk]
+    double* d_sums = nullptr;   // [nsums]
+    double* d_res = nullptr;    // [nres]
+    double* d_min = nullptr;    // [1]
+    double* d_scal = nullptr;   // [2048] scratch scalars (dots, errors, block partials)
+    double* h_pinned = nullptr; // pinned host scratch (nres + 64 doubles)
+    // generic scratch for stiefel / xy (lazy, sized on demand)
+    cplx* d_tmp1 = nullptr; size_t tmp1_elems = 0;
+    cplx* d_tmp2 = nullptr; size_t tmp2_elems = 0;
+    cplx* d_XY = nullptr;  cplx* d_GXY = nullptr;   // [nk][nw*nw+nb*nw]
+
+    DmmaPlan* dmma = nullptr;  // tensor-path state (nullptr: CUDA-core rotation)
+    int rotation_kernel = 0;
+
+    int nsums() const { return 4 * nw + 2; }
+    int nres() const { return 8 + 4 * nw; }
+};
+
+#define WB_CUDA(ctx, call)                                                                      \
+    do {                                                                                        \
+        cudaError_t e_ = (call);                                                                \
+        if (e_ != cudaSuccess) {                                                                \
+            (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e_);                    \
+            return WB200_ERR_CUDA;                                                              \
+        }                                                                                       \
+    } while (0)
+
+#define WB_TRY(expr)                  \
+    do {                              \
+        int s_ = (expr);              \
+        if (s_ != WB200_OK) return s_; \
+    } while (0)
+
+#define WB_LAUNCH_CHECK(ctx)                                                 \
+    do {                                                                     \
+        (ctx)->launches++;                                                   \
+        cudaError_t e_ = cudaGetLastError();                                 \
+        if (e_ != cudaSuccess) {                                             \
+            (ctx)->err = std::string("kernel launch: ") + cudaGetErrorString(e_) + " at " + \
+                         __FILE__ + ":" + std::to_string(__LINE__);          \
+            return WB200_ERR_CUDA;                                           \
+        }                                                                    \
+    } while (0)
+
+// ---- kernels_generic.cu ----
+int wb_zgemm_batched(wb200_ctx* ctx, const ZgemmArgs& a);
+int wb_rotate_generic(wb200_ctx* ctx, const cplx* dU);              // MU, dN, fro(=||MU||^2)
+int wb_form_N(wb200_ctx* ctx, const cplx* dU);                      // N = U_k^H MU, fro = ||N||^2
+int wb_pair_reduce(wb200_ctx* ctx, double* dsums);                  // part -> sums (+ min)
+int wb_finalize(wb200_ctx* ctx, const double* dsums, double* dres);
+int wb_grad(wb200_ctx* ctx, const double* dsums, cplx* dG);
+int wb_ensure_tmp(wb200_ctx* ctx, size_t e1, size_t e2);
+int wb_ensure_N(wb200_ctx* ctx);
+
+// ---- stiefel.cu ----
+int wb_project_tangent_dev(wb200_ctx* ctx, const cplx* dX, cplx* dG, int nrow, int ncol, int count);
+int wb_retract_dev(wb200_ctx* ctx, cplx* dX, int nrow, int ncol, int count, int* iters);
+int wb_retract_xy(wb200_ctx* ctx, cplx* dXY);
+int wb_project_xy(wb200_ctx* ctx, const cplx* dXY, cplx* dG);
+int wb_xy_to_u(wb200_ctx* ctx, const cplx* dXY, cplx* dU);
+int wb_gu_to_gxy(wb200_ctx* ctx, const cplx* dXY, const cplx* dGU, cplx* dGXY);
+
+// ---- vecops (stiefel.cu) ----
+int wb_dot(wb200_ctx* ctx, const double* a, const double* b, size_t n, double* out_host);
+int wb_absmax(wb200_ctx* ctx, const double* a, size_t n, double* out_host);
+int wb_axpby(wb200_ctx* ctx, double alpha, const double* x, double beta, double* y, size_t n);  // y = a x + b y
+int wb_axpbyz(wb200_ctx* ctx, double alpha, const double* x, double beta, const double* y, double* z, size_t n);
+
+// ---- rotate_dmma.cu ----
+int wb_dmma_plan_create(wb200_ctx* ctx, const double* hM);   // may leave ctx->dmma == nullptr if not applicable
+void wb_dmma_plan_destroy(wb200_ctx* ctx);
+int wb_rotate_dmma(wb200_ctx* ctx, const cplx* dU);           // MU, dN, fro(=||MU||^2)
+
+// ---- optimizer.cu ----
+int wb_lbfgs(wb200_ctx* ctx, int mode /*0 maxloc, 1 disentangle*/, cplx* dx, double f_tol,
+             double g_tol, int max_iter, int history, double* f_final, int* iters, int* n_fg);

@@ -1,0 +1,388 @@
+// rotate_dmma.cu — the hot kernel: batched complex-FP64 rotation MU_kb = M_kb U_{k+b} on the FP64
+// tensor pipe (DMMA.8x8x4, the only FP64 MMA sm_100a has; tcgen05 has no f64 kind), fused with
+// the diag(N_kb) = diag(U_k^H MU_kb) and ||MU_kb||_F^2 reductions.
+//
+// Replaces compute_MU_UtMU! (src/spread.jl:164-195) for 32 < nb <= 256: one GEMM per (k,b) pair
+// instead of two — everything omega!/omega_grad! need from N is its diagonal (spread.jl:307-312,
+// 459-470), which is an O(nb nw) epilogue on the accumulator registers.
+//
+// Structure (one CTA per (k, column tile), looping over the nn neighbours of k):
+//   * M is re-laid-out ONCE at ctx creation into the exact shared-memory image of the A operand
+//     (DMMA fragment order), so a pipeline stage is ONE contiguous 1-D bulk async copy
+//     (cp.async.bulk -> UBLKCP, completion on an mbarrier); the gauge U is permuted into the B
+//     operand image by pack_gauge_kernel once per evaluation (16 B per element either way).
+//   * warp 8 is the producer (one elected lane issues the bulk copies through a KC-deep ring of
+//     full/empty mbarriers that never drains between the nn pairs of a k-point);
+//     warps 0-7 are consumers: warp tile 32 x 16 complex = 4 x 2 DMMA tiles x (re, im).
+//   * U_k's column tile stays in shared memory (accumulator-fragment order) for the whole CTA, so
+//     the epilogue of every pair is registers + LDS only; per-warp partial diagonals go straight
+//     to global (summed in fixed order by pair_reduce_kernel) — no CTA-wide barrier anywhere in
+//     the main loop, and results are bitwise deterministic.
+#include "common.cuh"
+
+struct DmmaPlan {
+    int WM = 0, WN = 0, KC = 0;   // warp grid (8 consumer warps), k-chunk
+    int NB = 0, NC = 0;           // padded rows, columns per CTA
+    int nct = 0;                  // column tiles = ceil(nw / NC)
+    int nch = 0;                  // k-chunks = ceil(nb / KC)
+    double* d_Mt = nullptr;       // [pairs][nch][NB*KC*2]
+    double* d_Up = nullptr;       // [nk_total][nct][nch][KC*NC*2]
+    cplx* d_dNp = nullptr;        // [pairs][WM][nw]  per-warp-row partial diagonals
+    double* d_frop = nullptr;     // [pairs][nct][8]
+    size_t smem = 0;
+};
+
+namespace {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WB_DONE;\n"
+        "bra WB_WAIT;\n"
+        "WB_DONE:\n"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+// 1-D bulk async copy global -> shared, completion counted on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+        "l"(src), "r"(bytes), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+__device__ __forceinline__ double neg_f64(double x) {  // sign flip on the ALU pipe, not the FP64 pipe
+    return __hiloint2double(__double2hiint(x) ^ (int)0x80000000, __double2loint(x));
+}
+
+// ---- one-off / per-evaluation layout kernels ------------------------------------------------
+// A-operand image of M: chunk = [wm][ks][mt(4)][lane][re,im],
+//   row = wm*32 + mt*8 + lane/4,  col = c*KC + ks*4 + lane%4   (zero padded)
+__global__ void tile_overlaps_kernel(int nb, int WM, int KC, int nch, const cplx* __restrict__ M,
+                                     cplx* __restrict__ Mt) {
+    const long long pair = blockIdx.x;
+    const int c = blockIdx.y;
+    const int KS = KC / 4;
+    const int per = WM * KS * 4 * 32;
+    const cplx* src = M + pair * (long long)nb * nb;
+    cplx* dst = Mt + (pair * nch + c) * (long long)per;
+    for (int o = threadIdx.x; o < per; o += blockDim.x) {
+        const int lane = o & 31, mt = (o >> 5) & 3, ks = (o >> 7) % KS, wm = (o >> 7) / KS;
+        const int row = wm * 32 + mt * 8 + (lane >> 2), col = c * KC + ks * 4 + (lane & 3);
+        dst[o] = (row < nb && col < nb) ? src[row + (long long)col * nb] : make_double2(0.0, 0.0);
+    }
+}
+// B-operand image of U: chunk = [wn][ks][nt(2)][lane][re,im],
+//   l = c*KC + ks*4 + lane%4,  n = ct*NC + wn*16 + nt*8 + lane/4   (zero padded)
+__global__ void pack_gauge_kernel(int nb, int nw, int WN, int KC, int nch, int nct,
+                                  const cplx* __restrict__ U, cplx* __restrict__ Up) {
+    const long long kg = blockIdx.x;
+    const int c = blockIdx.y % nch, ct = blockIdx.y / nch;
+    const int KS = KC / 4;
+    const int per = WN * KS * 2 * 32;
+    const cplx* src = U + kg * (long long)nb * nw;
+    cplx* dst = Up + ((kg * nct + ct) * nch + c) * (long long)per;
+    for (int o = threadIdx.x; o < per; o += blockDim.x) {
+        const int lane = o & 31, nt = (o >> 5) & 1, ks = (o >> 6) % KS, wn = (o >> 6) / KS;
+        const int l = c * KC + ks * 4 + (lane & 3), n = ct * (16 * WN) + wn * 16 + nt * 8 + (lane >> 2);
+        dst[o] = (l < nb && n < nw) ? src[l + (long long)n * nb] : make_double2(0.0, 0.0);
+    }
+}
+
+// ---- the rotation kernel ---------------------------------------------------------------------
+template <int WM, int WN, int KC, int STAGES>
+__global__ void __launch_bounds__(288, 1)
+rotate_dmma_kernel(int nb, int nw, int nn, int nch, int nct, int k_begin,
+                   const int32_t* __restrict__ kpb, const double* __restrict__ Mt,
+                   const double* __restrict__ Up, const cplx* __restrict__ U,
+                   cplx* __restrict__ MU, cplx* __restrict__ dNp, double* __restrict__ frop) {
+    constexpr int KS = KC / 4;
+    constexpr int NC = 16 * WN;
+    constexpr int A_D2 = WM * KS * 4 * 32;   // double2 per A stage
+    constexpr int B_D2 = WN * KS * 2 * 32;   // double2 per B stage
+    constexpr uint32_t A_BYTES = A_D2 * 16, B_BYTES = B_D2 * 16;
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    cplx* sUk = reinterpret_cast<cplx*>(smem_raw);                     // [8 warps][16][32]
+    cplx* sA = sUk + 8 * 16 * 32;                                      // [STAGES][A_D2]
+    cplx* sB = sA + STAGES * A_D2;                                     // [STAGES][B_D2]
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(sB + STAGES * B_D2);
+    // bars[0..STAGES) full, bars[STAGES..2 STAGES) empty
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int kl = blockIdx.x / nct, ct = blockIdx.x % nct;
+    const int n0 = ct * NC;
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; s++) {
+            mbar_init(smem_u32(&bars[s]), 1);
+            mbar_init(smem_u32(&bars[STAGES + s]), 8);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // U_k column tile in accumulator-fragment order: sUk[(w*16 + idx)*32 + lane],
+    //   idx = (mt*2 + nt)*2 + j -> m = wm*32 + mt*8 + lane/4, n = n0 + wn*16 + nt*8 + 2*(lane%4) + j
+    {
+        const cplx* Uk = U + (long long)(k_begin + kl) * nb * nw;
+        for (int o = tid; o < 8 * 16 * 32; o += 288) {
+            const int l = o & 31, idx = (o >> 5) & 15, w = o >> 9;
+            const int wm = w / WN, wn = w % WN;
+            const int j = idx & 1, nt = (idx >> 1) & 1, mt = idx >> 2;
+            const int m = wm * 32 + mt * 8 + (l >> 2), n = n0 + wn * 16 + nt * 8 + 2 * (l & 3) + j;
+            sUk[o] = (m < nb && n < nw) ? Uk[m + (long long)n * nb] : make_double2(0.0, 0.0);
+        }
+    }
+    __syncthreads();
+
+    const int total = nn * nch;  // chunks streamed by this CTA
+    if (warp == 8) {
+        // ===== producer =====
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0;
+            for (int b = 0; b < nn; b++) {
+                const long long pair = (long long)kl * nn + b;
+                const long long kp = kpb[pair];
+                const double* srcA = Mt + pair * nch * (long long)(A_D2 * 2);
+                const double* srcB = Up + (kp * nct + ct) * nch * (long long)(B_D2 * 2);
+                for (int c = 0; c < nch; c++) {
+                    mbar_wait(smem_u32(&bars[STAGES + s]), ph ^ 1);
+                    const uint32_t full = smem_u32(&bars[s]);
+                    mbar_arrive_expect_tx(full, A_BYTES + B_BYTES);
+                    bulk_g2s(smem_u32(sA + s * A_D2), srcA + (long long)c * (A_D2 * 2), A_BYTES, full);
+                    bulk_g2s(smem_u32(sB + s * B_D2), srcB + (long long)c * (B_D2 * 2), B_BYTES, full);
+                    if (++s == STAGES) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+        return;
+    }
+    (void)total;
+
+    // ===== consumers =====
+    const int wm = warp / WN, wn = warp % WN;
+    const int g = lane >> 2, t = lane & 3;
+    double cre[4][2][2], cim[4][2][2];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 2; j++) cre[i][j][0] = cre[i][j][1] = cim[i][j][0] = cim[i][j][1] = 0.0;
+
+    int s = 0;
+    uint32_t ph = 0;
+    for (int b = 0; b < nn; b++) {
+        for (int c = 0; c < nch; c++) {
+            mbar_wait(smem_u32(&bars[s]), ph);
+            const cplx* Ap = sA + s * A_D2 + (wm * KS * 4) * 32 + lane;
+            const cplx* Bp = sB + s * B_D2 + (wn * KS * 2) * 32 + lane;
+#pragma unroll
+            for (int ks = 0; ks < KS; ks++) {
+                cplx a[4], bb[2];
+                double nbi[2];
+#pragma unroll
+                for (int mt = 0; mt < 4; mt++) a[mt] = Ap[(ks * 4 + mt) * 32];
+#pragma unroll
+                for (int nt = 0; nt < 2; nt++) {
+                    bb[nt] = Bp[(ks * 2 + nt) * 32];
+                    nbi[nt] = neg_f64(bb[nt].y);
+                }
+#pragma unroll
+                for (int mt = 0; mt < 4; mt++)
+#pragma unroll
+                    for (int nt = 0; nt < 2; nt++) {
+                        dmma884(cre[mt][nt][0], cre[mt][nt][1], a[mt].x, bb[nt].x);
+                        dmma884(cim[mt][nt][0], cim[mt][nt][1], a[mt].x, bb[nt].y);
+                    }
+#pragma unroll
+                for (int mt = 0; mt < 4; mt++)
+#pragma unroll
+                    for (int nt = 0; nt < 2; nt++) {
+                        dmma884(cre[mt][nt][0], cre[mt][nt][1], a[mt].y, nbi[nt]);
+                        dmma884(cim[mt][nt][0], cim[mt][nt][1], a[mt].y, bb[nt].x);
+                    }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&bars[STAGES + s]));
+            if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+        // ----- epilogue of pair (k, b): store MU, partial diag N, partial ||MU||_F^2 -----
+        const long long pair = (long long)kl * nn + b;
+        cplx* mu = MU + pair * (long long)nb * nw;
+        const cplx* uk = sUk + (warp * 16) * 32 + lane;
+        cplx d[2][2];
+        double f = 0.0;
+#pragma unroll
+        for (int nt = 0; nt < 2; nt++)
+#pragma unroll
+            for (int j = 0; j < 2; j++) d[nt][j] = make_double2(0.0, 0.0);
+#pragma unroll
+        for (int mt = 0; mt < 4; mt++)
+#pragma unroll
+            for (int nt = 0; nt < 2; nt++)
+#pragma unroll
+                for (int j = 0; j < 2; j++) {
+                    const cplx x = make_double2(cre[mt][nt][j], cim[mt][nt][j]);
+                    const int m = wm * 32 + mt * 8 + g, n = n0 + wn * 16 + nt * 8 + 2 * t + j;
+                    if (m < nb && n < nw) mu[m + (long long)n * nb] = x;
+                    cfma_conj(d[nt][j], uk[((mt * 2 + nt) * 2 + j) * 32], x);
+                    f = fma(x.x, x.x, f);
+                    f = fma(x.y, x.y, f);
+                    cre[mt][nt][j] = 0.0;
+                    cim[mt][nt][j] = 0.0;
+                }
+        // reduce over the 8 row groups g (lanes with equal t)
+#pragma unroll
+        for (int nt = 0; nt < 2; nt++)
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+#pragma unroll
+                for (int o = 4; o < 32; o <<= 1) {
+                    d[nt][j].x += __shfl_xor_sync(0xffffffffu, d[nt][j].x, o);
+                    d[nt][j].y += __shfl_xor_sync(0xffffffffu, d[nt][j].y, o);
+                }
+            }
+        f = warp_sum(f);
+        if (g == 0) {
+#pragma unroll
+            for (int nt = 0; nt < 2; nt++)
+#pragma unroll
+                for (int j = 0; j < 2; j++) {
+                    const int n = n0 + wn * 16 + nt * 8 + 2 * t + j;
+                    if (n < nw) dNp[(pair * WM + wm) * nw + n] = d[nt][j];
+                }
+        }
+        if (lane == 0) frop[(pair * nct + ct) * 8 + warp] = f;
+    }
+}
+
+// dN[pair][n] = sum_wm dNp[pair][wm][n];  fro[pair] = sum frop[pair][:]   (fixed order)
+__global__ void __launch_bounds__(128) combine_partials_kernel(int nw, int WM, int nfro,
+                                                               const cplx* __restrict__ dNp,
+                                                               const double* __restrict__ frop,
+                                                               cplx* __restrict__ dN,
+                                                               double* __restrict__ fro) {
+    const long long pair = blockIdx.x;
+    for (int n = threadIdx.x; n < nw; n += blockDim.x) {
+        cplx s = make_double2(0.0, 0.0);
+        for (int w = 0; w < WM; w++) {
+            const cplx v = dNp[(pair * WM + w) * nw + n];
+            s.x += v.x;
+            s.y += v.y;
+        }
+        dN[pair * nw + n] = s;
+    }
+    if (threadIdx.x == 0) {
+        double f = 0.0;
+        for (int i = 0; i < nfro; i++) f += frop[pair * nfro + i];
+        fro[pair] = f;
+    }
+}
+
+template <int WM, int WN, int KC, int STAGES>
+size_t smem_bytes() {
+    constexpr int KS = KC / 4;
+    return sizeof(cplx) * (8 * 16 * 32 + (size_t)STAGES * (WM * KS * 4 * 32 + WN * KS * 2 * 32)) +
+           sizeof(unsigned long long) * 2 * STAGES;
+}
+
+template <int WM, int WN, int KC, int STAGES>
+int launch_rotate(wb200_ctx* ctx, const cplx* dU) {
+    DmmaPlan* p = ctx->dmma;
+    auto kern = rotate_dmma_kernel<WM, WN, KC, STAGES>;
+    static bool attr_done[16] = {false};
+    if (!attr_done[ctx->device & 15]) {
+        WB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
+        attr_done[ctx->device & 15] = true;
+    }
+    kern<<<ctx->nk * p->nct, 288, p->smem, ctx->stream>>>(ctx->nb, ctx->nw, ctx->nn, p->nch, p->nct,
+                                                          ctx->k_begin, ctx->d_kpb, p->d_Mt, p->d_Up,
+                                                          dU, ctx->d_MU, p->d_dNp, p->d_frop);
+    WB_LAUNCH_CHECK(ctx);
+    return WB200_OK;
+}
+
+}  // namespace
+
+// KC / STAGES per configuration (shared memory: 64 KB U_k tile + STAGES x (A + B) stage)
+#define WB_CFG_128 4, 2, 16, 4   /* 64 < nb <= 128: CTA 128 x 32, stage 32+8 KB  -> 224 KB */
+#define WB_CFG_256 8, 1, 8, 4    /* 128 < nb <= 256: CTA 256 x 16, stage 32+2 KB -> 200 KB */
+#define WB_CFG_64 2, 4, 16, 4    /* 32 < nb <= 64:  CTA 64 x 64, stage 16+16 KB  -> 192 KB */
+
+int wb_dmma_plan_create(wb200_ctx* ctx, const double* /*hM*/) {
+    const int nb = ctx->nb, nw = ctx->nw;
+    if (nb <= 32 || nb > 256) return WB200_OK;  // CUDA-core path
+    DmmaPlan* p = new DmmaPlan();
+    if (nb <= 64) { p->WM = 2; p->WN = 4; p->KC = 16; p->smem = smem_bytes<WB_CFG_64>(); }
+    else if (nb <= 128) { p->WM = 4; p->WN = 2; p->KC = 16; p->smem = smem_bytes<WB_CFG_128>(); }
+    else { p->WM = 8; p->WN = 1; p->KC = 8; p->smem = smem_bytes<WB_CFG_256>(); }
+    p->NB = 32 * p->WM;
+    p->NC = 16 * p->WN;
+    p->nct = (nw + p->NC - 1) / p->NC;
+    p->nch = (nb + p->KC - 1) / p->KC;
+    ctx->dmma = p;
+    const size_t pairs = (size_t)ctx->nk * ctx->nn;
+    const size_t a_stage = (size_t)p->NB * p->KC * 2, b_stage = (size_t)p->KC * p->NC * 2;
+    WB_CUDA(ctx, cudaMalloc(&p->d_Mt, sizeof(double) * pairs * p->nch * a_stage));
+    WB_CUDA(ctx, cudaMalloc(&p->d_Up, sizeof(double) * (size_t)ctx->nk_total * p->nct * p->nch * b_stage));
+    WB_CUDA(ctx, cudaMalloc(&p->d_dNp, sizeof(cplx) * pairs * p->WM * nw));
+    WB_CUDA(ctx, cudaMalloc(&p->d_frop, sizeof(double) * pairs * p->nct * 8));
+    // re-lay-out M (already uploaded to d_M) into the A-operand image; d_M is then released:
+    // the tensor path never reads the plain layout again.
+    const int ZMAX = 65535;
+    (void)ZMAX;
+    dim3 grid((unsigned)pairs, (unsigned)p->nch);
+    tile_overlaps_kernel<<<grid, 256, 0, ctx->stream>>>(nb, p->WM, p->KC, p->nch, ctx->d_M,
+                                                        (cplx*)p->d_Mt);
+    WB_LAUNCH_CHECK(ctx);
+    WB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->d_M);
+    ctx->d_M = nullptr;
+    return WB200_OK;
+}
+
+void wb_dmma_plan_destroy(wb200_ctx* ctx) {
+    DmmaPlan* p = ctx->dmma;
+    if (!p) return;
+    if (p->d_Mt) cudaFree(p->d_Mt);
+    if (p->d_Up) cudaFree(p->d_Up);
+    if (p->d_dNp) cudaFree(p->d_dNp);
+    if (p->d_frop) cudaFree(p->d_frop);
+    delete p;
+    ctx->dmma = nullptr;
+}
+
+int wb_rotate_dmma(wb200_ctx* ctx, const cplx* dU) {
+    DmmaPlan* p = ctx->dmma;
+    dim3 g((unsigned)ctx->nk_total, (unsigned)(p->nch * p->nct));
+    pack_gauge_kernel<<<g, 256, 0, ctx->stream>>>(ctx->nb, ctx->nw, p->WN, p->KC, p->nch, p->nct, dU,
+                                                  (cplx*)p->d_Up);
+    WB_LAUNCH_CHECK(ctx);
+    if (p->WM == 2) WB_TRY((launch_rotate<WB_CFG_64>(ctx, dU)));
+    else if (p->WM == 4) WB_TRY((launch_rotate<WB_CFG_128>(ctx, dU)));
+    else WB_TRY((launch_rotate<WB_CFG_256>(ctx, dU)));
+    combine_partials_kernel<<<ctx->nk * ctx->nn, 128, 0, ctx->stream>>>(
+        ctx->nw, p->WM, p->nct * 8, p->d_dNp, p->d_frop, ctx->d_dN, ctx->d_fro);
+    WB_LAUNCH_CHECK(ctx);
+    return WB200_OK;
+}

@@ -1,0 +1,338 @@
+// stiefel.cu — per-k Stiefel-manifold operations, the (X, Y) disentanglement chain and the flat
+// vector kernels the device-resident optimiser needs.
+//
+// Replaces (reference tree):
+//   Optim.Stiefel_SVD project_tangent! / retract!  (third-party Optim.jl; call sites
+//       src/localization/max_localize.jl:62-63, src/localization/disentangle.jl:687-690)
+//   X_Y_to_U!      src/localization/disentangle.jl:351-356
+//   XY_to_X_Y!     src/localization/disentangle.jl:424-435   (a view: column ik of XY already IS
+//                  [X_k col-major ; Y_k col-major], so no copy is made)
+//   GU_to_GX_GY    src/localization/disentangle.jl:481-501
+#include "common.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// S <- (S + S^H)/2 for a batch of n x n matrices (contiguous)
+// ---------------------------------------------------------------------------------------------
+__global__ void hermitize_kernel(int n, long long total, cplx* __restrict__ S) {
+    const long long nn2 = (long long)n * n;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+         e += (long long)gridDim.x * blockDim.x) {
+        const long long mat = e / nn2;
+        const int r = (int)(e % nn2);
+        const int i = r % n, j = r / n;
+        if (i > j) continue;
+        cplx* base = S + mat * nn2;
+        const cplx a = base[i + (long long)j * n], b = base[j + (long long)i * n];
+        const cplx h = make_double2(0.5 * (a.x + b.x), 0.5 * (a.y - b.y));
+        base[i + (long long)j * n] = h;
+        base[j + (long long)i * n] = cconj(h);
+    }
+}
+
+static int project_strided(wb200_ctx* ctx, const cplx* dX, cplx* dG, int nrow, int ncol, int ld,
+                           long long stride, int count) {
+    WB_TRY(wb_ensure_tmp(ctx, (size_t)count * ncol * ncol, 0));
+    ZgemmArgs a{};
+    a.m = ncol; a.n = ncol; a.k = nrow;
+    a.A = dX; a.strideA = stride; a.lda = ld; a.transA = 1;
+    a.B = dG; a.strideB = stride; a.ldb = ld; a.transB = 0;
+    a.C = ctx->d_tmp1; a.strideC = (long long)ncol * ncol; a.ldc = ncol;
+    a.alpha = 1.0; a.beta = 0.0; a.batch = count;
+    WB_TRY(wb_zgemm_batched(ctx, a));
+    const long long total = (long long)count * ncol * ncol;
+    const int blocks = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
+    hermitize_kernel<<<blocks, 256, 0, ctx->stream>>>(ncol, total, ctx->d_tmp1);
+    WB_LAUNCH_CHECK(ctx);
+    ZgemmArgs b{};
+    b.m = nrow; b.n = ncol; b.k = ncol;
+    b.A = dX; b.strideA = stride; b.lda = ld; b.transA = 0;
+    b.B = ctx->d_tmp1; b.strideB = (long long)ncol * ncol; b.ldb = ncol; b.transB = 0;
+    b.C = dG; b.strideC = stride; b.ldc = ld;
+    b.alpha = -1.0; b.beta = 1.0; b.batch = count;
+    WB_TRY(wb_zgemm_batched(ctx, b));
+    return WB200_OK;
+}
+
+int wb_project_tangent_dev(wb200_ctx* ctx, const cplx* dX, cplx* dG, int nrow, int ncol, int count) {
+    return project_strided(ctx, dX, dG, nrow, ncol, nrow, (long long)nrow * ncol, count);
+}
+
+// ---------------------------------------------------------------------------------------------
+// polar factor by Newton-Schulz:  X <- X (3 I - X^H X)/2
+// The kernel below turns P = X^H X into T = s (1.5 I - 0.5 s^2 P) in place (s = 1 unless the
+// matrix is far from unitary, then s = 1/||X||_F so that all singular values are < sqrt 3) and
+// records max_k ||P_k - I||_F.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ns_prepare_kernel(int n, cplx* __restrict__ P,
+                                                         double* __restrict__ err_max) {
+    cplx* p = P + (long long)blockIdx.x * n * n;
+    double e2 = 0.0, tr = 0.0;
+    for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+        const int i = e % n, j = e / n;
+        const cplx v = p[e];
+        const double dx = v.x - (i == j ? 1.0 : 0.0);
+        e2 += dx * dx + v.y * v.y;
+        if (i == j) tr += v.x;
+    }
+    __shared__ double s1[8], s2[8];
+    __shared__ double scale;
+    e2 = warp_sum(e2);
+    tr = warp_sum(tr);
+    if ((threadIdx.x & 31) == 0) { s1[threadIdx.x >> 5] = e2; s2[threadIdx.x >> 5] = tr; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0, b = 0.0;
+        for (int w = 0; w < 8; w++) { a += s1[w]; b += s2[w]; }
+        const double err = sqrt(a);
+        // err >= max |sigma^2 - 1|; Newton-Schulz needs sigma^2 < 3
+        scale = (err < 1.5) ? 1.0 : rsqrt(b);
+        atomicMax((unsigned long long*)err_max, (unsigned long long)__double_as_longlong(err));
+    }
+    __syncthreads();
+    const double s = scale, s3 = 0.5 * s * s * s;
+    for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+        const int i = e % n, j = e / n;
+        cplx v = p[e];
+        v.x = (i == j ? 1.5 * s : 0.0) - s3 * v.x;
+        v.y = -s3 * v.y;
+        p[e] = v;
+    }
+}
+
+__global__ void copy_strided_kernel(int nrow, int ncol, int ld, long long stride, long long total,
+                                    const cplx* __restrict__ src, cplx* __restrict__ dst) {
+    const long long per = (long long)nrow * ncol;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+         e += (long long)gridDim.x * blockDim.x) {
+        const long long mat = e / per;
+        const int r = (int)(e % per);
+        dst[mat * stride + (r % nrow) + (long long)(r / nrow) * ld] = src[e];
+    }
+}
+
+static int retract_strided(wb200_ctx* ctx, cplx* dX, int nrow, int ncol, int ld, long long stride,
+                           int count, int* iters_out) {
+    const int MAXIT = 100;
+    const double TOL = 2e-8;  // quadratic convergence: the update applied at err<2e-8 leaves ~1e-15
+    WB_TRY(wb_ensure_tmp(ctx, (size_t)count * ncol * ncol, (size_t)count * nrow * ncol));
+    int it = 0;
+    double err = 0.0;
+    for (; it < MAXIT; it++) {
+        ZgemmArgs a{};
+        a.m = ncol; a.n = ncol; a.k = nrow;
+        a.A = dX; a.strideA = stride; a.lda = ld; a.transA = 1;
+        a.B = dX; a.strideB = stride; a.ldb = ld; a.transB = 0;
+        a.C = ctx->d_tmp1; a.strideC = (long long)ncol * ncol; a.ldc = ncol;
+        a.alpha = 1.0; a.beta = 0.0; a.batch = count;
+        WB_TRY(wb_zgemm_batched(ctx, a));
+        WB_CUDA(ctx, cudaMemsetAsync(ctx->d_scal, 0, sizeof(double), ctx->stream));
+        ns_prepare_kernel<<<count, 256, 0, ctx->stream>>>(ncol, ctx->d_tmp1, ctx->d_scal);
+        WB_LAUNCH_CHECK(ctx);
+        WB_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, ctx->d_scal, sizeof(double),
+                                     cudaMemcpyDeviceToHost, ctx->stream));
+        ZgemmArgs b{};
+        b.m = nrow; b.n = ncol; b.k = ncol;
+        b.A = dX; b.strideA = stride; b.lda = ld; b.transA = 0;
+        b.B = ctx->d_tmp1; b.strideB = (long long)ncol * ncol; b.ldb = ncol; b.transB = 0;
+        b.C = ctx->d_tmp2; b.strideC = (long long)nrow * ncol; b.ldc = nrow;
+        b.alpha = 1.0; b.beta = 0.0; b.batch = count;
+        WB_TRY(wb_zgemm_batched(ctx, b));
+        const long long total = (long long)count * nrow * ncol;
+        if (ld == nrow && stride == (long long)nrow * ncol) {
+            WB_CUDA(ctx, cudaMemcpyAsync(dX, ctx->d_tmp2, sizeof(cplx) * total,
+                                         cudaMemcpyDeviceToDevice, ctx->stream));
+        } else {
+            const int blocks = (int)((total + 255) / 256 < 8192 ? (total + 255) / 256 : 8192);
+            copy_strided_kernel<<<blocks, 256, 0, ctx->stream>>>(nrow, ncol, ld, stride, total,
+                                                                 ctx->d_tmp2, dX);
+            WB_LAUNCH_CHECK(ctx);
+        }
+        WB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        err = ctx->h_pinned[0];
+        if (!(err == err)) {
+            ctx->err = "retract: NaN in X^H X";
+            return WB200_ERR_NOCONV;
+        }
+        if (err < TOL) { it++; break; }
+    }
+    if (iters_out) *iters_out = it;
+    if (err >= TOL) {
+        ctx->err = "retract: Newton-Schulz polar iteration did not converge (||X^H X - I||_F = " +
+                   std::to_string(err) + ")";
+        return WB200_ERR_NOCONV;
+    }
+    return WB200_OK;
+}
+
+int wb_retract_dev(wb200_ctx* ctx, cplx* dX, int nrow, int ncol, int count, int* iters) {
+    return retract_strided(ctx, dX, nrow, ncol, nrow, (long long)nrow * ncol, count, iters);
+}
+
+// manifold ops on the packed XY array (product manifold per k)
+int wb_retract_xy(wb200_ctx* ctx, cplx* dXY) {
+    const int nb = ctx->nb, nw = ctx->nw;
+    const long long st = (long long)nw * nw + (long long)nb * nw;
+    WB_TRY(retract_strided(ctx, dXY, nw, nw, nw, st, ctx->nk, nullptr));
+    WB_TRY(retract_strided(ctx, dXY + (long long)nw * nw, nb, nw, nb, st, ctx->nk, nullptr));
+    return WB200_OK;
+}
+int wb_project_xy(wb200_ctx* ctx, const cplx* dXY, cplx* dG) {
+    const int nb = ctx->nb, nw = ctx->nw;
+    const long long st = (long long)nw * nw + (long long)nb * nw;
+    WB_TRY(project_strided(ctx, dXY, dG, nw, nw, nw, st, ctx->nk));
+    WB_TRY(project_strided(ctx, dXY + (long long)nw * nw, dG + (long long)nw * nw, nb, nw, nb, st,
+                           ctx->nk));
+    return WB200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// (X, Y) chain
+// ---------------------------------------------------------------------------------------------
+int wb_xy_to_u(wb200_ctx* ctx, const cplx* dXY, cplx* dU) {
+    const int nb = ctx->nb, nw = ctx->nw;
+    const long long st = (long long)nw * nw + (long long)nb * nw;
+    ZgemmArgs a{};
+    a.m = nb; a.n = nw; a.k = nw;
+    a.A = dXY + (long long)nw * nw; a.strideA = st; a.lda = nb; a.transA = 0;   // Y_k
+    a.B = dXY; a.strideB = st; a.ldb = nw; a.transB = 0;                        // X_k
+    a.C = dU; a.strideC = (long long)nb * nw; a.ldc = nb;
+    a.alpha = 1.0; a.beta = 0.0; a.batch = ctx->nk;
+    return wb_zgemm_batched(ctx, a);
+}
+
+// zero G_Y[frozen rows, :] and G_Y[:, 0:n_frozen)   (disentangle.jl:495-496)
+__global__ void mask_gy_kernel(int nb, int nw, long long st, const uint8_t* __restrict__ frozen,
+                               const int32_t* __restrict__ nfrozen, cplx* __restrict__ GXY) {
+    const int k = blockIdx.x;
+    cplx* gy = GXY + (long long)k * st + (long long)nw * nw;
+    const int nf = nfrozen[k];
+    for (int e = threadIdx.x; e < nb * nw; e += blockDim.x) {
+        const int m = e % nb, n = e / nb;
+        if (frozen[(long long)k * nb + m] || n < nf) gy[e] = make_double2(0.0, 0.0);
+    }
+}
+
+int wb_gu_to_gxy(wb200_ctx* ctx, const cplx* dXY, const cplx* dGU, cplx* dGXY) {
+    const int nb = ctx->nb, nw = ctx->nw;
+    const long long st = (long long)nw * nw + (long long)nb * nw;
+    ZgemmArgs a{};  // G_X = Y^H G_U
+    a.m = nw; a.n = nw; a.k = nb;
+    a.A = dXY + (long long)nw * nw; a.strideA = st; a.lda = nb; a.transA = 1;
+    a.B = dGU; a.strideB = (long long)nb * nw; a.ldb = nb; a.transB = 0;
+    a.C = dGXY; a.strideC = st; a.ldc = nw;
+    a.alpha = 1.0; a.beta = 0.0; a.batch = ctx->nk;
+    WB_TRY(wb_zgemm_batched(ctx, a));
+    ZgemmArgs b{};  // G_Y = G_U X^H
+    b.m = nb; b.n = nw; b.k = nw;
+    b.A = dGU; b.strideA = (long long)nb * nw; b.lda = nb; b.transA = 0;
+    b.B = dXY; b.strideB = st; b.ldb = nw; b.transB = 1;
+    b.C = dGXY + (long long)nw * nw; b.strideC = st; b.ldc = nb;
+    b.alpha = 1.0; b.beta = 0.0; b.batch = ctx->nk;
+    WB_TRY(wb_zgemm_batched(ctx, b));
+    if (ctx->d_frozen) {
+        mask_gy_kernel<<<ctx->nk, 256, 0, ctx->stream>>>(nb, nw, st, ctx->d_frozen, ctx->d_nfrozen,
+                                                          dGXY);
+        WB_LAUNCH_CHECK(ctx);
+    }
+    return WB200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// flat vector kernels (arrays of doubles; complex arrays are passed as 2n doubles)
+// ---------------------------------------------------------------------------------------------
+#define WB_RED_BLOCKS 1184  // 148 SMs x 8
+
+__global__ void __launch_bounds__(256) dot_stage1(const double* __restrict__ a,
+                                                  const double* __restrict__ b, size_t n,
+                                                  double* __restrict__ partial) {
+    double s = 0.0;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x)
+        s = fma(a[i], b[i], s);
+    __shared__ double sh[8];
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; w++) t += sh[w];
+        partial[blockIdx.x] = t;
+    }
+}
+// complex modulus max (Optim's g_tol is on maximum(abs, g) of the complex array)
+__global__ void __launch_bounds__(256) cabsmax_stage1(const cplx* __restrict__ a, size_t n,
+                                                      double* __restrict__ partial) {
+    double s = 0.0;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const cplx v = a[i];
+        s = fmax(s, v.x * v.x + v.y * v.y);
+    }
+    __shared__ double sh[8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s = fmax(s, __shfl_xor_sync(0xffffffffu, s, o));
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; w++) t = fmax(t, sh[w]);
+        partial[blockIdx.x] = t;
+    }
+}
+__global__ void __launch_bounds__(256) red_stage2(const double* __restrict__ partial, int n,
+                                                  int is_max, double* __restrict__ out) {
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s = is_max ? fmax(s, partial[i]) : s + partial[i];
+    __shared__ double sh[8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double t = __shfl_xor_sync(0xffffffffu, s, o);
+        s = is_max ? fmax(s, t) : s + t;
+    }
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; w++) t = is_max ? fmax(t, sh[w]) : t + sh[w];
+        *out = is_max ? sqrt(t) : t;
+    }
+}
+
+static int red_finish(wb200_ctx* ctx, int is_max, double* out_host) {
+    red_stage2<<<1, 256, 0, ctx->stream>>>(ctx->d_scal + 8, WB_RED_BLOCKS, is_max, ctx->d_scal);
+    WB_LAUNCH_CHECK(ctx);
+    WB_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, ctx->d_scal, sizeof(double), cudaMemcpyDeviceToHost,
+                                 ctx->stream));
+    WB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *out_host = ctx->h_pinned[0];
+    return WB200_OK;
+}
+
+int wb_dot(wb200_ctx* ctx, const double* a, const double* b, size_t n, double* out_host) {
+    dot_stage1<<<WB_RED_BLOCKS, 256, 0, ctx->stream>>>(a, b, n, ctx->d_scal + 8);
+    WB_LAUNCH_CHECK(ctx);
+    return red_finish(ctx, 0, out_host);
+}
+int wb_absmax(wb200_ctx* ctx, const double* a, size_t n, double* out_host) {
+    cabsmax_stage1<<<WB_RED_BLOCKS, 256, 0, ctx->stream>>>((const cplx*)a, n / 2, ctx->d_scal + 8);
+    WB_LAUNCH_CHECK(ctx);
+    return red_finish(ctx, 1, out_host);
+}
+
+__global__ void axpbyz_kernel(double alpha, const double* x, double beta, const double* y, double* z,
+                              size_t n) {  // z may alias x or y (same index only)
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x)
+        z[i] = alpha * x[i] + (beta == 0.0 ? 0.0 : beta * y[i]);
+}
+int wb_axpbyz(wb200_ctx* ctx, double alpha, const double* x, double beta, const double* y, double* z,
+              size_t n) {
+    const size_t want = (n + 255) / 256;
+    const int blocks = (int)(want < 148 * 16 ? (want ? want : 1) : 148 * 16);
+    axpbyz_kernel<<<blocks, 256, 0, ctx->stream>>>(alpha, x, beta, y, z, n);
+    WB_LAUNCH_CHECK(ctx);
+    return WB200_OK;
+}
+int wb_axpby(wb200_ctx* ctx, double alpha, const double* x, double beta, double* y, size_t n) {
+    return wb_axpbyz(ctx, alpha, x, beta, y, y, n);
+}

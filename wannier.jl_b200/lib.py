@@ -1,0 +1,285 @@
+"""ctypes binding of libwannier_b200.so (the C-ABI declared in include/wannier_b200.h).
+
+This is the same thin layer a Julia `ccall` wrapper would be: plain
+pointers and sizes in, status codes out.  There is NO fallback of any kind: if the shared library
+is missing or a call fails, an exception is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libwannier_b200.so")
+
+# every symbol include/wannier_b200.h declares (tests check that the .so exports all of them)
+SYMBOLS = [
+    "wb200_create", "wb200_destroy", "wb200_last_error", "wb200_version", "wb200_set_stream",
+    "wb200_synchronize", "wb200_rotation_kernel", "wb200_launch_count", "wb200_set_penalty",
+    "wb200_set_frozen", "wb200_fg", "wb200_spread", "wb200_center", "wb200_rotate_overlaps",
+    "wb200_fg_xy", "wb200_project_tangent", "wb200_retract", "wb200_max_localize",
+    "wb200_disentangle", "wb200_nsums", "wb200_nres", "wb200_fg_phase1_dev", "wb200_fg_phase2_dev",
+    "wb200_fg_dev", "wb200_min_abs_diag", "wb200_project_tangent_dev", "wb200_retract_dev",
+]
+
+FLAG_DEFAULT = 0
+FLAG_NO_TENSOR = 1
+FLAG_FORCE_TENSOR = 2
+
+
+class WB200Error(RuntimeError):
+    def __init__(self, status, msg):
+        super().__init__(f"libwannier_b200 status {status}: {msg}")
+        self.status = status
+
+
+_lib = None
+
+
+def load():
+    """dlopen the library (once).  Raises if it has not been built: the product path never
+    degrades to a CPU implementation."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise FileNotFoundError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'`"
+            " (there is no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, dbl = C.c_void_p, C.c_int, C.c_double
+    pd = C.c_void_p  # all array arguments are passed as raw addresses
+    lib.wb200_create.argtypes = [C.POINTER(vp), i32, i32, i32, i32, i32, i32, i32, pd, pd, pd, pd,
+                                 C.c_uint]
+    lib.wb200_create.restype = i32
+    lib.wb200_destroy.argtypes = [vp]
+    lib.wb200_destroy.restype = None
+    lib.wb200_last_error.argtypes = [vp]
+    lib.wb200_last_error.restype = C.c_char_p
+    lib.wb200_version.argtypes = []
+    lib.wb200_version.restype = C.c_char_p
+    lib.wb200_set_stream.argtypes = [vp, vp]
+    lib.wb200_synchronize.argtypes = [vp]
+    lib.wb200_rotation_kernel.argtypes = [vp]
+    lib.wb200_launch_count.argtypes = [vp]
+    lib.wb200_launch_count.restype = C.c_longlong
+    lib.wb200_set_penalty.argtypes = [vp, pd, dbl]
+    lib.wb200_set_frozen.argtypes = [vp, pd]
+    lib.wb200_fg.argtypes = [vp, pd, pd, pd]
+    lib.wb200_spread.argtypes = [vp, pd, pd, pd, pd, pd]
+    lib.wb200_center.argtypes = [vp, pd, pd]
+    lib.wb200_rotate_overlaps.argtypes = [vp, pd, pd, pd]
+    lib.wb200_fg_xy.argtypes = [vp, pd, pd, pd]
+    lib.wb200_project_tangent.argtypes = [vp, pd, pd, i32, i32, i32]
+    lib.wb200_retract.argtypes = [vp, pd, i32, i32, i32]
+    lib.wb200_max_localize.argtypes = [vp, pd, dbl, dbl, i32, i32, pd, pd, pd]
+    lib.wb200_disentangle.argtypes = [vp, pd, dbl, dbl, i32, i32, pd, pd, pd]
+    lib.wb200_nsums.argtypes = [vp]
+    lib.wb200_nres.argtypes = [vp]
+    lib.wb200_fg_phase1_dev.argtypes = [vp, pd, pd, i32]
+    lib.wb200_fg_phase2_dev.argtypes = [vp, pd, pd, pd]
+    lib.wb200_fg_dev.argtypes = [vp, pd, pd, pd, i32]
+    lib.wb200_min_abs_diag.argtypes = [vp, pd]
+    lib.wb200_project_tangent_dev.argtypes = [vp, pd, pd, i32, i32, i32]
+    lib.wb200_retract_dev.argtypes = [vp, pd, i32, i32, i32, pd]
+    for name in SYMBOLS:
+        f = getattr(lib, name)
+        if name not in ("wb200_destroy", "wb200_last_error", "wb200_version", "wb200_launch_count"):
+            f.restype = i32
+    _lib = lib
+    return lib
+
+
+def _addr(a):
+    """address of a numpy array / int pointer / None"""
+    if a is None:
+        return None
+    if isinstance(a, (int, np.integer)):
+        return int(a)
+    return a.ctypes.data
+
+
+def _check_array(a, dtype, size, name):
+    if not isinstance(a, np.ndarray) or a.dtype != dtype or not a.flags["C_CONTIGUOUS"]:
+        raise TypeError(f"{name}: need a C-contiguous numpy array of {dtype}")
+    if a.size != size:
+        raise ValueError(f"{name}: expected {size} elements, got {a.size}")
+
+
+class Context:
+    """Owns one wb200_ctx (one k-slab on one B200).  Arrays are passed in the C-ABI's memory
+    layout (= Julia's): U [nk][nw][nb] complex128, M [nk][nn][nb(l)][nb(m)], G like U."""
+
+    def __init__(self, nb, nw, nk_total, nn, kpb_k, bvec, bweights, M, *, device=0, k_begin=0,
+                 nk=None, flags=FLAG_DEFAULT):
+        self._h = None
+        lib = load()
+        nk = nk_total if nk is None else nk
+        kpb_k = np.ascontiguousarray(kpb_k, dtype=np.int32)
+        bvec = np.ascontiguousarray(bvec, dtype=np.float64)
+        bweights = np.ascontiguousarray(bweights, dtype=np.float64)
+        _check_array(kpb_k, np.int32, nk * nn, "kpb_k")
+        _check_array(bvec, np.float64, nk * nn * 3, "bvec")
+        _check_array(bweights, np.float64, nn, "bweights")
+        if not isinstance(M, (int, np.integer)):      # an int is a raw (device) address
+            _check_array(M, np.complex128, nk * nn * nb * nb, "M")
+        self.nb, self.nw, self.nk_total, self.nn, self.nk, self.k_begin = nb, nw, nk_total, nn, nk, k_begin
+        self.device = device
+        h = C.c_void_p()
+        st = lib.wb200_create(C.byref(h), device, nb, nw, nk_total, k_begin, nk, nn, _addr(kpb_k),
+                              _addr(bvec), _addr(bweights), _addr(M), flags)
+        if st != 0:
+            raise WB200Error(st, lib.wb200_last_error(None).decode())
+        self._h = h
+        self._lib = lib
+
+    # -- plumbing ---------------------------------------------------------------------------
+    def close(self):
+        if self._h is not None:
+            self._lib.wb200_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, st):
+        if st != 0:
+            raise WB200Error(st, self._lib.wb200_last_error(self._h).decode())
+
+    @property
+    def rotation_kernel(self):
+        return ("cuda-core-fp64", "dmma-fp64")[self._lib.wb200_rotation_kernel(self._h)]
+
+    @property
+    def launch_count(self):
+        return int(self._lib.wb200_launch_count(self._h))
+
+    @property
+    def nsums(self):
+        return self._lib.wb200_nsums(self._h)
+
+    @property
+    def nres(self):
+        return self._lib.wb200_nres(self._h)
+
+    def set_stream(self, stream_ptr):
+        self._ck(self._lib.wb200_set_stream(self._h, stream_ptr))
+
+    def synchronize(self):
+        self._ck(self._lib.wb200_synchronize(self._h))
+
+    def set_penalty(self, r0, lam):
+        if r0 is None:
+            self._ck(self._lib.wb200_set_penalty(self._h, None, 0.0))
+            return
+        r0 = np.ascontiguousarray(r0, dtype=np.float64)
+        _check_array(r0, np.float64, 3 * self.nw, "r0")
+        self._ck(self._lib.wb200_set_penalty(self._h, _addr(r0), float(lam)))
+
+    def set_frozen(self, frozen):
+        if frozen is None:
+            self._ck(self._lib.wb200_set_frozen(self._h, None))
+            return
+        fr = np.ascontiguousarray(frozen, dtype=np.uint8)
+        _check_array(fr, np.uint8, self.nk * self.nb, "frozen")
+        self._ck(self._lib.wb200_set_frozen(self._h, _addr(fr)))
+
+    # -- host entry points ------------------------------------------------------------------
+    def _u(self, U):
+        _check_array(U, np.complex128, self.nk_total * self.nb * self.nw, "U")
+        return _addr(U)
+
+    def fg(self, U, want_f=True, G=None):
+        """fg!(F, G, U): returns f (or None); writes G in place when given."""
+        f = C.c_double(0.0)
+        if G is not None:
+            _check_array(G, np.complex128, self.nk * self.nb * self.nw, "G")
+        self._ck(self._lib.wb200_fg(self._h, self._u(U), C.addressof(f) if want_f else None, _addr(G)))
+        return f.value if want_f else None
+
+    def spread(self, U):
+        out5 = np.zeros(5)
+        om = np.zeros(self.nw)
+        r = np.zeros((self.nw, 3))
+        mn = C.c_double(0.0)
+        self._ck(self._lib.wb200_spread(self._h, self._u(U), _addr(out5), _addr(om), _addr(r),
+                                        C.addressof(mn)))
+        return out5, om, r, mn.value
+
+    def center(self, U):
+        r = np.zeros((self.nw, 3))
+        self._ck(self._lib.wb200_center(self._h, self._u(U), _addr(r)))
+        return r
+
+    def rotate_overlaps(self, U, want_N=True, want_MU=False):
+        N = np.empty((self.nk, self.nn, self.nw, self.nw), dtype=np.complex128) if want_N else None
+        MU = np.empty((self.nk, self.nn, self.nw, self.nb), dtype=np.complex128) if want_MU else None
+        self._ck(self._lib.wb200_rotate_overlaps(self._h, self._u(U), _addr(N), _addr(MU)))
+        return N, MU
+
+    def fg_xy(self, XY, want_f=True, G=None):
+        n = self.nk * (self.nw * self.nw + self.nb * self.nw)
+        _check_array(XY, np.complex128, n, "XY")
+        if G is not None:
+            _check_array(G, np.complex128, n, "G_XY")
+        f = C.c_double(0.0)
+        self._ck(self._lib.wb200_fg_xy(self._h, _addr(XY), C.addressof(f) if want_f else None, _addr(G)))
+        return f.value if want_f else None
+
+    def project_tangent(self, X, G, nrow, ncol):
+        count = X.size // (nrow * ncol)
+        _check_array(X, np.complex128, count * nrow * ncol, "X")
+        _check_array(G, np.complex128, count * nrow * ncol, "G")
+        self._ck(self._lib.wb200_project_tangent(self._h, _addr(X), _addr(G), nrow, ncol, count))
+
+    def retract(self, X, nrow, ncol):
+        count = X.size // (nrow * ncol)
+        _check_array(X, np.complex128, count * nrow * ncol, "X")
+        self._ck(self._lib.wb200_retract(self._h, _addr(X), nrow, ncol, count))
+
+    def max_localize(self, U, f_tol=1e-7, g_tol=1e-5, max_iter=200, history=3):
+        self._u(U)
+        f = C.c_double(0.0)
+        it = C.c_int(0)
+        nfg = C.c_int(0)
+        self._ck(self._lib.wb200_max_localize(self._h, _addr(U), f_tol, g_tol, max_iter, history,
+                                              C.addressof(f), C.addressof(it), C.addressof(nfg)))
+        return f.value, it.value, nfg.value
+
+    def disentangle(self, XY, f_tol=1e-7, g_tol=1e-5, max_iter=200, history=3):
+        n = self.nk * (self.nw * self.nw + self.nb * self.nw)
+        _check_array(XY, np.complex128, n, "XY")
+        f = C.c_double(0.0)
+        it = C.c_int(0)
+        nfg = C.c_int(0)
+        self._ck(self._lib.wb200_disentangle(self._h, _addr(XY), f_tol, g_tol, max_iter, history,
+                                             C.addressof(f), C.addressof(it), C.addressof(nfg)))
+        return f.value, it.value, nfg.value
+
+    # -- device-pointer entry points (raw addresses, e.g. torch.Tensor.data_ptr()) -----------
+    def fg_phase1_dev(self, dU, dsums, exact_split=False):
+        self._ck(self._lib.wb200_fg_phase1_dev(self._h, dU, dsums, int(exact_split)))
+
+    def fg_phase2_dev(self, dsums, dres, dG):
+        self._ck(self._lib.wb200_fg_phase2_dev(self._h, dsums, dres, dG))
+
+    def fg_dev(self, dU, dres, dG, exact_split=False):
+        self._ck(self._lib.wb200_fg_dev(self._h, dU, dres, dG, int(exact_split)))
+
+    def min_abs_diag(self):
+        v = C.c_double(0.0)
+        self._ck(self._lib.wb200_min_abs_diag(self._h, C.addressof(v)))
+        return v.value
+
+    def project_tangent_dev(self, dX, dG, nrow, ncol, count):
+        self._ck(self._lib.wb200_project_tangent_dev(self._h, dX, dG, nrow, ncol, count))
+
+    def retract_dev(self, dX, nrow, ncol, count):
+        it = C.c_int(0)
+        self._ck(self._lib.wb200_retract_dev(self._h, dX, nrow, ncol, count, C.addressof(it)))
+        return it.value
