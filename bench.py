@@ -1,0 +1,352 @@
+#!/usr/bin/env python
+"""bench.py — fused spread+gradient evaluations per second (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config NAME]
+
+One "step" = one fg!(F, G, U) of src/localization/max_localize.jl:13-23 on synthetic inputs of the
+named shape: rotation of all (k, b) overlaps, centres/spreads (Omega, r, omega_n, Omega_I/OD/D)
+and the gradient G.  Default workload: BASELINE configs[3] (n_wann = 128, 16^3 k, 12 b), the
+configuration the metric is quoted on; it fits one B200 (about 55 GB resident).
+
+  value  evaluations/s with U already resident in HBM (device-pointer C-ABI, CUDA events on the
+         launching stream, max over ranks).
+  e2e    the same through the host-pointer drop-in call wb200_fg: U copied host->device from pinned
+         memory and Omega, G copied back, inside the timed region.
+  N > 1  strong scaling: the k-points are sharded in contiguous slabs, one process per GPU; every
+         step all-gathers the gauge slabs (NCCL), runs phase 1 on the slab, all-reduces the
+         4 nw + 2 spread sums (NCCL) and runs phase 2 (gradient of the slab).
+  --impl reference   the CPU restatement of the reference algorithm (oracle/, numpy + OpenBLAS,
+         all host cores) on a bounded k-point sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def _peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([x.strip() for x in out.strip().split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def work_per_eval(nb, nw, nk, nn):
+    pairs = nk * nn
+    flops = 8.0 * pairs * nb * nb * nw + 8.0 * pairs * nb * nw      # one GEMM + diag/scale
+    bytes_min = 16.0 * pairs * nb * nb + 2 * 16.0 * nk * nb * nw    # M once, U once, G once
+    return flops, bytes_min
+
+
+# ------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the oracle on a bounded sample, all host cores
+# ------------------------------------------------------------------------------------------
+def cpu_reference(cfg_name, steps, warmup, sample_k=None, seconds_budget=25.0):
+    from oracle import cpu_baseline as cb
+    import __graft_entry__ as ge
+    w = ge.load_package()
+    lat, grid, nb, nw = w.synthetic.CONFIGS[cfg_name]
+    st = w.synthetic.make_stencil(w.synthetic.LATTICES[lat](), grid)
+    nk, nn = st["kpb_k"].shape
+    cores = os.cpu_count() or 1
+    if sample_k is None:
+        # about 0.25 s of work per core per step at ~5 GFLOP/s/core of complex GEMM
+        per_k = 8.0 * nn * (nb * nb * nw + nb * nw * nw)
+        sample_k = int(max(cores, min(nk, cores * 8e9 / per_k)))
+    ks = np.linspace(0, nk - 1, sample_k).astype(np.int64)
+    M, U = cb.sample_inputs(w, st, nb, nw, ks)
+    run = lambda: cb.fg_sample(M, st["kpb_k"][ks], st["bvec"][ks], st["wb"], U, ks, nk, threads=cores)
+    for _ in range(warmup):
+        run()
+    ts = []
+    t_all = time.perf_counter()
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        run()
+        ts.append(time.perf_counter() - t0)
+        if time.perf_counter() - t_all > seconds_budget and len(ts) >= 2:
+            break
+    t = float(np.mean(ts))
+    value = (sample_k / nk) / t
+    return dict(value=value, unit="evals/s", cores=cores, kind="port",
+                sample=f"{sample_k} of {nk} k-points ({sample_k * nn} pairs, both ZGEMMs per pair as "
+                       f"spread.jl:173-174, omega!/omega_grad! loops), {len(ts)} x {t:.3f} s, "
+                       f"numpy+OpenBLAS, {cores} threads over k; extrapolated to the full k-grid"), t, len(ts)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="cfg4_nw128")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    metric = "spread+gradient evals/sec at n_wann=128, 16^3 k; HBM/FP64 roofline fraction"
+
+    import __graft_entry__ as ge
+    w = ge.load_package()
+    lat, grid, nb, nw = w.synthetic.CONFIGS[args.config]
+    nk = int(np.prod(grid))
+    config = {"workload": f"{args.config}: synthetic spread+gradient, n_bands={nb}, n_wann={nw}, "
+                          f"k-grid {grid[0]}x{grid[1]}x{grid[2]}", "lattice": lat,
+              "cache": "inputs larger than L2 (overlaps %.2f GB streamed every step)" %
+                       (16.0 * nk * 12 * nb * nb / 1e9)}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        cb, t, n = cpu_reference(args.config, args.steps, args.warmup)
+        line = {"impl": "reference", "metric": metric, "value": cb["value"], "unit": "evals/s",
+                "n_gpus": args.gpus, "steps": n, "warmup": args.warmup, "ms_per_step": t * 1e3,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic", "config": config, "cpu_baseline": cb,
+                "e2e": {"value": cb["value"], "unit": "evals/s", "h2d_bytes_per_step": 0,
+                        "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    st = w.synthetic.make_stencil(w.synthetic.LATTICES[lat](), grid)
+    nn = st["kpb_k"].shape[1]
+    # contiguous k-slabs along the slowest grid axis
+    bounds = [(nk * r) // world for r in range(world + 1)]
+    k0, k1 = bounds[rank], bounds[rank + 1]
+    nkl = k1 - k0
+    M = w.synthetic.make_overlaps_torch(st, nb, dev, k_begin=k0, nk=nkl)
+    dU = w.synthetic.make_gauge_torch(nk, nb, nw, dev)                      # [nk][nw][nb] abi image
+    cpu_sample = None
+    if rank == 0 and not args.no_cpu_baseline:
+        from oracle import cpu_baseline as cbm
+        cores = os.cpu_count() or 1
+        per_k = 8.0 * nn * (nb * nb * nw + nb * nw * nw)
+        sample_k = int(max(min(cores, nkl), min(nkl, cores * 8e9 / per_k)))
+        ks = np.linspace(0, nkl - 1, sample_k).astype(np.int64)
+        cpu_sample = (ks, M[torch.as_tensor(ks, device=dev)].transpose(2, 3).cpu().numpy(),
+                      dU.transpose(1, 2).cpu().numpy())
+    torch.cuda.synchronize()
+    ctx = w.Context(nb, nw, nk, nn, st["kpb_k"][k0:k1], st["bvec"][k0:k1], st["wb"], M.data_ptr(),
+                    device=local_rank, k_begin=k0, nk=nkl)
+    del M
+    torch.cuda.empty_cache()
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+    dG = torch.zeros((nkl, nw, nb), dtype=torch.complex128, device=dev)
+    dres = torch.zeros(ctx.nres, dtype=torch.float64, device=dev)
+    dsums = torch.zeros(ctx.nsums, dtype=torch.float64, device=dev)
+    dUslab = dU[k0:k1].clone()
+
+    def step():
+        if world == 1:
+            ctx.fg_dev(dU.data_ptr(), dres.data_ptr(), dG.data_ptr())
+        else:
+            # the optimiser owns U slab-wise: gather the gauges, evaluate the slab, reduce the sums
+            dist.all_gather_into_tensor(dU.view(torch.float64).view(-1), dUslab.view(torch.float64).view(-1)) \
+                if nk % world == 0 else None
+            ctx.fg_phase1_dev(dU.data_ptr(), dsums.data_ptr())
+            dist.all_reduce(dsums)
+            ctx.fg_phase2_dev(dsums.data_ptr(), dres.data_ptr(), dG.data_ptr())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    ctx.profile(True)
+    l0 = ctx.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as cs:
+        barrier()
+        e0.record(stream)
+        for _ in range(args.steps):
+            step()
+        e1.record(stream)
+        barrier()
+    ms_total = e0.elapsed_time(e1)
+    launches = ctx.launch_count - l0
+    prof = ctx.profile_read()
+    ctx.profile(False)
+    if world > 1:
+        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = t.item()
+    ms_step = ms_total / args.steps
+    value = 1e3 / ms_step
+    omega_val = dres[0].item()
+
+    # ---- end-to-end through the host-pointer drop-in call (N = 1: wb200_fg; N > 1: slab copies) ----
+    e2e = None
+    if not args.no_e2e:
+        hU = torch.empty((nk, nw, nb), dtype=torch.complex128).pin_memory()
+        hU.copy_(dU)
+        hG = torch.empty((nkl, nw, nb), dtype=torch.complex128).pin_memory()
+        hres = torch.empty(ctx.nres, dtype=torch.float64).pin_memory()
+        hUn, hGn = hU.numpy(), hG.numpy()
+
+        def step_e2e():
+            if world == 1:
+                return ctx.fg(hUn, want_f=True, G=hGn)        # wb200_fg: H2D U, compute, D2H f and G
+            dU.copy_(hU, non_blocking=True)
+            ctx.fg_phase1_dev(dU.data_ptr(), dsums.data_ptr())
+            dist.all_reduce(dsums)
+            ctx.fg_phase2_dev(dsums.data_ptr(), dres.data_ptr(), dG.data_ptr())
+            hG.copy_(dG, non_blocking=True)
+            hres.copy_(dres, non_blocking=True)
+            torch.cuda.synchronize()
+            return hres[5].item()
+
+        n_e2e = max(2, min(args.steps, 5))
+        step_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            f_e2e = step_e2e()
+        barrier()
+        dt = (time.perf_counter() - t0) / n_e2e
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = t.item()
+        e2e = {"value": 1.0 / dt, "unit": "evals/s", "h2d_bytes_per_step": int(hU.numel() * 16 * world),
+               "d2h_bytes_per_step": int(16 * nk * nb * nw + 8 * world), "steps": n_e2e,
+               "check_f": f_e2e, "api": "wb200_fg (host pointers, pinned)" if world == 1 else
+               "H2D U + phase1/all-reduce/phase2 + D2H G per rank"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    flops, bytes_min = work_per_eval(nb, nw, nk, nn)
+    dmma_peak, dfma_peak = w.lib.probe_fp64_peak(local_rank)
+    pk = _peaks()
+    hbm_peak = pk["hbm_gbs"] if pk else 6650.0
+    rot_ms, rot_n = prof["rotate"]
+    rot_ms_avg = rot_ms / max(rot_n, 1)
+    # rotation kernel: one complex GEMM per pair of the rank's slab
+    rot_flops = 8.0 * nkl * nn * nb * nb * nw
+    tensor = ctx.rotation_kernel == "dmma-fp64"
+    peak_tf = dmma_peak if tensor else dfma_peak
+    roof = {"bound": "tensor", "kernel": "rotate_dmma_kernel" if tensor else "zgemm_kernel (CUDA-core FP64)",
+            "achieved": rot_flops / (rot_ms_avg * 1e-3) / 1e12, "peak": peak_tf, "unit": "TFLOP/s",
+            "frac": rot_flops / (rot_ms_avg * 1e-3) / 1e12 / peak_tf, "traffic": None,
+            "peak_source": "FP64 %s peak measured live by wb200_probe_fp64_peak (MEASURED_PEAKS.json has "
+                           "no FP64 figure; tcgen05 has no f64 kind)" % ("DMMA.8x8x4" if tensor else "DFMA"),
+            "ms_per_launch": rot_ms_avg, "launches_timed": rot_n,
+            "share_of_step": rot_ms / ms_total if world == 1 else None,
+            "whole_step": {"fp64_frac": flops / world / (ms_step * 1e-3) / 1e12 / peak_tf,
+                           "hbm_frac": bytes_min / world / (ms_step * 1e-3) / 1e9 / hbm_peak,
+                           "hbm_peak_gbs": hbm_peak,
+                           "hbm_peak_source": "MEASURED_PEAKS.json" if pk else "fallback 6.65 TB/s",
+                           "algorithmic_flops_per_eval": flops, "algorithmic_bytes_per_eval": bytes_min},
+            "kernel_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()}}
+
+    line = {"metric": metric, "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": dict(config, n_bvectors=nn, rotation_kernel=ctx.rotation_kernel,
+                           parallelism=f"k-slab x{world}", omega_check=omega_val),
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": cs.summary(), "roofline": roof}
+
+    if cpu_sample is not None:
+        from oracle import cpu_baseline as cbm
+        ks, Ms, Uh = cpu_sample
+        cores = os.cpu_count() or 1
+        run = lambda: cbm.fg_sample(Ms, st["kpb_k"][k0:k1][ks], st["bvec"][k0:k1][ks], st["wb"], Uh,
+                                    ks + k0, nk, threads=cores)
+        run()
+        ts = []
+        t_all = time.perf_counter()
+        while len(ts) < 3 or (time.perf_counter() - t_all < 12.0 and len(ts) < 20):
+            t0 = time.perf_counter()
+            run()
+            ts.append(time.perf_counter() - t0)
+        t = float(np.mean(ts))
+        line["cpu_baseline"] = {
+            "value": (len(ks) / nk) / t, "unit": "evals/s", "cores": cores, "kind": "port",
+            "sample": f"{len(ks)} of {nk} k-points ({len(ks) * nn} pairs; both ZGEMMs per pair as "
+                      f"spread.jl:173-174 plus the omega!/omega_grad! loops), {len(ts)} x {t:.3f} s, "
+                      f"numpy+OpenBLAS with {cores} threads over k; extrapolated to the full k-grid"}
+    print(json.dumps(line))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -67,8 +67,8 @@ int wb200_create(wb200_ctx** out, int device, int nb, int nw, int nk_total, int 
 void wb200_destroy(wb200_ctx* ctx);
 const char* wb200_last_error(const wb200_ctx* ctx); /* ctx may be NULL: last create error */
 const char* wb200_version(void);
-/* use the given cudaStream_t (e.g. torch's current stream) for all subsequent work; NULL = the
- * ctx's own stream */
+/* use the given cudaStream_t (e.g. torch's current stream) for all subsequent work.  NULL is CUDA's
+ * legacy default stream.  A fresh ctx works on a private non-blocking stream. */
 int wb200_set_stream(wb200_ctx* ctx, void* cuda_stream);
 int wb200_synchronize(wb200_ctx* ctx);
 /* which rotation kernel the ctx selected: 0 = CUDA-core FP64, 1 = FP64 DMMA tensor path */
@@ -148,6 +148,17 @@ int wb200_min_abs_diag(wb200_ctx* ctx, double* out);
 int wb200_project_tangent_dev(wb200_ctx* ctx, const double* dX, double* dG, int nrow, int ncol,
                               int count);
 int wb200_retract_dev(wb200_ctx* ctx, double* dX, int nrow, int ncol, int count, int* iters);
+
+/* ---- measurement helpers (bench.py) -------------------------------------------------------------
+ * wb200_profile: when enabled, every launch of the four kernel classes below is bracketed by CUDA
+ * events on the ctx's stream; wb200_profile_read synchronises, returns the summed milliseconds and
+ * launch counts since the last read and resets them.
+ *   class 0: gauge packing   1: rotation (the dominant kernel)   2: spread reductions   3: gradient
+ * wb200_probe_fp64_peak: short live measurement of this device's FP64 peaks (TFLOP/s): tensor-pipe
+ * DMMA.8x8x4 and CUDA-core DFMA (MEASURED_PEAKS.json holds only HBM and bf16 figures).           */
+int wb200_profile(wb200_ctx* ctx, int enable);
+int wb200_profile_read(wb200_ctx* ctx, double ms[4], int counts[4]);
+int wb200_probe_fp64_peak(int device, double* dmma_tflops, double* dfma_tflops);
 
 #ifdef __cplusplus
 }

@@ -220,6 +220,38 @@ def fg_maxloc(M, kpb_k, bvec, wb, U, r0=None, lam=0.0):
 
 
 # --------------------------------------------------------------------------
+# chunk-wise pieces used by oracle/cpu_baseline.py (same arithmetic, gathered operands)
+# --------------------------------------------------------------------------
+def compute_MU_UtMU_gathered(M, Uk, Ukpb):
+    """MU = M U_{k+b}; N = U_k^H MU for already-gathered operands.  src/spread.jl:173-174.
+    M [c, nn, nb, nb], Uk [c, nb, nw], Ukpb [c, nn, nb, nw]."""
+    MU = M @ Ukpb
+    N = np.conj(np.swapaxes(Uk, -1, -2))[:, None] @ MU
+    return MU, N
+
+
+def partial_sums_from_N(N, bvec, wb):
+    """Un-normalised sums of omega!'s inner loops for a chunk of k.  src/spread.jl:284-322."""
+    a2 = np.abs(N) ** 2
+    ts = a2.sum(axis=(-1, -2))
+    dN = np.diagonal(N, axis1=-2, axis2=-1)
+    phi = imaglog(dN)
+    a2d = np.abs(dN) ** 2
+    nw = N.shape[-1]
+    return dict(wbphi=np.einsum("b,kbx,kbn->nx", wb, bvec, phi),
+                r2=np.einsum("b,kbn->n", wb, 1.0 - a2d + phi ** 2),
+                OI=np.einsum("b,kb->", wb, nw - ts), OOD=np.einsum("b,kb->", wb, ts - a2d.sum(-1)))
+
+
+def grad_from_MU_N_r(MU, N, bvec, wb, r, nk):
+    """omega_grad! inner loops for a chunk given the global centres r.  src/spread.jl:448-478."""
+    dN = np.diagonal(N, axis1=-2, axis2=-1)
+    q = imaglog(dN) + np.einsum("nx,kbx->kbn", r, bvec)
+    c = -1j * q / dN - np.conj(dN)
+    return 4.0 * np.einsum("b,kbmn,kbn->kmn", wb, MU, c) / nk
+
+
+# --------------------------------------------------------------------------
 # Stiefel manifold pieces (Optim.jl Stiefel_SVD used at max_localize.jl:62-63)
 # --------------------------------------------------------------------------
 def stiefel_retract(X):

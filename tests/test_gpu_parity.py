@@ -20,10 +20,10 @@ def rel(a, b):
 
 def check_spread(got, ref):
     out5, om, r, _ = got
-    scale = abs(ref["Omega"])
+    scale = max(abs(ref["Omega"]), 1.0)   # degenerate stencils give Omega ~ 1e-14: absolute floor
     for i, key in enumerate(["Omega", "OmegaI", "OmegaOD", "OmegaD", "OmegaTilde"]):
         assert abs(out5[i] - ref[key]) <= RTOL * scale, (key, out5[i], ref[key])
-    assert rel(om, ref["omega"]) < RTOL
+    assert np.abs(om - ref["omega"]).max() <= RTOL * max(np.abs(ref["omega"]).max(), 1.0)
     assert np.abs(r - ref["r"]).max() <= RTOL * max(1.0, np.abs(ref["r"]).max())
 
 
@@ -206,7 +206,8 @@ def test_disentangle_driver(w, silicon):
     ("fcc", (2, 2, 2), 64, 64),
     ("fcc", (2, 1, 2), 40, 33),
     ("tetragonal", (3, 3, 1), 256, 256),   # self-neighbours with G != 0 (config 5 shape)
-    ("cubic", (2, 1, 1), 200, 130),
+    ("cubic", (3, 1, 2), 200, 130),
+    ("cubic", (2, 1, 1), 33, 33),     # degenerate: every neighbour is a periodic image, Omega ~ 0
     ("fcc", (3, 3, 3), 18, 9),        # config 2 shape (CUDA-core kernel)
     ("bcc", (3, 3, 3), 32, 32),       # config 3 shape
     ("cubic", (1, 1, 1), 5, 3),       # single k-point, all neighbours are the point itself
@@ -222,8 +223,8 @@ def test_synthetic_both_kernels(w, lat, grid, nb, nw):
         kernels.add(ctx.rotation_kernel)
         G = np.empty((nk, nw, nb), dtype=np.complex128)
         f = ctx.fg(w.api.to_abi_U(U), G=G)
-        assert abs(f - f_ref) < RTOL * abs(f_ref), ctx.rotation_kernel
-        assert rel(w.api.from_abi_U(G), G_ref) < RTOL, ctx.rotation_kernel
+        assert abs(f - f_ref) < RTOL * max(abs(f_ref), 1.0), ctx.rotation_kernel
+        assert np.abs(w.api.from_abi_U(G) - G_ref).max() < RTOL * max(np.abs(G_ref).max(), 1.0), ctx.rotation_kernel
         check_spread(ctx.spread(w.api.to_abi_U(U)), sp_ref)
         N, MU = ctx.rotate_overlaps(w.api.to_abi_U(U), want_N=True, want_MU=True)
         MU_ref, N_ref = so.compute_MU_UtMU(M, st["kpb_k"], U)

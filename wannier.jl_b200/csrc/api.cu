@@ -23,6 +23,8 @@ extern "C" void wb200_destroy(wb200_ctx* ctx) {
                     ctx->d_min, ctx->d_scal, ctx->d_tmp1, ctx->d_tmp2, ctx->d_XY, ctx->d_GXY};
     for (void* p : ptrs)
         if (p) cudaFree(p);
+    for (auto& v : ctx->prof_events)
+        for (auto& pr : v) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -122,7 +124,7 @@ extern "C" int wb200_create(wb200_ctx** out, int device, int nb, int nw, int nk_
 
 extern "C" int wb200_set_stream(wb200_ctx* ctx, void* s) {
     if (!ctx) return WB200_ERR_ARG;
-    ctx->stream = s ? (cudaStream_t)s : ctx->own_stream;
+    ctx->stream = (cudaStream_t)s;   // NULL is CUDA's legacy default stream (what torch uses by default)
     return WB200_OK;
 }
 extern "C" int wb200_synchronize(wb200_ctx* ctx) {
@@ -430,4 +432,98 @@ extern "C" int wb200_disentangle(wb200_ctx* ctx, double* XY, double f_tol, doubl
     }
     cudaFree(dx);
     return s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// measurement helpers
+// ---------------------------------------------------------------------------------------------
+extern "C" int wb200_profile(wb200_ctx* ctx, int enable) {
+    if (!ctx) return WB200_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    WB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->profiling = enable ? 1 : 0;
+    for (int c = 0; c < 4; c++) ctx->prof_used[c] = 0;
+    return WB200_OK;
+}
+
+extern "C" int wb200_profile_read(wb200_ctx* ctx, double ms[4], int counts[4]) {
+    if (!ctx || !ms || !counts) return WB200_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    WB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int c = 0; c < 4; c++) {
+        double t = 0.0;
+        for (size_t i = 0; i < ctx->prof_used[c]; i++) {
+            float e = 0.f;
+            WB_CUDA(ctx, cudaEventElapsedTime(&e, ctx->prof_events[c][i].first, ctx->prof_events[c][i].second));
+            t += e;
+        }
+        ms[c] = t;
+        counts[c] = (int)ctx->prof_used[c];
+        ctx->prof_used[c] = 0;
+    }
+    return WB200_OK;
+}
+
+namespace {
+__global__ void __launch_bounds__(256) probe_dfma_kernel(double* out, int iters, double a, double b) {
+    double c[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) c[i] = threadIdx.x * 1e-9 + i;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < 16; i++) c[i] = fma(c[i], a, b);
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) s += c[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+__global__ void __launch_bounds__(256) probe_dmma_kernel(double* out, int iters, double a0, double b0) {
+    double c[16][2];
+#pragma unroll
+    for (int i = 0; i < 16; i++) { c[i][0] = threadIdx.x * 1e-9; c[i][1] = i; }
+    const double a = a0 + threadIdx.x * 1e-12, b = b0;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < 16; i++)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(c[i][0]), "+d"(c[i][1]) : "d"(a), "d"(b));
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) s += c[i][0] + c[i][1];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+}  // namespace
+
+extern "C" int wb200_probe_fp64_peak(int device, double* dmma_tflops, double* dfma_tflops) {
+    if (cudaSetDevice(device) != cudaSuccess) return WB200_ERR_NODEVICE;
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, device) != cudaSuccess) return WB200_ERR_CUDA;
+    const int sms = p.multiProcessorCount;
+    double* out = nullptr;
+    if (cudaMalloc(&out, sizeof(double) * sms * 2 * 256) != cudaSuccess) return WB200_ERR_CUDA;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    double best_mma = 0.0, best_fma = 0.0;
+    for (int rep = 0; rep < 6; rep++) {   // first reps are warm-up (clock ramp); keep the best
+        float ms = 0.f;
+        const int it_mma = 4000, it_fma = 20000;
+        cudaEventRecord(e0);
+        probe_dmma_kernel<<<sms * 2, 256>>>(out, it_mma, 1.0000001, 1e-3);
+        cudaEventRecord(e1); cudaEventSynchronize(e1); cudaEventElapsedTime(&ms, e0, e1);
+        double tf = 512.0 * 16 * it_mma * 8.0 * sms * 2 / (ms * 1e-3) / 1e12;
+        if (tf > best_mma) best_mma = tf;
+        cudaEventRecord(e0);
+        probe_dfma_kernel<<<sms * 2, 256>>>(out, it_fma, 1.0000001, 1e-9);
+        cudaEventRecord(e1); cudaEventSynchronize(e1); cudaEventElapsedTime(&ms, e0, e1);
+        tf = 2.0 * 16 * it_fma * 256.0 * sms * 2 / (ms * 1e-3) / 1e12;
+        if (tf > best_fma) best_fma = tf;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(out);
+    if (cudaGetLastError() != cudaSuccess) return WB200_ERR_CUDA;
+    if (dmma_tflops) *dmma_tflops = best_mma;
+    if (dfma_tflops) *dfma_tflops = best_fma;
+    return WB200_OK;
 }

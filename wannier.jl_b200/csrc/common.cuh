@@ -112,6 +112,11 @@ struct wb200_ctx {
     cplx* d_tmp2 = nullptr; size_t tmp2_elems = 0;
     cplx* d_XY = nullptr;  cplx* d_GXY = nullptr;   // [nk][nw*nw+nb*nw]
 
+    // optional per-class kernel timing (wb200_profile)
+    int profiling = 0;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events[4];
+    size_t prof_used[4] = {0, 0, 0, 0};
+
     DmmaPlan* dmma = nullptr;  // tensor-path state (nullptr: CUDA-core rotation)
     int rotation_kernel = 0;
 
@@ -144,6 +149,24 @@ struct wb200_ctx {
             return WB200_ERR_CUDA;                                           \
         }                                                                    \
     } while (0)
+
+// RAII bracket: records start/stop events around a kernel class when profiling is on
+struct ProfScope {
+    wb200_ctx* c; int cls; cudaEvent_t stop = nullptr;
+    ProfScope(wb200_ctx* ctx, int k) : c(ctx), cls(k) {
+        if (!c->profiling) return;
+        auto& v = c->prof_events[cls];
+        if (c->prof_used[cls] == v.size()) {
+            cudaEvent_t a, b;
+            cudaEventCreate(&a); cudaEventCreate(&b);
+            v.emplace_back(a, b);
+        }
+        auto& pr = v[c->prof_used[cls]++];
+        cudaEventRecord(pr.first, c->stream);
+        stop = pr.second;
+    }
+    ~ProfScope() { if (stop) cudaEventRecord(stop, c->stream); }
+};
 
 // ---- kernels_generic.cu ----
 int wb_zgemm_batched(wb200_ctx* ctx, const ZgemmArgs& a);

@@ -175,6 +175,7 @@ int wb_rotate_generic(wb200_ctx* ctx, const cplx* dU) {
     a.B = dU; a.strideB = (long long)nb * nw; a.ldb = nb; a.idxB = ctx->d_kpb;
     a.C = ctx->d_MU; a.strideC = (long long)nb * nw; a.ldc = nb;
     a.alpha = 1.0; a.beta = 0.0; a.batch = pairs; a.transA = 0; a.transB = 0;
+    ProfScope ps(ctx, 1);
     WB_TRY(wb_zgemm_batched(ctx, a));
     diag_kernel<<<pairs, 256, 0, ctx->stream>>>(nb, nw, dU, ctx->d_kself, ctx->d_MU, ctx->d_dN,
                                                  ctx->d_fro);
@@ -288,6 +289,7 @@ __global__ void __launch_bounds__(256) sum_over_k_kernel(int nk, int ns, const d
 }
 
 int wb_pair_reduce(wb200_ctx* ctx, double* dsums) {
+    ProfScope ps(ctx, 2);
     pair_reduce_kernel<<<ctx->nk, 128, 0, ctx->stream>>>(ctx->nw, ctx->nn, ctx->nk, ctx->d_dN,
                                                           ctx->d_fro, ctx->d_bvec, ctx->d_wb,
                                                           ctx->d_part, ctx->d_pmin);
@@ -401,6 +403,7 @@ __global__ void __launch_bounds__(256) grad_kernel(int nb, int nw, int nn, int n
 }
 
 int wb_grad(wb200_ctx* ctx, const double* dsums, cplx* dG) {
+    ProfScope ps(ctx, 3);
     dim3 g(ctx->nk, (ctx->nw + WB_GRAD_NT - 1) / WB_GRAD_NT);
     const size_t smem = sizeof(cplx) * (size_t)ctx->nn * WB_GRAD_NT;
     grad_kernel<<<g, 256, smem, ctx->stream>>>(ctx->nb, ctx->nw, ctx->nn, ctx->nk_total, ctx->d_MU,

@@ -375,12 +375,19 @@ void wb_dmma_plan_destroy(wb200_ctx* ctx) {
 int wb_rotate_dmma(wb200_ctx* ctx, const cplx* dU) {
     DmmaPlan* p = ctx->dmma;
     dim3 g((unsigned)ctx->nk_total, (unsigned)(p->nch * p->nct));
-    pack_gauge_kernel<<<g, 256, 0, ctx->stream>>>(ctx->nb, ctx->nw, p->WN, p->KC, p->nch, p->nct, dU,
-                                                  (cplx*)p->d_Up);
+    {
+        ProfScope ps(ctx, 0);
+        pack_gauge_kernel<<<g, 256, 0, ctx->stream>>>(ctx->nb, ctx->nw, p->WN, p->KC, p->nch, p->nct,
+                                                      dU, (cplx*)p->d_Up);
+    }
     WB_LAUNCH_CHECK(ctx);
-    if (p->WM == 2) WB_TRY((launch_rotate<WB_CFG_64>(ctx, dU)));
-    else if (p->WM == 4) WB_TRY((launch_rotate<WB_CFG_128>(ctx, dU)));
-    else WB_TRY((launch_rotate<WB_CFG_256>(ctx, dU)));
+    {
+        ProfScope ps(ctx, 1);
+        if (p->WM == 2) WB_TRY((launch_rotate<WB_CFG_64>(ctx, dU)));
+        else if (p->WM == 4) WB_TRY((launch_rotate<WB_CFG_128>(ctx, dU)));
+        else WB_TRY((launch_rotate<WB_CFG_256>(ctx, dU)));
+    }
+    ProfScope ps2(ctx, 2);
     combine_partials_kernel<<<ctx->nk * ctx->nn, 128, 0, ctx->stream>>>(
         ctx->nw, p->WM, p->nct * 8, p->d_dNp, p->d_frop, ctx->d_dN, ctx->d_fro);
     WB_LAUNCH_CHECK(ctx);

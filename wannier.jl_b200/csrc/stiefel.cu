@@ -60,19 +60,20 @@ int wb_project_tangent_dev(wb200_ctx* ctx, const cplx* dX, cplx* dG, int nrow, i
 // ---------------------------------------------------------------------------------------------
 // polar factor by Newton-Schulz:  X <- X (3 I - X^H X)/2
 // The kernel below turns P = X^H X into T = s (1.5 I - 0.5 s^2 P) in place (s = 1 unless the
-// matrix is far from unitary, then s = 1/||X||_F so that all singular values are < sqrt 3) and
+// matrix is far from unitary, then s = ||X^H X||_F^(-1/2) so that all singular values are <= 1) and
 // records max_k ||P_k - I||_F.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) ns_prepare_kernel(int n, cplx* __restrict__ P,
-                                                         double* __restrict__ err_max) {
+                                                         double* __restrict__ err_max,
+                                                         int allow_scale) {
     cplx* p = P + (long long)blockIdx.x * n * n;
-    double e2 = 0.0, tr = 0.0;
+    double e2 = 0.0, tr = 0.0;   // ||P - I||_F^2 and ||P||_F^2
     for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
         const int i = e % n, j = e / n;
         const cplx v = p[e];
         const double dx = v.x - (i == j ? 1.0 : 0.0);
         e2 += dx * dx + v.y * v.y;
-        if (i == j) tr += v.x;
+        tr += v.x * v.x + v.y * v.y;
     }
     __shared__ double s1[8], s2[8];
     __shared__ double scale;
@@ -84,8 +85,9 @@ __global__ void __launch_bounds__(256) ns_prepare_kernel(int n, cplx* __restrict
         double a = 0.0, b = 0.0;
         for (int w = 0; w < 8; w++) { a += s1[w]; b += s2[w]; }
         const double err = sqrt(a);
-        // err >= max |sigma^2 - 1|; Newton-Schulz needs sigma^2 < 3
-        scale = (err < 1.5) ? 1.0 : rsqrt(b);
+        // sigma_max^2 <= 1 + err: Newton-Schulz needs sigma^2 < 3.  Otherwise (first pass only;
+        // the map keeps sigma in (0, 1] afterwards) scale by ||P||_F^(-1/2) >= 1/sigma_max.
+        scale = (err < 1.9 || !allow_scale) ? 1.0 : rsqrt(sqrt(b));
         atomicMax((unsigned long long*)err_max, (unsigned long long)__double_as_longlong(err));
     }
     __syncthreads();
@@ -126,7 +128,7 @@ static int retract_strided(wb200_ctx* ctx, cplx* dX, int nrow, int ncol, int ld,
         a.alpha = 1.0; a.beta = 0.0; a.batch = count;
         WB_TRY(wb_zgemm_batched(ctx, a));
         WB_CUDA(ctx, cudaMemsetAsync(ctx->d_scal, 0, sizeof(double), ctx->stream));
-        ns_prepare_kernel<<<count, 256, 0, ctx->stream>>>(ncol, ctx->d_tmp1, ctx->d_scal);
+        ns_prepare_kernel<<<count, 256, 0, ctx->stream>>>(ncol, ctx->d_tmp1, ctx->d_scal, it == 0);
         WB_LAUNCH_CHECK(ctx);
         WB_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, ctx->d_scal, sizeof(double),
                                      cudaMemcpyDeviceToHost, ctx->stream));

@@ -22,6 +22,7 @@ SYMBOLS = [
     "wb200_fg_xy", "wb200_project_tangent", "wb200_retract", "wb200_max_localize",
     "wb200_disentangle", "wb200_nsums", "wb200_nres", "wb200_fg_phase1_dev", "wb200_fg_phase2_dev",
     "wb200_fg_dev", "wb200_min_abs_diag", "wb200_project_tangent_dev", "wb200_retract_dev",
+    "wb200_profile", "wb200_profile_read", "wb200_probe_fp64_peak",
 ]
 
 FLAG_DEFAULT = 0
@@ -84,6 +85,9 @@ def load():
     lib.wb200_min_abs_diag.argtypes = [vp, pd]
     lib.wb200_project_tangent_dev.argtypes = [vp, pd, pd, i32, i32, i32]
     lib.wb200_retract_dev.argtypes = [vp, pd, i32, i32, i32, pd]
+    lib.wb200_profile.argtypes = [vp, i32]
+    lib.wb200_profile_read.argtypes = [vp, pd, pd]
+    lib.wb200_probe_fp64_peak.argtypes = [i32, pd, pd]
     for name in SYMBOLS:
         f = getattr(lib, name)
         if name not in ("wb200_destroy", "wb200_last_error", "wb200_version", "wb200_launch_count"):
@@ -189,6 +193,16 @@ class Context:
         _check_array(fr, np.uint8, self.nk * self.nb, "frozen")
         self._ck(self._lib.wb200_set_frozen(self._h, _addr(fr)))
 
+    def profile(self, enable):
+        self._ck(self._lib.wb200_profile(self._h, int(enable)))
+
+    def profile_read(self):
+        """{class: (ms, launches)} since the last read; classes: pack, rotate, reduce, grad"""
+        ms = np.zeros(4)
+        cnt = np.zeros(4, dtype=np.int32)
+        self._ck(self._lib.wb200_profile_read(self._h, _addr(ms), _addr(cnt)))
+        return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(("pack", "rotate", "reduce", "grad"))}
+
     # -- host entry points ------------------------------------------------------------------
     def _u(self, U):
         _check_array(U, np.complex128, self.nk_total * self.nb * self.nw, "U")
@@ -283,3 +297,13 @@ class Context:
         it = C.c_int(0)
         self._ck(self._lib.wb200_retract_dev(self._h, dX, nrow, ncol, count, C.addressof(it)))
         return it.value
+
+
+def probe_fp64_peak(device=0):
+    """(dmma_tflops, dfma_tflops) measured live on `device`."""
+    lib = load()
+    a, b = C.c_double(0.0), C.c_double(0.0)
+    st = lib.wb200_probe_fp64_peak(device, C.addressof(a), C.addressof(b))
+    if st != 0:
+        raise WB200Error(st, "wb200_probe_fp64_peak failed")
+    return a.value, b.value

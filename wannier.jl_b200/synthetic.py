@@ -160,11 +160,14 @@ def make_model_arrays(lattice_name, grid, nb, nw, eps=0.05):
 
 
 # ---- torch / GPU generation for the large bench shapes (plumbing only; same recipe) -----------
-def _polar_torch(A, iters=40):
+def _polar_torch(A, iters=60):
     """polar factor by Newton-Schulz on the GPU (matmul only); A is close to an isometry."""
     import torch
-    X = A
     eye = torch.eye(A.shape[-1], dtype=A.dtype, device=A.device)
+    # scale so that every singular value is <= 1 (sigma_max^2 <= ||A^H A||_F): Newton-Schulz then
+    # converges monotonically for any full-rank A
+    P = A.mH @ A
+    X = A * torch.linalg.matrix_norm(P).pow(-0.5)[..., None, None].to(A.dtype)
     for _ in range(iters):
         P = X.mH @ X
         err = (P - eye).abs().amax().item()
