@@ -268,7 +268,8 @@ def test_k_slab_sharding_on_one_gpu(w):
     stream = torch.cuda.current_stream().cuda_stream
     ctxs, sums = [], []
     for (k0, k1) in ((0, 6), (6, 16)):
-        c = w.Context(nb, nw, nk, 12, st["kpb_k"][k0:k1], st["bvec"][k0:k1], st["wb"],
+        # anisotropic grid: 18 neighbours in 3 shells, two of them with ~0 weight
+        c = w.Context(nb, nw, nk, st["kpb_k"].shape[1], st["kpb_k"][k0:k1], st["bvec"][k0:k1], st["wb"],
                       w.api.to_abi_M(M[k0:k1]), k_begin=k0, nk=k1 - k0)
         c.set_stream(stream)
         s = torch.zeros(c.nsums, dtype=torch.float64, device="cuda")
@@ -304,4 +305,39 @@ def test_error_behaviour(w, valence):
     U[:, :, 0] = 0
     mn = ctx.spread(w.api.to_abi_U(U))[3]
     assert mn < 1e-10
+    ctx.close()
+
+
+def test_multi_wave_determinism_and_parity(w):
+    """864 CTAs of the DMMA kernel (about 6 waves on 148 SMs): results must be bitwise identical
+    from call to call and match the oracle.  Guards the shared-memory ring of the rotation kernel
+    (a missing cross-proxy fence once let a stage be overwritten under a slow warp, visible only
+    with more CTAs than SMs)."""
+    import torch
+    st = w.synthetic.make_stencil(w.synthetic.LATTICES["bcc"](), (6, 6, 6))
+    nk, nn = st["kpb_k"].shape
+    nb = nw = 128
+    dev = torch.device("cuda", 0)
+    M = w.synthetic.make_overlaps_torch(st, nb, dev)
+    dU = w.synthetic.make_gauge_torch(nk, nb, nw, dev)
+    ctx = w.Context(nb, nw, nk, nn, st["kpb_k"], st["bvec"], st["wb"], M.data_ptr())
+    assert ctx.rotation_kernel == "dmma-fp64"
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    res = torch.zeros(ctx.nres, dtype=torch.float64, device=dev)
+    G = torch.zeros((nk, nw, nb), dtype=torch.complex128, device=dev)
+    outs = []
+    for _ in range(6):
+        ctx.fg_dev(dU.data_ptr(), res.data_ptr(), G.data_ptr())
+        torch.cuda.synchronize()
+        outs.append((res.cpu().numpy().copy(), G.cpu().numpy().copy()))
+    for r, g in outs[1:]:
+        assert np.array_equal(r, outs[0][0]) and np.array_equal(g, outs[0][1])
+    Mh = M.transpose(2, 3).cpu().numpy()
+    Uh = dU.cpu().numpy().transpose(0, 2, 1)
+    f_ref, G_ref = so.fg_maxloc(Mh, st["kpb_k"], st["bvec"], st["wb"], Uh)
+    assert abs(outs[0][0][5] - f_ref) < RTOL * abs(f_ref)
+    assert rel(outs[0][1].transpose(0, 2, 1), G_ref) < RTOL
+    _, MU = ctx.rotate_overlaps(dU.cpu().numpy(), want_N=False, want_MU=True)
+    MU_ref, _ = so.compute_MU_UtMU(Mh, st["kpb_k"], Uh)
+    assert np.abs(MU.transpose(0, 1, 3, 2) - MU_ref).max() < 1e-13
     ctx.close()

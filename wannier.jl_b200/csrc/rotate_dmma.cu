@@ -6,18 +6,25 @@
 // instead of two — everything omega!/omega_grad! need from N is its diagonal (spread.jl:307-312,
 // 459-470), which is an O(nb nw) epilogue on the accumulator registers.
 //
+// Arithmetic: the kernel is bound by the FP64 tensor pipe (measured 36.9 TFLOP/s, profiles/), so
+// the complex product uses Gauss' three real multiplications instead of four:
+//     P1 = (Ar + Ai) Br,  P2 = Ar (Bi - Br),  P3 = Ai (Br + Bi);   Cr = P1 - P3,  Ci = P1 + P2
+// A = M is constant, so the plane Ar + Ai is built ONCE with the tiled copy of M; the B planes
+// (Br, Bi - Br, Br + Bi) are built by the per-evaluation gauge packing kernel.  24 instead of 32
+// DMMA per k-step; the extra additions are exact to one rounding each (error stays O(eps |A||B|)).
+//
 // Structure (one CTA per (k, column tile), looping over the nn neighbours of k):
 //   * M is re-laid-out ONCE at ctx creation into the exact shared-memory image of the A operand
-//     (DMMA fragment order), so a pipeline stage is ONE contiguous 1-D bulk async copy
-//     (cp.async.bulk -> UBLKCP, completion on an mbarrier); the gauge U is permuted into the B
-//     operand image by pack_gauge_kernel once per evaluation (16 B per element either way).
-//   * warp 8 is the producer (one elected lane issues the bulk copies through a KC-deep ring of
-//     full/empty mbarriers that never drains between the nn pairs of a k-point);
-//     warps 0-7 are consumers: warp tile 32 x 16 complex = 4 x 2 DMMA tiles x (re, im).
+//     (DMMA fragment order, three planes), so a pipeline stage is ONE contiguous 1-D bulk async
+//     copy (cp.async.bulk -> UBLKCP, completion on an mbarrier); likewise the packed gauge.
+//   * warp 8 is the producer: one elected lane drives a STAGES-deep ring of full/empty mbarriers
+//     that never drains between the nn pairs of a k-point, and is primed BEFORE the U_k tile is
+//     staged so the first chunks are in flight while the CTA sets up;
+//     warps 0-7 are consumers: warp tile 32 x 16 complex = 4 x 2 DMMA tiles x (P1, P2, P3).
 //   * U_k's column tile stays in shared memory (accumulator-fragment order) for the whole CTA, so
 //     the epilogue of every pair is registers + LDS only; per-warp partial diagonals go straight
-//     to global (summed in fixed order by pair_reduce_kernel) — no CTA-wide barrier anywhere in
-//     the main loop, and results are bitwise deterministic.
+//     to global (summed in fixed order by combine_partials_kernel) — no CTA-wide barrier anywhere
+//     in the main loop, and results are bitwise deterministic.
 #include "common.cuh"
 
 struct DmmaPlan {
@@ -25,8 +32,9 @@ struct DmmaPlan {
     int NB = 0, NC = 0;           // padded rows, columns per CTA
     int nct = 0;                  // column tiles = ceil(nw / NC)
     int nch = 0;                  // k-chunks = ceil(nb / KC)
-    double* d_Mt = nullptr;       // [pairs][nch][NB*KC*2]
-    double* d_Up = nullptr;       // [nk_total][nct][nch][KC*NC*2]
+    size_t a_stage = 0, b_stage = 0;  // doubles per stage
+    double* d_Mt = nullptr;       // [pairs][nch][a_stage]
+    double* d_Up = nullptr;       // [nk_total][nct][nch][b_stage]
     cplx* d_dNp = nullptr;        // [pairs][WM][nw]  per-warp-row partial diagonals
     double* d_frop = nullptr;     // [pairs][nct][8]
     size_t smem = 0;
@@ -72,41 +80,63 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                  : "+d"(c0), "+d"(c1)
                  : "d"(a), "d"(b));
 }
-__device__ __forceinline__ double neg_f64(double x) {  // sign flip on the ALU pipe, not the FP64 pipe
-    return __hiloint2double(__double2hiint(x) ^ (int)0x80000000, __double2loint(x));
-}
 
 // ---- one-off / per-evaluation layout kernels ------------------------------------------------
-// A-operand image of M: chunk = [wm][ks][mt(4)][lane][re,im],
-//   row = wm*32 + mt*8 + lane/4,  col = c*KC + ks*4 + lane%4   (zero padded)
+// A-operand image of M.  Chunk c = [wm][ks][j(6)][lane] double2; the 12 doubles of a lane are
+//   (re, im, re+im) of mt = 0..3 with row = wm*32 + mt*8 + lane/4, col = c*KC + ks*4 + lane%4.
 __global__ void tile_overlaps_kernel(int nb, int WM, int KC, int nch, const cplx* __restrict__ M,
-                                     cplx* __restrict__ Mt) {
+                                     double* __restrict__ Mt) {
     const long long pair = blockIdx.x;
     const int c = blockIdx.y;
     const int KS = KC / 4;
-    const int per = WM * KS * 4 * 32;
+    const int items = WM * KS * 32;
     const cplx* src = M + pair * (long long)nb * nb;
-    cplx* dst = Mt + (pair * nch + c) * (long long)per;
-    for (int o = threadIdx.x; o < per; o += blockDim.x) {
-        const int lane = o & 31, mt = (o >> 5) & 3, ks = (o >> 7) % KS, wm = (o >> 7) / KS;
-        const int row = wm * 32 + mt * 8 + (lane >> 2), col = c * KC + ks * 4 + (lane & 3);
-        dst[o] = (row < nb && col < nb) ? src[row + (long long)col * nb] : make_double2(0.0, 0.0);
+    double* dst = Mt + (pair * nch + c) * (long long)(items * 12);
+    for (int o = threadIdx.x; o < items; o += blockDim.x) {
+        const int lane = o & 31, ks = (o >> 5) % KS, wm = (o >> 5) / KS;
+        const int col = c * KC + ks * 4 + (lane & 3);
+        double q[12];
+#pragma unroll
+        for (int mt = 0; mt < 4; mt++) {
+            const int row = wm * 32 + mt * 8 + (lane >> 2);
+            const cplx v = (row < nb && col < nb) ? src[row + (long long)col * nb] : make_double2(0.0, 0.0);
+            q[3 * mt] = v.x;
+            q[3 * mt + 1] = v.y;
+            q[3 * mt + 2] = v.x + v.y;
+        }
+        double2* d2 = reinterpret_cast<double2*>(dst) + ((long long)(wm * KS + ks) * 6) * 32 + lane;
+#pragma unroll
+        for (int j = 0; j < 6; j++) d2[j * 32] = make_double2(q[2 * j], q[2 * j + 1]);
     }
 }
-// B-operand image of U: chunk = [wn][ks][nt(2)][lane][re,im],
-//   l = c*KC + ks*4 + lane%4,  n = ct*NC + wn*16 + nt*8 + lane/4   (zero padded)
-__global__ void pack_gauge_kernel(int nb, int nw, int WN, int KC, int nch, int nct,
-                                  const cplx* __restrict__ U, cplx* __restrict__ Up) {
+// B-operand image of U.  Chunk c = [wn][ks][j(3)][lane] double2; the 6 doubles of a lane are
+//   (Br, Bi-Br, Br+Bi) of nt = 0..1 with l = c*KC + ks*4 + lane%4, n = ct*NC + wn*16 + nt*8 + lane/4.
+__global__ void __launch_bounds__(256) pack_gauge_kernel(int nb, int nw, int WN, int KC, int nch, int nct,
+                                                         const cplx* __restrict__ U,
+                                                         double* __restrict__ Up) {
     const long long kg = blockIdx.x;
-    const int c = blockIdx.y % nch, ct = blockIdx.y / nch;
+    const int ct = blockIdx.y;
     const int KS = KC / 4;
-    const int per = WN * KS * 2 * 32;
+    const int items = WN * KS * 32;              // per chunk
     const cplx* src = U + kg * (long long)nb * nw;
-    cplx* dst = Up + ((kg * nct + ct) * nch + c) * (long long)per;
-    for (int o = threadIdx.x; o < per; o += blockDim.x) {
-        const int lane = o & 31, nt = (o >> 5) & 1, ks = (o >> 6) % KS, wn = (o >> 6) / KS;
-        const int l = c * KC + ks * 4 + (lane & 3), n = ct * (16 * WN) + wn * 16 + nt * 8 + (lane >> 2);
-        dst[o] = (l < nb && n < nw) ? src[l + (long long)n * nb] : make_double2(0.0, 0.0);
+    double* dst0 = Up + ((kg * nct + ct) * nch) * (long long)(items * 6);
+    for (int oo = threadIdx.x; oo < items * nch; oo += blockDim.x) {
+        const int c = oo / items, o = oo - c * items;
+        const int lane = o & 31, ks = (o >> 5) % KS, wn = (o >> 5) / KS;
+        const int l = c * KC + ks * 4 + (lane & 3);
+        double q[6];
+#pragma unroll
+        for (int nt = 0; nt < 2; nt++) {
+            const int n = ct * (16 * WN) + wn * 16 + nt * 8 + (lane >> 2);
+            const cplx v = (l < nb && n < nw) ? src[l + (long long)n * nb] : make_double2(0.0, 0.0);
+            q[3 * nt] = v.x;
+            q[3 * nt + 1] = v.y - v.x;
+            q[3 * nt + 2] = v.x + v.y;
+        }
+        double2* d2 = reinterpret_cast<double2*>(dst0 + (long long)c * (items * 6)) +
+                      ((long long)(wn * KS + ks) * 3) * 32 + lane;
+#pragma unroll
+        for (int j = 0; j < 3; j++) d2[j * 32] = make_double2(q[2 * j], q[2 * j + 1]);
     }
 }
 
@@ -119,8 +149,8 @@ rotate_dmma_kernel(int nb, int nw, int nn, int nch, int nct, int k_begin,
                    cplx* __restrict__ MU, cplx* __restrict__ dNp, double* __restrict__ frop) {
     constexpr int KS = KC / 4;
     constexpr int NC = 16 * WN;
-    constexpr int A_D2 = WM * KS * 4 * 32;   // double2 per A stage
-    constexpr int B_D2 = WN * KS * 2 * 32;   // double2 per B stage
+    constexpr int A_D2 = WM * KS * 6 * 32;   // double2 per A stage
+    constexpr int B_D2 = WN * KS * 3 * 32;   // double2 per B stage
     constexpr uint32_t A_BYTES = A_D2 * 16, B_BYTES = B_D2 * 16;
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -133,95 +163,106 @@ rotate_dmma_kernel(int nb, int nw, int nn, int nch, int nct, int k_begin,
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int kl = blockIdx.x / nct, ct = blockIdx.x % nct;
     const int n0 = ct * NC;
+    const int total = nn * nch;  // chunks streamed by this CTA
 
-    if (tid == 0) {
-        for (int s = 0; s < STAGES; s++) {
-            mbar_init(smem_u32(&bars[s]), 1);
-            mbar_init(smem_u32(&bars[STAGES + s]), 8);
+    // producer state (only meaningful in warp 8 lane 0)
+    auto produce = [&](int i) {
+        const int s = i % STAGES;
+        const uint32_t round = (uint32_t)(i / STAGES);
+        const int b = i / nch, c = i - b * nch;
+        const long long pair = (long long)kl * nn + b;
+        const long long kp = kpb[pair];
+        mbar_wait(smem_u32(&bars[STAGES + s]), (round & 1u) ^ 1u);
+        const uint32_t full = smem_u32(&bars[s]);
+        mbar_arrive_expect_tx(full, A_BYTES + B_BYTES);
+        bulk_g2s(smem_u32(sA + s * A_D2), Mt + (pair * nch + c) * (long long)(A_D2 * 2), A_BYTES, full);
+        bulk_g2s(smem_u32(sB + s * B_D2), Up + ((kp * nct + ct) * nch + c) * (long long)(B_D2 * 2),
+                 B_BYTES, full);
+    };
+    const int npre = total < STAGES ? total : STAGES;
+
+    if (warp == 8) {
+        if (lane == 0) {
+            for (int s = 0; s < STAGES; s++) {
+                mbar_init(smem_u32(&bars[s]), 1);
+                mbar_init(smem_u32(&bars[STAGES + s]), 8);
+            }
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            for (int i = 0; i < npre; i++) produce(i);   // prime the ring while the CTA sets up
         }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    // U_k column tile in accumulator-fragment order: sUk[(w*16 + idx)*32 + lane],
-    //   idx = (mt*2 + nt)*2 + j -> m = wm*32 + mt*8 + lane/4, n = n0 + wn*16 + nt*8 + 2*(lane%4) + j
-    {
+    } else {
+        // U_k column tile in accumulator-fragment order: sUk[(w*16 + idx)*32 + lane],
+        //   idx = (mt*2 + nt)*2 + j -> m = wm*32 + mt*8 + lane/4, n = n0 + wn*16 + nt*8 + 2*(lane%4) + j
         const cplx* Uk = U + (long long)(k_begin + kl) * nb * nw;
-        for (int o = tid; o < 8 * 16 * 32; o += 288) {
+        cplx v[16];
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            const int o = tid + i * 256;
             const int l = o & 31, idx = (o >> 5) & 15, w = o >> 9;
             const int wm = w / WN, wn = w % WN;
             const int j = idx & 1, nt = (idx >> 1) & 1, mt = idx >> 2;
             const int m = wm * 32 + mt * 8 + (l >> 2), n = n0 + wn * 16 + nt * 8 + 2 * (l & 3) + j;
-            sUk[o] = (m < nb && n < nw) ? Uk[m + (long long)n * nb] : make_double2(0.0, 0.0);
+            v[i] = (m < nb && n < nw) ? Uk[m + (long long)n * nb] : make_double2(0.0, 0.0);
         }
+#pragma unroll
+        for (int i = 0; i < 16; i++) sUk[tid + i * 256] = v[i];
     }
     __syncthreads();
 
-    const int total = nn * nch;  // chunks streamed by this CTA
     if (warp == 8) {
         // ===== producer =====
-        if (lane == 0) {
-            int s = 0;
-            uint32_t ph = 0;
-            for (int b = 0; b < nn; b++) {
-                const long long pair = (long long)kl * nn + b;
-                const long long kp = kpb[pair];
-                const double* srcA = Mt + pair * nch * (long long)(A_D2 * 2);
-                const double* srcB = Up + (kp * nct + ct) * nch * (long long)(B_D2 * 2);
-                for (int c = 0; c < nch; c++) {
-                    mbar_wait(smem_u32(&bars[STAGES + s]), ph ^ 1);
-                    const uint32_t full = smem_u32(&bars[s]);
-                    mbar_arrive_expect_tx(full, A_BYTES + B_BYTES);
-                    bulk_g2s(smem_u32(sA + s * A_D2), srcA + (long long)c * (A_D2 * 2), A_BYTES, full);
-                    bulk_g2s(smem_u32(sB + s * B_D2), srcB + (long long)c * (B_D2 * 2), B_BYTES, full);
-                    if (++s == STAGES) { s = 0; ph ^= 1; }
-                }
-            }
-        }
+        if (lane == 0)
+            for (int i = npre; i < total; i++) produce(i);
         return;
     }
-    (void)total;
 
     // ===== consumers =====
     const int wm = warp / WN, wn = warp % WN;
     const int g = lane >> 2, t = lane & 3;
-    double cre[4][2][2], cim[4][2][2];
+    double p1[4][2][2], p2[4][2][2], p3[4][2][2];
 #pragma unroll
     for (int i = 0; i < 4; i++)
 #pragma unroll
-        for (int j = 0; j < 2; j++) cre[i][j][0] = cre[i][j][1] = cim[i][j][0] = cim[i][j][1] = 0.0;
+        for (int j = 0; j < 2; j++)
+#pragma unroll
+            for (int e = 0; e < 2; e++) p1[i][j][e] = p2[i][j][e] = p3[i][j][e] = 0.0;
 
     int s = 0;
     uint32_t ph = 0;
     for (int b = 0; b < nn; b++) {
         for (int c = 0; c < nch; c++) {
             mbar_wait(smem_u32(&bars[s]), ph);
-            const cplx* Ap = sA + s * A_D2 + (wm * KS * 4) * 32 + lane;
-            const cplx* Bp = sB + s * B_D2 + (wn * KS * 2) * 32 + lane;
+            const cplx* Ap = sA + s * A_D2 + (wm * KS * 6) * 32 + lane;
+            const cplx* Bp = sB + s * B_D2 + (wn * KS * 3) * 32 + lane;
 #pragma unroll
             for (int ks = 0; ks < KS; ks++) {
-                cplx a[4], bb[2];
-                double nbi[2];
+                double qa[12], qb[6];
 #pragma unroll
-                for (int mt = 0; mt < 4; mt++) a[mt] = Ap[(ks * 4 + mt) * 32];
-#pragma unroll
-                for (int nt = 0; nt < 2; nt++) {
-                    bb[nt] = Bp[(ks * 2 + nt) * 32];
-                    nbi[nt] = neg_f64(bb[nt].y);
+                for (int j = 0; j < 6; j++) {
+                    const cplx x = Ap[(ks * 6 + j) * 32];
+                    qa[2 * j] = x.x;
+                    qa[2 * j + 1] = x.y;
                 }
 #pragma unroll
+                for (int j = 0; j < 3; j++) {
+                    const cplx x = Bp[(ks * 3 + j) * 32];
+                    qb[2 * j] = x.x;
+                    qb[2 * j + 1] = x.y;
+                }
+                // qa[3 mt + {0,1,2}] = Ar, Ai, Ar+Ai ; qb[3 nt + {0,1,2}] = Br, Bi-Br, Br+Bi
+#pragma unroll
                 for (int mt = 0; mt < 4; mt++)
 #pragma unroll
                     for (int nt = 0; nt < 2; nt++) {
-                        dmma884(cre[mt][nt][0], cre[mt][nt][1], a[mt].x, bb[nt].x);
-                        dmma884(cim[mt][nt][0], cim[mt][nt][1], a[mt].x, bb[nt].y);
-                    }
-#pragma unroll
-                for (int mt = 0; mt < 4; mt++)
-#pragma unroll
-                    for (int nt = 0; nt < 2; nt++) {
-                        dmma884(cre[mt][nt][0], cre[mt][nt][1], a[mt].y, nbi[nt]);
-                        dmma884(cim[mt][nt][0], cim[mt][nt][1], a[mt].y, bb[nt].x);
+                        dmma884(p1[mt][nt][0], p1[mt][nt][1], qa[3 * mt + 2], qb[3 * nt]);
+                        dmma884(p2[mt][nt][0], p2[mt][nt][1], qa[3 * mt], qb[3 * nt + 1]);
+                        dmma884(p3[mt][nt][0], p3[mt][nt][1], qa[3 * mt + 1], qb[3 * nt + 2]);
                     }
             }
+            // WAR across proxies: our generic-proxy LDS reads of this stage must be ordered before
+            // the producer's next async-proxy bulk write into it (without this fence a stage was
+            // observed being overwritten under a slow warp; see tests: multi-wave determinism)
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&bars[STAGES + s]));
             if (++s == STAGES) { s = 0; ph ^= 1; }
@@ -242,14 +283,15 @@ rotate_dmma_kernel(int nb, int nw, int nn, int nch, int nct, int k_begin,
             for (int nt = 0; nt < 2; nt++)
 #pragma unroll
                 for (int j = 0; j < 2; j++) {
-                    const cplx x = make_double2(cre[mt][nt][j], cim[mt][nt][j]);
+                    const cplx x = make_double2(p1[mt][nt][j] - p3[mt][nt][j], p1[mt][nt][j] + p2[mt][nt][j]);
                     const int m = wm * 32 + mt * 8 + g, n = n0 + wn * 16 + nt * 8 + 2 * t + j;
                     if (m < nb && n < nw) mu[m + (long long)n * nb] = x;
                     cfma_conj(d[nt][j], uk[((mt * 2 + nt) * 2 + j) * 32], x);
                     f = fma(x.x, x.x, f);
                     f = fma(x.y, x.y, f);
-                    cre[mt][nt][j] = 0.0;
-                    cim[mt][nt][j] = 0.0;
+                    p1[mt][nt][j] = 0.0;
+                    p2[mt][nt][j] = 0.0;
+                    p3[mt][nt][j] = 0.0;
                 }
         // reduce over the 8 row groups g (lanes with equal t)
 #pragma unroll
@@ -302,7 +344,7 @@ __global__ void __launch_bounds__(128) combine_partials_kernel(int nw, int WM, i
 template <int WM, int WN, int KC, int STAGES>
 size_t smem_bytes() {
     constexpr int KS = KC / 4;
-    return sizeof(cplx) * (8 * 16 * 32 + (size_t)STAGES * (WM * KS * 4 * 32 + WN * KS * 2 * 32)) +
+    return sizeof(cplx) * (8 * 16 * 32 + (size_t)STAGES * (WM * KS * 6 * 32 + WN * KS * 3 * 32)) +
            sizeof(unsigned long long) * 2 * STAGES;
 }
 
@@ -324,36 +366,35 @@ int launch_rotate(wb200_ctx* ctx, const cplx* dU) {
 
 }  // namespace
 
-// KC / STAGES per configuration (shared memory: 64 KB U_k tile + STAGES x (A + B) stage)
-#define WB_CFG_128 4, 2, 16, 4   /* 64 < nb <= 128: CTA 128 x 32, stage 32+8 KB  -> 224 KB */
-#define WB_CFG_256 8, 1, 8, 4    /* 128 < nb <= 256: CTA 256 x 16, stage 32+2 KB -> 200 KB */
-#define WB_CFG_64 2, 4, 16, 4    /* 32 < nb <= 64:  CTA 64 x 64, stage 16+16 KB  -> 192 KB */
+// WM, WN, KC, STAGES per configuration.  Shared memory: 64 KB U_k tile + STAGES x (A + B) stage,
+// A stage = WM*KC*6 KB/16... in bytes: WM*(KC/4)*6*512, B stage = WN*(KC/4)*3*512.
+#define WB_CFG_128 4, 2, 8, 5    /* 64 < nb <= 128: CTA 128 x 32, stage 24+6 KB    -> 214 KB */
+#define WB_CFG_256 8, 1, 8, 3    /* 128 < nb <= 256: CTA 256 x 16, stage 48+3 KB   -> 217 KB */
+#define WB_CFG_64 2, 4, 16, 3    /* 32 < nb <= 64:  CTA 64 x 64, stage 24+24 KB    -> 208 KB */
 
 int wb_dmma_plan_create(wb200_ctx* ctx, const double* /*hM*/) {
     const int nb = ctx->nb, nw = ctx->nw;
     if (nb <= 32 || nb > 256) return WB200_OK;  // CUDA-core path
     DmmaPlan* p = new DmmaPlan();
     if (nb <= 64) { p->WM = 2; p->WN = 4; p->KC = 16; p->smem = smem_bytes<WB_CFG_64>(); }
-    else if (nb <= 128) { p->WM = 4; p->WN = 2; p->KC = 16; p->smem = smem_bytes<WB_CFG_128>(); }
+    else if (nb <= 128) { p->WM = 4; p->WN = 2; p->KC = 8; p->smem = smem_bytes<WB_CFG_128>(); }
     else { p->WM = 8; p->WN = 1; p->KC = 8; p->smem = smem_bytes<WB_CFG_256>(); }
     p->NB = 32 * p->WM;
     p->NC = 16 * p->WN;
     p->nct = (nw + p->NC - 1) / p->NC;
     p->nch = (nb + p->KC - 1) / p->KC;
+    p->a_stage = (size_t)p->WM * (p->KC / 4) * 32 * 12;
+    p->b_stage = (size_t)p->WN * (p->KC / 4) * 32 * 6;
     ctx->dmma = p;
     const size_t pairs = (size_t)ctx->nk * ctx->nn;
-    const size_t a_stage = (size_t)p->NB * p->KC * 2, b_stage = (size_t)p->KC * p->NC * 2;
-    WB_CUDA(ctx, cudaMalloc(&p->d_Mt, sizeof(double) * pairs * p->nch * a_stage));
-    WB_CUDA(ctx, cudaMalloc(&p->d_Up, sizeof(double) * (size_t)ctx->nk_total * p->nct * p->nch * b_stage));
+    WB_CUDA(ctx, cudaMalloc(&p->d_Mt, sizeof(double) * pairs * p->nch * p->a_stage));
+    WB_CUDA(ctx, cudaMalloc(&p->d_Up, sizeof(double) * (size_t)ctx->nk_total * p->nct * p->nch * p->b_stage));
     WB_CUDA(ctx, cudaMalloc(&p->d_dNp, sizeof(cplx) * pairs * p->WM * nw));
     WB_CUDA(ctx, cudaMalloc(&p->d_frop, sizeof(double) * pairs * p->nct * 8));
     // re-lay-out M (already uploaded to d_M) into the A-operand image; d_M is then released:
     // the tensor path never reads the plain layout again.
-    const int ZMAX = 65535;
-    (void)ZMAX;
     dim3 grid((unsigned)pairs, (unsigned)p->nch);
-    tile_overlaps_kernel<<<grid, 256, 0, ctx->stream>>>(nb, p->WM, p->KC, p->nch, ctx->d_M,
-                                                        (cplx*)p->d_Mt);
+    tile_overlaps_kernel<<<grid, 128, 0, ctx->stream>>>(nb, p->WM, p->KC, p->nch, ctx->d_M, p->d_Mt);
     WB_LAUNCH_CHECK(ctx);
     WB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     cudaFree(ctx->d_M);
@@ -374,11 +415,11 @@ void wb_dmma_plan_destroy(wb200_ctx* ctx) {
 
 int wb_rotate_dmma(wb200_ctx* ctx, const cplx* dU) {
     DmmaPlan* p = ctx->dmma;
-    dim3 g((unsigned)ctx->nk_total, (unsigned)(p->nch * p->nct));
+    dim3 g((unsigned)ctx->nk_total, (unsigned)p->nct);
     {
         ProfScope ps(ctx, 0);
         pack_gauge_kernel<<<g, 256, 0, ctx->stream>>>(ctx->nb, ctx->nw, p->WN, p->KC, p->nch, p->nct,
-                                                      dU, (cplx*)p->d_Up);
+                                                     dU, p->d_Up);
     }
     WB_LAUNCH_CHECK(ctx);
     {

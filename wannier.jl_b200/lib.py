@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libwannier_b200.so")
+LIB_PATH = os.environ.get("WB200_LIB") or os.path.join(_HERE, "lib", "libwannier_b200.so")
 
 # every symbol include/wannier_b200.h declares (tests check that the .so exports all of them)
 SYMBOLS = [
