@@ -17,7 +17,8 @@
 //   * M is re-laid-out ONCE at ctx creation into the exact shared-memory image of the A operand
 //     (DMMA fragment order, three planes), so a pipeline stage is ONE contiguous 1-D bulk async
 //     copy (cp.async.bulk -> UBLKCP, completion on an mbarrier); likewise the packed gauge.
-//   * warp 8 is the producer: one elected lane drives a STAGES-deep ring of full/empty mbarriers
+//   * warps 8-11 are the producer warpgroup (setmaxnreg hands its registers to the consumers):
+//     one elected lane drives a STAGES-deep ring of full/empty mbarriers
 //     that never drains between the nn pairs of a k-point, and is primed BEFORE the U_k tile is
 //     staged so the first chunks are in flight while the CTA sets up;
 //     warps 0-7 are consumers: warp tile 32 x 16 complex = 4 x 2 DMMA tiles x (P1, P2, P3).
@@ -41,6 +42,10 @@ struct DmmaPlan {
 };
 
 namespace {
+
+#ifdef WB_TIMING
+__device__ long long* wb_dbg = nullptr;
+#endif
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return (uint32_t)__cvta_generic_to_shared(p);
@@ -142,7 +147,7 @@ __global__ void __launch_bounds__(256) pack_gauge_kernel(int nb, int nw, int WN,
 
 // ---- the rotation kernel ---------------------------------------------------------------------
 template <int WM, int WN, int KC, int STAGES>
-__global__ void __launch_bounds__(288, 1)
+__global__ void __launch_bounds__(384, 1)
 rotate_dmma_kernel(int nb, int nw, int nn, int nch, int nct, int k_begin,
                    const int32_t* __restrict__ kpb, const double* __restrict__ Mt,
                    const double* __restrict__ Up, const cplx* __restrict__ U,
@@ -160,7 +165,11 @@ rotate_dmma_kernel(int nb, int nw, int nn, int nch, int nct, int k_begin,
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(sB + STAGES * B_D2);
     // bars[0..STAGES) full, bars[STAGES..2 STAGES) empty
 
+#ifdef WB_TIMING
+    const long long t_cta0 = clock64();
+#endif
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t bar_base = smem_u32(bars), sA_base = smem_u32(sA), sB_base = smem_u32(sB);
     const int kl = blockIdx.x / nct, ct = blockIdx.x % nct;
     const int n0 = ct * NC;
     const int total = nn * nch;  // chunks streamed by this CTA
@@ -172,53 +181,59 @@ rotate_dmma_kernel(int nb, int nw, int nn, int nch, int nct, int k_begin,
         const int b = i / nch, c = i - b * nch;
         const long long pair = (long long)kl * nn + b;
         const long long kp = kpb[pair];
-        mbar_wait(smem_u32(&bars[STAGES + s]), (round & 1u) ^ 1u);
-        const uint32_t full = smem_u32(&bars[s]);
+        mbar_wait(bar_base + 8u * (STAGES + s), (round & 1u) ^ 1u);
+        const uint32_t full = bar_base + 8u * s;
         mbar_arrive_expect_tx(full, A_BYTES + B_BYTES);
-        bulk_g2s(smem_u32(sA + s * A_D2), Mt + (pair * nch + c) * (long long)(A_D2 * 2), A_BYTES, full);
-        bulk_g2s(smem_u32(sB + s * B_D2), Up + ((kp * nct + ct) * nch + c) * (long long)(B_D2 * 2),
+        bulk_g2s(sA_base + s * A_BYTES, Mt + (pair * nch + c) * (long long)(A_D2 * 2), A_BYTES, full);
+        bulk_g2s(sB_base + s * B_BYTES, Up + ((kp * nct + ct) * nch + c) * (long long)(B_D2 * 2),
                  B_BYTES, full);
     };
     const int npre = total < STAGES ? total : STAGES;
 
-    if (warp == 8) {
-        if (lane == 0) {
+    // consumer warp coordinates (unused by the producer warpgroup)
+    const int wm = (warp & 7) / WN, wn = (warp & 7) % WN;
+    const int g = lane >> 2, t = lane & 3;
+    // element e = (mt*2 + nt)*2 + j of this thread's accumulator fragment:
+    //   m = wm*32 + mt*8 + g,  n = n0 + wn*16 + nt*8 + 2t + j
+    cplx v[16];  // U_k values of this thread's 16 elements (prefetched, parked in its own smem slots)
+
+    if (warp >= 8) {
+        if (tid == 256) {
             for (int s = 0; s < STAGES; s++) {
-                mbar_init(smem_u32(&bars[s]), 1);
-                mbar_init(smem_u32(&bars[STAGES + s]), 8);
+                mbar_init(bar_base + 8u * s, 1);
+                mbar_init(bar_base + 8u * (STAGES + s), 8);
             }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
             for (int i = 0; i < npre; i++) produce(i);   // prime the ring while the CTA sets up
         }
     } else {
-        // U_k column tile in accumulator-fragment order: sUk[(w*16 + idx)*32 + lane],
-        //   idx = (mt*2 + nt)*2 + j -> m = wm*32 + mt*8 + lane/4, n = n0 + wn*16 + nt*8 + 2*(lane%4) + j
         const cplx* Uk = U + (long long)(k_begin + kl) * nb * nw;
-        cplx v[16];
 #pragma unroll
-        for (int i = 0; i < 16; i++) {
-            const int o = tid + i * 256;
-            const int l = o & 31, idx = (o >> 5) & 15, w = o >> 9;
-            const int wm = w / WN, wn = w % WN;
-            const int j = idx & 1, nt = (idx >> 1) & 1, mt = idx >> 2;
-            const int m = wm * 32 + mt * 8 + (l >> 2), n = n0 + wn * 16 + nt * 8 + 2 * (l & 3) + j;
-            v[i] = (m < nb && n < nw) ? Uk[m + (long long)n * nb] : make_double2(0.0, 0.0);
+        for (int e = 0; e < 16; e++) {
+            const int m = wm * 32 + (e >> 2) * 8 + g, n = n0 + wn * 16 + ((e >> 1) & 1) * 8 + 2 * t + (e & 1);
+            v[e] = (m < nb && n < nw) ? Uk[m + (long long)n * nb] : make_double2(0.0, 0.0);
         }
-#pragma unroll
-        for (int i = 0; i < 16; i++) sUk[tid + i * 256] = v[i];
     }
-    __syncthreads();
+    __syncthreads();   // barrier inits visible to the consumers
 
-    if (warp == 8) {
-        // ===== producer =====
-        if (lane == 0)
+    if (warp >= 8) {
+        // ===== producer warpgroup: hand its registers to the consumers, one lane drives the ring =====
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        if (tid == 256)
             for (int i = npre; i < total; i++) produce(i);
         return;
     }
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+#ifdef WB_TIMING
+    const long long t_setup = clock64() - t_cta0;
+#endif
 
     // ===== consumers =====
-    const int wm = warp / WN, wn = warp % WN;
-    const int g = lane >> 2, t = lane & 3;
+    // each thread parks its U_k values in smem slots only it ever touches (no barrier needed)
+    cplx* uk = sUk + (warp * 16) * 32 + lane;
+#pragma unroll
+    for (int e = 0; e < 16; e++) uk[e * 32] = v[e];
+
     double p1[4][2][2], p2[4][2][2], p3[4][2][2];
 #pragma unroll
     for (int i = 0; i < 4; i++)
@@ -227,52 +242,20 @@ rotate_dmma_kernel(int nb, int nw, int nn, int nch, int nct, int k_begin,
 #pragma unroll
             for (int e = 0; e < 2; e++) p1[i][j][e] = p2[i][j][e] = p3[i][j][e] = 0.0;
 
-    int s = 0;
-    uint32_t ph = 0;
-    for (int b = 0; b < nn; b++) {
-        for (int c = 0; c < nch; c++) {
-            mbar_wait(smem_u32(&bars[s]), ph);
-            const cplx* Ap = sA + s * A_D2 + (wm * KS * 6) * 32 + lane;
-            const cplx* Bp = sB + s * B_D2 + (wn * KS * 3) * 32 + lane;
-#pragma unroll
-            for (int ks = 0; ks < KS; ks++) {
-                double qa[12], qb[6];
-#pragma unroll
-                for (int j = 0; j < 6; j++) {
-                    const cplx x = Ap[(ks * 6 + j) * 32];
-                    qa[2 * j] = x.x;
-                    qa[2 * j + 1] = x.y;
-                }
-#pragma unroll
-                for (int j = 0; j < 3; j++) {
-                    const cplx x = Bp[(ks * 3 + j) * 32];
-                    qb[2 * j] = x.x;
-                    qb[2 * j + 1] = x.y;
-                }
-                // qa[3 mt + {0,1,2}] = Ar, Ai, Ar+Ai ; qb[3 nt + {0,1,2}] = Br, Bi-Br, Br+Bi
-#pragma unroll
-                for (int mt = 0; mt < 4; mt++)
-#pragma unroll
-                    for (int nt = 0; nt < 2; nt++) {
-                        dmma884(p1[mt][nt][0], p1[mt][nt][1], qa[3 * mt + 2], qb[3 * nt]);
-                        dmma884(p2[mt][nt][0], p2[mt][nt][1], qa[3 * mt], qb[3 * nt + 1]);
-                        dmma884(p3[mt][nt][0], p3[mt][nt][1], qa[3 * mt + 1], qb[3 * nt + 2]);
-                    }
-            }
-            // WAR across proxies: our generic-proxy LDS reads of this stage must be ordered before
-            // the producer's next async-proxy bulk write into it (without this fence a stage was
-            // observed being overwritten under a slow warp; see tests: multi-wave determinism)
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&bars[STAGES + s]));
-            if (++s == STAGES) { s = 0; ph ^= 1; }
-        }
-        // ----- epilogue of pair (k, b): store MU, partial diag N, partial ||MU||_F^2 -----
-        const long long pair = (long long)kl * nn + b;
-        cplx* mu = MU + pair * (long long)nb * nw;
-        const cplx* uk = sUk + (warp * 16) * 32 + lane;
-        cplx d[2][2];
-        double f = 0.0;
+    // Deferred epilogue.  At the end of pair b the accumulators are combined into x[16] (the MU
+    // values of this thread) and cleared; the expensive part of the epilogue — 16 STG.128 of MU,
+    // the diagonal and norm accumulations — is then issued in 8 slices of two elements BETWEEN the
+    // DMMA groups of the first 8 k-steps of pair b+1, so the store burst (64 KB per CTA) and the
+    // FP64 CUDA-core work hide under tensor-pipe time instead of stalling all eight warps at once.
+    cplx x[16];
+    cplx d[2][2];
+    double f = 0.0;
+    long long epi_pair = 0;
+    constexpr int EPI_CHUNKS = 8 / KS;   // chunks over which the 8 slices are spread
+
+    auto epi_begin = [&](long long pair) {
+        epi_pair = pair;
+        f = 0.0;
 #pragma unroll
         for (int nt = 0; nt < 2; nt++)
 #pragma unroll
@@ -283,16 +266,28 @@ rotate_dmma_kernel(int nb, int nw, int nn, int nch, int nct, int k_begin,
             for (int nt = 0; nt < 2; nt++)
 #pragma unroll
                 for (int j = 0; j < 2; j++) {
-                    const cplx x = make_double2(p1[mt][nt][j] - p3[mt][nt][j], p1[mt][nt][j] + p2[mt][nt][j]);
-                    const int m = wm * 32 + mt * 8 + g, n = n0 + wn * 16 + nt * 8 + 2 * t + j;
-                    if (m < nb && n < nw) mu[m + (long long)n * nb] = x;
-                    cfma_conj(d[nt][j], uk[((mt * 2 + nt) * 2 + j) * 32], x);
-                    f = fma(x.x, x.x, f);
-                    f = fma(x.y, x.y, f);
+                    x[(mt * 2 + nt) * 2 + j] = make_double2(p1[mt][nt][j] - p3[mt][nt][j],
+                                                            p1[mt][nt][j] + p2[mt][nt][j]);
                     p1[mt][nt][j] = 0.0;
                     p2[mt][nt][j] = 0.0;
                     p3[mt][nt][j] = 0.0;
                 }
+    };
+    auto epi_slice = [&](int sl) {   // elements 2*sl, 2*sl+1 (sl static after unrolling)
+        cplx* mu = MU + epi_pair * (long long)nb * nw;
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+            const int e = 2 * sl + q;
+            const int mt = e >> 2, nt = (e >> 1) & 1, j = e & 1;
+            const int m = wm * 32 + mt * 8 + g, n = n0 + wn * 16 + nt * 8 + 2 * t + j;
+            const cplx xv = x[e];
+            if (m < nb && n < nw) mu[m + (long long)n * nb] = xv;
+            cfma_conj(d[nt][j], uk[e * 32], xv);
+            f = fma(xv.x, xv.x, f);
+            f = fma(xv.y, xv.y, f);
+        }
+    };
+    auto epi_end = [&]() {
         // reduce over the 8 row groups g (lanes with equal t)
 #pragma unroll
         for (int nt = 0; nt < 2; nt++)
@@ -311,11 +306,107 @@ rotate_dmma_kernel(int nb, int nw, int nn, int nch, int nct, int k_begin,
 #pragma unroll
                 for (int j = 0; j < 2; j++) {
                     const int n = n0 + wn * 16 + nt * 8 + 2 * t + j;
-                    if (n < nw) dNp[(pair * WM + wm) * nw + n] = d[nt][j];
+                    if (n < nw) dNp[(epi_pair * WM + wm) * nw + n] = d[nt][j];
                 }
         }
-        if (lane == 0) frop[(pair * nct + ct) * 8 + warp] = f;
+        if (lane == 0) frop[(epi_pair * nct + ct) * 8 + warp] = f;
+    };
+
+#ifdef WB_TIMING
+    long long t_wait = 0, t_epi = 0, t_first = 0;
+    const long long t_start = clock64();
+    unsigned long long g_start;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g_start));
+#define WB_T0 const long long tt0_ = clock64();
+#define WB_T1(acc) acc += clock64() - tt0_;
+#else
+#define WB_T0
+#define WB_T1(acc)
+#endif
+
+    int s = 0;
+    uint32_t ph = 0;
+    // one chunk: wait for the stage, KS k-steps of 24 DMMA, release the stage.
+    // SLICES: issue deferred-epilogue slice (c*KS + ks) after the DMMA group of each k-step.
+    auto chunk = [&](int c, bool slices) {
+        {
+            WB_T0
+            mbar_wait(bar_base + 8u * s, ph);
+            WB_T1(t_wait)
+        }
+        const cplx* Ap = sA + s * A_D2 + (wm * KS * 6) * 32 + lane;
+        const cplx* Bp = sB + s * B_D2 + (wn * KS * 3) * 32 + lane;
+#pragma unroll
+        for (int ks = 0; ks < KS; ks++) {
+            double qa[12], qb[6];
+#pragma unroll
+            for (int j = 0; j < 6; j++) {
+                const cplx y = Ap[(ks * 6 + j) * 32];
+                qa[2 * j] = y.x;
+                qa[2 * j + 1] = y.y;
+            }
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                const cplx y = Bp[(ks * 3 + j) * 32];
+                qb[2 * j] = y.x;
+                qb[2 * j + 1] = y.y;
+            }
+            // qa[3 mt + {0,1,2}] = Ar, Ai, Ar+Ai ; qb[3 nt + {0,1,2}] = Br, Bi-Br, Br+Bi
+#pragma unroll
+            for (int mt = 0; mt < 4; mt++)
+#pragma unroll
+                for (int nt = 0; nt < 2; nt++) {
+                    dmma884(p1[mt][nt][0], p1[mt][nt][1], qa[3 * mt + 2], qb[3 * nt]);
+                    dmma884(p2[mt][nt][0], p2[mt][nt][1], qa[3 * mt], qb[3 * nt + 1]);
+                    dmma884(p3[mt][nt][0], p3[mt][nt][1], qa[3 * mt + 1], qb[3 * nt + 2]);
+                }
+            if (slices) epi_slice(c * KS + ks);
+        }
+        // WAR across proxies: our generic-proxy LDS reads of this stage must be ordered before
+        // the producer's next async-proxy bulk write into it (without this fence a stage was
+        // observed being overwritten under a slow warp; see tests: multi-wave determinism)
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_base + 8u * (STAGES + s));
+        if (++s == STAGES) { s = 0; ph ^= 1; }
+    };
+
+    for (int b = 0; b < nn; b++) {
+        // first EPI_CHUNKS chunks of the pair carry the deferred epilogue of the previous pair
+        if (b > 0) {
+#pragma unroll
+            for (int c = 0; c < EPI_CHUNKS; c++) chunk(c, true);
+            WB_T0
+            epi_end();
+            WB_T1(t_epi)
+        } else {
+#pragma unroll 1
+            for (int c = 0; c < EPI_CHUNKS; c++) chunk(c, false);
+        }
+#pragma unroll 1
+        for (int c = EPI_CHUNKS; c < nch; c++) chunk(c, false);
+        WB_T0
+        epi_begin((long long)kl * nn + b);
+        WB_T1(t_epi)
     }
+    {   // the last pair has no successor to hide under
+        WB_T0
+#pragma unroll
+        for (int sl = 0; sl < 8; sl++) epi_slice(sl);
+        epi_end();
+        WB_T1(t_epi)
+    }
+#ifdef WB_TIMING
+    if (lane == 0 && wb_dbg) {
+        unsigned long long g_end;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g_end));
+        unsigned smid;
+        asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+        long long* dd = wb_dbg + ((long long)blockIdx.x * 8 + warp) * 8;
+        dd[0] = clock64() - t_start; dd[1] = t_wait; dd[2] = t_epi; dd[3] = t_first;
+        dd[4] = (long long)g_start; dd[5] = (long long)g_end; dd[6] = smid; dd[7] = t_setup;
+    }
+#endif
 }
 
 // dN[pair][n] = sum_wm dNp[pair][wm][n];  fro[pair] = sum frop[pair][:]   (fixed order)
@@ -357,7 +448,7 @@ int launch_rotate(wb200_ctx* ctx, const cplx* dU) {
         WB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
         attr_done[ctx->device & 15] = true;
     }
-    kern<<<ctx->nk * p->nct, 288, p->smem, ctx->stream>>>(ctx->nb, ctx->nw, ctx->nn, p->nch, p->nct,
+    kern<<<ctx->nk * p->nct, 384, p->smem, ctx->stream>>>(ctx->nb, ctx->nw, ctx->nn, p->nch, p->nct,
                                                           ctx->k_begin, ctx->d_kpb, p->d_Mt, p->d_Up,
                                                           dU, ctx->d_MU, p->d_dNp, p->d_frop);
     WB_LAUNCH_CHECK(ctx);
@@ -434,3 +525,9 @@ int wb_rotate_dmma(wb200_ctx* ctx, const cplx* dU) {
     WB_LAUNCH_CHECK(ctx);
     return WB200_OK;
 }
+
+#ifdef WB_TIMING
+extern "C" int wb200_debug_set_timing_buffer(long long* dptr) {
+    return cudaMemcpyToSymbol(wb_dbg, &dptr, sizeof(dptr)) == cudaSuccess ? 0 : -2;
+}
+#endif

@@ -78,6 +78,15 @@ int main() {
         double tf = 512.0 * 16 * iters * 8.0 * sms * bps / (ms * 1e-3) / 1e12;
         printf(", \"dmma_tflops_%dwarps_16acc\": %.2f", bps * 8, tf);
     }
+    {   // one warp per SMSP: can a single warp saturate the pipe?
+        const int iters = 4000;
+        float ms = best_ms([&] { dmma_kernel<16><<<sms, 128>>>(out, iters, 1.0000001, 1e-3); });
+        printf(", \"dmma_tflops_4warps_16acc\": %.2f", 512.0 * 16 * iters * 4.0 * sms / (ms * 1e-3) / 1e12);
+        ms = best_ms([&] { dmma_kernel<24><<<sms, 128>>>(out, iters, 1.0000001, 1e-3); });
+        printf(", \"dmma_tflops_4warps_24acc\": %.2f", 512.0 * 24 * iters * 4.0 * sms / (ms * 1e-3) / 1e12);
+        ms = best_ms([&] { dmma_kernel<24><<<sms, 384>>>(out, iters, 1.0000001, 1e-3); });
+        printf(", \"dmma_tflops_12warps_24acc\": %.2f", 512.0 * 24 * iters * 12.0 * sms / (ms * 1e-3) / 1e12);
+    }
     {
         const int iters = 4000;
         float ms = best_ms([&] { dmma_kernel<4><<<sms, 256>>>(out, iters, 1.0000001, 1e-3); });
