@@ -13,7 +13,7 @@ configuration the metric is quoted on; it fits one B200 (about 55 GB resident).
   e2e    the same through the host-pointer drop-in call wb200_fg: U copied host->device from pinned
          memory and Omega, G copied back, inside the timed region.
   N > 1  strong scaling: the k-points are sharded in contiguous slabs, one process per GPU; every
-         step all-gathers the gauge slabs (NCCL), runs phase 1 on the slab, all-reduces the
+         step exchanges the neighbour-gauge halo (NCCL all-to-all), runs phase 1 on the slab, all-reduces the
          4 nw + 2 spread sums (NCCL) and runs phase 2 (gradient of the slab).
   --impl reference   the CPU restatement of the reference algorithm (oracle/, numpy + OpenBLAS,
          all host cores) on a bounded k-point sample of the same workload.
@@ -177,6 +177,7 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")   # keep NCCL's version banner off stdout (one JSON line)
         dist.init_process_group("nccl", device_id=dev)
 
     st = w.synthetic.make_stencil(w.synthetic.LATTICES[lat](), grid)
@@ -206,15 +207,15 @@ def main():
     dG = torch.zeros((nkl, nw, nb), dtype=torch.complex128, device=dev)
     dres = torch.zeros(ctx.nres, dtype=torch.float64, device=dev)
     dsums = torch.zeros(ctx.nsums, dtype=torch.float64, device=dev)
-    dUslab = dU[k0:k1].clone()
+    plan = w.sharding.HaloPlan(st["kpb_k"], bounds, rank)
 
     def step():
         if world == 1:
             ctx.fg_dev(dU.data_ptr(), dres.data_ptr(), dG.data_ptr())
         else:
-            # the optimiser owns U slab-wise: gather the gauges, evaluate the slab, reduce the sums
-            dist.all_gather_into_tensor(dU.view(torch.float64).view(-1), dUslab.view(torch.float64).view(-1)) \
-                if nk % world == 0 else None
+            # the optimiser owns U slab-wise: fetch the neighbour gauges other ranks own (halo),
+            # evaluate the slab, reduce the spread sums
+            plan.exchange(dU, dist)
             ctx.fg_phase1_dev(dU.data_ptr(), dsums.data_ptr())
             dist.all_reduce(dsums)
             ctx.fg_phase2_dev(dsums.data_ptr(), dres.data_ptr(), dG.data_ptr())
@@ -320,7 +321,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": dict(config, n_bvectors=nn, rotation_kernel=ctx.rotation_kernel,
-                           parallelism=f"k-slab x{world}", omega_check=omega_val),
+                           parallelism=f"k-slab x{world}", halo_k_per_rank=plan.n_halo, omega_check=omega_val),
             "e2e": e2e, "gpu_launches": int(launches), "clocks": cs.summary(), "roofline": roof}
 
     if cpu_sample is not None:

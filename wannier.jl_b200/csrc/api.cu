@@ -17,7 +17,7 @@ extern "C" void wb200_destroy(wb200_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     wb_dmma_plan_destroy(ctx);
-    void* ptrs[] = {ctx->d_kpb, ctx->d_kself, ctx->d_bvec, ctx->d_wb, ctx->d_M, ctx->d_r0,
+    void* ptrs[] = {ctx->d_need, ctx->d_kpb, ctx->d_kself, ctx->d_bvec, ctx->d_wb, ctx->d_M, ctx->d_r0,
                     ctx->d_frozen, ctx->d_nfrozen, ctx->d_U, ctx->d_G, ctx->d_MU, ctx->d_N,
                     ctx->d_dN, ctx->d_fro, ctx->d_part, ctx->d_pmin, ctx->d_sums, ctx->d_res,
                     ctx->d_min, ctx->d_scal, ctx->d_tmp1, ctx->d_tmp2, ctx->d_XY, ctx->d_GXY};
@@ -101,6 +101,16 @@ extern "C" int wb200_create(wb200_ctx** out, int device, int nb, int nw, int nk_
 
     std::vector<int32_t> kself(pairs);
     for (size_t p = 0; p < pairs; p++) kself[p] = k_begin + (int32_t)(p / nn);
+    {   // k-points whose gauges this slab reads
+        std::vector<char> mark(nk_total, 0);
+        for (int k = 0; k < nk; k++) mark[k_begin + k] = 1;
+        for (size_t p = 0; p < pairs; p++) mark[kpb_k[p]] = 1;
+        std::vector<int32_t> need;
+        for (int k = 0; k < nk_total; k++) if (mark[k]) need.push_back(k);
+        ctx->n_need = (int)need.size();
+        CREATE_CUDA(cudaMalloc(&ctx->d_need, sizeof(int32_t) * need.size()));
+        CREATE_CUDA(cudaMemcpy(ctx->d_need, need.data(), sizeof(int32_t) * need.size(), cudaMemcpyHostToDevice));
+    }
     CREATE_CUDA(cudaMemcpy(ctx->d_kpb, kpb_k, sizeof(int32_t) * pairs, cudaMemcpyHostToDevice));
     CREATE_CUDA(cudaMemcpy(ctx->d_kself, kself.data(), sizeof(int32_t) * pairs, cudaMemcpyHostToDevice));
     CREATE_CUDA(cudaMemcpy(ctx->d_bvec, bvec_cart, sizeof(double) * pairs * 3, cudaMemcpyHostToDevice));

@@ -80,6 +80,8 @@ struct wb200_ctx {
     // constant data (uploaded once)
     int32_t* d_kpb = nullptr;    // [nk][nn] global index of k+b
     int32_t* d_kself = nullptr;  // [nk*nn] global index of k for every pair
+    int32_t* d_need = nullptr;   // [n_need] sorted global k indices the slab reads (own + k+b)
+    int n_need = 0;
     double* d_bvec = nullptr;    // [nk][nn][3]
     double* d_wb = nullptr;      // [nn]
     cplx* d_M = nullptr;         // [nk][nn][nb*nb] col-major (generic path / exact N)

@@ -117,9 +117,10 @@ __global__ void tile_overlaps_kernel(int nb, int WM, int KC, int nch, const cplx
 // B-operand image of U.  Chunk c = [wn][ks][j(3)][lane] double2; the 6 doubles of a lane are
 //   (Br, Bi-Br, Br+Bi) of nt = 0..1 with l = c*KC + ks*4 + lane%4, n = ct*NC + wn*16 + nt*8 + lane/4.
 __global__ void __launch_bounds__(256) pack_gauge_kernel(int nb, int nw, int WN, int KC, int nch, int nct,
+                                                         const int32_t* __restrict__ need,
                                                          const cplx* __restrict__ U,
                                                          double* __restrict__ Up) {
-    const long long kg = blockIdx.x;
+    const long long kg = need[blockIdx.x];   // only the k-points this slab reads (own + neighbours)
     const int ct = blockIdx.y;
     const int KS = KC / 4;
     const int items = WN * KS * 32;              // per chunk
@@ -506,11 +507,11 @@ void wb_dmma_plan_destroy(wb200_ctx* ctx) {
 
 int wb_rotate_dmma(wb200_ctx* ctx, const cplx* dU) {
     DmmaPlan* p = ctx->dmma;
-    dim3 g((unsigned)ctx->nk_total, (unsigned)p->nct);
+    dim3 g((unsigned)ctx->n_need, (unsigned)p->nct);
     {
         ProfScope ps(ctx, 0);
         pack_gauge_kernel<<<g, 256, 0, ctx->stream>>>(ctx->nb, ctx->nw, p->WN, p->KC, p->nch, p->nct,
-                                                     dU, p->d_Up);
+                                                      ctx->d_need, dU, p->d_Up);
     }
     WB_LAUNCH_CHECK(ctx);
     {

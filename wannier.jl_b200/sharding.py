@@ -1,0 +1,72 @@
+"""k-point sharding across processes (one process per GPU): slab bounds and the gauge halo exchange.
+
+The reference is single-process; what shards is the (k, b) pair loop of compute_MU_UtMU! /
+omega! / omega_grad! (src/spread.jl:164-195, 254-360, 398-481).  Rank r owns a contiguous
+k-slab: its overlaps M, its gradient G and its rows of U never move.  Per evaluation:
+  1. halo exchange: rank r receives U_{k+b} for the neighbours of its slab that other ranks own
+     (`HaloPlan.exchange`, one NCCL all-to-all with per-peer index lists), or an all-gather of
+     the whole gauge when slabs are thin;
+  2. wb200_fg_phase1_dev on the slab -> 4 nw + 2 partial sums; all-reduce(sum) over ranks;
+  3. wb200_fg_phase2_dev -> spread scalars (identical on every rank) and the slab's gradient.
+Pure host logic (torch.distributed); works with the gloo backend on CPU tensors for testing.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def slab_bounds(nk, world):
+    """[k_begin of rank r] + [nk]: contiguous, as even as possible (k index = (i*n2 + j)*n3 + l, so
+    slabs are planes of the slowest grid axis when world divides n1)."""
+    return [(nk * r) // world for r in range(world + 1)]
+
+
+def owner_of(k, bounds):
+    return np.searchsorted(np.asarray(bounds[1:]), k, side="right")
+
+
+class HaloPlan:
+    """Index lists for the neighbour-gauge exchange, computed identically on every rank from the
+    global kpb_k table [nk, nn] (it is tiny: nk * nn int32)."""
+
+    def __init__(self, kpb_k, bounds, rank):
+        self.rank = rank
+        self.world = len(bounds) - 1
+        self.bounds = list(bounds)
+        kpb_k = np.asarray(kpb_k)
+        need_from = []   # need_from[dst][src] = sorted k owned by src that dst reads
+        for dst in range(self.world):
+            k0, k1 = bounds[dst], bounds[dst + 1]
+            nb_k = np.unique(kpb_k[k0:k1])
+            own = owner_of(nb_k, bounds)
+            need_from.append([nb_k[(own == src)] if src != dst else nb_k[:0] for src in range(self.world)])
+        self.recv_idx = [np.asarray(a, dtype=np.int64) for a in need_from[rank]]
+        self.send_idx = [np.asarray(need_from[dst][rank], dtype=np.int64) for dst in range(self.world)]
+        self.recv_counts = [len(a) for a in self.recv_idx]
+        self.send_counts = [len(a) for a in self.send_idx]
+        self.n_halo = int(sum(self.recv_counts))
+
+    def exchange(self, U, dist, scratch=None):
+        """U: tensor [nk_total, ...] whose own slab is current; fills the halo rows in place.
+        `dist` is torch.distributed (passed in so this module imports without torch)."""
+        import torch
+        per = U[0].numel()
+        flat = U.reshape(U.shape[0], per)
+        send_rows = np.concatenate(self.send_idx) if self.world > 1 else np.zeros(0, dtype=np.int64)
+        recv_rows = np.concatenate(self.recv_idx) if self.world > 1 else np.zeros(0, dtype=np.int64)
+        if len(send_rows) == 0 and len(recv_rows) == 0:
+            return
+        key = str(U.device)
+        if getattr(self, "_dev_key", None) != key:      # index tensors live on the device, built once
+            self._si = torch.as_tensor(send_rows, device=U.device)
+            self._ri = torch.as_tensor(recv_rows, device=U.device)
+            self._dev_key = key
+        si, ri = self._si, self._ri
+        send = flat.index_select(0, si).contiguous()
+        recv = torch.empty((len(recv_rows), per), dtype=U.dtype, device=U.device)
+        # complex tensors travel as real pairs (not every backend has complex collectives)
+        s_r = torch.view_as_real(send) if send.is_complex() else send
+        r_r = torch.view_as_real(recv) if recv.is_complex() else recv
+        dist.all_to_all_single(r_r, s_r, output_split_sizes=self.recv_counts,
+                               input_split_sizes=self.send_counts)
+        flat.index_copy_(0, ri, recv)
