@@ -253,8 +253,9 @@ def main():
     # ---- end-to-end through the host-pointer drop-in call (N = 1: wb200_fg; N > 1: slab copies) ----
     e2e = None
     if not args.no_e2e:
-        hU = torch.empty((nk, nw, nb), dtype=torch.complex128).pin_memory()
-        hU.copy_(dU)
+        # every process holds ITS k-slab of U (and receives its slab of G) in pinned host memory
+        hU = torch.empty((nkl if world > 1 else nk, nw, nb), dtype=torch.complex128).pin_memory()
+        hU.copy_(dU[k0:k1] if world > 1 else dU)
         hG = torch.empty((nkl, nw, nb), dtype=torch.complex128).pin_memory()
         hres = torch.empty(ctx.nres, dtype=torch.float64).pin_memory()
         hUn, hGn = hU.numpy(), hG.numpy()
@@ -262,7 +263,8 @@ def main():
         def step_e2e():
             if world == 1:
                 return ctx.fg(hUn, want_f=True, G=hGn)        # wb200_fg: H2D U, compute, D2H f and G
-            dU.copy_(hU, non_blocking=True)
+            dU[k0:k1].copy_(hU, non_blocking=True)            # own slab host -> device
+            plan.exchange(dU, dist)                           # neighbour gauges over NVLink
             ctx.fg_phase1_dev(dU.data_ptr(), dsums.data_ptr())
             dist.all_reduce(dsums)
             ctx.fg_phase2_dev(dsums.data_ptr(), dres.data_ptr(), dG.data_ptr())
@@ -283,10 +285,10 @@ def main():
             t = torch.tensor([dt], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = t.item()
-        e2e = {"value": 1.0 / dt, "unit": "evals/s", "h2d_bytes_per_step": int(hU.numel() * 16 * world),
+        e2e = {"value": 1.0 / dt, "unit": "evals/s", "h2d_bytes_per_step": int(16 * nk * nb * nw),
                "d2h_bytes_per_step": int(16 * nk * nb * nw + 8 * world), "steps": n_e2e,
                "check_f": f_e2e, "api": "wb200_fg (host pointers, pinned)" if world == 1 else
-               "H2D U + phase1/all-reduce/phase2 + D2H G per rank"}
+               "per rank: H2D own U slab, halo exchange, phase1 / all-reduce / phase2, D2H own G slab"}
 
     if rank != 0:
         if world > 1:
