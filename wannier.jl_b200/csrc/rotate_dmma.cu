@@ -372,6 +372,10 @@ rotate_dmma_kernel(int nb, int nw, int nn, int nch, int nct, int k_begin,
         if (++s == STAGES) { s = 0; ph ^= 1; }
     };
 
+    // (Measured, tools/dmma_mix.cu: next to a saturating DMMA stream a CUDA-core FP64 instruction gets
+    // a pipe slot only every ~10 cycles.  Staggering the slices of the two warps of an SMSP, or
+    // skewing the warps by whole chunks, was tried and is slower: the warps drift apart and stall on
+    // the 5-stage ring.)
     for (int b = 0; b < nn; b++) {
         // first EPI_CHUNKS chunks of the pair carry the deferred epilogue of the previous pair
         if (b > 0) {
