@@ -26,6 +26,10 @@ extern "C" void wb200_destroy(wb200_ctx* ctx) {
     for (auto& v : ctx->prof_events)
         for (auto& pr : v) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    for (auto e : ctx->ev_up) cudaEventDestroy(e);
+    for (auto e : ctx->ev_grad) cudaEventDestroy(e);
+    if (ctx->h2d_stream) cudaStreamDestroy(ctx->h2d_stream);
+    if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -117,6 +121,7 @@ extern "C" int wb200_create(wb200_ctx** out, int device, int nb, int nw, int nk_
     CREATE_CUDA(cudaMemcpy(ctx->d_wb, bweights, sizeof(double) * nn, cudaMemcpyHostToDevice));
     CREATE_CUDA(cudaMemcpy(ctx->d_M, M, sizeof(cplx) * pairs * nb * nb, cudaMemcpyDefault));  // host or device
     ctx->h_wb.assign(bweights, bweights + nn);
+    ctx->h_kpb.assign(kpb_k, kpb_k + pairs);
     ctx->wsum = 0.0;
     for (int b = 0; b < nn; b++) ctx->wsum += bweights[b];
 
@@ -183,9 +188,14 @@ extern "C" int wb200_set_frozen(wb200_ctx* ctx, const uint8_t* frozen) {
 // ---------------------------------------------------------------------------------------------
 // device pipeline
 // ---------------------------------------------------------------------------------------------
+// rotation of the local k-points [ka, kb); the tensor path needs the gauge packed first
+static int rotate_range(wb200_ctx* ctx, const cplx* dU, int ka, int kb) {
+    if (ctx->dmma) return wb_rotate_dmma(ctx, dU, ka, kb);
+    return wb_rotate_generic(ctx, dU, ka, kb);
+}
 static int rotate(wb200_ctx* ctx, const cplx* dU) {
-    if (ctx->dmma) return wb_rotate_dmma(ctx, dU);
-    return wb_rotate_generic(ctx, dU);
+    if (ctx->dmma) WB_TRY(wb_pack_dmma(ctx, dU, 0, ctx->n_need));
+    return rotate_range(ctx, dU, 0, ctx->nk);
 }
 
 extern "C" int wb200_fg_phase1_dev(wb200_ctx* ctx, const double* dU, double* dsums, int exact_split) {
@@ -201,7 +211,7 @@ extern "C" int wb200_fg_phase2_dev(wb200_ctx* ctx, const double* dsums, double* 
     if (!ctx || !dsums) return WB200_ERR_ARG;
     cudaSetDevice(ctx->device);
     if (dres) WB_TRY(wb_finalize(ctx, dsums, dres));
-    if (dG) WB_TRY(wb_grad(ctx, dsums, (cplx*)dG));
+    if (dG) WB_TRY(wb_grad(ctx, dsums, (cplx*)dG, 0, ctx->nk));
     return WB200_OK;
 }
 
@@ -248,18 +258,96 @@ static int upload_U(wb200_ctx* ctx, const double* U) {
     return WB200_OK;
 }
 
+// Sub-slab plan of the pipelined host entry point: contiguous k sub-slabs and, for each, the
+// sub-slabs of U its pairs read (from kpb_k).  Built once per ctx.
+static int ensure_pipeline(wb200_ctx* ctx, const std::vector<int32_t>& kpb_host) {
+    if (!ctx->sub_bounds.empty()) return WB200_OK;
+    const int nk = ctx->nk;
+    const size_t bytes = sizeof(cplx) * (size_t)nk * ctx->nb * ctx->nw;
+    int S = 1;
+    if (bytes >= (size_t)32 << 20) S = nk < 16 ? nk : 16;   // only worth it when PCIe time matters
+    for (int i = 0; i <= S; i++) ctx->sub_bounds.push_back((int)((long long)nk * i / S));
+    ctx->sub_deps.assign(S, {});
+    for (int i = 0; i < S; i++) {
+        std::vector<char> mark(S, 0);
+        mark[i] = 1;
+        for (long long p = (long long)ctx->sub_bounds[i] * ctx->nn; p < (long long)ctx->sub_bounds[i + 1] * ctx->nn; p++) {
+            const int k = kpb_host[p];
+            int j = (int)((long long)k * S / nk);
+            while (j > 0 && k < ctx->sub_bounds[j]) j--;
+            while (j + 1 < S && k >= ctx->sub_bounds[j + 1]) j++;
+            mark[j] = 1;
+        }
+        for (int j = 0; j < S; j++) if (mark[j]) ctx->sub_deps[i].push_back(j);
+    }
+    WB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking));
+    WB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
+    ctx->ev_up.resize(S);
+    ctx->ev_grad.resize(S);
+    for (int i = 0; i < S; i++) {
+        WB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_up[i], cudaEventDisableTiming));
+        WB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_grad[i], cudaEventDisableTiming));
+    }
+    return WB200_OK;
+}
+
+// fg!(F, G, U) with host pointers.  The PCIe copies are pipelined against the compute:
+// U is uploaded sub-slab by sub-slab in the order the rotation needs it (a sub-slab starts as soon
+// as the sub-slabs holding its neighbours k+b have landed), and G goes back sub-slab by sub-slab
+// behind the gradient kernel.  G itself cannot start earlier: it needs the centres r of ALL k.
 extern "C" int wb200_fg(wb200_ctx* ctx, const double* U, double* f, double* G) {
     if (!ctx || !U) return WB200_ERR_ARG;
     cudaSetDevice(ctx->device);
     WB_TRY(require_single_slab(ctx, "wb200_fg"));
-    WB_TRY(upload_U(ctx, U));
-    WB_TRY(wb_fg_device(ctx, ctx->d_U, ctx->d_res, G ? ctx->d_G : nullptr, 0));
-    if (G)
-        WB_CUDA(ctx, cudaMemcpyAsync(G, ctx->d_G, sizeof(cplx) * (size_t)ctx->nk * ctx->nb * ctx->nw,
-                                     cudaMemcpyDeviceToHost, ctx->stream));
+    WB_TRY(ensure_pipeline(ctx, ctx->h_kpb));
+    const int S = (int)ctx->sub_bounds.size() - 1;
+    const size_t mat = (size_t)ctx->nb * ctx->nw;
+    const cplx* hU = (const cplx*)U;
+    cplx* hG = (cplx*)G;
+    if (S == 1) {
+        WB_TRY(upload_U(ctx, U));
+        WB_TRY(wb_fg_device(ctx, ctx->d_U, ctx->d_res, G ? ctx->d_G : nullptr, 0));
+        if (G)
+            WB_CUDA(ctx, cudaMemcpyAsync(G, ctx->d_G, sizeof(cplx) * (size_t)ctx->nk * mat,
+                                         cudaMemcpyDeviceToHost, ctx->stream));
+    } else {
+        std::vector<char> uploaded(S, 0);
+        // the copy stream must not overtake work of earlier calls still reading d_U
+        WB_CUDA(ctx, cudaEventRecord(ctx->ev_grad[0], ctx->stream));
+        WB_CUDA(ctx, cudaStreamWaitEvent(ctx->h2d_stream, ctx->ev_grad[0], 0));
+        for (int i = 0; i < S; i++) {
+            for (int j : ctx->sub_deps[i]) {
+                if (uploaded[j]) continue;
+                const size_t off = (size_t)ctx->sub_bounds[j] * mat;
+                const size_t cnt = (size_t)(ctx->sub_bounds[j + 1] - ctx->sub_bounds[j]) * mat;
+                WB_CUDA(ctx, cudaMemcpyAsync(ctx->d_U + off, hU + off, sizeof(cplx) * cnt,
+                                             cudaMemcpyHostToDevice, ctx->h2d_stream));
+                WB_CUDA(ctx, cudaEventRecord(ctx->ev_up[j], ctx->h2d_stream));
+                WB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_up[j], 0));
+                if (ctx->dmma) WB_TRY(wb_pack_dmma(ctx, ctx->d_U, ctx->sub_bounds[j], ctx->sub_bounds[j + 1]));
+                uploaded[j] = 1;
+            }
+            WB_TRY(rotate_range(ctx, ctx->d_U, ctx->sub_bounds[i], ctx->sub_bounds[i + 1]));
+            WB_TRY(wb_pair_partial(ctx, ctx->sub_bounds[i], ctx->sub_bounds[i + 1]));
+        }
+        WB_TRY(wb_sum_over_k(ctx, ctx->d_sums));
+        WB_TRY(wb_finalize(ctx, ctx->d_sums, ctx->d_res));
+        if (G) {
+            for (int i = 0; i < S; i++) {
+                const size_t off = (size_t)ctx->sub_bounds[i] * mat;
+                const size_t cnt = (size_t)(ctx->sub_bounds[i + 1] - ctx->sub_bounds[i]) * mat;
+                WB_TRY(wb_grad(ctx, ctx->d_sums, ctx->d_G, ctx->sub_bounds[i], ctx->sub_bounds[i + 1]));
+                WB_CUDA(ctx, cudaEventRecord(ctx->ev_grad[i], ctx->stream));
+                WB_CUDA(ctx, cudaStreamWaitEvent(ctx->d2h_stream, ctx->ev_grad[i], 0));
+                WB_CUDA(ctx, cudaMemcpyAsync(hG + off, ctx->d_G + off, sizeof(cplx) * cnt,
+                                             cudaMemcpyDeviceToHost, ctx->d2h_stream));
+            }
+        }
+    }
     WB_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, ctx->d_res, sizeof(double) * 8, cudaMemcpyDeviceToHost,
                                  ctx->stream));
     WB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (S > 1 && G) WB_CUDA(ctx, cudaStreamSynchronize(ctx->d2h_stream));
     if (f) *f = ctx->h_pinned[5];
     return WB200_OK;
 }

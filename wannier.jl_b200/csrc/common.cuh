@@ -73,6 +73,10 @@ struct wb200_ctx {
     int nb = 0, nw = 0, nk_total = 0, k_begin = 0, nk = 0, nn = 0;
     unsigned flags = 0;
     cudaStream_t own_stream = nullptr;
+    cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;   // pipelined host entry point
+    std::vector<cudaEvent_t> ev_up, ev_grad;
+    std::vector<int> sub_bounds;                  // sub-slab bounds of the pipelined wb200_fg
+    std::vector<std::vector<int>> sub_deps;       // sub-slabs of U each sub-slab reads
     cudaStream_t stream = nullptr;
     long long launches = 0;
     std::string err;
@@ -87,6 +91,7 @@ struct wb200_ctx {
     cplx* d_M = nullptr;         // [nk][nn][nb*nb] col-major (generic path / exact N)
     double wsum = 0.0;           // sum_b w_b
     std::vector<double> h_wb;
+    std::vector<int32_t> h_kpb;  // host copy of kpb_k (sub-slab dependency plan)
 
     // penalty / frozen
     int has_penalty = 0;
@@ -172,11 +177,13 @@ struct ProfScope {
 
 // ---- kernels_generic.cu ----
 int wb_zgemm_batched(wb200_ctx* ctx, const ZgemmArgs& a);
-int wb_rotate_generic(wb200_ctx* ctx, const cplx* dU);              // MU, dN, fro(=||MU||^2)
+int wb_rotate_generic(wb200_ctx* ctx, const cplx* dU, int ka, int kb);  // MU, dN, fro(=||MU||^2) of local k in [ka, kb)
 int wb_form_N(wb200_ctx* ctx, const cplx* dU);                      // N = U_k^H MU, fro = ||N||^2
 int wb_pair_reduce(wb200_ctx* ctx, double* dsums);                  // part -> sums (+ min)
+int wb_pair_partial(wb200_ctx* ctx, int ka, int kb);                // per-k partial sums of local k in [ka, kb)
+int wb_sum_over_k(wb200_ctx* ctx, double* dsums);
 int wb_finalize(wb200_ctx* ctx, const double* dsums, double* dres);
-int wb_grad(wb200_ctx* ctx, const double* dsums, cplx* dG);
+int wb_grad(wb200_ctx* ctx, const double* dsums, cplx* dG, int ka, int kb);
 int wb_ensure_tmp(wb200_ctx* ctx, size_t e1, size_t e2);
 int wb_ensure_N(wb200_ctx* ctx);
 
@@ -197,7 +204,8 @@ int wb_axpbyz(wb200_ctx* ctx, double alpha, const double* x, double beta, const 
 // ---- rotate_dmma.cu ----
 int wb_dmma_plan_create(wb200_ctx* ctx, const double* hM);   // may leave ctx->dmma == nullptr if not applicable
 void wb_dmma_plan_destroy(wb200_ctx* ctx);
-int wb_rotate_dmma(wb200_ctx* ctx, const cplx* dU);           // MU, dN, fro(=||MU||^2)
+int wb_pack_dmma(wb200_ctx* ctx, const cplx* dU, int ja, int jb);     // pack need[ja:jb) of the gauge
+int wb_rotate_dmma(wb200_ctx* ctx, const cplx* dU, int ka, int kb);   // MU, dN, fro(=||MU||^2) of local k in [ka, kb)
 
 // ---- optimizer.cu ----
 int wb_lbfgs(wb200_ctx* ctx, int mode /*0 maxloc, 1 disentangle*/, cplx* dx, double f_tol,

@@ -167,18 +167,20 @@ __global__ void __launch_bounds__(256) fro_kernel(int len, const cplx* __restric
     }
 }
 
-int wb_rotate_generic(wb200_ctx* ctx, const cplx* dU) {
-    const int nb = ctx->nb, nw = ctx->nw, pairs = ctx->nk * ctx->nn;
+int wb_rotate_generic(wb200_ctx* ctx, const cplx* dU, int ka, int kb) {
+    const int nb = ctx->nb, nw = ctx->nw;
+    const long long p0 = (long long)ka * ctx->nn;
+    const int pairs = (kb - ka) * ctx->nn;
     ZgemmArgs a{};
     a.m = nb; a.n = nw; a.k = nb;
-    a.A = ctx->d_M; a.strideA = (long long)nb * nb; a.lda = nb; a.idxA = nullptr;
-    a.B = dU; a.strideB = (long long)nb * nw; a.ldb = nb; a.idxB = ctx->d_kpb;
-    a.C = ctx->d_MU; a.strideC = (long long)nb * nw; a.ldc = nb;
+    a.A = ctx->d_M + p0 * nb * nb; a.strideA = (long long)nb * nb; a.lda = nb; a.idxA = nullptr;
+    a.B = dU; a.strideB = (long long)nb * nw; a.ldb = nb; a.idxB = ctx->d_kpb + p0;
+    a.C = ctx->d_MU + p0 * nb * nw; a.strideC = (long long)nb * nw; a.ldc = nb;
     a.alpha = 1.0; a.beta = 0.0; a.batch = pairs; a.transA = 0; a.transB = 0;
     ProfScope ps(ctx, 1);
     WB_TRY(wb_zgemm_batched(ctx, a));
-    diag_kernel<<<pairs, 256, 0, ctx->stream>>>(nb, nw, dU, ctx->d_kself, ctx->d_MU, ctx->d_dN,
-                                                 ctx->d_fro);
+    diag_kernel<<<pairs, 256, 0, ctx->stream>>>(nb, nw, dU, ctx->d_kself + p0, ctx->d_MU + p0 * nb * nw,
+                                                 ctx->d_dN + p0 * nw, ctx->d_fro + p0);
     WB_LAUNCH_CHECK(ctx);
     return WB200_OK;
 }
@@ -211,14 +213,14 @@ int wb_form_N(wb200_ctx* ctx, const cplx* dU) {
 //   part[j][k], j in [0, 4nw+2):  3n+a: sum_b w_b b_a phi   3nw+n: sum_b w_b (1-|N|^2+phi^2)
 //   4nw: sum_b w_b ||N||_F^2       4nw+1: sum_b w_b sum_n |N_nn|^2
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) pair_reduce_kernel(int nw, int nn, int nk,
+__global__ void __launch_bounds__(128) pair_reduce_kernel(int nw, int nn, int nk, int k_off,
                                                           const cplx* __restrict__ dN,
                                                           const double* __restrict__ fro,
                                                           const double* __restrict__ bvec,
                                                           const double* __restrict__ wb,
                                                           double* __restrict__ part,
                                                           double* __restrict__ pmin) {
-    const int k = blockIdx.x;
+    const int k = blockIdx.x + k_off;
     double sd = 0.0, mn = 1e300;
     for (int n = threadIdx.x; n < nw; n += blockDim.x) {
         double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
@@ -288,16 +290,26 @@ __global__ void __launch_bounds__(256) sum_over_k_kernel(int nk, int ns, const d
     }
 }
 
-int wb_pair_reduce(wb200_ctx* ctx, double* dsums) {
+int wb_pair_partial(wb200_ctx* ctx, int ka, int kb) {
     ProfScope ps(ctx, 2);
-    pair_reduce_kernel<<<ctx->nk, 128, 0, ctx->stream>>>(ctx->nw, ctx->nn, ctx->nk, ctx->d_dN,
+    pair_reduce_kernel<<<kb - ka, 128, 0, ctx->stream>>>(ctx->nw, ctx->nn, ctx->nk, ka, ctx->d_dN,
                                                           ctx->d_fro, ctx->d_bvec, ctx->d_wb,
                                                           ctx->d_part, ctx->d_pmin);
     WB_LAUNCH_CHECK(ctx);
+    return WB200_OK;
+}
+
+int wb_sum_over_k(wb200_ctx* ctx, double* dsums) {
+    ProfScope ps(ctx, 2);
     sum_over_k_kernel<<<ctx->nsums() + 1, 256, 0, ctx->stream>>>(ctx->nk, ctx->nsums(), ctx->d_part,
                                                                   ctx->d_pmin, dsums, ctx->d_min);
     WB_LAUNCH_CHECK(ctx);
     return WB200_OK;
+}
+
+int wb_pair_reduce(wb200_ctx* ctx, double* dsums) {
+    WB_TRY(wb_pair_partial(ctx, 0, ctx->nk));
+    return wb_sum_over_k(ctx, dsums);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -356,7 +368,7 @@ int wb_finalize(wb200_ctx* ctx, const double* dsums, double* dres) {
 // grid (nk, ceil(nw/NT)); coefficients for the block's NT columns are built once in smem.
 // ------------------------------------------------------------------------------------------
 #define WB_GRAD_NT 32
-__global__ void __launch_bounds__(256) grad_kernel(int nb, int nw, int nn, int nk_total,
+__global__ void __launch_bounds__(256) grad_kernel(int nb, int nw, int nn, int nk_total, int k_off,
                                                    const cplx* __restrict__ MU,
                                                    const cplx* __restrict__ dN,
                                                    const double* __restrict__ bvec,
@@ -365,7 +377,7 @@ __global__ void __launch_bounds__(256) grad_kernel(int nb, int nw, int nn, int n
                                                    double lambda, const double* __restrict__ r0,
                                                    cplx* __restrict__ G) {
     extern __shared__ cplx coef[];  // [nn][WB_GRAD_NT]
-    const int k = blockIdx.x;
+    const int k = blockIdx.x + k_off;
     const int n0 = blockIdx.y * WB_GRAD_NT;
     const int nt = min(WB_GRAD_NT, nw - n0);
     const double inv = 1.0 / (double)nk_total;
@@ -402,11 +414,11 @@ __global__ void __launch_bounds__(256) grad_kernel(int nb, int nw, int nn, int n
     }
 }
 
-int wb_grad(wb200_ctx* ctx, const double* dsums, cplx* dG) {
+int wb_grad(wb200_ctx* ctx, const double* dsums, cplx* dG, int ka, int kb) {
     ProfScope ps(ctx, 3);
-    dim3 g(ctx->nk, (ctx->nw + WB_GRAD_NT - 1) / WB_GRAD_NT);
+    dim3 g(kb - ka, (ctx->nw + WB_GRAD_NT - 1) / WB_GRAD_NT);
     const size_t smem = sizeof(cplx) * (size_t)ctx->nn * WB_GRAD_NT;
-    grad_kernel<<<g, 256, smem, ctx->stream>>>(ctx->nb, ctx->nw, ctx->nn, ctx->nk_total, ctx->d_MU,
+    grad_kernel<<<g, 256, smem, ctx->stream>>>(ctx->nb, ctx->nw, ctx->nn, ctx->nk_total, ka, ctx->d_MU,
                                                ctx->d_dN, ctx->d_bvec, ctx->d_wb, dsums,
                                                ctx->has_penalty, ctx->lambda, ctx->d_r0, dG);
     WB_LAUNCH_CHECK(ctx);

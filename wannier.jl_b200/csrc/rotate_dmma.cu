@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(256) pack_gauge_kernel(int nb, int nw, int WN,
 // ---- the rotation kernel ---------------------------------------------------------------------
 template <int WM, int WN, int KC, int STAGES>
 __global__ void __launch_bounds__(384, 1)
-rotate_dmma_kernel(int nb, int nw, int nn, int nch, int nct, int k_begin,
+rotate_dmma_kernel(int nb, int nw, int nn, int nch, int nct, int k_begin, int k_off,
                    const int32_t* __restrict__ kpb, const double* __restrict__ Mt,
                    const double* __restrict__ Up, const cplx* __restrict__ U,
                    cplx* __restrict__ MU, cplx* __restrict__ dNp, double* __restrict__ frop) {
@@ -171,7 +171,7 @@ rotate_dmma_kernel(int nb, int nw, int nn, int nch, int nct, int k_begin,
 #endif
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t bar_base = smem_u32(bars), sA_base = smem_u32(sA), sB_base = smem_u32(sB);
-    const int kl = blockIdx.x / nct, ct = blockIdx.x % nct;
+    const int kl = blockIdx.x / nct + k_off, ct = blockIdx.x % nct;
     const int n0 = ct * NC;
     const int total = nn * nch;  // chunks streamed by this CTA
 
@@ -415,12 +415,12 @@ rotate_dmma_kernel(int nb, int nw, int nn, int nch, int nct, int k_begin,
 }
 
 // dN[pair][n] = sum_wm dNp[pair][wm][n];  fro[pair] = sum frop[pair][:]   (fixed order)
-__global__ void __launch_bounds__(128) combine_partials_kernel(int nw, int WM, int nfro,
+__global__ void __launch_bounds__(128) combine_partials_kernel(int nw, int WM, int nfro, long long pair_off,
                                                                const cplx* __restrict__ dNp,
                                                                const double* __restrict__ frop,
                                                                cplx* __restrict__ dN,
                                                                double* __restrict__ fro) {
-    const long long pair = blockIdx.x;
+    const long long pair = blockIdx.x + pair_off;
     for (int n = threadIdx.x; n < nw; n += blockDim.x) {
         cplx s = make_double2(0.0, 0.0);
         for (int w = 0; w < WM; w++) {
@@ -445,7 +445,7 @@ size_t smem_bytes() {
 }
 
 template <int WM, int WN, int KC, int STAGES>
-int launch_rotate(wb200_ctx* ctx, const cplx* dU) {
+int launch_rotate(wb200_ctx* ctx, const cplx* dU, int ka, int kb) {
     DmmaPlan* p = ctx->dmma;
     auto kern = rotate_dmma_kernel<WM, WN, KC, STAGES>;
     static bool attr_done[16] = {false};
@@ -453,8 +453,8 @@ int launch_rotate(wb200_ctx* ctx, const cplx* dU) {
         WB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
         attr_done[ctx->device & 15] = true;
     }
-    kern<<<ctx->nk * p->nct, 384, p->smem, ctx->stream>>>(ctx->nb, ctx->nw, ctx->nn, p->nch, p->nct,
-                                                          ctx->k_begin, ctx->d_kpb, p->d_Mt, p->d_Up,
+    kern<<<(kb - ka) * p->nct, 384, p->smem, ctx->stream>>>(ctx->nb, ctx->nw, ctx->nn, p->nch, p->nct,
+                                                          ctx->k_begin, ka, ctx->d_kpb, p->d_Mt, p->d_Up,
                                                           dU, ctx->d_MU, p->d_dNp, p->d_frop);
     WB_LAUNCH_CHECK(ctx);
     return WB200_OK;
@@ -509,24 +509,27 @@ void wb_dmma_plan_destroy(wb200_ctx* ctx) {
     ctx->dmma = nullptr;
 }
 
-int wb_rotate_dmma(wb200_ctx* ctx, const cplx* dU) {
+int wb_pack_dmma(wb200_ctx* ctx, const cplx* dU, int ja, int jb) {
     DmmaPlan* p = ctx->dmma;
-    dim3 g((unsigned)ctx->n_need, (unsigned)p->nct);
-    {
-        ProfScope ps(ctx, 0);
-        pack_gauge_kernel<<<g, 256, 0, ctx->stream>>>(ctx->nb, ctx->nw, p->WN, p->KC, p->nch, p->nct,
-                                                      ctx->d_need, dU, p->d_Up);
-    }
+    dim3 g((unsigned)(jb - ja), (unsigned)p->nct);
+    ProfScope ps(ctx, 0);
+    pack_gauge_kernel<<<g, 256, 0, ctx->stream>>>(ctx->nb, ctx->nw, p->WN, p->KC, p->nch, p->nct,
+                                                  ctx->d_need + ja, dU, p->d_Up);
     WB_LAUNCH_CHECK(ctx);
+    return WB200_OK;
+}
+
+int wb_rotate_dmma(wb200_ctx* ctx, const cplx* dU, int ka, int kb) {
+    DmmaPlan* p = ctx->dmma;
     {
         ProfScope ps(ctx, 1);
-        if (p->WM == 2) WB_TRY((launch_rotate<WB_CFG_64>(ctx, dU)));
-        else if (p->WM == 4) WB_TRY((launch_rotate<WB_CFG_128>(ctx, dU)));
-        else WB_TRY((launch_rotate<WB_CFG_256>(ctx, dU)));
+        if (p->WM == 2) WB_TRY((launch_rotate<WB_CFG_64>(ctx, dU, ka, kb)));
+        else if (p->WM == 4) WB_TRY((launch_rotate<WB_CFG_128>(ctx, dU, ka, kb)));
+        else WB_TRY((launch_rotate<WB_CFG_256>(ctx, dU, ka, kb)));
     }
     ProfScope ps2(ctx, 2);
-    combine_partials_kernel<<<ctx->nk * ctx->nn, 128, 0, ctx->stream>>>(
-        ctx->nw, p->WM, p->nct * 8, p->d_dNp, p->d_frop, ctx->d_dN, ctx->d_fro);
+    combine_partials_kernel<<<(kb - ka) * ctx->nn, 128, 0, ctx->stream>>>(
+        ctx->nw, p->WM, p->nct * 8, (long long)ka * ctx->nn, p->d_dNp, p->d_frop, ctx->d_dN, ctx->d_fro);
     WB_LAUNCH_CHECK(ctx);
     return WB200_OK;
 }
