@@ -140,6 +140,9 @@ def main():
     ap.add_argument("--config", default="cfg4_nw128")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--halo", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: read neighbour gauges from peer memory inside the pack kernel (CUDA IPC "
+                         "over NVLink) or exchange them with an NCCL all-to-all / send-recv first")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -208,14 +211,60 @@ def main():
     dres = torch.zeros(ctx.nres, dtype=torch.float64, device=dev)
     dsums = torch.zeros(ctx.nsums, dtype=torch.float64, device=dev)
     plan = w.sharding.HaloPlan(st["kpb_k"], bounds, rank)
+    halo = args.halo if world > 1 else "none"
+    ready = torch.zeros(1, dtype=torch.float64, device=dev)
+    if halo == "peer":
+        # every rank keeps the FULL gauge array in an IPC-shareable allocation and owns its slab rows;
+        # the other ranks map it and their pack kernels read the rows they need over NVLink
+        try:
+            my_ptr, my_handle = w.lib.ipc_alloc(local_rank, 16 * nk * nb * nw)
+            handles = [None] * world
+            dist.all_gather_object(handles, my_handle)
+            peer_ptrs = [my_ptr if r == rank else w.lib.ipc_open(local_rank, handles[r]) for r in range(world)]
+            Ushared = torch.as_tensor(w.lib.DeviceArray(my_ptr, (nk, nw, nb)), device=dev)
+            Ushared.fill_(complex(float("nan"), float("nan")))      # rows of other ranks are never valid here
+            Ushared[k0:k1].copy_(dU[k0:k1])
+            ctx.set_peer_gauges(peer_ptrs, bounds)
+            dU = Ushared
+            ok = torch.ones(1, device=dev)
+        except Exception as e:                                        # CUDA IPC unavailable
+            print(f"[rank {rank}] peer-memory halo unavailable ({e}); using the NCCL exchange", file=sys.stderr)
+            ok = torch.zeros(1, device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if ok.item() == 0:
+            ctx.set_peer_gauges(None, None)
+            halo = "nccl"
+        torch.cuda.synchronize()
+        dist.barrier()
+
+    breakdown = os.environ.get("WB_BENCH_BREAKDOWN") == "1" and world > 1
+    bd_events = []
 
     def step():
+        if breakdown:
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+            ev[0].record(stream)
+            if halo == "peer":
+                dist.all_reduce(ready)
+            else:
+                plan.exchange(dU, dist)
+            ev[1].record(stream)
+            ctx.fg_phase1_dev(dU.data_ptr(), dsums.data_ptr()); ev[2].record(stream)
+            dist.all_reduce(dsums); ev[3].record(stream)
+            ctx.fg_phase2_dev(dsums.data_ptr(), dres.data_ptr(), dG.data_ptr()); ev[4].record(stream)
+            bd_events.append(ev)
+            return
         if world == 1:
             ctx.fg_dev(dU.data_ptr(), dres.data_ptr(), dG.data_ptr())
         else:
-            # the optimiser owns U slab-wise: fetch the neighbour gauges other ranks own (halo),
-            # evaluate the slab, reduce the spread sums
-            plan.exchange(dU, dist)
+            # the optimiser owns U slab-wise.  halo = peer: a one-element all-reduce stands in for
+            # "every rank has finished updating its rows" (in the optimiser loop the line-search
+            # reductions play that role), then phase 1 reads neighbour rows from peer memory inside
+            # its pack kernel.  halo = nccl: explicit exchange of the neighbour rows first.
+            if halo == "peer":
+                dist.all_reduce(ready)
+            else:
+                plan.exchange(dU, dist)
             ctx.fg_phase1_dev(dU.data_ptr(), dsums.data_ptr())
             dist.all_reduce(dsums)
             ctx.fg_phase2_dev(dsums.data_ptr(), dres.data_ptr(), dG.data_ptr())
@@ -264,7 +313,10 @@ def main():
             if world == 1:
                 return ctx.fg(hUn, want_f=True, G=hGn)        # wb200_fg: H2D U, compute, D2H f and G
             dU[k0:k1].copy_(hU, non_blocking=True)            # own slab host -> device
-            plan.exchange(dU, dist)                           # neighbour gauges over NVLink
+            if halo == "peer":
+                dist.all_reduce(ready)                        # rows of every rank are in place
+            else:
+                plan.exchange(dU, dist)                       # neighbour gauges over NVLink
             ctx.fg_phase1_dev(dU.data_ptr(), dsums.data_ptr())
             dist.all_reduce(dsums)
             ctx.fg_phase2_dev(dsums.data_ptr(), dres.data_ptr(), dG.data_ptr())
@@ -290,6 +342,14 @@ def main():
                "check_f": f_e2e, "api": "wb200_fg (host pointers, pinned)" if world == 1 else
                "per rank: H2D own U slab, halo exchange, phase1 / all-reduce / phase2, D2H own G slab"}
 
+    if breakdown:
+        torch.cuda.synchronize()
+        names = ["exchange", "phase1", "allreduce", "phase2"]
+        tot = np.zeros(4)
+        for ev in bd_events[-args.steps:]:
+            tot += [ev[i].elapsed_time(ev[i + 1]) for i in range(4)]
+        print(f"[rank {rank}] breakdown ms/step: " + ", ".join(f"{n} {t / args.steps:.3f}" for n, t in zip(names, tot)),
+              file=sys.stderr, flush=True)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -326,7 +386,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": dict(config, n_bvectors=nn, rotation_kernel=ctx.rotation_kernel,
-                           parallelism=f"k-slab x{world}", halo_k_per_rank=plan.n_halo, omega_check=omega_val),
+                           parallelism=f"k-slab x{world}", halo=halo, halo_k_per_rank=plan.n_halo, omega_check=omega_val),
             "e2e": e2e, "gpu_launches": int(launches), "clocks": cs.summary(), "roofline": roof}
 
     if cpu_sample is not None:

@@ -149,6 +149,25 @@ int wb200_project_tangent_dev(wb200_ctx* ctx, const double* dX, double* dG, int 
                               int count);
 int wb200_retract_dev(wb200_ctx* ctx, double* dX, int nrow, int ncol, int count, int* iters);
 
+/* ---- peer memory (NVLink) for k-sharded runs, one process per GPU -------------------------------
+ * Instead of a separate halo exchange, the gauge-packing kernel of the tensor path reads the rows
+ * U_{k+b} that another rank owns DIRECTLY from that rank's memory over NVLink (plain loads on a
+ * CUDA-IPC mapped pointer), fusing the neighbour-gauge exchange into the kernel that consumes it.
+ *   wb200_ipc_alloc : cudaMalloc + cudaIpcGetMemHandle (every rank allocates a FULL [nk_total][nw][nb]
+ *                     gauge array and owns the rows of its slab)
+ *   wb200_ipc_open  : map a peer's allocation (handle exchanged by the host, e.g. all_gather_object)
+ *   wb200_set_peer_gauges : U_ptrs[r] = device pointer of rank r's array as visible from this
+ *                     device (own rank: the local pointer), bounds[r] = first k of rank r's slab.
+ *                     Afterwards phase1 reads row k from the array of the rank that owns k.
+ * The caller orders the accesses: peers must have finished writing their rows before phase1 is
+ * enqueued (any collective after the update does), and must not overwrite them before every
+ * rank's phase1 has completed (the all-reduce of the sums between phase1 and phase2 does).       */
+int wb200_ipc_alloc(int device, size_t bytes, void** dptr, unsigned char handle[64]);
+int wb200_ipc_open(int device, const unsigned char handle[64], void** dptr);
+int wb200_ipc_close(int device, void* dptr);
+int wb200_ipc_free(int device, void* dptr);
+int wb200_set_peer_gauges(wb200_ctx* ctx, int world, const void* const* U_ptrs, const int32_t* bounds);
+
 /* ---- measurement helpers (bench.py) -------------------------------------------------------------
  * wb200_profile: when enabled, every launch of the four kernel classes below is bracketed by CUDA
  * events on the ctx's stream; wb200_profile_read synchronises, returns the summed milliseconds and

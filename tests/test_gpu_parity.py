@@ -341,3 +341,45 @@ def test_multi_wave_determinism_and_parity(w):
     MU_ref, _ = so.compute_MU_UtMU(Mh, st["kpb_k"], Uh)
     assert np.abs(MU.transpose(0, 1, 3, 2) - MU_ref).max() < 1e-13
     ctx.close()
+
+
+@pytest.mark.parametrize("nb,nw", [(64, 48), (12, 8)])
+def test_peer_gauge_reads_fused_into_phase1(w, nb, nw):
+    """k-sharded run where each rank's gauge array holds ONLY its own rows: phase 1 must fetch the
+    neighbour rows from the owning rank's array (peer pointers; two arrays on one GPU stand in for
+    two GPUs, the kernels cannot tell).  Covers the fused read in the tensor path's pack kernel
+    (nb = 64) and the halo-fetch kernel of the CUDA-core path (nb = 12)."""
+    import torch
+    st, M, U = w.synthetic.make_model_arrays("bcc", (4, 2, 2), nb, nw)
+    nk, nn = st["kpb_k"].shape
+    f_ref, G_ref = so.fg_maxloc(M, st["kpb_k"], st["bvec"], st["wb"], U)
+    bounds = [0, 6, 16]
+    Uabi = torch.from_numpy(w.api.to_abi_U(U)).cuda()
+    arrays = []
+    for r in range(2):
+        a = torch.full_like(Uabi, complex(float("nan"), float("nan")))
+        a[bounds[r]:bounds[r + 1]] = Uabi[bounds[r]:bounds[r + 1]]
+        arrays.append(a)
+    stream = torch.cuda.current_stream().cuda_stream
+    ctxs, sums = [], []
+    for r in range(2):
+        k0, k1 = bounds[r], bounds[r + 1]
+        c = w.Context(nb, nw, nk, nn, st["kpb_k"][k0:k1], st["bvec"][k0:k1], st["wb"],
+                      w.api.to_abi_M(M[k0:k1]), k_begin=k0, nk=k1 - k0)
+        c.set_stream(stream)
+        c.set_peer_gauges([a.data_ptr() for a in arrays], bounds)
+        s = torch.zeros(c.nsums, dtype=torch.float64, device="cuda")
+        c.fg_phase1_dev(arrays[r].data_ptr(), s.data_ptr())
+        ctxs.append(c)
+        sums.append(s)
+    total = sums[0] + sums[1]
+    G = torch.zeros((nk, nw, nb), dtype=torch.complex128, device="cuda")
+    res = torch.zeros(ctxs[0].nres, dtype=torch.float64, device="cuda")
+    for r, c in enumerate(ctxs):
+        c.fg_phase2_dev(total.data_ptr(), res.data_ptr(), G[bounds[r]:bounds[r + 1]].data_ptr())
+    torch.cuda.synchronize()
+    assert abs(res[5].item() - f_ref) < RTOL * abs(f_ref)
+    assert rel(G.cpu().numpy().transpose(0, 2, 1), G_ref) < RTOL
+    for c in ctxs:
+        c.set_peer_gauges(None, None)
+        c.close()

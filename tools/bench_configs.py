@@ -1,0 +1,48 @@
+"""GPU: time one spread+gradient evaluation (U resident) for every BASELINE config, and a device
+max_localize at config 3."""
+import sys, os, time, json, numpy as np, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import __graft_entry__ as ge
+w = ge.load_package()
+dev = torch.device("cuda", 0)
+out = {}
+for name in sys.argv[1:] or ["cfg2_cu_shape", "cfg3_nw32", "cfg5_2d_nw256", "cfg4_nw128"]:
+    lat, grid, nb, nw = w.synthetic.CONFIGS[name]
+    st = w.synthetic.make_stencil(w.synthetic.LATTICES[lat](), grid)
+    nk, nn = st["kpb_k"].shape
+    M = w.synthetic.make_overlaps_torch(st, nb, dev)
+    dU = w.synthetic.make_gauge_torch(nk, nb, nw, dev)
+    ctx = w.Context(nb, nw, nk, nn, st["kpb_k"], st["bvec"], st["wb"], M.data_ptr())
+    del M
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    res = torch.zeros(ctx.nres, dtype=torch.float64, device=dev)
+    G = torch.zeros((nk, nw, nb), dtype=torch.complex128, device=dev)
+    for _ in range(5):
+        ctx.fg_dev(dU.data_ptr(), res.data_ptr(), G.data_ptr())
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n = 20
+    ctx.profile(True)
+    e0.record()
+    for _ in range(n):
+        ctx.fg_dev(dU.data_ptr(), res.data_ptr(), G.data_ptr())
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    prof = {k: v[0] / n for k, v in ctx.profile_read().items()}
+    ctx.profile(False)
+    flops = 8.0 * nk * nn * nb * nb * nw
+    r = dict(kernel=ctx.rotation_kernel, nb=nb, nw=nw, nk=nk, nn=nn, ms=ms, evals_per_s=1e3 / ms,
+             tflops=flops / ms / 1e9, kernel_ms=prof, omega=res[0].item())
+    if name == "cfg3_nw32" or "--maxloc" in sys.argv:
+        hU = dU.cpu().numpy().copy()
+        t0 = time.perf_counter()
+        f, it, nfg = ctx.max_localize(hU, f_tol=1e-7, g_tol=1e-5, max_iter=200)
+        dt = time.perf_counter() - t0
+        r["max_localize"] = dict(f=f, iters=it, n_fg=nfg, seconds=dt, ms_per_fg=1e3 * dt / max(nfg, 1))
+        un = hU.transpose(0, 2, 1)
+        r["max_localize"]["unitarity"] = float(np.abs(np.conj(un.transpose(0, 2, 1)) @ un - np.eye(nw)).max())
+    out[name] = r
+    print(name, json.dumps(r), flush=True)
+    ctx.close(); del dU, G
+    torch.cuda.empty_cache()
+json.dump(out, open("gpurun_out/bench_configs.json", "w"), indent=1)

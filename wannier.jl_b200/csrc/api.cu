@@ -17,7 +17,7 @@ extern "C" void wb200_destroy(wb200_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     wb_dmma_plan_destroy(ctx);
-    void* ptrs[] = {ctx->d_need, ctx->d_kpb, ctx->d_kself, ctx->d_bvec, ctx->d_wb, ctx->d_M, ctx->d_r0,
+    void* ptrs[] = {(void*)ctx->d_peerU, ctx->d_need_owner, ctx->d_need, ctx->d_kpb, ctx->d_kself, ctx->d_bvec, ctx->d_wb, ctx->d_M, ctx->d_r0,
                     ctx->d_frozen, ctx->d_nfrozen, ctx->d_U, ctx->d_G, ctx->d_MU, ctx->d_N,
                     ctx->d_dN, ctx->d_fro, ctx->d_part, ctx->d_pmin, ctx->d_sums, ctx->d_res,
                     ctx->d_min, ctx->d_scal, ctx->d_tmp1, ctx->d_tmp2, ctx->d_XY, ctx->d_GXY};
@@ -112,6 +112,7 @@ extern "C" int wb200_create(wb200_ctx** out, int device, int nb, int nw, int nk_
         std::vector<int32_t> need;
         for (int k = 0; k < nk_total; k++) if (mark[k]) need.push_back(k);
         ctx->n_need = (int)need.size();
+        ctx->h_need = need;
         CREATE_CUDA(cudaMalloc(&ctx->d_need, sizeof(int32_t) * need.size()));
         CREATE_CUDA(cudaMemcpy(ctx->d_need, need.data(), sizeof(int32_t) * need.size(), cudaMemcpyHostToDevice));
     }
@@ -201,6 +202,9 @@ static int rotate(wb200_ctx* ctx, const cplx* dU) {
 extern "C" int wb200_fg_phase1_dev(wb200_ctx* ctx, const double* dU, double* dsums, int exact_split) {
     if (!ctx || !dU || !dsums) return WB200_ERR_ARG;
     cudaSetDevice(ctx->device);
+    // with peer gauges the tensor path reads remote rows inside its pack kernel; every other
+    // consumer (CUDA-core rotation, exact N) reads dU[k+b] directly, so fetch the halo rows first
+    if (ctx->d_peerU && (!ctx->dmma || exact_split)) WB_TRY(wb_halo_fetch(ctx, (cplx*)dU));
     WB_TRY(rotate(ctx, (const cplx*)dU));
     if (exact_split) WB_TRY(wb_form_N(ctx, (const cplx*)dU));
     WB_TRY(wb_pair_reduce(ctx, dsums));
@@ -623,5 +627,58 @@ extern "C" int wb200_probe_fp64_peak(int device, double* dmma_tflops, double* df
     if (cudaGetLastError() != cudaSuccess) return WB200_ERR_CUDA;
     if (dmma_tflops) *dmma_tflops = best_mma;
     if (dfma_tflops) *dfma_tflops = best_fma;
+    return WB200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// peer memory
+// ---------------------------------------------------------------------------------------------
+extern "C" int wb200_ipc_alloc(int device, size_t bytes, void** dptr, unsigned char handle[64]) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    if (!dptr || !handle || cudaSetDevice(device) != cudaSuccess) return WB200_ERR_ARG;
+    if (cudaMalloc(dptr, bytes) != cudaSuccess) return WB200_ERR_CUDA;
+    cudaIpcMemHandle_t h;
+    if (cudaIpcGetMemHandle(&h, *dptr) != cudaSuccess) { cudaFree(*dptr); *dptr = nullptr; return WB200_ERR_CUDA; }
+    memcpy(handle, &h, 64);
+    return WB200_OK;
+}
+extern "C" int wb200_ipc_open(int device, const unsigned char handle[64], void** dptr) {
+    if (!dptr || !handle || cudaSetDevice(device) != cudaSuccess) return WB200_ERR_ARG;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    return cudaIpcOpenMemHandle(dptr, h, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess ? WB200_OK : WB200_ERR_CUDA;
+}
+extern "C" int wb200_ipc_close(int device, void* dptr) {
+    if (cudaSetDevice(device) != cudaSuccess) return WB200_ERR_ARG;
+    return cudaIpcCloseMemHandle(dptr) == cudaSuccess ? WB200_OK : WB200_ERR_CUDA;
+}
+extern "C" int wb200_ipc_free(int device, void* dptr) {
+    if (cudaSetDevice(device) != cudaSuccess) return WB200_ERR_ARG;
+    return cudaFree(dptr) == cudaSuccess ? WB200_OK : WB200_ERR_CUDA;
+}
+
+extern "C" int wb200_set_peer_gauges(wb200_ctx* ctx, int world, const void* const* U_ptrs,
+                                     const int32_t* bounds) {
+    if (!ctx) return WB200_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    if (ctx->d_peerU) { cudaFree((void*)ctx->d_peerU); ctx->d_peerU = nullptr; }
+    if (ctx->d_need_owner) { cudaFree(ctx->d_need_owner); ctx->d_need_owner = nullptr; }
+    ctx->peer_world = 0;
+    if (world <= 0 || !U_ptrs) return WB200_OK;   // back to purely local reads
+    if (!bounds || bounds[0] != 0 || bounds[world] != ctx->nk_total) {
+        ctx->err = "wb200_set_peer_gauges: bounds must run from 0 to nk_total";
+        return WB200_ERR_ARG;
+    }
+    std::vector<int32_t> owner(ctx->n_need);
+    for (int i = 0; i < ctx->n_need; i++) {
+        int r = 0;
+        while (r + 1 < world && ctx->h_need[i] >= bounds[r + 1]) r++;
+        owner[i] = r;
+    }
+    WB_CUDA(ctx, cudaMalloc((void**)&ctx->d_peerU, sizeof(void*) * world));
+    WB_CUDA(ctx, cudaMalloc(&ctx->d_need_owner, sizeof(int32_t) * ctx->n_need));
+    WB_CUDA(ctx, cudaMemcpy((void*)ctx->d_peerU, U_ptrs, sizeof(void*) * world, cudaMemcpyHostToDevice));
+    WB_CUDA(ctx, cudaMemcpy(ctx->d_need_owner, owner.data(), sizeof(int32_t) * ctx->n_need, cudaMemcpyHostToDevice));
+    ctx->peer_world = world;
     return WB200_OK;
 }

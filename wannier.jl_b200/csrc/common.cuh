@@ -86,6 +86,11 @@ struct wb200_ctx {
     int32_t* d_kself = nullptr;  // [nk*nn] global index of k for every pair
     int32_t* d_need = nullptr;   // [n_need] sorted global k indices the slab reads (own + k+b)
     int n_need = 0;
+    std::vector<int32_t> h_need;
+    // peer gauges (wb200_set_peer_gauges): row k is read from the array of the rank owning k
+    const cplx** d_peerU = nullptr;   // [world] device pointers (device array)
+    int32_t* d_need_owner = nullptr;  // [n_need] owner rank of need[i]
+    int peer_world = 0;
     double* d_bvec = nullptr;    // [nk][nn][3]
     double* d_wb = nullptr;      // [nn]
     cplx* d_M = nullptr;         // [nk][nn][nb*nb] col-major (generic path / exact N)
@@ -186,6 +191,7 @@ int wb_finalize(wb200_ctx* ctx, const double* dsums, double* dres);
 int wb_grad(wb200_ctx* ctx, const double* dsums, cplx* dG, int ka, int kb);
 int wb_ensure_tmp(wb200_ctx* ctx, size_t e1, size_t e2);
 int wb_ensure_N(wb200_ctx* ctx);
+int wb_halo_fetch(wb200_ctx* ctx, cplx* dU);   // copy the remote rows of `need` into the local array (CUDA-core path)
 
 // ---- stiefel.cu ----
 int wb_project_tangent_dev(wb200_ctx* ctx, const cplx* dX, cplx* dG, int nrow, int ncol, int count);

@@ -425,6 +425,28 @@ int wb_grad(wb200_ctx* ctx, const double* dsums, cplx* dG, int ka, int kb) {
     return WB200_OK;
 }
 
+// copy the rows of `need` that another rank owns from its (peer-mapped) array into the local one
+__global__ void __launch_bounds__(256) halo_fetch_kernel(long long mat, int k_begin, int k_end,
+                                                         const int32_t* __restrict__ need,
+                                                         const int32_t* __restrict__ owner,
+                                                         const cplx* const* __restrict__ peerU,
+                                                         cplx* __restrict__ U) {
+    const long long kg = need[blockIdx.x];
+    if (kg >= k_begin && kg < k_end) return;   // own row
+    const cplx* src = peerU[owner[blockIdx.x]] + kg * mat;
+    cplx* dst = U + kg * mat;
+    for (long long e = threadIdx.x; e < mat; e += blockDim.x) dst[e] = src[e];
+}
+
+int wb_halo_fetch(wb200_ctx* ctx, cplx* dU) {
+    ProfScope ps(ctx, 0);
+    halo_fetch_kernel<<<ctx->n_need, 256, 0, ctx->stream>>>((long long)ctx->nb * ctx->nw, ctx->k_begin,
+                                                            ctx->k_begin + ctx->nk, ctx->d_need,
+                                                            ctx->d_need_owner, ctx->d_peerU, dU);
+    WB_LAUNCH_CHECK(ctx);
+    return WB200_OK;
+}
+
 int wb_ensure_tmp(wb200_ctx* ctx, size_t e1, size_t e2) {
     if (e1 > ctx->tmp1_elems) {
         if (ctx->d_tmp1) cudaFree(ctx->d_tmp1);

@@ -118,9 +118,14 @@ __global__ void tile_overlaps_kernel(int nb, int WM, int KC, int nch, const cplx
 //   (Br, Bi-Br, Br+Bi) of nt = 0..1 with l = c*KC + ks*4 + lane%4, n = ct*NC + wn*16 + nt*8 + lane/4.
 __global__ void __launch_bounds__(256) pack_gauge_kernel(int nb, int nw, int WN, int KC, int nch, int nct,
                                                          const int32_t* __restrict__ need,
+                                                         const int32_t* __restrict__ owner,
+                                                         const cplx* const* __restrict__ peerU,
                                                          const cplx* __restrict__ U,
                                                          double* __restrict__ Up) {
     const long long kg = need[blockIdx.x];   // only the k-points this slab reads (own + neighbours)
+    // k-sharded runs: a row another rank owns is read straight from that rank's memory over NVLink
+    // (peer-mapped pointer) — the halo exchange is fused into the packing
+    if (peerU) U = peerU[owner[blockIdx.x]];
     const int ct = blockIdx.y;
     const int KS = KC / 4;
     const int items = WN * KS * 32;              // per chunk
@@ -514,7 +519,9 @@ int wb_pack_dmma(wb200_ctx* ctx, const cplx* dU, int ja, int jb) {
     dim3 g((unsigned)(jb - ja), (unsigned)p->nct);
     ProfScope ps(ctx, 0);
     pack_gauge_kernel<<<g, 256, 0, ctx->stream>>>(ctx->nb, ctx->nw, p->WN, p->KC, p->nch, p->nct,
-                                                  ctx->d_need + ja, dU, p->d_Up);
+                                                  ctx->d_need + ja,
+                                                  ctx->d_need_owner ? ctx->d_need_owner + ja : nullptr,
+                                                  ctx->d_peerU, dU, p->d_Up);
     WB_LAUNCH_CHECK(ctx);
     return WB200_OK;
 }

@@ -23,6 +23,7 @@ SYMBOLS = [
     "wb200_disentangle", "wb200_nsums", "wb200_nres", "wb200_fg_phase1_dev", "wb200_fg_phase2_dev",
     "wb200_fg_dev", "wb200_min_abs_diag", "wb200_project_tangent_dev", "wb200_retract_dev",
     "wb200_profile", "wb200_profile_read", "wb200_probe_fp64_peak",
+    "wb200_ipc_alloc", "wb200_ipc_open", "wb200_ipc_close", "wb200_ipc_free", "wb200_set_peer_gauges",
 ]
 
 FLAG_DEFAULT = 0
@@ -85,6 +86,11 @@ def load():
     lib.wb200_min_abs_diag.argtypes = [vp, pd]
     lib.wb200_project_tangent_dev.argtypes = [vp, pd, pd, i32, i32, i32]
     lib.wb200_retract_dev.argtypes = [vp, pd, i32, i32, i32, pd]
+    lib.wb200_ipc_alloc.argtypes = [i32, C.c_size_t, C.POINTER(vp), pd]
+    lib.wb200_ipc_open.argtypes = [i32, pd, C.POINTER(vp)]
+    lib.wb200_ipc_close.argtypes = [i32, vp]
+    lib.wb200_ipc_free.argtypes = [i32, vp]
+    lib.wb200_set_peer_gauges.argtypes = [vp, i32, pd, pd]
     lib.wb200_profile.argtypes = [vp, i32]
     lib.wb200_profile_read.argtypes = [vp, pd, pd]
     lib.wb200_probe_fp64_peak.argtypes = [i32, pd, pd]
@@ -192,6 +198,15 @@ class Context:
         fr = np.ascontiguousarray(frozen, dtype=np.uint8)
         _check_array(fr, np.uint8, self.nk * self.nb, "frozen")
         self._ck(self._lib.wb200_set_frozen(self._h, _addr(fr)))
+
+    def set_peer_gauges(self, ptrs, bounds):
+        """ptrs[r]: device address of rank r's full gauge array as mapped on this device; None resets."""
+        if ptrs is None:
+            self._ck(self._lib.wb200_set_peer_gauges(self._h, 0, None, None))
+            return
+        p = np.asarray(ptrs, dtype=np.uint64)
+        b = np.ascontiguousarray(bounds, dtype=np.int32)
+        self._ck(self._lib.wb200_set_peer_gauges(self._h, len(p), _addr(p), _addr(b)))
 
     def profile(self, enable):
         self._ck(self._lib.wb200_profile(self._h, int(enable)))
@@ -307,3 +322,39 @@ def probe_fp64_peak(device=0):
     if st != 0:
         raise WB200Error(st, "wb200_probe_fp64_peak failed")
     return a.value, b.value
+
+
+def ipc_alloc(device, nbytes):
+    """(device address, 64-byte handle) of a cudaMalloc allocation that peers can map."""
+    lib = load()
+    ptr = C.c_void_p()
+    h = (C.c_ubyte * 64)()
+    st = lib.wb200_ipc_alloc(device, nbytes, C.byref(ptr), C.addressof(h))
+    if st != 0:
+        raise WB200Error(st, "wb200_ipc_alloc failed")
+    return ptr.value, bytes(h)
+
+
+def ipc_open(device, handle):
+    lib = load()
+    ptr = C.c_void_p()
+    buf = (C.c_ubyte * 64).from_buffer_copy(handle)
+    st = lib.wb200_ipc_open(device, C.addressof(buf), C.byref(ptr))
+    if st != 0:
+        raise WB200Error(st, "wb200_ipc_open failed (CUDA IPC not available between these processes?)")
+    return ptr.value
+
+
+def ipc_close(device, ptr):
+    load().wb200_ipc_close(device, ptr)
+
+
+def ipc_free(device, ptr):
+    load().wb200_ipc_free(device, ptr)
+
+
+class DeviceArray:
+    """Lets torch (or cupy) wrap a raw device allocation: torch.as_tensor(DeviceArray(...), device=...)."""
+
+    def __init__(self, ptr, shape, typestr="<c16"):
+        self.__cuda_array_interface__ = dict(shape=tuple(shape), typestr=typestr, data=(int(ptr), False), version=2)
