@@ -383,3 +383,73 @@ def test_peer_gauge_reads_fused_into_phase1(w, nb, nw):
     for c in ctxs:
         c.set_peer_gauges(None, None)
         c.close()
+
+
+def test_full_size_north_star_properties(w):
+    """BASELINE config 4 at full size (n_wann = 128, 16^3 k, 12 b: 49 152 pairs, 13 GB of overlaps).
+    The oracle cannot run this in seconds, so parity is checked through size-independent
+    properties plus an oracle spot check on a few k-points."""
+    import torch
+    free, _ = torch.cuda.mem_get_info()
+    if free < 90e9:
+        pytest.skip("needs ~80 GB of free HBM")
+    lat, grid, nb, nw = w.synthetic.CONFIGS["cfg4_nw128"]
+    st = w.synthetic.make_stencil(w.synthetic.LATTICES[lat](), grid)
+    nk, nn = st["kpb_k"].shape
+    dev = torch.device("cuda", 0)
+    M = w.synthetic.make_overlaps_torch(st, nb, dev)
+    dU = w.synthetic.make_gauge_torch(nk, nb, nw, dev)
+    spot = np.array([0, 1377, 4095])
+    M_spot = M[torch.as_tensor(spot, device=dev)].transpose(2, 3).cpu().numpy()      # [3, nn, m, l]
+    ctx = w.Context(nb, nw, nk, nn, st["kpb_k"], st["bvec"], st["wb"], M.data_ptr())
+    del M
+    torch.cuda.empty_cache()
+    assert ctx.rotation_kernel == "dmma-fp64"
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    res = torch.zeros(ctx.nres, dtype=torch.float64, device=dev)
+    G = torch.zeros((nk, nw, nb), dtype=torch.complex128, device=dev)
+
+    def fg(U, want_G=True, exact=False):
+        ctx.fg_dev(U.data_ptr(), res.data_ptr(), G.data_ptr() if want_G else None, exact_split=exact)
+        torch.cuda.synchronize()
+        return res.cpu().numpy().copy()
+
+    a = fg(dU)
+    G0 = G.clone()
+    Om, OI, OOD, OD, Ot = a[:5]
+    omega_n, r = a[8:8 + nw], a[8 + nw:8 + 4 * nw].reshape(nw, 3)
+    # (1) the decomposition closes and is consistent
+    assert abs(omega_n.sum() - Om) < 1e-10 * Om
+    assert abs(OI + OOD + OD - Om) < 1e-10 * Om and abs(Ot - (Om - OI)) < 1e-10 * Om
+    assert OI > 0 and OOD > 0
+    # (2) one-GEMM shortcut (||N||_F = ||MU||_F for unitary U) == full N (second GEMM)
+    b = fg(dU, want_G=False, exact=True)
+    assert np.abs(a[:5] - b[:5]).max() < 1e-10 * Om
+    # (3) gauge covariance under a global unitary W: Omega_I invariant; under diagonal phases D
+    #     Omega, omega_n, r invariant and G(U D) = G(U) D
+    g = torch.Generator(device="cpu").manual_seed(7)
+    Wm = torch.linalg.qr(torch.view_as_complex(torch.randn((nw, nw, 2), generator=g, dtype=torch.float64)))[0].to(dev)
+    # abi image of U_k is [n][m] = U_k^T, so (U W)^T = W^T U^T
+    c = fg(torch.matmul(Wm.T.contiguous(), dU).contiguous(), want_G=False, exact=True)
+    assert abs(c[1] - b[1]) < 1e-10 * Om
+    ph = torch.exp(2j * np.pi * torch.rand(nw, generator=g, dtype=torch.float64)).to(dev)
+    d = fg((dU * ph[None, :, None]).contiguous())
+    assert abs(d[0] - Om) < 1e-10 * Om and np.abs(d[8:8 + 4 * nw] - a[8:8 + 4 * nw]).max() < 1e-9
+    assert (G - G0 * ph[None, :, None]).abs().max().item() < 1e-10 * G0.abs().max().item()
+    # (4) the gradient is the derivative: central difference along a random direction
+    Z = torch.view_as_complex(torch.randn((nk, nw, nb, 2), generator=torch.Generator(device="cpu").manual_seed(8),
+                                          dtype=torch.float64)).to(dev)
+    h = 1e-6
+    fp = fg(dU + h * Z, want_G=False)[5]
+    fm = fg(dU - h * Z, want_G=False)[5]
+    an = torch.sum(G0.real * Z.real + G0.imag * Z.imag).item()
+    assert abs((fp - fm) / (2 * h) - an) < 1e-6 * abs(an)
+    # (5) oracle spot check on three k-points: MU, diag N and G_k (with the global r of the GPU run)
+    fg(dU)
+    Uh = dU.cpu().numpy().transpose(0, 2, 1)
+    kpb = st["kpb_k"][spot]
+    MU_ref, N_ref = so.compute_MU_UtMU_gathered(M_spot, Uh[spot], Uh[kpb])
+    G_ref = so.grad_from_MU_N_r(MU_ref, N_ref, st["bvec"][spot], st["wb"], r, nk)
+    Gh = G0[torch.as_tensor(spot, device=dev)].cpu().numpy().transpose(0, 2, 1)
+    assert np.abs(Gh - G_ref).max() < 1e-10 * np.abs(G_ref).max()
+    ctx.close()
