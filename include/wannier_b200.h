@@ -149,6 +149,24 @@ int wb200_project_tangent_dev(wb200_ctx* ctx, const double* dX, double* dG, int 
                               int count);
 int wb200_retract_dev(wb200_ctx* ctx, double* dX, int nrow, int ncol, int count, int* iters);
 
+/* ---- by-products of the rotation (same U_k^H M_kb U_{k+b}, different epilogue) -------------------
+ * wb200_omega_local      = omega_local(stencil, M, U) (src/spread.jl:522-548): loc [nk].
+ * wb200_fg_rotate        = f / g! of get_fg!_rotate (src/localization/opt_rotate.jl:12-81): one global
+ *                          rotation W [nw*nw] applied at every k (the caller pre-rotates M and uses
+ *                          identity gauges, opt_rotate.jl:113-116); G [nw*nw] = sum_k G_k.
+ * wb200_opt_rotate       = opt_rotate(model; ...) (opt_rotate.jl:97-154): L-BFGS on one Stiefel matrix.
+ * wb200_position_op      = position_op(stencil, M, U) (src/spread.jl:674-716): R [nw][nw][3] complex
+ *                          (Julia Matrix{Vec3{ComplexF64}} image: component fastest, then m, then n).
+ * wb200_berry_connection = compute_berry_connection_kspace (src/spread.jl:747-793):
+ *                          A [nk][nw][nw][3] complex, same per-k image.                           */
+int wb200_omega_local(wb200_ctx* ctx, const double* U, double* loc);
+int wb200_fg_rotate(wb200_ctx* ctx, const double* W, double* f, double* G);
+int wb200_opt_rotate(wb200_ctx* ctx, double* W_inout, double f_tol, double g_tol, int max_iter,
+                     int history, double* f_final, int* iters, int* n_fg);
+int wb200_position_op(wb200_ctx* ctx, const double* U, double* R);
+int wb200_berry_connection(wb200_ctx* ctx, const double* U, double* A, int imlog_diag,
+                           int force_hermiticity);
+
 /* ---- peer memory (NVLink) for k-sharded runs, one process per GPU -------------------------------
  * Instead of a separate halo exchange, the gauge-packing kernel of the tensor path reads the rows
  * U_{k+b} that another rank owns DIRECTLY from that rank's memory over NVLink (plain loads on a

@@ -391,6 +391,26 @@ def position_op(M, kpb_k, bvec, wb, U):
     return R / (-1j * nk)
 
 
+def fg_rotate(M, kpb_k, bvec, wb, W):
+    """f and g! of get_fg!_rotate for identity base gauges (src/localization/opt_rotate.jl:12-81):
+    U_k = W for every k; G_W = sum_k G_k (the comment at :38-42 says exactly that)."""
+    nk = M.shape[0]
+    U = np.broadcast_to(W, (nk,) + W.shape).copy()
+    f, G = fg_maxloc(M, kpb_k, bvec, wb, U)
+    return f, G.sum(axis=0)
+
+
+def opt_rotate(M, kpb_k, bvec, wb, U0, **kw):
+    """opt_rotate(model) (opt_rotate.jl:97-154): pre-rotate M by U0, optimise one W from identity."""
+    N = transform_gauge(M, kpb_k, U0)
+    nw = U0.shape[2]
+    fg = lambda W: fg_rotate(N, kpb_k, bvec, wb, W[0])
+    fg1 = lambda W: (lambda f, G: (f, G[None]))(*fg(W))
+    W, f, it, hist = lbfgs_stiefel(fg1, np.eye(nw, dtype=complex)[None], stiefel_retract,
+                                   stiefel_project_tangent, **kw)
+    return W[0], f, it
+
+
 # --------------------------------------------------------------------------
 # Riemannian L-BFGS driver (stands in for Optim.jl at max_localize.jl:73-84)
 # --------------------------------------------------------------------------

@@ -443,7 +443,9 @@ def test_full_size_north_star_properties(w):
     fp = fg(dU + h * Z, want_G=False)[5]
     fm = fg(dU - h * Z, want_G=False)[5]
     an = torch.sum(G0.real * Z.real + G0.imag * Z.imag).item()
-    assert abs((fp - fm) / (2 * h) - an) < 1e-6 * abs(an)
+    diag = dict(f0=Om, fp=fp, fm=fm, an=an, fp_again=fg(dU + h * Z, want_G=False)[5],
+                f0_again=fg(dU, want_G=False)[5], f0_copy=fg(dU + 0.0 * Z, want_G=False)[5])
+    assert abs((fp - fm) / (2 * h) - an) < 1e-6 * abs(an), diag
     # (5) oracle spot check on three k-points: MU, diag N and G_k (with the global r of the GPU run)
     fg(dU)
     Uh = dU.cpu().numpy().transpose(0, 2, 1)
@@ -453,3 +455,38 @@ def test_full_size_north_star_properties(w):
     Gh = G0[torch.as_tensor(spot, device=dev)].cpu().numpy().transpose(0, 2, 1)
     assert np.abs(Gh - G_ref).max() < 1e-10 * np.abs(G_ref).max()
     ctx.close()
+
+
+def test_next_rows_omega_local_position_berry_opt_rotate(w, valence, silicon):
+    """SURVEY 8f 'next' rows: by-products of the same rotation, each against the oracle."""
+    from test_oracle_golden import W_OPTROT_REF
+    for d, nw in ((valence, 4), (silicon, 8)):
+        st = w.KspaceStencil(d["recip"], d["kpoints"], d["wb"], d["kpb_k"], d["kpb_G"])
+        U = d["U"]
+        args = oracle_args(d)
+        assert rel(w.omega_local(st, d["M"], U), so.omega_local(d["M"], d["kpb_k"], d["wb"], U)) < 1e-12
+        assert rel(w.position_op(st, d["M"], U), so.position_op(*args, U)) < 1e-12
+        for imlog in (True, False):
+            for herm in (True, False):
+                A = w.compute_berry_connection_kspace(st, d["M"], U, imlog_diag=imlog, force_hermiticity=herm)
+                assert rel(A, so.berry_connection_kspace(*args, U, imlog, herm)) < 1e-12
+    # opt_rotate (test/localization/opt_rotate.jl): gradient vs oracle, optimum vs the reference's Wmin
+    st = w.KspaceStencil(valence["recip"], valence["kpoints"], valence["wb"], valence["kpb_k"], valence["kpb_G"])
+    args = oracle_args(valence)
+    model = w.Model(valence["lattice"], st, valence["M"], valence["U"])
+    f, g = w.get_fg_rotate(model)
+    N = so.transform_gauge(valence["M"], valence["kpb_k"], valence["U"])
+    for W0 in (np.eye(4, dtype=complex), valence["W1"]):
+        G = np.zeros((4, 4), dtype=complex)
+        g(G, W0)
+        f_ref, G_ref = so.fg_rotate(N, *args[1:], W0)
+        assert abs(f(W0) - f_ref) < RTOL * abs(f_ref) and rel(G, G_ref) < RTOL
+    f.cache.close()
+    model = w.Model(valence["lattice"], st, valence["M"], valence["U_ptg"])
+    W, info = w.opt_rotate(model, f_tol=1e-12, g_tol=1e-8, max_iter=300, return_info=True)
+    f_ref = so.omega(*args, valence["U_ptg"] @ so.stiefel_retract(W_OPTROT_REF))["Omega"]
+    assert abs(info["f"] - f_ref) < 1e-6 and info["f"] <= f_ref + 1e-9
+    assert abs(so.omega(*args, valence["U_ptg"] @ W)["Omega"] - info["f"]) < 1e-10
+    with pytest.raises(ValueError):
+        w.opt_rotate(w.Model(silicon["lattice"], w.KspaceStencil(silicon["recip"], silicon["kpoints"], silicon["wb"],
+                                                                silicon["kpb_k"], silicon["kpb_G"]), silicon["M"], silicon["U"]))

@@ -115,3 +115,31 @@ def test_max_localize_converges_to_reference_optimum(valence):
     assert abs(sp["OmegaOD"] - ref[2]) < 1e-8
     assert abs(sp["OmegaTilde"] - ref[3]) < 1e-8
     assert np.abs(np.conj(U.transpose(0, 2, 1)) @ U - np.eye(4)).max() < 1e-12
+
+
+# Wref literal of test/localization/opt_rotate.jl:44-49 (opt_rotate from the parallel-transport gauge)
+W_OPTROT_REF = np.array([
+    [0.49473+0.0355699j, 0.0673789-0.511771j, 0.418917+0.104404j, -0.478045-0.26946j],
+    [0.194747-0.371381j, 0.71448+0.0268801j, -0.419172-0.274175j, -0.232225+0.090227j],
+    [-0.633051-0.179746j, 0.360712+0.121724j, 0.6137-0.012567j, -0.212654-0.000510533j],
+    [0.26149-0.276926j, 0.185667-0.207231j, 0.382741-0.198633j, 0.768156+0.0388423j]])
+
+
+def test_opt_rotate_matches_reference_Wmin(valence):
+    # test/localization/opt_rotate.jl:36-51: the spread reached by our driver equals the spread of
+    # the reference's Wmin (W itself is only defined up to column phases / permutations)
+    args = (valence["M"], valence["kpb_k"], valence["bvec"], valence["wb"])
+    U0 = valence["U_ptg"]
+    W, f, it = so.opt_rotate(*args, U0, f_tol=1e-12, g_tol=1e-8, max_iter=300)
+    f_ref = so.omega(*args, U0 @ so.stiefel_retract(W_OPTROT_REF))["Omega"]
+    assert abs(f - f_ref) < 1e-6          # Wref is printed with 6 digits
+    assert f <= f_ref + 1e-9
+    # gradient of the single-rotation functional vs finite differences (opt_rotate.jl:9-34)
+    N = so.transform_gauge(valence["M"], valence["kpb_k"], valence["U"])
+    rng = np.random.default_rng(4)
+    for W0 in (np.eye(4, dtype=complex), valence["W1"]):
+        _, G = so.fg_rotate(N, *args[1:], W0)
+        d = rng.standard_normal((4, 4)) + 1j * rng.standard_normal((4, 4))
+        h = 1e-5
+        fd = (so.fg_rotate(N, *args[1:], W0 + h * d)[0] - so.fg_rotate(N, *args[1:], W0 - h * d)[0]) / (2 * h)
+        assert abs(fd - np.real(np.vdot(G, d))) < 1e-6 * max(1.0, abs(fd))

@@ -8,5 +8,6 @@ from . import lib, api, synthetic, sharding  # noqa: F401
 from .api import (KspaceStencil, Model, Spread, SpreadCenter, SpreadPenalty, CenterSpreadPenalty,  # noqa: F401
                   Cache, omega, omega_grad, omega_center, center, compute_MU_UtMU, transform_gauge,
                   get_fg_maxloc, max_localize, get_fg_disentangle, disentangle, X_Y_to_U, X_Y_to_XY,
-                  XY_to_X_Y, U_to_X_Y)
+                  XY_to_X_Y, U_to_X_Y, omega_local, position_op, compute_berry_connection_kspace,
+                  get_fg_rotate, opt_rotate, merge_gauge)
 from .lib import Context, WB200Error  # noqa: F401

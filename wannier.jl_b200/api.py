@@ -267,6 +267,84 @@ def transform_gauge(M, kstencil_or_kpb, U, cache=None):
     return np.ascontiguousarray(N.transpose(0, 1, 3, 2))
 
 
+def omega_local(*args, cache=None):
+    """omega_local(stencil, M, U) -> loc[nk]   (src/spread.jl:522-548)"""
+    p, cache, U, own = _with_cache(args, cache)
+    try:
+        return cache.ctx.omega_local(to_abi_U(U))
+    finally:
+        if own:
+            cache.close()
+
+
+def position_op(*args, cache=None):
+    """position_op(model[, U]) / position_op(stencil, M, U) -> R[m, n, alpha]  (src/spread.jl:674-736)"""
+    p, cache, U, own = _with_cache(args, cache)
+    try:
+        return np.ascontiguousarray(cache.ctx.position_op(to_abi_U(U)).transpose(1, 0, 2))
+    finally:
+        if own:
+            cache.close()
+
+
+def compute_berry_connection_kspace(*args, imlog_diag=True, force_hermiticity=True, cache=None):
+    """compute_berry_connection_kspace(model[, gauges]; imlog_diag, force_hermiticity)
+    -> A[k, m, n, alpha]   (src/spread.jl:747-801)"""
+    p, cache, U, own = _with_cache(args, cache)
+    try:
+        A = cache.ctx.berry_connection(to_abi_U(U), imlog_diag, force_hermiticity)
+        return np.ascontiguousarray(A.transpose(0, 2, 1, 3))
+    finally:
+        if own:
+            cache.close()
+
+
+# ------------------------------------------------------------------------------------------
+# opt_rotate: one global rotation W
+# ------------------------------------------------------------------------------------------
+def merge_gauge(U, W):
+    """U_k W for every k"""
+    return np.asarray(U) @ np.asarray(W)
+
+
+def _rotated_cache(model):
+    """model2 of opt_rotate.jl:113-116: overlaps pre-rotated by the model's gauges, identity gauges."""
+    if model.n_bands != model.n_wannier:
+        raise ValueError("n_bands != n_wann, run instead disentanglement?")      # opt_rotate.jl:101
+    N = transform_gauge(model.overlaps, model.kstencil, model.gauges)
+    return Cache(model.kstencil, N, model.n_wannier)
+
+
+def get_fg_rotate(model):
+    """get_fg!_rotate(model) -> (f, g!)  (src/localization/opt_rotate.jl:12-81); f(W) -> Omega,
+    g(G, W) writes G[m, n] in place."""
+    cache = _rotated_cache(model)
+    nw = model.n_wannier
+
+    def f(W):
+        return cache.ctx.fg_rotate(np.ascontiguousarray(np.asarray(W, dtype=np.complex128).T))
+
+    def g(G, W):
+        Gb = np.empty((nw, nw), dtype=np.complex128)
+        cache.ctx.fg_rotate(np.ascontiguousarray(np.asarray(W, dtype=np.complex128).T), want_f=False, G=Gb)
+        G[...] = Gb.T
+
+    f.cache = cache
+    return f, g
+
+
+def opt_rotate(model, f_tol=1e-7, g_tol=1e-5, max_iter=200, history_size=3, return_info=False):
+    """opt_rotate(model; ...) -> Wmin[m, n]   (src/localization/opt_rotate.jl:97-154)"""
+    cache = _rotated_cache(model)
+    try:
+        W = np.eye(model.n_wannier, dtype=np.complex128)
+        f, iters, nfg = cache.ctx.opt_rotate(W, f_tol, g_tol, max_iter, history_size)
+    finally:
+        cache.close()
+    Wm = np.ascontiguousarray(W.T)
+    return (Wm, dict(f=f, iterations=iters, n_fg=nfg)) if return_info else Wm
+
+
 # ------------------------------------------------------------------------------------------
 # max_localize
 # ------------------------------------------------------------------------------------------

@@ -121,6 +121,10 @@ extern "C" int wb200_create(wb200_ctx** out, int device, int nb, int nw, int nk_
     CREATE_CUDA(cudaMemcpy(ctx->d_bvec, bvec_cart, sizeof(double) * pairs * 3, cudaMemcpyHostToDevice));
     CREATE_CUDA(cudaMemcpy(ctx->d_wb, bweights, sizeof(double) * nn, cudaMemcpyHostToDevice));
     CREATE_CUDA(cudaMemcpy(ctx->d_M, M, sizeof(cplx) * pairs * nb * nb, cudaMemcpyDefault));  // host or device
+    // M may be a device pointer: a device-to-device cudaMemcpy returns before the copy has run and
+    // is ordered only on the legacy default stream, while everything below runs on the ctx's own
+    // non-blocking stream.  Drain the device once (one-off cost at creation).
+    CREATE_CUDA(cudaDeviceSynchronize());
     ctx->h_wb.assign(bweights, bweights + nn);
     ctx->h_kpb.assign(kpb_k, kpb_k + pairs);
     ctx->wsum = 0.0;
@@ -508,6 +512,31 @@ extern "C" int wb200_max_localize(wb200_ctx* ctx, double* U, double f_tol, doubl
     }
     if (s == WB200_OK) s = wb_lbfgs(ctx, 0, dx, f_tol, g_tol, max_iter, history, f_final, iters, n_fg);
     if (s == WB200_OK && (cudaMemcpyAsync(U, dx, sizeof(cplx) * e, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+                          cudaStreamSynchronize(ctx->stream) != cudaSuccess)) {
+        ctx->err = "D2H copy failed"; s = WB200_ERR_CUDA;
+    }
+    cudaFree(dx);
+    return s;
+}
+
+extern "C" int wb200_opt_rotate(wb200_ctx* ctx, double* W, double f_tol, double g_tol, int max_iter,
+                                int history, double* f_final, int* iters, int* n_fg) {
+    if (!ctx || !W) return WB200_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    WB_TRY(require_single_slab(ctx, "wb200_opt_rotate"));
+    if (ctx->nb != ctx->nw) {   // opt_rotate.jl:101
+        ctx->err = "n_bands != n_wann, run instead disentanglement?";
+        return WB200_ERR_ARG;
+    }
+    const size_t e = (size_t)ctx->nw * ctx->nw;
+    cplx* dx = nullptr;
+    WB_CUDA(ctx, cudaMalloc(&dx, sizeof(cplx) * e));
+    int s = WB200_OK;
+    if (cudaMemcpyAsync(dx, W, sizeof(cplx) * e, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) {
+        ctx->err = "H2D copy failed"; s = WB200_ERR_CUDA;
+    }
+    if (s == WB200_OK) s = wb_lbfgs(ctx, 2, dx, f_tol, g_tol, max_iter, history, f_final, iters, n_fg);
+    if (s == WB200_OK && (cudaMemcpyAsync(W, dx, sizeof(cplx) * e, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
                           cudaStreamSynchronize(ctx->stream) != cudaSuccess)) {
         ctx->err = "D2H copy failed"; s = WB200_ERR_CUDA;
     }

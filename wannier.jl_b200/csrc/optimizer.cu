@@ -14,20 +14,24 @@
 #include <deque>
 
 int wb_fg_device(wb200_ctx* ctx, const cplx* dU, double* dres, cplx* dG, int exact_split);  // api.cu
+int wb_fg_rotate_device(wb200_ctx* ctx, const cplx* dW, double* dres, cplx* dGW);           // extras.cu
 
 namespace {
 
 struct Problem {
     wb200_ctx* ctx;
-    int mode;     // 0: U on (Stiefel nb x nw)^nk ; 1: XY on (Stiefel nw x nw  x  Stiefel nb x nw)^nk
+    int mode;     // 0: U on (Stiefel nb x nw)^nk ; 1: XY on (Stiefel nw x nw  x  Stiefel nb x nw)^nk ;
+                  // 2: one global W on Stiefel nw x nw (opt_rotate)
     size_t n;     // doubles per vector
     int n_fg = 0;
 
     int retract(cplx* x) {
+        if (mode == 2) return wb_retract_dev(ctx, x, ctx->nw, ctx->nw, 1, nullptr);
         if (mode == 0) return wb_retract_dev(ctx, x, ctx->nb, ctx->nw, ctx->nk, nullptr);
         return wb_retract_xy(ctx, x);
     }
     int project(const cplx* x, cplx* g) {
+        if (mode == 2) return wb_project_tangent_dev(ctx, x, g, ctx->nw, ctx->nw, 1);
         if (mode == 0) return wb_project_tangent_dev(ctx, x, g, ctx->nb, ctx->nw, ctx->nk);
         return wb_project_xy(ctx, x, g);
     }
@@ -36,6 +40,8 @@ struct Problem {
         n_fg++;
         if (mode == 0) {
             WB_TRY(wb_fg_device(ctx, x, ctx->d_res, g, 0));
+        } else if (mode == 2) {
+            WB_TRY(wb_fg_rotate_device(ctx, x, ctx->d_res, g));
         } else {
             WB_TRY(wb_xy_to_u(ctx, x, ctx->d_U));
             WB_TRY(wb_fg_device(ctx, ctx->d_U, ctx->d_res, ctx->d_G, 0));
@@ -55,8 +61,9 @@ struct Problem {
 int wb_lbfgs(wb200_ctx* ctx, int mode, cplx* dx, double f_tol, double g_tol, int max_iter,
              int history, double* f_final, int* iters_out, int* n_fg_out) {
     Problem P{ctx, mode, 0};
-    const size_t ncplx = (mode == 0) ? (size_t)ctx->nk * ctx->nb * ctx->nw
-                                     : (size_t)ctx->nk * ((size_t)ctx->nw * ctx->nw + (size_t)ctx->nb * ctx->nw);
+    const size_t ncplx = (mode == 2) ? (size_t)ctx->nw * ctx->nw
+                         : (mode == 0) ? (size_t)ctx->nk * ctx->nb * ctx->nw
+                                       : (size_t)ctx->nk * ((size_t)ctx->nw * ctx->nw + (size_t)ctx->nb * ctx->nw);
     P.n = 2 * ncplx;
     const size_t n = P.n;
     const int m = history > 0 ? history : 3;

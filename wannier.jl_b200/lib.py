@@ -23,6 +23,7 @@ SYMBOLS = [
     "wb200_disentangle", "wb200_nsums", "wb200_nres", "wb200_fg_phase1_dev", "wb200_fg_phase2_dev",
     "wb200_fg_dev", "wb200_min_abs_diag", "wb200_project_tangent_dev", "wb200_retract_dev",
     "wb200_profile", "wb200_profile_read", "wb200_probe_fp64_peak",
+    "wb200_omega_local", "wb200_fg_rotate", "wb200_opt_rotate", "wb200_position_op", "wb200_berry_connection",
     "wb200_ipc_alloc", "wb200_ipc_open", "wb200_ipc_close", "wb200_ipc_free", "wb200_set_peer_gauges",
 ]
 
@@ -86,6 +87,11 @@ def load():
     lib.wb200_min_abs_diag.argtypes = [vp, pd]
     lib.wb200_project_tangent_dev.argtypes = [vp, pd, pd, i32, i32, i32]
     lib.wb200_retract_dev.argtypes = [vp, pd, i32, i32, i32, pd]
+    lib.wb200_omega_local.argtypes = [vp, pd, pd]
+    lib.wb200_fg_rotate.argtypes = [vp, pd, pd, pd]
+    lib.wb200_opt_rotate.argtypes = [vp, pd, dbl, dbl, i32, i32, pd, pd, pd]
+    lib.wb200_position_op.argtypes = [vp, pd, pd]
+    lib.wb200_berry_connection.argtypes = [vp, pd, pd, i32, i32]
     lib.wb200_ipc_alloc.argtypes = [i32, C.c_size_t, C.POINTER(vp), pd]
     lib.wb200_ipc_open.argtypes = [i32, pd, C.POINTER(vp)]
     lib.wb200_ipc_close.argtypes = [i32, vp]
@@ -289,6 +295,37 @@ class Context:
         self._ck(self._lib.wb200_disentangle(self._h, _addr(XY), f_tol, g_tol, max_iter, history,
                                              C.addressof(f), C.addressof(it), C.addressof(nfg)))
         return f.value, it.value, nfg.value
+
+    def omega_local(self, U):
+        loc = np.zeros(self.nk)
+        self._ck(self._lib.wb200_omega_local(self._h, self._u(U), _addr(loc)))
+        return loc
+
+    def fg_rotate(self, W, want_f=True, G=None):
+        _check_array(W, np.complex128, self.nw * self.nw, "W")
+        if G is not None:
+            _check_array(G, np.complex128, self.nw * self.nw, "G")
+        f = C.c_double(0.0)
+        self._ck(self._lib.wb200_fg_rotate(self._h, _addr(W), C.addressof(f) if want_f else None, _addr(G)))
+        return f.value if want_f else None
+
+    def opt_rotate(self, W, f_tol=1e-7, g_tol=1e-5, max_iter=200, history=3):
+        _check_array(W, np.complex128, self.nw * self.nw, "W")
+        f, it, nfg = C.c_double(0.0), C.c_int(0), C.c_int(0)
+        self._ck(self._lib.wb200_opt_rotate(self._h, _addr(W), f_tol, g_tol, max_iter, history,
+                                            C.addressof(f), C.addressof(it), C.addressof(nfg)))
+        return f.value, it.value, nfg.value
+
+    def position_op(self, U):
+        R = np.empty((self.nw, self.nw, 3), dtype=np.complex128)      # [n][m][a]
+        self._ck(self._lib.wb200_position_op(self._h, self._u(U), _addr(R)))
+        return R
+
+    def berry_connection(self, U, imlog_diag=True, force_hermiticity=True):
+        A = np.empty((self.nk, self.nw, self.nw, 3), dtype=np.complex128)   # [k][n][m][a]
+        self._ck(self._lib.wb200_berry_connection(self._h, self._u(U), _addr(A), int(imlog_diag),
+                                                  int(force_hermiticity)))
+        return A
 
     # -- device-pointer entry points (raw addresses, e.g. torch.Tensor.data_ptr()) -----------
     def fg_phase1_dev(self, dU, dsums, exact_split=False):
