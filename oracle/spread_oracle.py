@@ -471,30 +471,30 @@ def lbfgs_stiefel(fg, x0, retract, project, f_tol=1e-7, g_tol=1e-5, max_iter=200
             if fn > f + c1 * alpha * dphi0 or (best is not None and fn >= f_lo and lo > 0):
                 hi = alpha
             elif abs(dn) <= -c2 * dphi0:
-                best = (fn, gn, xn)
+                best = (fn, gn, xn, alpha)
                 break
             elif dn >= 0:
                 hi = alpha
             else:
                 lo, f_lo, d_lo = alpha, fn, dn
-                best = (fn, gn, xn)
+                best = (fn, gn, xn, alpha)
             if hi is None:
                 alpha *= 2.0
             else:
                 alpha = 0.5 * (lo + hi)
         if best is None:
             break
-        fn, gn, xn = best
-        s = project(xn - x, xn)
-        y = gn - project(g, xn)
+        fn, gn, xn, a_best = best
+        # secant pair as Optim.jl's LBFGS forms it on a manifold (update_state! / update_h!):
+        # dx = alpha * s (the step before retraction), dg = g_new - g_previous with each gradient
+        # projected at its own point; the history is not transported.
+        s = a_best * d
+        y = gn - g
         sy = _rdot(s, y)
         if sy > 1e-14 * np.sqrt(_rdot(s, s) * _rdot(y, y)):
             S.append(s); Yh.append(y); rho.append(1.0 / sy)
             if len(S) > m:
                 S.pop(0); Yh.pop(0); rho.pop(0)
-        # transport history to the new tangent space by projection
-        S = [project(v, xn) for v in S]
-        Yh = [project(v, xn) for v in Yh]
         df = abs(fn - f)
         x, f_prev, f, g = xn, f, fn, gn
         hist.append(f)

@@ -36,7 +36,11 @@ def oracle_args(d):
 # ---------------------------------------------------------------------------------------------
 def test_valence_spread_and_known_answers(w, valence):
     ctx = make_ctx(w, fixture_stencil(valence), valence["M"], 4)
-    assert ctx.rotation_kernel == "cuda-core-fp64"
+    assert ctx.rotation_kernel == "dmma-fp64"      # nb <= 32: warp-pair-per-pair tensor kernel (zero padded)
+    ctx_cc = make_ctx(w, fixture_stencil(valence), valence["M"], 4, flags=w.lib.FLAG_NO_TENSOR)
+    assert ctx_cc.rotation_kernel == "cuda-core-fp64"
+    check_spread(ctx_cc.spread(w.api.to_abi_U(valence["U"])), so.omega(*oracle_args(valence), valence["U"]))
+    ctx_cc.close()
     for U in (valence["U"], valence["U_ptg"], valence["U"] @ valence["W1"]):
         got = ctx.spread(w.api.to_abi_U(U))
         check_spread(got, so.omega(*oracle_args(valence), U))
@@ -211,6 +215,7 @@ def test_disentangle_driver(w, silicon):
     ("fcc", (3, 3, 3), 18, 9),        # config 2 shape (CUDA-core kernel)
     ("bcc", (3, 3, 3), 32, 32),       # config 3 shape
     ("cubic", (1, 1, 1), 5, 3),       # single k-point, all neighbours are the point itself
+    ("cubic", (2, 2, 2), 260, 20),    # nb > 256: CUDA-core kernel only
 ])
 def test_synthetic_both_kernels(w, lat, grid, nb, nw):
     st, M, U = w.synthetic.make_model_arrays(lat, grid, nb, nw)
@@ -235,7 +240,7 @@ def test_synthetic_both_kernels(w, lat, grid, nb, nw):
         f2 = ctx.fg(w.api.to_abi_U(U), G=G2)
         assert f2 == f and np.array_equal(G, G2)
         ctx.close()
-    assert kernels == ({"cuda-core-fp64", "dmma-fp64"} if 32 < nb <= 256 else {"cuda-core-fp64"})
+    assert kernels == ({"cuda-core-fp64", "dmma-fp64"} if nb <= 256 else {"cuda-core-fp64"})
 
 
 def test_unitary_shortcut_vs_exact_split(w):

@@ -201,6 +201,12 @@ int wb_project_xy(wb200_ctx* ctx, const cplx* dXY, cplx* dG);
 int wb_xy_to_u(wb200_ctx* ctx, const cplx* dXY, cplx* dU);
 int wb_gu_to_gxy(wb200_ctx* ctx, const cplx* dXY, const cplx* dGU, cplx* dGXY);
 
+// ---- stiefel_small.cu ----
+bool wb_small_applicable(int nrow, int ncol);
+int wb_retract_small(wb200_ctx* ctx, cplx* dX, int nrow, int ncol, int ld, long long stride, int count);
+int wb_project_small(wb200_ctx* ctx, const cplx* dX, cplx* dG, int nrow, int ncol, int ld, long long stride,
+                     int count);
+
 // ---- vecops (stiefel.cu) ----
 int wb_dot(wb200_ctx* ctx, const double* a, const double* b, size_t n, double* out_host);
 int wb_absmax(wb200_ctx* ctx, const double* a, size_t n, double* out_host);

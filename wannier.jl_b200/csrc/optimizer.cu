@@ -137,7 +137,7 @@ int wb_lbfgs(wb200_ctx* ctx, int mode, cplx* dx, double f_tol, double g_tol, int
         const double c1 = 1e-4, c2 = 0.9;
         double lo = 0.0, hi = -1.0, f_lo = f;
         bool have_best = false;
-        double f_best = 0.0;
+        double f_best = 0.0, a_best = 0.0;
         // the best trial point so far lives in (xb, gb); (xn, gn) is the current trial
         for (int ls = 0; ls < 30; ls++) {
             // xn = retract(x + alpha d)
@@ -155,26 +155,25 @@ int wb_lbfgs(wb200_ctx* ctx, int mode, cplx* dx, double f_tol, double g_tol, int
                 hi = alpha;
             } else if (fabs(dn) <= -c2 * dphi0) {
                 std::swap(xn, xb); std::swap(gn, gb);
-                f_best = fn; have_best = true;
+                f_best = fn; a_best = alpha; have_best = true;
                 break;
             } else if (dn >= 0.0) {
                 hi = alpha;
             } else {
                 lo = alpha; f_lo = fn;
                 std::swap(xn, xb); std::swap(gn, gb);
-                f_best = fn; have_best = true;
+                f_best = fn; a_best = alpha; have_best = true;
             }
             alpha = (hi < 0.0) ? 2.0 * alpha : 0.5 * (lo + hi);
         }
         if (!have_best) break;
-        // s = project(xb - x, xb); y = gb - project(g, xb)
+        // secant pair as Optim.jl's LBFGS forms it on a manifold (update_state! / update_h!):
+        // dx = alpha * s (the step before retraction), dg = g_new - g_previous, each gradient
+        // projected at its own point; the history is not transported.
         const int slot = free_slots.back();
         free_slots.pop_back();
-        WB_TRY(wb_axpbyz(ctx, 1.0, xb, -1.0, x, S(slot), n));
-        WB_TRY(P.project((cplx*)xb, (cplx*)S(slot)));
-        WB_TRY(wb_axpbyz(ctx, 1.0, g, 0.0, g, td, n));
-        WB_TRY(P.project((cplx*)xb, (cplx*)td));
-        WB_TRY(wb_axpbyz(ctx, 1.0, gb, -1.0, td, Y(slot), n));
+        WB_TRY(wb_axpbyz(ctx, a_best, d, 0.0, d, S(slot), n));
+        WB_TRY(wb_axpbyz(ctx, 1.0, gb, -1.0, g, Y(slot), n));
         double sy = 0.0, ss = 0.0, yy = 0.0;
         WB_TRY(wb_dot(ctx, S(slot), Y(slot), n, &sy));
         WB_TRY(wb_dot(ctx, S(slot), S(slot), n, &ss));
@@ -185,11 +184,6 @@ int wb_lbfgs(wb200_ctx* ctx, int mode, cplx* dx, double f_tol, double g_tol, int
             if ((int)slots.size() > m) { free_slots.push_back(slots.front()); slots.pop_front(); }
         } else {
             free_slots.push_back(slot);
-        }
-        // transport the history to the new tangent space by projection
-        for (int s : slots) {
-            WB_TRY(P.project((cplx*)xb, (cplx*)S(s)));
-            WB_TRY(P.project((cplx*)xb, (cplx*)Y(s)));
         }
         const double df = fabs(f_best - f);
         // x <- xb, g <- gb

@@ -29,6 +29,7 @@
 #include "common.cuh"
 
 struct DmmaPlan {
+    bool small = false;           // nb <= 32: rotate_small_kernel (no smem, warp pair per (k,b) pair)
     int WM = 0, WN = 0, KC = 0;   // warp grid (8 consumer warps), k-chunk
     int NB = 0, NC = 0;           // padded rows, columns per CTA
     int nct = 0;                  // column tiles = ceil(nw / NC)
@@ -287,10 +288,16 @@ rotate_dmma_kernel(int nb, int nw, int nn, int nch, int nct, int k_begin, int k_
             const int mt = e >> 2, nt = (e >> 1) & 1, j = e & 1;
             const int m = wm * 32 + mt * 8 + g, n = n0 + wn * 16 + nt * 8 + 2 * t + j;
             const cplx xv = x[e];
+#ifndef WB_EPI_NOSTG
             if (m < nb && n < nw) mu[m + (long long)n * nb] = xv;
+#else
+            if (xv.x == 1.2345e300) mu[m + (long long)n * nb] = xv;   // ablation build only
+#endif
+#ifndef WB_EPI_NOMATH
             cfma_conj(d[nt][j], uk[e * 32], xv);
             f = fma(xv.x, xv.x, f);
             f = fma(xv.y, xv.y, f);
+#endif
         }
     };
     auto epi_end = [&]() {
@@ -419,6 +426,116 @@ rotate_dmma_kernel(int nb, int nw, int nn, int nch, int nct, int k_begin, int k_
 #endif
 }
 
+// ---- small shapes (nb <= 32): one pair per WARP PAIR, operands straight from global ------------
+// A 32 x 32 (zero padded) pair needs no shared memory at all: the fragment-ordered images of M and
+// of the packed gauge are read with coalesced LDG.128 directly into DMMA fragments (one k-step
+// ahead), warp 2i computes columns 0-15 and warp 2i+1 columns 16-31 of pair i (the second read of
+// the A image hits L1), and each warp covers all 32 rows, so diag(N) is complete inside the warp.
+// 8 warps (4 pairs) per CTA, no barriers, no producer.
+__global__ void __launch_bounds__(256, 1)
+rotate_small_kernel(int nb, int nw, int nn, long long pair0, long long pair_end, int k_begin,
+                    const int32_t* __restrict__ kpb, const double* __restrict__ Mt,
+                    const double* __restrict__ Up, const cplx* __restrict__ U, cplx* __restrict__ MU,
+                    cplx* __restrict__ dN, double* __restrict__ frop) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long p = pair0 + (long long)blockIdx.x * 4 + (warp >> 1);
+    const int half = warp & 1;
+    if (p >= pair_end) return;
+    const int g = lane >> 2, t = lane & 3;
+    const long long kl = p / nn, kp = kpb[p];
+    const cplx* A = reinterpret_cast<const cplx*>(Mt) + p * 1536 + lane;               // [(ks*6 + j)*32]
+    const cplx* B = reinterpret_cast<const cplx*>(Up) + kp * 1536 + (half * 24) * 32 + lane;  // [(ks*3 + j)*32]
+
+    double p1[4][2][2], p2[4][2][2], p3[4][2][2];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 2; j++)
+#pragma unroll
+            for (int e = 0; e < 2; e++) p1[i][j][e] = p2[i][j][e] = p3[i][j][e] = 0.0;
+    double qa[2][12], qb[2][6];
+    auto load = [&](int ks, double (&a)[12], double (&b)[6]) {
+#pragma unroll
+        for (int j = 0; j < 6; j++) {
+            const cplx y = __ldg(A + (ks * 6 + j) * 32);
+            a[2 * j] = y.x;
+            a[2 * j + 1] = y.y;
+        }
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            const cplx y = __ldg(B + (ks * 3 + j) * 32);
+            b[2 * j] = y.x;
+            b[2 * j + 1] = y.y;
+        }
+    };
+    load(0, qa[0], qb[0]);
+#pragma unroll
+    for (int ks = 0; ks < 8; ks++) {
+        const int cur = ks & 1;
+        if (ks + 1 < 8) load(ks + 1, qa[cur ^ 1], qb[cur ^ 1]);
+#pragma unroll
+        for (int mt = 0; mt < 4; mt++)
+#pragma unroll
+            for (int nt = 0; nt < 2; nt++) {
+                dmma884(p1[mt][nt][0], p1[mt][nt][1], qa[cur][3 * mt + 2], qb[cur][3 * nt]);
+                dmma884(p2[mt][nt][0], p2[mt][nt][1], qa[cur][3 * mt], qb[cur][3 * nt + 1]);
+                dmma884(p3[mt][nt][0], p3[mt][nt][1], qa[cur][3 * mt + 1], qb[cur][3 * nt + 2]);
+            }
+    }
+    // epilogue: MU, diag(U_k^H MU) (complete: the warp holds all rows), ||MU||_F^2 of this half
+    cplx* mu = MU + p * (long long)nb * nw;
+    const cplx* Uk = U + (long long)(k_begin + kl) * nb * nw;
+    cplx d[2][2];
+    double f = 0.0;
+#pragma unroll
+    for (int nt = 0; nt < 2; nt++)
+#pragma unroll
+        for (int j = 0; j < 2; j++) d[nt][j] = make_double2(0.0, 0.0);
+#pragma unroll
+    for (int mt = 0; mt < 4; mt++)
+#pragma unroll
+        for (int nt = 0; nt < 2; nt++)
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                const cplx x = make_double2(p1[mt][nt][j] - p3[mt][nt][j], p1[mt][nt][j] + p2[mt][nt][j]);
+                const int m = mt * 8 + g, n = half * 16 + nt * 8 + 2 * t + j;
+                if (m < nb && n < nw) {
+                    mu[m + (long long)n * nb] = x;
+                    cfma_conj(d[nt][j], Uk[m + (long long)n * nb], x);
+                }
+                f = fma(x.x, x.x, f);
+                f = fma(x.y, x.y, f);
+            }
+#pragma unroll
+    for (int nt = 0; nt < 2; nt++)
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+#pragma unroll
+            for (int o = 4; o < 32; o <<= 1) {
+                d[nt][j].x += __shfl_xor_sync(0xffffffffu, d[nt][j].x, o);
+                d[nt][j].y += __shfl_xor_sync(0xffffffffu, d[nt][j].y, o);
+            }
+        }
+    f = warp_sum(f);
+    if (g == 0) {
+#pragma unroll
+        for (int nt = 0; nt < 2; nt++)
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                const int n = half * 16 + nt * 8 + 2 * t + j;
+                if (n < nw) dN[p * nw + n] = d[nt][j];
+            }
+    }
+    if (lane == 0) frop[p * 2 + half] = f;
+}
+
+// fro[pair] = frop[pair][0] + frop[pair][1]
+__global__ void fro_pair_sum_kernel(long long pair0, long long pair_end, const double* __restrict__ frop,
+                                    double* __restrict__ fro) {
+    const long long p = pair0 + blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (p < pair_end) fro[p] = frop[2 * p] + frop[2 * p + 1];
+}
+
 // dN[pair][n] = sum_wm dNp[pair][wm][n];  fro[pair] = sum frop[pair][:]   (fixed order)
 __global__ void __launch_bounds__(128) combine_partials_kernel(int nw, int WM, int nfro, long long pair_off,
                                                                const cplx* __restrict__ dNp,
@@ -475,9 +592,10 @@ int launch_rotate(wb200_ctx* ctx, const cplx* dU, int ka, int kb) {
 
 int wb_dmma_plan_create(wb200_ctx* ctx, const double* /*hM*/) {
     const int nb = ctx->nb, nw = ctx->nw;
-    if (nb <= 32 || nb > 256) return WB200_OK;  // CUDA-core path
+    if (nb > 256 || (nb <= 32 && nw > 32)) return WB200_OK;  // CUDA-core path
     DmmaPlan* p = new DmmaPlan();
-    if (nb <= 64) { p->WM = 2; p->WN = 4; p->KC = 16; p->smem = smem_bytes<WB_CFG_64>(); }
+    if (nb <= 32) { p->small = true; p->WM = 1; p->WN = 2; p->KC = 32; p->smem = 0; }
+    else if (nb <= 64) { p->WM = 2; p->WN = 4; p->KC = 16; p->smem = smem_bytes<WB_CFG_64>(); }
     else if (nb <= 128) { p->WM = 4; p->WN = 2; p->KC = 8; p->smem = smem_bytes<WB_CFG_128>(); }
     else { p->WM = 8; p->WN = 1; p->KC = 8; p->smem = smem_bytes<WB_CFG_256>(); }
     p->NB = 32 * p->WM;
@@ -490,8 +608,8 @@ int wb_dmma_plan_create(wb200_ctx* ctx, const double* /*hM*/) {
     const size_t pairs = (size_t)ctx->nk * ctx->nn;
     WB_CUDA(ctx, cudaMalloc(&p->d_Mt, sizeof(double) * pairs * p->nch * p->a_stage));
     WB_CUDA(ctx, cudaMalloc(&p->d_Up, sizeof(double) * (size_t)ctx->nk_total * p->nct * p->nch * p->b_stage));
-    WB_CUDA(ctx, cudaMalloc(&p->d_dNp, sizeof(cplx) * pairs * p->WM * nw));
-    WB_CUDA(ctx, cudaMalloc(&p->d_frop, sizeof(double) * pairs * p->nct * 8));
+    if (!p->small) WB_CUDA(ctx, cudaMalloc(&p->d_dNp, sizeof(cplx) * pairs * p->WM * nw));
+    WB_CUDA(ctx, cudaMalloc(&p->d_frop, sizeof(double) * pairs * (p->small ? 2 : p->nct * 8)));
     // re-lay-out M (already uploaded to d_M) into the A-operand image; d_M is then released:
     // the tensor path never reads the plain layout again.
     dim3 grid((unsigned)pairs, (unsigned)p->nch);
@@ -528,6 +646,20 @@ int wb_pack_dmma(wb200_ctx* ctx, const cplx* dU, int ja, int jb) {
 
 int wb_rotate_dmma(wb200_ctx* ctx, const cplx* dU, int ka, int kb) {
     DmmaPlan* p = ctx->dmma;
+    if (p->small) {
+        const long long p0 = (long long)ka * ctx->nn, p1 = (long long)kb * ctx->nn;
+        {
+            ProfScope ps(ctx, 1);
+            rotate_small_kernel<<<(unsigned)((p1 - p0 + 3) / 4), 256, 0, ctx->stream>>>(
+                ctx->nb, ctx->nw, ctx->nn, p0, p1, ctx->k_begin, ctx->d_kpb, p->d_Mt, p->d_Up, dU, ctx->d_MU,
+                ctx->d_dN, p->d_frop);
+        }
+        WB_LAUNCH_CHECK(ctx);
+        ProfScope ps2(ctx, 2);
+        fro_pair_sum_kernel<<<(unsigned)((p1 - p0 + 255) / 256), 256, 0, ctx->stream>>>(p0, p1, p->d_frop, ctx->d_fro);
+        WB_LAUNCH_CHECK(ctx);
+        return WB200_OK;
+    }
     {
         ProfScope ps(ctx, 1);
         if (p->WM == 2) WB_TRY((launch_rotate<WB_CFG_64>(ctx, dU, ka, kb)));

@@ -31,6 +31,7 @@ __global__ void hermitize_kernel(int n, long long total, cplx* __restrict__ S) {
 
 static int project_strided(wb200_ctx* ctx, const cplx* dX, cplx* dG, int nrow, int ncol, int ld,
                            long long stride, int count) {
+    if (wb_small_applicable(nrow, ncol)) return wb_project_small(ctx, dX, dG, nrow, ncol, ld, stride, count);
     WB_TRY(wb_ensure_tmp(ctx, (size_t)count * ncol * ncol, 0));
     ZgemmArgs a{};
     a.m = ncol; a.n = ncol; a.k = nrow;
@@ -114,6 +115,10 @@ __global__ void copy_strided_kernel(int nrow, int ncol, int ld, long long stride
 
 static int retract_strided(wb200_ctx* ctx, cplx* dX, int nrow, int ncol, int ld, long long stride,
                            int count, int* iters_out) {
+    if (wb_small_applicable(nrow, ncol)) {   // fused single-launch kernel, convergence tested on the device
+        if (iters_out) *iters_out = -1;
+        return wb_retract_small(ctx, dX, nrow, ncol, ld, stride, count);
+    }
     const int MAXIT = 100;
     const double TOL = 2e-8;  // quadratic convergence: the update applied at err<2e-8 leaves ~1e-15
     WB_TRY(wb_ensure_tmp(ctx, (size_t)count * ncol * ncol, (size_t)count * nrow * ncol));
