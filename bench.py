@@ -369,8 +369,8 @@ def main():
             "achieved": rot_flops / (rot_ms_avg * 1e-3) / 1e12, "peak": peak_tf, "unit": "TFLOP/s",
             "frac": rot_flops / (rot_ms_avg * 1e-3) / 1e12 / peak_tf,
             # DRAM read+write bytes per launch from the committed ncu --set full capture of this exact
-            # workload at N = 1 (profiles/r1c_ncu_full_summary.json); not re-measured at run time
-            "traffic": 41.81e9 if (args.config == "cfg4_nw128" and world == 1 and tensor) else None,
+            # workload at N = 1 (profiles/r1e_ncu_full_summary.json); not re-measured at run time
+            "traffic": 41.79e9 if (args.config == "cfg4_nw128" and world == 1 and tensor) else None,
             "peak_source": "FP64 %s peak measured live by wb200_probe_fp64_peak (MEASURED_PEAKS.json has "
                            "no FP64 figure; tcgen05 has no f64 kind)" % ("DMMA.8x8x4" if tensor else "DFMA"),
             "ms_per_launch": rot_ms_avg, "launches_timed": rot_n,
