@@ -186,6 +186,17 @@ int wb200_ipc_close(int device, void* dptr);
 int wb200_ipc_free(int device, void* dptr);
 int wb200_set_peer_gauges(wb200_ctx* ctx, int world, const void* const* U_ptrs, const int32_t* bounds);
 
+/* ---- sharded optimiser: caller-supplied collective ------------------------------------------------
+ * With one process per GPU the library does not own a communicator.  The host registers a callback
+ * that all-reduces `count` doubles at device pointer `dptr` IN PLACE over all ranks, enqueued on
+ * `cuda_stream` (op 0 = sum, 1 = max) — ncclAllReduce from Julia/C, torch.distributed from Python.
+ * With the callback and wb200_set_peer_gauges in place, wb200_max_localize runs on a k-slab ctx:
+ * U_inout is then the SLAB [nk][nw][nb]; every rank calls it collectively with the same arguments.
+ * Vectors of the L-BFGS live slab-local; scalar products, |g|_inf, the spread sums and a one-element
+ * "gauges are in place" reduction before each evaluation go through the callback.               */
+typedef void (*wb200_allreduce_fn)(void* dptr, int count, int op, void* cuda_stream, void* user);
+int wb200_set_allreduce(wb200_ctx* ctx, wb200_allreduce_fn fn, void* user);
+
 /* ---- measurement helpers (bench.py) -------------------------------------------------------------
  * wb200_profile: when enabled, every launch of the four kernel classes below is bracketed by CUDA
  * events on the ctx's stream; wb200_profile_read synchronises, returns the summed milliseconds and

@@ -1,0 +1,85 @@
+"""Multi-GPU tests (-m gpu; skipped with fewer than 2 GPUs): one process per GPU over NCCL, gauges
+shared through CUDA-IPC peer memory, the L-BFGS driver running k-sharded through the caller-supplied
+all-reduce.  The sharded run must reach the same spread as the single-GPU run."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, case, out):
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as ge
+    w = ge.load_package()
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        lat, grid, nb = case
+        st, M, U = w.synthetic.make_model_arrays(lat, grid, nb, nb, eps=0.02)
+        nk, nn = st["kpb_k"].shape
+        bounds = w.sharding.slab_bounds(nk, world)
+        k0, k1 = bounds[rank], bounds[rank + 1]
+        ctx = w.Context(nb, nb, nk, nn, st["kpb_k"][k0:k1], st["bvec"][k0:k1], st["wb"],
+                        w.api.to_abi_M(M[k0:k1]), device=rank, k_begin=k0, nk=k1 - k0)
+        ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+        ptr, handle = w.lib.ipc_alloc(rank, 16 * nk * nb * nb)
+        handles = [None] * world
+        dist.all_gather_object(handles, handle)
+        ptrs = [ptr if r == rank else w.lib.ipc_open(rank, handles[r]) for r in range(world)]
+        ctx.set_peer_gauges(ptrs, bounds)
+        ctx.set_allreduce(w.sharding.torch_allreduce(dist, dev))
+        Uslab = w.api.to_abi_U(U[k0:k1])
+        f, it, nfg = ctx.max_localize(Uslab, f_tol=1e-10, g_tol=1e-7, max_iter=40)
+        torch.cuda.synchronize()
+        dist.barrier()
+        out[rank] = (f, it, nfg, Uslab.copy())
+        ctx.set_allreduce(None)
+        ctx.set_peer_gauges(None, None)
+        ctx.close()
+        for r in range(world):
+            if r != rank:
+                w.lib.ipc_close(rank, ptrs[r])
+        dist.barrier()
+        w.lib.ipc_free(rank, ptr)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("case", [("bcc", (4, 2, 2), 16), ("cubic", (4, 2, 2), 64)])
+def test_sharded_max_localize_matches_single_gpu(w, case):
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from oracle import spread_oracle as so
+    lat, grid, nb = case
+    st, M, U = w.synthetic.make_model_arrays(lat, grid, nb, nb, eps=0.02)
+    nk, nn = st["kpb_k"].shape
+    ctx = w.Context(nb, nb, nk, nn, st["kpb_k"], st["bvec"], st["wb"], w.api.to_abi_M(M))
+    U1 = w.api.to_abi_U(U)
+    f1, it1, nfg1 = ctx.max_localize(U1, f_tol=1e-10, g_tol=1e-7, max_iter=40)
+    ctx.close()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(2, _free_port(), case, out), nprocs=2, join=True)
+    (fa, ita, nfga, Ua), (fb, itb, nfgb, Ub) = out[0], out[1]
+    assert fa == fb and ita == itb and nfga == nfgb            # same control flow on every rank
+    assert ita == it1 and abs(fa - f1) < 1e-9 * abs(f1)        # same trajectory as one GPU
+    Ush = np.concatenate([Ua, Ub], axis=0)
+    assert np.abs(Ush - U1).max() < 1e-8
+    f_check = so.omega(M, st["kpb_k"], st["bvec"], st["wb"], w.api.from_abi_U(Ush))["Omega"]
+    assert abs(f_check - fa) < 1e-9 * abs(fa)

@@ -224,6 +224,22 @@ extern "C" int wb200_fg_phase2_dev(wb200_ctx* ctx, const double* dsums, double* 
 }
 
 int wb_fg_device(wb200_ctx* ctx, const cplx* dU, double* dres, cplx* dG, int exact_split) {
+    if (ctx->allreduce && ctx->peer_self) {
+        // k-sharded evaluation: dU is this rank's SLAB.  Put it into the rank's rows of the shared
+        // full-size gauge array, make sure every rank has done so (a one-element reduction on the
+        // same stream), let phase 1 read the neighbour rows from peer memory, reduce the sums.
+        const size_t mat = (size_t)ctx->nb * ctx->nw;
+        cplx* rows = ctx->peer_self + (size_t)ctx->k_begin * mat;
+        if (dU != rows)
+            WB_CUDA(ctx, cudaMemcpyAsync(rows, dU, sizeof(cplx) * mat * ctx->nk, cudaMemcpyDeviceToDevice,
+                                         ctx->stream));
+        WB_CUDA(ctx, cudaMemsetAsync(ctx->d_scal + 2, 0, sizeof(double), ctx->stream));
+        ctx->allreduce(ctx->d_scal + 2, 1, 0, (void*)ctx->stream, ctx->allreduce_user);
+        WB_TRY(wb200_fg_phase1_dev(ctx, (const double*)ctx->peer_self, ctx->d_sums, exact_split));
+        ctx->allreduce(ctx->d_sums, ctx->nsums(), 0, (void*)ctx->stream, ctx->allreduce_user);
+        WB_TRY(wb200_fg_phase2_dev(ctx, ctx->d_sums, dres, (double*)dG));
+        return WB200_OK;
+    }
     WB_TRY(wb200_fg_phase1_dev(ctx, (const double*)dU, ctx->d_sums, exact_split));
     WB_TRY(wb200_fg_phase2_dev(ctx, ctx->d_sums, dres, (double*)dG));
     return WB200_OK;
@@ -498,7 +514,7 @@ extern "C" int wb200_max_localize(wb200_ctx* ctx, double* U, double f_tol, doubl
                                   int history, double* f_final, int* iters, int* n_fg) {
     if (!ctx || !U) return WB200_ERR_ARG;
     cudaSetDevice(ctx->device);
-    WB_TRY(require_single_slab(ctx, "wb200_max_localize"));
+    if (!(ctx->allreduce && ctx->peer_self)) WB_TRY(require_single_slab(ctx, "wb200_max_localize"));
     if (ctx->nb != ctx->nw) {  // max_localize.jl:52-53
         ctx->err = "n_bands != n_wann, run instead disentanglement?";
         return WB200_ERR_ARG;
@@ -693,6 +709,8 @@ extern "C" int wb200_set_peer_gauges(wb200_ctx* ctx, int world, const void* cons
     if (ctx->d_peerU) { cudaFree((void*)ctx->d_peerU); ctx->d_peerU = nullptr; }
     if (ctx->d_need_owner) { cudaFree(ctx->d_need_owner); ctx->d_need_owner = nullptr; }
     ctx->peer_world = 0;
+    ctx->peer_self = nullptr;
+    ctx->peer_rank = -1;
     if (world <= 0 || !U_ptrs) return WB200_OK;   // back to purely local reads
     if (!bounds || bounds[0] != 0 || bounds[world] != ctx->nk_total) {
         ctx->err = "wb200_set_peer_gauges: bounds must run from 0 to nk_total";
@@ -709,5 +727,15 @@ extern "C" int wb200_set_peer_gauges(wb200_ctx* ctx, int world, const void* cons
     WB_CUDA(ctx, cudaMemcpy((void*)ctx->d_peerU, U_ptrs, sizeof(void*) * world, cudaMemcpyHostToDevice));
     WB_CUDA(ctx, cudaMemcpy(ctx->d_need_owner, owner.data(), sizeof(int32_t) * ctx->n_need, cudaMemcpyHostToDevice));
     ctx->peer_world = world;
+    ctx->peer_rank = 0;
+    while (ctx->peer_rank + 1 < world && ctx->k_begin >= bounds[ctx->peer_rank + 1]) ctx->peer_rank++;
+    ctx->peer_self = (cplx*)U_ptrs[ctx->peer_rank];
+    return WB200_OK;
+}
+
+extern "C" int wb200_set_allreduce(wb200_ctx* ctx, wb200_allreduce_fn fn, void* user) {
+    if (!ctx) return WB200_ERR_ARG;
+    ctx->allreduce = fn;
+    ctx->allreduce_user = user;
     return WB200_OK;
 }

@@ -91,6 +91,10 @@ struct wb200_ctx {
     const cplx** d_peerU = nullptr;   // [world] device pointers (device array)
     int32_t* d_need_owner = nullptr;  // [n_need] owner rank of need[i]
     int peer_world = 0;
+    int peer_rank = -1;
+    cplx* peer_self = nullptr;        // this rank's full gauge array (U_ptrs[rank])
+    wb200_allreduce_fn allreduce = nullptr;   // caller-supplied collective (sharded optimiser)
+    void* allreduce_user = nullptr;
     double* d_bvec = nullptr;    // [nk][nn][3]
     double* d_wb = nullptr;      // [nn]
     cplx* d_M = nullptr;         // [nk][nn][nb*nb] col-major (generic path / exact N)

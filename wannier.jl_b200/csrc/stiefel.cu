@@ -308,6 +308,8 @@ __global__ void __launch_bounds__(256) red_stage2(const double* __restrict__ par
 static int red_finish(wb200_ctx* ctx, int is_max, double* out_host) {
     red_stage2<<<1, 256, 0, ctx->stream>>>(ctx->d_scal + 8, WB_RED_BLOCKS, is_max, ctx->d_scal);
     WB_LAUNCH_CHECK(ctx);
+    if (ctx->allreduce)   // k-sharded optimiser: vectors are slab-local, scalars are global
+        ctx->allreduce(ctx->d_scal, 1, is_max ? 1 : 0, (void*)ctx->stream, ctx->allreduce_user);
     WB_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, ctx->d_scal, sizeof(double), cudaMemcpyDeviceToHost,
                                  ctx->stream));
     WB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

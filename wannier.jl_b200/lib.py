@@ -24,6 +24,7 @@ SYMBOLS = [
     "wb200_fg_dev", "wb200_min_abs_diag", "wb200_project_tangent_dev", "wb200_retract_dev",
     "wb200_profile", "wb200_profile_read", "wb200_probe_fp64_peak",
     "wb200_omega_local", "wb200_fg_rotate", "wb200_opt_rotate", "wb200_position_op", "wb200_berry_connection",
+    "wb200_set_allreduce",
     "wb200_ipc_alloc", "wb200_ipc_open", "wb200_ipc_close", "wb200_ipc_free", "wb200_set_peer_gauges",
 ]
 
@@ -92,6 +93,7 @@ def load():
     lib.wb200_opt_rotate.argtypes = [vp, pd, dbl, dbl, i32, i32, pd, pd, pd]
     lib.wb200_position_op.argtypes = [vp, pd, pd]
     lib.wb200_berry_connection.argtypes = [vp, pd, pd, i32, i32]
+    lib.wb200_set_allreduce.argtypes = [vp, vp, vp]
     lib.wb200_ipc_alloc.argtypes = [i32, C.c_size_t, C.POINTER(vp), pd]
     lib.wb200_ipc_open.argtypes = [i32, pd, C.POINTER(vp)]
     lib.wb200_ipc_close.argtypes = [i32, vp]
@@ -214,6 +216,17 @@ class Context:
         b = np.ascontiguousarray(bounds, dtype=np.int32)
         self._ck(self._lib.wb200_set_peer_gauges(self._h, len(p), _addr(p), _addr(b)))
 
+    def set_allreduce(self, fn):
+        """fn(dptr: int, count: int, op: int (0 sum, 1 max), stream: int) all-reduces `count` doubles
+        in place over the ranks on `stream`; None unregisters.  The ctypes thunk is kept alive here."""
+        if fn is None:
+            self._cb = None
+            self._ck(self._lib.wb200_set_allreduce(self._h, None, None))
+            return
+        proto = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p)
+        self._cb = proto(lambda dptr, count, op, stream, user: fn(dptr or 0, count, op, stream or 0))
+        self._ck(self._lib.wb200_set_allreduce(self._h, C.cast(self._cb, C.c_void_p), None))
+
     def profile(self, enable):
         self._ck(self._lib.wb200_profile(self._h, int(enable)))
 
@@ -278,7 +291,8 @@ class Context:
         self._ck(self._lib.wb200_retract(self._h, _addr(X), nrow, ncol, count))
 
     def max_localize(self, U, f_tol=1e-7, g_tol=1e-5, max_iter=200, history=3):
-        self._u(U)
+        # U is the ctx's k-slab (= everything for a single-slab ctx)
+        _check_array(U, np.complex128, self.nk * self.nb * self.nw, "U")
         f = C.c_double(0.0)
         it = C.c_int(0)
         nfg = C.c_int(0)

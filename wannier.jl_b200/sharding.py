@@ -98,3 +98,17 @@ class HaloPlan:
         dist.all_to_all_single(r_r, s_r, output_split_sizes=self.recv_counts,
                                input_split_sizes=self.send_counts)
         flat.index_copy_(0, ri, recv)
+
+
+def torch_allreduce(dist, device):
+    """The callback wb200_set_allreduce wants, on top of torch.distributed (NCCL): wraps the raw
+    device pointer as a tensor and reduces it in place on torch's current stream (the stream the
+    ctx must have been given with set_stream)."""
+    import torch
+    from .lib import DeviceArray
+
+    def fn(dptr, count, op, stream):
+        t = torch.as_tensor(DeviceArray(dptr, (count,), "<f8"), device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX if op == 1 else dist.ReduceOp.SUM)
+
+    return fn
