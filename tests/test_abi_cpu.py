@@ -94,3 +94,28 @@ def test_host_layout_helpers_match_oracle(w, silicon):
     assert np.allclose(st.bvectors_cart(), silicon["bvec"], atol=1e-12)
     m = w.Model(silicon["lattice"], st, silicon["M"], U, fro)
     assert (m.n_bands, m.n_wannier, m.n_kpoints, m.n_bvectors) == (12, 8, 64, 8)
+
+
+def test_w90_ingest_matches_goldens(w, valence, silicon):
+    """Product-side parsers (wannier.jl_b200/io_w90.py) against the goldens the oracle-side parsers
+    produced from the same reference fixtures: two independent implementations of the formats."""
+    import os
+    gold = os.path.join(ROOT, "tests", "golden")
+    io = w.io_w90
+    win = io.read_win(os.path.join(gold, "w90_valence", "silicon.win"))
+    assert np.allclose(win["lattice"], valence["lattice"]) and np.allclose(win["kpoints"], valence["kpoints"])
+    assert (win["num_wann"], win["num_bands"], win["mp_grid"]) == (4, 4, [4, 4, 4])
+    M, kpb_k, kpb_G = io.read_mmn(os.path.join(gold, "w90_valence", "silicon.mmn"))
+    assert np.array_equal(M, valence["M"]) and np.array_equal(kpb_k, valence["kpb_k"]) and np.array_equal(kpb_G, valence["kpb_G"])
+    recip = 2 * np.pi * np.linalg.inv(win["lattice"]).T
+    st = w.KspaceStencil(recip, win["kpoints"], np.ones(8), kpb_k, kpb_G)
+    assert np.allclose(st.bvectors_cart(), valence["bvec"], atol=1e-13)
+    assert np.allclose(io.compute_bweights(st.bvectors_cart()[0]), valence["wb"], rtol=1e-12)
+    A = io.read_amn(os.path.join(gold, "w90_valence", "silicon.amn"))
+    assert np.abs(so.orthonorm_lowdin(A) - valence["U"]).max() < 1e-13
+    # frozen window of the 12 -> 8 silicon model (dis_froz_max = 10 eV)
+    win2 = io.read_win(os.path.join(gold, "w90_silicon", "silicon.win"))
+    E = io.read_eig(os.path.join(gold, "w90_silicon", "silicon.eig"))
+    assert np.array_equal(E, silicon["E"])
+    assert np.array_equal(io.frozen_bands(E, win2["dis_froz_max"], win2.get("dis_froz_min", -np.inf)), silicon["frozen"])
+    assert (win2["num_wann"], win2["num_bands"]) == (8, 12)

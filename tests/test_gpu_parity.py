@@ -495,3 +495,18 @@ def test_next_rows_omega_local_position_berry_opt_rotate(w, valence, silicon):
     with pytest.raises(ValueError):
         w.opt_rotate(w.Model(silicon["lattice"], w.KspaceStencil(silicon["recip"], silicon["kpoints"], silicon["wb"],
                                                                 silicon["kpb_k"], silicon["kpb_G"]), silicon["M"], silicon["U"]))
+
+
+def test_read_w90_to_max_localize(w, valence):
+    """The whole drop-in flow from Wannier90 files: parse, Lowdin on the GPU, spread, max_localize
+    (test/localization/max_localize.jl builds its model with read_w90 on this same fixture)."""
+    import os
+    prefix = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "w90_valence", "silicon")
+    model = w.read_w90(prefix)
+    assert np.abs(model.gauges - valence["U"]).max() < 1e-12            # device Lowdin == SVD Lowdin
+    sp = w.omega(model)
+    ref = so.omega(*oracle_args(valence), valence["U"])
+    assert abs(sp.Omega - ref["Omega"]) < RTOL * ref["Omega"]
+    assert abs(sp.OmegaI - valence["ref_maxloc"][1]) < 1e-10             # reference constant
+    U = w.max_localize(model, f_tol=1e-13, g_tol=1e-8, max_iter=500)
+    assert abs(so.omega(*oracle_args(valence), U)["Omega"] - valence["ref_maxloc"][0]) < 1e-8

@@ -4,7 +4,8 @@ path behind the reference's own function API.  See DESIGN.md / INTEGRATION.md.
 The directory name contains a dot, so the package is loaded by path (see
 ``__graft_entry__.load_package``) under the module name ``wannier_jl_b200``.
 """
-from . import lib, api, synthetic, sharding  # noqa: F401
+from . import lib, api, synthetic, sharding, io_w90  # noqa: F401
+from .io_w90 import read_w90  # noqa: F401
 from .api import (KspaceStencil, Model, Spread, SpreadCenter, SpreadPenalty, CenterSpreadPenalty,  # noqa: F401
                   Cache, omega, omega_grad, omega_center, center, compute_MU_UtMU, transform_gauge,
                   get_fg_maxloc, max_localize, get_fg_disentangle, disentangle, X_Y_to_U, X_Y_to_XY,
