@@ -510,3 +510,15 @@ def test_read_w90_to_max_localize(w, valence):
     assert abs(sp.OmegaI - valence["ref_maxloc"][1]) < 1e-10             # reference constant
     U = w.max_localize(model, f_tol=1e-13, g_tol=1e-8, max_iter=500)
     assert abs(so.omega(*oracle_args(valence), U)["Omega"] - valence["ref_maxloc"][0]) < 1e-8
+
+
+def test_opt_rotate_singular_guard(w, valence):
+    # opt_rotate.jl:60-62: g! raises "N^kb too small" when a diagonal element vanishes
+    st = w.KspaceStencil(valence["recip"], valence["kpoints"], valence["wb"], valence["kpb_k"], valence["kpb_G"])
+    f, g = w.get_fg_rotate(w.Model(valence["lattice"], st, valence["M"], valence["U"]))
+    W = np.eye(4, dtype=complex)
+    W[:, 0] = 0
+    with pytest.raises(w.WB200Error) as e:
+        g(np.zeros((4, 4), dtype=complex), W)
+    assert e.value.status == -5
+    f.cache.close()

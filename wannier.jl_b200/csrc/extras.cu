@@ -159,8 +159,13 @@ extern "C" int wb200_fg_rotate(wb200_ctx* ctx, const double* W, double* f, doubl
     WB_TRY(wb_fg_rotate_device(ctx, dW, ctx->d_res, G ? dGW : nullptr));
     if (G) WB_CUDA(ctx, cudaMemcpyAsync(G, dGW, sizeof(cplx) * mat, cudaMemcpyDeviceToHost, ctx->stream));
     WB_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, ctx->d_res, sizeof(double) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    WB_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned + 8, ctx->d_min, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     WB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (f) *f = ctx->h_pinned[5];
+    if (G && ctx->h_pinned[8] < 1e-10) {   // the guard g! keeps (opt_rotate.jl:60-62)
+        ctx->err = "N^kb too small! (|N_nn| < 1e-10)";
+        return WB200_ERR_SINGULAR;
+    }
     return WB200_OK;
 }
 

@@ -49,9 +49,15 @@ struct Problem {
         }
         WB_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned + 16, ctx->d_res + 5, sizeof(double),
                                      cudaMemcpyDeviceToHost, ctx->stream));
+        WB_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned + 17, ctx->d_min, sizeof(double),
+                                     cudaMemcpyDeviceToHost, ctx->stream));
         WB_TRY(project(x, g));
         WB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         *f = ctx->h_pinned[16];
+        if (mode == 2 && !ctx->allreduce && ctx->h_pinned[17] < 1e-10) {   // opt_rotate.jl:60-62
+            ctx->err = "N^kb too small! (|N_nn| < 1e-10)";
+            return WB200_ERR_SINGULAR;
+        }
         return WB200_OK;
     }
 };
