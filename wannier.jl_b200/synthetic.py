@@ -144,6 +144,7 @@ def make_frozen(nk, nb, n_frozen):
 
 CONFIGS = {
     # name: (lattice name, grid, nb, nw)  — BASELINE.json configs
+    "cfg1_si_valence_shape": ("fcc", (4, 4, 4), 4, 4),
     "cfg2_cu_shape": ("fcc", (9, 9, 9), 18, 9),
     "cfg3_nw32": ("bcc", (12, 12, 12), 32, 32),
     "cfg4_nw128": ("bcc", (16, 16, 16), 128, 128),
