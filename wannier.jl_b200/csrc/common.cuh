@@ -116,6 +116,8 @@ struct wb200_ctx {
     cplx* d_N = nullptr;     // [nk][nn][nw*nw]   (lazy; exact split / rotate_overlaps)
     cplx* d_dN = nullptr;    // [nk][nn][nw]      diag N
     double* d_fro = nullptr; // [nk][nn]          ||N||_F^2 (or ||MU||_F^2)
+    const double* fro_src = nullptr;  // where pair_reduce finds ||.||^2: nullptr = d_fro, else partials
+    int fro_parts = 1;
     double* d_part = nullptr;   // [nk][nsums]
     double* d_pmin = nullptr;   // [nk]
     double* d_sums = nullptr;   // [nsums]

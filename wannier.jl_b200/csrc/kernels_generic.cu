@@ -178,6 +178,7 @@ int wb_rotate_generic(wb200_ctx* ctx, const cplx* dU, int ka, int kb) {
     a.C = ctx->d_MU + p0 * nb * nw; a.strideC = (long long)nb * nw; a.ldc = nb;
     a.alpha = 1.0; a.beta = 0.0; a.batch = pairs; a.transA = 0; a.transB = 0;
     ProfScope ps(ctx, 1);
+    ctx->fro_src = nullptr;
     WB_TRY(wb_zgemm_batched(ctx, a));
     diag_kernel<<<pairs, 256, 0, ctx->stream>>>(nb, nw, dU, ctx->d_kself + p0, ctx->d_MU + p0 * nb * nw,
                                                  ctx->d_dN + p0 * nw, ctx->d_fro + p0);
@@ -203,6 +204,7 @@ int wb_form_N(wb200_ctx* ctx, const cplx* dU) {
     a.C = ctx->d_N; a.strideC = (long long)nw * nw; a.ldc = nw;
     a.alpha = 1.0; a.beta = 0.0; a.batch = pairs;
     WB_TRY(wb_zgemm_batched(ctx, a));
+    ctx->fro_src = nullptr;   // from here on ||N||_F^2 of the exact N
     fro_kernel<<<pairs, 256, 0, ctx->stream>>>(nw * nw, ctx->d_N, ctx->d_fro);
     WB_LAUNCH_CHECK(ctx);
     return WB200_OK;
@@ -215,7 +217,7 @@ int wb_form_N(wb200_ctx* ctx, const cplx* dU) {
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) pair_reduce_kernel(int nw, int nn, int nk, int k_off,
                                                           const cplx* __restrict__ dN,
-                                                          const double* __restrict__ fro,
+                                                          const double* __restrict__ fro, int nfro,
                                                           const double* __restrict__ bvec,
                                                           const double* __restrict__ wb,
                                                           double* __restrict__ part,
@@ -251,7 +253,11 @@ __global__ void __launch_bounds__(128) pair_reduce_kernel(int nw, int nn, int nk
         double t = 0.0, m = 1e300;
         for (int w = 0; w < (int)(blockDim.x >> 5); w++) { t += ssum[w]; m = fmin(m, smin[w]); }
         double sf = 0.0;
-        for (int b = 0; b < nn; b++) sf += wb[b] * fro[(long long)k * nn + b];
+        for (int b = 0; b < nn; b++) {   // a rotation kernel may leave ||.||^2 of a pair in nfro partials
+            double fp = 0.0;
+            for (int i = 0; i < nfro; i++) fp += fro[((long long)k * nn + b) * nfro + i];
+            sf += wb[b] * fp;
+        }
         part[(long long)(4 * nw) * nk + k] = sf;
         part[(long long)(4 * nw + 1) * nk + k] = t;
         pmin[k] = sqrt(m);
@@ -293,7 +299,8 @@ __global__ void __launch_bounds__(256) sum_over_k_kernel(int nk, int ns, const d
 int wb_pair_partial(wb200_ctx* ctx, int ka, int kb) {
     ProfScope ps(ctx, 2);
     pair_reduce_kernel<<<kb - ka, 128, 0, ctx->stream>>>(ctx->nw, ctx->nn, ctx->nk, ka, ctx->d_dN,
-                                                          ctx->d_fro, ctx->d_bvec, ctx->d_wb,
+                                                          ctx->fro_src ? ctx->fro_src : ctx->d_fro, ctx->fro_src ? ctx->fro_parts : 1,
+                                                          ctx->d_bvec, ctx->d_wb,
                                                           ctx->d_part, ctx->d_pmin);
     WB_LAUNCH_CHECK(ctx);
     return WB200_OK;

@@ -646,6 +646,7 @@ int wb_pack_dmma(wb200_ctx* ctx, const cplx* dU, int ja, int jb) {
 
 int wb_rotate_dmma(wb200_ctx* ctx, const cplx* dU, int ka, int kb) {
     DmmaPlan* p = ctx->dmma;
+    ctx->fro_src = nullptr;
     if (p->small) {
         const long long p0 = (long long)ka * ctx->nn, p1 = (long long)kb * ctx->nn;
         {
@@ -655,9 +656,8 @@ int wb_rotate_dmma(wb200_ctx* ctx, const cplx* dU, int ka, int kb) {
                 ctx->d_dN, p->d_frop);
         }
         WB_LAUNCH_CHECK(ctx);
-        ProfScope ps2(ctx, 2);
-        fro_pair_sum_kernel<<<(unsigned)((p1 - p0 + 255) / 256), 256, 0, ctx->stream>>>(p0, p1, p->d_frop, ctx->d_fro);
-        WB_LAUNCH_CHECK(ctx);
+        ctx->fro_src = p->d_frop;   // pair_reduce_kernel adds the two half-tile norms itself
+        ctx->fro_parts = 2;
         return WB200_OK;
     }
     {
