@@ -522,3 +522,30 @@ def test_opt_rotate_singular_guard(w, valence):
         g(np.zeros((4, 4), dtype=complex), W)
     assert e.value.status == -5
     f.cache.close()
+
+
+@pytest.mark.parametrize("lat,grid,n", [("bcc", (2, 2, 2), 128), ("cubic", (3, 3, 1), 72), ("tetragonal", (3, 3, 1), 256)])
+def test_stiefel_ops_on_the_tensor_pipe(w, lat, grid, n):
+    """n x n Stiefel GEMMs (X^H X, X T, X^H G, X S) routed through the DMMA rotation kernel when the
+    matrices have the ctx's own shape (max_localize at large n_wann): projection, retraction and a few
+    L-BFGS iterations against the oracle."""
+    st, M, U = w.synthetic.make_model_arrays(lat, grid, n, n, eps=0.02)
+    nk = len(U)
+    ctx = make_ctx(w, st, M, n)
+    assert ctx.rotation_kernel == "dmma-fp64"
+    rng = np.random.default_rng(11)
+    G = rng.standard_normal(U.shape) + 1j * rng.standard_normal(U.shape)
+    Gc = w.api.to_abi_U(G)
+    ctx.project_tangent(w.api.to_abi_U(U), Gc, n, n)
+    assert rel(w.api.from_abi_U(Gc), so.stiefel_project_tangent(G, U)) < 1e-12
+    Xp = U + 0.05 * G / np.sqrt(n)
+    Xc = w.api.to_abi_U(Xp)
+    ctx.retract(Xc, n, n)
+    assert np.abs(w.api.from_abi_U(Xc) - so.stiefel_retract(Xp)).max() < 1e-12
+    # a short optimisation: same iterates as the oracle's driver
+    Uc = w.api.to_abi_U(U)
+    f, it, nfg = ctx.max_localize(Uc, f_tol=1e-12, g_tol=1e-9, max_iter=3)
+    Uo, fo, ito, _ = so.max_localize(M, st["kpb_k"], st["bvec"], st["wb"], U, f_tol=1e-12, g_tol=1e-9, max_iter=3)
+    assert it == ito and abs(f - fo) < 1e-9 * max(abs(fo), 1.0)   # degenerate stencils give Omega ~ 0
+    assert np.abs(w.api.from_abi_U(Uc) - Uo).max() < 1e-8
+    ctx.close()

@@ -225,6 +225,9 @@ void wb_dmma_plan_destroy(wb200_ctx* ctx);
 int wb_pack_dmma(wb200_ctx* ctx, const cplx* dU, int ja, int jb);     // pack need[ja:jb) of the gauge
 int wb_rotate_dmma(wb200_ctx* ctx, const cplx* dU, int ka, int kb);   // MU, dN, fro(=||MU||^2) of local k in [ka, kb)
 
+bool wb_zgemm_dmma_applicable(const wb200_ctx* ctx, int nrow, int ncol);
+int wb_zgemm_dmma(wb200_ctx* ctx, int transA, const cplx* A, const cplx* B, cplx* C, int count);   // C = op(A) B, n x n
+
 // ---- optimizer.cu ----
 int wb_lbfgs(wb200_ctx* ctx, int mode /*0 maxloc, 1 disentangle*/, cplx* dx, double f_tol,
              double g_tol, int max_iter, int history, double* f_final, int* iters, int* n_fg);

@@ -40,6 +40,9 @@ struct DmmaPlan {
     cplx* d_dNp = nullptr;        // [pairs][WM][nw]  per-warp-row partial diagonals
     double* d_frop = nullptr;     // [pairs][nct][8]
     size_t smem = 0;
+    // scratch of the batched-GEMM engine (wb_zgemm_dmma), sized on first use
+    double* g_At = nullptr; double* g_Bp = nullptr; cplx* g_dNp = nullptr; double* g_frop = nullptr;
+    int32_t* g_iota = nullptr; int g_count = 0;
 };
 
 namespace {
@@ -91,7 +94,7 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 // A-operand image of M.  Chunk c = [wm][ks][j(6)][lane] double2; the 12 doubles of a lane are
 //   (re, im, re+im) of mt = 0..3 with row = wm*32 + mt*8 + lane/4, col = c*KC + ks*4 + lane%4.
 __global__ void tile_overlaps_kernel(int nb, int WM, int KC, int nch, const cplx* __restrict__ M,
-                                     double* __restrict__ Mt) {
+                                     double* __restrict__ Mt, int conj_transpose = 0) {
     const long long pair = blockIdx.x;
     const int c = blockIdx.y;
     const int KS = KC / 4;
@@ -105,7 +108,9 @@ __global__ void tile_overlaps_kernel(int nb, int WM, int KC, int nch, const cplx
 #pragma unroll
         for (int mt = 0; mt < 4; mt++) {
             const int row = wm * 32 + mt * 8 + (lane >> 2);
-            const cplx v = (row < nb && col < nb) ? src[row + (long long)col * nb] : make_double2(0.0, 0.0);
+            cplx v = make_double2(0.0, 0.0);
+            if (row < nb && col < nb)   // conj_transpose: the A operand is src^H (Stiefel GEMMs X^H X, X^H G)
+                v = conj_transpose ? cconj(src[col + (long long)row * nb]) : src[row + (long long)col * nb];
             q[3 * mt] = v.x;
             q[3 * mt + 1] = v.y;
             q[3 * mt + 2] = v.x + v.y;
@@ -123,7 +128,7 @@ __global__ void __launch_bounds__(256) pack_gauge_kernel(int nb, int nw, int WN,
                                                          const cplx* const* __restrict__ peerU,
                                                          const cplx* __restrict__ U,
                                                          double* __restrict__ Up) {
-    const long long kg = need[blockIdx.x];   // only the k-points this slab reads (own + neighbours)
+    const long long kg = need ? need[blockIdx.x] : blockIdx.x;   // only the k-points this slab reads
     // k-sharded runs: a row another rank owns is read straight from that rank's memory over NVLink
     // (peer-mapped pointer) — the halo exchange is fused into the packing
     if (peerU) U = peerU[owner[blockIdx.x]];
@@ -559,6 +564,10 @@ __global__ void __launch_bounds__(128) combine_partials_kernel(int nw, int WM, i
     }
 }
 
+struct RotateOverride {
+    const int32_t* iota; const double* At; const double* Bp; cplx* C; cplx* dNp; double* frop;
+};
+
 template <int WM, int WN, int KC, int STAGES>
 size_t smem_bytes() {
     constexpr int KS = KC / 4;
@@ -567,7 +576,7 @@ size_t smem_bytes() {
 }
 
 template <int WM, int WN, int KC, int STAGES>
-int launch_rotate(wb200_ctx* ctx, const cplx* dU, int ka, int kb) {
+int launch_rotate(wb200_ctx* ctx, const cplx* dU, int ka, int kb, const RotateOverride* ov = nullptr) {
     DmmaPlan* p = ctx->dmma;
     auto kern = rotate_dmma_kernel<WM, WN, KC, STAGES>;
     static bool attr_done[16] = {false};
@@ -575,9 +584,13 @@ int launch_rotate(wb200_ctx* ctx, const cplx* dU, int ka, int kb) {
         WB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
         attr_done[ctx->device & 15] = true;
     }
-    kern<<<(kb - ka) * p->nct, 384, p->smem, ctx->stream>>>(ctx->nb, ctx->nw, ctx->nn, p->nch, p->nct,
-                                                          ctx->k_begin, ka, ctx->d_kpb, p->d_Mt, p->d_Up,
-                                                          dU, ctx->d_MU, p->d_dNp, p->d_frop);
+    if (ov)   // batched-GEMM use: one "pair" per matrix, neighbour table = identity
+        kern<<<(kb - ka) * p->nct, 384, p->smem, ctx->stream>>>(ctx->nb, ctx->nw, 1, p->nch, p->nct, 0, ka, ov->iota,
+                                                              ov->At, ov->Bp, dU, ov->C, ov->dNp, ov->frop);
+    else
+        kern<<<(kb - ka) * p->nct, 384, p->smem, ctx->stream>>>(ctx->nb, ctx->nw, ctx->nn, p->nch, p->nct,
+                                                              ctx->k_begin, ka, ctx->d_kpb, p->d_Mt, p->d_Up,
+                                                              dU, ctx->d_MU, p->d_dNp, p->d_frop);
     WB_LAUNCH_CHECK(ctx);
     return WB200_OK;
 }
@@ -628,6 +641,11 @@ void wb_dmma_plan_destroy(wb200_ctx* ctx) {
     if (p->d_Up) cudaFree(p->d_Up);
     if (p->d_dNp) cudaFree(p->d_dNp);
     if (p->d_frop) cudaFree(p->d_frop);
+    if (p->g_At) cudaFree(p->g_At);
+    if (p->g_Bp) cudaFree(p->g_Bp);
+    if (p->g_dNp) cudaFree(p->g_dNp);
+    if (p->g_frop) cudaFree(p->g_frop);
+    if (p->g_iota) cudaFree(p->g_iota);
     delete p;
     ctx->dmma = nullptr;
 }
@@ -678,3 +696,52 @@ extern "C" int wb200_debug_set_timing_buffer(long long* dptr) {
     return cudaMemcpyToSymbol(wb_dbg, &dptr, sizeof(dptr)) == cudaSuccess ? 0 : -2;
 }
 #endif
+
+// ---------------------------------------------------------------------------------------------
+// Batched square complex GEMM on the tensor pipe:  C[i] = op(A[i]) * B[i],  op = identity or ^H,
+// for `count` contiguous n x n matrices with n = ctx->nb = ctx->nw (the Stiefel GEMMs of
+// max_localize at large n: X^H X, X T, X^H G, X S).  It is the rotation kernel with one "pair" per
+// matrix: A is tiled (optionally conjugate-transposed) and B packed into the operand images first.
+// ---------------------------------------------------------------------------------------------
+bool wb_zgemm_dmma_applicable(const wb200_ctx* ctx, int nrow, int ncol) {
+    return ctx->dmma && !ctx->dmma->small && nrow == ncol && nrow == ctx->nb && ctx->nb == ctx->nw;
+}
+
+__global__ void iota_kernel(int n, int32_t* out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = i;
+}
+
+int wb_zgemm_dmma(wb200_ctx* ctx, int transA, const cplx* A, const cplx* B, cplx* C, int count) {
+    DmmaPlan* p = ctx->dmma;
+    const int n = ctx->nb;
+    if (count > p->g_count) {
+        if (p->g_At) cudaFree(p->g_At);
+        if (p->g_Bp) cudaFree(p->g_Bp);
+        if (p->g_dNp) cudaFree(p->g_dNp);
+        if (p->g_frop) cudaFree(p->g_frop);
+        if (p->g_iota) cudaFree(p->g_iota);
+        p->g_At = p->g_Bp = p->g_frop = nullptr; p->g_dNp = nullptr; p->g_iota = nullptr; p->g_count = 0;
+        WB_CUDA(ctx, cudaMalloc(&p->g_At, sizeof(double) * (size_t)count * p->nch * p->a_stage));
+        WB_CUDA(ctx, cudaMalloc(&p->g_Bp, sizeof(double) * (size_t)count * p->nct * p->nch * p->b_stage));
+        WB_CUDA(ctx, cudaMalloc(&p->g_dNp, sizeof(cplx) * (size_t)count * p->WM * n));
+        WB_CUDA(ctx, cudaMalloc(&p->g_frop, sizeof(double) * (size_t)count * p->nct * 8));
+        WB_CUDA(ctx, cudaMalloc(&p->g_iota, sizeof(int32_t) * count));
+        iota_kernel<<<(count + 255) / 256, 256, 0, ctx->stream>>>(count, p->g_iota);
+        WB_LAUNCH_CHECK(ctx);
+        p->g_count = count;
+    }
+    dim3 gt((unsigned)count, (unsigned)p->nch);
+    tile_overlaps_kernel<<<gt, 128, 0, ctx->stream>>>(n, p->WM, p->KC, p->nch, A, p->g_At, transA);
+    WB_LAUNCH_CHECK(ctx);
+    dim3 gp((unsigned)count, (unsigned)p->nct);
+    pack_gauge_kernel<<<gp, 256, 0, ctx->stream>>>(n, n, p->WN, p->KC, p->nch, p->nct, nullptr, nullptr, nullptr, B,
+                                                  p->g_Bp);
+    WB_LAUNCH_CHECK(ctx);
+    RotateOverride ov{p->g_iota, p->g_At, p->g_Bp, C, p->g_dNp, p->g_frop};
+    // the kernel's diag epilogue needs some n x n array per matrix for its U_k tile: B serves
+    if (p->WM == 2) WB_TRY((launch_rotate<WB_CFG_64>(ctx, B, 0, count, &ov)));
+    else if (p->WM == 4) WB_TRY((launch_rotate<WB_CFG_128>(ctx, B, 0, count, &ov)));
+    else WB_TRY((launch_rotate<WB_CFG_256>(ctx, B, 0, count, &ov)));
+    return WB200_OK;
+}

@@ -32,7 +32,16 @@ __global__ void hermitize_kernel(int n, long long total, cplx* __restrict__ S) {
 static int project_strided(wb200_ctx* ctx, const cplx* dX, cplx* dG, int nrow, int ncol, int ld,
                            long long stride, int count) {
     if (wb_small_applicable(nrow, ncol)) return wb_project_small(ctx, dX, dG, nrow, ncol, ld, stride, count);
-    WB_TRY(wb_ensure_tmp(ctx, (size_t)count * ncol * ncol, 0));
+    const bool tensor = wb_zgemm_dmma_applicable(ctx, nrow, ncol) && ld == nrow && stride == (long long)nrow * ncol;
+    WB_TRY(wb_ensure_tmp(ctx, (size_t)count * ncol * ncol, tensor ? (size_t)count * nrow * ncol : 0));
+    if (tensor) {   // S = X^H G, S <- sym(S), G <- G - X S  with both GEMMs on the tensor pipe
+        WB_TRY(wb_zgemm_dmma(ctx, 1, dX, dG, ctx->d_tmp1, count));
+        const long long tot = (long long)count * ncol * ncol;
+        hermitize_kernel<<<(int)((tot + 255) / 256 < 4096 ? (tot + 255) / 256 : 4096), 256, 0, ctx->stream>>>(ncol, tot, ctx->d_tmp1);
+        WB_LAUNCH_CHECK(ctx);
+        WB_TRY(wb_zgemm_dmma(ctx, 0, dX, ctx->d_tmp1, ctx->d_tmp2, count));
+        return wb_axpby(ctx, -1.0, (const double*)ctx->d_tmp2, 1.0, (double*)dG, 2 * (size_t)count * nrow * ncol);
+    }
     ZgemmArgs a{};
     a.m = ncol; a.n = ncol; a.k = nrow;
     a.A = dX; a.strideA = stride; a.lda = ld; a.transA = 1;
@@ -124,6 +133,7 @@ static int retract_strided(wb200_ctx* ctx, cplx* dX, int nrow, int ncol, int ld,
     WB_TRY(wb_ensure_tmp(ctx, (size_t)count * ncol * ncol, (size_t)count * nrow * ncol));
     int it = 0;
     double err = 0.0;
+    const bool tensor = wb_zgemm_dmma_applicable(ctx, nrow, ncol) && ld == nrow && stride == (long long)nrow * ncol;
     for (; it < MAXIT; it++) {
         ZgemmArgs a{};
         a.m = ncol; a.n = ncol; a.k = nrow;
@@ -131,7 +141,8 @@ static int retract_strided(wb200_ctx* ctx, cplx* dX, int nrow, int ncol, int ld,
         a.B = dX; a.strideB = stride; a.ldb = ld; a.transB = 0;
         a.C = ctx->d_tmp1; a.strideC = (long long)ncol * ncol; a.ldc = ncol;
         a.alpha = 1.0; a.beta = 0.0; a.batch = count;
-        WB_TRY(wb_zgemm_batched(ctx, a));
+        if (tensor) WB_TRY(wb_zgemm_dmma(ctx, 1, dX, dX, ctx->d_tmp1, count));   // P = X^H X
+        else WB_TRY(wb_zgemm_batched(ctx, a));
         WB_CUDA(ctx, cudaMemsetAsync(ctx->d_scal, 0, sizeof(double), ctx->stream));
         ns_prepare_kernel<<<count, 256, 0, ctx->stream>>>(ncol, ctx->d_tmp1, ctx->d_scal, it == 0);
         WB_LAUNCH_CHECK(ctx);
@@ -143,7 +154,8 @@ static int retract_strided(wb200_ctx* ctx, cplx* dX, int nrow, int ncol, int ld,
         b.B = ctx->d_tmp1; b.strideB = (long long)ncol * ncol; b.ldb = ncol; b.transB = 0;
         b.C = ctx->d_tmp2; b.strideC = (long long)nrow * ncol; b.ldc = nrow;
         b.alpha = 1.0; b.beta = 0.0; b.batch = count;
-        WB_TRY(wb_zgemm_batched(ctx, b));
+        if (tensor) WB_TRY(wb_zgemm_dmma(ctx, 0, dX, ctx->d_tmp1, ctx->d_tmp2, count));   // X T
+        else WB_TRY(wb_zgemm_batched(ctx, b));
         const long long total = (long long)count * nrow * ncol;
         if (ld == nrow && stride == (long long)nrow * ncol) {
             WB_CUDA(ctx, cudaMemcpyAsync(dX, ctx->d_tmp2, sizeof(cplx) * total,
