@@ -534,13 +534,6 @@ rotate_small_kernel(int nb, int nw, int nn, long long pair0, long long pair_end,
     if (lane == 0) frop[p * 2 + half] = f;
 }
 
-// fro[pair] = frop[pair][0] + frop[pair][1]
-__global__ void fro_pair_sum_kernel(long long pair0, long long pair_end, const double* __restrict__ frop,
-                                    double* __restrict__ fro) {
-    const long long p = pair0 + blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (p < pair_end) fro[p] = frop[2 * p] + frop[2 * p + 1];
-}
-
 // dN[pair][n] = sum_wm dNp[pair][wm][n];  fro[pair] = sum frop[pair][:]   (fixed order)
 __global__ void __launch_bounds__(128) combine_partials_kernel(int nw, int WM, int nfro, long long pair_off,
                                                                const cplx* __restrict__ dNp,
