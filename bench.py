@@ -180,7 +180,9 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "WARN")   # keep NCCL's version banner off stdout (one JSON line)
+        # NCCL prints its version banner (and any NCCL_DEBUG output) to stdout by default; stdout must
+        # carry exactly one JSON line, so send NCCL's log to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     st = w.synthetic.make_stencil(w.synthetic.LATTICES[lat](), grid)
