@@ -144,6 +144,12 @@ def main():
                     help="N > 1: read neighbour gauges from peer memory inside the pack kernel (CUDA IPC "
                          "over NVLink) or exchange them with an NCCL all-to-all / send-recv first")
     args = ap.parse_args()
+    # stdout must carry exactly ONE JSON line.  Native libraries (NCCL's version banner, any
+    # NCCL_DEBUG output) write to file descriptor 1 directly, so keep a private handle on the real
+    # stdout for the JSON line and point fd 1 at stderr for everything else.
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
     rank = int(os.environ.get("RANK", "0"))
@@ -170,7 +176,7 @@ def main():
                 "data": "synthetic", "config": config, "cpu_baseline": cb,
                 "e2e": {"value": cb["value"], "unit": "evals/s", "h2d_bytes_per_step": 0,
                         "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        print(json.dumps(line), file=json_out, flush=True)
         return
 
     import torch
@@ -180,8 +186,6 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        # NCCL prints its version banner (and any NCCL_DEBUG output) to stdout by default; stdout must
-        # carry exactly one JSON line, so send NCCL's log to stderr
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
@@ -414,7 +418,7 @@ def main():
             "sample": f"{len(ks)} of {nk} k-points ({len(ks) * nn} pairs; both ZGEMMs per pair as "
                       f"spread.jl:173-174 plus the omega!/omega_grad! loops), {len(ts)} x {t:.3f} s, "
                       f"numpy+OpenBLAS with {cores} threads over k; extrapolated to the full k-grid"}
-    print(json.dumps(line))
+    print(json.dumps(line), file=json_out, flush=True)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()

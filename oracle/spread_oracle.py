@@ -460,7 +460,8 @@ def lbfgs_stiefel(fg, x0, retract, project, f_tol=1e-7, g_tol=1e-5, max_iter=200
             xn = retract(x + a_ * d)
             fn, gn = fg(xn)
             gn = project(gn, xn)
-            return fn, gn, xn, _rdot(gn, project(d, xn))
+            # gn is tangent at xn and the tangent projection is self-adjoint, so <gn, P(d)> = <gn, d>
+            return fn, gn, xn, _rdot(gn, d)
 
         c1, c2 = 1e-4, 0.9
         lo, hi = 0.0, None

@@ -17,11 +17,17 @@ for name in sys.argv[1:] or ["cfg2_cu_shape", "cfg3_nw32", "cfg5_2d_nw256", "cfg
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)
     res = torch.zeros(ctx.nres, dtype=torch.float64, device=dev)
     G = torch.zeros((nk, nw, nb), dtype=torch.complex128, device=dev)
-    for _ in range(5):
-        ctx.fg_dev(dU.data_ptr(), res.data_ptr(), G.data_ptr())
-    torch.cuda.synchronize()
+    # warm up for at least 0.4 s (clocks ramp from idle), then time about 0.4 s worth of evaluations
+    t0 = time.perf_counter()
+    nwarm = 0
+    while time.perf_counter() - t0 < 0.4 or nwarm < 5:
+        for _ in range(5):
+            ctx.fg_dev(dU.data_ptr(), res.data_ptr(), G.data_ptr())
+        torch.cuda.synchronize()
+        nwarm += 5
+    est = (time.perf_counter() - t0) / nwarm
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    n = 20
+    n = int(min(2000, max(20, 0.4 / est)))
     ctx.profile(True)
     e0.record()
     for _ in range(n):

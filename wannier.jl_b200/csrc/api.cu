@@ -20,7 +20,7 @@ extern "C" void wb200_destroy(wb200_ctx* ctx) {
     void* ptrs[] = {(void*)ctx->d_peerU, ctx->d_need_owner, ctx->d_need, ctx->d_kpb, ctx->d_kself, ctx->d_bvec, ctx->d_wb, ctx->d_M, ctx->d_r0,
                     ctx->d_frozen, ctx->d_nfrozen, ctx->d_U, ctx->d_G, ctx->d_MU, ctx->d_N,
                     ctx->d_dN, ctx->d_fro, ctx->d_part, ctx->d_pmin, ctx->d_sums, ctx->d_res,
-                    ctx->d_min, ctx->d_scal, ctx->d_tmp1, ctx->d_tmp2, ctx->d_XY, ctx->d_GXY};
+                    ctx->d_min, ctx->d_scal, ctx->d_red, ctx->d_tmp1, ctx->d_tmp2, ctx->d_XY, ctx->d_GXY};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     for (auto& v : ctx->prof_events)

@@ -123,7 +123,8 @@ struct wb200_ctx {
     double* d_sums = nullptr;   // [nsums]
     double* d_res = nullptr;    // [nres]
     double* d_min = nullptr;    // [1]
-    double* d_scal = nullptr;   // [2048] scratch scalars (dots, errors, block partials)
+    double* d_scal = nullptr;   // [2048] scratch scalars (errors, flags)
+    double* d_red = nullptr;    // block partials + results of the fused inner-product kernel (lazy)
     double* h_pinned = nullptr; // pinned host scratch (nres + 64 doubles)
     // generic scratch for stiefel / xy (lazy, sized on demand)
     cplx* d_tmp1 = nullptr; size_t tmp1_elems = 0;
@@ -213,11 +214,28 @@ int wb_retract_small(wb200_ctx* ctx, cplx* dX, int nrow, int ncol, int ld, long 
 int wb_project_small(wb200_ctx* ctx, const cplx* dX, cplx* dG, int nrow, int ncol, int ld, long long stride,
                      int count);
 
-// ---- vecops (stiefel.cu) ----
-int wb_dot(wb200_ctx* ctx, const double* a, const double* b, size_t n, double* out_host);
-int wb_absmax(wb200_ctx* ctx, const double* a, size_t n, double* out_host);
+// ---- vecops.cu ----
+#define WB_CROSS_NA 3
+#define WB_CROSS_NB 7
+#define WB_CROSS_NOUT (WB_CROSS_NA * WB_CROSS_NB + 1)   // sums [na][7] row-major, then max |a_0|^2
+#define WB_PIN_CROSS 24                                 // offset of the results in ctx->h_pinned
+struct WbCrossArgs {
+    const double* a[WB_CROSS_NA];
+    const double* b[WB_CROSS_NB];
+    int na, nb;
+    int a_in_b;   // a[i] is b[i] for i < na: read once
+};
+struct WbLinArgs {
+    const double* v[WB_CROSS_NB];
+    double c[WB_CROSS_NB];
+    int nv;
+    double beta;
+};
+int wb_cross_launch(wb200_ctx* ctx, const WbCrossArgs& p, size_t n);   // results in h_pinned after a sync
+int wb_lincomb(wb200_ctx* ctx, const WbLinArgs& p, double* out, size_t n);   // out = beta out + sum c_j v_j
+int wb_secant(wb200_ctx* ctx, double alpha, const double* d, const double* gnew, const double* g, double* s,
+              double* y, size_t n);                                    // s = alpha d, y = gnew - g
 int wb_axpby(wb200_ctx* ctx, double alpha, const double* x, double beta, double* y, size_t n);  // y = a x + b y
-int wb_axpbyz(wb200_ctx* ctx, double alpha, const double* x, double beta, const double* y, double* z, size_t n);
 
 // ---- rotate_dmma.cu ----
 int wb_dmma_plan_create(wb200_ctx* ctx, const double* hM);   // may leave ctx->dmma == nullptr if not applicable

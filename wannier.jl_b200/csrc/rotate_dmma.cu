@@ -29,7 +29,9 @@
 #include "common.cuh"
 
 struct DmmaPlan {
-    bool small = false;           // nb <= 32: rotate_small_kernel (no smem, warp pair per (k,b) pair)
+    bool small = false;           // nb <= 32: warp pair per (k,b) pair
+    bool small_ring = true;       // ... operands through a bulk-copy ring (WB200_SMALL_RING=0: straight from global)
+    int num_sms = 148;
     int WM = 0, WN = 0, KC = 0;   // warp grid (8 consumer warps), k-chunk
     int NB = 0, NC = 0;           // padded rows, columns per CTA
     int nct = 0;                  // column tiles = ceil(nw / NC)
@@ -534,6 +536,199 @@ rotate_small_kernel(int nb, int nw, int nn, long long pair0, long long pair_end,
     if (lane == 0) frop[p * 2 + half] = f;
 }
 
+// ---- small shapes, ring version ---------------------------------------------------------------
+// rotate_small_kernel above keeps only one k-step of loads in flight per warp (2 warps per SMSP, one
+// CTA per SM because of the 96 accumulator registers), so it runs at DRAM latency, not bandwidth.
+// Here a persistent CTA owns a contiguous range of pairs; a producer warp streams the operand images
+// with 1-D bulk async copies into per-warp-pair rings of 4 slots x 2 k-steps (12 KB per slot, 192 KB
+// per CTA), so every warp pair always has three chunks (~37 KB per warp pair, ~150 KB per SM) in
+// flight while it computes on the fourth.  Warp 2w / 2w+1 compute columns 0-15 / 16-31 of the pairs
+// i = w (mod 4) of the CTA's range; the U_k values of the epilogue are loaded at the start of the
+// pair so their latency hides under the DMMAs.
+constexpr int SR_KS = 2;                                  // k-steps per chunk
+constexpr int SR_NCH = 8 / SR_KS;                         // chunks per pair
+constexpr int SR_SLOTS = 4;                               // slots per warp pair
+constexpr uint32_t SR_A_BYTES = SR_KS * 6 * 32 * 16;      // 6144
+constexpr uint32_t SR_B_BYTES = SR_KS * 3 * 32 * 16;      // 3072 per column half
+constexpr uint32_t SR_SLOT_BYTES = SR_A_BYTES + 2 * SR_B_BYTES;   // 12288
+constexpr size_t SR_SMEM = (size_t)4 * SR_SLOTS * SR_SLOT_BYTES + 8 * 2 * 4 * SR_SLOTS;
+
+__global__ void __launch_bounds__(384, 1)
+rotate_small_ring_kernel(int nb, int nw, int nn, long long pair0, long long pair_end, int k_begin,
+                         const int32_t* __restrict__ kpb, const double* __restrict__ Mt,
+                         const double* __restrict__ Up, const cplx* __restrict__ U, cplx* __restrict__ MU,
+                         cplx* __restrict__ dN, double* __restrict__ frop) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem_raw + (size_t)4 * SR_SLOTS * SR_SLOT_BYTES);
+    // bars[(wp*SR_SLOTS + s)*2 + {0 full, 1 empty}]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t ring_base = smem_u32(smem_raw), bar_base = smem_u32(bars);
+    const long long total = pair_end - pair0;
+    const long long per = (total + gridDim.x - 1) / gridDim.x;
+    const long long my0 = pair0 + (long long)blockIdx.x * per;
+    const long long my1 = my0 + per < pair_end ? my0 + per : pair_end;
+    const int cnt = my1 > my0 ? (int)(my1 - my0) : 0;
+    if (cnt == 0) return;
+
+    if (warp == 8 && lane == 0) {
+        for (int i = 0; i < 4 * SR_SLOTS; i++) {
+            mbar_init(bar_base + 16u * i, 1);
+            mbar_init(bar_base + 16u * i + 8u, 2);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    // warp pair w owns the contiguous quarter [q0(w), q0(w + 1)) of the CTA's pairs: consecutive pairs
+    // share k (nn neighbours each), so the U_k values of the epilogue are reloaded once per k-point
+    auto q0 = [&](int w) { return (int)((long long)cnt * w / 4); };
+
+    if (warp >= 8) {
+        // producer warpgroup (warps 8-11): hands its registers to the consumers; warp 8 drives the rings
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        if (warp != 8) return;
+        // the u-th chunk of a warp pair goes to its slot u % SR_SLOTS.  Lane l keeps the neighbour
+        // index of pair (l % 8) of the current group of 8 of stream l / 8 (one coalesced load per
+        // group), so the issuing lane never waits on a dependent global load between copies.
+        const int w_l = lane >> 3, j_l = lane & 7;
+        const int len_l = q0(w_l + 1) - q0(w_l);
+        int maxlen = 0;
+        for (int w = 0; w < 4; w++) maxlen = max(maxlen, q0(w + 1) - q0(w));
+        for (int qb = 0; qb < maxlen; qb += 8) {
+            const int mine = qb + j_l < len_l ? kpb[my0 + q0(w_l) + qb + j_l] : 0;
+            for (int j = 0; j < 8; j++)
+                for (int wp = 0; wp < 4; wp++) {
+                    const long long kp = __shfl_sync(0xffffffffu, mine, wp * 8 + j);
+                    const int q = qb + j;
+                    if (lane != 0 || q >= q0(wp + 1) - q0(wp)) continue;
+                    const long long p = my0 + q0(wp) + q;
+                    const char* a = reinterpret_cast<const char*>(Mt) + p * 24576;
+                    const char* b = reinterpret_cast<const char*>(Up) + kp * 24576;
+#pragma unroll
+                    for (int c = 0; c < SR_NCH; c++) {
+                        const int u = q * SR_NCH + c;
+                        const int s = u % SR_SLOTS;
+                        const uint32_t full = bar_base + 16u * (wp * SR_SLOTS + s), empty = full + 8u;
+                        mbar_wait(empty, ((uint32_t)(u / SR_SLOTS) & 1u) ^ 1u);
+                        mbar_arrive_expect_tx(full, SR_SLOT_BYTES);
+                        const uint32_t dst = ring_base + (uint32_t)(wp * SR_SLOTS + s) * SR_SLOT_BYTES;
+                        bulk_g2s(dst, a + c * SR_A_BYTES, SR_A_BYTES, full);
+                        bulk_g2s(dst + SR_A_BYTES, b + c * SR_B_BYTES, SR_B_BYTES, full);
+                        bulk_g2s(dst + SR_A_BYTES + SR_B_BYTES, b + 12288 + c * SR_B_BYTES, SR_B_BYTES, full);
+                    }
+                }
+        }
+        return;
+    }
+
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    const int wp = warp >> 1, half = warp & 1;
+    const int g = lane >> 2, t = lane & 3;
+    int u = 0;   // chunk counter of this warp pair
+    long long kl_have = -1;
+    cplx uk[16];   // U_k values of this thread's 16 outputs
+    for (int i = q0(wp); i < q0(wp + 1); i++) {
+        const long long p = my0 + i;
+        const long long kl = p / nn;
+        if (kl != kl_have) {   // in flight while the DMMAs run
+            kl_have = kl;
+            const cplx* Uk = U + (long long)(k_begin + kl) * nb * nw;
+#pragma unroll
+            for (int e = 0; e < 16; e++) {
+                const int m = (e >> 2) * 8 + g, n = half * 16 + ((e >> 1) & 1) * 8 + 2 * t + (e & 1);
+                uk[e] = (m < nb && n < nw) ? __ldg(Uk + m + (long long)n * nb) : make_double2(0.0, 0.0);
+            }
+        }
+        double p1[4][2][2], p2[4][2][2], p3[4][2][2];
+#pragma unroll
+        for (int a = 0; a < 4; a++)
+#pragma unroll
+            for (int b = 0; b < 2; b++)
+#pragma unroll
+                for (int e = 0; e < 2; e++) p1[a][b][e] = p2[a][b][e] = p3[a][b][e] = 0.0;
+#pragma unroll 1
+        for (int c = 0; c < SR_NCH; c++, u++) {
+            const int s = u % SR_SLOTS;
+            const uint32_t full = bar_base + 16u * (wp * SR_SLOTS + s);
+            mbar_wait(full, (uint32_t)(u / SR_SLOTS) & 1u);
+            const cplx* Ap = reinterpret_cast<const cplx*>(smem_raw + (size_t)(wp * SR_SLOTS + s) * SR_SLOT_BYTES) + lane;
+            const cplx* Bp = Ap + (SR_A_BYTES + half * SR_B_BYTES) / 16;
+#pragma unroll
+            for (int ks = 0; ks < SR_KS; ks++) {
+                double qa[12], qb[6];
+#pragma unroll
+                for (int j = 0; j < 6; j++) {
+                    const cplx y = Ap[(ks * 6 + j) * 32];
+                    qa[2 * j] = y.x;
+                    qa[2 * j + 1] = y.y;
+                }
+#pragma unroll
+                for (int j = 0; j < 3; j++) {
+                    const cplx y = Bp[(ks * 3 + j) * 32];
+                    qb[2 * j] = y.x;
+                    qb[2 * j + 1] = y.y;
+                }
+#pragma unroll
+                for (int mt = 0; mt < 4; mt++)
+#pragma unroll
+                    for (int nt = 0; nt < 2; nt++) {
+                        dmma884(p1[mt][nt][0], p1[mt][nt][1], qa[3 * mt + 2], qb[3 * nt]);
+                        dmma884(p2[mt][nt][0], p2[mt][nt][1], qa[3 * mt], qb[3 * nt + 1]);
+                        dmma884(p3[mt][nt][0], p3[mt][nt][1], qa[3 * mt + 1], qb[3 * nt + 2]);
+                    }
+            }
+            // generic-proxy reads of the slot before the producer's next async-proxy write into it
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(full + 8u);
+        }
+        // epilogue: MU, diag(U_k^H MU) (complete: the warp holds all rows), ||MU||_F^2 of this half
+        cplx* mu = MU + p * (long long)nb * nw;
+        cplx d[2][2];
+        double f = 0.0;
+#pragma unroll
+        for (int nt = 0; nt < 2; nt++)
+#pragma unroll
+            for (int j = 0; j < 2; j++) d[nt][j] = make_double2(0.0, 0.0);
+#pragma unroll
+        for (int mt = 0; mt < 4; mt++)
+#pragma unroll
+            for (int nt = 0; nt < 2; nt++)
+#pragma unroll
+                for (int j = 0; j < 2; j++) {
+                    const cplx x = make_double2(p1[mt][nt][j] - p3[mt][nt][j], p1[mt][nt][j] + p2[mt][nt][j]);
+                    const int m = mt * 8 + g, n = half * 16 + nt * 8 + 2 * t + j;
+                    if (m < nb && n < nw) {
+                        mu[m + (long long)n * nb] = x;
+                        cfma_conj(d[nt][j], uk[(mt * 2 + nt) * 2 + j], x);
+                    }
+                    f = fma(x.x, x.x, f);
+                    f = fma(x.y, x.y, f);
+                }
+#pragma unroll
+        for (int nt = 0; nt < 2; nt++)
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+#pragma unroll
+                for (int o = 4; o < 32; o <<= 1) {
+                    d[nt][j].x += __shfl_xor_sync(0xffffffffu, d[nt][j].x, o);
+                    d[nt][j].y += __shfl_xor_sync(0xffffffffu, d[nt][j].y, o);
+                }
+            }
+        f = warp_sum(f);
+        if (g == 0) {
+#pragma unroll
+            for (int nt = 0; nt < 2; nt++)
+#pragma unroll
+                for (int j = 0; j < 2; j++) {
+                    const int n = half * 16 + nt * 8 + 2 * t + j;
+                    if (n < nw) dN[p * nw + n] = d[nt][j];
+                }
+        }
+        if (lane == 0) frop[p * 2 + half] = f;
+    }
+}
+
 // dN[pair][n] = sum_wm dNp[pair][wm][n];  fro[pair] = sum frop[pair][:]   (fixed order)
 __global__ void __launch_bounds__(128) combine_partials_kernel(int nw, int WM, int nfro, long long pair_off,
                                                                const cplx* __restrict__ dNp,
@@ -600,7 +795,12 @@ int wb_dmma_plan_create(wb200_ctx* ctx, const double* /*hM*/) {
     const int nb = ctx->nb, nw = ctx->nw;
     if (nb > 256 || (nb <= 32 && nw > 32)) return WB200_OK;  // CUDA-core path
     DmmaPlan* p = new DmmaPlan();
-    if (nb <= 32) { p->small = true; p->WM = 1; p->WN = 2; p->KC = 32; p->smem = 0; }
+    if (nb <= 32) {
+        p->small = true; p->WM = 1; p->WN = 2; p->KC = 32; p->smem = 0;
+        const char* e = getenv("WB200_SMALL_RING");
+        p->small_ring = !(e && e[0] == '0');
+        cudaDeviceGetAttribute(&p->num_sms, cudaDevAttrMultiProcessorCount, ctx->device);
+    }
     else if (nb <= 64) { p->WM = 2; p->WN = 4; p->KC = 16; p->smem = smem_bytes<WB_CFG_64>(); }
     else if (nb <= 128) { p->WM = 4; p->WN = 2; p->KC = 16; p->smem = smem_bytes<WB_CFG_128>(); }
     else { p->WM = 8; p->WN = 1; p->KC = 8; p->smem = smem_bytes<WB_CFG_256>(); }
@@ -662,9 +862,24 @@ int wb_rotate_dmma(wb200_ctx* ctx, const cplx* dU, int ka, int kb) {
         const long long p0 = (long long)ka * ctx->nn, p1 = (long long)kb * ctx->nn;
         {
             ProfScope ps(ctx, 1);
-            rotate_small_kernel<<<(unsigned)((p1 - p0 + 3) / 4), 256, 0, ctx->stream>>>(
-                ctx->nb, ctx->nw, ctx->nn, p0, p1, ctx->k_begin, ctx->d_kpb, p->d_Mt, p->d_Up, dU, ctx->d_MU,
-                ctx->d_dN, p->d_frop);
+            if (p->small_ring) {
+                static bool attr_done[16] = {false};
+                if (!attr_done[ctx->device & 15]) {
+                    WB_CUDA(ctx, cudaFuncSetAttribute(rotate_small_ring_kernel,
+                                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SR_SMEM));
+                    attr_done[ctx->device & 15] = true;
+                }
+                // persistent: one CTA per SM, each a contiguous range of pairs (4 in flight per CTA)
+                const long long want = (p1 - p0 + 3) / 4;
+                const int grid = (int)(want < p->num_sms ? want : p->num_sms);
+                rotate_small_ring_kernel<<<grid, 384, SR_SMEM, ctx->stream>>>(
+                    ctx->nb, ctx->nw, ctx->nn, p0, p1, ctx->k_begin, ctx->d_kpb, p->d_Mt, p->d_Up, dU, ctx->d_MU,
+                    ctx->d_dN, p->d_frop);
+            } else {
+                rotate_small_kernel<<<(unsigned)((p1 - p0 + 3) / 4), 256, 0, ctx->stream>>>(
+                    ctx->nb, ctx->nw, ctx->nn, p0, p1, ctx->k_begin, ctx->d_kpb, p->d_Mt, p->d_Up, dU, ctx->d_MU,
+                    ctx->d_dN, p->d_frop);
+            }
         }
         WB_LAUNCH_CHECK(ctx);
         ctx->fro_src = p->d_frop;   // pair_reduce_kernel adds the two half-tile norms itself

@@ -1,5 +1,4 @@
-// stiefel.cu — per-k Stiefel-manifold operations, the (X, Y) disentanglement chain and the flat
-// vector kernels the device-resident optimiser needs.
+// stiefel.cu — per-k Stiefel-manifold operations and the (X, Y) disentanglement chain.
 //
 // Replaces (reference tree):
 //   Optim.Stiefel_SVD project_tangent! / retract!  (third-party Optim.jl; call sites
@@ -9,6 +8,8 @@
 //                  [X_k col-major ; Y_k col-major], so no copy is made)
 //   GU_to_GX_GY    src/localization/disentangle.jl:481-501
 #include "common.cuh"
+
+#include <algorithm>
 
 // ---------------------------------------------------------------------------------------------
 // S <- (S + S^H)/2 for a batch of n x n matrices (contiguous)
@@ -134,6 +135,31 @@ static int retract_strided(wb200_ctx* ctx, cplx* dX, int nrow, int ncol, int ld,
     int it = 0;
     double err = 0.0;
     const bool tensor = wb_zgemm_dmma_applicable(ctx, nrow, ncol) && ld == nrow && stride == (long long)nrow * ncol;
+    if (tensor) {
+        // both GEMMs on the tensor pipe; X ping-pongs between the caller's array and tmp2, so an
+        // iteration is two GEMMs and the error pass, with no copy back
+        cplx *cur = dX, *other = ctx->d_tmp2;
+        for (; it < MAXIT; it++) {
+            WB_TRY(wb_zgemm_dmma(ctx, 1, cur, cur, ctx->d_tmp1, count));   // P = X^H X
+            WB_CUDA(ctx, cudaMemsetAsync(ctx->d_scal, 0, sizeof(double), ctx->stream));
+            ns_prepare_kernel<<<count, 256, 0, ctx->stream>>>(ncol, ctx->d_tmp1, ctx->d_scal, it == 0);
+            WB_LAUNCH_CHECK(ctx);
+            WB_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, ctx->d_scal, sizeof(double),
+                                         cudaMemcpyDeviceToHost, ctx->stream));
+            WB_TRY(wb_zgemm_dmma(ctx, 0, cur, ctx->d_tmp1, other, count));   // X T
+            std::swap(cur, other);
+            WB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            err = ctx->h_pinned[0];
+            if (!(err == err)) {
+                ctx->err = "retract: NaN in X^H X";
+                return WB200_ERR_NOCONV;
+            }
+            if (err < TOL) { it++; break; }
+        }
+        if (cur != dX)
+            WB_CUDA(ctx, cudaMemcpyAsync(dX, cur, sizeof(cplx) * (size_t)count * nrow * ncol,
+                                         cudaMemcpyDeviceToDevice, ctx->stream));
+    } else
     for (; it < MAXIT; it++) {
         ZgemmArgs a{};
         a.m = ncol; a.n = ncol; a.k = nrow;
@@ -141,8 +167,7 @@ static int retract_strided(wb200_ctx* ctx, cplx* dX, int nrow, int ncol, int ld,
         a.B = dX; a.strideB = stride; a.ldb = ld; a.transB = 0;
         a.C = ctx->d_tmp1; a.strideC = (long long)ncol * ncol; a.ldc = ncol;
         a.alpha = 1.0; a.beta = 0.0; a.batch = count;
-        if (tensor) WB_TRY(wb_zgemm_dmma(ctx, 1, dX, dX, ctx->d_tmp1, count));   // P = X^H X
-        else WB_TRY(wb_zgemm_batched(ctx, a));
+        WB_TRY(wb_zgemm_batched(ctx, a));   // P = X^H X
         WB_CUDA(ctx, cudaMemsetAsync(ctx->d_scal, 0, sizeof(double), ctx->stream));
         ns_prepare_kernel<<<count, 256, 0, ctx->stream>>>(ncol, ctx->d_tmp1, ctx->d_scal, it == 0);
         WB_LAUNCH_CHECK(ctx);
@@ -154,8 +179,7 @@ static int retract_strided(wb200_ctx* ctx, cplx* dX, int nrow, int ncol, int ld,
         b.B = ctx->d_tmp1; b.strideB = (long long)ncol * ncol; b.ldb = ncol; b.transB = 0;
         b.C = ctx->d_tmp2; b.strideC = (long long)nrow * ncol; b.ldc = nrow;
         b.alpha = 1.0; b.beta = 0.0; b.batch = count;
-        if (tensor) WB_TRY(wb_zgemm_dmma(ctx, 0, dX, ctx->d_tmp1, ctx->d_tmp2, count));   // X T
-        else WB_TRY(wb_zgemm_batched(ctx, b));
+        WB_TRY(wb_zgemm_batched(ctx, b));   // X T
         const long long total = (long long)count * nrow * ncol;
         if (ld == nrow && stride == (long long)nrow * ncol) {
             WB_CUDA(ctx, cudaMemcpyAsync(dX, ctx->d_tmp2, sizeof(cplx) * total,
@@ -254,106 +278,4 @@ int wb_gu_to_gxy(wb200_ctx* ctx, const cplx* dXY, const cplx* dGU, cplx* dGXY) {
         WB_LAUNCH_CHECK(ctx);
     }
     return WB200_OK;
-}
-
-// ---------------------------------------------------------------------------------------------
-// flat vector kernels (arrays of doubles; complex arrays are passed as 2n doubles)
-// ---------------------------------------------------------------------------------------------
-#define WB_RED_BLOCKS 1184  // 148 SMs x 8
-
-__global__ void __launch_bounds__(256) dot_stage1(const double* __restrict__ a,
-                                                  const double* __restrict__ b, size_t n,
-                                                  double* __restrict__ partial) {
-    double s = 0.0;
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
-         i += (size_t)gridDim.x * blockDim.x)
-        s = fma(a[i], b[i], s);
-    __shared__ double sh[8];
-    s = warp_sum(s);
-    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double t = 0.0;
-        for (int w = 0; w < 8; w++) t += sh[w];
-        partial[blockIdx.x] = t;
-    }
-}
-// complex modulus max (Optim's g_tol is on maximum(abs, g) of the complex array)
-__global__ void __launch_bounds__(256) cabsmax_stage1(const cplx* __restrict__ a, size_t n,
-                                                      double* __restrict__ partial) {
-    double s = 0.0;
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
-         i += (size_t)gridDim.x * blockDim.x) {
-        const cplx v = a[i];
-        s = fmax(s, v.x * v.x + v.y * v.y);
-    }
-    __shared__ double sh[8];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s = fmax(s, __shfl_xor_sync(0xffffffffu, s, o));
-    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double t = 0.0;
-        for (int w = 0; w < 8; w++) t = fmax(t, sh[w]);
-        partial[blockIdx.x] = t;
-    }
-}
-__global__ void __launch_bounds__(256) red_stage2(const double* __restrict__ partial, int n,
-                                                  int is_max, double* __restrict__ out) {
-    double s = 0.0;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) s = is_max ? fmax(s, partial[i]) : s + partial[i];
-    __shared__ double sh[8];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const double t = __shfl_xor_sync(0xffffffffu, s, o);
-        s = is_max ? fmax(s, t) : s + t;
-    }
-    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double t = 0.0;
-        for (int w = 0; w < 8; w++) t = is_max ? fmax(t, sh[w]) : t + sh[w];
-        *out = is_max ? sqrt(t) : t;
-    }
-}
-
-static int red_finish(wb200_ctx* ctx, int is_max, double* out_host) {
-    red_stage2<<<1, 256, 0, ctx->stream>>>(ctx->d_scal + 8, WB_RED_BLOCKS, is_max, ctx->d_scal);
-    WB_LAUNCH_CHECK(ctx);
-    if (ctx->allreduce)   // k-sharded optimiser: vectors are slab-local, scalars are global
-        ctx->allreduce(ctx->d_scal, 1, is_max ? 1 : 0, (void*)ctx->stream, ctx->allreduce_user);
-    WB_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, ctx->d_scal, sizeof(double), cudaMemcpyDeviceToHost,
-                                 ctx->stream));
-    WB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    *out_host = ctx->h_pinned[0];
-    return WB200_OK;
-}
-
-int wb_dot(wb200_ctx* ctx, const double* a, const double* b, size_t n, double* out_host) {
-    dot_stage1<<<WB_RED_BLOCKS, 256, 0, ctx->stream>>>(a, b, n, ctx->d_scal + 8);
-    WB_LAUNCH_CHECK(ctx);
-    return red_finish(ctx, 0, out_host);
-}
-int wb_absmax(wb200_ctx* ctx, const double* a, size_t n, double* out_host) {
-    cabsmax_stage1<<<WB_RED_BLOCKS, 256, 0, ctx->stream>>>((const cplx*)a, n / 2, ctx->d_scal + 8);
-    WB_LAUNCH_CHECK(ctx);
-    return red_finish(ctx, 1, out_host);
-}
-
-__global__ void axpbyz_kernel(double alpha, const double* x, double beta, const double* y, double* z,
-                              size_t n) {  // z may alias x or y (same index only)
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
-         i += (size_t)gridDim.x * blockDim.x)
-        z[i] = alpha * x[i] + (beta == 0.0 ? 0.0 : beta * y[i]);
-}
-int wb_axpbyz(wb200_ctx* ctx, double alpha, const double* x, double beta, const double* y, double* z,
-              size_t n) {
-    const size_t want = (n + 255) / 256;
-    const int blocks = (int)(want < 148 * 16 ? (want ? want : 1) : 148 * 16);
-    axpbyz_kernel<<<blocks, 256, 0, ctx->stream>>>(alpha, x, beta, y, z, n);
-    WB_LAUNCH_CHECK(ctx);
-    return WB200_OK;
-}
-int wb_axpby(wb200_ctx* ctx, double alpha, const double* x, double beta, double* y, size_t n) {
-    return wb_axpbyz(ctx, alpha, x, beta, y, y, n);
 }

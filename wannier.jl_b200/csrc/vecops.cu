@@ -1,0 +1,176 @@
+// vecops.cu — flat-vector kernels of the device-resident optimiser (optimizer.cu).
+//
+// The L-BFGS driver that replaces Optim.optimize(... LBFGS(manifold, HagerZhang, m)) at
+// src/localization/max_localize.jl:73-84 / disentangle.jl:702-713 / opt_rotate.jl:118-141 works on
+// vectors of nk*nb*nw complex numbers (1.07 GB each at the north-star shape), so its cost is HBM
+// passes and host round trips, not flops.  Three fused kernels keep both small:
+//   * cross:   every inner product <a_i, b_j> of up to 3 x 7 vectors in ONE pass over memory (the
+//              Gram rows the two-loop recursion needs) plus max |a_0| (Optim's g_tol test), reduced
+//              in a fixed order (bitwise deterministic) and, in k-sharded runs, all-reduced;
+//   * lincomb: out = beta out + sum_j c_j v_j of up to 7 vectors in one pass (the search direction
+//              straight from the two-loop coefficients, the trial point x + alpha d);
+//   * secant:  s = alpha d and y = g_new - g in one pass.
+// Complex arrays are treated as arrays of double2; inner products are the real ones Optim uses on
+// complex arrays, real(dot(a, b)).
+#include "common.cuh"
+
+namespace {
+
+constexpr int RED_THREADS = 256;
+constexpr int RED_MAX_BLOCKS = 148 * 8;
+
+__global__ void __launch_bounds__(RED_THREADS) cross_stage1(WbCrossArgs p, size_t n2,
+                                                            double* __restrict__ partial) {
+    double acc[WB_CROSS_NA][WB_CROSS_NB];
+    double mx = 0.0;
+#pragma unroll
+    for (int i = 0; i < WB_CROSS_NA; i++)
+#pragma unroll
+        for (int j = 0; j < WB_CROSS_NB; j++) acc[i][j] = 0.0;
+    for (size_t e = blockIdx.x * (size_t)RED_THREADS + threadIdx.x; e < n2;
+         e += (size_t)gridDim.x * RED_THREADS) {
+        double2 b[WB_CROSS_NB], a[WB_CROSS_NA];
+#pragma unroll
+        for (int j = 0; j < WB_CROSS_NB; j++)
+            if (j < p.nb) b[j] = reinterpret_cast<const double2*>(p.b[j])[e];
+#pragma unroll
+        for (int i = 0; i < WB_CROSS_NA; i++)
+            if (i < p.na) a[i] = p.a_in_b ? b[i] : reinterpret_cast<const double2*>(p.a[i])[e];
+        mx = fmax(mx, a[0].x * a[0].x + a[0].y * a[0].y);
+#pragma unroll
+        for (int i = 0; i < WB_CROSS_NA; i++)
+#pragma unroll
+            for (int j = 0; j < WB_CROSS_NB; j++)
+                if (i < p.na && j < p.nb) acc[i][j] = fma(a[i].x, b[j].x, fma(a[i].y, b[j].y, acc[i][j]));
+    }
+    __shared__ double sh[RED_THREADS / 32][WB_CROSS_NOUT];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int i = 0; i < WB_CROSS_NA; i++)
+#pragma unroll
+        for (int j = 0; j < WB_CROSS_NB; j++) {
+            const double v = warp_sum(acc[i][j]);
+            if (lane == 0) sh[warp][i * WB_CROSS_NB + j] = v;
+        }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) sh[warp][WB_CROSS_NOUT - 1] = mx;
+    __syncthreads();
+    if (threadIdx.x < WB_CROSS_NOUT) {
+        const int q = threadIdx.x;
+        double t = 0.0;
+        for (int w = 0; w < RED_THREADS / 32; w++)
+            t = (q == WB_CROSS_NOUT - 1) ? fmax(t, sh[w][q]) : t + sh[w][q];
+        partial[(size_t)blockIdx.x * WB_CROSS_NOUT + q] = t;
+    }
+}
+
+// one CTA: warp w reduces outputs w, w + 8, w + 16 over the block partials in a fixed order
+__global__ void __launch_bounds__(RED_THREADS) cross_stage2(const double* __restrict__ partial, int blocks,
+                                                            double* __restrict__ out) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int q = warp; q < WB_CROSS_NOUT; q += RED_THREADS / 32) {
+        const bool is_max = q == WB_CROSS_NOUT - 1;
+        double t = 0.0;
+        for (int b = lane; b < blocks; b += 32) {
+            const double v = partial[(size_t)b * WB_CROSS_NOUT + q];
+            t = is_max ? fmax(t, v) : t + v;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double v = __shfl_xor_sync(0xffffffffu, t, o);
+            t = is_max ? fmax(t, v) : t + v;
+        }
+        if (lane == 0) out[q] = t;
+    }
+}
+
+__global__ void __launch_bounds__(256) lincomb_kernel(WbLinArgs p, double2* out, size_t n2) {
+    for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < n2;
+         e += (size_t)gridDim.x * blockDim.x) {
+        double2 r = make_double2(0.0, 0.0);
+        if (p.beta != 0.0) {
+            const double2 o = out[e];
+            r = make_double2(p.beta * o.x, p.beta * o.y);
+        }
+#pragma unroll
+        for (int j = 0; j < WB_CROSS_NB; j++)
+            if (j < p.nv) {
+                const double2 v = reinterpret_cast<const double2*>(p.v[j])[e];
+                r.x = fma(p.c[j], v.x, r.x);
+                r.y = fma(p.c[j], v.y, r.y);
+            }
+        out[e] = r;
+    }
+}
+
+__global__ void __launch_bounds__(256) secant_kernel(double alpha, const double2* __restrict__ d,
+                                                     const double2* __restrict__ gnew,
+                                                     const double2* __restrict__ g, double2* __restrict__ s,
+                                                     double2* __restrict__ y, size_t n2) {
+    for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < n2;
+         e += (size_t)gridDim.x * blockDim.x) {
+        const double2 dv = d[e], a = gnew[e], b = g[e];
+        s[e] = make_double2(alpha * dv.x, alpha * dv.y);
+        y[e] = make_double2(a.x - b.x, a.y - b.y);
+    }
+}
+
+int stream_blocks(size_t n2) {
+    const size_t want = (n2 + 255) / 256;
+    return (int)(want < 148 * 16 ? (want ? want : 1) : 148 * 16);
+}
+
+}  // namespace
+
+// Launches the cross products; the WB_CROSS_NOUT results (row-major [na][7] sums, then max |a_0|^2)
+// are copied to ctx->h_pinned + WB_PIN_CROSS and are valid after the next stream synchronisation.
+int wb_cross_launch(wb200_ctx* ctx, const WbCrossArgs& p, size_t n) {
+    if (p.na < 1 || p.na > WB_CROSS_NA || p.nb < 1 || p.nb > WB_CROSS_NB || (n & 1) ||
+        (p.a_in_b && p.na > p.nb)) {
+        ctx->err = "wb_cross_launch: bad arguments";
+        return WB200_ERR_ARG;
+    }
+    const size_t n2 = n / 2;
+    const size_t want = (n2 + RED_THREADS - 1) / RED_THREADS;
+    const int blocks = (int)(want < (size_t)RED_MAX_BLOCKS ? (want ? want : 1) : RED_MAX_BLOCKS);
+    if (!ctx->d_red) WB_CUDA(ctx, cudaMalloc(&ctx->d_red, sizeof(double) * WB_CROSS_NOUT * (RED_MAX_BLOCKS + 1)));
+    double* out = ctx->d_red + (size_t)WB_CROSS_NOUT * RED_MAX_BLOCKS;
+    cross_stage1<<<blocks, RED_THREADS, 0, ctx->stream>>>(p, n2, ctx->d_red);
+    WB_LAUNCH_CHECK(ctx);
+    cross_stage2<<<1, RED_THREADS, 0, ctx->stream>>>(ctx->d_red, blocks, out);
+    WB_LAUNCH_CHECK(ctx);
+    if (ctx->allreduce) {   // k-sharded optimiser: the vectors are slab-local, the scalars global
+        ctx->allreduce(out, WB_CROSS_NOUT - 1, 0, (void*)ctx->stream, ctx->allreduce_user);
+        ctx->allreduce(out + WB_CROSS_NOUT - 1, 1, 1, (void*)ctx->stream, ctx->allreduce_user);
+    }
+    WB_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned + WB_PIN_CROSS, out, sizeof(double) * WB_CROSS_NOUT,
+                                 cudaMemcpyDeviceToHost, ctx->stream));
+    return WB200_OK;
+}
+
+int wb_lincomb(wb200_ctx* ctx, const WbLinArgs& p, double* out, size_t n) {
+    if (p.nv < 0 || p.nv > WB_CROSS_NB || (n & 1)) {
+        ctx->err = "wb_lincomb: bad arguments";
+        return WB200_ERR_ARG;
+    }
+    lincomb_kernel<<<stream_blocks(n / 2), 256, 0, ctx->stream>>>(p, reinterpret_cast<double2*>(out), n / 2);
+    WB_LAUNCH_CHECK(ctx);
+    return WB200_OK;
+}
+
+int wb_secant(wb200_ctx* ctx, double alpha, const double* d, const double* gnew, const double* g, double* s,
+              double* y, size_t n) {
+    secant_kernel<<<stream_blocks(n / 2), 256, 0, ctx->stream>>>(
+        alpha, reinterpret_cast<const double2*>(d), reinterpret_cast<const double2*>(gnew),
+        reinterpret_cast<const double2*>(g), reinterpret_cast<double2*>(s), reinterpret_cast<double2*>(y), n / 2);
+    WB_LAUNCH_CHECK(ctx);
+    return WB200_OK;
+}
+
+// y = alpha x + beta y   (kept for the Stiefel projection)
+int wb_axpby(wb200_ctx* ctx, double alpha, const double* x, double beta, double* y, size_t n) {
+    WbLinArgs p{};
+    p.v[0] = x; p.c[0] = alpha; p.nv = 1; p.beta = beta;
+    return wb_lincomb(ctx, p, y, n);
+}
