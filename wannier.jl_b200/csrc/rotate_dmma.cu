@@ -31,6 +31,7 @@
 struct DmmaPlan {
     bool small = false;           // nb <= 32: warp pair per (k,b) pair
     bool small_ring = true;       // ... operands through a bulk-copy ring (WB200_SMALL_RING=0: straight from global)
+    long long small_ring_min = 0;   // fewer pairs than this: the launch-bound problem takes the plain kernel
     int num_sms = 148;
     int WM = 0, WN = 0, KC = 0;   // warp grid (8 consumer warps), k-chunk
     int NB = 0, NC = 0;           // padded rows, columns per CTA
@@ -551,7 +552,8 @@ constexpr int SR_SLOTS = 4;                               // slots per warp pair
 constexpr uint32_t SR_A_BYTES = SR_KS * 6 * 32 * 16;      // 6144
 constexpr uint32_t SR_B_BYTES = SR_KS * 3 * 32 * 16;      // 3072 per column half
 constexpr uint32_t SR_SLOT_BYTES = SR_A_BYTES + 2 * SR_B_BYTES;   // 12288
-constexpr size_t SR_SMEM = (size_t)4 * SR_SLOTS * SR_SLOT_BYTES + 8 * 2 * 4 * SR_SLOTS;
+constexpr size_t SR_RING_BYTES = (size_t)4 * SR_SLOTS * SR_SLOT_BYTES;
+constexpr size_t SR_SMEM = SR_RING_BYTES + 8 * 2 * 4 * SR_SLOTS;
 
 __global__ void __launch_bounds__(384, 1)
 rotate_small_ring_kernel(int nb, int nw, int nn, long long pair0, long long pair_end, int k_begin,
@@ -559,7 +561,7 @@ rotate_small_ring_kernel(int nb, int nw, int nn, long long pair0, long long pair
                          const double* __restrict__ Up, const cplx* __restrict__ U, cplx* __restrict__ MU,
                          cplx* __restrict__ dN, double* __restrict__ frop) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem_raw + (size_t)4 * SR_SLOTS * SR_SLOT_BYTES);
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem_raw + SR_RING_BYTES);
     // bars[(wp*SR_SLOTS + s)*2 + {0 full, 1 empty}]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t ring_base = smem_u32(smem_raw), bar_base = smem_u32(bars);
@@ -586,20 +588,21 @@ rotate_small_ring_kernel(int nb, int nw, int nn, long long pair0, long long pair
     if (warp >= 8) {
         // producer warpgroup (warps 8-11): hands its registers to the consumers; warp 8 drives the rings
         asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-        if (warp != 8) return;
-        // the u-th chunk of a warp pair goes to its slot u % SR_SLOTS.  Lane l keeps the neighbour
-        // index of pair (l % 8) of the current group of 8 of stream l / 8 (one coalesced load per
-        // group), so the issuing lane never waits on a dependent global load between copies.
-        const int w_l = lane >> 3, j_l = lane & 7;
+        if (warp > 9) return;
+        // warp 8 feeds the rings of warp pairs 0-1, warp 9 those of warp pairs 2-3.  The u-th chunk
+        // of a warp pair goes to its slot u % SR_SLOTS.  Lane l keeps the neighbour index of pair
+        // (l % 16) of the current group of 16 of stream l / 16 (one coalesced load per group), so
+        // the issuing lane never waits on a dependent global load between copies.
+        const int wbase = 2 * (warp - 8);
+        const int w_l = wbase + (lane >> 4), j_l = lane & 15;
         const int len_l = q0(w_l + 1) - q0(w_l);
-        int maxlen = 0;
-        for (int w = 0; w < 4; w++) maxlen = max(maxlen, q0(w + 1) - q0(w));
-        for (int qb = 0; qb < maxlen; qb += 8) {
+        const int maxlen = max(q0(wbase + 1) - q0(wbase), q0(wbase + 2) - q0(wbase + 1));
+        for (int qb = 0; qb < maxlen; qb += 16) {
             const int mine = qb + j_l < len_l ? kpb[my0 + q0(w_l) + qb + j_l] : 0;
-            for (int j = 0; j < 8; j++)
-                for (int wp = 0; wp < 4; wp++) {
-                    const long long kp = __shfl_sync(0xffffffffu, mine, wp * 8 + j);
-                    const int q = qb + j;
+            for (int j = 0; j < 16; j++)
+                for (int ws = 0; ws < 2; ws++) {
+                    const long long kp = __shfl_sync(0xffffffffu, mine, ws * 16 + j);
+                    const int wp = wbase + ws, q = qb + j;
                     if (lane != 0 || q >= q0(wp + 1) - q0(wp)) continue;
                     const long long p = my0 + q0(wp) + q;
                     const char* a = reinterpret_cast<const char*>(Mt) + p * 24576;
@@ -625,13 +628,13 @@ rotate_small_ring_kernel(int nb, int nw, int nn, long long pair0, long long pair
     const int wp = warp >> 1, half = warp & 1;
     const int g = lane >> 2, t = lane & 3;
     int u = 0;   // chunk counter of this warp pair
-    long long kl_have = -1;
     cplx uk[16];   // U_k values of this thread's 16 outputs
-    for (int i = q0(wp); i < q0(wp + 1); i++) {
-        const long long p = my0 + i;
-        const long long kl = p / nn;
-        if (kl != kl_have) {   // in flight while the DMMAs run
-            kl_have = kl;
+    long long p = my0 + q0(wp);
+    long long kl = p / nn;
+    int bi = (int)(p - kl * nn);
+    bool fresh = true;
+    for (int i = q0(wp); i < q0(wp + 1); i++, p++) {
+        if (fresh) {   // new k-point (once per nn pairs): its gauge values are in flight while the DMMAs run
             const cplx* Uk = U + (long long)(k_begin + kl) * nb * nw;
 #pragma unroll
             for (int e = 0; e < 16; e++) {
@@ -646,7 +649,7 @@ rotate_small_ring_kernel(int nb, int nw, int nn, long long pair0, long long pair
             for (int b = 0; b < 2; b++)
 #pragma unroll
                 for (int e = 0; e < 2; e++) p1[a][b][e] = p2[a][b][e] = p3[a][b][e] = 0.0;
-#pragma unroll 1
+#pragma unroll
         for (int c = 0; c < SR_NCH; c++, u++) {
             const int s = u % SR_SLOTS;
             const uint32_t full = bar_base + 16u * (wp * SR_SLOTS + s);
@@ -682,10 +685,12 @@ rotate_small_ring_kernel(int nb, int nw, int nn, long long pair0, long long pair
             __syncwarp();
             if (lane == 0) mbar_arrive(full + 8u);
         }
-        // epilogue: MU, diag(U_k^H MU) (complete: the warp holds all rows), ||MU||_F^2 of this half
+        // epilogue: MU, diag(U_k^H MU) (complete: the warp holds all rows), ||MU||_F^2 of this half.
+        // (Deferring it into the next pair's k-steps, as rotate_dmma_kernel does, was measured slower
+        // here: 0.246 vs 0.196 ms at nb = 32, 12^3 k — eight k-steps cannot hide eight slices.)
         cplx* mu = MU + p * (long long)nb * nw;
         cplx d[2][2];
-        double f = 0.0;
+        double f4[2][2] = {{0.0, 0.0}, {0.0, 0.0}};   // independent chains; summed below
 #pragma unroll
         for (int nt = 0; nt < 2; nt++)
 #pragma unroll
@@ -702,8 +707,7 @@ rotate_small_ring_kernel(int nb, int nw, int nn, long long pair0, long long pair
                         mu[m + (long long)n * nb] = x;
                         cfma_conj(d[nt][j], uk[(mt * 2 + nt) * 2 + j], x);
                     }
-                    f = fma(x.x, x.x, f);
-                    f = fma(x.y, x.y, f);
+                    f4[nt][j] = fma(x.x, x.x, fma(x.y, x.y, f4[nt][j]));
                 }
 #pragma unroll
         for (int nt = 0; nt < 2; nt++)
@@ -715,7 +719,7 @@ rotate_small_ring_kernel(int nb, int nw, int nn, long long pair0, long long pair
                     d[nt][j].y += __shfl_xor_sync(0xffffffffu, d[nt][j].y, o);
                 }
             }
-        f = warp_sum(f);
+        const double f = warp_sum((f4[0][0] + f4[0][1]) + (f4[1][0] + f4[1][1]));
         if (g == 0) {
 #pragma unroll
             for (int nt = 0; nt < 2; nt++)
@@ -726,6 +730,8 @@ rotate_small_ring_kernel(int nb, int nw, int nn, long long pair0, long long pair
                 }
         }
         if (lane == 0) frop[p * 2 + half] = f;
+        fresh = ++bi == nn;
+        if (fresh) { bi = 0; kl++; }
     }
 }
 
@@ -800,6 +806,7 @@ int wb_dmma_plan_create(wb200_ctx* ctx, const double* /*hM*/) {
         const char* e = getenv("WB200_SMALL_RING");
         p->small_ring = !(e && e[0] == '0');
         cudaDeviceGetAttribute(&p->num_sms, cudaDevAttrMultiProcessorCount, ctx->device);
+        p->small_ring_min = (long long)p->num_sms * 4 * 2;   // two pairs per warp pair: below that a ring never fills
     }
     else if (nb <= 64) { p->WM = 2; p->WN = 4; p->KC = 16; p->smem = smem_bytes<WB_CFG_64>(); }
     else if (nb <= 128) { p->WM = 4; p->WN = 2; p->KC = 16; p->smem = smem_bytes<WB_CFG_128>(); }
@@ -862,7 +869,7 @@ int wb_rotate_dmma(wb200_ctx* ctx, const cplx* dU, int ka, int kb) {
         const long long p0 = (long long)ka * ctx->nn, p1 = (long long)kb * ctx->nn;
         {
             ProfScope ps(ctx, 1);
-            if (p->small_ring) {
+            if (p->small_ring && p1 - p0 >= p->small_ring_min) {
                 static bool attr_done[16] = {false};
                 if (!attr_done[ctx->device & 15]) {
                     WB_CUDA(ctx, cudaFuncSetAttribute(rotate_small_ring_kernel,
