@@ -143,7 +143,8 @@ def test_silicon_rectangular_fg_and_disentangle_chain(w, silicon):
 def test_stiefel_project_and_retract(w, valence, silicon):
     ctx = make_ctx(w, fixture_stencil(valence), valence["M"], 4)
     rng = np.random.default_rng(7)
-    for (nrow, ncol, count) in ((4, 4, 64), (12, 8, 17), (128, 128, 3), (40, 24, 5)):
+    for (nrow, ncol, count) in ((4, 4, 64), (12, 8, 17), (128, 128, 3), (40, 24, 5), (32, 32, 9), (31, 17, 6),
+                               (9, 9, 5), (18, 9, 7), (1, 1, 3), (33, 32, 2)):
         X = so.stiefel_retract(rng.standard_normal((count, nrow, ncol)) + 1j * rng.standard_normal((count, nrow, ncol)))
         G = rng.standard_normal(X.shape) + 1j * rng.standard_normal(X.shape)
         Gc = w.api.to_abi_U(G)

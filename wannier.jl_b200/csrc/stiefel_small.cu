@@ -144,11 +144,227 @@ __global__ void __launch_bounds__(WB_SMALL_THREADS) project_small_kernel(int nro
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// n <= 32: the same two operations on the FP64 tensor pipe.
+// The kernels above read two 16-byte shared-memory operands per complex multiply-add and run at
+// shared-memory bandwidth.  DMMA.8x8x4 needs one operand element per lane per 512 flops, so for the
+// sizes that dominate max_localize at the reference-like shapes (n_wann <= 32) a CTA of 8 warps
+// owns FOUR matrices (a warp pair each, warp h of the pair computes columns 16 h .. 16 h + 15,
+// zero padded to 32 x 32), keeps them in shared memory (column-major, leading dimension 36 complex
+// so the B-operand / A^H-operand fragment loads are conflict-free) and does every product with the
+// Gauss 3-multiplication complex DMMA of the rotation kernels.
+// ---------------------------------------------------------------------------------------------
+constexpr int S32_LD = 36;
+constexpr int S32_MAT = 32 * S32_LD;   // complex elements per padded matrix
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+// c[(mt*2 + nt)*2 + j] = sum_l opA[m][l] * B[l][n],  m = mt*8 + g,  n = half*16 + nt*8 + 2t + j
+//   AH = true : opA[m][l] = conj(sA[m*LD + l])   (A^H of the column-major array sA)
+//   AH = false: opA[m][l] = sA[l*LD + m]
+//   B[l][n] = loadB(l, n)
+// mtiles: row tiles (of 8) that can be non-zero; ksteps: k-steps (of 4) that can be non-zero.
+template <bool AH, typename LoadB>
+__device__ __forceinline__ void zgemm32(const cplx* __restrict__ sA, LoadB loadB, int mtiles, int ksteps,
+                                        int half, int lane, cplx (&c)[16]) {
+    const int g = lane >> 2, t = lane & 3;
+    double p1[4][2][2], p2[4][2][2], p3[4][2][2];
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int b = 0; b < 2; b++)
+#pragma unroll
+            for (int e = 0; e < 2; e++) p1[a][b][e] = p2[a][b][e] = p3[a][b][e] = 0.0;
+    for (int ks = 0; ks < ksteps; ks++) {
+        double qb[2][3];
+#pragma unroll
+        for (int nt = 0; nt < 2; nt++) {
+            const cplx b = loadB(ks * 4 + t, half * 16 + nt * 8 + g);
+            qb[nt][0] = b.x;
+            qb[nt][1] = b.y - b.x;
+            qb[nt][2] = b.x + b.y;
+        }
+#pragma unroll
+        for (int mt = 0; mt < 4; mt++) {
+            if (mt < mtiles) {
+                const cplx a = AH ? cconj(sA[(mt * 8 + g) * S32_LD + ks * 4 + t]) : sA[(ks * 4 + t) * S32_LD + mt * 8 + g];
+                const double as = a.x + a.y;
+#pragma unroll
+                for (int nt = 0; nt < 2; nt++) {
+                    dmma884(p1[mt][nt][0], p1[mt][nt][1], as, qb[nt][0]);
+                    dmma884(p2[mt][nt][0], p2[mt][nt][1], a.x, qb[nt][1]);
+                    dmma884(p3[mt][nt][0], p3[mt][nt][1], a.y, qb[nt][2]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int mt = 0; mt < 4; mt++)
+#pragma unroll
+        for (int nt = 0; nt < 2; nt++)
+#pragma unroll
+            for (int j = 0; j < 2; j++)
+                c[(mt * 2 + nt) * 2 + j] = make_double2(p1[mt][nt][j] - p3[mt][nt][j], p1[mt][nt][j] + p2[mt][nt][j]);
+}
+
+// zero-padded copy of matrix `mat` (nrow x ncol, leading dimension ld) into smem, by the 64 threads of its warp pair
+__device__ __forceinline__ void load32(const cplx* __restrict__ g, int nrow, int ncol, int ld, cplx* sm, int t64) {
+    for (int e = t64; e < 32 * 32; e += 64) {
+        const int m = e & 31, n = e >> 5;
+        sm[n * S32_LD + m] = (m < nrow && n < ncol) ? g[n * (long long)ld + m] : make_double2(0.0, 0.0);
+    }
+}
+
+__global__ void __launch_bounds__(256, 1) retract32_kernel(int nrow, int ncol, int ld, long long stride,
+                                                           cplx* __restrict__ X, int count, int maxit,
+                                                           double tol, int* __restrict__ flag) {
+    extern __shared__ cplx sm[];
+    __shared__ double red[8][2];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int q = warp >> 1, half = warp & 1, g = lane >> 2, t = lane & 3;
+    const int mat = blockIdx.x * 4 + q;
+    const bool valid = mat < count;
+    cplx* sX = sm + q * 2 * S32_MAT;
+    cplx* sT = sX + S32_MAT;
+    cplx* gX = X + (long long)(valid ? mat : 0) * stride;
+    load32(gX, valid ? nrow : 0, ncol, ld, sX, tid & 63);
+    __syncthreads();
+    const int kr = (nrow + 3) / 4, kc = (ncol + 3) / 4, tr = (nrow + 7) / 8, tc = (ncol + 7) / 8;
+    bool converged = !valid, bad = false;
+    for (int it = 0; it < maxit; it++) {
+        cplx c[16];
+        // P = X^H X (this warp: columns of its half)
+        zgemm32<true>(sX, [&](int l, int n) { return sX[n * S32_LD + l]; }, tc, kr, half, lane, c);
+        double e2 = 0.0, f2 = 0.0;
+#pragma unroll
+        for (int e = 0; e < 16; e++) {
+            const int m = (e >> 2) * 8 + g, n = half * 16 + ((e >> 1) & 1) * 8 + 2 * t + (e & 1);
+            if (m < ncol && n < ncol) {
+                const double dx = c[e].x - (m == n ? 1.0 : 0.0);
+                e2 += dx * dx + c[e].y * c[e].y;
+                f2 += c[e].x * c[e].x + c[e].y * c[e].y;
+            }
+        }
+        e2 = warp_sum(e2);
+        f2 = warp_sum(f2);
+        if (lane == 0) { red[warp][0] = e2; red[warp][1] = f2; }
+        __syncthreads();
+        const double err = sqrt(red[2 * q][0] + red[2 * q + 1][0]);
+        const double fro = sqrt(red[2 * q][1] + red[2 * q + 1][1]);
+        if (valid && !(err == err)) bad = true;   // NaN input
+        if (valid && err < tol) converged = true;   // the update below takes err -> ~err^2
+        // sigma_max^2 <= 1 + err: Newton-Schulz needs sigma^2 < 3; otherwise (first pass only)
+        // scale by ||P||_F^(-1/2) so that all singular values are <= 1
+        const double s = (it == 0 && err >= 1.9) ? rsqrt(fro) : 1.0;
+        const double s3 = 0.5 * s * s * s;
+        // T = s (1.5 I - 0.5 s^2 P): this warp's columns, which are exactly the ones its X T needs
+#pragma unroll
+        for (int e = 0; e < 16; e++) {
+            const int m = (e >> 2) * 8 + g, n = half * 16 + ((e >> 1) & 1) * 8 + 2 * t + (e & 1);
+            cplx v = make_double2(0.0, 0.0);
+            if (m < ncol && n < ncol) v = make_double2((m == n ? 1.5 * s : 0.0) - s3 * c[e].x, -s3 * c[e].y);
+            sT[n * S32_LD + m] = v;
+        }
+        __syncwarp();
+        zgemm32<false>(sX, [&](int l, int n) { return sT[n * S32_LD + l]; }, tr, kc, half, lane, c);
+        // every warp has finished reading the old X; the CTA stops once all four matrices are done
+        const int all_done = __syncthreads_and(converged || bad);
+#pragma unroll
+        for (int e = 0; e < 16; e++) {
+            const int m = (e >> 2) * 8 + g, n = half * 16 + ((e >> 1) & 1) * 8 + 2 * t + (e & 1);
+            sX[n * S32_LD + m] = c[e];
+        }
+        __syncthreads();
+        if (all_done) break;
+    }
+    if (valid) {
+        for (int e = tid & 63; e < nrow * ncol; e += 64) {
+            const int m = e % nrow, n = e / nrow;
+            gX[n * (long long)ld + m] = sX[n * S32_LD + m];
+        }
+        if ((!converged || bad) && (tid & 63) == 0) atomicMax(flag, 1);
+    }
+}
+
+// G <- G - X (X^H G + G^H X)/2
+__global__ void __launch_bounds__(256, 1) project32_kernel(int nrow, int ncol, int ld, long long stride,
+                                                           const cplx* __restrict__ X, cplx* __restrict__ G,
+                                                           int count) {
+    extern __shared__ cplx sm[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int q = warp >> 1, half = warp & 1, g = lane >> 2, t = lane & 3;
+    const int mat = blockIdx.x * 4 + q;
+    const bool valid = mat < count;
+    cplx* sX = sm + q * 3 * S32_MAT;
+    cplx* sG = sX + S32_MAT;
+    cplx* sS = sG + S32_MAT;
+    const cplx* gX = X + (long long)(valid ? mat : 0) * stride;
+    cplx* gG = G + (long long)(valid ? mat : 0) * stride;
+    load32(gX, valid ? nrow : 0, ncol, ld, sX, tid & 63);
+    load32(gG, valid ? nrow : 0, ncol, ld, sG, tid & 63);
+    __syncthreads();
+    const int kr = (nrow + 3) / 4, kc = (ncol + 3) / 4, tr = (nrow + 7) / 8, tc = (ncol + 7) / 8;
+    cplx c[16];
+    zgemm32<true>(sX, [&](int l, int n) { return sG[n * S32_LD + l]; }, tc, kr, half, lane, c);   // S = X^H G
+#pragma unroll
+    for (int e = 0; e < 16; e++) {
+        const int m = (e >> 2) * 8 + g, n = half * 16 + ((e >> 1) & 1) * 8 + 2 * t + (e & 1);
+        sS[n * S32_LD + m] = c[e];
+    }
+    __syncthreads();   // the Hermitian part needs the other half's columns
+    zgemm32<false>(sX,
+                   [&](int l, int n) {
+                       const cplx a = sS[n * S32_LD + l], b = sS[l * S32_LD + n];
+                       return make_double2(0.5 * (a.x + b.x), 0.5 * (a.y - b.y));
+                   },
+                   tr, kc, half, lane, c);
+    if (valid) {
+#pragma unroll
+        for (int e = 0; e < 16; e++) {
+            const int m = (e >> 2) * 8 + g, n = half * 16 + ((e >> 1) & 1) * 8 + 2 * t + (e & 1);
+            if (m < nrow && n < ncol) {
+                const cplx o = sG[n * S32_LD + m];
+                gG[n * (long long)ld + m] = make_double2(o.x - c[e].x, o.y - c[e].y);
+            }
+        }
+    }
+}
+
 }  // namespace
 
 bool wb_small_applicable(int nrow, int ncol) { return nrow <= WB_SMALL_MAX && ncol <= WB_SMALL_MAX; }
 
+static bool use32(int nrow, int ncol) {
+    static const bool off = [] { const char* e = getenv("WB200_STIEFEL_DMMA"); return e && e[0] == '0'; }();
+    return !off && nrow <= 32 && ncol <= 32;
+}
+
 int wb_retract_small(wb200_ctx* ctx, cplx* dX, int nrow, int ncol, int ld, long long stride, int count) {
+    if (use32(nrow, ncol)) {
+        const size_t smem32 = sizeof(cplx) * 4 * 2 * S32_MAT;
+        static bool attr32[16] = {false};
+        if (!attr32[ctx->device & 15]) {
+            WB_CUDA(ctx, cudaFuncSetAttribute(retract32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32));
+            attr32[ctx->device & 15] = true;
+        }
+        int* flag = reinterpret_cast<int*>(ctx->d_scal + 4);
+        WB_CUDA(ctx, cudaMemsetAsync(flag, 0, sizeof(int), ctx->stream));
+        retract32_kernel<<<(count + 3) / 4, 256, smem32, ctx->stream>>>(nrow, ncol, ld, stride, dX, count, 100, 2e-8, flag);
+        WB_LAUNCH_CHECK(ctx);
+        int* hflag = reinterpret_cast<int*>(ctx->h_pinned + 8);
+        WB_CUDA(ctx, cudaMemcpyAsync(hflag, flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        WB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (*hflag) {
+            ctx->err = "retract: Newton-Schulz polar iteration did not converge (singular or NaN input?)";
+            return WB200_ERR_NOCONV;
+        }
+        return WB200_OK;
+    }
     const size_t smem = sizeof(cplx) * ((size_t)ncol * (nrow + 1) + (size_t)ncol * ncol);
     static bool attr_done[16] = {false};
     if (!attr_done[ctx->device & 15]) {
@@ -172,6 +388,17 @@ int wb_retract_small(wb200_ctx* ctx, cplx* dX, int nrow, int ncol, int ld, long 
 
 int wb_project_small(wb200_ctx* ctx, const cplx* dX, cplx* dG, int nrow, int ncol, int ld, long long stride,
                      int count) {
+    if (use32(nrow, ncol)) {
+        const size_t smem32 = sizeof(cplx) * 4 * 3 * S32_MAT;
+        static bool attr32[16] = {false};
+        if (!attr32[ctx->device & 15]) {
+            WB_CUDA(ctx, cudaFuncSetAttribute(project32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32));
+            attr32[ctx->device & 15] = true;
+        }
+        project32_kernel<<<(count + 3) / 4, 256, smem32, ctx->stream>>>(nrow, ncol, ld, stride, dX, dG, count);
+        WB_LAUNCH_CHECK(ctx);
+        return WB200_OK;
+    }
     const size_t smem = sizeof(cplx) * (2 * (size_t)ncol * (nrow + 1) + (size_t)ncol * ncol);
     static bool attr_done[16] = {false};
     if (!attr_done[ctx->device & 15]) {
