@@ -212,11 +212,19 @@ __device__ __forceinline__ void zgemm32(const cplx* __restrict__ sA, LoadB loadB
                 c[(mt * 2 + nt) * 2 + j] = make_double2(p1[mt][nt][j] - p3[mt][nt][j], p1[mt][nt][j] + p2[mt][nt][j]);
 }
 
-// zero-padded copy of matrix `mat` (nrow x ncol, leading dimension ld) into smem, by the 64 threads of its warp pair
+// zero-padded copy of a matrix (nrow x ncol, leading dimension ld) into smem by the 64 threads of its
+// warp pair; the 16 loads of a thread are issued together (one exposed latency, not sixteen)
 __device__ __forceinline__ void load32(const cplx* __restrict__ g, int nrow, int ncol, int ld, cplx* sm, int t64) {
-    for (int e = t64; e < 32 * 32; e += 64) {
-        const int m = e & 31, n = e >> 5;
-        sm[n * S32_LD + m] = (m < nrow && n < ncol) ? g[n * (long long)ld + m] : make_double2(0.0, 0.0);
+    cplx v[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        const int e = t64 + 64 * k, m = e & 31, n = e >> 5;
+        v[k] = (m < nrow && n < ncol) ? g[n * (long long)ld + m] : make_double2(0.0, 0.0);
+    }
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        const int e = t64 + 64 * k, m = e & 31, n = e >> 5;
+        sm[n * S32_LD + m] = v[k];
     }
 }
 

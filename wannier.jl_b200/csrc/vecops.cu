@@ -19,69 +19,73 @@ namespace {
 constexpr int RED_THREADS = 256;
 constexpr int RED_MAX_BLOCKS = 148 * 8;
 
+// NA x NB inner products in one pass; A_IN_B: a[i] is b[i] (read once)
+template <int NA, int NB, bool A_IN_B>
 __global__ void __launch_bounds__(RED_THREADS) cross_stage1(WbCrossArgs p, size_t n2,
                                                             double* __restrict__ partial) {
-    double acc[WB_CROSS_NA][WB_CROSS_NB];
+    constexpr int NOUT = NA * NB + 1;
+    double acc[NA][NB];
     double mx = 0.0;
 #pragma unroll
-    for (int i = 0; i < WB_CROSS_NA; i++)
+    for (int i = 0; i < NA; i++)
 #pragma unroll
-        for (int j = 0; j < WB_CROSS_NB; j++) acc[i][j] = 0.0;
+        for (int j = 0; j < NB; j++) acc[i][j] = 0.0;
     for (size_t e = blockIdx.x * (size_t)RED_THREADS + threadIdx.x; e < n2;
          e += (size_t)gridDim.x * RED_THREADS) {
-        double2 b[WB_CROSS_NB], a[WB_CROSS_NA];
+        double2 b[NB], a[NA];
 #pragma unroll
-        for (int j = 0; j < WB_CROSS_NB; j++)
-            if (j < p.nb) b[j] = reinterpret_cast<const double2*>(p.b[j])[e];
+        for (int j = 0; j < NB; j++) b[j] = reinterpret_cast<const double2*>(p.b[j])[e];
 #pragma unroll
-        for (int i = 0; i < WB_CROSS_NA; i++)
-            if (i < p.na) a[i] = p.a_in_b ? b[i] : reinterpret_cast<const double2*>(p.a[i])[e];
+        for (int i = 0; i < NA; i++) a[i] = A_IN_B ? b[i < NB ? i : 0] : reinterpret_cast<const double2*>(p.a[i])[e];
         mx = fmax(mx, a[0].x * a[0].x + a[0].y * a[0].y);
 #pragma unroll
-        for (int i = 0; i < WB_CROSS_NA; i++)
+        for (int i = 0; i < NA; i++)
 #pragma unroll
-            for (int j = 0; j < WB_CROSS_NB; j++)
-                if (i < p.na && j < p.nb) acc[i][j] = fma(a[i].x, b[j].x, fma(a[i].y, b[j].y, acc[i][j]));
+            for (int j = 0; j < NB; j++) acc[i][j] = fma(a[i].x, b[j].x, fma(a[i].y, b[j].y, acc[i][j]));
     }
-    __shared__ double sh[RED_THREADS / 32][WB_CROSS_NOUT];
+    __shared__ double sh[RED_THREADS / 32][NOUT];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
-    for (int i = 0; i < WB_CROSS_NA; i++)
+    for (int i = 0; i < NA; i++)
 #pragma unroll
-        for (int j = 0; j < WB_CROSS_NB; j++) {
+        for (int j = 0; j < NB; j++) {
             const double v = warp_sum(acc[i][j]);
-            if (lane == 0) sh[warp][i * WB_CROSS_NB + j] = v;
+            if (lane == 0) sh[warp][i * NB + j] = v;
         }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    if (lane == 0) sh[warp][WB_CROSS_NOUT - 1] = mx;
+    if (lane == 0) sh[warp][NOUT - 1] = mx;
     __syncthreads();
-    if (threadIdx.x < WB_CROSS_NOUT) {
+    if (threadIdx.x < NOUT) {
         const int q = threadIdx.x;
         double t = 0.0;
-        for (int w = 0; w < RED_THREADS / 32; w++)
-            t = (q == WB_CROSS_NOUT - 1) ? fmax(t, sh[w][q]) : t + sh[w][q];
-        partial[(size_t)blockIdx.x * WB_CROSS_NOUT + q] = t;
+        for (int w = 0; w < RED_THREADS / 32; w++) t = (q == NOUT - 1) ? fmax(t, sh[w][q]) : t + sh[w][q];
+        // results in the fixed layout [na][WB_CROSS_NB] + max, whatever NB is
+        const int slot = (q == NOUT - 1) ? WB_CROSS_NOUT - 1 : (q / NB) * WB_CROSS_NB + (q % NB);
+        partial[(size_t)slot * gridDim.x + blockIdx.x] = t;
     }
 }
 
-// one CTA: warp w reduces outputs w, w + 8, w + 16 over the block partials in a fixed order
+// one CTA per output: sums (or maximises) the block partials of that output in a fixed order
 __global__ void __launch_bounds__(RED_THREADS) cross_stage2(const double* __restrict__ partial, int blocks,
                                                             double* __restrict__ out) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int q = warp; q < WB_CROSS_NOUT; q += RED_THREADS / 32) {
-        const bool is_max = q == WB_CROSS_NOUT - 1;
-        double t = 0.0;
-        for (int b = lane; b < blocks; b += 32) {
-            const double v = partial[(size_t)b * WB_CROSS_NOUT + q];
-            t = is_max ? fmax(t, v) : t + v;
-        }
+    const int q = blockIdx.x;
+    const bool is_max = q == WB_CROSS_NOUT - 1;
+    const double* src = partial + (size_t)q * blocks;
+    double t = 0.0;
+    for (int b = threadIdx.x; b < blocks; b += RED_THREADS) t = is_max ? fmax(t, src[b]) : t + src[b];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const double v = __shfl_xor_sync(0xffffffffu, t, o);
-            t = is_max ? fmax(t, v) : t + v;
-        }
-        if (lane == 0) out[q] = t;
+    for (int o = 16; o > 0; o >>= 1) {
+        const double v = __shfl_xor_sync(0xffffffffu, t, o);
+        t = is_max ? fmax(t, v) : t + v;
+    }
+    __shared__ double sh[RED_THREADS / 32];
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = t;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double r = 0.0;
+        for (int w = 0; w < RED_THREADS / 32; w++) r = is_max ? fmax(r, sh[w]) : r + sh[w];
+        out[q] = r;
     }
 }
 
@@ -134,11 +138,35 @@ int wb_cross_launch(wb200_ctx* ctx, const WbCrossArgs& p, size_t n) {
     const size_t n2 = n / 2;
     const size_t want = (n2 + RED_THREADS - 1) / RED_THREADS;
     const int blocks = (int)(want < (size_t)RED_MAX_BLOCKS ? (want ? want : 1) : RED_MAX_BLOCKS);
-    if (!ctx->d_red) WB_CUDA(ctx, cudaMalloc(&ctx->d_red, sizeof(double) * WB_CROSS_NOUT * (RED_MAX_BLOCKS + 1)));
+    if (!ctx->d_red) {
+        const size_t bytes = sizeof(double) * WB_CROSS_NOUT * (RED_MAX_BLOCKS + 1);
+        WB_CUDA(ctx, cudaMalloc(&ctx->d_red, bytes));
+        WB_CUDA(ctx, cudaMemsetAsync(ctx->d_red, 0, bytes, ctx->stream));   // slots a small instantiation never writes
+    }
     double* out = ctx->d_red + (size_t)WB_CROSS_NOUT * RED_MAX_BLOCKS;
-    cross_stage1<<<blocks, RED_THREADS, 0, ctx->stream>>>(p, n2, ctx->d_red);
+    // the shapes the optimiser uses get exact-size instantiations (no predicates, fewer registers);
+    // anything else is padded to 3 x 7 with repeats of the first vector (extra products are ignored)
+    WbCrossArgs a = p;
+    if (p.na == 1 && p.nb == 1 && !p.a_in_b) {
+        cross_stage1<1, 1, false><<<blocks, RED_THREADS, 0, ctx->stream>>>(a, n2, ctx->d_red);
+    } else if (p.na == 1 && p.nb == 1) {
+        cross_stage1<1, 1, true><<<blocks, RED_THREADS, 0, ctx->stream>>>(a, n2, ctx->d_red);
+    } else if (p.na == 1 && p.nb == 3 && p.a_in_b) {
+        cross_stage1<1, 3, true><<<blocks, RED_THREADS, 0, ctx->stream>>>(a, n2, ctx->d_red);
+    } else if (p.na == 3 && p.nb == 7 && p.a_in_b) {
+        cross_stage1<3, 7, true><<<blocks, RED_THREADS, 0, ctx->stream>>>(a, n2, ctx->d_red);
+    } else {
+        for (int i = p.na; i < WB_CROSS_NA; i++) a.a[i] = p.a[0];
+        for (int j = p.nb; j < WB_CROSS_NB; j++) a.b[j] = p.b[0];
+        if (p.a_in_b) {
+            // the prefix property is lost by the padding unless a is read separately
+            for (int i = 0; i < p.na; i++) a.a[i] = p.b[i];
+            for (int i = p.na; i < WB_CROSS_NA; i++) a.a[i] = p.b[0];
+        }
+        cross_stage1<WB_CROSS_NA, WB_CROSS_NB, false><<<blocks, RED_THREADS, 0, ctx->stream>>>(a, n2, ctx->d_red);
+    }
     WB_LAUNCH_CHECK(ctx);
-    cross_stage2<<<1, RED_THREADS, 0, ctx->stream>>>(ctx->d_red, blocks, out);
+    cross_stage2<<<WB_CROSS_NOUT, RED_THREADS, 0, ctx->stream>>>(ctx->d_red, blocks, out);
     WB_LAUNCH_CHECK(ctx);
     if (ctx->allreduce) {   // k-sharded optimiser: the vectors are slab-local, the scalars global
         ctx->allreduce(out, WB_CROSS_NOUT - 1, 0, (void*)ctx->stream, ctx->allreduce_user);
