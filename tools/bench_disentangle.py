@@ -25,5 +25,16 @@ out = dict(fg_xy_ms=1e3 * dt, f=f, kernel=cache.ctx.rotation_kernel)
 t0 = time.perf_counter()
 Umin, info = w.disentangle(model, max_iter=50, return_info=True, cache=cache)
 out["disentangle"] = dict(seconds=time.perf_counter() - t0, **info)
+# the device driver alone (warm; the call above also pays U_to_X_Y on the host and one-off allocations)
+reps = []
+for _ in range(3):
+    XYc = XY.copy()
+    l0 = cache.ctx.launch_count
+    t0 = time.perf_counter()
+    f, iters, nfg = cache.ctx.disentangle(XYc, 1e-7, 1e-5, 50, 3)
+    dt = time.perf_counter() - t0
+    reps.append(dict(seconds=dt, f=f, iterations=iters, n_fg=nfg, ms_per_fg=1e3 * dt / nfg,
+                     launches=cache.ctx.launch_count - l0))
+out["disentangle_driver_warm"] = reps
 print(json.dumps(out))
 json.dump(out, open("gpurun_out/bench_disentangle.json", "w"), indent=1)

@@ -223,13 +223,23 @@ __global__ void __launch_bounds__(128) pair_reduce_kernel(int nw, int nn, int nk
                                                           double* __restrict__ part,
                                                           double* __restrict__ pmin) {
     const int k = blockIdx.x + k_off;
+    // phase 1: one (b, n) element per thread — the atan2 calls (the expensive part) run in parallel
+    // over all nn * nw diagonal elements of the k-point instead of serially over b
+    extern __shared__ double sphi[];            // [nn][nw] phi, then [nn][nw] |N_nn|^2
+    double* sa2 = sphi + nn * nw;
+    for (int i = threadIdx.x; i < nn * nw; i += blockDim.x) {
+        const cplx z = dN[(long long)k * nn * nw + i];
+        sphi[i] = atan2(z.y, z.x);              // imaglog, src/utils/linalg.jl:15
+        sa2[i] = z.x * z.x + z.y * z.y;
+    }
+    __syncthreads();
+    // phase 2: per n, the sums over b in the reference's order
     double sd = 0.0, mn = 1e300;
     for (int n = threadIdx.x; n < nw; n += blockDim.x) {
         double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
         for (int b = 0; b < nn; b++) {
-            const cplx z = dN[((long long)k * nn + b) * nw + n];
-            const double phi = atan2(z.y, z.x);  // imaglog, src/utils/linalg.jl:15
-            const double a2 = z.x * z.x + z.y * z.y;
+            const double phi = sphi[b * nw + n];
+            const double a2 = sa2[b * nw + n];
             const double w = wb[b];
             const double* bv = bvec + ((long long)k * nn + b) * 3;
             s0 += w * bv[0] * phi;
@@ -298,7 +308,19 @@ __global__ void __launch_bounds__(256) sum_over_k_kernel(int nk, int ns, const d
 
 int wb_pair_partial(wb200_ctx* ctx, int ka, int kb) {
     ProfScope ps(ctx, 2);
-    pair_reduce_kernel<<<kb - ka, 128, 0, ctx->stream>>>(ctx->nw, ctx->nn, ctx->nk, ka, ctx->d_dN,
+    const size_t smem = sizeof(double) * 2 * (size_t)ctx->nn * ctx->nw;
+    if (smem > 48 * 1024) {
+        static bool attr_done[16] = {false};
+        if (!attr_done[ctx->device & 15]) {
+            WB_CUDA(ctx, cudaFuncSetAttribute(pair_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            attr_done[ctx->device & 15] = true;
+        }
+        if (smem > 200 * 1024) {
+            ctx->err = "pair_reduce: nn * nw too large for the shared-memory staging";
+            return WB200_ERR_ARG;
+        }
+    }
+    pair_reduce_kernel<<<kb - ka, 128, smem, ctx->stream>>>(ctx->nw, ctx->nn, ctx->nk, ka, ctx->d_dN,
                                                           ctx->fro_src ? ctx->fro_src : ctx->d_fro, ctx->fro_src ? ctx->fro_parts : 1,
                                                           ctx->d_bvec, ctx->d_wb,
                                                           ctx->d_part, ctx->d_pmin);

@@ -231,9 +231,90 @@ int wb_project_xy(wb200_ctx* ctx, const cplx* dXY, cplx* dG) {
 // ---------------------------------------------------------------------------------------------
 // (X, Y) chain
 // ---------------------------------------------------------------------------------------------
+// Small shapes (nb <= 64): one CTA per k-point keeps X_k, Y_k (and G_k) in shared memory and does the
+// whole step in one launch.  The batched 32 x 32-tile GEMM kernel below leaves most of its threads idle
+// on 18 x 9 matrices and needs three launches per evaluation (0.4 of the 0.52 ms of an (X, Y)
+// evaluation at the Cu-like shape were spent there).
+#define WB_XY_SMALL_MAX 64
+
+__global__ void __launch_bounds__(128) xy_to_u_small_kernel(int nb, int nw, long long st,
+                                                            const cplx* __restrict__ XY, cplx* __restrict__ U) {
+    extern __shared__ cplx sxy[];
+    cplx* sX = sxy;                 // [nw][nw] col-major
+    cplx* sY = sxy + nw * nw;       // [nw][nb + 1] col-major, padded
+    const cplx* g = XY + (long long)blockIdx.x * st;
+    for (int e = threadIdx.x; e < nw * nw; e += blockDim.x) sX[e] = g[e];
+    for (int e = threadIdx.x; e < nb * nw; e += blockDim.x) sY[(e / nb) * (nb + 1) + (e % nb)] = g[nw * nw + e];
+    __syncthreads();
+    cplx* u = U + (long long)blockIdx.x * nb * nw;
+    for (int e = threadIdx.x; e < nb * nw; e += blockDim.x) {
+        const int m = e % nb, n = e / nb;
+        cplx acc = make_double2(0.0, 0.0);
+        for (int l = 0; l < nw; l++) cfma(acc, sY[l * (nb + 1) + m], sX[n * nw + l]);   // U = Y X
+        u[e] = acc;
+    }
+}
+
+// G_X = Y^H G_U, G_Y = G_U X^H, then zero G_Y[frozen rows, :] and G_Y[:, 0:n_frozen)   (disentangle.jl:481-501)
+__global__ void __launch_bounds__(128) gu_to_gxy_small_kernel(int nb, int nw, long long st,
+                                                              const cplx* __restrict__ XY,
+                                                              const cplx* __restrict__ GU,
+                                                              const uint8_t* __restrict__ frozen,
+                                                              const int32_t* __restrict__ nfrozen,
+                                                              cplx* __restrict__ GXY) {
+    extern __shared__ cplx sxy[];
+    cplx* sX = sxy;                       // [nw][nw + 1]
+    cplx* sY = sX + nw * (nw + 1);        // [nw][nb + 1]
+    cplx* sG = sY + nw * (nb + 1);        // [nw][nb + 1]
+    const int k = blockIdx.x;
+    const cplx* g = XY + (long long)k * st;
+    const cplx* gu = GU + (long long)k * nb * nw;
+    for (int e = threadIdx.x; e < nw * nw; e += blockDim.x) sX[(e / nw) * (nw + 1) + (e % nw)] = g[e];
+    for (int e = threadIdx.x; e < nb * nw; e += blockDim.x) {
+        sY[(e / nb) * (nb + 1) + (e % nb)] = g[nw * nw + e];
+        sG[(e / nb) * (nb + 1) + (e % nb)] = gu[e];
+    }
+    __syncthreads();
+    cplx* out = GXY + (long long)k * st;
+    for (int e = threadIdx.x; e < nw * nw; e += blockDim.x) {   // G_X[i][n] = sum_m conj(Y[m][i]) G[m][n]
+        const int i = e % nw, n = e / nw;
+        cplx acc = make_double2(0.0, 0.0);
+        for (int m = 0; m < nb; m++) cfma_conj(acc, sY[i * (nb + 1) + m], sG[n * (nb + 1) + m]);
+        out[e] = acc;
+    }
+    const int nf = frozen ? nfrozen[k] : 0;
+    for (int e = threadIdx.x; e < nb * nw; e += blockDim.x) {   // G_Y[m][l] = sum_n G[m][n] conj(X[l][n])
+        const int m = e % nb, l = e / nb;
+        cplx acc = make_double2(0.0, 0.0);
+        if (!(frozen && (frozen[(long long)k * nb + m] || l < nf)))
+            for (int n = 0; n < nw; n++) {
+                const cplx x = sX[n * (nw + 1) + l];
+                cfma(acc, sG[n * (nb + 1) + m], cconj(x));
+            }
+        out[nw * nw + e] = acc;
+    }
+}
+
+static int xy_small_attr(wb200_ctx* ctx) {
+    static bool done[16] = {false};
+    if (!done[ctx->device & 15]) {
+        WB_CUDA(ctx, cudaFuncSetAttribute(xy_to_u_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        WB_CUDA(ctx, cudaFuncSetAttribute(gu_to_gxy_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        done[ctx->device & 15] = true;
+    }
+    return WB200_OK;
+}
+
 int wb_xy_to_u(wb200_ctx* ctx, const cplx* dXY, cplx* dU) {
     const int nb = ctx->nb, nw = ctx->nw;
     const long long st = (long long)nw * nw + (long long)nb * nw;
+    if (nb <= WB_XY_SMALL_MAX) {
+        WB_TRY(xy_small_attr(ctx));
+        const size_t smem = sizeof(cplx) * ((size_t)nw * nw + (size_t)nw * (nb + 1));
+        xy_to_u_small_kernel<<<ctx->nk, 128, smem, ctx->stream>>>(nb, nw, st, dXY, dU);
+        WB_LAUNCH_CHECK(ctx);
+        return WB200_OK;
+    }
     ZgemmArgs a{};
     a.m = nb; a.n = nw; a.k = nw;
     a.A = dXY + (long long)nw * nw; a.strideA = st; a.lda = nb; a.transA = 0;   // Y_k
@@ -258,6 +339,14 @@ __global__ void mask_gy_kernel(int nb, int nw, long long st, const uint8_t* __re
 int wb_gu_to_gxy(wb200_ctx* ctx, const cplx* dXY, const cplx* dGU, cplx* dGXY) {
     const int nb = ctx->nb, nw = ctx->nw;
     const long long st = (long long)nw * nw + (long long)nb * nw;
+    if (nb <= WB_XY_SMALL_MAX) {
+        WB_TRY(xy_small_attr(ctx));
+        const size_t smem = sizeof(cplx) * ((size_t)nw * (nw + 1) + 2 * (size_t)nw * (nb + 1));
+        gu_to_gxy_small_kernel<<<ctx->nk, 128, smem, ctx->stream>>>(nb, nw, st, dXY, dGU, ctx->d_frozen,
+                                                                    ctx->d_nfrozen, dGXY);
+        WB_LAUNCH_CHECK(ctx);
+        return WB200_OK;
+    }
     ZgemmArgs a{};  // G_X = Y^H G_U
     a.m = nw; a.n = nw; a.k = nb;
     a.A = dXY + (long long)nw * nw; a.strideA = st; a.lda = nb; a.transA = 1;
