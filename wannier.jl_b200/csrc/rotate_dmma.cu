@@ -87,6 +87,25 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
         "l"(src), "r"(bytes), "r"(bar)
         : "memory");
 }
+// the same with an L2 eviction policy (createpolicy): the overlaps are streamed once per evaluation
+// (evict first), the packed gauges are re-read by every neighbour (evict last)
+__device__ __forceinline__ void bulk_g2s_hint(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar,
+                                              uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+        "l"(src), "r"(bytes), "r"(bar), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                  : "+d"(c0), "+d"(c1)
@@ -593,6 +612,7 @@ rotate_small_ring_kernel(int nb, int nw, int nn, long long pair0, long long pair
         // of a warp pair goes to its slot u % SR_SLOTS.  Lane l keeps the neighbour index of pair
         // (l % 16) of the current group of 16 of stream l / 16 (one coalesced load per group), so
         // the issuing lane never waits on a dependent global load between copies.
+        const uint64_t pol_a = l2_policy_evict_first(), pol_b = l2_policy_evict_last();
         const int wbase = 2 * (warp - 8);
         const int w_l = wbase + (lane >> 4), j_l = lane & 15;
         const int len_l = q0(w_l + 1) - q0(w_l);
@@ -615,9 +635,9 @@ rotate_small_ring_kernel(int nb, int nw, int nn, long long pair0, long long pair
                         mbar_wait(empty, ((uint32_t)(u / SR_SLOTS) & 1u) ^ 1u);
                         mbar_arrive_expect_tx(full, SR_SLOT_BYTES);
                         const uint32_t dst = ring_base + (uint32_t)(wp * SR_SLOTS + s) * SR_SLOT_BYTES;
-                        bulk_g2s(dst, a + c * SR_A_BYTES, SR_A_BYTES, full);
-                        bulk_g2s(dst + SR_A_BYTES, b + c * SR_B_BYTES, SR_B_BYTES, full);
-                        bulk_g2s(dst + SR_A_BYTES + SR_B_BYTES, b + 12288 + c * SR_B_BYTES, SR_B_BYTES, full);
+                        bulk_g2s_hint(dst, a + c * SR_A_BYTES, SR_A_BYTES, full, pol_a);
+                        bulk_g2s_hint(dst + SR_A_BYTES, b + c * SR_B_BYTES, SR_B_BYTES, full, pol_b);
+                        bulk_g2s_hint(dst + SR_A_BYTES + SR_B_BYTES, b + 12288 + c * SR_B_BYTES, SR_B_BYTES, full, pol_b);
                     }
                 }
         }
