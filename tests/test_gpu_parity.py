@@ -217,6 +217,12 @@ def test_disentangle_driver(w, silicon):
     ("bcc", (3, 3, 3), 32, 32),       # config 3 shape
     ("cubic", (1, 1, 1), 5, 3),       # single k-point, all neighbours are the point itself
     ("cubic", (2, 2, 2), 260, 20),    # nb > 256: CUDA-core kernel only
+    # >= 1184 pairs with nb <= 32: the persistent ring kernel (rotate_small_ring_kernel); pair counts
+    # that do not divide by the CTA / warp-pair split, padded rows and columns, rectangular U
+    ("fcc", (6, 6, 6), 18, 9),
+    ("bcc", (5, 5, 5), 32, 32),
+    ("cubic", (8, 8, 5), 7, 7),
+    ("bcc", (5, 4, 5), 31, 17),
 ])
 def test_synthetic_both_kernels(w, lat, grid, nb, nw):
     st, M, U = w.synthetic.make_model_arrays(lat, grid, nb, nw)
