@@ -218,6 +218,9 @@ rotate_dmma_kernel(int nb, int nw, int nn, int nch, int nct, int k_begin, int k_
         mbar_wait(bar_base + 8u * (STAGES + s), (round & 1u) ^ 1u);
         const uint32_t full = bar_base + 8u * s;
         mbar_arrive_expect_tx(full, A_BYTES + B_BYTES);
+        // (L2 eviction policies on these copies were measured and make no difference here: evict-first
+        // on the overlaps costs DRAM reads, 28.5 -> 33.0 GB — the four column-tile CTAs of a k-point
+        // re-fetch them — and evict-last on the gauges changes nothing, 28.3 GB; profiles/r1f_summary.md)
         bulk_g2s(sA_base + s * A_BYTES, Mt + (pair * nch + c) * (long long)(A_D2 * 2), A_BYTES, full);
         bulk_g2s(sB_base + s * B_BYTES, Up + ((kp * nct + ct) * nch + c) * (long long)(B_D2 * 2),
                  B_BYTES, full);
