@@ -180,6 +180,10 @@ def test_max_localize_reaches_reference_optimum(w, valence):
     # same algorithm as the oracle's driver: same iteration count and optimum
     Uo, fo, ito, _ = so.max_localize(*oracle_args(valence), valence["U_ptg"], f_tol=1e-13, g_tol=1e-8, max_iter=500)
     assert abs(fo - info["f"]) < 1e-9
+    # other history sizes (the Gram pass is chunked above 3 pairs): same optimum
+    for hist in (1, 5, 9):
+        U, info = w.max_localize(model, f_tol=1e-13, g_tol=1e-8, max_iter=500, history_size=hist, return_info=True)
+        assert abs(info["f"] - ref[0]) < 1e-8, hist
     with pytest.raises(ValueError):   # max_localize.jl:52-53
         w.max_localize(w.Model(valence["lattice"], st, np.zeros((64, 8, 5, 5), complex), np.zeros((64, 5, 4), complex)))
 
