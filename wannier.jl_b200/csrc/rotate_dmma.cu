@@ -577,6 +577,8 @@ constexpr uint32_t SR_SLOT_BYTES = SR_A_BYTES + 2 * SR_B_BYTES;   // 12288
 constexpr size_t SR_RING_BYTES = (size_t)4 * SR_SLOTS * SR_SLOT_BYTES;
 constexpr size_t SR_SMEM = SR_RING_BYTES + 8 * 2 * 4 * SR_SLOTS;
 
+// FULL: nb > 28 and nw > 24, nothing to skip: no predicates in the main loop
+template <bool FULL>
 __global__ void __launch_bounds__(384, 1)
 rotate_small_ring_kernel(int nb, int nw, int nn, long long pair0, long long pair_end, int k_begin,
                          const int32_t* __restrict__ kpb, const double* __restrict__ Mt,
@@ -602,6 +604,12 @@ rotate_small_ring_kernel(int nb, int nw, int nn, long long pair0, long long pair
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+
+    // zero padding is never multiplied: k-steps, row tiles and column tiles beyond nb / nw are skipped
+    // (at nb = 18, nw = 9 that leaves 5 of 8 k-steps, 3 of 4 row tiles and one of the two column
+    // halves), and chunks that hold only padding are neither copied nor waited for
+    const int ksteps = (nb + 3) / 4, mtiles = (nb + 7) / 8;
+    const int nch_act = FULL ? SR_NCH : (ksteps + SR_KS - 1) / SR_KS;
 
     // warp pair w owns the contiguous quarter [q0(w), q0(w + 1)) of the CTA's pairs: consecutive pairs
     // share k (nn neighbours each), so the U_k values of the epilogue are reloaded once per k-point
@@ -632,7 +640,8 @@ rotate_small_ring_kernel(int nb, int nw, int nn, long long pair0, long long pair
                     const char* b = reinterpret_cast<const char*>(Up) + kp * 24576;
 #pragma unroll
                     for (int c = 0; c < SR_NCH; c++) {
-                        const int u = q * SR_NCH + c;
+                        if (!FULL && c >= nch_act) break;
+                        const int u = q * nch_act + c;
                         const int s = u % SR_SLOTS;
                         const uint32_t full = bar_base + 16u * (wp * SR_SLOTS + s), empty = full + 8u;
                         mbar_wait(empty, ((uint32_t)(u / SR_SLOTS) & 1u) ^ 1u);
@@ -648,9 +657,23 @@ rotate_small_ring_kernel(int nb, int nw, int nn, long long pair0, long long pair
     }
 
     asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
-    const int wp = warp >> 1, half = warp & 1;
+    // column half of this warp; swapped in warp pairs 2-3 so that, when only half 0 has columns
+    // (nw <= 16), the four working warps sit on four different SMSPs
+    const int wp = warp >> 1, half = (warp & 1) ^ ((warp >> 2) & 1);
     const int g = lane >> 2, t = lane & 3;
+    const int ntiles = nw - half * 16 >= 16 ? 2 : (nw - half * 16 + 7) / 8;   // <= 0: no columns at all
     int u = 0;   // chunk counter of this warp pair
+    if (!FULL && ntiles <= 0) {   // nothing to compute: keep the ring protocol going, report a zero norm
+        for (int i = q0(wp); i < q0(wp + 1); i++) {
+            for (int c = 0; c < nch_act; c++, u++) {
+                const uint32_t full = bar_base + 16u * (wp * SR_SLOTS + u % SR_SLOTS);
+                mbar_wait(full, (uint32_t)(u / SR_SLOTS) & 1u);
+                if (lane == 0) mbar_arrive(full + 8u);
+            }
+            if (lane == 0) frop[(my0 + i) * 2 + half] = 0.0;
+        }
+        return;
+    }
     cplx uk[16];   // U_k values of this thread's 16 outputs
     long long p = my0 + q0(wp);
     long long kl = p / nn;
@@ -673,7 +696,8 @@ rotate_small_ring_kernel(int nb, int nw, int nn, long long pair0, long long pair
 #pragma unroll
                 for (int e = 0; e < 2; e++) p1[a][b][e] = p2[a][b][e] = p3[a][b][e] = 0.0;
 #pragma unroll
-        for (int c = 0; c < SR_NCH; c++, u++) {
+        for (int c = 0; c < SR_NCH; c++) {
+            if (!FULL && c >= nch_act) break;
             const int s = u % SR_SLOTS;
             const uint32_t full = bar_base + 16u * (wp * SR_SLOTS + s);
             mbar_wait(full, (uint32_t)(u / SR_SLOTS) & 1u);
@@ -681,6 +705,7 @@ rotate_small_ring_kernel(int nb, int nw, int nn, long long pair0, long long pair
             const cplx* Bp = Ap + (SR_A_BYTES + half * SR_B_BYTES) / 16;
 #pragma unroll
             for (int ks = 0; ks < SR_KS; ks++) {
+                if (!FULL && c * SR_KS + ks >= ksteps) break;
                 double qa[12], qb[6];
 #pragma unroll
                 for (int j = 0; j < 6; j++) {
@@ -698,15 +723,18 @@ rotate_small_ring_kernel(int nb, int nw, int nn, long long pair0, long long pair
                 for (int mt = 0; mt < 4; mt++)
 #pragma unroll
                     for (int nt = 0; nt < 2; nt++) {
-                        dmma884(p1[mt][nt][0], p1[mt][nt][1], qa[3 * mt + 2], qb[3 * nt]);
-                        dmma884(p2[mt][nt][0], p2[mt][nt][1], qa[3 * mt], qb[3 * nt + 1]);
-                        dmma884(p3[mt][nt][0], p3[mt][nt][1], qa[3 * mt + 1], qb[3 * nt + 2]);
+                        if (FULL || (mt < mtiles && nt < ntiles)) {
+                            dmma884(p1[mt][nt][0], p1[mt][nt][1], qa[3 * mt + 2], qb[3 * nt]);
+                            dmma884(p2[mt][nt][0], p2[mt][nt][1], qa[3 * mt], qb[3 * nt + 1]);
+                            dmma884(p3[mt][nt][0], p3[mt][nt][1], qa[3 * mt + 1], qb[3 * nt + 2]);
+                        }
                     }
             }
             // generic-proxy reads of the slot before the producer's next async-proxy write into it
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(full + 8u);
+            u++;
         }
         // epilogue: MU, diag(U_k^H MU) (complete: the warp holds all rows), ||MU||_F^2 of this half.
         // (Deferring it into the next pair's k-steps, as rotate_dmma_kernel does, was measured slower
@@ -895,16 +923,23 @@ int wb_rotate_dmma(wb200_ctx* ctx, const cplx* dU, int ka, int kb) {
             if (p->small_ring && p1 - p0 >= p->small_ring_min) {
                 static bool attr_done[16] = {false};
                 if (!attr_done[ctx->device & 15]) {
-                    WB_CUDA(ctx, cudaFuncSetAttribute(rotate_small_ring_kernel,
+                    WB_CUDA(ctx, cudaFuncSetAttribute(rotate_small_ring_kernel<true>,
+                                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SR_SMEM));
+                    WB_CUDA(ctx, cudaFuncSetAttribute(rotate_small_ring_kernel<false>,
                                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SR_SMEM));
                     attr_done[ctx->device & 15] = true;
                 }
                 // persistent: one CTA per SM, each a contiguous range of pairs (4 in flight per CTA)
                 const long long want = (p1 - p0 + 3) / 4;
                 const int grid = (int)(want < p->num_sms ? want : p->num_sms);
-                rotate_small_ring_kernel<<<grid, 384, SR_SMEM, ctx->stream>>>(
-                    ctx->nb, ctx->nw, ctx->nn, p0, p1, ctx->k_begin, ctx->d_kpb, p->d_Mt, p->d_Up, dU, ctx->d_MU,
-                    ctx->d_dN, p->d_frop);
+                if (ctx->nb > 28 && ctx->nw > 24)
+                    rotate_small_ring_kernel<true><<<grid, 384, SR_SMEM, ctx->stream>>>(
+                        ctx->nb, ctx->nw, ctx->nn, p0, p1, ctx->k_begin, ctx->d_kpb, p->d_Mt, p->d_Up, dU, ctx->d_MU,
+                        ctx->d_dN, p->d_frop);
+                else
+                    rotate_small_ring_kernel<false><<<grid, 384, SR_SMEM, ctx->stream>>>(
+                        ctx->nb, ctx->nw, ctx->nn, p0, p1, ctx->k_begin, ctx->d_kpb, p->d_Mt, p->d_Up, dU, ctx->d_MU,
+                        ctx->d_dN, p->d_frop);
             } else {
                 rotate_small_kernel<<<(unsigned)((p1 - p0 + 3) / 4), 256, 0, ctx->stream>>>(
                     ctx->nb, ctx->nw, ctx->nn, p0, p1, ctx->k_begin, ctx->d_kpb, p->d_Mt, p->d_Up, dU, ctx->d_MU,
