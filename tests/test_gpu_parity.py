@@ -140,6 +140,37 @@ def test_silicon_rectangular_fg_and_disentangle_chain(w, silicon):
     ctx.close()
 
 
+@pytest.mark.parametrize("lat,grid,nb,nw,nfroz", [
+    ("fcc", (3, 3, 3), 18, 9, 5),      # config 2 shape: fused single-launch (X, Y) kernels (nb <= 64)
+    ("cubic", (2, 2, 2), 40, 24, 7),   # fused kernels, CUDA-core Stiefel kernels (32 < n <= 64)
+    ("fcc", (2, 2, 2), 72, 40, 9),     # nb > 64: batched-GEMM (X, Y) chain
+])
+def test_synthetic_xy_chain_and_disentangle(w, lat, grid, nb, nw, nfroz):
+    # disentangle.jl:351-356, 424-466, 481-548: U = Y X, G_X = Y^H G_U, G_Y = G_U X^H with the frozen masks
+    st, M, U = w.synthetic.make_model_arrays(lat, grid, nb, nw)
+    nk = len(U)
+    frozen = w.synthetic.make_frozen(nk, nb, nfroz)
+    ctx = make_ctx(w, st, M, nw)
+    ctx.set_frozen(frozen)
+    X, Y = so.U_to_X_Y(U, frozen)
+    XY = np.ascontiguousarray(so.X_Y_to_XY(X, Y))
+    Gxy = np.empty_like(XY)
+    f = ctx.fg_xy(XY, G=Gxy)
+    f_ref, G_ref = so.fg_disentangle(M, st["kpb_k"], st["bvec"], st["wb"], XY, nb, nw, frozen)
+    assert abs(f - f_ref) < RTOL * abs(f_ref)
+    assert rel(Gxy, G_ref) < RTOL
+    # a few steps of the device driver: the spread goes down, U stays semi-unitary, frozen states stay in
+    XYd = XY.copy()
+    f1, iters, nfg = ctx.disentangle(XYd, 1e-7, 1e-5, 5, 3)
+    assert f1 < f_ref and iters >= 1
+    Xd, Yd = so.XY_to_X_Y(XYd, nb, nw)
+    Ud = so.X_Y_to_U(Xd, Yd)
+    assert abs(so.omega(M, st["kpb_k"], st["bvec"], st["wb"], Ud)["Omega"] - f1) < 1e-9 * abs(f1)
+    assert np.abs(np.conj(Ud.transpose(0, 2, 1)) @ Ud - np.eye(nw)).max() < 1e-11
+    assert np.abs((np.abs(Ud) ** 2).sum(axis=2)[frozen] - 1).max() < 1e-10
+    ctx.close()
+
+
 def test_stiefel_project_and_retract(w, valence, silicon):
     ctx = make_ctx(w, fixture_stencil(valence), valence["M"], 4)
     rng = np.random.default_rng(7)
