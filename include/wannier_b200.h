@@ -190,8 +190,9 @@ int wb200_set_peer_gauges(wb200_ctx* ctx, int world, const void* const* U_ptrs, 
  * With one process per GPU the library does not own a communicator.  The host registers a callback
  * that all-reduces `count` doubles at device pointer `dptr` IN PLACE over all ranks, enqueued on
  * `cuda_stream` (op 0 = sum, 1 = max) — ncclAllReduce from Julia/C, torch.distributed from Python.
- * With the callback and wb200_set_peer_gauges in place, wb200_max_localize runs on a k-slab ctx:
- * U_inout is then the SLAB [nk][nw][nb]; every rank calls it collectively with the same arguments.
+ * With the callback and wb200_set_peer_gauges in place, wb200_max_localize and wb200_disentangle run
+ * on a k-slab ctx: U_inout / XY is then the SLAB ([nk][nw][nb] / [nk][nw*nw + nb*nw]; frozen bands
+ * per slab); every rank calls them collectively with the same arguments.
  * Vectors of the L-BFGS live slab-local; scalar products, |g|_inf, the spread sums and a one-element
  * "gauges are in place" reduction before each evaluation go through the callback.               */
 typedef void (*wb200_allreduce_fn)(void* dptr, int count, int op, void* cuda_stream, void* user);

@@ -28,22 +28,31 @@ def _worker(rank, world, port, case, out):
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     try:
-        lat, grid, nb = case
-        st, M, U = w.synthetic.make_model_arrays(lat, grid, nb, nb, eps=0.02)
+        lat, grid, nb = case[:3]
+        nw = case[3] if len(case) > 3 else nb
+        st, M, U = w.synthetic.make_model_arrays(lat, grid, nb, nw, eps=0.02)
         nk, nn = st["kpb_k"].shape
         bounds = w.sharding.slab_bounds(nk, world)
         k0, k1 = bounds[rank], bounds[rank + 1]
-        ctx = w.Context(nb, nb, nk, nn, st["kpb_k"][k0:k1], st["bvec"][k0:k1], st["wb"],
+        ctx = w.Context(nb, nw, nk, nn, st["kpb_k"][k0:k1], st["bvec"][k0:k1], st["wb"],
                         w.api.to_abi_M(M[k0:k1]), device=rank, k_begin=k0, nk=k1 - k0)
         ctx.set_stream(torch.cuda.current_stream().cuda_stream)
-        ptr, handle = w.lib.ipc_alloc(rank, 16 * nk * nb * nb)
+        ptr, handle = w.lib.ipc_alloc(rank, 16 * nk * nb * nw)
         handles = [None] * world
         dist.all_gather_object(handles, handle)
         ptrs = [ptr if r == rank else w.lib.ipc_open(rank, handles[r]) for r in range(world)]
         ctx.set_peer_gauges(ptrs, bounds)
         ctx.set_allreduce(w.sharding.torch_allreduce(dist, dev))
-        Uslab = w.api.to_abi_U(U[k0:k1])
-        f, it, nfg = ctx.max_localize(Uslab, f_tol=1e-10, g_tol=1e-7, max_iter=40)
+        if len(case) > 3:      # disentangle: (X, Y) slab, frozen bands of the slab
+            from oracle import spread_oracle as so
+            frozen = w.synthetic.make_frozen(nk, nb, case[4])
+            ctx.set_frozen(frozen[k0:k1])
+            X, Y = so.U_to_X_Y(U, frozen)
+            Uslab = np.ascontiguousarray(so.X_Y_to_XY(X, Y)[k0:k1])
+            f, it, nfg = ctx.disentangle(Uslab, 1e-10, 1e-7, 25, 3)
+        else:
+            Uslab = w.api.to_abi_U(U[k0:k1])
+            f, it, nfg = ctx.max_localize(Uslab, f_tol=1e-10, g_tol=1e-7, max_iter=40)
         torch.cuda.synchronize()
         dist.barrier()
         out[rank] = (f, it, nfg, Uslab.copy())
@@ -82,4 +91,34 @@ def test_sharded_max_localize_matches_single_gpu(w, case):
     Ush = np.concatenate([Ua, Ub], axis=0)
     assert np.abs(Ush - U1).max() < 1e-8
     f_check = so.omega(M, st["kpb_k"], st["bvec"], st["wb"], w.api.from_abi_U(Ush))["Omega"]
+    assert abs(f_check - fa) < 1e-9 * abs(fa)
+
+
+def test_sharded_disentangle_matches_single_gpu(w):
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from oracle import spread_oracle as so
+    case = ("fcc", (4, 2, 2), 18, 9, 5)
+    lat, grid, nb, nw, nfroz = case
+    st, M, U = w.synthetic.make_model_arrays(lat, grid, nb, nw, eps=0.02)
+    nk, nn = st["kpb_k"].shape
+    frozen = w.synthetic.make_frozen(nk, nb, nfroz)
+    ctx = w.Context(nb, nw, nk, nn, st["kpb_k"], st["bvec"], st["wb"], w.api.to_abi_M(M))
+    ctx.set_frozen(frozen)
+    X, Y = so.U_to_X_Y(U, frozen)
+    XY1 = np.ascontiguousarray(so.X_Y_to_XY(X, Y))
+    f1, it1, nfg1 = ctx.disentangle(XY1, 1e-10, 1e-7, 25, 3)
+    ctx.close()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(2, _free_port(), case, out), nprocs=2, join=True)
+    (fa, ita, nfga, Xa), (fb, itb, nfgb, Xb) = out[0], out[1]
+    assert fa == fb and ita == itb and nfga == nfgb
+    assert ita == it1 and abs(fa - f1) < 1e-9 * abs(f1)
+    XYsh = np.concatenate([Xa, Xb], axis=0)
+    assert np.abs(XYsh - XY1).max() < 1e-8
+    Xs, Ys = so.XY_to_X_Y(XYsh, nb, nw)
+    f_check = so.omega(M, st["kpb_k"], st["bvec"], st["wb"], so.X_Y_to_U(Xs, Ys))["Omega"]
     assert abs(f_check - fa) < 1e-9 * abs(fa)

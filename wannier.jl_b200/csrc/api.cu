@@ -564,7 +564,9 @@ extern "C" int wb200_disentangle(wb200_ctx* ctx, double* XY, double f_tol, doubl
                                  int history, double* f_final, int* iters, int* n_fg) {
     if (!ctx || !XY) return WB200_ERR_ARG;
     cudaSetDevice(ctx->device);
-    WB_TRY(require_single_slab(ctx, "wb200_disentangle"));
+    // k-sharded like wb200_max_localize: with the all-reduce callback and peer gauges in place XY is
+    // the slab [nk][nw*nw + nb*nw]; the (X, Y) chain and the Stiefel operations are per k-point
+    if (!(ctx->allreduce && ctx->peer_self)) WB_TRY(require_single_slab(ctx, "wb200_disentangle"));
     const size_t e = (size_t)ctx->nk * ((size_t)ctx->nw * ctx->nw + (size_t)ctx->nb * ctx->nw);
     cplx* dx = nullptr;
     WB_CUDA(ctx, cudaMalloc(&dx, sizeof(cplx) * e));
