@@ -114,7 +114,8 @@ int wb200_retract(wb200_ctx* ctx, double* X, int nrow, int ncol, int count);
 /* max_localize(model; f_tol, g_tol, max_iter, history_size) (max_localize.jl:44-101) with the
  * optimiser loop device-resident (L-BFGS on the power Stiefel manifold, strong-Wolfe line search,
  * Optim's stopping rules |df| <= f_tol |f| or |g|_inf <= g_tol).  U_inout [nk][nw][nb], nb == nw.
- * Single-slab ctx only.  iters / n_fg may be NULL.                                               */
+ * Single-slab ctx, or a k-slab ctx with wb200_set_allreduce + wb200_set_peer_gauges (see below).
+ * iters / n_fg may be NULL.                                                                      */
 int wb200_max_localize(wb200_ctx* ctx, double* U_inout, double f_tol, double g_tol, int max_iter,
                        int history, double* f_final, int* iters, int* n_fg);
 /* disentangle(model; ...) (disentangle.jl:631-728) on the product manifold (X, Y); frozen set by

@@ -88,4 +88,38 @@ function Wannier.max_localize(p, model::Model, c::B200Cache; f_tol=1e-7, g_tol=1
         c.ptr, U, f_tol, g_tol, max_iter, history_size, f, it, nfg))
     return [U[:, :, ik] for ik in 1:size(U, 3)]          # Vector{Matrix}, as max_localize.jl:94-98
 end
+
+"frozen bands of the disentanglement (model.frozen_bands :: Vector{BitVector}) as the [nb, nk] byte mask the library wants"
+function set_frozen!(c::B200Cache, frozen_bands::AbstractVector)
+    mask = Matrix{UInt8}(undef, c.nb, c.nk)
+    for ik in 1:c.nk
+        mask[:, ik] .= frozen_bands[ik]
+    end
+    check(c.ptr, ccall((:wb200_set_frozen, LIB), Cint, (Ptr{Cvoid}, Ptr{UInt8}), c.ptr, mask))
+end
+
+"fg!(Ω, G, XY) of get_fg!_disentangle (src/localization/disentangle.jl:586-614); XY, G :: Matrix{ComplexF64} (nw^2 + nb*nw, nk)."
+function get_fg!_disentangle(c::B200Cache)
+    return function fg!(F, G, XY::Matrix{ComplexF64})
+        f = Ref{Float64}(0.0)
+        check(c.ptr, ccall((:wb200_fg_xy, LIB), Cint,
+            (Ptr{Cvoid}, Ptr{ComplexF64}, Ptr{Float64}, Ptr{ComplexF64}),
+            c.ptr, XY, F === nothing ? C_NULL : f, G === nothing ? C_NULL : G))
+        return F === nothing ? nothing : f[]
+    end
+end
+
+"disentangle(model; ...) (src/localization/disentangle.jl:631-728) with the optimiser loop on the device"
+function Wannier.disentangle(p, model::Model, c::B200Cache; f_tol=1e-7, g_tol=1e-5, max_iter=200, history_size=3)
+    set_penalty!(c, p)
+    set_frozen!(c, model.frozen_bands)
+    X0, Y0 = Wannier.U_to_X_Y(model.gauges, model.frozen_bands)   # disentangle.jl:666 (host, one-off)
+    XY = Wannier.X_Y_to_XY(X0, Y0)                                 # :670, (nw^2 + nb*nw, nk)
+    f = Ref{Float64}(0.0); it = Ref{Cint}(0); nfg = Ref{Cint}(0)
+    check(c.ptr, ccall((:wb200_disentangle, LIB), Cint,
+        (Ptr{Cvoid}, Ptr{ComplexF64}, Float64, Float64, Cint, Cint, Ptr{Float64}, Ptr{Cint}, Ptr{Cint}),
+        c.ptr, XY, f_tol, g_tol, max_iter, history_size, f, it, nfg))
+    Xmin, Ymin = Wannier.XY_to_X_Y(XY, c.nb, c.nw)                 # disentangle.jl:721-722
+    return Wannier.X_Y_to_U(Xmin, Ymin)
+end
 end # module
