@@ -125,10 +125,30 @@ def cpu_reference(cfg_name, steps, warmup, sample_k=None, seconds_budget=25.0):
             break
     t = float(np.mean(ts))
     value = (sample_k / nk) / t
+    one = one_thread_figure(cb, M, st["kpb_k"][ks], st["bvec"][ks], st["wb"], U, ks, nk)
     return dict(value=value, unit="evals/s", cores=cores, kind="port",
                 sample=f"{sample_k} of {nk} k-points ({sample_k * nn} pairs, both ZGEMMs per pair as "
                        f"spread.jl:173-174, omega!/omega_grad! loops), {len(ts)} x {t:.3f} s, "
-                       f"numpy+OpenBLAS, {cores} threads over k; extrapolated to the full k-grid"), t, len(ts)
+                       f"numpy+OpenBLAS, {cores} threads over k; extrapolated to the full k-grid",
+                one_thread=one), t, len(ts)
+
+
+def one_thread_figure(cbm, M, kpb, bvec, wb, U, ks, nk, seconds=6.0):
+    """The reference's own benchmark setting (one thread, benchmark/runbenchmarks.jl:3-7) on a slice of
+    the multithreaded sample, extrapolated the same way."""
+    n1 = max(2, len(ks) // 16)
+    sel = np.arange(n1)
+    run = lambda: cbm.fg_sample(M[sel], kpb[sel], bvec[sel], wb, U, ks[sel], nk, threads=1, single_blas=True)
+    run()
+    ts = []
+    t_all = time.perf_counter()
+    while len(ts) < 2 or (time.perf_counter() - t_all < seconds and len(ts) < 10):
+        t0 = time.perf_counter()
+        run()
+        ts.append(time.perf_counter() - t0)
+    t = float(np.mean(ts))
+    return {"value": (n1 / nk) / t, "unit": "evals/s", "cores": 1,
+            "sample": f"{n1} of {nk} k-points, {len(ts)} x {t:.3f} s, one thread (one OpenBLAS thread)"}
 
 
 def main():
@@ -417,7 +437,9 @@ def main():
             "value": (len(ks) / nk) / t, "unit": "evals/s", "cores": cores, "kind": "port",
             "sample": f"{len(ks)} of {nk} k-points ({len(ks) * nn} pairs; both ZGEMMs per pair as "
                       f"spread.jl:173-174 plus the omega!/omega_grad! loops), {len(ts)} x {t:.3f} s, "
-                      f"numpy+OpenBLAS with {cores} threads over k; extrapolated to the full k-grid"}
+                      f"numpy+OpenBLAS with {cores} threads over k; extrapolated to the full k-grid",
+            "one_thread": one_thread_figure(cbm, Ms, st["kpb_k"][k0:k1][ks], st["bvec"][k0:k1][ks], st["wb"], Uh,
+                                            ks + k0, nk)}
     print(json.dumps(line), file=json_out, flush=True)
     ctx.close()
     if world > 1:

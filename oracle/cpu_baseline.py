@@ -45,9 +45,11 @@ def sample_inputs(w, st, nb, nw, ks):
     return M, (U, umap)
 
 
-def fg_sample(M, kpb, bvec, wb, U, ks, nk_total, threads=1):
+def fg_sample(M, kpb, bvec, wb, U, ks, nk_total, threads=1, single_blas=False):
     """One spread+gradient evaluation restricted to the sampled k-points.  U is either the full
-    [nk_total, nb, nw] array or (compact, umap).  Returns (Omega_sample, G_sample)."""
+    [nk_total, nb, nw] array or (compact, umap).  Returns (Omega_sample, G_sample).
+    threads = 1 with single_blas = True is the reference's own benchmark setting (one Julia thread,
+    one OpenBLAS thread: benchmark/runbenchmarks.jl:3-7)."""
     if isinstance(U, tuple):
         U, umap = U
         ik, ikpb = umap[ks], umap[kpb]
@@ -68,7 +70,7 @@ def fg_sample(M, kpb, bvec, wb, U, ks, nk_total, threads=1):
         sel = chunks[ci]
         return so.grad_from_MU_N_r(MU[ci], N[ci], bvec[sel], wb, r, ns)
 
-    ctxmgr = threadpool_limits(limits=1) if (threadpool_limits and threads > 1) else None
+    ctxmgr = threadpool_limits(limits=1) if (threadpool_limits and (threads > 1 or single_blas)) else None
     try:
         if ctxmgr is not None:
             ctxmgr.__enter__()
