@@ -2,7 +2,10 @@
 CPU only."""
 import numpy as np
 
+from oracle import optim_lbfgs as ol
 from oracle import spread_oracle as so
+from optim_goldens import (CC_DISENTANGLE_IT4, CC_MAXLOC_IT4, DISENTANGLE_IT4, MAXLOC_DEFAULT,
+                           check_spread)
 
 
 def _fd_directional(f, x, d, h=1e-5):
@@ -143,3 +146,58 @@ def test_opt_rotate_matches_reference_Wmin(valence):
         h = 1e-5
         fd = (so.fg_rotate(N, *args[1:], W0 + h * d)[0] - so.fg_rotate(N, *args[1:], W0 - h * d)[0]) / (2 * h)
         assert abs(fd - np.real(np.vdot(G, d))) < 1e-6 * max(1.0, abs(fd))
+
+
+# ---- the third-party optimiser (Optim.LBFGS + HagerZhang) restated in oracle/optim_lbfgs.py, pinned
+# ---- by the reference's trajectory-dependent goldens (max_iter = 4) and its default-tolerance run
+def _xy_manifold(nb, nw):
+    def retract(xy):
+        X, Y = so.XY_to_X_Y(xy, nb, nw)
+        return so.X_Y_to_XY(so.stiefel_retract(X), so.stiefel_retract(Y))
+
+    def project(gxy, xy):
+        X, Y = so.XY_to_X_Y(xy, nb, nw)
+        GX, GY = so.XY_to_X_Y(gxy, nb, nw)
+        return so.X_Y_to_XY(so.stiefel_project_tangent(GX, X), so.stiefel_project_tangent(GY, Y))
+    return retract, project
+
+
+def _optim_disentangle(d, r0=None, lam=0.0, **kw):
+    nb, nw = d["M"].shape[2], d["U"].shape[2]
+    args = (d["M"], d["kpb_k"], d["bvec"], d["wb"])
+    X, Y = so.U_to_X_Y(d["U"], d["frozen"])
+    retract, project = _xy_manifold(nb, nw)
+    fg = lambda xy: so.fg_disentangle(*args, xy, nb, nw, d["frozen"], r0, lam)
+    xy, f, it, info = ol.optim_lbfgs(fg, so.X_Y_to_XY(X, Y), retract, project, **kw)
+    X, Y = so.XY_to_X_Y(xy, nb, nw)
+    return so.omega(*args, so.X_Y_to_U(X, Y)), f, it, info
+
+
+def test_optim_restatement_default_tolerances_maxloc(valence):
+    # test/localization/max_localize.jl:45-56 verbatim: default f_tol = 1e-7, g_tol = 1e-5, atol 1e-7
+    args = (valence["M"], valence["kpb_k"], valence["bvec"], valence["wb"])
+    fg = lambda U: so.fg_maxloc(*args, U)
+    U, f, it, info = ol.optim_lbfgs(fg, valence["U_ptg"], so.stiefel_retract, so.stiefel_project_tangent)
+    assert info["converged"] and info["stop"] == "f_tol"
+    check_spread(so.omega(*args, U), MAXLOC_DEFAULT)
+
+
+def test_optim_restatement_trajectory_goldens(valence, silicon):
+    # max_iter = 4 results depend on every detail of the line search and of the history update
+    sp, f, it, info = _optim_disentangle(silicon, max_iter=4)
+    assert it == 4
+    check_spread(sp, DISENTANGLE_IT4)
+    ref = CC_DISENTANGLE_IT4
+    sp, f, it, info = _optim_disentangle(silicon, ref["r0"], ref["lam"], max_iter=4)
+    check_spread(sp, ref)
+    assert abs(f - ref["Omegat"]) < 1e-7
+    ref = CC_MAXLOC_IT4
+    args = (valence["M"], valence["kpb_k"], valence["bvec"], valence["wb"])
+    fg = lambda U: so.fg_maxloc(*args, U, ref["r0"], ref["lam"])
+    U, f, it, info = ol.optim_lbfgs(fg, valence["U_ptg"], so.stiefel_retract, so.stiefel_project_tangent,
+                                    max_iter=4)
+    sp = so.omega(*args, U)
+    check_spread(sp, ref)
+    spc = so.omega_center(sp, ref["r0"], ref["lam"])
+    assert abs(f - ref["Omegat"]) < 1e-7 and abs(spc["Omegac"] - ref["Omegac"]) < 1e-7
+    assert np.abs(spc["omegac"] - ref["omegac"]).max() < 1e-7
