@@ -195,8 +195,12 @@ int wb200_set_peer_gauges(wb200_ctx* ctx, int world, const void* const* U_ptrs, 
  * on a k-slab ctx: U_inout / XY is then the SLAB ([nk][nw][nb] / [nk][nw*nw + nb*nw]; frozen bands
  * per slab); every rank calls them collectively with the same arguments.
  * Vectors of the L-BFGS live slab-local; scalar products, |g|_inf, the spread sums and a one-element
- * "gauges are in place" reduction before each evaluation go through the callback.               */
-typedef void (*wb200_allreduce_fn)(void* dptr, int count, int op, void* cuda_stream, void* user);
+ * "gauges are in place" reduction before each evaluation go through the callback.
+ * The callback returns 0 on success; any other value aborts the call with WB200_ERR_CUDA (the ranks
+ * are then out of step and the contexts must be destroyed).  Every branch of the optimiser depends
+ * only on reduced scalars, so all ranks stay in step; a rank-local failure of a retraction turns
+ * that evaluation's reduced sums into NaN, i.e. the trial point is rejected on every rank.       */
+typedef int (*wb200_allreduce_fn)(void* dptr, int count, int op, void* cuda_stream, void* user);
 int wb200_set_allreduce(wb200_ctx* ctx, wb200_allreduce_fn fn, void* user);
 
 /* ---- measurement helpers (bench.py) -------------------------------------------------------------

@@ -406,111 +406,55 @@ def opt_rotate(M, kpb_k, bvec, wb, U0, **kw):
     nw = U0.shape[2]
     fg = lambda W: fg_rotate(N, kpb_k, bvec, wb, W[0])
     fg1 = lambda W: (lambda f, G: (f, G[None]))(*fg(W))
-    W, f, it, hist = lbfgs_stiefel(fg1, np.eye(nw, dtype=complex)[None], stiefel_retract,
+    W, f, it, info = lbfgs_stiefel(fg1, np.eye(nw, dtype=complex)[None], stiefel_retract,
                                    stiefel_project_tangent, **kw)
     return W[0], f, it
 
 
 # --------------------------------------------------------------------------
-# Riemannian L-BFGS driver (stands in for Optim.jl at max_localize.jl:73-84)
+# Optimiser-driven calls: Optim.LBFGS + HagerZhang as restated in oracle/optim_lbfgs.py
 # --------------------------------------------------------------------------
-def _rdot(a, b):
-    return float(np.real(np.vdot(a, b)))
-
-
 def lbfgs_stiefel(fg, x0, retract, project, f_tol=1e-7, g_tol=1e-5, max_iter=200, m=3,
                   verbose=False):
-    """Manifold L-BFGS with a strong-Wolfe bracketing line search.
-
-    Optim.jl's exact LBFGS/HagerZhang trajectory is third-party code that is not in
-    /root/reference (Project.toml compat Optim = "1.7"); only the converged optimum is
-    pinnable (test/localization/max_localize.jl:52-55).  Same stopping rules as
-    Optim.Options at max_localize.jl:77-83: |f - f_prev| <= f_tol*|f| or max|g| <= g_tol.
-    The CUDA driver (csrc/optimizer.cu) implements this same algorithm."""
-    x = retract(x0)
-    f, g = fg(x)
-    g = project(g, x)
-    S, Yh, rho = [], [], []
-    it = 0
-    hist = [f]
-    while it < max_iter:
-        if np.max(np.abs(g)) <= g_tol:
-            break
-        # two-loop recursion
-        q = g.copy()
-        al = []
-        for s, y, r_ in zip(reversed(S), reversed(Yh), reversed(rho)):
-            a = r_ * _rdot(s, q)
-            al.append(a)
-            q -= a * y
-        if S:
-            q *= _rdot(S[-1], Yh[-1]) / _rdot(Yh[-1], Yh[-1])
-        for (s, y, r_), a in zip(zip(S, Yh, rho), reversed(al)):
-            b = r_ * _rdot(y, q)
-            q += (a - b) * s
-        d = project(-q, x)
-        dphi0 = _rdot(g, d)
-        if dphi0 >= 0:
-            d = -g
-            dphi0 = _rdot(g, d)
-            S, Yh, rho = [], [], []
-        alpha = 1.0 if S else min(1.0, 1.0 / max(np.sqrt(_rdot(g, g)), 1e-300))
-
-        def phi(a_):
-            xn = retract(x + a_ * d)
-            fn, gn = fg(xn)
-            gn = project(gn, xn)
-            # gn is tangent at xn and the tangent projection is self-adjoint, so <gn, P(d)> = <gn, d>
-            return fn, gn, xn, _rdot(gn, d)
-
-        c1, c2 = 1e-4, 0.9
-        lo, hi = 0.0, None
-        f_lo, d_lo = f, dphi0
-        best = None
-        for _ in range(30):
-            fn, gn, xn, dn = phi(alpha)
-            if fn > f + c1 * alpha * dphi0 or (best is not None and fn >= f_lo and lo > 0):
-                hi = alpha
-            elif abs(dn) <= -c2 * dphi0:
-                best = (fn, gn, xn, alpha)
-                break
-            elif dn >= 0:
-                hi = alpha
-            else:
-                lo, f_lo, d_lo = alpha, fn, dn
-                best = (fn, gn, xn, alpha)
-            if hi is None:
-                alpha *= 2.0
-            else:
-                alpha = 0.5 * (lo + hi)
-        if best is None:
-            break
-        fn, gn, xn, a_best = best
-        # secant pair as Optim.jl's LBFGS forms it on a manifold (update_state! / update_h!):
-        # dx = alpha * s (the step before retraction), dg = g_new - g_previous with each gradient
-        # projected at its own point; the history is not transported.
-        s = a_best * d
-        y = gn - g
-        sy = _rdot(s, y)
-        if sy > 1e-14 * np.sqrt(_rdot(s, s) * _rdot(y, y)):
-            S.append(s); Yh.append(y); rho.append(1.0 / sy)
-            if len(S) > m:
-                S.pop(0); Yh.pop(0); rho.pop(0)
-        df = abs(fn - f)
-        x, f_prev, f, g = xn, f, fn, gn
-        hist.append(f)
-        it += 1
-        if verbose:
-            print(f"iter {it:4d} f={f:.12f} |g|inf={np.max(np.abs(g)):.3e}")
-        if df <= f_tol * abs(f):
-            break
-    return x, f, it, hist
+    """Optim.optimize(only_fg!(fg!), x0, LBFGS(manifold, HagerZhang, m), Options(f_tol, g_tol,
+    iterations)) — see oracle/optim_lbfgs.py (pinned by the reference's max_iter = 4 goldens).
+    Returns (x, f, iterations, info)."""
+    from . import optim_lbfgs as ol
+    return ol.optim_lbfgs(fg, x0, retract, project, f_tol=f_tol, g_tol=g_tol, max_iter=max_iter, m=m,
+                          verbose=verbose)
 
 
 def max_localize(M, kpb_k, bvec, wb, U0, r0=None, lam=0.0, f_tol=1e-7, g_tol=1e-5,
                  max_iter=200, m=3, verbose=False):
-    """max_localize(model).  src/localization/max_localize.jl:44-101."""
+    """max_localize([p,] model).  src/localization/max_localize.jl:44-101."""
     assert U0.shape[1] == U0.shape[2], "n_bands != n_wann, run instead disentanglement?"
     fg = lambda U: fg_maxloc(M, kpb_k, bvec, wb, U, r0, lam)
     return lbfgs_stiefel(fg, U0, stiefel_retract, stiefel_project_tangent,
                          f_tol, g_tol, max_iter, m, verbose)
+
+
+def xy_retract(XY, nb, nw):
+    """retract! of ProductManifold(Stiefel_SVD, Stiefel_SVD) per k (disentangle.jl:687-690)."""
+    X, Y = XY_to_X_Y(XY, nb, nw)
+    return X_Y_to_XY(stiefel_retract(X), stiefel_retract(Y))
+
+
+def xy_project_tangent(GXY, XY, nb, nw):
+    X, Y = XY_to_X_Y(XY, nb, nw)
+    GX, GY = XY_to_X_Y(GXY, nb, nw)
+    return X_Y_to_XY(stiefel_project_tangent(GX, X), stiefel_project_tangent(GY, Y))
+
+
+def disentangle(M, kpb_k, bvec, wb, U0, frozen, r0=None, lam=0.0, f_tol=1e-7, g_tol=1e-5,
+                max_iter=200, m=3, verbose=False, XY0=None):
+    """disentangle([p,] model).  src/localization/disentangle.jl:631-728.  Returns (U, XY, f, it, info)."""
+    nb, nw = U0.shape[1], U0.shape[2]
+    if XY0 is None:
+        X0, Y0 = U_to_X_Y(U0, frozen)
+        XY0 = X_Y_to_XY(X0, Y0)
+    fg = lambda xy: fg_disentangle(M, kpb_k, bvec, wb, xy, nb, nw, frozen, r0, lam)
+    xy, f, it, info = lbfgs_stiefel(fg, XY0, lambda a: xy_retract(a, nb, nw),
+                                    lambda g, a: xy_project_tangent(g, a, nb, nw), f_tol, g_tol, max_iter, m,
+                                    verbose)
+    X, Y = XY_to_X_Y(xy, nb, nw)
+    return X_Y_to_U(X, Y), xy, f, it, info

@@ -7,6 +7,7 @@ import pytest
 
 from oracle import spread_oracle as so
 from conftest import make_ctx, fixture_stencil
+import optim_goldens as og
 
 pytestmark = pytest.mark.gpu
 
@@ -193,14 +194,31 @@ def test_stiefel_project_and_retract(w, valence, silicon):
     ctx.close()
 
 
+def _model(w, d, U=None, frozen=False):
+    st = w.KspaceStencil(d["recip"], d["kpoints"], d["wb"], d["kpb_k"], d["kpb_G"])
+    return w.Model(d["lattice"], st, d["M"], d["U"] if U is None else U, d["frozen"] if frozen else None)
+
+
+def _as_dict(sp):
+    return dict(Omega=sp.Omega, OmegaI=sp.OmegaI, OmegaOD=sp.OmegaOD, OmegaD=sp.OmegaD,
+                OmegaTilde=sp.OmegaTilde, omega=sp.omega, r=sp.r)
+
+
 def test_max_localize_reaches_reference_optimum(w, valence):
-    # test/localization/max_localize.jl:45-56: Omega = 6.374823673444644 etc. (atol 1e-7 there;
-    # north_star: within 1e-8 A^2)
+    # test/localization/max_localize.jl:45-56 verbatim: max_localize(p, model) with the DEFAULT
+    # tolerances (f_tol 1e-7, g_tol 1e-5), then the reference's own assertions at atol 1e-7;
+    # north_star: with tight tolerances within 1e-8 A^2
     ref = valence["ref_maxloc"]
-    st = w.KspaceStencil(valence["recip"], valence["kpoints"], valence["wb"], valence["kpb_k"], valence["kpb_G"])
-    model = w.Model(valence["lattice"], st, valence["M"], valence["U_ptg"])
+    model = _model(w, valence, valence["U_ptg"])
     U, info = w.max_localize(model, return_info=True)             # reference default tolerances
-    assert abs(so.omega(*oracle_args(valence), U)["Omega"] - ref[0]) < 2e-6
+    sp = w.omega(model, U)
+    og.check_spread(_as_dict(sp), og.MAXLOC_DEFAULT, atol=1e-7)
+    # the device driver is Optim's LBFGS + HagerZhang step for step: same iterations, evaluations and
+    # spread as the oracle's restatement (which the reference's max_iter = 4 goldens pin)
+    Uo, fo, ito, infoo = so.max_localize(*oracle_args(valence), valence["U_ptg"])
+    assert info["iterations"] == ito and info["n_fg"] == infoo["n_fg"]
+    assert abs(info["f"] - fo) < 1e-9
+    assert np.abs(U - Uo).max() < 1e-6
     U, info = w.max_localize(model, f_tol=1e-13, g_tol=1e-8, max_iter=500, return_info=True)
     sp = so.omega(*oracle_args(valence), U)
     assert abs(sp["Omega"] - ref[0]) < 1e-8
@@ -208,28 +226,55 @@ def test_max_localize_reaches_reference_optimum(w, valence):
     assert abs(sp["OmegaOD"] - ref[2]) < 1e-8
     assert abs(info["f"] - sp["Omega"]) < 1e-10
     assert np.abs(np.conj(U.transpose(0, 2, 1)) @ U - np.eye(4)).max() < 1e-12
-    # same algorithm as the oracle's driver: same iteration count and optimum
-    Uo, fo, ito, _ = so.max_localize(*oracle_args(valence), valence["U_ptg"], f_tol=1e-13, g_tol=1e-8, max_iter=500)
-    assert abs(fo - info["f"]) < 1e-9
     # other history sizes (the Gram pass is chunked above 3 pairs): same optimum
     for hist in (1, 5, 9):
         U, info = w.max_localize(model, f_tol=1e-13, g_tol=1e-8, max_iter=500, history_size=hist, return_info=True)
         assert abs(info["f"] - ref[0]) < 1e-8, hist
     with pytest.raises(ValueError):   # max_localize.jl:52-53
+        st = model.kstencil
         w.max_localize(w.Model(valence["lattice"], st, np.zeros((64, 8, 5, 5), complex), np.zeros((64, 5, 4), complex)))
 
 
+def test_optimiser_trajectory_goldens(w, valence, silicon):
+    """The reference's trajectory-dependent known answers (Optim LBFGS + HagerZhang, max_iter = 4),
+    through the public API and the device-resident driver, at the reference's own atol 1e-7."""
+    # test/localization/disentangle.jl:56-97
+    model = _model(w, silicon, frozen=True)
+    U, info = w.disentangle(model, max_iter=4, return_info=True)
+    assert info["iterations"] == 4
+    og.check_spread(_as_dict(w.omega(model, U)), og.DISENTANGLE_IT4)
+    # test/localization/constrain_center/disentangle.jl:43-120
+    ref = og.CC_DISENTANGLE_IT4
+    p = w.CenterSpreadPenalty(ref["r0"], ref["lam"])
+    U, info = w.disentangle(p, model, max_iter=4, return_info=True)
+    spc = w.omega(p, model, U)
+    og.check_spread(_as_dict(spc), ref)
+    assert abs(spc.Omegac - ref["Omegac"]) < 1e-7 and abs(spc.Omegat - ref["Omegat"]) < 1e-7
+    assert abs(info["f"] - ref["Omegat"]) < 1e-7
+    # test/localization/constrain_center/max_localize.jl:46-96
+    ref = og.CC_MAXLOC_IT4
+    model = _model(w, valence, valence["U_ptg"])
+    p = w.CenterSpreadPenalty(ref["r0"], ref["lam"])
+    U, info = w.max_localize(p, model, max_iter=4, return_info=True)
+    spc = w.omega(p, model, U)
+    og.check_spread(_as_dict(spc), ref)
+    assert abs(spc.Omegac - ref["Omegac"]) < 1e-7 and abs(spc.Omegat - ref["Omegat"]) < 1e-7
+    assert np.abs(spc.omegac - ref["omegac"]).max() < 1e-7
+
+
 def test_disentangle_driver(w, silicon):
-    # test/localization/disentangle.jl:56-97 pins Optim's 4-step trajectory (unpinnable without
-    # Optim.jl); here: the device driver decreases Omega, keeps frozen states, agrees with the oracle's fg
-    st = w.KspaceStencil(silicon["recip"], silicon["kpoints"], silicon["wb"], silicon["kpb_k"], silicon["kpb_G"])
-    model = w.Model(silicon["lattice"], st, silicon["M"], silicon["U"], silicon["frozen"])
+    # the device driver against the oracle's driver on the 12 -> 8 silicon model (same iterations, same
+    # evaluations, same spread), semi-unitarity and frozen states kept
+    model = _model(w, silicon, frozen=True)
     X0, Y0 = so.U_to_X_Y(silicon["U"], silicon["frozen"])
     f0 = so.omega(*oracle_args(silicon), so.X_Y_to_U(X0, Y0))["Omega"]
     U, info = w.disentangle(model, max_iter=30, return_info=True)
     sp = so.omega(*oracle_args(silicon), U)
     assert abs(sp["Omega"] - info["f"]) < 1e-9
     assert info["f"] < f0 - 1.0
+    Uo, xyo, fo, ito, infoo = so.disentangle(*oracle_args(silicon), silicon["U"], silicon["frozen"], max_iter=30)
+    assert info["iterations"] == ito and info["n_fg"] == infoo["n_fg"]
+    assert abs(info["f"] - fo) < 1e-8
     assert np.abs(np.conj(U.transpose(0, 2, 1)) @ U - np.eye(8)).max() < 1e-11
     # frozen states stay inside the span of U:  sum_n |U[m, n]|^2 == 1 for frozen m
     w2 = (np.abs(U) ** 2).sum(axis=2)

@@ -188,11 +188,15 @@ def _split_args(args):
 
 
 def _with_cache(args, cache):
+    """In the reference the penalty travels with every call; here it is state of the device context.
+    A caller-owned cache keeps whatever penalty it has (e.g. the one its fg closure set) unless this
+    call names one."""
     p, st, M, U = _split_args(args)
     own = cache is None
     if own:
         cache = Cache(st, M, U.shape[2])
-    cache.set_penalty(p)
+    if own or p is not None:
+        cache.set_penalty(p)
     return p, cache, U, own
 
 
@@ -330,6 +334,7 @@ def get_fg_rotate(model):
         G[...] = Gb.T
 
     f.cache = cache
+    f.close = g.close = cache.close      # the pair owns a device context (tiled M, MU, U): release it when done
     return f, g
 
 
@@ -357,6 +362,7 @@ def get_fg_maxloc(p, model, cache=None):
     Gbuf = np.empty((cache.nk, cache.nw, cache.nb), dtype=np.complex128)
 
     def fg(F, G, U):
+        cache.set_penalty(p)      # the closure's penalty, whatever else used the cache in between
         f = cache.ctx.fg(to_abi_U(U), want_f=F is not None, G=Gbuf if G is not None else None)
         if G is not None:
             G[...] = Gbuf.transpose(0, 2, 1)
@@ -462,6 +468,7 @@ def get_fg_disentangle(p, model, cache=None):
     cache.set_penalty(p)
 
     def fg(F, G, XY):
+        cache.set_penalty(p)
         XY = np.ascontiguousarray(XY, dtype=np.complex128)
         Gb = np.empty_like(XY) if G is not None else None
         f = cache.ctx.fg_xy(XY, want_f=F is not None, G=Gb)

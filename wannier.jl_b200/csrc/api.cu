@@ -223,6 +223,24 @@ extern "C" int wb200_fg_phase2_dev(wb200_ctx* ctx, const double* dsums, double* 
     return WB200_OK;
 }
 
+int wb_allreduce(wb200_ctx* ctx, double* dptr, int count, int op) {
+    const int rc = ctx->allreduce(dptr, count, op, (void*)ctx->stream, ctx->allreduce_user);
+    if (rc != 0) {
+        ctx->err = "all-reduce callback failed (status " + std::to_string(rc) + "); the ranks are no longer in step";
+        return WB200_ERR_CUDA;
+    }
+    return WB200_OK;
+}
+
+// a rank-local failure before this evaluation (wb_lbfgs: retraction of a trial point): NaN sums make
+// f = NaN on every rank once reduced, so all ranks reject the point together
+static int poison_sums(wb200_ctx* ctx) {
+    if (!ctx->poison_next) return WB200_OK;
+    ctx->poison_next = 0;
+    WB_CUDA(ctx, cudaMemsetAsync(ctx->d_sums, 0xFF, sizeof(double) * ctx->nsums(), ctx->stream));
+    return WB200_OK;
+}
+
 int wb_fg_device(wb200_ctx* ctx, const cplx* dU, double* dres, cplx* dG, int exact_split) {
     if (ctx->allreduce && ctx->peer_self) {
         // k-sharded evaluation: dU is this rank's SLAB.  Put it into the rank's rows of the shared
@@ -234,13 +252,15 @@ int wb_fg_device(wb200_ctx* ctx, const cplx* dU, double* dres, cplx* dG, int exa
             WB_CUDA(ctx, cudaMemcpyAsync(rows, dU, sizeof(cplx) * mat * ctx->nk, cudaMemcpyDeviceToDevice,
                                          ctx->stream));
         WB_CUDA(ctx, cudaMemsetAsync(ctx->d_scal + 2, 0, sizeof(double), ctx->stream));
-        ctx->allreduce(ctx->d_scal + 2, 1, 0, (void*)ctx->stream, ctx->allreduce_user);
+        WB_TRY(wb_allreduce(ctx, ctx->d_scal + 2, 1, 0));
         WB_TRY(wb200_fg_phase1_dev(ctx, (const double*)ctx->peer_self, ctx->d_sums, exact_split));
-        ctx->allreduce(ctx->d_sums, ctx->nsums(), 0, (void*)ctx->stream, ctx->allreduce_user);
+        WB_TRY(poison_sums(ctx));
+        WB_TRY(wb_allreduce(ctx, ctx->d_sums, ctx->nsums(), 0));
         WB_TRY(wb200_fg_phase2_dev(ctx, ctx->d_sums, dres, (double*)dG));
         return WB200_OK;
     }
     WB_TRY(wb200_fg_phase1_dev(ctx, (const double*)dU, ctx->d_sums, exact_split));
+    WB_TRY(poison_sums(ctx));
     WB_TRY(wb200_fg_phase2_dev(ctx, ctx->d_sums, dres, (double*)dG));
     return WB200_OK;
 }

@@ -95,6 +95,8 @@ struct wb200_ctx {
     cplx* peer_self = nullptr;        // this rank's full gauge array (U_ptrs[rank])
     wb200_allreduce_fn allreduce = nullptr;   // caller-supplied collective (sharded optimiser)
     void* allreduce_user = nullptr;
+    int poison_next = 0;   // the next evaluation's sums are replaced by NaN before they are reduced (a
+                           // rank-local failure, e.g. of a retraction, must be seen by every rank)
     double* d_bvec = nullptr;    // [nk][nn][3]
     double* d_wb = nullptr;      // [nn]
     cplx* d_M = nullptr;         // [nk][nn][nb*nb] col-major (generic path / exact N)
@@ -186,6 +188,9 @@ struct ProfScope {
     }
     ~ProfScope() { if (stop) cudaEventRecord(stop, c->stream); }
 };
+
+// ---- api.cu ----
+int wb_allreduce(wb200_ctx* ctx, double* dptr, int count, int op);   // checked call of the registered collective
 
 // ---- kernels_generic.cu ----
 int wb_zgemm_batched(wb200_ctx* ctx, const ZgemmArgs& a);

@@ -1,30 +1,204 @@
 // optimizer.cu — device-resident Riemannian L-BFGS for max_localize / disentangle / opt_rotate.
 //
-// Replaces the Optim.optimize(only_fg!(fg!), x0, LBFGS(manifold, HagerZhang, m)) calls at
-// src/localization/max_localize.jl:73-84, src/localization/disentangle.jl:702-713 and
-// src/localization/opt_rotate.jl:118-141.  Optim.jl is third-party code that is not in the
-// reference tree; its exact trajectory cannot be pinned.  This driver keeps Optim's
-// stopping rules (|f - f_prev| <= f_tol |f| or max|g| <= g_tol on the projected gradient,
-// max_iter) and is the same algorithm as oracle/spread_oracle.py::lbfgs_stiefel, which the parity
-// tests compare it with.
+// Replaces the Optim.optimize(only_fg!(fg!), x0, LBFGS(manifold, HagerZhang, m), Options(...)) calls
+// at src/localization/max_localize.jl:73-84, src/localization/disentangle.jl:702-713 and
+// src/localization/opt_rotate.jl:118-141.  Optim.jl / LineSearches.jl are third-party code that is
+// not in the reference tree; this driver follows their published algorithms step for step, exactly as
+// oracle/optim_lbfgs.py restates them (that restatement reproduces the reference's trajectory-
+// dependent max_iter = 4 goldens to 1e-14, tests/test_oracle_golden.py):
+//   * optimize loop: initial |g|_inf test, then update_state! -> update_g! -> assess_convergence ->
+//     update_h!; f_tol is relative (Options.f_reltol) and must hold on successive_f_tol + 1 = 2
+//     consecutive iterations, g_tol is absolute on the projected gradient, a zero step ends the run;
+//   * LBFGS on a manifold: two-loop recursion with the Nocedal-Wright (7.20) scaling, direction
+//     projected at x, pairs dx = alpha s (before retraction), dg = g_new - g_previous (each projected
+//     at its own point, not transported), rejected only when <dx, dg> = 0; a non-descent direction
+//     resets to steepest descent;
+//   * alphaguess InitialStatic (alpha = 1), line search LineSearches.HagerZhang with its defaults;
+//   * phi(a) = f(retract(x + a s)), phi'(a) = <project(grad f, retract(x + a s)), s>.
 //
 // x, g, the search direction and the 2m history vectors never leave HBM.  The two-loop recursion is
-// done in COEFFICIENT space: the Gram matrix of {g, s_i, y_i} is kept on the host (the rows of g
-// and of the newest secant pair are refreshed by ONE fused pass over memory per iteration,
-// wb_cross_launch), the recursion runs on those 7 x 7 numbers, and the search direction is ONE
-// linear-combination pass (wb_lincomb).  Per iteration that is 3 host round trips and ~27 vector
-// reads/writes instead of 13 round trips and ~64 (it was one kernel + one synchronisation per
-// inner product and per axpy).
+// done in COEFFICIENT space: the Gram matrix of {g, dx_i, dg_i} is kept on the host (the rows of g
+// and of the newest pair are refreshed by ONE fused pass over memory per iteration, wb_cross_launch),
+// the recursion runs on those 7 x 7 numbers, and the search direction is ONE linear-combination pass
+// (wb_lincomb).  In k-sharded runs every scalar the control flow depends on is all-reduced, so all
+// ranks take the same branches; a rank-local failure of the retraction poisons that evaluation's
+// sums with NaN (f = NaN on every rank), which the line search treats as a rejected trial point.
 #include "common.cuh"
 
 #include <algorithm>
 #include <cmath>
 #include <deque>
+#include <functional>
+#include <limits>
 
 int wb_fg_device(wb200_ctx* ctx, const cplx* dU, double* dres, cplx* dG, int exact_split);  // api.cu
 int wb_fg_rotate_device(wb200_ctx* ctx, const cplx* dW, double* dres, cplx* dGW);           // extras.cu
 
 namespace {
+
+// ---------------------------------------------------------------------------------------------
+// LineSearches.HagerZhang (Hager & Zhang, ACM TOMS 32 (2006), Algorithm 851) with the package
+// defaults; indices are 0-based.  phidphi(a, phi, dphi) returns a WB200 status.
+// ---------------------------------------------------------------------------------------------
+struct HagerZhang {
+    double delta = 0.1, sigma = 0.9, alphamax = INFINITY, rho = 5.0, epsilon = 1e-6, gamma = 0.66, psi3 = 0.1;
+    int linesearchmax = 50;
+    std::function<int(double, double&, double&)> phidphi;
+    std::vector<double> alphas, values, slopes;
+    double phi_lim = 0.0;
+    std::string msg;
+
+    enum { LS_OK = 0, LS_EXCEPTION = 1 };   // LS_EXCEPTION: LineSearchException (alpha still returned)
+
+    static bool fin(double a, double b) { return std::isfinite(a) && std::isfinite(b); }
+    static double eps_of(double x) { return std::nextafter(std::fabs(x), INFINITY) - std::fabs(x); }
+    static double nextfloat(double x) { return std::nextafter(x, INFINITY); }
+    bool wolfe(double c, double phi_c, double dphi_c, double phi_0, double dphi_0) const {
+        const bool w1 = delta * dphi_0 >= (phi_c - phi_0) / c && dphi_c >= sigma * dphi_0;
+        const bool w2 = (2 * delta - 1) * dphi_0 >= dphi_c && dphi_c >= sigma * dphi_0 && phi_c <= phi_lim;
+        return w1 || w2;
+    }
+    int eval(double c, double& p, double& d) { return phidphi(c, p, d); }
+    void push(double c, double p, double d) { alphas.push_back(c); values.push_back(p); slopes.push_back(d); }
+
+    // status < 0: WB200 error; LS_OK / LS_EXCEPTION otherwise
+    int run(double c, double phi_0, double dphi_0, double& alpha_out, double& phi_out) {
+        const double eps64 = std::numeric_limits<double>::epsilon();
+        alpha_out = 0.0; phi_out = phi_0;
+        if (!fin(phi_0, dphi_0)) { msg = "Value and slope at step length = 0 must be finite."; return LS_EXCEPTION; }
+        if (dphi_0 >= eps64 * std::fabs(phi_0)) { msg = "Search direction is not a direction of descent."; return LS_EXCEPTION; }
+        if (dphi_0 >= 0.0) return LS_OK;
+        double amax = alphamax;
+        const int iterfinitemax = (int)std::ceil(-std::log2(eps64));
+        alphas = {0.0}; values = {phi_0}; slopes = {dphi_0};
+        phi_lim = phi_0 + epsilon * std::fabs(phi_0);
+        if (c <= eps64) return LS_OK;
+        double phi_c, dphi_c;
+        WB_TRY(eval(c, phi_c, dphi_c));
+        int iterfinite = 1;
+        while (!fin(phi_c, dphi_c) && iterfinite < iterfinitemax) {
+            iterfinite++;
+            c *= psi3;
+            WB_TRY(eval(c, phi_c, dphi_c));
+        }
+        if (!fin(phi_c, dphi_c)) return LS_OK;   // "Failed to achieve finite new evaluation point, using alpha=0"
+        push(c, phi_c, dphi_c);
+        // (mayterminate is never set by InitialStatic: the first point is not tested for Wolfe here)
+        bool isbracketed = false;
+        int ia = 0, ib = 1, iter = 1;
+        double cold = -1.0, phi_cold = phi_0;
+        while (!isbracketed && iter < linesearchmax) {
+            if (dphi_c >= 0.0) {
+                ib = (int)alphas.size() - 1;
+                for (int i = ib - 1; i >= 0; i--)
+                    if (values[i] <= phi_lim) { ia = i; break; }
+                isbracketed = true;
+            } else if (values.back() > phi_lim) {
+                ib = (int)alphas.size() - 1;
+                ia = 0;
+                WB_TRY(bisect(ia, ib));
+                isbracketed = true;
+            } else {
+                cold = c; phi_cold = phi_c;
+                if (nextfloat(cold) >= amax) { alpha_out = cold; phi_out = phi_cold; return LS_OK; }
+                c *= rho;
+                if (c > amax) c = amax;
+                WB_TRY(eval(c, phi_c, dphi_c));
+                iterfinite = 1;
+                while (!fin(phi_c, dphi_c) && c > nextfloat(cold) && iterfinite < iterfinitemax) {
+                    amax = c;
+                    iterfinite++;
+                    c = (cold + c) / 2;
+                    WB_TRY(eval(c, phi_c, dphi_c));
+                }
+                if (!fin(phi_c, dphi_c)) { alpha_out = cold; phi_out = phi_cold; return LS_OK; }
+                push(c, phi_c, dphi_c);
+            }
+            iter++;
+        }
+        while (iter < linesearchmax) {
+            const double a = alphas[ia], b = alphas[ib];
+            if (!(b > a)) { msg = "HagerZhang: bracket lost (b <= a)"; return WB200_ERR_NOCONV; }
+            if (b - a <= eps_of(b)) { alpha_out = a; phi_out = values[ia]; return LS_OK; }
+            bool iswolfe = false;
+            int iA = ia, iB = ib;
+            WB_TRY(secant2(ia, ib, phi_0, dphi_0, iswolfe, iA, iB));
+            if (iswolfe) { alpha_out = alphas[iA]; phi_out = values[iA]; return LS_OK; }
+            const double A = alphas[iA], B = alphas[iB];
+            if (!(B > A)) { msg = "HagerZhang: bracket lost (B <= A)"; return WB200_ERR_NOCONV; }
+            if (B - A < gamma * (b - a)) {
+                if (nextfloat(values[ia]) >= values[ib] && nextfloat(values[iA]) >= values[iB]) {
+                    alpha_out = A; phi_out = values[iA];   // so flat that secant did nothing useful
+                    return LS_OK;
+                }
+                ia = iA; ib = iB;
+            } else {
+                c = (A + B) / 2;
+                WB_TRY(eval(c, phi_c, dphi_c));
+                if (!fin(phi_c, dphi_c)) { msg = "HagerZhang: non-finite value inside the bracket"; return WB200_ERR_NOCONV; }
+                push(c, phi_c, dphi_c);
+                ia = iA; ib = iB;
+                WB_TRY(update(ia, ib, (int)alphas.size() - 1));
+            }
+            iter++;
+        }
+        msg = "Linesearch failed to converge, reached maximum iterations.";
+        alpha_out = alphas[ia]; phi_out = values[ia];
+        return LS_EXCEPTION;
+    }
+
+    int secant2(int ia, int ib, double phi_0, double dphi_0, bool& iswolfe, int& iA, int& iB) {
+        const double a = alphas[ia], b = alphas[ib], da = slopes[ia], db = slopes[ib];
+        iswolfe = false;
+        if (!(da < 0.0 && db >= 0.0)) { msg = "HagerZhang: search direction is not a direction of descent"; return WB200_ERR_NOCONV; }
+        double c = (a * db - b * da) / (db - da);
+        double phi_c, dphi_c;
+        WB_TRY(eval(c, phi_c, dphi_c));
+        if (!fin(phi_c, dphi_c)) { msg = "HagerZhang: non-finite value in secant2"; return WB200_ERR_NOCONV; }
+        push(c, phi_c, dphi_c);
+        int ic = (int)alphas.size() - 1;
+        if (wolfe(c, phi_c, dphi_c, phi_0, dphi_0)) { iswolfe = true; iA = iB = ic; return WB200_OK; }
+        iA = ia; iB = ib;
+        WB_TRY(update(iA, iB, ic));
+        const double a2 = alphas[iA], b2 = alphas[iB];
+        if (iB == ic) c = (alphas[ib] * slopes[iB] - alphas[iB] * slopes[ib]) / (slopes[iB] - slopes[ib]);
+        else if (iA == ic) c = (alphas[ia] * slopes[iA] - alphas[iA] * slopes[ia]) / (slopes[iA] - slopes[ia]);
+        if ((iA == ic || iB == ic) && a2 <= c && c <= b2) {
+            WB_TRY(eval(c, phi_c, dphi_c));
+            if (!fin(phi_c, dphi_c)) { msg = "HagerZhang: non-finite value in secant2"; return WB200_ERR_NOCONV; }
+            push(c, phi_c, dphi_c);
+            ic = (int)alphas.size() - 1;
+            if (wolfe(c, phi_c, dphi_c, phi_0, dphi_0)) { iswolfe = true; iA = iB = ic; return WB200_OK; }
+            WB_TRY(update(iA, iB, ic));
+        }
+        return WB200_OK;
+    }
+
+    // (ia, ib) in/out
+    int update(int& ia, int& ib, int ic) {
+        const double a = alphas[ia], b = alphas[ib], c = alphas[ic];
+        if (c < a || c > b) return WB200_OK;
+        if (slopes[ic] >= 0.0) { ib = ic; return WB200_OK; }
+        if (values[ic] <= phi_lim) { ia = ic; return WB200_OK; }
+        ib = ic;
+        return bisect(ia, ib);
+    }
+
+    int bisect(int& ia, int& ib) {
+        double a = alphas[ia], b = alphas[ib];
+        while (b - a > eps_of(b)) {
+            const double d = (a + b) / 2;
+            double phi_d, g;
+            WB_TRY(eval(d, phi_d, g));
+            if (!fin(phi_d, g)) { msg = "HagerZhang: non-finite value in bisect"; return WB200_ERR_NOCONV; }
+            push(d, phi_d, g);
+            const int id = (int)alphas.size() - 1;
+            if (g >= 0.0) { ib = id; return WB200_OK; }
+            if (phi_d <= phi_lim) { a = d; ia = id; } else { b = d; ib = id; }
+        }
+        return WB200_OK;
+    }
+};
 
 struct Problem {
     wb200_ctx* ctx;
@@ -89,31 +263,30 @@ int wb_lbfgs(wb200_ctx* ctx, int mode, cplx* dx, double f_tol, double g_tol, int
     P.n = 2 * ncplx;
     const size_t n = P.n;
     const int m = history > 0 ? history : 3;
+    const int successive_f_tol = 1;   // Optim.Options default
 
-    // work vectors: g, d, xn, gn + two spare (x, g) buffers for the best trial point + (m + 1)
-    // history pairs (m live + one candidate)
-    const int nfixed = 6;
-    const int nvec = nfixed + 2 * (m + 1);
+    // work vectors: g, s, xn, gn + m history pairs
+    const int nfixed = 4;
+    const int nvec = nfixed + 2 * m;
     double* pool = nullptr;
     WB_CUDA(ctx, cudaMalloc(&pool, sizeof(double) * n * nvec));
     struct Free { double* p; ~Free() { cudaFree(p); } } guard{pool};
     auto vec = [&](int i) { return pool + (size_t)i * n; };
-    // x lives in the caller's array or in one of the spares (pointer swaps instead of copies)
-    double *x = (double*)dx, *g = vec(0), *d = vec(1), *xn = vec(2), *gn = vec(3), *xb = vec(4),
-           *gb = vec(5);
-    auto S = [&](int s) { return vec(nfixed + 2 * s); };
-    auto Y = [&](int s) { return vec(nfixed + 2 * s + 1); };
-    std::deque<int> slots;            // live history slots, oldest first
+    // x lives in the caller's array or in a spare (pointer swaps instead of copies)
+    double *x = (double*)dx, *g = vec(0), *s = vec(1), *xn = vec(2), *gn = vec(3);
+    auto DX = [&](int sl) { return vec(nfixed + 2 * sl); };
+    auto DG = [&](int sl) { return vec(nfixed + 2 * sl + 1); };
+    std::deque<int> slots;            // live history slots, oldest first (Optim's ring mod1(pseudo, m))
     std::vector<int> free_slots;
-    for (int i = m; i >= 0; i--) free_slots.push_back(i);
+    for (int i = m - 1; i >= 0; i--) free_slots.push_back(i);
 
-    // Gram matrix of the vectors {g, S(0..m), Y(0..m)} by id: 0 = g, 1 + s = S(s), 2 + m + s = Y(s)
-    const int nid = 1 + 2 * (m + 1);
+    // Gram matrix of the vectors {g, DX(0..m-1), DG(0..m-1)} by id: 0 = g, 1 + sl = DX(sl), 1 + m + sl = DG(sl)
+    const int nid = 1 + 2 * m;
     std::vector<double> GM((size_t)nid * nid, 0.0);
-    auto idS = [&](int s) { return 1 + s; };
-    auto idY = [&](int s) { return 2 + m + s; };
+    auto idX = [&](int sl) { return 1 + sl; };
+    auto idG = [&](int sl) { return 1 + m + sl; };
     auto ptr_of = [&](int id) -> const double* {
-        return id == 0 ? g : (id <= m + 1 ? S(id - 1) : Y(id - 2 - m));
+        return id == 0 ? g : (id <= m ? DX(id - 1) : DG(id - 1 - m));
     };
     // refresh the Gram rows of the first `na` ids of `ids` (against all of `ids`); returns max |g|
     auto refresh = [&](const std::vector<int>& ids, int na, double* gmax) -> int {
@@ -126,7 +299,7 @@ int wb_lbfgs(wb200_ctx* ctx, int mode, cplx* dx, double f_tol, double g_tol, int
             c.a_in_b = off == 0;
             WB_TRY(wb_cross_launch(ctx, c, n));
             WB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-            const double* h = ctx->h_pinned + WB_PIN_CROSS;
+                const double* h = ctx->h_pinned + WB_PIN_CROSS;
             for (int i = 0; i < na; i++)
                 for (int j = 0; j < c.nb; j++) {
                     const int a = ids[i], b = ids[off + j];
@@ -137,39 +310,26 @@ int wb_lbfgs(wb200_ctx* ctx, int mode, cplx* dx, double f_tol, double g_tol, int
         return WB200_OK;
     };
 
-    WB_TRY(P.retract(dx));
+    // ---- initial_state: retract!, value_gradient!!, project_tangent! ----
+    {
+        int st = P.retract(dx);
+        if (st == WB200_ERR_NOCONV && ctx->allreduce) ctx->poison_next = 1;   // peers must see the failure too
+        else WB_TRY(st);
+    }
     double f = 0.0;
     WB_TRY(P.fg(dx, &f, (cplx*)g, nullptr, nullptr));
-    int it = 0;
-    int pending = -1;   // slot of the secant pair formed by the last iteration, not yet admitted
-    while (it < max_iter) {
-        // ---- Gram rows of g (and of the new pair), max |g| : one pass over memory ----
-        // (a full history evicts its oldest pair when the new one is admitted, so that pair is left
-        // out of the pass: g + new pair + the m - 1 newest pairs = 7 vectors at m = 3)
-        const bool skip_oldest = pending >= 0 && (int)slots.size() == m;
-        std::vector<int> ids{0};
-        if (pending >= 0) { ids.push_back(idS(pending)); ids.push_back(idY(pending)); }
-        for (size_t i = skip_oldest ? 1 : 0; i < slots.size(); i++) ids.push_back(idS(slots[i]));
-        for (size_t i = skip_oldest ? 1 : 0; i < slots.size(); i++) ids.push_back(idY(slots[i]));
-        double gmax = 0.0;
-        WB_TRY(refresh(ids, pending >= 0 ? 3 : 1, &gmax));
-        if (pending >= 0) {   // admit the pair if it has positive curvature
-            const double sy = GM[(size_t)idS(pending) * nid + idY(pending)];
-            const double ss = GM[(size_t)idS(pending) * nid + idS(pending)];
-            const double yy = GM[(size_t)idY(pending) * nid + idY(pending)];
-            if (sy > 1e-14 * sqrt(ss * yy)) {
-                slots.push_back(pending);
-                if ((int)slots.size() > m) { free_slots.push_back(slots.front()); slots.pop_front(); }
-            } else {
-                free_slots.push_back(pending);
-                if (skip_oldest)   // the oldest pair stays: its products with the new g are still missing
-                    WB_TRY(refresh({0, idS(slots.front()), idY(slots.front())}, 1, nullptr));
-            }
-            pending = -1;
-        }
-        if (gmax <= g_tol) break;
-
-        // ---- two-loop recursion on the coefficients of q = sum_id c[id] v_id ----
+    if (!std::isfinite(f)) {
+        ctx->err = "initial point: spread is not finite (retraction failed or singular overlaps)";
+        return WB200_ERR_NOCONV;
+    }
+    double gmax = 0.0;
+    WB_TRY(refresh({0}, 1, &gmax));
+    bool converged = gmax <= g_tol;   // initial_convergence
+    int it = 0, counter_f_tol = 0;
+    bool hist_reset = false;
+    while (!converged && it < max_iter) {
+        it++;
+        // ---- update_state!: two-loop recursion on the coefficients of q = sum_id c[id] v_id ----
         std::vector<double> c(nid, 0.0);
         c[0] = 1.0;
         auto dotq = [&](int id) {
@@ -177,27 +337,26 @@ int wb_lbfgs(wb200_ctx* ctx, int mode, cplx* dx, double f_tol, double g_tol, int
             for (int j = 0; j < nid; j++) if (c[j] != 0.0) t += c[j] * GM[(size_t)id * nid + j];
             return t;
         };
-        auto rho = [&](int s) { return 1.0 / GM[(size_t)idS(s) * nid + idY(s)]; };
+        auto rho = [&](int sl) { return 1.0 / GM[(size_t)idX(sl) * nid + idG(sl)]; };
         std::vector<double> al;
         for (auto itS = slots.rbegin(); itS != slots.rend(); ++itS) {
-            const double a = rho(*itS) * dotq(idS(*itS));
+            const double a = rho(*itS) * dotq(idX(*itS));
             al.push_back(a);
-            c[idY(*itS)] -= a;
+            c[idG(*itS)] -= a;
         }
-        if (!slots.empty()) {
+        if (!slots.empty()) {   // Nocedal & Wright (7.20) with the newest pair
             const int last = slots.back();
-            const double gamma = GM[(size_t)idS(last) * nid + idY(last)] / GM[(size_t)idY(last) * nid + idY(last)];
-            for (double& v : c) v *= gamma;
+            const double scaling = GM[(size_t)idX(last) * nid + idG(last)] / GM[(size_t)idG(last) * nid + idG(last)];
+            for (double& v : c) v *= scaling;
         }
         {
             int j = (int)al.size() - 1;
             for (auto itS = slots.begin(); itS != slots.end(); ++itS, --j) {
-                const double b = rho(*itS) * dotq(idY(*itS));
-                c[idS(*itS)] += al[j] - b;
+                const double b = rho(*itS) * dotq(idG(*itS));
+                c[idX(*itS)] += al[j] - b;
             }
         }
-        // d = -q in one pass (chunks of 7 vectors)
-        {
+        {   // s = -q in one pass (chunks of 7 vectors), then project_tangent!(s, x)
             std::vector<int> used;
             for (int id = 0; id < nid; id++) if (c[id] != 0.0) used.push_back(id);
             if (used.empty()) used.push_back(0);
@@ -206,74 +365,91 @@ int wb_lbfgs(wb200_ctx* ctx, int mode, cplx* dx, double f_tol, double g_tol, int
                 l.nv = (int)std::min<size_t>(WB_CROSS_NB, used.size() - off);
                 for (int j = 0; j < l.nv; j++) { l.v[j] = ptr_of(used[off + j]); l.c[j] = -c[used[off + j]]; }
                 l.beta = off == 0 ? 0.0 : 1.0;
-                WB_TRY(wb_lincomb(ctx, l, d, n));
+                WB_TRY(wb_lincomb(ctx, l, s, n));
             }
         }
-        WB_TRY(P.project((const cplx*)x, (cplx*)d));
+        WB_TRY(P.project((const cplx*)x, (cplx*)s));
+        // ---- perform_linesearch! ----
         const double gg = GM[0];
         double dphi0 = 0.0;
         {
             WbCrossArgs cr{};
-            cr.a[0] = g; cr.na = 1; cr.b[0] = d; cr.nb = 1;
+            cr.a[0] = g; cr.na = 1; cr.b[0] = s; cr.nb = 1;
             WB_TRY(wb_cross_launch(ctx, cr, n));
             WB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-            dphi0 = ctx->h_pinned[WB_PIN_CROSS];
+                dphi0 = ctx->h_pinned[WB_PIN_CROSS];
         }
-        if (dphi0 >= 0.0) {   // not a descent direction: steepest descent, forget the history
+        hist_reset = false;
+        if (dphi0 >= 0.0) {   // reset_search_direction!: steepest descent, pseudo_iteration = 1
             WbLinArgs l{};
             l.v[0] = g; l.c[0] = -1.0; l.nv = 1;
-            WB_TRY(wb_lincomb(ctx, l, d, n));
+            WB_TRY(wb_lincomb(ctx, l, s, n));
             dphi0 = -gg;
+            hist_reset = true;
+        }
+        const double f_prev = f;
+        double last_alpha = -1.0, last_f = 0.0;
+        HagerZhang hz;
+        hz.phidphi = [&](double a, double& phi, double& dphi) -> int {
+            WbLinArgs l{};
+            l.v[0] = x; l.c[0] = 1.0; l.v[1] = s; l.c[1] = a; l.nv = 2;
+            WB_TRY(wb_lincomb(ctx, l, xn, n));
+            int st = P.retract((cplx*)xn);
+            if (st == WB200_ERR_NOCONV) ctx->poison_next = 1;   // this trial point is rejected on every rank
+            else WB_TRY(st);
+            double fv = 0.0, dv = 0.0;
+            WB_TRY(P.fg((cplx*)xn, &fv, (cplx*)gn, s, &dv));
+            phi = fv; dphi = dv;
+            last_alpha = a; last_f = fv;
+            return WB200_OK;
+        };
+        double alpha = 0.0, phi_a = f;
+        const int ls = hz.run(1.0 /* InitialStatic */, f, dphi0, alpha, phi_a);
+        if (ls < 0) {
+            if (ctx->err.empty() || ls == WB200_ERR_NOCONV) ctx->err = hz.msg.empty() ? ctx->err : hz.msg;
+            return ls;
+        }
+        if (alpha == 0.0) {   // x_converged: the iterate did not move (Optim counts the iteration)
+            converged = true;
+            break;
+        }
+        if (alpha != last_alpha) {   // update_g! re-evaluates when the accepted point is not the last trial
+            double pa, da;
+            WB_TRY(hz.phidphi(alpha, pa, da));
+            phi_a = pa;
+            if (!std::isfinite(pa)) {
+                ctx->err = "line search returned a point with a non-finite spread";
+                return WB200_ERR_NOCONV;
+            }
+        } else {
+            phi_a = last_f;
+        }
+        // ---- update_h!: dx = alpha s, dg = g_new - g_previous into the slot mod1(pseudo_iteration, m) ----
+        if (hist_reset) while (!slots.empty()) { free_slots.push_back(slots.front()); slots.pop_front(); }
+        int sl;
+        if (free_slots.empty()) { sl = slots.front(); slots.pop_front(); }
+        else { sl = free_slots.back(); free_slots.pop_back(); }
+        WB_TRY(wb_secant(ctx, alpha, s, gn, g, DX(sl), DG(sl), n));
+        std::swap(x, xn);   // x <- accepted point, g <- its projected gradient (the old ones become the trial buffers)
+        std::swap(g, gn);
+        f = phi_a;
+        slots.push_back(sl);
+        {   // Gram rows of g and of the new pair against everything live: one pass over memory
+            std::vector<int> ids{0, idX(sl), idG(sl)};
+            for (size_t i = 0; i + 1 < slots.size(); i++) ids.push_back(idX(slots[i]));
+            for (size_t i = 0; i + 1 < slots.size(); i++) ids.push_back(idG(slots[i]));
+            WB_TRY(refresh(ids, 3, &gmax));
+        }
+        const double sy = GM[(size_t)idX(sl) * nid + idG(sl)];
+        if (sy == 0.0 || !std::isfinite(1.0 / sy)) {   // isinf(rho): pseudo_iteration = 0, history dropped
             while (!slots.empty()) { free_slots.push_back(slots.front()); slots.pop_front(); }
         }
-        double alpha = slots.empty() ? fmin(1.0, 1.0 / fmax(sqrt(gg), 1e-300)) : 1.0;
-
-        // ---- strong-Wolfe bracketing line search ----
-        // phi'(alpha) = <g(x_alpha), d> with g projected at x_alpha (the tangent projection is
-        // self-adjoint, so projecting d as well would not change the product)
-        const double c1 = 1e-4, c2 = 0.9;
-        double lo = 0.0, hi = -1.0, f_lo = f;
-        bool have_best = false;
-        double f_best = 0.0, a_best = 0.0;
-        // the best trial point so far lives in (xb, gb); (xn, gn) is the current trial
-        for (int ls = 0; ls < 30; ls++) {
-            WbLinArgs l{};
-            l.v[0] = x; l.c[0] = 1.0; l.v[1] = d; l.c[1] = alpha; l.nv = 2;
-            WB_TRY(wb_lincomb(ctx, l, xn, n));
-            WB_TRY(P.retract((cplx*)xn));
-            double fn = 0.0, dn = 0.0;
-            WB_TRY(P.fg((cplx*)xn, &fn, (cplx*)gn, d, &dn));
-            if (!(fn == fn)) {  // NaN: shrink
-                hi = alpha;
-            } else if (fn > f + c1 * alpha * dphi0 || (have_best && fn >= f_lo && lo > 0.0)) {
-                hi = alpha;
-            } else if (fabs(dn) <= -c2 * dphi0) {
-                std::swap(xn, xb); std::swap(gn, gb);
-                f_best = fn; a_best = alpha; have_best = true;
-                break;
-            } else if (dn >= 0.0) {
-                hi = alpha;
-            } else {
-                lo = alpha; f_lo = fn;
-                std::swap(xn, xb); std::swap(gn, gb);
-                f_best = fn; a_best = alpha; have_best = true;
-            }
-            alpha = (hi < 0.0) ? 2.0 * alpha : 0.5 * (lo + hi);
-        }
-        if (!have_best) break;
-        // secant pair as Optim.jl's LBFGS forms it on a manifold (update_state! / update_h!):
-        // dx = alpha * s (the step before retraction), dg = g_new - g_previous, each gradient
-        // projected at its own point; the history is not transported.  Its inner products are
-        // taken by the next iteration's Gram pass, which also decides whether it is admitted.
-        pending = free_slots.back();
-        free_slots.pop_back();
-        WB_TRY(wb_secant(ctx, a_best, d, gb, g, S(pending), Y(pending), n));
-        const double df = fabs(f_best - f);
-        std::swap(x, xb);   // x <- best trial point, g <- its gradient (the old ones become spares)
-        std::swap(g, gb);
-        f = f_best;
-        it++;
-        if (df <= f_tol * fabs(f)) break;
+        // ---- assess_convergence ----
+        const bool f_converged = fabs(f - f_prev) <= f_tol * fabs(f);
+        const bool g_converged = gmax <= g_tol;
+        counter_f_tol = f_converged ? counter_f_tol + 1 : 0;
+        converged = g_converged || counter_f_tol > successive_f_tol;
+        if (ls == HagerZhang::LS_EXCEPTION) break;   // Optim leaves the loop when the line search failed
     }
     if (x != (double*)dx)
         WB_CUDA(ctx, cudaMemcpyAsync(dx, x, sizeof(double) * n, cudaMemcpyDeviceToDevice, ctx->stream));

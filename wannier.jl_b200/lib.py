@@ -166,6 +166,10 @@ class Context:
             pass
 
     def _ck(self, st):
+        cb_error = getattr(self, "_cb_error", None)
+        if cb_error is not None:
+            self._cb_error = None
+            raise cb_error
         if st != 0:
             raise WB200Error(st, self._lib.wb200_last_error(self._h).decode())
 
@@ -223,8 +227,19 @@ class Context:
             self._cb = None
             self._ck(self._lib.wb200_set_allreduce(self._h, None, None))
             return
-        proto = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p)
-        self._cb = proto(lambda dptr, count, op, stream, user: fn(dptr or 0, count, op, stream or 0))
+        proto = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p)
+
+        def thunk(dptr, count, op, stream, user):
+            # an exception must not be swallowed by ctypes: latch it, return a failure status (the C
+            # side then aborts the call with WB200_ERR_CUDA) and re-raise it from _ck
+            try:
+                fn(dptr or 0, count, op, stream or 0)
+                return 0
+            except BaseException as e:      # noqa: BLE001
+                self._cb_error = e
+                return 1
+
+        self._cb = proto(thunk)
         self._ck(self._lib.wb200_set_allreduce(self._h, C.cast(self._cb, C.c_void_p), None))
 
     def profile(self, enable):
