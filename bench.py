@@ -96,59 +96,97 @@ def work_per_eval(nb, nw, nk, nn):
 
 
 # ------------------------------------------------------------------------------------------
-# reference arm / cpu_baseline: the oracle on a bounded sample, all host cores
+# reference arm / cpu_baseline: the compiled CPU port (oracle/spread_ref.cpp: C++17, OpenMP over k,
+# OpenBLAS ZGEMM per pair exactly as the reference's mul! calls), all host cores, FULL k-grid when
+# the host memory allows it (otherwise a stated k-point sample, extrapolated linearly)
 # ------------------------------------------------------------------------------------------
-def cpu_reference(cfg_name, steps, warmup, sample_k=None, seconds_budget=25.0):
-    from oracle import cpu_baseline as cb
-    import __graft_entry__ as ge
-    w = ge.load_package()
-    lat, grid, nb, nw = w.synthetic.CONFIGS[cfg_name]
-    st = w.synthetic.make_stencil(w.synthetic.LATTICES[lat](), grid)
+def _host_inputs(w, st, nb, nw, ks, device=None):
+    """(M [len(ks)][nn][nb][nb], U [nk][nw][nb]) in the C-ABI layout on the host, from the product's
+    synthetic recipe.  The subspace family V_k is generated on the GPU when there is one (input
+    generation only — nothing timed), the overlaps M_kb = V_k^H V_{k+b} by the CPU port itself."""
+    from oracle import cpu_ref as cr
+    syn = w.synthetic
+    nk = len(st["kpoints"])
+    need = np.unique(np.concatenate([ks, st["kpb_k"][ks].ravel()]))
+    umap = -np.ones(nk, dtype=np.int64)
+    umap[need] = np.arange(len(need))
+    Rs, c = syn._coeffs(nb, syn.SEED_M)
+    if device is not None:
+        import torch
+        kp = torch.as_tensor(st["kpoints"][need], device=device)
+        phase = torch.exp(2j * np.pi * (kp @ torch.as_tensor(Rs, device=device).T))
+        B = torch.einsum("kr,rhn->khn", phase, torch.as_tensor(c, device=device))
+        B[:, :nb, :] += torch.eye(nb, dtype=B.dtype, device=device)
+        V = syn._polar_torch(B).cpu().numpy()
+        U = syn.make_gauge_torch(nk, nb, nw, device).cpu().numpy()
+        del B
+        torch.cuda.empty_cache()
+    else:
+        phase = np.exp(2j * np.pi * (st["kpoints"][need] @ Rs.T))
+        B = np.einsum("kr,rhn->khn", phase, c)
+        B[:, :nb, :] += np.eye(nb)
+        V = syn._polar_np(B)
+        U = np.ascontiguousarray(syn.make_gauge(nk, nb, nw).transpose(0, 2, 1))
+    Vcat = np.concatenate([V[umap[ks]], V], axis=0)
+    kpb = (len(ks) + umap[st["kpb_k"][ks]]).astype(np.int32)
+    M = cr.overlaps_from_subspaces(Vcat, kpb)
+    return np.ascontiguousarray(M), np.ascontiguousarray(U)
+
+
+def cpu_port_figure(w, st, nb, nw, steps, warmup, device=None, seconds_budget=60.0):
+    """Times oracle/spread_ref.cpp on the host cores.  Returns (cpu_baseline dict, seconds per step, steps)."""
+    import psutil
+    from oracle import cpu_ref as cr
+    cr.load()
     nk, nn = st["kpb_k"].shape
     cores = os.cpu_count() or 1
-    if sample_k is None:
-        # about 0.25 s of work per core per step at ~5 GFLOP/s/core of complex GEMM
-        per_k = 8.0 * nn * (nb * nb * nw + nb * nw * nw)
-        sample_k = int(max(cores, min(nk, cores * 8e9 / per_k)))
-    ks = np.linspace(0, nk - 1, sample_k).astype(np.int64)
-    M, U = cb.sample_inputs(w, st, nb, nw, ks)
-    run = lambda: cb.fg_sample(M, st["kpb_k"][ks], st["bvec"][ks], st["wb"], U, ks, nk, threads=cores)
-    for _ in range(warmup):
-        run()
+    per_k = 16.0 * nn * (nb * nb + nb * nw + nw * nw) + 16.0 * nb * nw      # M, MU, N of the pairs of a k-point, G
+    avail = psutil.virtual_memory().available
+    need_full = per_k * nk + 3 * 16.0 * nk * nb * nw + 16.0 * nk * (nb + max(8, nb // 4)) * nb
+    if need_full < 0.45 * avail and (device is not None or nk * nb * nb <= 4e6):
+        ks = np.arange(nk, dtype=np.int64)
+    else:   # bounded sample: what fits, at least a k-point per core, at most ~1 s per step
+        n_s = int(max(cores, min(nk, 0.2 * avail / per_k, cores * 8e9 / (8.0 * nn * (nb * nb * nw + nb * nw * nw)))))
+        ks = np.linspace(0, nk - 1, n_s).astype(np.int64)
+    M, U = _host_inputs(w, st, nb, nw, ks, device)
+    ws = cr.Workspace(nb, nw, len(ks), nn)
+    full = len(ks) == nk
+    run = lambda th=cores, sel=slice(None): cr.fg_abi(M[sel], st["kpb_k"], st["bvec"], st["wb"], U, nk,
+                                                        k_sel=None if (full and sel == slice(None)) else ks[sel],
+                                                        threads=th, ws=ws)
+    for _ in range(max(1, min(warmup, 2))):
+        res, _ = run()
     ts = []
     t_all = time.perf_counter()
-    for _ in range(steps):
+    for _ in range(max(steps, 2)):
         t0 = time.perf_counter()
-        run()
+        res, _ = run()
         ts.append(time.perf_counter() - t0)
         if time.perf_counter() - t_all > seconds_budget and len(ts) >= 2:
             break
     t = float(np.mean(ts))
-    value = (sample_k / nk) / t
-    one = one_thread_figure(cb, M, st["kpb_k"][ks], st["bvec"][ks], st["wb"], U, ks, nk)
-    return dict(value=value, unit="evals/s", cores=cores, kind="port",
-                sample=f"{sample_k} of {nk} k-points ({sample_k * nn} pairs, both ZGEMMs per pair as "
-                       f"spread.jl:173-174, omega!/omega_grad! loops), {len(ts)} x {t:.3f} s, "
-                       f"numpy+OpenBLAS, {cores} threads over k; extrapolated to the full k-grid",
-                one_thread=one), t, len(ts)
-
-
-def one_thread_figure(cbm, M, kpb, bvec, wb, U, ks, nk, seconds=6.0):
-    """The reference's own benchmark setting (one thread, benchmark/runbenchmarks.jl:3-7) on a slice of
-    the multithreaded sample, extrapolated the same way."""
-    n1 = max(2, len(ks) // 16)
-    sel = np.arange(n1)
-    run = lambda: cbm.fg_sample(M[sel], kpb[sel], bvec[sel], wb, U, ks[sel], nk, threads=1, single_blas=True)
-    run()
-    ts = []
+    value = (len(ks) / nk) / t
+    # the reference's own benchmark setting: one thread (benchmark/runbenchmarks.jl:3-7), on a slice
+    n1 = int(max(2, min(len(ks), 16)))
+    sel = slice(0, n1)
+    run(1, sel)
+    t1s = []
     t_all = time.perf_counter()
-    while len(ts) < 2 or (time.perf_counter() - t_all < seconds and len(ts) < 10):
+    while len(t1s) < 2 or (time.perf_counter() - t_all < 5.0 and len(t1s) < 10):
         t0 = time.perf_counter()
-        run()
-        ts.append(time.perf_counter() - t0)
-    t = float(np.mean(ts))
-    return {"value": (n1 / nk) / t, "unit": "evals/s", "cores": 1,
-            "sample": f"{n1} of {nk} k-points, {len(ts)} x {t:.3f} s, one thread (one OpenBLAS thread)"}
+        run(1, sel)
+        t1s.append(time.perf_counter() - t0)
+    t1 = float(np.mean(t1s))
+    what = (f"FULL k-grid ({nk} k-points, {nk * nn} pairs)" if full else
+            f"{len(ks)} of {nk} k-points ({len(ks) * nn} pairs), extrapolated linearly to the full grid")
+    cb = dict(value=value, unit="evals/s", cores=cores, kind="port",
+              sample=f"{what}; both ZGEMMs per pair as spread.jl:173-174 + center!/omega_grad!/omega! loops in "
+                     f"reference order; {len(ts)} x {t:.3f} s; oracle/spread_ref.cpp (C++17 -O3 -fopenmp, {cores} "
+                     f"threads over k, {cr.blas_name().split(' from ')[0]}, one BLAS thread per caller)",
+              omega_check=float(res[0]) if full else None,
+              one_thread={"value": (n1 / nk) / t1, "unit": "evals/s", "cores": 1,
+                          "sample": f"{n1} of {nk} k-points, {len(t1s)} x {t1:.3f} s, one thread"})
+    return cb, t, len(ts)
 
 
 def main():
@@ -189,7 +227,15 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        cb, t, n = cpu_reference(args.config, args.steps, args.warmup)
+        dev_gen = None
+        try:
+            import torch
+            if torch.cuda.is_available():
+                dev_gen = torch.device("cuda", local_rank)       # input generation only; nothing timed runs there
+        except Exception:
+            pass
+        st = w.synthetic.make_stencil(w.synthetic.LATTICES[lat](), grid)
+        cb, t, n = cpu_port_figure(w, st, nb, nw, args.steps, args.warmup, dev_gen, seconds_budget=150.0)
         line = {"impl": "reference", "metric": metric, "value": cb["value"], "unit": "evals/s",
                 "n_gpus": args.gpus, "steps": n, "warmup": args.warmup, "ms_per_step": t * 1e3,
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
@@ -217,15 +263,6 @@ def main():
     nkl = k1 - k0
     M = w.synthetic.make_overlaps_torch(st, nb, dev, k_begin=k0, nk=nkl)
     dU = w.synthetic.make_gauge_torch(nk, nb, nw, dev)                      # [nk][nw][nb] abi image
-    cpu_sample = None
-    if rank == 0 and not args.no_cpu_baseline:
-        from oracle import cpu_baseline as cbm
-        cores = os.cpu_count() or 1
-        per_k = 8.0 * nn * (nb * nb * nw + nb * nw * nw)
-        sample_k = int(max(min(cores, nkl), min(nkl, cores * 8e9 / per_k)))
-        ks = np.linspace(0, nkl - 1, sample_k).astype(np.int64)
-        cpu_sample = (ks, M[torch.as_tensor(ks, device=dev)].transpose(2, 3).cpu().numpy(),
-                      dU.transpose(1, 2).cpu().numpy())
     torch.cuda.synchronize()
     ctx = w.Context(nb, nw, nk, nn, st["kpb_k"][k0:k1], st["bvec"][k0:k1], st["wb"], M.data_ptr(),
                     device=local_rank, k_begin=k0, nk=nkl)
@@ -324,6 +361,12 @@ def main():
     ms_step = ms_total / args.steps
     value = 1e3 / ms_step
     omega_val = dres[0].item()
+    # checksum of the gradient over ALL ranks (the sharded run must reproduce the one-GPU gradient, not
+    # only the spread): sum |G|^2, all-reduced
+    gsq = torch.view_as_real(dG).square().sum().reshape(1)
+    if world > 1:
+        dist.all_reduce(gsq)
+    g_check = gsq.item()
 
     # ---- end-to-end through the host-pointer drop-in call (N = 1: wb200_fg; N > 1: slab copies) ----
     e2e = None
@@ -385,6 +428,10 @@ def main():
     dmma_peak, dfma_peak = w.lib.probe_fp64_peak(local_rank)
     pk = _peaks()
     hbm_peak = pk["hbm_gbs"] if pk else 6650.0
+    try:   # per-kernel DRAM bytes of the latest committed ncu capture
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.config, {})
+    except Exception:
+        traffic = {}
     rot_ms, rot_n = prof["rotate"]
     rot_ms_avg = rot_ms / max(rot_n, 1)
     # rotation kernel: one complex GEMM per pair of the rank's slab
@@ -394,9 +441,11 @@ def main():
     roof = {"bound": "tensor", "kernel": "rotate_dmma_kernel" if tensor else "zgemm_kernel (CUDA-core FP64)",
             "achieved": rot_flops / (rot_ms_avg * 1e-3) / 1e12, "peak": peak_tf, "unit": "TFLOP/s",
             "frac": rot_flops / (rot_ms_avg * 1e-3) / 1e12 / peak_tf,
-            # DRAM read+write bytes per launch from the committed ncu --set full capture of this exact
-            # workload at N = 1 (profiles/r1e_ncu_full_summary.json); not re-measured at run time
-            "traffic": 41.79e9 if (args.config == "cfg4_nw128" and world == 1 and tensor) else None,
+            # DRAM read+write bytes per launch of this kernel from the committed ncu --set full capture of
+            # this exact workload at N = 1 (not re-measured at run time: ncu cannot run inside a timed job)
+            "traffic": traffic.get("rotate") if (world == 1 and tensor) else None,
+            "traffic_source": traffic.get("source") if (world == 1 and tensor) else None,
+            "traffic_whole_evaluation": traffic.get("evaluation") if (world == 1 and tensor) else None,
             "peak_source": "FP64 %s peak measured live by wb200_probe_fp64_peak (MEASURED_PEAKS.json has "
                            "no FP64 figure; tcgen05 has no f64 kind)" % ("DMMA.8x8x4" if tensor else "DFMA"),
             "ms_per_launch": rot_ms_avg, "launches_timed": rot_n,
@@ -416,32 +465,17 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": dict(config, n_bvectors=nn, rotation_kernel=ctx.rotation_kernel,
-                           parallelism=f"k-slab x{world}", halo=halo, halo_k_per_rank=plan.n_halo, omega_check=omega_val),
+                           parallelism=f"k-slab x{world}", halo=halo, halo_k_per_rank=plan.n_halo, omega_check=omega_val,
+                           g_check=g_check),
             "e2e": e2e, "gpu_launches": int(launches), "clocks": cs.summary(), "roofline": roof}
 
-    if cpu_sample is not None:
-        from oracle import cpu_baseline as cbm
-        ks, Ms, Uh = cpu_sample
-        cores = os.cpu_count() or 1
-        run = lambda: cbm.fg_sample(Ms, st["kpb_k"][k0:k1][ks], st["bvec"][k0:k1][ks], st["wb"], Uh,
-                                    ks + k0, nk, threads=cores)
-        run()
-        ts = []
-        t_all = time.perf_counter()
-        while len(ts) < 3 or (time.perf_counter() - t_all < 12.0 and len(ts) < 20):
-            t0 = time.perf_counter()
-            run()
-            ts.append(time.perf_counter() - t0)
-        t = float(np.mean(ts))
-        line["cpu_baseline"] = {
-            "value": (len(ks) / nk) / t, "unit": "evals/s", "cores": cores, "kind": "port",
-            "sample": f"{len(ks)} of {nk} k-points ({len(ks) * nn} pairs; both ZGEMMs per pair as "
-                      f"spread.jl:173-174 plus the omega!/omega_grad! loops), {len(ts)} x {t:.3f} s, "
-                      f"numpy+OpenBLAS with {cores} threads over k; extrapolated to the full k-grid",
-            "one_thread": one_thread_figure(cbm, Ms, st["kpb_k"][k0:k1][ks], st["bvec"][k0:k1][ks], st["wb"], Uh,
-                                            ks + k0, nk)}
-    print(json.dumps(line), file=json_out, flush=True)
     ctx.close()
+    del ctx, dG
+    torch.cuda.empty_cache()
+    if not args.no_cpu_baseline and world == 1:
+        cb, _, _ = cpu_port_figure(w, st, nb, nw, 3, 1, dev, seconds_budget=25.0)
+        line["cpu_baseline"] = cb
+    print(json.dumps(line), file=json_out, flush=True)
     if world > 1:
         dist.destroy_process_group()
 

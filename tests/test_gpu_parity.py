@@ -175,8 +175,12 @@ def test_synthetic_xy_chain_and_disentangle(w, lat, grid, nb, nw, nfroz):
 def test_stiefel_project_and_retract(w, valence, silicon):
     ctx = make_ctx(w, fixture_stencil(valence), valence["M"], 4)
     rng = np.random.default_rng(7)
+    # shapes above 64 run on the plain-layout tensor GEMM (zgemm_dmma.cu): ragged m / n / k, one and
+    # several row / column tiles, both CTA shapes (m <= 64: 64 x 64 tiles; above: 128 x 32), A^H and beta = 1
     for (nrow, ncol, count) in ((4, 4, 64), (12, 8, 17), (128, 128, 3), (40, 24, 5), (32, 32, 9), (31, 17, 6),
-                               (9, 9, 5), (18, 9, 7), (1, 1, 3), (33, 32, 2)):
+                               (9, 9, 5), (18, 9, 7), (1, 1, 3), (33, 32, 2), (72, 40, 5), (100, 100, 7),
+                               (130, 70, 3), (257, 129, 2), (65, 65, 11), (200, 33, 4), (256, 256, 2),
+                               (96, 64, 301)):
         X = so.stiefel_retract(rng.standard_normal((count, nrow, ncol)) + 1j * rng.standard_normal((count, nrow, ncol)))
         G = rng.standard_normal(X.shape) + 1j * rng.standard_normal(X.shape)
         Gc = w.api.to_abi_U(G)

@@ -184,3 +184,30 @@ def test_optim_restatement_trajectory_goldens(valence, silicon):
     spc = so.omega_center(sp, ref["r0"], ref["lam"])
     assert abs(f - ref["Omegat"]) < 1e-7 and abs(spc["Omegac"] - ref["Omegac"]) < 1e-7
     assert np.abs(spc["omegac"] - ref["omegac"]).max() < 1e-7
+
+
+# ---- the compiled CPU port (oracle/spread_ref.cpp: the timed CPU baseline) against the same pins ----
+def test_compiled_port_matches_goldens_and_numpy_oracle(valence, silicon):
+    from oracle import cpu_ref as cr
+    assert "OpenBLAS" in cr.blas_name()        # the reference's mul! is OpenBLAS ZGEMM too
+    for d, U in ((valence, valence["U_ptg"]), (valence, valence["U"] @ valence["W1"]), (silicon, silicon["U"]),
+                 (silicon, silicon["U_chk"])):
+        args = (d["M"], d["kpb_k"], d["bvec"], d["wb"])
+        sp, G = cr.fg(*args, U, threads=3)
+        ref = so.omega(*args, U)
+        for key in ("Omega", "OmegaI", "OmegaOD", "OmegaD", "OmegaTilde"):
+            assert abs(sp[key] - ref[key]) < 1e-12 * max(1.0, abs(ref["Omega"]))
+        assert np.abs(sp["r"] - ref["r"]).max() < 1e-12 and np.abs(sp["omega"] - ref["omega"]).max() < 1e-12
+        _, G_ref = so.fg_maxloc(*args, U)
+        assert np.abs(G - G_ref).max() < 1e-12 * np.abs(G_ref).max()
+    # reference-held constants directly (test/localization/max_localize.jl:53; silicon.wout final state)
+    sp, _ = cr.fg(valence["M"], valence["kpb_k"], valence["bvec"], valence["wb"], valence["U_ptg"])
+    assert abs(sp["OmegaI"] - valence["ref_maxloc"][1]) < 1e-11
+    sp, _ = cr.fg(silicon["M"], silicon["kpb_k"], silicon["bvec"], silicon["wb"], silicon["U_chk"])
+    got = np.array([sp["Omega"], sp["OmegaI"], sp["OmegaOD"], sp["OmegaD"]])
+    assert np.allclose(got, silicon["wout_final"], rtol=3e-8, atol=0)
+    # centre penalty (spread.jl:227, 246-252)
+    r0 = np.zeros((4, 3))
+    sp, G = cr.fg(valence["M"], valence["kpb_k"], valence["bvec"], valence["wb"], valence["U"], r0=r0, lam=10.0)
+    f_ref, G_ref = so.fg_maxloc(valence["M"], valence["kpb_k"], valence["bvec"], valence["wb"], valence["U"], r0, 10.0)
+    assert abs(sp["f"] - f_ref) < 1e-11 and np.abs(G - G_ref).max() < 1e-12

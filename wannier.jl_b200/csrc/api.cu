@@ -20,7 +20,7 @@ extern "C" void wb200_destroy(wb200_ctx* ctx) {
     void* ptrs[] = {(void*)ctx->d_peerU, ctx->d_need_owner, ctx->d_need, ctx->d_kpb, ctx->d_kself, ctx->d_bvec, ctx->d_wb, ctx->d_M, ctx->d_r0,
                     ctx->d_frozen, ctx->d_nfrozen, ctx->d_U, ctx->d_G, ctx->d_MU, ctx->d_N,
                     ctx->d_dN, ctx->d_fro, ctx->d_part, ctx->d_pmin, ctx->d_sums, ctx->d_res,
-                    ctx->d_min, ctx->d_scal, ctx->d_red, ctx->d_tmp1, ctx->d_tmp2, ctx->d_XY, ctx->d_GXY};
+                    ctx->d_min, ctx->d_scal, ctx->d_red, ctx->d_zpart, ctx->d_tmp1, ctx->d_tmp2, ctx->d_XY, ctx->d_GXY};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     for (auto& v : ctx->prof_events)
@@ -76,6 +76,7 @@ extern "C" int wb200_create(wb200_ctx** out, int device, int nb, int nw, int nk_
 
     ctx = new wb200_ctx();
     ctx->device = device;
+    ctx->num_sms = prop.multiProcessorCount;
     ctx->nb = nb; ctx->nw = nw; ctx->nk_total = nk_total; ctx->k_begin = k_begin; ctx->nk = nk;
     ctx->nn = nn; ctx->flags = flags;
     CREATE_CUDA(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));

@@ -70,6 +70,7 @@ struct DmmaPlan;  // rotate_dmma.cu
 
 struct wb200_ctx {
     int device = 0;
+    int num_sms = 148;
     int nb = 0, nw = 0, nk_total = 0, k_begin = 0, nk = 0, nn = 0;
     unsigned flags = 0;
     cudaStream_t own_stream = nullptr;
@@ -127,6 +128,7 @@ struct wb200_ctx {
     double* d_min = nullptr;    // [1]
     double* d_scal = nullptr;   // [2048] scratch scalars (errors, flags)
     double* d_red = nullptr;    // block partials + results of the fused inner-product kernel (lazy)
+    double* d_zpart = nullptr; size_t zpart_elems = 0;   // per-warp norm partials of the tensor GEMM epilogues (lazy)
     double* h_pinned = nullptr; // pinned host scratch (nres + 64 doubles)
     // generic scratch for stiefel / xy (lazy, sized on demand)
     cplx* d_tmp1 = nullptr; size_t tmp1_elems = 0;
@@ -250,6 +252,18 @@ int wb_rotate_dmma(wb200_ctx* ctx, const cplx* dU, int ka, int kb);   // MU, dN,
 
 bool wb_zgemm_dmma_applicable(const wb200_ctx* ctx, int nrow, int ncol);
 int wb_zgemm_dmma(wb200_ctx* ctx, int transA, const cplx* A, const cplx* B, cplx* C, int count);   // C = op(A) B, n x n
+
+// ---- zgemm_dmma.cu: batched complex GEMM on the FP64 tensor pipe from plain column-major operands ----
+bool wb_zgemm_tensor_applicable(int m, int n, int k);
+long long wb_zgemm_tensor_items(int m, int n, int batch);
+// epi 0: C = alpha op(A) op(B) + beta C;  1: also per-warp ||AB||_F^2 partials into part;
+// 2: C = 1.5 I - 0.5 AB and per-warp ||AB - I||_F^2 partials (Newton-Schulz step matrix)
+int wb_zgemm_tensor(wb200_ctx* ctx, const ZgemmArgs& a, int epi, double* part);
+int wb_zgemm_tensor_err(wb200_ctx* ctx, int m, int n, int batch, const double* part, double* derr);
+int wb_zgemm_tensor_fro(wb200_ctx* ctx, int m, int n, int batch, const double* part, double* dfro);
+int wb_ensure_zpart(wb200_ctx* ctx, size_t elems);
+// tensor pipe where the shape allows it (and WB200_FLAG_NO_TENSOR is not set), CUDA cores otherwise
+int wb_zgemm(wb200_ctx* ctx, const ZgemmArgs& a);
 
 // ---- optimizer.cu ----
 int wb_lbfgs(wb200_ctx* ctx, int mode /*0 maxloc, 1 disentangle*/, cplx* dx, double f_tol,

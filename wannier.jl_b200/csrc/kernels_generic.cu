@@ -167,6 +167,21 @@ __global__ void __launch_bounds__(256) fro_kernel(int len, const cplx* __restric
     }
 }
 
+int wb_ensure_zpart(wb200_ctx* ctx, size_t elems) {
+    if (elems <= ctx->zpart_elems) return WB200_OK;
+    if (ctx->d_zpart) cudaFree(ctx->d_zpart);
+    ctx->d_zpart = nullptr; ctx->zpart_elems = 0;
+    WB_CUDA(ctx, cudaMalloc(&ctx->d_zpart, sizeof(double) * elems));
+    ctx->zpart_elems = elems;
+    return WB200_OK;
+}
+
+int wb_zgemm(wb200_ctx* ctx, const ZgemmArgs& a) {
+    if (!(ctx->flags & WB200_FLAG_NO_TENSOR) && !(a.transA && a.transB) && wb_zgemm_tensor_applicable(a.m, a.n, a.k))
+        return wb_zgemm_tensor(ctx, a, 0, nullptr);
+    return wb_zgemm_batched(ctx, a);
+}
+
 int wb_rotate_generic(wb200_ctx* ctx, const cplx* dU, int ka, int kb) {
     const int nb = ctx->nb, nw = ctx->nw;
     const long long p0 = (long long)ka * ctx->nn;
@@ -179,7 +194,7 @@ int wb_rotate_generic(wb200_ctx* ctx, const cplx* dU, int ka, int kb) {
     a.alpha = 1.0; a.beta = 0.0; a.batch = pairs; a.transA = 0; a.transB = 0;
     ProfScope ps(ctx, 1);
     ctx->fro_src = nullptr;
-    WB_TRY(wb_zgemm_batched(ctx, a));
+    WB_TRY(wb_zgemm(ctx, a));     // nb > 256 lands here: tensor pipe from the plain layout of M
     diag_kernel<<<pairs, 256, 0, ctx->stream>>>(nb, nw, dU, ctx->d_kself + p0, ctx->d_MU + p0 * nb * nw,
                                                  ctx->d_dN + p0 * nw, ctx->d_fro + p0);
     WB_LAUNCH_CHECK(ctx);
@@ -203,8 +218,14 @@ int wb_form_N(wb200_ctx* ctx, const cplx* dU) {
     a.B = ctx->d_MU; a.strideB = (long long)nb * nw; a.ldb = nb; a.idxB = nullptr; a.transB = 0;
     a.C = ctx->d_N; a.strideC = (long long)nw * nw; a.ldc = nw;
     a.alpha = 1.0; a.beta = 0.0; a.batch = pairs;
-    WB_TRY(wb_zgemm_batched(ctx, a));
     ctx->fro_src = nullptr;   // from here on ||N||_F^2 of the exact N
+    if (!(ctx->flags & WB200_FLAG_NO_TENSOR) && wb_zgemm_tensor_applicable(a.m, a.n, a.k)) {
+        // tensor pipe, ||N||_F^2 from the accumulators (per-warp partials summed in fixed order)
+        WB_TRY(wb_ensure_zpart(ctx, (size_t)wb_zgemm_tensor_items(a.m, a.n, pairs) * 8));
+        WB_TRY(wb_zgemm_tensor(ctx, a, 1, ctx->d_zpart));
+        return wb_zgemm_tensor_fro(ctx, a.m, a.n, pairs, ctx->d_zpart, ctx->d_fro);
+    }
+    WB_TRY(wb_zgemm_batched(ctx, a));
     fro_kernel<<<pairs, 256, 0, ctx->stream>>>(nw * nw, ctx->d_N, ctx->d_fro);
     WB_LAUNCH_CHECK(ctx);
     return WB200_OK;

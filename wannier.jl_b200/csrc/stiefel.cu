@@ -33,23 +33,16 @@ __global__ void hermitize_kernel(int n, long long total, cplx* __restrict__ S) {
 static int project_strided(wb200_ctx* ctx, const cplx* dX, cplx* dG, int nrow, int ncol, int ld,
                            long long stride, int count) {
     if (wb_small_applicable(nrow, ncol)) return wb_project_small(ctx, dX, dG, nrow, ncol, ld, stride, count);
-    const bool tensor = wb_zgemm_dmma_applicable(ctx, nrow, ncol) && ld == nrow && stride == (long long)nrow * ncol;
-    WB_TRY(wb_ensure_tmp(ctx, (size_t)count * ncol * ncol, tensor ? (size_t)count * nrow * ncol : 0));
-    if (tensor) {   // S = X^H G, S <- sym(S), G <- G - X S  with both GEMMs on the tensor pipe
-        WB_TRY(wb_zgemm_dmma(ctx, 1, dX, dG, ctx->d_tmp1, count));
-        const long long tot = (long long)count * ncol * ncol;
-        hermitize_kernel<<<(int)((tot + 255) / 256 < 4096 ? (tot + 255) / 256 : 4096), 256, 0, ctx->stream>>>(ncol, tot, ctx->d_tmp1);
-        WB_LAUNCH_CHECK(ctx);
-        WB_TRY(wb_zgemm_dmma(ctx, 0, dX, ctx->d_tmp1, ctx->d_tmp2, count));
-        return wb_axpby(ctx, -1.0, (const double*)ctx->d_tmp2, 1.0, (double*)dG, 2 * (size_t)count * nrow * ncol);
-    }
+    // S = X^H G, S <- (S + S^H)/2, G <- G - X S: two batched GEMMs (FP64 tensor pipe from the plain
+    // layouts where the shape allows, the second one accumulating into G) and one small pass over S
+    WB_TRY(wb_ensure_tmp(ctx, (size_t)count * ncol * ncol, 0));
     ZgemmArgs a{};
     a.m = ncol; a.n = ncol; a.k = nrow;
     a.A = dX; a.strideA = stride; a.lda = ld; a.transA = 1;
     a.B = dG; a.strideB = stride; a.ldb = ld; a.transB = 0;
     a.C = ctx->d_tmp1; a.strideC = (long long)ncol * ncol; a.ldc = ncol;
     a.alpha = 1.0; a.beta = 0.0; a.batch = count;
-    WB_TRY(wb_zgemm_batched(ctx, a));
+    WB_TRY(wb_zgemm(ctx, a));
     const long long total = (long long)count * ncol * ncol;
     const int blocks = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
     hermitize_kernel<<<blocks, 256, 0, ctx->stream>>>(ncol, total, ctx->d_tmp1);
@@ -60,7 +53,7 @@ static int project_strided(wb200_ctx* ctx, const cplx* dX, cplx* dG, int nrow, i
     b.B = ctx->d_tmp1; b.strideB = (long long)ncol * ncol; b.ldb = ncol; b.transB = 0;
     b.C = dG; b.strideC = stride; b.ldc = ld;
     b.alpha = -1.0; b.beta = 1.0; b.batch = count;
-    WB_TRY(wb_zgemm_batched(ctx, b));
+    WB_TRY(wb_zgemm(ctx, b));
     return WB200_OK;
 }
 
@@ -132,71 +125,68 @@ static int retract_strided(wb200_ctx* ctx, cplx* dX, int nrow, int ncol, int ld,
     const int MAXIT = 100;
     const double TOL = 2e-8;  // quadratic convergence: the update applied at err<2e-8 leaves ~1e-15
     WB_TRY(wb_ensure_tmp(ctx, (size_t)count * ncol * ncol, (size_t)count * nrow * ncol));
+    const bool tensor = !(ctx->flags & WB200_FLAG_NO_TENSOR) && wb_zgemm_tensor_applicable(ncol, ncol, nrow);
+    if (tensor) WB_TRY(wb_ensure_zpart(ctx, (size_t)wb_zgemm_tensor_items(ncol, ncol, count) * 8));
+    // X ping-pongs between the caller's array and tmp2 (dense), so an iteration is two GEMMs with no
+    // copy back.  Tensor path: the P = X^H X GEMM writes the step matrix T = 1.5 I - 0.5 P straight from
+    // its accumulators together with ||P - I||_F^2 partials (no separate pass over P).
+    struct Mat { cplx* p; int ld; long long stride; };
+    Mat cur{dX, ld, stride}, other{ctx->d_tmp2, nrow, (long long)nrow * ncol};
     int it = 0;
     double err = 0.0;
-    const bool tensor = wb_zgemm_dmma_applicable(ctx, nrow, ncol) && ld == nrow && stride == (long long)nrow * ncol;
-    if (tensor) {
-        // both GEMMs on the tensor pipe; X ping-pongs between the caller's array and tmp2, so an
-        // iteration is two GEMMs and the error pass, with no copy back
-        cplx *cur = dX, *other = ctx->d_tmp2;
-        for (; it < MAXIT; it++) {
-            WB_TRY(wb_zgemm_dmma(ctx, 1, cur, cur, ctx->d_tmp1, count));   // P = X^H X
-            WB_CUDA(ctx, cudaMemsetAsync(ctx->d_scal, 0, sizeof(double), ctx->stream));
-            ns_prepare_kernel<<<count, 256, 0, ctx->stream>>>(ncol, ctx->d_tmp1, ctx->d_scal, it == 0);
-            WB_LAUNCH_CHECK(ctx);
-            WB_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, ctx->d_scal, sizeof(double),
-                                         cudaMemcpyDeviceToHost, ctx->stream));
-            WB_TRY(wb_zgemm_dmma(ctx, 0, cur, ctx->d_tmp1, other, count));   // X T
-            std::swap(cur, other);
-            WB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-            err = ctx->h_pinned[0];
-            if (!(err == err)) {
-                ctx->err = "retract: NaN in X^H X";
-                return WB200_ERR_NOCONV;
-            }
-            if (err < TOL) { it++; break; }
-        }
-        if (cur != dX)
-            WB_CUDA(ctx, cudaMemcpyAsync(dX, cur, sizeof(cplx) * (size_t)count * nrow * ncol,
-                                         cudaMemcpyDeviceToDevice, ctx->stream));
-    } else
     for (; it < MAXIT; it++) {
         ZgemmArgs a{};
         a.m = ncol; a.n = ncol; a.k = nrow;
-        a.A = dX; a.strideA = stride; a.lda = ld; a.transA = 1;
-        a.B = dX; a.strideB = stride; a.ldb = ld; a.transB = 0;
+        a.A = cur.p; a.strideA = cur.stride; a.lda = cur.ld; a.transA = 1;
+        a.B = cur.p; a.strideB = cur.stride; a.ldb = cur.ld; a.transB = 0;
         a.C = ctx->d_tmp1; a.strideC = (long long)ncol * ncol; a.ldc = ncol;
         a.alpha = 1.0; a.beta = 0.0; a.batch = count;
-        WB_TRY(wb_zgemm_batched(ctx, a));   // P = X^H X
-        WB_CUDA(ctx, cudaMemsetAsync(ctx->d_scal, 0, sizeof(double), ctx->stream));
-        ns_prepare_kernel<<<count, 256, 0, ctx->stream>>>(ncol, ctx->d_tmp1, ctx->d_scal, it == 0);
-        WB_LAUNCH_CHECK(ctx);
-        WB_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, ctx->d_scal, sizeof(double),
-                                     cudaMemcpyDeviceToHost, ctx->stream));
         ZgemmArgs b{};
         b.m = nrow; b.n = ncol; b.k = ncol;
-        b.A = dX; b.strideA = stride; b.lda = ld; b.transA = 0;
+        b.A = cur.p; b.strideA = cur.stride; b.lda = cur.ld; b.transA = 0;
         b.B = ctx->d_tmp1; b.strideB = (long long)ncol * ncol; b.ldb = ncol; b.transB = 0;
-        b.C = ctx->d_tmp2; b.strideC = (long long)nrow * ncol; b.ldc = nrow;
+        b.C = other.p; b.strideC = other.stride; b.ldc = other.ld;
         b.alpha = 1.0; b.beta = 0.0; b.batch = count;
-        WB_TRY(wb_zgemm_batched(ctx, b));   // X T
-        const long long total = (long long)count * nrow * ncol;
-        if (ld == nrow && stride == (long long)nrow * ncol) {
-            WB_CUDA(ctx, cudaMemcpyAsync(dX, ctx->d_tmp2, sizeof(cplx) * total,
-                                         cudaMemcpyDeviceToDevice, ctx->stream));
+        WB_CUDA(ctx, cudaMemsetAsync(ctx->d_scal, 0, sizeof(double), ctx->stream));
+        bool fused = tensor;
+        if (fused) {
+            WB_TRY(wb_zgemm_tensor(ctx, a, 2, ctx->d_zpart));   // T and the error partials
+            WB_TRY(wb_zgemm_tensor_err(ctx, ncol, ncol, count, ctx->d_zpart, ctx->d_scal));
         } else {
-            const int blocks = (int)((total + 255) / 256 < 8192 ? (total + 255) / 256 : 8192);
-            copy_strided_kernel<<<blocks, 256, 0, ctx->stream>>>(nrow, ncol, ld, stride, total,
-                                                                 ctx->d_tmp2, dX);
+            WB_TRY(wb_zgemm(ctx, a));   // P = X^H X
+            ns_prepare_kernel<<<count, 256, 0, ctx->stream>>>(ncol, ctx->d_tmp1, ctx->d_scal, it == 0);
             WB_LAUNCH_CHECK(ctx);
         }
+        WB_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, ctx->d_scal, sizeof(double), cudaMemcpyDeviceToHost,
+                                     ctx->stream));
+        WB_TRY(wb_zgemm(ctx, b));   // X T (enqueued before the host knows err: no bubble in the common case)
         WB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         err = ctx->h_pinned[0];
         if (!(err == err)) {
             ctx->err = "retract: NaN in X^H X";
             return WB200_ERR_NOCONV;
         }
+        if (fused && it == 0 && err >= 1.9) {
+            // far from unitary (first pass only, e.g. projections before Lowdin): Newton-Schulz needs
+            // sigma^2 < 3, so redo the step with the scaled matrix s (1.5 I - 0.5 s^2 P), s = ||P||_F^(-1/2)
+            WB_TRY(wb_zgemm(ctx, a));
+            WB_CUDA(ctx, cudaMemsetAsync(ctx->d_scal, 0, sizeof(double), ctx->stream));
+            ns_prepare_kernel<<<count, 256, 0, ctx->stream>>>(ncol, ctx->d_tmp1, ctx->d_scal, 1);
+            WB_LAUNCH_CHECK(ctx);
+            WB_TRY(wb_zgemm(ctx, b));
+        }
+        std::swap(cur, other);
         if (err < TOL) { it++; break; }
+    }
+    if (cur.p != dX) {
+        const long long total = (long long)count * nrow * ncol;
+        if (ld == nrow && stride == (long long)nrow * ncol) {
+            WB_CUDA(ctx, cudaMemcpyAsync(dX, cur.p, sizeof(cplx) * total, cudaMemcpyDeviceToDevice, ctx->stream));
+        } else {
+            const int blocks = (int)((total + 255) / 256 < 8192 ? (total + 255) / 256 : 8192);
+            copy_strided_kernel<<<blocks, 256, 0, ctx->stream>>>(nrow, ncol, ld, stride, total, cur.p, dX);
+            WB_LAUNCH_CHECK(ctx);
+        }
     }
     if (iters_out) *iters_out = it;
     if (err >= TOL) {
@@ -321,7 +311,7 @@ int wb_xy_to_u(wb200_ctx* ctx, const cplx* dXY, cplx* dU) {
     a.B = dXY; a.strideB = st; a.ldb = nw; a.transB = 0;                        // X_k
     a.C = dU; a.strideC = (long long)nb * nw; a.ldc = nb;
     a.alpha = 1.0; a.beta = 0.0; a.batch = ctx->nk;
-    return wb_zgemm_batched(ctx, a);
+    return wb_zgemm(ctx, a);
 }
 
 // zero G_Y[frozen rows, :] and G_Y[:, 0:n_frozen)   (disentangle.jl:495-496)
@@ -353,14 +343,14 @@ int wb_gu_to_gxy(wb200_ctx* ctx, const cplx* dXY, const cplx* dGU, cplx* dGXY) {
     a.B = dGU; a.strideB = (long long)nb * nw; a.ldb = nb; a.transB = 0;
     a.C = dGXY; a.strideC = st; a.ldc = nw;
     a.alpha = 1.0; a.beta = 0.0; a.batch = ctx->nk;
-    WB_TRY(wb_zgemm_batched(ctx, a));
+    WB_TRY(wb_zgemm(ctx, a));
     ZgemmArgs b{};  // G_Y = G_U X^H
     b.m = nb; b.n = nw; b.k = nw;
     b.A = dGU; b.strideA = (long long)nb * nw; b.lda = nb; b.transA = 0;
     b.B = dXY; b.strideB = st; b.ldb = nw; b.transB = 1;
     b.C = dGXY + (long long)nw * nw; b.strideC = st; b.ldc = nb;
     b.alpha = 1.0; b.beta = 0.0; b.batch = ctx->nk;
-    WB_TRY(wb_zgemm_batched(ctx, b));
+    WB_TRY(wb_zgemm(ctx, b));
     if (ctx->d_frozen) {
         mask_gy_kernel<<<ctx->nk, 256, 0, ctx->stream>>>(nb, nw, st, ctx->d_frozen, ctx->d_nfrozen,
                                                           dGXY);
