@@ -96,7 +96,9 @@ int wb200_set_frozen(wb200_ctx* ctx, const uint8_t* frozen);
  *                 (either may be NULL).
  * wb200_fg_xy   = fg!(Omega, G, XY) of get_fg!_disentangle (disentangle.jl:586-614); XY and G_XY
  *                 are (nw*nw + nb*nw) x nk column-major, column ik = [vec(X_k); vec(Y_k)].
- *                 Single-slab ctx only (k_begin = 0, nk = nk_total).                            */
+ * A single-slab ctx (k_begin = 0, nk = nk_total) takes the whole model's arrays.  A k-slab ctx of a
+ * sharded run (wb200_set_allreduce + wb200_set_peer_gauges) takes the SLAB's rows of U / XY / G in
+ * wb200_fg, wb200_spread, wb200_center and wb200_fg_xy; every rank calls collectively.          */
 int wb200_fg(wb200_ctx* ctx, const double* U, double* f, double* G);
 int wb200_spread(wb200_ctx* ctx, const double* U, double out5[5], double* omega_n, double* r,
                  double* min_abs_Nnn);
@@ -190,7 +192,7 @@ int wb200_set_peer_gauges(wb200_ctx* ctx, int world, const void* const* U_ptrs, 
 /* ---- sharded optimiser: caller-supplied collective ------------------------------------------------
  * With one process per GPU the library does not own a communicator.  The host registers a callback
  * that all-reduces `count` doubles at device pointer `dptr` IN PLACE over all ranks, enqueued on
- * `cuda_stream` (op 0 = sum, 1 = max) — ncclAllReduce from Julia/C, torch.distributed from Python.
+ * `cuda_stream` (op 0 = sum, 1 = max, 2 = min) — ncclAllReduce from Julia/C, torch.distributed from Python.
  * With the callback and wb200_set_peer_gauges in place, wb200_max_localize and wb200_disentangle run
  * on a k-slab ctx: U_inout / XY is then the SLAB ([nk][nw][nb] / [nk][nw*nw + nb*nw]; frozen bands
  * per slab); every rank calls them collectively with the same arguments.
@@ -202,6 +204,38 @@ int wb200_set_peer_gauges(wb200_ctx* ctx, int world, const void* const* U_ptrs, 
  * that evaluation's reduced sums into NaN, i.e. the trial point is rejected on every rank.       */
 typedef int (*wb200_allreduce_fn)(void* dptr, int count, int op, void* cuda_stream, void* user);
 int wb200_set_allreduce(wb200_ctx* ctx, wb200_allreduce_fn fn, void* user);
+
+/* ---- one call, several GPUs (devices[], ndev) -----------------------------------------------
+ * The reference's callers are single calls from one process: max_localize(model)
+ * (src/localization/max_localize.jl:44-101), disentangle(model) (disentangle.jl:631-728), omega(model)
+ * (src/spread.jl:370-381), fg!(F, G, U) (max_localize.jl:13-23).  A wb200_multi shards the k-points in
+ * contiguous slabs over `devices` (one slab context per entry; a device may be listed more than once),
+ * keeps one host thread per slab for the duration of a call, lets the pack kernels read neighbour gauges
+ * from the owning device through peer access (NVLink) and reduces the spread sums / optimiser scalars in
+ * rank order in pinned host memory (deterministic, identical on every slab).  All arrays are the FULL
+ * model's, host pointers, laid out as for the single-device calls; M is uploaded slab by slab.
+ * The same slab contexts can be driven one process per GPU: wb200_fg / wb200_spread / wb200_center /
+ * wb200_fg_xy / wb200_max_localize / wb200_disentangle accept a k-slab ctx once wb200_set_allreduce and
+ * wb200_set_peer_gauges are in place (arrays are then the SLAB's rows and every rank calls collectively). */
+typedef struct wb200_multi wb200_multi;
+int wb200_multi_create(wb200_multi** out, const int* devices, int ndev, int nb, int nw, int nk, int nn,
+                       const int32_t* kpb_k, const double* bvec_cart, const double* bweights,
+                       const double* M, unsigned flags);
+void wb200_multi_destroy(wb200_multi* m);
+const char* wb200_multi_last_error(const wb200_multi* m);   /* m may be NULL: last create error */
+int wb200_multi_ndev(const wb200_multi* m);
+int wb200_multi_slab_begin(const wb200_multi* m, int r);   /* first k of slab r (r = ndev: nk) */
+long long wb200_multi_launch_count(const wb200_multi* m);
+int wb200_multi_set_penalty(wb200_multi* m, const double* r0, double lambda);
+int wb200_multi_set_frozen(wb200_multi* m, const uint8_t* frozen /*[nk][nb]*/);
+int wb200_multi_fg(wb200_multi* m, const double* U, double* f, double* G);
+int wb200_multi_spread(wb200_multi* m, const double* U, double out5[5], double* omega_n, double* r,
+                       double* min_abs_Nnn);
+int wb200_multi_fg_xy(wb200_multi* m, const double* XY, double* f, double* G_XY);
+int wb200_multi_max_localize(wb200_multi* m, double* U_inout, double f_tol, double g_tol, int max_iter,
+                             int history, double* f_final, int* iters, int* n_fg);
+int wb200_multi_disentangle(wb200_multi* m, double* XY_inout, double f_tol, double g_tol, int max_iter,
+                            int history, double* f_final, int* iters, int* n_fg);
 
 /* ---- measurement helpers (bench.py) -------------------------------------------------------------
  * wb200_profile: when enabled, every launch of the four kernel classes below is bracketed by CUDA

@@ -1,0 +1,98 @@
+"""The k-sharded code path on ONE GPU (-m gpu): several slab contexts on device 0 behind the single-call
+multi-device boundary (wb200_multi_*: one host thread per slab, neighbour gauges read through peer
+pointers, in-process all-reduce).  Everything the multi-process runs do — halo reads inside the pack
+kernel, the reduction of the spread sums, the k-sharded L-BFGS with its collectives — must reproduce
+the single-slab results, so the sharded optimiser is covered on a one-GPU box too.
+(tests/test_gpu_multi.py runs the same slabs one process per GPU over NCCL when >= 2 GPUs exist.)"""
+import numpy as np
+import pytest
+
+from oracle import spread_oracle as so
+import optim_goldens as og
+
+pytestmark = pytest.mark.gpu
+
+
+def _multi(w, st, M, nw, devices, **kw):
+    nk, nn, nb, _ = M.shape
+    return w.MultiContext(nb, nw, nk, nn, st["kpb_k"], st["bvec"], st["wb"], w.api.to_abi_M(M), devices=devices, **kw)
+
+
+@pytest.mark.parametrize("lat,grid,nb,nw,ndev", [
+    ("bcc", (4, 2, 2), 16, 16, 2),        # small ring / warp-pair rotation kernel
+    ("cubic", (3, 2, 2), 72, 40, 3),      # DMMA rotation kernel, rectangular U, ragged slabs (12 k over 3)
+    ("fcc", (4, 2, 2), 18, 9, 2),
+    ("bcc", (2, 2, 2), 128, 128, 2),      # north-star matrix size
+])
+def test_multislab_fg_and_spread_match_oracle(w, lat, grid, nb, nw, ndev):
+    st, M, U = w.synthetic.make_model_arrays(lat, grid, nb, nw)
+    nk = len(U)
+    m = _multi(w, st, M, nw, [0] * ndev)
+    assert m.bounds[0] == 0 and m.bounds[-1] == nk
+    G = np.empty((nk, nw, nb), dtype=np.complex128)
+    f = m.fg(w.api.to_abi_U(U), G=G)
+    f_ref, G_ref = so.fg_maxloc(M, st["kpb_k"], st["bvec"], st["wb"], U)
+    assert abs(f - f_ref) < 1e-10 * abs(f_ref)
+    assert np.abs(G.transpose(0, 2, 1) - G_ref).max() < 1e-10 * np.abs(G_ref).max()
+    out5, om, r, mn = m.spread(w.api.to_abi_U(U))
+    ref = so.omega(M, st["kpb_k"], st["bvec"], st["wb"], U)
+    for i, key in enumerate(["Omega", "OmegaI", "OmegaOD", "OmegaD", "OmegaTilde"]):
+        assert abs(out5[i] - ref[key]) < 1e-10 * max(1.0, abs(ref["Omega"])), key
+    assert np.abs(r - ref["r"]).max() < 1e-10 and np.abs(om - ref["omega"]).max() < 1e-10
+    _, N = so.compute_MU_UtMU(M, st["kpb_k"], U)
+    assert abs(mn - np.abs(np.diagonal(N, axis1=2, axis2=3)).min()) < 1e-12     # min over ALL slabs
+    m.close()
+
+
+def test_multislab_max_localize_reference_goldens(w, valence):
+    """max_localize(model) through the multi-device boundary: the reference's default-tolerance assertion
+    (test/localization/max_localize.jl:45-56) and its constrained max_iter = 4 golden, same iterations and
+    evaluations as the single-slab driver."""
+    st = w.KspaceStencil(valence["recip"], valence["kpoints"], valence["wb"], valence["kpb_k"], valence["kpb_G"])
+    model = w.Model(valence["lattice"], st, valence["M"], valence["U_ptg"])
+    U1, info1 = w.max_localize(model, return_info=True)
+    U2, info2 = w.max_localize(model, return_info=True, devices=[0, 0])
+    assert info1["iterations"] == info2["iterations"] and info1["n_fg"] == info2["n_fg"]
+    assert abs(info1["f"] - info2["f"]) < 1e-10 and np.abs(U1 - U2).max() < 1e-8
+    sp = w.omega(model, U2)
+    og.check_spread(dict(Omega=sp.Omega, OmegaI=sp.OmegaI, OmegaOD=sp.OmegaOD, OmegaTilde=sp.OmegaTilde), og.MAXLOC_DEFAULT)
+    ref = og.CC_MAXLOC_IT4
+    p = w.CenterSpreadPenalty(ref["r0"], ref["lam"])
+    U3, info3 = w.max_localize(p, model, max_iter=4, return_info=True, devices=[0, 0, 0])
+    spc = w.omega(p, model, U3)
+    assert abs(spc.Omega - ref["Omega"]) < 1e-7 and abs(spc.Omegat - ref["Omegat"]) < 1e-7
+    assert np.abs(spc.r - ref["r"]).max() < 1e-7
+
+
+def test_multislab_disentangle_reference_golden(w, silicon):
+    # test/localization/disentangle.jl:56-97 (max_iter = 4, trajectory dependent) on two and three slabs
+    st = w.KspaceStencil(silicon["recip"], silicon["kpoints"], silicon["wb"], silicon["kpb_k"], silicon["kpb_G"])
+    model = w.Model(silicon["lattice"], st, silicon["M"], silicon["U"], silicon["frozen"])
+    for devs in ([0, 0], [0, 0, 0]):
+        U, info = w.disentangle(model, max_iter=4, return_info=True, devices=devs)
+        assert info["iterations"] == 4
+        sp = w.omega(model, U)
+        og.check_spread(dict(Omega=sp.Omega, OmegaI=sp.OmegaI, OmegaOD=sp.OmegaOD, OmegaD=sp.OmegaD,
+                             OmegaTilde=sp.OmegaTilde, omega=sp.omega, r=sp.r), og.DISENTANGLE_IT4)
+
+
+def test_multislab_large_n_optimiser_matches_single_slab(w):
+    # the tensor-GEMM Stiefel path (n = 72) k-sharded: same trajectory as one slab
+    st, M, U = w.synthetic.make_model_arrays("cubic", (4, 2, 1), 72, 72, eps=0.02)
+    nk, nn = st["kpb_k"].shape
+    ctx = w.Context(72, 72, nk, nn, st["kpb_k"], st["bvec"], st["wb"], w.api.to_abi_M(M))
+    U1 = w.api.to_abi_U(U)
+    f1, it1, nfg1 = ctx.max_localize(U1, f_tol=1e-10, g_tol=1e-7, max_iter=5)
+    ctx.close()
+    m = _multi(w, st, M, 72, [0, 0])
+    U2 = w.api.to_abi_U(U)
+    f2, it2, nfg2 = m.max_localize(U2, f_tol=1e-10, g_tol=1e-7, max_iter=5)
+    m.close()
+    assert (it1, nfg1) == (it2, nfg2) and abs(f1 - f2) < 1e-9 * abs(f1)
+    assert np.abs(U1 - U2).max() < 1e-8
+
+
+def test_multi_create_errors(w, valence):
+    st = dict(kpb_k=valence["kpb_k"], bvec=valence["bvec"], wb=valence["wb"])
+    with pytest.raises(w.WB200Error):
+        _multi(w, st, valence["M"], 4, [0, 99])          # no such device

@@ -145,11 +145,18 @@ class Cache:
     """Cache(model) / Cache(stencil, M, U) (src/spread.jl:139-162): here it owns the device
     context — M resident in HBM, all work buffers — instead of host MU/UtMU arrays."""
 
-    def __init__(self, kstencil, M, n_wann, *, device=0, flags=_lib.FLAG_DEFAULT):
+    def __init__(self, kstencil, M, n_wann, *, device=0, devices=None, flags=_lib.FLAG_DEFAULT):
+        """devices = [d0, d1, ...]: shard the k-points over several GPUs behind the same calls
+        (omega, omega_grad, center, the fg closures, max_localize, disentangle)."""
         nk, nn, nb, _ = M.shape
         self.nb, self.nw, self.nk, self.nn = nb, n_wann, nk, nn
-        self.ctx = _lib.Context(nb, n_wann, nk, nn, kstencil.kpb_k, kstencil.bvectors_cart(),
-                                kstencil.bweights, to_abi_M(M), device=device, flags=flags)
+        if devices is not None and len(devices) > 1:
+            self.ctx = _lib.MultiContext(nb, n_wann, nk, nn, kstencil.kpb_k, kstencil.bvectors_cart(),
+                                         kstencil.bweights, to_abi_M(M), devices=devices, flags=flags)
+        else:
+            self.ctx = _lib.Context(nb, n_wann, nk, nn, kstencil.kpb_k, kstencil.bvectors_cart(),
+                                    kstencil.bweights, to_abi_M(M), device=devices[0] if devices else device,
+                                    flags=flags)
         self._penalty = None
 
     @classmethod
@@ -239,6 +246,8 @@ def center(*args, cache=None):
     """center(model[, U]) / center(stencil, M, U) -> r[nw, 3]   (src/spread.jl:560-564)"""
     p, cache, U, own = _with_cache(args, cache)
     try:
+        if not hasattr(cache.ctx, "center"):      # several GPUs: the centres come with the spread
+            return cache.ctx.spread(to_abi_U(U))[2]
         return cache.ctx.center(to_abi_U(U))
     finally:
         if own:
@@ -373,7 +382,7 @@ def get_fg_maxloc(p, model, cache=None):
 
 
 def max_localize(*args, f_tol=1e-7, g_tol=1e-5, max_iter=200, history_size=3, cache=None,
-                 return_info=False):
+                 return_info=False, devices=None):
     """max_localize([p,] model; f_tol, g_tol, max_iter, history_size) -> gauges U[k, m, n]
     (src/localization/max_localize.jl:44-101).  The whole optimiser loop is device-resident."""
     args = list(args)
@@ -384,7 +393,7 @@ def max_localize(*args, f_tol=1e-7, g_tol=1e-5, max_iter=200, history_size=3, ca
     if model.n_bands != model.n_wannier:
         raise ValueError("n_bands != n_wann, run instead disentanglement?")   # max_localize.jl:52-53
     own = cache is None
-    cache = cache or Cache.from_model(model)
+    cache = cache or Cache.from_model(model, devices=devices)
     cache.set_penalty(p)
     try:
         Uc = to_abi_U(model.gauges)
@@ -481,7 +490,7 @@ def get_fg_disentangle(p, model, cache=None):
 
 
 def disentangle(*args, f_tol=1e-7, g_tol=1e-5, max_iter=200, history_size=3, cache=None,
-                return_info=False):
+                return_info=False, devices=None):
     """disentangle([p,] model; ...) -> gauges U[k, m, n]   (disentangle.jl:631-728)"""
     args = list(args)
     p = SpreadPenalty()
@@ -491,7 +500,7 @@ def disentangle(*args, f_tol=1e-7, g_tol=1e-5, max_iter=200, history_size=3, cac
     if model.frozen_bands is None:
         raise ValueError("disentangle needs model.frozen_bands")
     own = cache is None
-    cache = cache or Cache.from_model(model)
+    cache = cache or Cache.from_model(model, devices=devices)
     cache.set_penalty(p)
     try:
         X0, Y0 = U_to_X_Y(model.gauges, model.frozen_bands)     # disentangle.jl:666

@@ -317,7 +317,8 @@ static int ensure_pipeline(wb200_ctx* ctx, const std::vector<int32_t>& kpb_host)
         std::vector<char> mark(S, 0);
         mark[i] = 1;
         for (long long p = (long long)ctx->sub_bounds[i] * ctx->nn; p < (long long)ctx->sub_bounds[i + 1] * ctx->nn; p++) {
-            const int k = kpb_host[p];
+            const int k = kpb_host[p] - ctx->k_begin;   // (dependencies are used by the single-slab upload pipeline only)
+            if (k < 0 || k >= nk) continue;
             int j = (int)((long long)k * S / nk);
             while (j > 0 && k < ctx->sub_bounds[j]) j--;
             while (j + 1 < S && k >= ctx->sub_bounds[j + 1]) j++;
@@ -336,6 +337,37 @@ static int ensure_pipeline(wb200_ctx* ctx, const std::vector<int32_t>& kpb_host)
     return WB200_OK;
 }
 
+static bool is_sharded(const wb200_ctx* ctx) { return ctx->allreduce && ctx->peer_self; }
+
+// Host-pointer evaluation on a k-slab ctx of a sharded run (all-reduce callback + peer gauges set; every
+// rank calls collectively): U_slab is THIS SLAB's [nk][nw][nb], results land in d_res (identical on
+// every rank) and, if wanted, the slab's gradient streams back sub-slab by sub-slab behind grad_kernel.
+static int sharded_eval_host(wb200_ctx* ctx, const cplx* U_slab_host, const cplx* U_slab_dev, int exact_split,
+                             cplx* G_slab_host) {
+    const size_t mat = (size_t)ctx->nb * ctx->nw;
+    cplx* rows = ctx->peer_self + (size_t)ctx->k_begin * mat;
+    if (U_slab_host)
+        WB_CUDA(ctx, cudaMemcpyAsync(rows, U_slab_host, sizeof(cplx) * mat * ctx->nk, cudaMemcpyHostToDevice, ctx->stream));
+    else if (U_slab_dev != rows)
+        WB_CUDA(ctx, cudaMemcpyAsync(rows, U_slab_dev, sizeof(cplx) * mat * ctx->nk, cudaMemcpyDeviceToDevice, ctx->stream));
+    WB_TRY(wb_fg_device(ctx, rows, ctx->d_res, nullptr, exact_split));   // ready, phase 1, reduced sums, spread
+    if (exact_split) WB_TRY(wb_allreduce(ctx, ctx->d_min, 1, 2));        // min |N_nn| over all slabs
+    if (G_slab_host) {
+        WB_TRY(ensure_pipeline(ctx, ctx->h_kpb));
+        const int S = (int)ctx->sub_bounds.size() - 1;
+        for (int i = 0; i < S; i++) {
+            const size_t off = (size_t)ctx->sub_bounds[i] * mat;
+            const size_t cnt = (size_t)(ctx->sub_bounds[i + 1] - ctx->sub_bounds[i]) * mat;
+            WB_TRY(wb_grad(ctx, ctx->d_sums, ctx->d_G, ctx->sub_bounds[i], ctx->sub_bounds[i + 1]));
+            WB_CUDA(ctx, cudaEventRecord(ctx->ev_grad[i], ctx->stream));
+            WB_CUDA(ctx, cudaStreamWaitEvent(ctx->d2h_stream, ctx->ev_grad[i], 0));
+            WB_CUDA(ctx, cudaMemcpyAsync(G_slab_host + off, ctx->d_G + off, sizeof(cplx) * cnt, cudaMemcpyDeviceToHost,
+                                         ctx->d2h_stream));
+        }
+    }
+    return WB200_OK;
+}
+
 // fg!(F, G, U) with host pointers.  The PCIe copies are pipelined against the compute:
 // U is uploaded sub-slab by sub-slab in the order the rotation needs it (a sub-slab starts as soon
 // as the sub-slabs holding its neighbours k+b have landed), and G goes back sub-slab by sub-slab
@@ -343,6 +375,14 @@ static int ensure_pipeline(wb200_ctx* ctx, const std::vector<int32_t>& kpb_host)
 extern "C" int wb200_fg(wb200_ctx* ctx, const double* U, double* f, double* G) {
     if (!ctx || !U) return WB200_ERR_ARG;
     cudaSetDevice(ctx->device);
+    if (is_sharded(ctx)) {   // k-slab of a sharded run: U and G are the slab's rows
+        WB_TRY(sharded_eval_host(ctx, (const cplx*)U, nullptr, 0, (cplx*)G));
+        WB_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, ctx->d_res, sizeof(double) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        WB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (G) WB_CUDA(ctx, cudaStreamSynchronize(ctx->d2h_stream));
+        if (f) *f = ctx->h_pinned[5];
+        return WB200_OK;
+    }
     WB_TRY(require_single_slab(ctx, "wb200_fg"));
     WB_TRY(ensure_pipeline(ctx, ctx->h_kpb));
     const int S = (int)ctx->sub_bounds.size() - 1;
@@ -401,9 +441,13 @@ extern "C" int wb200_spread(wb200_ctx* ctx, const double* U, double out5[5], dou
                             double* r, double* min_abs_Nnn) {
     if (!ctx || !U) return WB200_ERR_ARG;
     cudaSetDevice(ctx->device);
-    WB_TRY(require_single_slab(ctx, "wb200_spread"));
-    WB_TRY(upload_U(ctx, U));
-    WB_TRY(wb_fg_device(ctx, ctx->d_U, ctx->d_res, nullptr, 1));
+    if (is_sharded(ctx)) {
+        WB_TRY(sharded_eval_host(ctx, (const cplx*)U, nullptr, 1, nullptr));
+    } else {
+        WB_TRY(require_single_slab(ctx, "wb200_spread"));
+        WB_TRY(upload_U(ctx, U));
+        WB_TRY(wb_fg_device(ctx, ctx->d_U, ctx->d_res, nullptr, 1));
+    }
     WB_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, ctx->d_res, sizeof(double) * ctx->nres(),
                                  cudaMemcpyDeviceToHost, ctx->stream));
     WB_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned + ctx->nres(), ctx->d_min, sizeof(double),
@@ -420,9 +464,13 @@ extern "C" int wb200_spread(wb200_ctx* ctx, const double* U, double out5[5], dou
 extern "C" int wb200_center(wb200_ctx* ctx, const double* U, double* r) {
     if (!ctx || !U || !r) return WB200_ERR_ARG;
     cudaSetDevice(ctx->device);
-    WB_TRY(require_single_slab(ctx, "wb200_center"));
-    WB_TRY(upload_U(ctx, U));
-    WB_TRY(wb_fg_device(ctx, ctx->d_U, ctx->d_res, nullptr, 0));
+    if (is_sharded(ctx)) {
+        WB_TRY(sharded_eval_host(ctx, (const cplx*)U, nullptr, 0, nullptr));
+    } else {
+        WB_TRY(require_single_slab(ctx, "wb200_center"));
+        WB_TRY(upload_U(ctx, U));
+        WB_TRY(wb_fg_device(ctx, ctx->d_U, ctx->d_res, nullptr, 0));
+    }
     WB_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, ctx->d_res, sizeof(double) * ctx->nres(),
                                  cudaMemcpyDeviceToHost, ctx->stream));
     WB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -459,12 +507,12 @@ static int ensure_xy(wb200_ctx* ctx) {
 extern "C" int wb200_fg_xy(wb200_ctx* ctx, const double* XY, double* f, double* G_XY) {
     if (!ctx || !XY) return WB200_ERR_ARG;
     cudaSetDevice(ctx->device);
-    WB_TRY(require_single_slab(ctx, "wb200_fg_xy"));
+    if (!is_sharded(ctx)) WB_TRY(require_single_slab(ctx, "wb200_fg_xy"));
     WB_TRY(ensure_xy(ctx));
     const size_t st = (size_t)ctx->nw * ctx->nw + (size_t)ctx->nb * ctx->nw;
     WB_CUDA(ctx, cudaMemcpyAsync(ctx->d_XY, XY, sizeof(cplx) * st * ctx->nk, cudaMemcpyHostToDevice,
                                  ctx->stream));
-    WB_TRY(wb_xy_to_u(ctx, ctx->d_XY, ctx->d_U));
+    WB_TRY(wb_xy_to_u(ctx, ctx->d_XY, ctx->d_U));      // the slab's nk gauges (d_U rows 0..nk)
     WB_TRY(wb_fg_device(ctx, ctx->d_U, ctx->d_res, G_XY ? ctx->d_G : nullptr, 0));
     if (G_XY) {
         WB_TRY(wb_gu_to_gxy(ctx, ctx->d_XY, ctx->d_G, ctx->d_GXY));

@@ -209,8 +209,10 @@ int wb_halo_fetch(wb200_ctx* ctx, cplx* dU);   // copy the remote rows of `need`
 
 // ---- stiefel.cu ----
 int wb_project_tangent_dev(wb200_ctx* ctx, const cplx* dX, cplx* dG, int nrow, int ncol, int count);
-int wb_retract_dev(wb200_ctx* ctx, cplx* dX, int nrow, int ncol, int count, int* iters);
-int wb_retract_xy(wb200_ctx* ctx, cplx* dXY);
+// tangent_step: X = X0 + a s with X0 on the manifold and s tangent at X0, hence X^H X = I + a^2 s^H s: every
+// singular value is >= 1, which the scaled Newton-Schulz iteration of the large-shape path exploits
+int wb_retract_dev(wb200_ctx* ctx, cplx* dX, int nrow, int ncol, int count, int* iters, bool tangent_step = false);
+int wb_retract_xy(wb200_ctx* ctx, cplx* dXY, bool tangent_step = false);
 int wb_project_xy(wb200_ctx* ctx, const cplx* dXY, cplx* dG);
 int wb_xy_to_u(wb200_ctx* ctx, const cplx* dXY, cplx* dU);
 int wb_gu_to_gxy(wb200_ctx* ctx, const cplx* dXY, const cplx* dGU, cplx* dGXY);
@@ -257,7 +259,8 @@ int wb_zgemm_dmma(wb200_ctx* ctx, int transA, const cplx* A, const cplx* B, cplx
 bool wb_zgemm_tensor_applicable(int m, int n, int k);
 long long wb_zgemm_tensor_items(int m, int n, int batch);
 // epi 0: C = alpha op(A) op(B) + beta C;  1: also per-warp ||AB||_F^2 partials into part;
-// 2: C = 1.5 I - 0.5 AB and per-warp ||AB - I||_F^2 partials (Newton-Schulz step matrix)
+// 2: C = alpha I - beta AB and per-warp ||AB - I||_F^2 partials (Newton-Schulz step matrix);
+// 3: C = AB and the same partials
 int wb_zgemm_tensor(wb200_ctx* ctx, const ZgemmArgs& a, int epi, double* part);
 int wb_zgemm_tensor_err(wb200_ctx* ctx, int m, int n, int batch, const double* part, double* derr);
 int wb_zgemm_tensor_fro(wb200_ctx* ctx, int m, int n, int batch, const double* part, double* dfro);

@@ -207,10 +207,11 @@ struct Problem {
     size_t n;     // doubles per vector
     int n_fg = 0;
 
-    int retract(cplx* x) {
-        if (mode == 2) return wb_retract_dev(ctx, x, ctx->nw, ctx->nw, 1, nullptr);
-        if (mode == 0) return wb_retract_dev(ctx, x, ctx->nb, ctx->nw, ctx->nk, nullptr);
-        return wb_retract_xy(ctx, x);
+    // tangent_step: x = x0 + a s with x0 on the manifold and s tangent at x0 (every trial point of a line search)
+    int retract(cplx* x, bool tangent_step = false) {
+        if (mode == 2) return wb_retract_dev(ctx, x, ctx->nw, ctx->nw, 1, nullptr, tangent_step);
+        if (mode == 0) return wb_retract_dev(ctx, x, ctx->nb, ctx->nw, ctx->nk, nullptr, tangent_step);
+        return wb_retract_xy(ctx, x, tangent_step);
     }
     int project(const cplx* x, cplx* g) {
         if (mode == 2) return wb_project_tangent_dev(ctx, x, g, ctx->nw, ctx->nw, 1);
@@ -394,7 +395,7 @@ int wb_lbfgs(wb200_ctx* ctx, int mode, cplx* dx, double f_tol, double g_tol, int
             WbLinArgs l{};
             l.v[0] = x; l.c[0] = 1.0; l.v[1] = s; l.c[1] = a; l.nv = 2;
             WB_TRY(wb_lincomb(ctx, l, xn, n));
-            int st = P.retract((cplx*)xn);
+            int st = P.retract((cplx*)xn, true);
             if (st == WB200_ERR_NOCONV) ctx->poison_next = 1;   // this trial point is rejected on every rank
             else WB_TRY(st);
             double fv = 0.0, dv = 0.0;

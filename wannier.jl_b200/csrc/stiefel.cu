@@ -116,8 +116,43 @@ __global__ void copy_strided_kernel(int nrow, int ncol, int ld, long long stride
     }
 }
 
+// T <- a I - b P in place for a batch of n x n matrices (first step of the scaled iteration)
+__global__ void __launch_bounds__(256) ns_scale_kernel(int n, long long total, double a, double b, cplx* __restrict__ P) {
+    const long long nn2 = (long long)n * n;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+         e += (long long)gridDim.x * blockDim.x) {
+        const int r = (int)(e % nn2);
+        const cplx v = P[e];
+        P[e] = make_double2(((r % n) == (r / n) ? a : 0.0) - b * v.x, -b * v.y);
+    }
+}
+
+// Newton-Schulz with the optimal scaling for a known singular-value interval [lo, hi]:
+//   X <- c X (3 I - c^2 X^H X) / 2,  c^2 = 3 / (lo^2 + lo hi + hi^2)  makes p(c lo) = p(c hi), the new lower
+//   bound, while the maximum of p(x) = x (3 - x^2) / 2, p(1) = 1, is the new upper bound.
+// Unscaled, a singular value s << 1 grows by 1.5 per iteration; scaled, the interval [lo, hi] collapses
+// like kappa -> ~sqrt(kappa).  The line search of the optimiser takes large trial steps in its first
+// iterations (Optim's alphaguess is 1), so this halves the GEMMs of those retractions.
+struct NsInterval {
+    double lo, hi;
+    double c() const { return sqrt(3.0 / (lo * lo + lo * hi + hi * hi)); }
+    static double p(double x) { return 0.5 * x * (3.0 - x * x); }
+    void tighten(double err) {   // rigorous: |lambda(X^H X) - 1| <= ||X^H X - I||_F
+        hi = fmin(hi, sqrt(1.0 + err));
+        if (err < 1.0) lo = fmax(lo, sqrt(1.0 - err));
+    }
+    void step(double cc) {
+        const double a = p(cc * lo), b = p(cc * hi);
+        const bool spans_one = cc * lo <= 1.0 && cc * hi >= 1.0;
+        lo = fmin(a, b);
+        hi = spans_one ? 1.0 : fmax(a, b);
+        lo = fmax(lo * (1.0 - 1e-12), 0.0);   // guard the analytic bounds against rounding
+        hi = hi * (1.0 + 1e-12);
+    }
+};
+
 static int retract_strided(wb200_ctx* ctx, cplx* dX, int nrow, int ncol, int ld, long long stride,
-                           int count, int* iters_out) {
+                           int count, int* iters_out, bool tangent_step) {
     if (wb_small_applicable(nrow, ncol)) {   // fused single-launch kernel, convergence tested on the device
         if (iters_out) *iters_out = -1;
         return wb_retract_small(ctx, dX, nrow, ncol, ld, stride, count);
@@ -128,12 +163,16 @@ static int retract_strided(wb200_ctx* ctx, cplx* dX, int nrow, int ncol, int ld,
     const bool tensor = !(ctx->flags & WB200_FLAG_NO_TENSOR) && wb_zgemm_tensor_applicable(ncol, ncol, nrow);
     if (tensor) WB_TRY(wb_ensure_zpart(ctx, (size_t)wb_zgemm_tensor_items(ncol, ncol, count) * 8));
     // X ping-pongs between the caller's array and tmp2 (dense), so an iteration is two GEMMs with no
-    // copy back.  Tensor path: the P = X^H X GEMM writes the step matrix T = 1.5 I - 0.5 P straight from
+    // copy back.  Tensor path: the P = X^H X GEMM writes the step matrix T = a I - b P straight from
     // its accumulators together with ||P - I||_F^2 partials (no separate pass over P).
     struct Mat { cplx* p; int ld; long long stride; };
     Mat cur{dX, ld, stride}, other{ctx->d_tmp2, nrow, (long long)nrow * ncol};
+    const long long ptotal = (long long)count * ncol * ncol;
+    const int pblocks = (int)((ptotal + 255) / 256 < 4096 ? (ptotal + 255) / 256 : 4096);
     int it = 0;
     double err = 0.0;
+    NsInterval iv{0.0, 0.0};
+    bool scaled = false;      // interval known: scaled iteration
     for (; it < MAXIT; it++) {
         ZgemmArgs a{};
         a.m = ncol; a.n = ncol; a.k = nrow;
@@ -148,32 +187,56 @@ static int retract_strided(wb200_ctx* ctx, cplx* dX, int nrow, int ncol, int ld,
         b.C = other.p; b.strideC = other.stride; b.ldc = other.ld;
         b.alpha = 1.0; b.beta = 0.0; b.batch = count;
         WB_CUDA(ctx, cudaMemsetAsync(ctx->d_scal, 0, sizeof(double), ctx->stream));
-        bool fused = tensor;
-        if (fused) {
-            WB_TRY(wb_zgemm_tensor(ctx, a, 2, ctx->d_zpart));   // T and the error partials
-            WB_TRY(wb_zgemm_tensor_err(ctx, ncol, ncol, count, ctx->d_zpart, ctx->d_scal));
-        } else {
+        if (!tensor) {
             WB_TRY(wb_zgemm(ctx, a));   // P = X^H X
             ns_prepare_kernel<<<count, 256, 0, ctx->stream>>>(ncol, ctx->d_tmp1, ctx->d_scal, it == 0);
             WB_LAUNCH_CHECK(ctx);
+            WB_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, ctx->d_scal, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+            WB_TRY(wb_zgemm(ctx, b));   // X T
+            WB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            err = ctx->h_pinned[0];
+        } else if (it == 0) {
+            // first pass: P itself and its distance from I; the host then knows the singular-value interval
+            WB_TRY(wb_zgemm_tensor(ctx, a, 3, ctx->d_zpart));
+            WB_TRY(wb_zgemm_tensor_err(ctx, ncol, ncol, count, ctx->d_zpart, ctx->d_scal));
+            WB_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, ctx->d_scal, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+            WB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            err = ctx->h_pinned[0];
+            if (err == err) {
+                if (tangent_step || err < 0.75) {
+                    iv.hi = sqrt(1.0 + err);
+                    iv.lo = tangent_step ? fmax(1.0 - 1e-9, err < 1.0 ? sqrt(1.0 - err) : 0.0) : sqrt(1.0 - err);
+                    scaled = true;
+                    const double cc = iv.c();
+                    ns_scale_kernel<<<pblocks, 256, 0, ctx->stream>>>(ncol, ptotal, 1.5 * cc, 0.5 * cc * cc * cc, ctx->d_tmp1);
+                    WB_LAUNCH_CHECK(ctx);
+                    iv.step(cc);
+                } else {
+                    // nothing known about the small singular values: Frobenius scaling, then the plain iteration
+                    WB_CUDA(ctx, cudaMemsetAsync(ctx->d_scal, 0, sizeof(double), ctx->stream));
+                    ns_prepare_kernel<<<count, 256, 0, ctx->stream>>>(ncol, ctx->d_tmp1, ctx->d_scal, 1);
+                    WB_LAUNCH_CHECK(ctx);
+                }
+                WB_TRY(wb_zgemm(ctx, b));
+            }
+        } else {
+            const double cc = scaled ? iv.c() : 1.0;
+            ZgemmArgs a2 = a;
+            a2.alpha = 1.5 * cc; a2.beta = 0.5 * cc * cc * cc;
+            WB_TRY(wb_zgemm_tensor(ctx, a2, 2, ctx->d_zpart));   // T = a I - b P and the error partials
+            WB_TRY(wb_zgemm_tensor_err(ctx, ncol, ncol, count, ctx->d_zpart, ctx->d_scal));
+            WB_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, ctx->d_scal, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+            WB_TRY(wb_zgemm(ctx, b));   // X T (enqueued before the host knows err: no bubble)
+            WB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            err = ctx->h_pinned[0];
+            if (scaled && err == err) {   // err belongs to the P of THIS iteration, i.e. to the interval before the step
+                iv.tighten(err);
+                iv.step(cc);
+            }
         }
-        WB_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, ctx->d_scal, sizeof(double), cudaMemcpyDeviceToHost,
-                                     ctx->stream));
-        WB_TRY(wb_zgemm(ctx, b));   // X T (enqueued before the host knows err: no bubble in the common case)
-        WB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        err = ctx->h_pinned[0];
         if (!(err == err)) {
             ctx->err = "retract: NaN in X^H X";
             return WB200_ERR_NOCONV;
-        }
-        if (fused && it == 0 && err >= 1.9) {
-            // far from unitary (first pass only, e.g. projections before Lowdin): Newton-Schulz needs
-            // sigma^2 < 3, so redo the step with the scaled matrix s (1.5 I - 0.5 s^2 P), s = ||P||_F^(-1/2)
-            WB_TRY(wb_zgemm(ctx, a));
-            WB_CUDA(ctx, cudaMemsetAsync(ctx->d_scal, 0, sizeof(double), ctx->stream));
-            ns_prepare_kernel<<<count, 256, 0, ctx->stream>>>(ncol, ctx->d_tmp1, ctx->d_scal, 1);
-            WB_LAUNCH_CHECK(ctx);
-            WB_TRY(wb_zgemm(ctx, b));
         }
         std::swap(cur, other);
         if (err < TOL) { it++; break; }
@@ -197,16 +260,16 @@ static int retract_strided(wb200_ctx* ctx, cplx* dX, int nrow, int ncol, int ld,
     return WB200_OK;
 }
 
-int wb_retract_dev(wb200_ctx* ctx, cplx* dX, int nrow, int ncol, int count, int* iters) {
-    return retract_strided(ctx, dX, nrow, ncol, nrow, (long long)nrow * ncol, count, iters);
+int wb_retract_dev(wb200_ctx* ctx, cplx* dX, int nrow, int ncol, int count, int* iters, bool tangent_step) {
+    return retract_strided(ctx, dX, nrow, ncol, nrow, (long long)nrow * ncol, count, iters, tangent_step);
 }
 
 // manifold ops on the packed XY array (product manifold per k)
-int wb_retract_xy(wb200_ctx* ctx, cplx* dXY) {
+int wb_retract_xy(wb200_ctx* ctx, cplx* dXY, bool tangent_step) {
     const int nb = ctx->nb, nw = ctx->nw;
     const long long st = (long long)nw * nw + (long long)nb * nw;
-    WB_TRY(retract_strided(ctx, dXY, nw, nw, nw, st, ctx->nk, nullptr));
-    WB_TRY(retract_strided(ctx, dXY + (long long)nw * nw, nb, nw, nb, st, ctx->nk, nullptr));
+    WB_TRY(retract_strided(ctx, dXY, nw, nw, nw, st, ctx->nk, nullptr, tangent_step));
+    WB_TRY(retract_strided(ctx, dXY + (long long)nw * nw, nb, nw, nb, st, ctx->nk, nullptr, tangent_step));
     return WB200_OK;
 }
 int wb_project_xy(wb200_ctx* ctx, const cplx* dXY, cplx* dG) {

@@ -61,6 +61,13 @@ __device__ __forceinline__ void zd_bulk_g2s(uint32_t dst, const void* src, uint3
         "l"(src), "r"(bytes), "r"(bar)
         : "memory");
 }
+// 16-byte LDGSTS with zero fill (src_bytes = 0 writes zeros) and its completion on an mbarrier
+__device__ __forceinline__ void zd_cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void zd_cp_async_arrive(uint32_t bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void zd_dmma(double& c0, double& c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                  : "+d"(c0), "+d"(c1)
@@ -75,8 +82,9 @@ struct ZdArgs {
     double alpha, beta;
     int tiles_m, tiles_n;
     long long items;      // batch * tiles_m * tiles_n
-    int epi;              // 0: C = alpha AB + beta C;  1: + per-warp ||AB||_F^2 partials;  2: C = 1.5 I - 0.5 AB
-                          //    and per-warp ||AB - I||_F^2 partials (Newton-Schulz step matrix)
+    int epi;              // 0: C = alpha AB + beta C;  1: + per-warp ||AB||_F^2 partials;
+                          // 2: C = alpha I - beta AB and per-warp ||AB - I||_F^2 partials (Newton-Schulz step
+                          //    matrix, plain: alpha = 1.5, beta = 0.5);  3: C = AB and the same partials
     double* part;         // epi 1, 2: [items][8]
 };
 
@@ -106,7 +114,7 @@ __global__ void __launch_bounds__(384, 1) zgemm_dmma_kernel(ZdArgs a) {
 
     if (tid == 256) {
         for (int s = 0; s < STAGES; s++) {
-            zd_mbar_init(bar_base + 8u * s, 1);
+            zd_mbar_init(bar_base + 8u * s, TA ? 129 : 1);   // bulk-copy thread (+ 128 LDGSTS threads for A^H)
             zd_mbar_init(bar_base + 8u * (STAGES + s), 8);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -118,9 +126,15 @@ __global__ void __launch_bounds__(384, 1) zgemm_dmma_kernel(ZdArgs a) {
     const int nch = (a.k + KC - 1) / KC;
 
     if (warp >= 8) {
-        // ===== producer warpgroup: its registers go to the consumers; warp 8 drives the ring =====
+        // ===== producer warpgroup: its registers go to the consumers.  Warp 8 issues the bulk copies of the
+        // operands whose contiguous runs are long (whole tile columns).  The rows of an A^H tile are only
+        // KC elements long (256 B): a bulk copy costs the TMA unit ~50 cycles whatever its size, so 128 of
+        // them per stage starve the tensor pipe (measured: 4.1 ms against 1.9 ms for the same flops).  Those
+        // tiles are loaded by all four producer warps with 16-byte LDGSTS (zero filled beyond m / k),
+        // completion counted on the same mbarrier. =====
         asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-        if (warp != 8) return;
+        if (!TA && warp != 8) return;
+        const int ptid = tid - 256;
         const uint32_t sA_base = zd_smem_u32(sA), sB_base = zd_smem_u32(sB);
         uint32_t u = 0;
         for (long long item = i0; item < i1; item++) {
@@ -137,22 +151,31 @@ __global__ void __launch_bounds__(384, 1) zgemm_dmma_kernel(ZdArgs a) {
                 const int k0 = c * KC, kv = min(KC, a.k - k0);
                 const uint32_t full = bar_base + 8u * s;
                 zd_mbar_wait(bar_base + 8u * (STAGES + s), (round & 1u) ^ 1u);
-                if (lane == 0) zd_mbar_expect_tx(full, (uint32_t)((rows + cols) * kv * 16));
-                __syncwarp();
                 const uint32_t dA = sA_base + (uint32_t)s * (Cfg::A_ELEMS * 16), dB = sB_base + (uint32_t)s * (Cfg::B_ELEMS * 16);
-                if (!TA) {
-                    for (int l = lane; l < kv; l += 32)
-                        zd_bulk_g2s(dA + (uint32_t)l * (LDA * 16), Ab + (long long)(k0 + l) * a.lda + m0, (uint32_t)rows * 16, full);
-                } else {
-                    for (int i = lane; i < rows; i += 32)
-                        zd_bulk_g2s(dA + (uint32_t)i * (LDA * 16), Ab + (long long)(m0 + i) * a.lda + k0, (uint32_t)kv * 16, full);
+                if (warp == 8) {
+                    if (lane == 0) zd_mbar_expect_tx(full, (uint32_t)(((TA ? 0 : rows) + cols) * kv * 16));
+                    __syncwarp();
+                    if (!TA) {
+                        for (int l = lane; l < kv; l += 32)
+                            zd_bulk_g2s(dA + (uint32_t)l * (LDA * 16), Ab + (long long)(k0 + l) * a.lda + m0, (uint32_t)rows * 16, full);
+                    }
+                    if (!TB) {
+                        for (int j = lane; j < cols; j += 32)
+                            zd_bulk_g2s(dB + (uint32_t)j * (LDB * 16), Bb + (long long)(n0 + j) * a.ldb + k0, (uint32_t)kv * 16, full);
+                    } else {
+                        for (int l = lane; l < kv; l += 32)
+                            zd_bulk_g2s(dB + (uint32_t)l * (LDB * 16), Bb + (long long)(k0 + l) * a.ldb + n0, (uint32_t)cols * 16, full);
+                    }
                 }
-                if (!TB) {
-                    for (int j = lane; j < cols; j += 32)
-                        zd_bulk_g2s(dB + (uint32_t)j * (LDB * 16), Bb + (long long)(n0 + j) * a.ldb + k0, (uint32_t)kv * 16, full);
-                } else {
-                    for (int l = lane; l < kv; l += 32)
-                        zd_bulk_g2s(dB + (uint32_t)l * (LDB * 16), Bb + (long long)(k0 + l) * a.ldb + n0, (uint32_t)cols * 16, full);
+                if (TA) {
+#pragma unroll 4
+                    for (int e = ptid; e < BM * KC; e += 128) {
+                        const int i = e / KC, l = e % KC;
+                        const bool ok = i < rows && l < kv;
+                        zd_cp_async16(dA + (uint32_t)(i * LDA + l) * 16, ok ? Ab + (long long)(m0 + i) * a.lda + k0 + l : Ab,
+                                      ok ? 16u : 0u);
+                    }
+                    zd_cp_async_arrive(full);
                 }
             }
         }
@@ -248,11 +271,11 @@ __global__ void __launch_bounds__(384, 1) zgemm_dmma_kernel(ZdArgs a) {
                     if (mi >= a.m || ni >= a.n) continue;
                     const cplx x = make_double2(p1[mt][nt][j] - p3[mt][nt][j], p1[mt][nt][j] + p2[mt][nt][j]);
                     cplx* dst = Cb + mi + (long long)ni * a.ldc;
-                    if (a.epi == 2) {
+                    if (a.epi >= 2) {
                         const double dg = mi == ni ? 1.0 : 0.0;
                         const double dx = x.x - dg;
                         f = fma(dx, dx, fma(x.y, x.y, f));
-                        *dst = make_double2(1.5 * dg - 0.5 * x.x, -0.5 * x.y);
+                        *dst = a.epi == 3 ? x : make_double2(a.alpha * dg - a.beta * x.x, -a.beta * x.y);
                     } else {
                         cplx v = make_double2(a.alpha * x.x, a.alpha * x.y);
                         if (a.beta != 0.0) {

@@ -26,6 +26,10 @@ SYMBOLS = [
     "wb200_omega_local", "wb200_fg_rotate", "wb200_opt_rotate", "wb200_position_op", "wb200_berry_connection",
     "wb200_set_allreduce",
     "wb200_ipc_alloc", "wb200_ipc_open", "wb200_ipc_close", "wb200_ipc_free", "wb200_set_peer_gauges",
+    "wb200_multi_create", "wb200_multi_destroy", "wb200_multi_last_error", "wb200_multi_ndev",
+    "wb200_multi_slab_begin", "wb200_multi_launch_count", "wb200_multi_set_penalty", "wb200_multi_set_frozen",
+    "wb200_multi_fg", "wb200_multi_spread", "wb200_multi_fg_xy", "wb200_multi_max_localize",
+    "wb200_multi_disentangle",
 ]
 
 FLAG_DEFAULT = 0
@@ -99,12 +103,29 @@ def load():
     lib.wb200_ipc_close.argtypes = [i32, vp]
     lib.wb200_ipc_free.argtypes = [i32, vp]
     lib.wb200_set_peer_gauges.argtypes = [vp, i32, pd, pd]
+    lib.wb200_multi_create.argtypes = [C.POINTER(vp), pd, i32, i32, i32, i32, i32, pd, pd, pd, pd, C.c_uint]
+    lib.wb200_multi_destroy.argtypes = [vp]
+    lib.wb200_multi_destroy.restype = None
+    lib.wb200_multi_last_error.argtypes = [vp]
+    lib.wb200_multi_last_error.restype = C.c_char_p
+    lib.wb200_multi_ndev.argtypes = [vp]
+    lib.wb200_multi_slab_begin.argtypes = [vp, i32]
+    lib.wb200_multi_launch_count.argtypes = [vp]
+    lib.wb200_multi_launch_count.restype = C.c_longlong
+    lib.wb200_multi_set_penalty.argtypes = [vp, pd, dbl]
+    lib.wb200_multi_set_frozen.argtypes = [vp, pd]
+    lib.wb200_multi_fg.argtypes = [vp, pd, pd, pd]
+    lib.wb200_multi_spread.argtypes = [vp, pd, pd, pd, pd, pd]
+    lib.wb200_multi_fg_xy.argtypes = [vp, pd, pd, pd]
+    lib.wb200_multi_max_localize.argtypes = [vp, pd, dbl, dbl, i32, i32, pd, pd, pd]
+    lib.wb200_multi_disentangle.argtypes = [vp, pd, dbl, dbl, i32, i32, pd, pd, pd]
     lib.wb200_profile.argtypes = [vp, i32]
     lib.wb200_profile_read.argtypes = [vp, pd, pd]
     lib.wb200_probe_fp64_peak.argtypes = [i32, pd, pd]
     for name in SYMBOLS:
         f = getattr(lib, name)
-        if name not in ("wb200_destroy", "wb200_last_error", "wb200_version", "wb200_launch_count"):
+        if name not in ("wb200_destroy", "wb200_last_error", "wb200_version", "wb200_launch_count",
+                        "wb200_multi_destroy", "wb200_multi_last_error", "wb200_multi_launch_count"):
             f.restype = i32
     _lib = lib
     return lib
@@ -378,6 +399,108 @@ class Context:
         it = C.c_int(0)
         self._ck(self._lib.wb200_retract_dev(self._h, dX, nrow, ncol, count, C.addressof(it)))
         return it.value
+
+
+class MultiContext:
+    """One call, several GPUs (wb200_multi_*): the k-points are sharded in contiguous slabs over `devices`
+    (a device may be listed more than once).  Same array conventions and method names as Context; all
+    arrays are the full model's."""
+
+    def __init__(self, nb, nw, nk, nn, kpb_k, bvec, bweights, M, *, devices, flags=FLAG_DEFAULT):
+        self._h = None
+        lib = load()
+        kpb_k = np.ascontiguousarray(kpb_k, dtype=np.int32)
+        bvec = np.ascontiguousarray(bvec, dtype=np.float64)
+        bweights = np.ascontiguousarray(bweights, dtype=np.float64)
+        _check_array(kpb_k, np.int32, nk * nn, "kpb_k")
+        _check_array(bvec, np.float64, nk * nn * 3, "bvec")
+        _check_array(bweights, np.float64, nn, "bweights")
+        _check_array(M, np.complex128, nk * nn * nb * nb, "M")
+        dv = np.ascontiguousarray(devices, dtype=np.int32)
+        self.nb, self.nw, self.nk, self.nk_total, self.nn = nb, nw, nk, nk, nn
+        self.devices = [int(d) for d in dv]
+        h = C.c_void_p()
+        st = lib.wb200_multi_create(C.byref(h), _addr(dv), len(dv), nb, nw, nk, nn, _addr(kpb_k), _addr(bvec),
+                                    _addr(bweights), _addr(M), flags)
+        if st != 0:
+            raise WB200Error(st, lib.wb200_multi_last_error(None).decode())
+        self._h = h
+        self._lib = lib
+
+    def close(self):
+        if self._h is not None:
+            self._lib.wb200_multi_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, st):
+        if st != 0:
+            raise WB200Error(st, self._lib.wb200_multi_last_error(self._h).decode())
+
+    @property
+    def launch_count(self):
+        return int(self._lib.wb200_multi_launch_count(self._h))
+
+    @property
+    def bounds(self):
+        return [self._lib.wb200_multi_slab_begin(self._h, r) for r in range(len(self.devices) + 1)]
+
+    def set_penalty(self, r0, lam):
+        if r0 is None:
+            self._ck(self._lib.wb200_multi_set_penalty(self._h, None, 0.0))
+            return
+        r0 = np.ascontiguousarray(r0, dtype=np.float64)
+        _check_array(r0, np.float64, 3 * self.nw, "r0")
+        self._ck(self._lib.wb200_multi_set_penalty(self._h, _addr(r0), float(lam)))
+
+    def set_frozen(self, frozen):
+        fr = None if frozen is None else np.ascontiguousarray(frozen, dtype=np.uint8)
+        if fr is not None:
+            _check_array(fr, np.uint8, self.nk * self.nb, "frozen")
+        self._ck(self._lib.wb200_multi_set_frozen(self._h, _addr(fr)))
+
+    def fg(self, U, want_f=True, G=None):
+        _check_array(U, np.complex128, self.nk * self.nb * self.nw, "U")
+        if G is not None:
+            _check_array(G, np.complex128, self.nk * self.nb * self.nw, "G")
+        f = C.c_double(0.0)
+        self._ck(self._lib.wb200_multi_fg(self._h, _addr(U), C.addressof(f) if want_f else None, _addr(G)))
+        return f.value if want_f else None
+
+    def spread(self, U):
+        _check_array(U, np.complex128, self.nk * self.nb * self.nw, "U")
+        out5, om, r, mn = np.zeros(5), np.zeros(self.nw), np.zeros((self.nw, 3)), C.c_double(0.0)
+        self._ck(self._lib.wb200_multi_spread(self._h, _addr(U), _addr(out5), _addr(om), _addr(r), C.addressof(mn)))
+        return out5, om, r, mn.value
+
+    def fg_xy(self, XY, want_f=True, G=None):
+        n = self.nk * (self.nw * self.nw + self.nb * self.nw)
+        _check_array(XY, np.complex128, n, "XY")
+        if G is not None:
+            _check_array(G, np.complex128, n, "G_XY")
+        f = C.c_double(0.0)
+        self._ck(self._lib.wb200_multi_fg_xy(self._h, _addr(XY), C.addressof(f) if want_f else None, _addr(G)))
+        return f.value if want_f else None
+
+    def max_localize(self, U, f_tol=1e-7, g_tol=1e-5, max_iter=200, history=3):
+        _check_array(U, np.complex128, self.nk * self.nb * self.nw, "U")
+        f, it, nfg = C.c_double(0.0), C.c_int(0), C.c_int(0)
+        self._ck(self._lib.wb200_multi_max_localize(self._h, _addr(U), f_tol, g_tol, max_iter, history,
+                                                    C.addressof(f), C.addressof(it), C.addressof(nfg)))
+        return f.value, it.value, nfg.value
+
+    def disentangle(self, XY, f_tol=1e-7, g_tol=1e-5, max_iter=200, history=3):
+        n = self.nk * (self.nw * self.nw + self.nb * self.nw)
+        _check_array(XY, np.complex128, n, "XY")
+        f, it, nfg = C.c_double(0.0), C.c_int(0), C.c_int(0)
+        self._ck(self._lib.wb200_multi_disentangle(self._h, _addr(XY), f_tol, g_tol, max_iter, history,
+                                                   C.addressof(f), C.addressof(it), C.addressof(nfg)))
+        return f.value, it.value, nfg.value
 
 
 def probe_fp64_peak(device=0):

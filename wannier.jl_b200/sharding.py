@@ -109,6 +109,6 @@ def torch_allreduce(dist, device):
 
     def fn(dptr, count, op, stream):
         t = torch.as_tensor(DeviceArray(dptr, (count,), "<f8"), device=device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX if op == 1 else dist.ReduceOp.SUM)
+        dist.all_reduce(t, op=(dist.ReduceOp.SUM, dist.ReduceOp.MAX, dist.ReduceOp.MIN)[op])
 
     return fn
