@@ -88,6 +88,27 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def bind_to_gpu_numa_node(index):
+    """N > 1: pin this process (and so the pages of its pinned staging buffers, first touch) to the CPUs
+    next to its GPU; eight processes streaming through one socket's memory halve each other's PCIe rate."""
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(index)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        txt = open(f"/sys/bus/pci/devices/{bdf}/local_cpulist").read().strip()
+        cpus = set()
+        for part in txt.split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return txt
+    except Exception:
+        pass
+    return None
+
+
 def work_per_eval(nb, nw, nk, nn):
     pairs = nk * nn
     flops = 8.0 * pairs * nb * nb * nw + 8.0 * pairs * nb * nw      # one GEMM + diag/scale (SURVEY 8d)
@@ -251,7 +272,9 @@ def main():
         raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = None
     if world > 1:
+        numa = bind_to_gpu_numa_node(local_rank)
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
@@ -378,14 +401,17 @@ def main():
         hres = torch.empty(ctx.nres, dtype=torch.float64).pin_memory()
         hUn, hGn = hU.numpy(), hG.numpy()
 
+        if world > 1 and halo == "peer":
+            # the slab context itself takes host pointers: H2D of the slab's rows, "rows are in place"
+            # reduction, phase 1 with peer-memory halo reads, all-reduce of the sums, phase 2 with the
+            # gradient streamed back sub-slab by sub-slab behind grad_kernel (wb200_fg on a k-slab ctx)
+            ctx.set_allreduce(w.sharding.torch_allreduce(dist, dev))
+
         def step_e2e():
-            if world == 1:
+            if world == 1 or halo == "peer":
                 return ctx.fg(hUn, want_f=True, G=hGn)        # wb200_fg: H2D U, compute, D2H f and G
             dU[k0:k1].copy_(hU, non_blocking=True)            # own slab host -> device
-            if halo == "peer":
-                dist.all_reduce(ready)                        # rows of every rank are in place
-            else:
-                plan.exchange(dU, dist)                       # neighbour gauges over NVLink
+            plan.exchange(dU, dist)                           # neighbour gauges over NVLink
             ctx.fg_phase1_dev(dU.data_ptr(), dsums.data_ptr())
             dist.all_reduce(dsums)
             ctx.fg_phase2_dev(dsums.data_ptr(), dres.data_ptr(), dG.data_ptr())
@@ -407,9 +433,13 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = t.item()
         e2e = {"value": 1.0 / dt, "unit": "evals/s", "h2d_bytes_per_step": int(16 * nk * nb * nw),
-               "d2h_bytes_per_step": int(16 * nk * nb * nw + 8 * world), "steps": n_e2e,
+               "d2h_bytes_per_step": int(16 * nk * nb * nw + 8 * world), "steps": n_e2e, "cpu_affinity": numa,
                "check_f": f_e2e, "api": "wb200_fg (host pointers, pinned)" if world == 1 else
-               "per rank: H2D own U slab, halo exchange, phase1 / all-reduce / phase2, D2H own G slab"}
+               ("wb200_fg on each rank's k-slab ctx (host pointers of the slab, pinned): H2D rows, peer-memory halo, "
+                "all-reduce of the sums, gradient streamed back" if halo == "peer" else
+                "per rank: H2D own U slab, NCCL halo exchange, phase1 / all-reduce / phase2, D2H own G slab")}
+        if world > 1 and halo == "peer":
+            ctx.set_allreduce(None)
 
     if breakdown:
         torch.cuda.synchronize()

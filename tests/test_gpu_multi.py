@@ -49,10 +49,10 @@ def _worker(rank, world, port, case, out):
             ctx.set_frozen(frozen[k0:k1])
             X, Y = so.U_to_X_Y(U, frozen)
             Uslab = np.ascontiguousarray(so.X_Y_to_XY(X, Y)[k0:k1])
-            f, it, nfg = ctx.disentangle(Uslab, 1e-10, 1e-7, 25, 3)
+            f, it, nfg = ctx.disentangle(Uslab, 1e-10, 1e-7, 10, 3)
         else:
             Uslab = w.api.to_abi_U(U[k0:k1])
-            f, it, nfg = ctx.max_localize(Uslab, f_tol=1e-10, g_tol=1e-7, max_iter=40)
+            f, it, nfg = ctx.max_localize(Uslab, f_tol=1e-10, g_tol=1e-7, max_iter=10)
         torch.cuda.synchronize()
         dist.barrier()
         out[rank] = (f, it, nfg, Uslab.copy())
@@ -80,7 +80,7 @@ def test_sharded_max_localize_matches_single_gpu(w, case):
     nk, nn = st["kpb_k"].shape
     ctx = w.Context(nb, nb, nk, nn, st["kpb_k"], st["bvec"], st["wb"], w.api.to_abi_M(M))
     U1 = w.api.to_abi_U(U)
-    f1, it1, nfg1 = ctx.max_localize(U1, f_tol=1e-10, g_tol=1e-7, max_iter=40)
+    f1, it1, nfg1 = ctx.max_localize(U1, f_tol=1e-10, g_tol=1e-7, max_iter=10)
     ctx.close()
     mgr = mp.Manager()
     out = mgr.dict()
@@ -109,7 +109,7 @@ def test_sharded_disentangle_matches_single_gpu(w):
     ctx.set_frozen(frozen)
     X, Y = so.U_to_X_Y(U, frozen)
     XY1 = np.ascontiguousarray(so.X_Y_to_XY(X, Y))
-    f1, it1, nfg1 = ctx.disentangle(XY1, 1e-10, 1e-7, 25, 3)
+    f1, it1, nfg1 = ctx.disentangle(XY1, 1e-10, 1e-7, 10, 3)
     ctx.close()
     mgr = mp.Manager()
     out = mgr.dict()
@@ -122,3 +122,28 @@ def test_sharded_disentangle_matches_single_gpu(w):
     Xs, Ys = so.XY_to_X_Y(XYsh, nb, nw)
     f_check = so.omega(M, st["kpb_k"], st["bvec"], st["wb"], so.X_Y_to_U(Xs, Ys))["Omega"]
     assert abs(f_check - fa) < 1e-9 * abs(fa)
+
+
+def test_multi_device_context_two_gpus(w):
+    """wb200_multi_* with two DISTINCT devices in one process (peer access over NVLink, no IPC): fg, spread
+    and the k-sharded max_localize against the single-device results."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from oracle import spread_oracle as so
+    st, M, U = w.synthetic.make_model_arrays("cubic", (4, 2, 2), 72, 72, eps=0.02)
+    nk, nn = st["kpb_k"].shape
+    m = w.MultiContext(72, 72, nk, nn, st["kpb_k"], st["bvec"], st["wb"], w.api.to_abi_M(M), devices=[0, 1])
+    G = np.empty((nk, 72, 72), dtype=np.complex128)
+    f = m.fg(w.api.to_abi_U(U), G=G)
+    f_ref, G_ref = so.fg_maxloc(M, st["kpb_k"], st["bvec"], st["wb"], U)
+    assert abs(f - f_ref) < 1e-10 * abs(f_ref)
+    assert np.abs(G.transpose(0, 2, 1) - G_ref).max() < 1e-10 * np.abs(G_ref).max()
+    U2 = w.api.to_abi_U(U)
+    f2, it2, nfg2 = m.max_localize(U2, f_tol=1e-10, g_tol=1e-7, max_iter=5)
+    m.close()
+    ctx = w.Context(72, 72, nk, nn, st["kpb_k"], st["bvec"], st["wb"], w.api.to_abi_M(M))
+    U1 = w.api.to_abi_U(U)
+    f1, it1, nfg1 = ctx.max_localize(U1, f_tol=1e-10, g_tol=1e-7, max_iter=5)
+    ctx.close()
+    assert (it1, nfg1) == (it2, nfg2) and abs(f1 - f2) < 1e-9 * abs(f1) and np.abs(U1 - U2).max() < 1e-8

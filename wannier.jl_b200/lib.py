@@ -246,8 +246,10 @@ class Context:
         in place over the ranks on `stream`; None unregisters.  The ctypes thunk is kept alive here."""
         if fn is None:
             self._cb = None
+            self._sharded = False
             self._ck(self._lib.wb200_set_allreduce(self._h, None, None))
             return
+        self._sharded = True
         proto = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p)
 
         def thunk(dptr, count, op, stream, user):
@@ -275,7 +277,10 @@ class Context:
 
     # -- host entry points ------------------------------------------------------------------
     def _u(self, U):
-        _check_array(U, np.complex128, self.nk_total * self.nb * self.nw, "U")
+        # single-slab ctx: the whole model's gauges; k-slab ctx of a sharded run (set_allreduce +
+        # set_peer_gauges): the slab's rows
+        n = (self.nk if getattr(self, "_sharded", False) else self.nk_total) * self.nb * self.nw
+        _check_array(U, np.complex128, n, "U")
         return _addr(U)
 
     def fg(self, U, want_f=True, G=None):
