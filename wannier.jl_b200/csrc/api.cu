@@ -23,6 +23,7 @@ extern "C" void wb200_destroy(wb200_ctx* ctx) {
                     ctx->d_min, ctx->d_scal, ctx->d_red, ctx->d_zpart, ctx->d_tmp1, ctx->d_tmp2, ctx->d_XY, ctx->d_GXY};
     for (void* p : ptrs)
         if (p) cudaFree(p);
+    for (auto& g : ctx->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
     for (auto& v : ctx->prof_events)
         for (auto& pr : v) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
@@ -77,6 +78,7 @@ extern "C" int wb200_create(wb200_ctx** out, int device, int nb, int nw, int nk_
     ctx = new wb200_ctx();
     ctx->device = device;
     ctx->num_sms = prop.multiProcessorCount;
+    { const char* e = getenv("WB200_GRAPH"); ctx->use_graphs = !(e && e[0] == '0'); }
     ctx->nb = nb; ctx->nw = nw; ctx->nk_total = nk_total; ctx->k_begin = k_begin; ctx->nk = nk;
     ctx->nn = nn; ctx->flags = flags;
     CREATE_CUDA(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
@@ -259,6 +261,54 @@ int wb_fg_device(wb200_ctx* ctx, const cplx* dU, double* dres, cplx* dG, int exa
         WB_TRY(wb_allreduce(ctx, ctx->d_sums, ctx->nsums(), 0));
         WB_TRY(wb200_fg_phase2_dev(ctx, ctx->d_sums, dres, (double*)dG));
         return WB200_OK;
+    }
+    // single slab: the launches of an evaluation are replayed from a CUDA graph when the same
+    // (U, res, G) buffers come back (bench loops, the optimiser's trial buffers): one submission
+    // instead of ~9 launches, which is what a small problem's evaluation time consists of
+    const bool graphable = ctx->use_graphs && !ctx->profiling && !ctx->poison_next && ctx->stream != nullptr;
+    if (graphable) {
+        wb200_ctx::EvalGraph* slot = nullptr;
+        for (auto& g : ctx->graphs)
+            if (g.seen && g.dU == dU && g.dres == dres && g.dG == dG && g.exact_split == exact_split &&
+                g.has_penalty == ctx->has_penalty && g.lambda == ctx->lambda && g.frozen == ctx->d_frozen) { slot = &g; break; }
+        if (slot && slot->exec) {
+            WB_CUDA(ctx, cudaGraphLaunch(slot->exec, ctx->stream));
+            ctx->launches += slot->nlaunch;
+            slot->stamp = ++ctx->graph_clock;
+            return WB200_OK;
+        }
+        if (!slot) {   // first sighting of this key: run plainly (lazy allocations, function attributes), remember it
+            slot = &ctx->graphs[0];
+            for (auto& g : ctx->graphs) if (g.stamp < slot->stamp) slot = &g;
+            if (slot->exec) { cudaGraphExecDestroy(slot->exec); slot->exec = nullptr; }
+            *slot = wb200_ctx::EvalGraph{};
+            slot->dU = dU; slot->dres = dres; slot->dG = dG; slot->exact_split = exact_split;
+            slot->has_penalty = ctx->has_penalty; slot->lambda = ctx->lambda; slot->frozen = ctx->d_frozen;
+            slot->seen = 1; slot->stamp = ++ctx->graph_clock;
+        } else {       // second sighting: capture
+            cudaGraph_t graph = nullptr;
+            const long long l0 = ctx->launches;
+            WB_CUDA(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+            int s = wb200_fg_phase1_dev(ctx, (const double*)dU, ctx->d_sums, exact_split);
+            if (s == WB200_OK) s = wb200_fg_phase2_dev(ctx, ctx->d_sums, dres, (double*)dG);
+            const cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
+            if (s != WB200_OK || e != cudaSuccess || !graph) {
+                if (graph) cudaGraphDestroy(graph);
+                cudaGetLastError();
+                ctx->use_graphs = 0;      // something on this path cannot be captured: plain launches from now on
+                if (s != WB200_OK) return s;
+            } else {
+                const cudaError_t ei = cudaGraphInstantiate(&slot->exec, graph, 0);
+                cudaGraphDestroy(graph);
+                if (ei != cudaSuccess) { slot->exec = nullptr; cudaGetLastError(); ctx->use_graphs = 0; }
+                else {
+                    slot->nlaunch = ctx->launches - l0;
+                    slot->stamp = ++ctx->graph_clock;
+                    WB_CUDA(ctx, cudaGraphLaunch(slot->exec, ctx->stream));
+                    return WB200_OK;
+                }
+            }
+        }
     }
     WB_TRY(wb200_fg_phase1_dev(ctx, (const double*)dU, ctx->d_sums, exact_split));
     WB_TRY(poison_sums(ctx));

@@ -140,6 +140,19 @@ struct wb200_ctx {
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events[4];
     size_t prof_used[4] = {0, 0, 0, 0};
 
+    // CUDA graphs of one evaluation (single-slab ctx): the ~9 launches of a small problem cost more than
+    // its arithmetic; a graph replays them in one submission.  Keyed by everything the captured launches
+    // bake in; a few entries because the optimiser alternates between trial buffers.
+    struct EvalGraph {
+        const void* dU = nullptr; const void* dres = nullptr; const void* dG = nullptr;
+        int exact_split = 0, has_penalty = 0; double lambda = 0.0; const void* frozen = nullptr;
+        cudaGraphExec_t exec = nullptr; long long nlaunch = 0; unsigned long long stamp = 0; int seen = 0;
+    };
+    EvalGraph graphs[6];
+    unsigned long long graph_clock = 0;
+    int use_graphs = 1;        // WB200_GRAPH=0 disables
+    unsigned zd_attr_mask = 0; // zgemm_dmma.cu: shared-memory attribute set for these instantiations
+
     DmmaPlan* dmma = nullptr;  // tensor-path state (nullptr: CUDA-core rotation)
     int rotation_kernel = 0;
 

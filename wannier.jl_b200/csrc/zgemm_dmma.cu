@@ -316,7 +316,11 @@ template <int WM, int WN, bool TA, bool TB>
 int zd_launch(wb200_ctx* ctx, const ZdArgs& a) {
     using Cfg = ZdCfg<WM, WN, TA, TB>;
     auto kern = zgemm_dmma_kernel<WM, WN, TA, TB>;
-    WB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+    const unsigned bit = 1u << ((WM == 4 ? 0 : 3) + (TA ? 1 : (TB ? 2 : 0)));   // once per ctx and instantiation
+    if (!(ctx->zd_attr_mask & bit)) {
+        WB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+        ctx->zd_attr_mask |= bit;
+    }
     const long long grid = a.items < ctx->num_sms ? a.items : ctx->num_sms;
     kern<<<(unsigned)grid, 384, Cfg::SMEM, ctx->stream>>>(a);
     WB_LAUNCH_CHECK(ctx);
