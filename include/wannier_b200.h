@@ -237,6 +237,35 @@ int wb200_multi_max_localize(wb200_multi* m, double* U_inout, double f_tol, doub
 int wb200_multi_disentangle(wb200_multi* m, double* XY_inout, double f_tol, double g_tol, int max_iter,
                             int history, double* f_final, int* iters, int* n_fg);
 
+/* ---- MagModel co-optimisation (src/localization/coopt.jl) ---------------------------------------------
+ * Spin-up and spin-down models coupled by the overlap of up and down Wannier functions.  A wb200_mag
+ * borrows two single-slab contexts on the same device (the up and down `Model`s of `MagModel`,
+ * coopt.jl:8-17; equal n_bands, n_wann, n_kpts as `disentangle(::MagModel)` asserts, :355-357) and owns
+ * Mud = <u_nk^up | u_mk^dn>, [nk][nb*nb] complex column-major (host or device pointer).
+ *   wb200_mag_overlap         = overlap_updn(model, Uup, Udn) (coopt.jl:114-135): Mw2 [nw*nw] real column-major
+ *                               = |sum_k Uup_k^H Mud_k Udn_k|^2 / nk^2 (may be NULL), and omega_updn (:146-160)
+ *                               = n_wann - tr(Mw2) (may be NULL).  Uup, Udn [nk][nw][nb].
+ *   wb200_mag_omega_updn_grad = omega_updn_grad(model, Uup, Udn) (coopt.jl:222-229): GUup, GUdn [nk][nw][nb].
+ *   wb200_mag_fg_xy           = f / g! of get_fg!_disentangle(model::MagModel, lambda) (coopt.jl:252-321):
+ *                               XY and G are 2 (nw*nw + nb*nw) x nk column-major, column ik =
+ *                               [vec(Xup_k); vec(Yup_k); vec(Xdn_k); vec(Ydn_k)]; frozen bands from each context
+ *                               (wb200_set_frozen).  f, G, out4 may be NULL; out4 = {Omega_updn, Omega_t,
+ *                               Omega_up, Omega_dn} (the scalar fields of SpreadMag, coopt.jl:46-64).
+ *   wb200_mag_disentangle     = disentangle(model::MagModel, lambda; f_tol, g_tol, max_iter, history_size)
+ *                               (coopt.jl:339-420), device-resident like wb200_disentangle; XY_inout from
+ *                               U_to_X_Y of both spins (:369-374).
+ * omega(model::MagModel, Uup, Udn, lambda) (coopt.jl:66-73) is wb200_spread on each context plus
+ * wb200_mag_overlap.  wb200_mag_destroy leaves the two contexts alive.                             */
+typedef struct wb200_mag wb200_mag;
+int wb200_mag_create(wb200_mag** out, wb200_ctx* up, wb200_ctx* dn, const double* Mud);
+void wb200_mag_destroy(wb200_mag* m);
+const char* wb200_mag_last_error(const wb200_mag* m);   /* m may be NULL: last create error */
+int wb200_mag_overlap(wb200_mag* m, const double* Uup, const double* Udn, double* Mw2, double* omega_updn);
+int wb200_mag_omega_updn_grad(wb200_mag* m, const double* Uup, const double* Udn, double* GUup, double* GUdn);
+int wb200_mag_fg_xy(wb200_mag* m, const double* XY, double lambda, double* f, double* G, double out4[4]);
+int wb200_mag_disentangle(wb200_mag* m, double* XY_inout, double lambda, double f_tol, double g_tol,
+                          int max_iter, int history, double* f_final, int* iters, int* n_fg);
+
 /* ---- measurement helpers (bench.py) -------------------------------------------------------------
  * wb200_profile: when enabled, every launch of the four kernel classes below is bracketed by CUDA
  * events on the ctx's stream; wb200_profile_read synchronises, returns the summed milliseconds and

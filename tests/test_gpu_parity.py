@@ -334,6 +334,44 @@ def test_synthetic_both_kernels(w, lat, grid, nb, nw):
     assert kernels == ({"cuda-core-fp64", "dmma-fp64"} if nb <= 256 else {"cuda-core-fp64"})
 
 
+@pytest.mark.parametrize("name", ["cfg2_cu_shape", "cfg3_nw32", "cfg5_2d_nw256"])
+def test_baseline_configs_at_their_exact_sizes(w, name):
+    """BASELINE.json configs 2, 3 and 5 at their full k-grids (9^3 / 12^3 / 10 x 10 x 1), not only as tile
+    shapes: Omega, the five-way split, r, omega_n and G against the oracle at 1e-10; config 2 through the
+    (X, Y) chain with the five lowest bands frozen (its path in the reference, disentangle.jl:586-614);
+    config 3 additionally two iterations of the device max_localize against the oracle's Optim restatement."""
+    lat, grid, nb, nw = w.synthetic.CONFIGS[name]
+    st, M, U = w.synthetic.make_model_arrays(lat, grid, nb, nw)
+    nk = len(U)
+    args = (M, st["kpb_k"], st["bvec"], st["wb"])
+    ctx = make_ctx(w, st, M, nw)
+    assert ctx.rotation_kernel == "dmma-fp64"
+    f_ref, G_ref = so.fg_maxloc(*args, U)
+    G = np.empty((nk, nw, nb), dtype=np.complex128)
+    f = ctx.fg(w.api.to_abi_U(U), G=G)
+    assert abs(f - f_ref) < RTOL * abs(f_ref)
+    assert rel(w.api.from_abi_U(G), G_ref) < RTOL
+    check_spread(ctx.spread(w.api.to_abi_U(U)), so.omega(*args, U))
+    if name == "cfg2_cu_shape":
+        frozen = w.synthetic.make_frozen(nk, nb, 5)
+        ctx.set_frozen(frozen)
+        X, Y = so.U_to_X_Y(U, frozen)
+        XY = np.ascontiguousarray(so.X_Y_to_XY(X, Y))
+        Gxy = np.empty_like(XY)
+        fx = ctx.fg_xy(XY, G=Gxy)
+        fx_ref, Gxy_ref = so.fg_disentangle(*args, XY, nb, nw, frozen)
+        assert abs(fx - fx_ref) < RTOL * abs(fx_ref)
+        assert rel(Gxy, Gxy_ref) < RTOL
+    if name == "cfg3_nw32":
+        Ud = np.ascontiguousarray(w.api.to_abi_U(U))
+        fd, itd, nfgd = ctx.max_localize(Ud, max_iter=2)
+        Uo, fo, ito, infoo = so.max_localize(*args, U, max_iter=2)
+        assert (itd, nfgd) == (ito, infoo["n_fg"])
+        assert abs(fd - fo) < 1e-9 * abs(fo)
+        assert np.abs(w.api.from_abi_U(Ud) - Uo).max() < 1e-8
+    ctx.close()
+
+
 def test_unitary_shortcut_vs_exact_split(w):
     # fg (one GEMM, ||N||_F = ||MU||_F for square unitary U) and spread (full N) agree on all
     # five scalars when nb == nw
@@ -640,3 +678,64 @@ def test_stiefel_ops_on_the_tensor_pipe(w, lat, grid, n):
     assert it == ito and abs(f - fo) < 1e-9 * max(abs(fo), 1.0)   # degenerate stencils give Omega ~ 0
     assert np.abs(w.api.from_abi_U(Uc) - Uo).max() < 1e-8
     ctx.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# MagModel co-optimisation (src/localization/coopt.jl)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("lat,grid,nb,nw,nfroz", [
+    ("fcc", (2, 2, 2), 6, 4, 2),        # fused small-shape kernels
+    ("cubic", (5, 4, 5), 18, 9, 5),     # > 64 k-points: two-stage reduction of diag(Mw)
+    ("fcc", (2, 2, 2), 72, 40, 9),      # batched GEMMs on the FP64 tensor pipe
+])
+def test_magmodel_coupling_and_disentangle(w, lat, grid, nb, nw, nfroz):
+    st, Mu, Md, Mud, Uu, Ud = w.synthetic.make_mag_arrays(lat, grid, nb, nw)
+    nk = len(Uu)
+    frozen = w.synthetic.make_frozen(nk, nb, nfroz)
+    stencil = w.KspaceStencil(st["recip"], st["kpoints"], st["wb"], st["kpb_k"], st["kpb_G"])
+    model = w.MagModel(w.Model(st["lattice"], stencil, Mu, Uu, frozen_bands=frozen),
+                       w.Model(st["lattice"], stencil, Md, Ud, frozen_bands=frozen), Mud)
+    cache = w.MagCache(model)
+    up = (Mu, st["kpb_k"], st["bvec"], st["wb"])
+    dn = (Md, st["kpb_k"], st["bvec"], st["wb"])
+    # overlap_updn, omega_updn, omega_updn_grad (coopt.jl:114-235)
+    Mw = w.overlap_updn(model, cache=cache)
+    assert rel(Mw, so.overlap_updn(Mud, Uu, Ud)) < RTOL
+    assert abs(w.omega_updn(model, cache=cache) - so.omega_updn(Mud, Uu, Ud)) < RTOL * nw
+    Gu, Gd = w.omega_updn_grad(model, Uu, Ud, cache=cache)
+    Gu_ref, Gd_ref = so.omega_updn_grad(Mud, Uu, Ud)
+    assert rel(Gu, Gu_ref) < RTOL and rel(Gd, Gd_ref) < RTOL
+    # omega(model::MagModel, lambda) (coopt.jl:66-77)
+    for lam in (1.0, 0.35):
+        sp = w.omega(model, lam, cache=cache)
+        ref = so.omega_mag(up, dn, Mud, Uu, Ud, lam)
+        assert abs(sp.Omegat - ref["Omegat"]) < RTOL * abs(ref["Omegat"])
+        assert abs(sp.up.Omega - ref["up"]["Omega"]) < RTOL * abs(ref["Omegat"])
+        assert abs(sp.Omegaupdn - ref["Omegaupdn"]) < RTOL * nw
+    # f / g! over XY = [XYup; XYdn] (coopt.jl:252-321), lambda = 0 included (the coupling is skipped)
+    XY = w.api.mag_XY(model)
+    ni = nw * nw + nb * nw
+    XY_ref = np.concatenate([so.X_Y_to_XY(*so.U_to_X_Y(Uu, frozen)), so.X_Y_to_XY(*so.U_to_X_Y(Ud, frozen))], axis=1)
+    assert np.abs(XY - XY_ref).max() < 1e-12
+    for lam in (1.0, 0.0, 2.5):
+        f, g = w.get_fg_disentangle(model, lam, cache=cache)
+        G = np.empty_like(XY)
+        g(G, XY)
+        f_ref, G_ref = so.fg_mag_disentangle(up, dn, Mud, XY, nb, nw, frozen, frozen, lam)
+        assert abs(f(XY) - f_ref) < RTOL * abs(f_ref), lam
+        assert rel(G, G_ref) < RTOL, lam
+    # the device driver against the oracle's driver (same Optim restatement): same path, same spread
+    Uup, Udn, info = w.disentangle(model, 1.0, max_iter=6, cache=cache, return_info=True)
+    Uo, Do, xyo, fo, ito, infoo = so.disentangle_mag(up, dn, Mud, Uu, Ud, frozen, frozen, lam=1.0, max_iter=6)
+    assert (info["iterations"], info["n_fg"]) == (ito, infoo["n_fg"])
+    assert abs(info["f"] - fo) < 1e-9 * abs(fo)
+    assert np.abs(Uup - Uo).max() < 1e-7 and np.abs(Udn - Do).max() < 1e-7
+    ref = so.omega_mag(up, dn, Mud, Uup, Udn, 1.0)
+    assert abs(ref["Omegat"] - info["f"]) < 1e-9 * abs(info["f"])
+    for U in (Uup, Udn):
+        assert np.abs(np.conj(U.transpose(0, 2, 1)) @ U - np.eye(nw)).max() < 1e-11
+        assert np.abs((np.abs(U) ** 2).sum(axis=2)[frozen] - 1).max() < 1e-10
+    cache.close()
+    # error behaviour: mismatched spin channels (coopt.jl:355-357)
+    with pytest.raises(ValueError):
+        w.MagCache(w.MagModel(model.up, w.Model(st["lattice"], stencil, Md, Ud[:, :, :nw - 1], frozen_bands=frozen), Mud))

@@ -13,6 +13,8 @@ Python module; names, argument meaning and error behaviour follow the reference
     get_fg_maxloc, max_localize               src/localization/max_localize.jl:10-101
     X_Y_to_XY, XY_to_X_Y, X_Y_to_U, U_to_X_Y  src/localization/disentangle.jl:351-466
     get_fg_disentangle, disentangle           src/localization/disentangle.jl:586-728
+    MagModel, SpreadMag, overlap_updn, omega_updn, omega_updn_grad,
+    omega / get_fg_disentangle / disentangle on a MagModel      src/localization/coopt.jl
 
 Arrays use math indexing in numpy C order: M[k, b, m, l], U[k, m, n], G[k, m, n]; they are
 converted to the C-ABI's column-major (Julia) memory image at this boundary.  All arithmetic of
@@ -209,7 +211,12 @@ def _with_cache(args, cache):
 
 def omega(*args, cache=None):
     """omega([penalty,] model[, U]) / omega([penalty,] stencil, M, U)  (src/spread.jl:370-381;
-    with CenterSpreadPenalty -> omega_center, :221)."""
+    with CenterSpreadPenalty -> omega_center, :221).  omega(model::MagModel, [Uup, Udn,] lambda) -> SpreadMag
+    (coopt.jl:66-77)."""
+    if args and isinstance(args[0], MagModel):
+        if len(args) == 2:
+            return omega_mag(args[0], lam=args[1], cache=cache)
+        return omega_mag(args[0], args[1], args[2], args[3], cache=cache)
     p, cache, U, own = _with_cache(args, cache)
     try:
         out5, om, r, mn = cache.ctx.spread(to_abi_U(U))
@@ -471,8 +478,11 @@ def U_to_X_Y(U, frozen):
     return X, Y
 
 
-def get_fg_disentangle(p, model, cache=None):
-    """get_fg!_disentangle (disentangle.jl:586-614): fg(F, G, XY) with XY [nk, nw*nw + nb*nw]."""
+def get_fg_disentangle(p, model=None, cache=None):
+    """get_fg!_disentangle (disentangle.jl:586-614): fg(F, G, XY) with XY [nk, nw*nw + nb*nw].
+    get_fg_disentangle(model::MagModel, lambda) -> (f, g!) (coopt.jl:252-321)."""
+    if isinstance(p, MagModel):
+        return get_fg_disentangle_mag(p, 1.0 if model is None else model, cache=cache)
     cache = cache or Cache.from_model(model)
     cache.set_penalty(p)
 
@@ -491,8 +501,12 @@ def get_fg_disentangle(p, model, cache=None):
 
 def disentangle(*args, f_tol=1e-7, g_tol=1e-5, max_iter=200, history_size=3, cache=None,
                 return_info=False, devices=None):
-    """disentangle([p,] model; ...) -> gauges U[k, m, n]   (disentangle.jl:631-728)"""
+    """disentangle([p,] model; ...) -> gauges U[k, m, n]   (disentangle.jl:631-728);
+    disentangle(model::MagModel[, lambda]; ...) -> (Uup, Udn)   (coopt.jl:339-420)"""
     args = list(args)
+    if isinstance(args[0], MagModel):
+        return disentangle_mag(args[0], args[1] if len(args) > 1 else 1.0, f_tol=f_tol, g_tol=g_tol,
+                               max_iter=max_iter, history_size=history_size, cache=cache, return_info=return_info)
     p = SpreadPenalty()
     if isinstance(args[0], (SpreadPenalty, CenterSpreadPenalty)):
         p = args.pop(0)
@@ -512,3 +526,130 @@ def disentangle(*args, f_tol=1e-7, g_tol=1e-5, max_iter=200, history_size=3, cac
     X, Y = XY_to_X_Y(XY, model.n_bands, model.n_wannier)
     U = X_Y_to_U(X, Y)
     return (U, dict(f=f, iterations=iters, n_fg=nfg)) if return_info else U
+
+
+# ------------------------------------------------------------------------------------------
+# MagModel: spin-up / spin-down co-optimisation (src/localization/coopt.jl)
+# ------------------------------------------------------------------------------------------
+@dataclass
+class MagModel:
+    """coopt.jl:8-17: the two spin channels and M[k, m, l] = <u_mk^up | u_lk^dn>."""
+    up: Model
+    dn: Model
+    M: np.ndarray
+
+
+@dataclass
+class SpreadMag:
+    """coopt.jl:46-64"""
+    up: Spread
+    dn: Spread
+    Omegaupdn: float
+    Omegat: float
+    M: np.ndarray
+    lam: float
+
+
+class MagCache:
+    """Device state of a MagModel: one Cache per spin channel and the coupling context."""
+
+    def __init__(self, model: MagModel, device=0):
+        if (model.up.n_bands, model.up.n_wannier, model.up.n_kpoints) != \
+                (model.dn.n_bands, model.dn.n_wannier, model.dn.n_kpoints):
+            raise ValueError("MagModel: up and down models differ in n_bands / n_wann / n_kpts")   # coopt.jl:355-357
+        self.up = Cache.from_model(model.up, device=device)
+        self.dn = Cache.from_model(model.dn, device=device)
+        Mud = np.ascontiguousarray(np.asarray(model.M, dtype=np.complex128).transpose(0, 2, 1))
+        self.mag = _lib.MagContext(self.up.ctx, self.dn.ctx, Mud)
+        self.nb, self.nw, self.nk = self.up.nb, self.up.nw, self.up.nk
+
+    def close(self):
+        self.mag.close()
+        self.up.close()
+        self.dn.close()
+
+
+def _mag_call(model, cache, fn):
+    own = cache is None
+    cache = cache or MagCache(model)
+    try:
+        return fn(cache)
+    finally:
+        if own:
+            cache.close()
+
+
+def overlap_updn(model, Uup=None, Udn=None, cache=None):
+    """overlap_updn(model[, Uup, Udn]) -> |sum_k Uup_k^H M_k Udn_k|^2 / nk^2  [nw, nw]  (coopt.jl:114-135)"""
+    Uup = model.up.gauges if Uup is None else Uup
+    Udn = model.dn.gauges if Udn is None else Udn
+    return _mag_call(model, cache, lambda c: np.ascontiguousarray(c.mag.overlap(to_abi_U(Uup), to_abi_U(Udn))[0].T))
+
+
+def omega_updn(model, Uup=None, Udn=None, cache=None):
+    """omega_updn(model[, Uup, Udn]) = n_wann - tr(overlap_updn)   (coopt.jl:146-160)"""
+    Uup = model.up.gauges if Uup is None else Uup
+    Udn = model.dn.gauges if Udn is None else Udn
+    return _mag_call(model, cache, lambda c: c.mag.overlap(to_abi_U(Uup), to_abi_U(Udn), want_M=False)[1])
+
+
+def omega_updn_grad(model, Uup, Udn, cache=None):
+    """omega_updn_grad(model, Uup, Udn) -> (GUup, GUdn)[k, m, n]   (coopt.jl:222-229)"""
+    def run(c):
+        Gu, Gd = c.mag.omega_updn_grad(to_abi_U(Uup), to_abi_U(Udn))
+        return from_abi_U(Gu), from_abi_U(Gd)
+    return _mag_call(model, cache, run)
+
+
+def omega_mag(model, Uup=None, Udn=None, lam=1.0, cache=None):
+    """omega(model::MagModel, [Uup, Udn,] lambda) -> SpreadMag   (coopt.jl:66-77)"""
+    Uup = model.up.gauges if Uup is None else Uup
+    Udn = model.dn.gauges if Udn is None else Udn
+
+    def run(c):
+        up = omega(model.up, Uup, cache=c.up)
+        dn = omega(model.dn, Udn, cache=c.dn)
+        Mw2, o = c.mag.overlap(to_abi_U(Uup), to_abi_U(Udn))
+        return SpreadMag(up, dn, o, up.Omega + dn.Omega + lam * o, np.ascontiguousarray(Mw2.T), lam)
+    return _mag_call(model, cache, run)
+
+
+def mag_XY(model):
+    """XY0 of disentangle(::MagModel) (coopt.jl:369-374): row k = [XYup_k; XYdn_k]."""
+    XYu = X_Y_to_XY(*U_to_X_Y(model.up.gauges, model.up.frozen_bands))
+    XYd = X_Y_to_XY(*U_to_X_Y(model.dn.gauges, model.dn.frozen_bands))
+    return np.ascontiguousarray(np.concatenate([XYu, XYd], axis=1))
+
+
+def get_fg_disentangle_mag(model, lam=1.0, cache=None):
+    """get_fg!_disentangle(model::MagModel, lambda) -> (f, g!)   (coopt.jl:252-321); XY [nk, 2 n_inner]."""
+    cache = cache or MagCache(model)
+
+    def f(XY):
+        return cache.mag.fg_xy(np.ascontiguousarray(XY, dtype=np.complex128), lam)[0]
+
+    def g(G, XY):
+        Gb = np.empty((cache.nk, 2 * cache.mag.n_inner), dtype=np.complex128)
+        cache.mag.fg_xy(np.ascontiguousarray(XY, dtype=np.complex128), lam, want_f=False, G=Gb)
+        G[...] = Gb
+
+    f.cache = cache
+    f.close = g.close = cache.close
+    return f, g
+
+
+def disentangle_mag(model, lam=1.0, f_tol=1e-7, g_tol=1e-5, max_iter=200, history_size=3, cache=None,
+                    return_info=False):
+    """disentangle(model::MagModel, lambda; ...) -> (Uup, Udn)   (coopt.jl:339-420)"""
+    if model.up.frozen_bands is None or model.dn.frozen_bands is None:
+        raise ValueError("disentangle needs frozen_bands on both spin channels")
+    nb, nw = model.up.n_bands, model.up.n_wannier
+    n_inner = nw * nw + nb * nw
+
+    def run(c):
+        XY = mag_XY(model)
+        f, iters, nfg = c.mag.disentangle(XY, lam, f_tol, g_tol, max_iter, history_size)
+        Uup = X_Y_to_U(*XY_to_X_Y(np.ascontiguousarray(XY[:, :n_inner]), nb, nw))
+        Udn = X_Y_to_U(*XY_to_X_Y(np.ascontiguousarray(XY[:, n_inner:]), nb, nw))
+        return (Uup, Udn, dict(f=f, iterations=iters, n_fg=nfg)) if return_info else (Uup, Udn)
+    return _mag_call(model, cache, run)

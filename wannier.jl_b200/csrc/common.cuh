@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -225,10 +226,12 @@ int wb_project_tangent_dev(wb200_ctx* ctx, const cplx* dX, cplx* dG, int nrow, i
 // tangent_step: X = X0 + a s with X0 on the manifold and s tangent at X0, hence X^H X = I + a^2 s^H s: every
 // singular value is >= 1, which the scaled Newton-Schulz iteration of the large-shape path exploits
 int wb_retract_dev(wb200_ctx* ctx, cplx* dX, int nrow, int ncol, int count, int* iters, bool tangent_step = false);
-int wb_retract_xy(wb200_ctx* ctx, cplx* dXY, bool tangent_step = false);
-int wb_project_xy(wb200_ctx* ctx, const cplx* dXY, cplx* dG);
-int wb_xy_to_u(wb200_ctx* ctx, const cplx* dXY, cplx* dU);
-int wb_gu_to_gxy(wb200_ctx* ctx, const cplx* dXY, const cplx* dGU, cplx* dGXY);
+// st: distance in complex elements between the [X_k; Y_k] blocks of consecutive k (0: nw*nw + nb*nw, the
+// packed XY array; the MagModel array interleaves the up and down blocks, st = 2 (nw*nw + nb*nw))
+int wb_retract_xy(wb200_ctx* ctx, cplx* dXY, bool tangent_step = false, long long st = 0);
+int wb_project_xy(wb200_ctx* ctx, const cplx* dXY, cplx* dG, long long st = 0);
+int wb_xy_to_u(wb200_ctx* ctx, const cplx* dXY, cplx* dU, long long st = 0);
+int wb_gu_to_gxy(wb200_ctx* ctx, const cplx* dXY, const cplx* dGU, cplx* dGXY, long long st = 0);
 
 // ---- stiefel_small.cu ----
 bool wb_small_applicable(int nrow, int ncol);
@@ -284,3 +287,13 @@ int wb_zgemm(wb200_ctx* ctx, const ZgemmArgs& a);
 // ---- optimizer.cu ----
 int wb_lbfgs(wb200_ctx* ctx, int mode /*0 maxloc, 1 disentangle*/, cplx* dx, double f_tol,
              double g_tol, int max_iter, int history, double* f_final, int* iters, int* n_fg);
+// the same driver on a caller-defined manifold problem (mag.cu): vectors of `ncplx` complex numbers on
+// ctx's device and stream; eval leaves f in ctx->d_res[5] and writes the Euclidean gradient
+struct WbCustomProblem {
+    size_t ncplx = 0;
+    std::function<int(cplx*, bool)> retract;             // (x, tangent_step)
+    std::function<int(const cplx*, cplx*)> project;      // (x, g): g <- projection of g on the tangent space at x
+    std::function<int(const cplx*, cplx*)> eval;         // (x, g)
+};
+int wb_lbfgs_custom(wb200_ctx* ctx, const WbCustomProblem& cp, cplx* dx, double f_tol, double g_tol,
+                    int max_iter, int history, double* f_final, int* iters, int* n_fg);

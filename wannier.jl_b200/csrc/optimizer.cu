@@ -206,14 +206,17 @@ struct Problem {
                   // 2: one global W on Stiefel nw x nw (opt_rotate)
     size_t n;     // doubles per vector
     int n_fg = 0;
+    const WbCustomProblem* custom = nullptr;   // mode 3
 
     // tangent_step: x = x0 + a s with x0 on the manifold and s tangent at x0 (every trial point of a line search)
     int retract(cplx* x, bool tangent_step = false) {
+        if (mode == 3) return custom->retract(x, tangent_step);
         if (mode == 2) return wb_retract_dev(ctx, x, ctx->nw, ctx->nw, 1, nullptr, tangent_step);
         if (mode == 0) return wb_retract_dev(ctx, x, ctx->nb, ctx->nw, ctx->nk, nullptr, tangent_step);
         return wb_retract_xy(ctx, x, tangent_step);
     }
     int project(const cplx* x, cplx* g) {
+        if (mode == 3) return custom->project(x, g);
         if (mode == 2) return wb_project_tangent_dev(ctx, x, g, ctx->nw, ctx->nw, 1);
         if (mode == 0) return wb_project_tangent_dev(ctx, x, g, ctx->nb, ctx->nw, ctx->nk);
         return wb_project_xy(ctx, x, g);
@@ -222,7 +225,9 @@ struct Problem {
     // one synchronisation returns f, min |N_nn| and the inner product
     int fg(const cplx* x, double* f, cplx* g, const double* d, double* gd) {
         n_fg++;
-        if (mode == 0) {
+        if (mode == 3) {
+            WB_TRY(custom->eval(x, g));
+        } else if (mode == 0) {
             WB_TRY(wb_fg_device(ctx, x, ctx->d_res, g, 0));
         } else if (mode == 2) {
             WB_TRY(wb_fg_rotate_device(ctx, x, ctx->d_res, g));
@@ -255,10 +260,23 @@ struct Problem {
 
 }  // namespace
 
+static int lbfgs_run(wb200_ctx* ctx, int mode, const WbCustomProblem* custom, cplx* dx, double f_tol, double g_tol,
+                     int max_iter, int history, double* f_final, int* iters_out, int* n_fg_out);
+
 int wb_lbfgs(wb200_ctx* ctx, int mode, cplx* dx, double f_tol, double g_tol, int max_iter,
              int history, double* f_final, int* iters_out, int* n_fg_out) {
+    return lbfgs_run(ctx, mode, nullptr, dx, f_tol, g_tol, max_iter, history, f_final, iters_out, n_fg_out);
+}
+int wb_lbfgs_custom(wb200_ctx* ctx, const WbCustomProblem& cp, cplx* dx, double f_tol, double g_tol,
+                    int max_iter, int history, double* f_final, int* iters_out, int* n_fg_out) {
+    return lbfgs_run(ctx, 3, &cp, dx, f_tol, g_tol, max_iter, history, f_final, iters_out, n_fg_out);
+}
+
+static int lbfgs_run(wb200_ctx* ctx, int mode, const WbCustomProblem* custom, cplx* dx, double f_tol, double g_tol,
+                     int max_iter, int history, double* f_final, int* iters_out, int* n_fg_out) {
     Problem P{ctx, mode, 0};
-    const size_t ncplx = (mode == 2) ? (size_t)ctx->nw * ctx->nw
+    P.custom = custom;
+    const size_t ncplx = (mode == 3) ? custom->ncplx : (mode == 2) ? (size_t)ctx->nw * ctx->nw
                          : (mode == 0) ? (size_t)ctx->nk * ctx->nb * ctx->nw
                                        : (size_t)ctx->nk * ((size_t)ctx->nw * ctx->nw + (size_t)ctx->nb * ctx->nw);
     P.n = 2 * ncplx;

@@ -265,16 +265,16 @@ int wb_retract_dev(wb200_ctx* ctx, cplx* dX, int nrow, int ncol, int count, int*
 }
 
 // manifold ops on the packed XY array (product manifold per k)
-int wb_retract_xy(wb200_ctx* ctx, cplx* dXY, bool tangent_step) {
+int wb_retract_xy(wb200_ctx* ctx, cplx* dXY, bool tangent_step, long long st) {
     const int nb = ctx->nb, nw = ctx->nw;
-    const long long st = (long long)nw * nw + (long long)nb * nw;
+    if (st <= 0) st = (long long)nw * nw + (long long)nb * nw;
     WB_TRY(retract_strided(ctx, dXY, nw, nw, nw, st, ctx->nk, nullptr, tangent_step));
     WB_TRY(retract_strided(ctx, dXY + (long long)nw * nw, nb, nw, nb, st, ctx->nk, nullptr, tangent_step));
     return WB200_OK;
 }
-int wb_project_xy(wb200_ctx* ctx, const cplx* dXY, cplx* dG) {
+int wb_project_xy(wb200_ctx* ctx, const cplx* dXY, cplx* dG, long long st) {
     const int nb = ctx->nb, nw = ctx->nw;
-    const long long st = (long long)nw * nw + (long long)nb * nw;
+    if (st <= 0) st = (long long)nw * nw + (long long)nb * nw;
     WB_TRY(project_strided(ctx, dXY, dG, nw, nw, nw, st, ctx->nk));
     WB_TRY(project_strided(ctx, dXY + (long long)nw * nw, dG + (long long)nw * nw, nb, nw, nb, st,
                            ctx->nk));
@@ -358,9 +358,9 @@ static int xy_small_attr(wb200_ctx* ctx) {
     return WB200_OK;
 }
 
-int wb_xy_to_u(wb200_ctx* ctx, const cplx* dXY, cplx* dU) {
+int wb_xy_to_u(wb200_ctx* ctx, const cplx* dXY, cplx* dU, long long st) {
     const int nb = ctx->nb, nw = ctx->nw;
-    const long long st = (long long)nw * nw + (long long)nb * nw;
+    if (st <= 0) st = (long long)nw * nw + (long long)nb * nw;
     if (nb <= WB_XY_SMALL_MAX) {
         WB_TRY(xy_small_attr(ctx));
         const size_t smem = sizeof(cplx) * ((size_t)nw * nw + (size_t)nw * (nb + 1));
@@ -389,9 +389,9 @@ __global__ void mask_gy_kernel(int nb, int nw, long long st, const uint8_t* __re
     }
 }
 
-int wb_gu_to_gxy(wb200_ctx* ctx, const cplx* dXY, const cplx* dGU, cplx* dGXY) {
+int wb_gu_to_gxy(wb200_ctx* ctx, const cplx* dXY, const cplx* dGU, cplx* dGXY, long long st) {
     const int nb = ctx->nb, nw = ctx->nw;
-    const long long st = (long long)nw * nw + (long long)nb * nw;
+    if (st <= 0) st = (long long)nw * nw + (long long)nb * nw;
     if (nb <= WB_XY_SMALL_MAX) {
         WB_TRY(xy_small_attr(ctx));
         const size_t smem = sizeof(cplx) * ((size_t)nw * (nw + 1) + 2 * (size_t)nw * (nb + 1));

@@ -30,6 +30,8 @@ SYMBOLS = [
     "wb200_multi_slab_begin", "wb200_multi_launch_count", "wb200_multi_set_penalty", "wb200_multi_set_frozen",
     "wb200_multi_fg", "wb200_multi_spread", "wb200_multi_fg_xy", "wb200_multi_max_localize",
     "wb200_multi_disentangle",
+    "wb200_mag_create", "wb200_mag_destroy", "wb200_mag_last_error", "wb200_mag_overlap",
+    "wb200_mag_omega_updn_grad", "wb200_mag_fg_xy", "wb200_mag_disentangle",
 ]
 
 FLAG_DEFAULT = 0
@@ -119,13 +121,23 @@ def load():
     lib.wb200_multi_fg_xy.argtypes = [vp, pd, pd, pd]
     lib.wb200_multi_max_localize.argtypes = [vp, pd, dbl, dbl, i32, i32, pd, pd, pd]
     lib.wb200_multi_disentangle.argtypes = [vp, pd, dbl, dbl, i32, i32, pd, pd, pd]
+    lib.wb200_mag_create.argtypes = [C.POINTER(vp), vp, vp, pd]
+    lib.wb200_mag_destroy.argtypes = [vp]
+    lib.wb200_mag_destroy.restype = None
+    lib.wb200_mag_last_error.argtypes = [vp]
+    lib.wb200_mag_last_error.restype = C.c_char_p
+    lib.wb200_mag_overlap.argtypes = [vp, pd, pd, pd, pd]
+    lib.wb200_mag_omega_updn_grad.argtypes = [vp, pd, pd, pd, pd]
+    lib.wb200_mag_fg_xy.argtypes = [vp, pd, dbl, pd, pd, pd]
+    lib.wb200_mag_disentangle.argtypes = [vp, pd, dbl, dbl, dbl, i32, i32, pd, pd, pd]
     lib.wb200_profile.argtypes = [vp, i32]
     lib.wb200_profile_read.argtypes = [vp, pd, pd]
     lib.wb200_probe_fp64_peak.argtypes = [i32, pd, pd]
     for name in SYMBOLS:
         f = getattr(lib, name)
         if name not in ("wb200_destroy", "wb200_last_error", "wb200_version", "wb200_launch_count",
-                        "wb200_multi_destroy", "wb200_multi_last_error", "wb200_multi_launch_count"):
+                        "wb200_multi_destroy", "wb200_multi_last_error", "wb200_multi_launch_count",
+                        "wb200_mag_destroy", "wb200_mag_last_error"):
             f.restype = i32
     _lib = lib
     return lib
@@ -552,3 +564,76 @@ class DeviceArray:
 
     def __init__(self, ptr, shape, typestr="<c16"):
         self.__cuda_array_interface__ = dict(shape=tuple(shape), typestr=typestr, data=(int(ptr), False), version=2)
+
+
+class MagContext:
+    """One wb200_mag (src/localization/coopt.jl): borrows the up and down single-slab contexts (same
+    device) and owns Mud [nk][nb(l)][nb(m)] (Julia M[ik], nb x nb column-major per k)."""
+
+    def __init__(self, up: Context, dn: Context, Mud):
+        self._h = None
+        lib = load()
+        if not isinstance(Mud, (int, np.integer)):
+            _check_array(Mud, np.complex128, up.nk * up.nb * up.nb, "Mud")
+        self.up, self.dn = up, dn
+        self.nb, self.nw, self.nk = up.nb, up.nw, up.nk
+        self.n_inner = self.nw * self.nw + self.nb * self.nw
+        h = C.c_void_p()
+        st = lib.wb200_mag_create(C.byref(h), up._h, dn._h, _addr(Mud))
+        if st != 0:
+            raise WB200Error(st, lib.wb200_mag_last_error(None).decode())
+        self._h = h
+        self._lib = lib
+
+    def close(self):
+        if self._h is not None:
+            self._lib.wb200_mag_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, st):
+        if st != 0:
+            raise WB200Error(st, self._lib.wb200_mag_last_error(self._h).decode())
+
+    def overlap(self, Uup, Udn, want_M=True):
+        """-> (Mw2 [nw(n)][nw(m)] column-major image or None, omega_updn)"""
+        n = self.nk * self.nb * self.nw
+        _check_array(Uup, np.complex128, n, "Uup")
+        _check_array(Udn, np.complex128, n, "Udn")
+        Mw2 = np.empty((self.nw, self.nw), dtype=np.float64) if want_M else None
+        o = C.c_double(0.0)
+        self._ck(self._lib.wb200_mag_overlap(self._h, _addr(Uup), _addr(Udn), _addr(Mw2), C.addressof(o)))
+        return Mw2, o.value
+
+    def omega_updn_grad(self, Uup, Udn):
+        n = self.nk * self.nb * self.nw
+        _check_array(Uup, np.complex128, n, "Uup")
+        _check_array(Udn, np.complex128, n, "Udn")
+        Gu = np.empty((self.nk, self.nw, self.nb), dtype=np.complex128)
+        Gd = np.empty_like(Gu)
+        self._ck(self._lib.wb200_mag_omega_updn_grad(self._h, _addr(Uup), _addr(Udn), _addr(Gu), _addr(Gd)))
+        return Gu, Gd
+
+    def fg_xy(self, XY, lam, want_f=True, G=None):
+        """-> (f or None, out4 = [Omega_updn, Omega_t, Omega_up, Omega_dn]); G [nk][2 n_inner] written in place"""
+        n = self.nk * 2 * self.n_inner
+        _check_array(XY, np.complex128, n, "XY")
+        if G is not None:
+            _check_array(G, np.complex128, n, "G")
+        f = C.c_double(0.0)
+        out4 = np.zeros(4, dtype=np.float64)
+        self._ck(self._lib.wb200_mag_fg_xy(self._h, _addr(XY), float(lam), C.addressof(f) if want_f else None,
+                                           _addr(G), _addr(out4)))
+        return (f.value if want_f else None), out4
+
+    def disentangle(self, XY, lam, f_tol=1e-7, g_tol=1e-5, max_iter=200, history=3):
+        _check_array(XY, np.complex128, self.nk * 2 * self.n_inner, "XY")
+        f, it, nfg = C.c_double(0.0), C.c_int(0), C.c_int(0)
+        self._ck(self._lib.wb200_mag_disentangle(self._h, _addr(XY), float(lam), f_tol, g_tol, max_iter, history,
+                                                 C.addressof(f), C.addressof(it), C.addressof(nfg)))
+        return f.value, it.value, nfg.value

@@ -116,16 +116,23 @@ def _polar_np(A):
     return W @ Vh
 
 
-def make_overlaps(st, nb, seed=SEED_M):
-    """numpy: M[k, b, m, l] complex128."""
-    Rs, c = _coeffs(nb, seed)
-    nH = c.shape[1]
+def _frames(st, nb, Rs, c):
+    """orthonormal frames V[k] (nH x nb) of the smooth subspace: polar factor of sum_R c_R e^{2 pi i k.R} + [I; 0]"""
     phase = np.exp(2j * np.pi * (st["kpoints"] @ Rs.T))            # [nk, 27]
     B = np.einsum("kr,rhn->khn", phase, c)
     B[:, :nb, :] += np.eye(nb)
-    V = _polar_np(B)                                               # [nk, nH, nb]
+    return _polar_np(B)                                            # [nk, nH, nb]
+
+
+def _overlaps_of(st, V):
     Vh = np.conj(V.transpose(0, 2, 1))
     return np.ascontiguousarray(Vh[:, None] @ V[st["kpb_k"]])       # [nk, nn, nb, nb]
+
+
+def make_overlaps(st, nb, seed=SEED_M):
+    """numpy: M[k, b, m, l] complex128."""
+    Rs, c = _coeffs(nb, seed)
+    return _overlaps_of(st, _frames(st, nb, Rs, c))
 
 
 def make_gauge(nk, nb, nw, eps=0.05, seed=SEED_U):
@@ -158,6 +165,21 @@ def make_model_arrays(lattice_name, grid, nb, nw, eps=0.05):
     M = make_overlaps(st, nb)
     U = make_gauge(len(st["kpoints"]), nb, nw, eps)
     return st, M, U
+
+
+def make_mag_arrays(lattice_name, grid, nb, nw, eps=0.05, mix=0.3):
+    """A synthetic spin-polarised pair for the MagModel path (src/localization/coopt.jl): the down frames are a
+    smooth perturbation of the up frames, so Mud[k, m, l] = <u_mk^up | u_lk^dn> is close to the identity, as
+    for a weakly polarised material.  Returns (st, M_up, M_dn, Mud, U_up, U_dn)."""
+    st = make_stencil(LATTICES[lattice_name](), grid)
+    Rs, c_up = _coeffs(nb, SEED_M)
+    _, c_2 = _coeffs(nb, SEED_M + 1)
+    V_up = _frames(st, nb, Rs, c_up)
+    V_dn = _frames(st, nb, Rs, c_up + mix * c_2)
+    nk = len(st["kpoints"])
+    Mud = np.ascontiguousarray(np.conj(V_up.transpose(0, 2, 1)) @ V_dn)
+    return (st, _overlaps_of(st, V_up), _overlaps_of(st, V_dn), Mud,
+            make_gauge(nk, nb, nw, eps, SEED_U), make_gauge(nk, nb, nw, eps, SEED_U + 1))
 
 
 # ---- torch / GPU generation for the large bench shapes (plumbing only; same recipe) -----------
