@@ -237,6 +237,27 @@ int wb200_multi_max_localize(wb200_multi* m, double* U_inout, double f_tol, doub
 int wb200_multi_disentangle(wb200_multi* m, double* XY_inout, double f_tol, double g_tol, int max_iter,
                             int history, double* f_final, int* iters, int* n_fg);
 
+/* ---- initial point of the disentanglement (src/localization/disentangle.jl:223-281, 369-402) --------------
+ * wb200_u_to_xy          = X_Y_to_XY(U_to_X_Y(U, frozen)...) (disentangle.jl:369-402, 454-466): the starting
+ *                          point `disentangle` builds at :666-670.  U [nk][nw][nb], frozen from wb200_set_frozen
+ *                          (none: nothing frozen), XY as in wb200_fg_xy.  One kernel completes the frozen rows of
+ *                          U_k to an orthonormal basis; the two polar factors come from the batched retraction.
+ *                          The free block of Y_k is AN orthonormal basis of range(Ur); the reference's is the
+ *                          LAPACK eigenbasis of a degenerate projector, i.e. defined up to a unitary mixing, so
+ *                          X_k and Y_k agree with the reference up to that mixing while Y_k X_k =
+ *                          orthonorm_freeze(U_k), the frozen rows of Y_k and X_k^H X_k = I agree exactly.
+ * wb200_orthonorm_freeze = orthonorm_freeze(U_k, frozen_k) for every k (disentangle.jl:223-281), in place.
+ * Errors: WB200_ERR_ARG (more frozen bands than n_wann), WB200_ERR_SINGULAR (frozen rows of U linearly
+ * dependent), WB200_ERR_NOCONV (the free rows do not span n_wann - n_frozen dimensions: the reference's
+ * assertion at :265).  Work on k-slab contexts too (slab rows, no communication).
+ * wb200_create_stiefel   : a context WITHOUT stencil and overlaps for callers that have no model at hand
+ *                          (U_to_X_Y(U, frozen) takes none): valid for wb200_set_frozen, wb200_u_to_xy,
+ *                          wb200_orthonorm_freeze, wb200_retract, wb200_project_tangent; every evaluation entry
+ *                          point returns WB200_ERR_ARG.                                                        */
+int wb200_u_to_xy(wb200_ctx* ctx, const double* U, double* XY);
+int wb200_orthonorm_freeze(wb200_ctx* ctx, double* U_inout);
+int wb200_create_stiefel(wb200_ctx** out, int device, int nb, int nw, int nk);
+
 /* ---- MagModel co-optimisation (src/localization/coopt.jl) ---------------------------------------------
  * Spin-up and spin-down models coupled by the overlap of up and down Wannier functions.  A wb200_mag
  * borrows two single-slab contexts on the same device (the up and down `Model`s of `MagModel`,

@@ -713,10 +713,13 @@ def test_magmodel_coupling_and_disentangle(w, lat, grid, nb, nw, nfroz):
         assert abs(sp.up.Omega - ref["up"]["Omega"]) < RTOL * abs(ref["Omegat"])
         assert abs(sp.Omegaupdn - ref["Omegaupdn"]) < RTOL * nw
     # f / g! over XY = [XYup; XYdn] (coopt.jl:252-321), lambda = 0 included (the coupling is skipped)
-    XY = w.api.mag_XY(model)
+    XY = np.concatenate([so.X_Y_to_XY(*so.U_to_X_Y(Uu, frozen)), so.X_Y_to_XY(*so.U_to_X_Y(Ud, frozen))], axis=1)
     ni = nw * nw + nb * nw
-    XY_ref = np.concatenate([so.X_Y_to_XY(*so.U_to_X_Y(Uu, frozen)), so.X_Y_to_XY(*so.U_to_X_Y(Ud, frozen))], axis=1)
-    assert np.abs(XY - XY_ref).max() < 1e-12
+    XYd = w.api.mag_XY(model)                 # device U_to_X_Y of both spins: same U = Y X per spin
+    for a, Uref in ((XYd[:, :ni], Uu), (XYd[:, ni:], Ud)):
+        Xa, Ya = so.XY_to_X_Y(np.ascontiguousarray(a), nb, nw)
+        Af = np.stack([so.orthonorm_freeze(Uref[k], frozen[k]) for k in range(nk)])
+        assert np.abs(so.X_Y_to_U(Xa, Ya) - Af).max() < 1e-10
     for lam in (1.0, 0.0, 2.5):
         f, g = w.get_fg_disentangle(model, lam, cache=cache)
         G = np.empty_like(XY)
@@ -725,8 +728,14 @@ def test_magmodel_coupling_and_disentangle(w, lat, grid, nb, nw, nfroz):
         assert abs(f(XY) - f_ref) < RTOL * abs(f_ref), lam
         assert rel(G, G_ref) < RTOL, lam
     # the device driver against the oracle's driver (same Optim restatement): same path, same spread
-    Uup, Udn, info = w.disentangle(model, 1.0, max_iter=6, cache=cache, return_info=True)
+    XYrun = XY.copy()
+    f1, it1, nfg1 = cache.mag.disentangle(XYrun, 1.0, max_iter=6)
     Uo, Do, xyo, fo, ito, infoo = so.disentangle_mag(up, dn, Mud, Uu, Ud, frozen, frozen, lam=1.0, max_iter=6)
+    assert (it1, nfg1) == (ito, infoo["n_fg"])
+    assert np.abs(XYrun - xyo).max() < 1e-7          # same starting point: the very same iterates
+    # through the public API the start comes from the device U_to_X_Y (another basis of the free range: the
+    # trajectory is the same up to that unitary mixing, the gauges U = Y X are the same)
+    Uup, Udn, info = w.disentangle(model, 1.0, max_iter=6, cache=cache, return_info=True)
     assert (info["iterations"], info["n_fg"]) == (ito, infoo["n_fg"])
     assert abs(info["f"] - fo) < 1e-9 * abs(fo)
     assert np.abs(Uup - Uo).max() < 1e-7 and np.abs(Udn - Do).max() < 1e-7
@@ -739,3 +748,63 @@ def test_magmodel_coupling_and_disentangle(w, lat, grid, nb, nw, nfroz):
     # error behaviour: mismatched spin channels (coopt.jl:355-357)
     with pytest.raises(ValueError):
         w.MagCache(w.MagModel(model.up, w.Model(st["lattice"], stencil, Md, Ud[:, :, :nw - 1], frozen_bands=frozen), Mud))
+
+
+# ---------------------------------------------------------------------------------------------
+# setup step on the device: orthonorm_freeze / U_to_X_Y, disentangle.jl:223-281, 369-402
+# ---------------------------------------------------------------------------------------------
+def _check_u_to_xy(w, U, frozen, ctx=None):
+    nk, nb, nw = U.shape
+    X, Y = w.U_to_X_Y(U, frozen, cache=ctx)
+    Af = np.stack([so.orthonorm_freeze(U[k], frozen[k]) for k in range(nk)])
+    assert np.abs(so.X_Y_to_U(X, Y) - Af).max() < 1e-10                      # Y X = orthonorm_freeze(U)
+    eye = np.eye(nw)
+    assert np.abs(np.conj(X.transpose(0, 2, 1)) @ X - eye).max() < 1e-11
+    assert np.abs(np.conj(Y.transpose(0, 2, 1)) @ Y - eye).max() < 1e-11
+    Xo, Yo = so.U_to_X_Y(U, frozen)
+    for k in range(nk):
+        f = frozen[k]
+        nf = int(f.sum())
+        # frozen block of Y exactly as in the reference (disentangle.jl:386): identity on the frozen rows
+        assert np.array_equal(Y[k][f, :nf], np.eye(nf)) and not Y[k][f, nf:].any() and not Y[k][~f, :nf].any()
+        # free block: the same subspace as the reference's eigenvectors (projectors agree)
+        P, Po = Y[k][~f, nf:] @ np.conj(Y[k][~f, nf:].T), Yo[k][~f, nf:] @ np.conj(Yo[k][~f, nf:].T)
+        assert np.abs(P - Po).max() < 1e-10
+    V = w.orthonorm_freeze(U, frozen, cache=ctx)
+    assert np.abs(V - Af).max() < 1e-10
+    return X, Y
+
+
+def test_device_u_to_xy_and_orthonorm_freeze(w, silicon):
+    # the reference's 12 -> 8 silicon model: 4 ... 8 frozen bands per k-point, n_frozen == n_wann included
+    _check_u_to_xy(w, silicon["U"], silicon["frozen"])
+    assert silicon["frozen"].sum(axis=1).max() == 8
+    # U <-> (X, Y) round trip of the reference's own test (test/localization/disentangle.jl:8-25)
+    X, Y = w.U_to_X_Y(silicon["U"], silicon["frozen"])
+    X2, Y2 = w.U_to_X_Y(so.X_Y_to_U(X, Y), silicon["frozen"])
+    assert np.abs(so.X_Y_to_U(X2, Y2) - so.X_Y_to_U(X, Y)).max() < 1e-10
+    # synthetic shapes: fused small kernels, batched-GEMM retraction (nb > 64), nothing frozen, ragged frozen sets
+    rng = np.random.default_rng(11)
+    for lat, grid, nb, nw, nfroz in (("fcc", (3, 3, 3), 18, 9, 5), ("fcc", (2, 2, 2), 72, 40, 9),
+                                     ("cubic", (2, 2, 2), 40, 24, 0), ("bcc", (2, 2, 2), 128, 96, 17)):
+        st, M, U = w.synthetic.make_model_arrays(lat, grid, nb, nw, eps=0.2)
+        frozen = np.zeros((len(U), nb), dtype=bool)
+        for k in range(len(U)):          # a different frozen set at every k-point, not the lowest bands
+            frozen[k, rng.choice(nb, size=rng.integers(0, nfroz + 1), replace=False)] = True
+        ctx = make_ctx(w, st, M, nw)
+        ctx.set_frozen(frozen)
+
+        class _C:        # api-level cache stand-in: only .ctx is read
+            pass
+        c = _C(); c.ctx = ctx
+        _check_u_to_xy(w, U, frozen, ctx=c)
+        ctx.close()
+    # more frozen bands than Wannier functions
+    st, M, U = w.synthetic.make_model_arrays("fcc", (2, 2, 2), 6, 4)
+    with pytest.raises(w.WB200Error):
+        w.U_to_X_Y(U, w.synthetic.make_frozen(len(U), 6, 5))
+    # a Stiefel-only context refuses evaluations
+    sc = w.StiefelContext(6, 4, len(U))
+    with pytest.raises(w.WB200Error):
+        sc.fg(w.api.to_abi_U(U))
+    sc.close()

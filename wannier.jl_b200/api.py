@@ -435,47 +435,45 @@ def XY_to_X_Y(XY, nb, nw):
     return np.ascontiguousarray(X), np.ascontiguousarray(Y)
 
 
-def _lowdin(A):
-    W, _, Vh = np.linalg.svd(A, full_matrices=False)
-    return W @ Vh
-
-
-def orthonorm_freeze(U, frozen, atol=1e-10):
-    """disentangle.jl:223-281 (one k-point; one-off host setup, not on the iterated path)."""
-    nb, nw = U.shape
-    Uf = U[frozen, :]
-    if Uf.shape[0] > 0:
-        Uf = _lowdin(Uf)
-    Ur = U[~frozen, :]
-    Ur = Ur - Ur @ np.conj(Uf.T) @ Uf
-    A, S, Bh = np.linalg.svd(Ur, full_matrices=False)
-    if int((S > atol).sum()) != nw - int(frozen.sum()):
-        raise ValueError("orthonorm_freeze: wrong number of non-zero singular values")
-    Ur = (A * (S > atol)) @ Bh
-    V = np.empty_like(U)
-    V[frozen, :] = Uf
-    V[~frozen, :] = Ur
-    return V
-
-
-def U_to_X_Y(U, frozen):
-    """disentangle.jl:369-402 (one-off host setup)."""
+def _stiefel_ctx(U, frozen, cache):
     nk, nb, nw = U.shape
-    X = np.zeros((nk, nw, nw), dtype=np.complex128)
-    Y = np.zeros((nk, nb, nw), dtype=np.complex128)
-    for k in range(nk):
-        f = np.asarray(frozen[k], dtype=bool)
-        nf = int(f.sum())
-        Af = orthonorm_freeze(U[k], f)
-        Ur = Af[~f, :]
-        Y[k][np.nonzero(f)[0], np.arange(nf)] = 1.0
-        if nf != nw:
-            Pr = Ur @ np.conj(Ur.T)
-            Pr = (Pr + np.conj(Pr.T)) / 2
-            _, V = np.linalg.eigh(Pr)
-            Y[k][np.ix_(np.nonzero(~f)[0], np.arange(nf, nw))] = V[:, V.shape[1] - (nw - nf):]
-        X[k] = _lowdin(np.conj(Y[k].T) @ Af)
-    return X, Y
+    if cache is not None:
+        return cache.ctx, False
+    ctx = _lib.StiefelContext(nb, nw, nk)
+    ctx.set_frozen(None if frozen is None else np.asarray(frozen, dtype=np.uint8))
+    return ctx, True
+
+
+def orthonorm_freeze(U, frozen, cache=None):
+    """orthonorm_freeze(U_k, frozen_k) for every k (disentangle.jl:223-281): U[k, m, n], frozen[k, m].
+    Runs on the GPU (wb200_orthonorm_freeze); `cache` supplies a context whose frozen bands are already set."""
+    U = np.asarray(U, dtype=np.complex128)
+    single = U.ndim == 2
+    if single:
+        U, frozen = U[None], np.asarray(frozen)[None]
+    ctx, own = _stiefel_ctx(U, frozen, cache)
+    try:
+        Uc = to_abi_U(U)
+        ctx.orthonorm_freeze(Uc)
+    finally:
+        if own:
+            ctx.close()
+    V = from_abi_U(Uc)
+    return V[0] if single else V
+
+
+def U_to_X_Y(U, frozen, cache=None):
+    """U_to_X_Y(U, frozen) -> (X[k, :, :], Y[k, :, :])   (disentangle.jl:369-402), on the GPU (wb200_u_to_xy).
+    The free block of Y_k is an orthonormal basis of the non-frozen range; the reference's is LAPACK's
+    eigenbasis of a degenerate projector, i.e. the same up to a unitary mixing that X_k absorbs."""
+    U = np.asarray(U, dtype=np.complex128)
+    ctx, own = _stiefel_ctx(U, frozen, cache)
+    try:
+        XY = ctx.u_to_xy(to_abi_U(U))
+    finally:
+        if own:
+            ctx.close()
+    return XY_to_X_Y(XY, U.shape[1], U.shape[2])
 
 
 def get_fg_disentangle(p, model=None, cache=None):
@@ -517,8 +515,10 @@ def disentangle(*args, f_tol=1e-7, g_tol=1e-5, max_iter=200, history_size=3, cac
     cache = cache or Cache.from_model(model, devices=devices)
     cache.set_penalty(p)
     try:
-        X0, Y0 = U_to_X_Y(model.gauges, model.frozen_bands)     # disentangle.jl:666
-        XY = X_Y_to_XY(X0, Y0)                                  # :670
+        if hasattr(cache.ctx, "u_to_xy"):
+            XY = cache.ctx.u_to_xy(to_abi_U(model.gauges))       # disentangle.jl:666-670, on the device
+        else:                                                   # several GPUs: set up on the first one
+            XY = X_Y_to_XY(*U_to_X_Y(model.gauges, model.frozen_bands))
         f, iters, nfg = cache.ctx.disentangle(XY, f_tol, g_tol, max_iter, history_size)
     finally:
         if own:
@@ -616,7 +616,7 @@ def omega_mag(model, Uup=None, Udn=None, lam=1.0, cache=None):
 
 def mag_XY(model):
     """XY0 of disentangle(::MagModel) (coopt.jl:369-374): row k = [XYup_k; XYdn_k]."""
-    XYu = X_Y_to_XY(*U_to_X_Y(model.up.gauges, model.up.frozen_bands))
+    XYu = X_Y_to_XY(*U_to_X_Y(model.up.gauges, model.up.frozen_bands))      # coopt.jl:369-370
     XYd = X_Y_to_XY(*U_to_X_Y(model.dn.gauges, model.dn.frozen_bands))
     return np.ascontiguousarray(np.concatenate([XYu, XYd], axis=1))
 

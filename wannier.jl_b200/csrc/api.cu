@@ -198,10 +198,15 @@ extern "C" int wb200_set_frozen(wb200_ctx* ctx, const uint8_t* frozen) {
 // ---------------------------------------------------------------------------------------------
 // rotation of the local k-points [ka, kb); the tensor path needs the gauge packed first
 static int rotate_range(wb200_ctx* ctx, const cplx* dU, int ka, int kb) {
+    if (ctx->nn == 0) {
+        ctx->err = "this context has no stencil / overlaps (wb200_create_stiefel): Stiefel and setup calls only";
+        return WB200_ERR_ARG;
+    }
     if (ctx->dmma) return wb_rotate_dmma(ctx, dU, ka, kb);
     return wb_rotate_generic(ctx, dU, ka, kb);
 }
 static int rotate(wb200_ctx* ctx, const cplx* dU) {
+    if (ctx->nn == 0) return rotate_range(ctx, dU, 0, 0);
     if (ctx->dmma) WB_TRY(wb_pack_dmma(ctx, dU, 0, ctx->n_need));
     return rotate_range(ctx, dU, 0, ctx->nk);
 }

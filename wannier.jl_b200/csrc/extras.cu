@@ -102,6 +102,10 @@ static int single(wb200_ctx* ctx, const char* who) {
     return WB200_OK;
 }
 static int rotate_all(wb200_ctx* ctx, const cplx* dU) {
+    if (ctx->nn == 0) {
+        ctx->err = "this context has no stencil / overlaps (wb200_create_stiefel): Stiefel and setup calls only";
+        return WB200_ERR_ARG;
+    }
     if (ctx->dmma) {
         WB_TRY(wb_pack_dmma(ctx, dU, 0, ctx->n_need));
         return wb_rotate_dmma(ctx, dU, 0, ctx->nk);

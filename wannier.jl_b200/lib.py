@@ -30,6 +30,7 @@ SYMBOLS = [
     "wb200_multi_slab_begin", "wb200_multi_launch_count", "wb200_multi_set_penalty", "wb200_multi_set_frozen",
     "wb200_multi_fg", "wb200_multi_spread", "wb200_multi_fg_xy", "wb200_multi_max_localize",
     "wb200_multi_disentangle",
+    "wb200_u_to_xy", "wb200_orthonorm_freeze", "wb200_create_stiefel",
     "wb200_mag_create", "wb200_mag_destroy", "wb200_mag_last_error", "wb200_mag_overlap",
     "wb200_mag_omega_updn_grad", "wb200_mag_fg_xy", "wb200_mag_disentangle",
 ]
@@ -121,6 +122,9 @@ def load():
     lib.wb200_multi_fg_xy.argtypes = [vp, pd, pd, pd]
     lib.wb200_multi_max_localize.argtypes = [vp, pd, dbl, dbl, i32, i32, pd, pd, pd]
     lib.wb200_multi_disentangle.argtypes = [vp, pd, dbl, dbl, i32, i32, pd, pd, pd]
+    lib.wb200_u_to_xy.argtypes = [vp, pd, pd]
+    lib.wb200_orthonorm_freeze.argtypes = [vp, pd]
+    lib.wb200_create_stiefel.argtypes = [C.POINTER(vp), i32, i32, i32, i32]
     lib.wb200_mag_create.argtypes = [C.POINTER(vp), vp, vp, pd]
     lib.wb200_mag_destroy.argtypes = [vp]
     lib.wb200_mag_destroy.restype = None
@@ -343,6 +347,18 @@ class Context:
         _check_array(X, np.complex128, count * nrow * ncol, "X")
         self._ck(self._lib.wb200_retract(self._h, _addr(X), nrow, ncol, count))
 
+    def u_to_xy(self, U):
+        """X_Y_to_XY(U_to_X_Y(U, frozen)) with the ctx's frozen bands -> XY [nk][nw*nw + nb*nw]"""
+        _check_array(U, np.complex128, self.nk * self.nb * self.nw, "U")
+        XY = np.empty((self.nk, self.nw * self.nw + self.nb * self.nw), dtype=np.complex128)
+        self._ck(self._lib.wb200_u_to_xy(self._h, _addr(U), _addr(XY)))
+        return XY
+
+    def orthonorm_freeze(self, U):
+        """in place on U [nk][nw][nb]"""
+        _check_array(U, np.complex128, self.nk * self.nb * self.nw, "U")
+        self._ck(self._lib.wb200_orthonorm_freeze(self._h, _addr(U)))
+
     def max_localize(self, U, f_tol=1e-7, g_tol=1e-5, max_iter=200, history=3):
         # U is the ctx's k-slab (= everything for a single-slab ctx)
         _check_array(U, np.complex128, self.nk * self.nb * self.nw, "U")
@@ -416,6 +432,23 @@ class Context:
         it = C.c_int(0)
         self._ck(self._lib.wb200_retract_dev(self._h, dX, nrow, ncol, count, C.addressof(it)))
         return it.value
+
+
+class StiefelContext(Context):
+    """wb200_create_stiefel: no stencil, no overlaps — the per-k Stiefel operations and the setup step
+    (U_to_X_Y / orthonorm_freeze) for callers that have no model at hand."""
+
+    def __init__(self, nb, nw, nk, *, device=0):
+        self._h = None
+        lib = load()
+        self.nb, self.nw, self.nk_total, self.nn, self.nk, self.k_begin = nb, nw, nk, 0, nk, 0
+        self.device = device
+        h = C.c_void_p()
+        st = lib.wb200_create_stiefel(C.byref(h), device, nb, nw, nk)
+        if st != 0:
+            raise WB200Error(st, "wb200_create_stiefel failed (bad sizes or no sm_100 device; there is no CPU fallback)")
+        self._h = h
+        self._lib = lib
 
 
 class MultiContext:
