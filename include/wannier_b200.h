@@ -258,6 +258,24 @@ int wb200_u_to_xy(wb200_ctx* ctx, const double* U, double* XY);
 int wb200_orthonorm_freeze(wb200_ctx* ctx, double* U_inout);
 int wb200_create_stiefel(wb200_ctx** out, int device, int nb, int nw, int nk);
 
+/* ---- Wannier90 text ingest (the setup step in front of the path) ---------------------------------------------
+ * The reference reads these files through WannierIO.jl (third party; `read_w90`, src/io/w90/model.jl:16-94).
+ * The parsers here are native and multithreaded (a 16^3 x 12 x 128^2 .mmn is ~13 GB of text) and write the
+ * C-ABI memory images directly, so their output can be handed to wb200_create unchanged:
+ *   wb200_mmn_read: M [nk][nn][nb*nb] complex column-major, kpb_k [nk][nn] 0-based, kpb_G [nk][nn][3]; the b index
+ *                   is the order of appearance of a k-point's pairs (src/kpoints/kstencil.jl:68-85).
+ *   wb200_amn_read: A [nk][nw][nb] complex (the projections; Lowdin via wb200_retract gives the initial gauges,
+ *                   src/io/w90/amn.jl:12-17).
+ *   wb200_eig_read: E [nk][nb].
+ * Sizes come from the *_header calls (.eig has no header: nb, nk from the .mmn).  nthreads <= 0: all cores
+ * (at most 32).  Errors: WB200_ERR_ARG with the reason in wb200_io_last_error (thread-local).            */
+int wb200_mmn_header(const char* path, int* nb, int* nk, int* nn);
+int wb200_mmn_read(const char* path, int nb, int nk, int nn, double* M, int32_t* kpb_k, int32_t* kpb_G, int nthreads);
+int wb200_amn_header(const char* path, int* nb, int* nk, int* nw);
+int wb200_amn_read(const char* path, int nb, int nk, int nw, double* A);
+int wb200_eig_read(const char* path, int nb, int nk, double* E);
+const char* wb200_io_last_error(void);
+
 /* ---- MagModel co-optimisation (src/localization/coopt.jl) ---------------------------------------------
  * Spin-up and spin-down models coupled by the overlap of up and down Wannier functions.  A wb200_mag
  * borrows two single-slab contexts on the same device (the up and down `Model`s of `MagModel`,

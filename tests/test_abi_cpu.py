@@ -118,3 +118,51 @@ def test_w90_ingest_matches_goldens(w, valence, silicon):
     assert np.array_equal(E, silicon["E"])
     assert np.array_equal(io.frozen_bands(E, win2["dis_froz_max"], win2.get("dis_froz_min", -np.inf)), silicon["frozen"])
     assert (win2["num_wann"], win2["num_bands"]) == (8, 12)
+
+
+def test_native_ingest_edge_cases(w, tmp_path):
+    """wb200_mmn_read / wb200_amn_read / wb200_eig_read: pairs not grouped by k-point, Fortran 'D' exponents,
+    blank lines, every thread count, malformed input (WannierIO.jl's read_mmn / read_amn / read_eig semantics:
+    b = order of appearance of a k-point's pairs, 1-based indices in the file)."""
+    rng = np.random.default_rng(5)
+    nb, nk, nn = 3, 4, 2
+    M = rng.standard_normal((nk, nn, nb, nb)) + 1j * rng.standard_normal((nk, nn, nb, nb))
+    kpb = rng.integers(0, nk, size=(nk, nn))
+    G = rng.integers(-1, 2, size=(nk, nn, 3))
+    order = [(k, b) for b in range(nn) for k in range(nk)]        # b-major: NOT grouped by k-point
+    lines = ["generated by the test", f"  {nb}  {nk}  {nn}"]
+    for k, b in order:
+        lines.append(f"  {k + 1}  {kpb[k, b] + 1}  {G[k, b, 0]}  {G[k, b, 1]}  {G[k, b, 2]}")
+        for l in range(nb):
+            for m in range(nb):
+                z = M[k, b, m, l]
+                re = f"{z.real:.17e}".replace("e", "D") if (l + m) % 2 else f"{z.real:+.17e}"
+                lines.append(f"  {re}   {z.imag:.17e}")
+        lines.append("")                                            # blank lines are skipped
+    path = tmp_path / "t.mmn"
+    path.write_text("\n".join(lines) + "\n")
+    for nthreads in (1, 2, 3, 7, 0):
+        Mc, kk, GG = w.lib.read_mmn_native(str(path), nthreads)
+        assert np.array_equal(Mc.transpose(0, 1, 3, 2), M) and np.array_equal(kk, kpb) and np.array_equal(GG, G)
+    M2, k2, G2 = w.io_w90.read_mmn(str(path))
+    assert np.array_equal(M2, M)
+    # .amn / .eig
+    nw = 2
+    A = rng.standard_normal((nk, nb, nw)) + 1j * rng.standard_normal((nk, nb, nw))
+    al = ["amn", f"{nb} {nk} {nw}"] + [f"{m + 1} {n + 1} {k + 1} {A[k, m, n].real:.17e} {A[k, m, n].imag:.17e}"
+                                        for k in range(nk) for n in range(nw) for m in range(nb)]
+    (tmp_path / "t.amn").write_text("\n".join(al) + "\n")
+    assert np.array_equal(w.io_w90.read_amn(str(tmp_path / "t.amn")), A)
+    E = rng.standard_normal((nk, nb))
+    (tmp_path / "t.eig").write_text("\n".join(f"{m + 1} {k + 1} {E[k, m]:.17e}" for k in range(nk) for m in range(nb)) + "\n")
+    assert np.array_equal(w.io_w90.read_eig(str(tmp_path / "t.eig")), E)
+    # truncated file, malformed number, missing file
+    (tmp_path / "short.mmn").write_text("\n".join(lines[:20]) + "\n")
+    with pytest.raises(w.WB200Error, match="ends before"):
+        w.lib.read_mmn_native(str(tmp_path / "short.mmn"))
+    bad = list(lines); bad[5] = "  0.1  abc"
+    (tmp_path / "bad.mmn").write_text("\n".join(bad) + "\n")
+    with pytest.raises(w.WB200Error, match="malformed"):
+        w.lib.read_mmn_native(str(tmp_path / "bad.mmn"))
+    with pytest.raises(w.WB200Error, match="cannot open"):
+        w.lib.read_mmn_native(str(tmp_path / "nope.mmn"))

@@ -69,48 +69,27 @@ def read_win(path):
 def read_mmn(path):
     """(M[k, b, m, l], kpb_k[k, b] 0-based, kpb_G[k, b, 3]).  After the header `nb nk nn` every pair
     is a line `ik ikpb G1 G2 G3` (1-based) followed by nb*nb lines `re im`, m fastest; the order
-    of appearance of the pairs of a k-point defines b."""
-    with open(path) as f:
-        f.readline()
-        nb, nk, nn = (int(x) for x in f.readline().split())
-        body = f.read().split()
-    per = 5 + 2 * nb * nb
-    tok = np.asarray(body[:per * nk * nn]).reshape(nk * nn, per)
-    head = tok[:, :5].astype(np.int64)
-    vals = tok[:, 5:].astype(np.float64).reshape(nk * nn, nb, nb, 2)        # [pair][l][m][re/im]
-    M = np.zeros((nk, nn, nb, nb), dtype=np.complex128)
-    kpb_k = np.zeros((nk, nn), dtype=np.int32)
-    kpb_G = np.zeros((nk, nn, 3), dtype=np.int32)
-    seen = np.zeros(nk, dtype=np.int64)
-    for p in range(nk * nn):
-        ik = head[p, 0] - 1
-        ib = seen[ik]
-        seen[ik] += 1
-        kpb_k[ik, ib] = head[p, 1] - 1
-        kpb_G[ik, ib] = head[p, 2:5]
-        M[ik, ib] = (vals[p, :, :, 0] + 1j * vals[p, :, :, 1]).T
-    if not (seen == nn).all():
-        raise ValueError("mmn: every k-point must have the same number of neighbours")
-    return M, kpb_k, kpb_G
+    of appearance of the pairs of a k-point defines b.  Parsed by the native multithreaded reader
+    (wb200_mmn_read), which fills the C-ABI image [k][b][l][m]; the view returned here is M[k, b, m, l]."""
+    Mc, kpb_k, kpb_G = _lib.read_mmn_native(path)
+    return Mc.transpose(0, 1, 3, 2), kpb_k, kpb_G
 
 
 def read_amn(path):
-    """A[k, m, n] from lines `m n ik re im` (1-based)."""
-    with open(path) as f:
-        f.readline()
-        nb, nk, nw = (int(x) for x in f.readline().split())
-        d = np.loadtxt(f, ndmin=2)
-    A = np.zeros((nk, nb, nw), dtype=np.complex128)
-    A[d[:, 2].astype(int) - 1, d[:, 0].astype(int) - 1, d[:, 1].astype(int) - 1] = d[:, 3] + 1j * d[:, 4]
-    return A
+    """A[k, m, n] from lines `m n ik re im` (1-based); native reader (wb200_amn_read)."""
+    return _lib.read_amn_native(path).transpose(0, 2, 1)
 
 
-def read_eig(path):
-    """E[k, m] from lines `m ik eps`."""
-    d = np.loadtxt(path, ndmin=2)
-    E = np.zeros((int(d[:, 1].max()), int(d[:, 0].max())))
-    E[d[:, 1].astype(int) - 1, d[:, 0].astype(int) - 1] = d[:, 2]
-    return E
+def read_eig(path, nb=None, nk=None):
+    """E[k, m] from lines `m ik eps`; native reader (wb200_eig_read).  Without nb / nk the sizes are taken
+    from the last line (Wannier90 writes m fastest, k slowest)."""
+    if nb is None or nk is None:
+        with open(path, "rb") as f:
+            f.seek(0, 2)
+            f.seek(max(0, f.tell() - 256))
+            last = [l for l in f.read().decode().splitlines() if l.strip()][-1].split()
+        nb, nk = int(last[0]), int(last[1])
+    return _lib.read_eig_native(path, nb, nk)
 
 
 def compute_bweights(bvectors, atol=1e-6, sigma_atol=1e-5):
@@ -177,6 +156,7 @@ def read_w90(prefix, ortho_amn=True, device=0):
     if nk != len(win["kpoints"]) or nb != win["num_bands"]:
         raise ValueError("win and mmn disagree on the number of k-points / bands")
     recip = 2.0 * np.pi * np.linalg.inv(win["lattice"]).T
+    M = np.ascontiguousarray(M)     # (Cache re-lays it out for the C-ABI; the native reader's image is a view)
     st = _api.KspaceStencil(recip, win["kpoints"], np.ones(nn), kpb_k, kpb_G)
     st.bweights = compute_bweights(st.bvectors_cart()[0])
     A = read_amn(prefix + ".amn")

@@ -31,6 +31,8 @@ SYMBOLS = [
     "wb200_multi_fg", "wb200_multi_spread", "wb200_multi_fg_xy", "wb200_multi_max_localize",
     "wb200_multi_disentangle",
     "wb200_u_to_xy", "wb200_orthonorm_freeze", "wb200_create_stiefel",
+    "wb200_mmn_header", "wb200_mmn_read", "wb200_amn_header", "wb200_amn_read", "wb200_eig_read",
+    "wb200_io_last_error",
     "wb200_mag_create", "wb200_mag_destroy", "wb200_mag_last_error", "wb200_mag_overlap",
     "wb200_mag_omega_updn_grad", "wb200_mag_fg_xy", "wb200_mag_disentangle",
 ]
@@ -125,6 +127,13 @@ def load():
     lib.wb200_u_to_xy.argtypes = [vp, pd, pd]
     lib.wb200_orthonorm_freeze.argtypes = [vp, pd]
     lib.wb200_create_stiefel.argtypes = [C.POINTER(vp), i32, i32, i32, i32]
+    lib.wb200_mmn_header.argtypes = [C.c_char_p, pd, pd, pd]
+    lib.wb200_mmn_read.argtypes = [C.c_char_p, i32, i32, i32, pd, pd, pd, i32]
+    lib.wb200_amn_header.argtypes = [C.c_char_p, pd, pd, pd]
+    lib.wb200_amn_read.argtypes = [C.c_char_p, i32, i32, i32, pd]
+    lib.wb200_eig_read.argtypes = [C.c_char_p, i32, i32, pd]
+    lib.wb200_io_last_error.argtypes = []
+    lib.wb200_io_last_error.restype = C.c_char_p
     lib.wb200_mag_create.argtypes = [C.POINTER(vp), vp, vp, pd]
     lib.wb200_mag_destroy.argtypes = [vp]
     lib.wb200_mag_destroy.restype = None
@@ -141,7 +150,7 @@ def load():
         f = getattr(lib, name)
         if name not in ("wb200_destroy", "wb200_last_error", "wb200_version", "wb200_launch_count",
                         "wb200_multi_destroy", "wb200_multi_last_error", "wb200_multi_launch_count",
-                        "wb200_mag_destroy", "wb200_mag_last_error"):
+                        "wb200_mag_destroy", "wb200_mag_last_error", "wb200_io_last_error"):
             f.restype = i32
     _lib = lib
     return lib
@@ -597,6 +606,43 @@ class DeviceArray:
 
     def __init__(self, ptr, shape, typestr="<c16"):
         self.__cuda_array_interface__ = dict(shape=tuple(shape), typestr=typestr, data=(int(ptr), False), version=2)
+
+
+def _io_ck(lib, st):
+    if st != 0:
+        raise WB200Error(st, lib.wb200_io_last_error().decode())
+
+
+def read_mmn_native(path, nthreads=0):
+    """-> (M [nk][nn][nb(l)][nb(m)] in the C-ABI image, kpb_k [nk][nn] 0-based int32, kpb_G [nk][nn][3] int32)"""
+    lib = load()
+    nb, nk, nn = C.c_int(0), C.c_int(0), C.c_int(0)
+    bp = os.fsencode(path)
+    _io_ck(lib, lib.wb200_mmn_header(bp, C.addressof(nb), C.addressof(nk), C.addressof(nn)))
+    nb, nk, nn = nb.value, nk.value, nn.value
+    M = np.empty((nk, nn, nb, nb), dtype=np.complex128)
+    kpb_k = np.empty((nk, nn), dtype=np.int32)
+    kpb_G = np.empty((nk, nn, 3), dtype=np.int32)
+    _io_ck(lib, lib.wb200_mmn_read(bp, nb, nk, nn, _addr(M), _addr(kpb_k), _addr(kpb_G), nthreads))
+    return M, kpb_k, kpb_G
+
+
+def read_amn_native(path):
+    """-> A [nk][nw][nb] complex (C-ABI image)"""
+    lib = load()
+    nb, nk, nw = C.c_int(0), C.c_int(0), C.c_int(0)
+    bp = os.fsencode(path)
+    _io_ck(lib, lib.wb200_amn_header(bp, C.addressof(nb), C.addressof(nk), C.addressof(nw)))
+    A = np.empty((nk.value, nw.value, nb.value), dtype=np.complex128)
+    _io_ck(lib, lib.wb200_amn_read(bp, nb.value, nk.value, nw.value, _addr(A)))
+    return A
+
+
+def read_eig_native(path, nb, nk):
+    lib = load()
+    E = np.empty((nk, nb), dtype=np.float64)
+    _io_ck(lib, lib.wb200_eig_read(os.fsencode(path), nb, nk, _addr(E)))
+    return E
 
 
 class MagContext:
