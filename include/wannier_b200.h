@@ -305,6 +305,14 @@ int wb200_mag_fg_xy(wb200_mag* m, const double* XY, double lambda, double* f, do
 int wb200_mag_disentangle(wb200_mag* m, double* XY_inout, double lambda, double f_tol, double g_tol,
                           int max_iter, int history, double* f_final, int* iters, int* n_fg);
 
+/* ---- pinned host memory ----------------------------------------------------------------------------------------
+ * The host-pointer entry points (wb200_fg, wb200_multi_fg, ...) overlap PCIe copies with compute; that needs
+ * page-locked memory.  Julia `Array`s and numpy arrays are pageable: register the U / G / XY buffers that are
+ * reused across calls once (cudaHostRegister, portable across devices) and unregister them before they are freed.
+ * Registering twice / unregistering an unknown pointer is not an error.  Message: wb200_last_error(NULL).   */
+int wb200_host_register(void* ptr, size_t bytes);
+int wb200_host_unregister(void* ptr);
+
 /* ---- measurement helpers (bench.py) -------------------------------------------------------------
  * wb200_profile: when enabled, every launch of the four kernel classes below is bracketed by CUDA
  * events on the ctx's stream; wb200_profile_read synchronises, returns the summed milliseconds and

@@ -166,3 +166,23 @@ def test_native_ingest_edge_cases(w, tmp_path):
         w.lib.read_mmn_native(str(tmp_path / "bad.mmn"))
     with pytest.raises(w.WB200Error, match="cannot open"):
         w.lib.read_mmn_native(str(tmp_path / "nope.mmn"))
+
+
+def test_julia_wrapper_binds_only_exported_symbols(w):
+    """julia/WannierB200Ext.jl cannot be executed here (no Julia runtime): at least every symbol it `ccall`s must be
+    exported by the library, and the reference functions north_star names must each have a binding."""
+    import os, re, ctypes
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(root, "julia", "WannierB200Ext.jl")).read()
+    syms = set(re.findall(r"\(:(wb200_[a-z0-9_]+), LIB\)", src))
+    lib = ctypes.CDLL(w.lib.LIB_PATH)
+    for s in syms:
+        assert hasattr(lib, s), s
+    for needed in ("wb200_fg", "wb200_spread", "wb200_center", "wb200_max_localize", "wb200_disentangle",
+                   "wb200_rotate_overlaps", "wb200_opt_rotate", "wb200_position_op", "wb200_berry_connection",
+                   "wb200_omega_local", "wb200_u_to_xy", "wb200_multi_create", "wb200_multi_max_localize",
+                   "wb200_mag_disentangle", "wb200_host_register", "wb200_retract", "wb200_project_tangent"):
+        assert needed in syms, needed
+    for fn in ("omega(", "omega_grad(", "center(", "max_localize(", "disentangle(", "get_fg!_maxloc(", "transform_gauge(",
+               "compute_MU_UtMU!(", "omega!(", "omega_grad!(", "opt_rotate(", "position_op(", "U_to_X_Y("):
+        assert fn in src, fn

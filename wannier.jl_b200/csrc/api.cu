@@ -707,6 +707,24 @@ extern "C" int wb200_disentangle(wb200_ctx* ctx, double* XY, double f_tol, doubl
     return s;
 }
 
+// Page-lock a caller-owned host array (a Julia `Array`, a numpy array) so the host-pointer entry points
+// copy at full PCIe speed and truly asynchronously; pageable memory is staged by the driver at roughly
+// half the rate.  Thin wrappers so the caller needs no CUDA binding of its own.
+extern "C" int wb200_host_register(void* ptr, size_t bytes) {
+    if (!ptr || bytes == 0) return WB200_ERR_ARG;
+    const cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterPortable);
+    if (e == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); return WB200_OK; }
+    if (e != cudaSuccess) { g_create_error = std::string("cudaHostRegister: ") + cudaGetErrorString(e); cudaGetLastError(); return WB200_ERR_CUDA; }
+    return WB200_OK;
+}
+extern "C" int wb200_host_unregister(void* ptr) {
+    if (!ptr) return WB200_ERR_ARG;
+    const cudaError_t e = cudaHostUnregister(ptr);
+    if (e == cudaErrorHostMemoryNotRegistered) { cudaGetLastError(); return WB200_OK; }
+    if (e != cudaSuccess) { g_create_error = std::string("cudaHostUnregister: ") + cudaGetErrorString(e); cudaGetLastError(); return WB200_ERR_CUDA; }
+    return WB200_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // measurement helpers
 // ---------------------------------------------------------------------------------------------

@@ -33,6 +33,7 @@ SYMBOLS = [
     "wb200_u_to_xy", "wb200_orthonorm_freeze", "wb200_create_stiefel",
     "wb200_mmn_header", "wb200_mmn_read", "wb200_amn_header", "wb200_amn_read", "wb200_eig_read",
     "wb200_io_last_error",
+    "wb200_host_register", "wb200_host_unregister",
     "wb200_mag_create", "wb200_mag_destroy", "wb200_mag_last_error", "wb200_mag_overlap",
     "wb200_mag_omega_updn_grad", "wb200_mag_fg_xy", "wb200_mag_disentangle",
 ]
@@ -134,6 +135,8 @@ def load():
     lib.wb200_eig_read.argtypes = [C.c_char_p, i32, i32, pd]
     lib.wb200_io_last_error.argtypes = []
     lib.wb200_io_last_error.restype = C.c_char_p
+    lib.wb200_host_register.argtypes = [pd, C.c_size_t]
+    lib.wb200_host_unregister.argtypes = [pd]
     lib.wb200_mag_create.argtypes = [C.POINTER(vp), vp, vp, pd]
     lib.wb200_mag_destroy.argtypes = [vp]
     lib.wb200_mag_destroy.restype = None
@@ -606,6 +609,21 @@ class DeviceArray:
 
     def __init__(self, ptr, shape, typestr="<c16"):
         self.__cuda_array_interface__ = dict(shape=tuple(shape), typestr=typestr, data=(int(ptr), False), version=2)
+
+
+def host_register(a):
+    """page-lock a numpy array that is reused across host-pointer calls (cudaHostRegister)"""
+    lib = load()
+    st = lib.wb200_host_register(_addr(a), a.nbytes)
+    if st != 0:
+        raise WB200Error(st, lib.wb200_last_error(None).decode())
+
+
+def host_unregister(a):
+    lib = load()
+    st = lib.wb200_host_unregister(_addr(a))
+    if st != 0:
+        raise WB200Error(st, lib.wb200_last_error(None).decode())
 
 
 def _io_ck(lib, st):
