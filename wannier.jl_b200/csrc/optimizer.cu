@@ -36,6 +36,30 @@ int wb_fg_rotate_device(wb200_ctx* ctx, const cplx* dW, double* dres, cplx* dGW)
 
 namespace {
 
+// WB200_TRACE: wall-clock share of each phase of the driver (the stream is drained at the end of every scope,
+// so this mode is for attribution only, not for timing the driver)
+struct Trace {
+    bool on = getenv("WB200_TRACE") != nullptr;
+    double t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long n[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    static double now() {
+        timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts);
+        return ts.tv_sec + 1e-9 * ts.tv_nsec;
+    }
+    void report() const {
+        if (!on) return;
+        static const char* names[8] = {"retract", "fg (rotation, spread, gradient)", "project g", "inner product + sync",
+                                       "direction (lincomb)", "project s", "trial point (lincomb)", "secant + Gram refresh"};
+        for (int i = 0; i < 8; i++)
+            if (n[i]) fprintf(stderr, "[wb200] %-34s %6ld calls %9.3f ms total %8.3f ms each\n", names[i], n[i], 1e3 * t[i], 1e3 * t[i] / n[i]);
+    }
+};
+struct TraceScope {
+    Trace& tr; int id; cudaStream_t st; double t0 = 0.0;
+    TraceScope(Trace& t, int i, cudaStream_t s) : tr(t), id(i), st(s) { if (tr.on) { cudaStreamSynchronize(st); t0 = Trace::now(); } }
+    ~TraceScope() { if (tr.on) { cudaStreamSynchronize(st); tr.t[id] += Trace::now() - t0; tr.n[id]++; } }
+};
+
 // ---------------------------------------------------------------------------------------------
 // LineSearches.HagerZhang (Hager & Zhang, ACM TOMS 32 (2006), Algorithm 851) with the package
 // defaults; indices are 0-based.  phidphi(a, phi, dphi) returns a WB200 status.
@@ -207,6 +231,7 @@ struct Problem {
     size_t n;     // doubles per vector
     int n_fg = 0;
     const WbCustomProblem* custom = nullptr;   // mode 3
+    Trace trace;
 
     // tangent_step: x = x0 + a s with x0 on the manifold and s tangent at x0 (every trial point of a line search)
     int retract(cplx* x, bool tangent_step = false) {
@@ -225,6 +250,8 @@ struct Problem {
     // one synchronisation returns f, min |N_nn| and the inner product
     int fg(const cplx* x, double* f, cplx* g, const double* d, double* gd) {
         n_fg++;
+        {
+        TraceScope ts_(trace, 1, ctx->stream);
         if (mode == 3) {
             WB_TRY(custom->eval(x, g));
         } else if (mode == 0) {
@@ -236,11 +263,16 @@ struct Problem {
             WB_TRY(wb_fg_device(ctx, ctx->d_U, ctx->d_res, ctx->d_G, 0));
             WB_TRY(wb_gu_to_gxy(ctx, x, ctx->d_G, g));
         }
+        }
         WB_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned + 16, ctx->d_res + 5, sizeof(double),
                                      cudaMemcpyDeviceToHost, ctx->stream));
         WB_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned + 17, ctx->d_min, sizeof(double),
                                      cudaMemcpyDeviceToHost, ctx->stream));
-        WB_TRY(project(x, g));
+        {
+            TraceScope ts_(trace, 2, ctx->stream);
+            WB_TRY(project(x, g));
+        }
+        TraceScope ts_(trace, 3, ctx->stream);
         if (d) {
             WbCrossArgs c{};
             c.a[0] = (const double*)g; c.na = 1;
@@ -331,6 +363,7 @@ static int lbfgs_run(wb200_ctx* ctx, int mode, const WbCustomProblem* custom, cp
 
     // ---- initial_state: retract!, value_gradient!!, project_tangent! ----
     {
+        TraceScope ts_(P.trace, 0, ctx->stream);
         int st = P.retract(dx);
         if (st == WB200_ERR_NOCONV && ctx->allreduce) ctx->poison_next = 1;   // peers must see the failure too
         else WB_TRY(st);
@@ -376,6 +409,7 @@ static int lbfgs_run(wb200_ctx* ctx, int mode, const WbCustomProblem* custom, cp
             }
         }
         {   // s = -q in one pass (chunks of 7 vectors), then project_tangent!(s, x)
+            TraceScope ts_(P.trace, 4, ctx->stream);
             std::vector<int> used;
             for (int id = 0; id < nid; id++) if (c[id] != 0.0) used.push_back(id);
             if (used.empty()) used.push_back(0);
@@ -387,7 +421,10 @@ static int lbfgs_run(wb200_ctx* ctx, int mode, const WbCustomProblem* custom, cp
                 WB_TRY(wb_lincomb(ctx, l, s, n));
             }
         }
-        WB_TRY(P.project((const cplx*)x, (cplx*)s));
+        {
+            TraceScope ts_(P.trace, 5, ctx->stream);
+            WB_TRY(P.project((const cplx*)x, (cplx*)s));
+        }
         // ---- perform_linesearch! ----
         const double gg = GM[0];
         double dphi0 = 0.0;
@@ -412,10 +449,16 @@ static int lbfgs_run(wb200_ctx* ctx, int mode, const WbCustomProblem* custom, cp
         hz.phidphi = [&](double a, double& phi, double& dphi) -> int {
             WbLinArgs l{};
             l.v[0] = x; l.c[0] = 1.0; l.v[1] = s; l.c[1] = a; l.nv = 2;
-            WB_TRY(wb_lincomb(ctx, l, xn, n));
-            int st = P.retract((cplx*)xn, true);
-            if (st == WB200_ERR_NOCONV) ctx->poison_next = 1;   // this trial point is rejected on every rank
-            else WB_TRY(st);
+            {
+                TraceScope ts_(P.trace, 6, ctx->stream);
+                WB_TRY(wb_lincomb(ctx, l, xn, n));
+            }
+            {
+                TraceScope ts_(P.trace, 0, ctx->stream);
+                int st = P.retract((cplx*)xn, true);
+                if (st == WB200_ERR_NOCONV) ctx->poison_next = 1;   // this trial point is rejected on every rank
+                else WB_TRY(st);
+            }
             double fv = 0.0, dv = 0.0;
             WB_TRY(P.fg((cplx*)xn, &fv, (cplx*)gn, s, &dv));
             phi = fv; dphi = dv;
@@ -448,6 +491,7 @@ static int lbfgs_run(wb200_ctx* ctx, int mode, const WbCustomProblem* custom, cp
         int sl;
         if (free_slots.empty()) { sl = slots.front(); slots.pop_front(); }
         else { sl = free_slots.back(); free_slots.pop_back(); }
+        TraceScope ts_secant(P.trace, 7, ctx->stream);
         WB_TRY(wb_secant(ctx, alpha, s, gn, g, DX(sl), DG(sl), n));
         std::swap(x, xn);   // x <- accepted point, g <- its projected gradient (the old ones become the trial buffers)
         std::swap(g, gn);
@@ -473,6 +517,7 @@ static int lbfgs_run(wb200_ctx* ctx, int mode, const WbCustomProblem* custom, cp
     if (x != (double*)dx)
         WB_CUDA(ctx, cudaMemcpyAsync(dx, x, sizeof(double) * n, cudaMemcpyDeviceToDevice, ctx->stream));
     WB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    P.trace.report();
     if (f_final) *f_final = f;
     if (iters_out) *iters_out = it;
     if (n_fg_out) *n_fg_out = P.n_fg;

@@ -252,6 +252,11 @@ static int retract_strided(wb200_ctx* ctx, cplx* dX, int nrow, int ncol, int ld,
         }
     }
     if (iters_out) *iters_out = it;
+    {
+        static const bool trace = getenv("WB200_TRACE") != nullptr;
+        if (trace) fprintf(stderr, "[wb200] retract %d x %d x %d: %d iterations, tangent_step %d, scaled %d, final err %.2e\n",
+                           nrow, ncol, count, it, (int)tangent_step, (int)scaled, err);
+    }
     if (err >= TOL) {
         ctx->err = "retract: Newton-Schulz polar iteration did not converge (||X^H X - I||_F = " +
                    std::to_string(err) + ")";
