@@ -219,6 +219,9 @@ def main():
     ap.add_argument("--config", default="cfg4_nw128")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-peer-flags", action="store_true",
+                    help="N > 1, --halo peer: open every evaluation with a one-element all-reduce instead of the "
+                         "point-to-point readiness flags in peer memory")
     ap.add_argument("--halo", default="peer", choices=["peer", "nccl"],
                     help="N > 1: read neighbour gauges from peer memory inside the pack kernel (CUDA IPC "
                          "over NVLink) or exchange them with an NCCL all-to-all / send-recv first")
@@ -303,14 +306,11 @@ def main():
         # every rank keeps the FULL gauge array in an IPC-shareable allocation and owns its slab rows;
         # the other ranks map it and their pack kernels read the rows they need over NVLink
         try:
-            my_ptr, my_handle = w.lib.ipc_alloc(local_rank, 16 * nk * nb * nw)
-            handles = [None] * world
-            dist.all_gather_object(handles, my_handle)
-            peer_ptrs = [my_ptr if r == rank else w.lib.ipc_open(local_rank, handles[r]) for r in range(world)]
-            Ushared = torch.as_tensor(w.lib.DeviceArray(my_ptr, (nk, nw, nb)), device=dev)
+            shared = w.sharding.SharedGauges(ctx, dist, local_rank, rank, world, nk, nb, nw, bounds,
+                                             flags=not args.no_peer_flags)
+            Ushared = torch.as_tensor(w.lib.DeviceArray(shared.ptr, (nk, nw, nb)), device=dev)
             Ushared.fill_(complex(float("nan"), float("nan")))      # rows of other ranks are never valid here
             Ushared[k0:k1].copy_(dU[k0:k1])
-            ctx.set_peer_gauges(peer_ptrs, bounds)
             dU = Ushared
             ok = torch.ones(1, device=dev)
         except Exception as e:                                        # CUDA IPC unavailable
@@ -323,6 +323,7 @@ def main():
         torch.cuda.synchronize()
         dist.barrier()
 
+    peer_flags = halo == "peer" and not args.no_peer_flags
     breakdown = os.environ.get("WB_BENCH_BREAKDOWN") == "1" and world > 1
     bd_events = []
 
@@ -331,7 +332,8 @@ def main():
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
             ev[0].record(stream)
             if halo == "peer":
-                dist.all_reduce(ready)
+                if not peer_flags:
+                    dist.all_reduce(ready)
             else:
                 plan.exchange(dU, dist)
             ev[1].record(stream)
@@ -348,7 +350,8 @@ def main():
             # reductions play that role), then phase 1 reads neighbour rows from peer memory inside
             # its pack kernel.  halo = nccl: explicit exchange of the neighbour rows first.
             if halo == "peer":
-                dist.all_reduce(ready)
+                if not peer_flags:
+                    dist.all_reduce(ready)     # with flags phase 1 publishes / waits neighbour to neighbour itself
             else:
                 plan.exchange(dU, dist)
             ctx.fg_phase1_dev(dU.data_ptr(), dsums.data_ptr())
@@ -463,7 +466,8 @@ def main():
     except Exception:
         traffic = {}
     rot_ms, rot_n = prof["rotate"]
-    rot_ms_avg = rot_ms / max(rot_n, 1)
+    # per evaluation: one launch, or two when the halo split rotates local- and remote-neighbour pairs separately
+    rot_ms_avg = rot_ms / args.steps
     # rotation kernel: one complex GEMM per pair of the rank's slab
     rot_flops = 8.0 * nkl * nn * nb * nb * nw
     tensor = ctx.rotation_kernel == "dmma-fp64"
@@ -495,7 +499,10 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": dict(config, n_bvectors=nn, rotation_kernel=ctx.rotation_kernel,
-                           parallelism=f"k-slab x{world}", halo=halo, halo_k_per_rank=plan.n_halo, omega_check=omega_val,
+                           parallelism=f"k-slab x{world}", halo=halo, halo_k_per_rank=plan.n_halo,
+                           halo_overlap=(os.environ.get("WB200_HALO_SPLIT", "1") != "0") if halo == "peer" else None,
+                           ready_sync=("peer flags" if peer_flags else "all-reduce") if halo == "peer" else None,
+                           omega_check=omega_val,
                            g_check=g_check),
             "e2e": e2e, "gpu_launches": int(launches), "clocks": cs.summary(), "roofline": roof}
 

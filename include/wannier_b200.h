@@ -188,6 +188,20 @@ int wb200_ipc_open(int device, const unsigned char handle[64], void** dptr);
 int wb200_ipc_close(int device, void* dptr);
 int wb200_ipc_free(int device, void* dptr);
 int wb200_set_peer_gauges(wb200_ctx* ctx, int world, const void* const* U_ptrs, const int32_t* bounds);
+/* Halo overlap.  Once peer gauges are set, phase 1 of the tensor path (32 < nb <= 256) splits the neighbours
+ * of every k-point into those whose gauge the rank owns and those a peer owns: the peer rows are fetched
+ * over NVLink and packed by a few fat CTAs on a second, high-priority stream WHILE the main stream packs the
+ * local rows and rotates the local-neighbour pairs; the remote-neighbour pairs follow.  dU passed to
+ * wb200_fg_phase1_dev must then be U_ptrs[rank].  WB200_HALO_SPLIT=0 (environment, read here) keeps the
+ * one-pass packing.
+ * wb200_set_peer_flags: point-to-point readiness flags instead of the "rows are in place" all-reduce in front
+ * of an evaluation.  flag_ptrs[q] = rank q's flag array (`world` 64-bit words, zeroed by the caller before the
+ * first evaluation), mapped like the gauge arrays.  Phase 1 then stores the rank's evaluation counter into
+ * every peer's array (remote stores) and the halo stream waits for the counters of the ranks it reads from;
+ * no collective precedes the rotation.  Every rank must make the same sequence of evaluations and a collective
+ * (the all-reduce of the sums) must separate consecutive evaluations.  One slab per device only (a spinning
+ * wait kernel must never share a hardware queue with the signal it waits for).  NULL removes the flags.   */
+int wb200_set_peer_flags(wb200_ctx* ctx, int world, void* const* flag_ptrs);
 
 /* ---- sharded optimiser: caller-supplied collective ------------------------------------------------
  * With one process per GPU the library does not own a communicator.  The host registers a callback

@@ -37,11 +37,8 @@ def _worker(rank, world, port, case, out):
         ctx = w.Context(nb, nw, nk, nn, st["kpb_k"][k0:k1], st["bvec"][k0:k1], st["wb"],
                         w.api.to_abi_M(M[k0:k1]), device=rank, k_begin=k0, nk=k1 - k0)
         ctx.set_stream(torch.cuda.current_stream().cuda_stream)
-        ptr, handle = w.lib.ipc_alloc(rank, 16 * nk * nb * nw)
-        handles = [None] * world
-        dist.all_gather_object(handles, handle)
-        ptrs = [ptr if r == rank else w.lib.ipc_open(rank, handles[r]) for r in range(world)]
-        ctx.set_peer_gauges(ptrs, bounds)
+        # every other case with point-to-point readiness flags, the rest with the one-element all-reduce
+        shared = w.sharding.SharedGauges(ctx, dist, rank, rank, world, nk, nb, nw, bounds, flags=(nb != 16))
         ctx.set_allreduce(w.sharding.torch_allreduce(dist, dev))
         if len(case) > 3:      # disentangle: (X, Y) slab, frozen bands of the slab
             from oracle import spread_oracle as so
@@ -57,13 +54,8 @@ def _worker(rank, world, port, case, out):
         dist.barrier()
         out[rank] = (f, it, nfg, Uslab.copy())
         ctx.set_allreduce(None)
-        ctx.set_peer_gauges(None, None)
+        shared.close()
         ctx.close()
-        for r in range(world):
-            if r != rank:
-                w.lib.ipc_close(rank, ptrs[r])
-        dist.barrier()
-        w.lib.ipc_free(rank, ptr)
     finally:
         dist.destroy_process_group()
 

@@ -35,13 +35,10 @@ del M
 torch.cuda.empty_cache()
 ctx.set_stream(torch.cuda.current_stream().cuda_stream)
 Uslab0 = w.synthetic.make_gauge_torch(nk, nb, nw, dev)[k0:k1].cpu().numpy().copy()
-ptrs = None
+shared = None
 if world > 1:
-    ptr, handle = w.lib.ipc_alloc(local, 16 * nk * nb * nw)
-    handles = [None] * world
-    dist.all_gather_object(handles, handle)
-    ptrs = [ptr if r == rank else w.lib.ipc_open(local, handles[r]) for r in range(world)]
-    ctx.set_peer_gauges(ptrs, bounds)
+    shared = w.sharding.SharedGauges(ctx, dist, local, rank, world, nk, nb, nw, bounds,
+                                     flags=os.environ.get("WB200_PEER_FLAGS", "1") != "0")
     ctx.set_allreduce(w.sharding.torch_allreduce(dist, dev))
 
 res = []
@@ -62,12 +59,7 @@ if rank == 0:
                           note="includes H2D of the U slab and D2H of the result")), flush=True)
 if world > 1:
     ctx.set_allreduce(None)
-    ctx.set_peer_gauges(None, None)
+    shared.close()
 ctx.close()
 if world > 1:
-    for r in range(world):
-        if r != rank:
-            w.lib.ipc_close(local, ptrs[r])
-    dist.barrier()
-    w.lib.ipc_free(local, ptrs[rank])
     dist.destroy_process_group()

@@ -17,7 +17,11 @@ extern "C" void wb200_destroy(wb200_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     wb_dmma_plan_destroy(ctx);
-    void* ptrs[] = {(void*)ctx->d_peerU, ctx->d_need_owner, ctx->d_need, ctx->d_kpb, ctx->d_kself, ctx->d_bvec, ctx->d_wb, ctx->d_M, ctx->d_r0,
+    if (ctx->halo_stream) cudaStreamDestroy(ctx->halo_stream);
+    if (ctx->ev_rows) cudaEventDestroy(ctx->ev_rows);
+    if (ctx->ev_halo) cudaEventDestroy(ctx->ev_halo);
+    void* ptrs[] = {(void*)ctx->d_flag_ptrs, ctx->d_need_split, ctx->d_owner_split, ctx->d_border, ctx->d_nloc,
+                    (void*)ctx->d_peerU, ctx->d_need_owner, ctx->d_need, ctx->d_kpb, ctx->d_kself, ctx->d_bvec, ctx->d_wb, ctx->d_M, ctx->d_r0,
                     ctx->d_frozen, ctx->d_nfrozen, ctx->d_U, ctx->d_G, ctx->d_MU, ctx->d_N,
                     ctx->d_dN, ctx->d_fro, ctx->d_part, ctx->d_pmin, ctx->d_sums, ctx->d_res,
                     ctx->d_min, ctx->d_scal, ctx->d_red, ctx->d_zpart, ctx->d_tmp1, ctx->d_tmp2, ctx->d_XY, ctx->d_GXY};
@@ -211,9 +215,77 @@ static int rotate(wb200_ctx* ctx, const cplx* dU) {
     return rotate_range(ctx, dU, 0, ctx->nk);
 }
 
+// ---- "my rows are in place" without a collective (wb200_set_peer_flags) ----
+namespace {
+// one thread per peer: publish this rank's epoch in the peer's flag array (a remote store over NVLink)
+__global__ void flag_signal_kernel(int world, int rank, unsigned long long* const* __restrict__ flags,
+                                   unsigned long long epoch) {
+    const int q = threadIdx.x;
+    if (q >= world || q == rank) return;
+    __threadfence_system();
+    *(volatile unsigned long long*)(flags[q] + rank) = epoch;
+}
+// one thread per peer this slab reads from: spin on the LOCAL flag word until that peer has published
+// `epoch`.  Bounded (~20 s): a peer that died must not hang the device.
+__global__ void flag_wait_kernel(int world, unsigned mask, const unsigned long long* my_flags, unsigned long long epoch) {
+    const int q = threadIdx.x;
+    if (q >= world || !((mask >> q) & 1u)) return;
+    const volatile unsigned long long* f = my_flags + q;
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    while (*f < epoch) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        if (t - t0 > 20000000000ull) __trap();
+        __nanosleep(200);
+    }
+    __threadfence_system();
+}
+}  // namespace
+
+// publish (on ctx->stream, after whatever wrote the rows) and wait (on `on`) for the owners of the halo rows
+static int flags_signal_wait(wb200_ctx* ctx, cudaStream_t on) {
+    ctx->epoch++;
+    flag_signal_kernel<<<1, 32, 0, ctx->stream>>>(ctx->peer_world, ctx->peer_rank, ctx->d_flag_ptrs, ctx->epoch);
+    WB_LAUNCH_CHECK(ctx);
+    flag_wait_kernel<<<1, 32, 0, on>>>(ctx->peer_world, ctx->peer_mask, ctx->my_flags, ctx->epoch);
+    WB_LAUNCH_CHECK(ctx);
+    return WB200_OK;
+}
+
 extern "C" int wb200_fg_phase1_dev(wb200_ctx* ctx, const double* dU, double* dsums, int exact_split) {
     if (!ctx || !dU || !dsums) return WB200_ERR_ARG;
     cudaSetDevice(ctx->device);
+    if (ctx->d_peerU && ctx->peer_self && (const cplx*)dU != ctx->peer_self) {
+        // the pack kernel reads every row, own rows included, through the peer table, while the epilogue of the
+        // rotation reads U_k from dU: two different arrays would be mixed silently
+        ctx->err = "wb200_fg_phase1_dev: with peer gauges set, dU must be this rank's shared gauge array (U_ptrs[rank])";
+        return WB200_ERR_ARG;
+    }
+    const bool split = ctx->halo_split && ctx->d_peerU && !exact_split && ctx->n_need_local < ctx->n_need &&
+                       wb_dmma_phases_supported(ctx);
+    if (split) {
+        // Rows peers own are fetched over NVLink and packed on a second stream while the main stream packs the
+        // local rows and rotates every pair whose neighbour is local; the remaining pairs follow once the
+        // halo has landed.  The U_k tiles of the epilogue are always local.
+        if (ctx->d_flag_ptrs) {
+            WB_CUDA(ctx, cudaEventRecord(ctx->ev_rows, ctx->stream));   // WAR on Up: the previous evaluation's rotation
+            WB_CUDA(ctx, cudaStreamWaitEvent(ctx->halo_stream, ctx->ev_rows, 0));
+            WB_TRY(flags_signal_wait(ctx, ctx->halo_stream));
+        } else {
+            WB_CUDA(ctx, cudaEventRecord(ctx->ev_rows, ctx->stream));
+            WB_CUDA(ctx, cudaStreamWaitEvent(ctx->halo_stream, ctx->ev_rows, 0));
+        }
+        WB_TRY(wb_pack_dmma_split(ctx, (const cplx*)dU, ctx->n_need_local, ctx->n_need, true));
+        WB_CUDA(ctx, cudaEventRecord(ctx->ev_halo, ctx->halo_stream));
+        WB_TRY(wb_pack_dmma_split(ctx, (const cplx*)dU, 0, ctx->n_need_local, false));
+        WB_TRY(wb_rotate_dmma(ctx, (const cplx*)dU, 0, ctx->nk, 1));
+        WB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_halo, 0));
+        WB_TRY(wb_rotate_dmma(ctx, (const cplx*)dU, 0, ctx->nk, 2));
+        WB_TRY(wb_pair_reduce(ctx, dsums));
+        return WB200_OK;
+    }
+    if (ctx->d_peerU && ctx->d_flag_ptrs) WB_TRY(flags_signal_wait(ctx, ctx->stream));
     // with peer gauges the tensor path reads remote rows inside its pack kernel; every other
     // consumer (CUDA-core rotation, exact N) reads dU[k+b] directly, so fetch the halo rows first
     if (ctx->d_peerU && (!ctx->dmma || exact_split)) WB_TRY(wb_halo_fetch(ctx, (cplx*)dU));
@@ -259,8 +331,10 @@ int wb_fg_device(wb200_ctx* ctx, const cplx* dU, double* dres, cplx* dG, int exa
         if (dU != rows)
             WB_CUDA(ctx, cudaMemcpyAsync(rows, dU, sizeof(cplx) * mat * ctx->nk, cudaMemcpyDeviceToDevice,
                                          ctx->stream));
-        WB_CUDA(ctx, cudaMemsetAsync(ctx->d_scal + 2, 0, sizeof(double), ctx->stream));
-        WB_TRY(wb_allreduce(ctx, ctx->d_scal + 2, 1, 0));
+        if (!ctx->d_flag_ptrs) {   // with peer flags phase 1 itself publishes and waits, neighbour to neighbour
+            WB_CUDA(ctx, cudaMemsetAsync(ctx->d_scal + 2, 0, sizeof(double), ctx->stream));
+            WB_TRY(wb_allreduce(ctx, ctx->d_scal + 2, 1, 0));
+        }
         WB_TRY(wb200_fg_phase1_dev(ctx, (const double*)ctx->peer_self, ctx->d_sums, exact_split));
         WB_TRY(poison_sums(ctx));
         WB_TRY(wb_allreduce(ctx, ctx->d_sums, ctx->nsums(), 0));
@@ -850,30 +924,108 @@ extern "C" int wb200_set_peer_gauges(wb200_ctx* ctx, int world, const void* cons
                                      const int32_t* bounds) {
     if (!ctx) return WB200_ERR_ARG;
     cudaSetDevice(ctx->device);
-    if (ctx->d_peerU) { cudaFree((void*)ctx->d_peerU); ctx->d_peerU = nullptr; }
-    if (ctx->d_need_owner) { cudaFree(ctx->d_need_owner); ctx->d_need_owner = nullptr; }
+    WB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->halo_stream) WB_CUDA(ctx, cudaStreamSynchronize(ctx->halo_stream));
+    void** owned[] = {(void**)&ctx->d_peerU, (void**)&ctx->d_need_owner, (void**)&ctx->d_need_split, (void**)&ctx->d_owner_split,
+                      (void**)&ctx->d_border, (void**)&ctx->d_nloc, (void**)&ctx->d_flag_ptrs};
+    for (void** p : owned)
+        if (*p) { cudaFree(*p); *p = nullptr; }
     ctx->peer_world = 0;
     ctx->peer_self = nullptr;
     ctx->peer_rank = -1;
+    ctx->my_flags = nullptr;
+    ctx->peer_mask = 0;
+    ctx->halo_split = 0;
     if (world <= 0 || !U_ptrs) return WB200_OK;   // back to purely local reads
     if (!bounds || bounds[0] != 0 || bounds[world] != ctx->nk_total) {
         ctx->err = "wb200_set_peer_gauges: bounds must run from 0 to nk_total";
         return WB200_ERR_ARG;
     }
+    int rank = 0;
+    while (rank + 1 < world && ctx->k_begin >= bounds[rank + 1]) rank++;
     std::vector<int32_t> owner(ctx->n_need);
     for (int i = 0; i < ctx->n_need; i++) {
         int r = 0;
         while (r + 1 < world && ctx->h_need[i] >= bounds[r + 1]) r++;
         owner[i] = r;
     }
+    // split lists: the rows this rank owns first, then the rows read from peers
+    std::vector<int32_t> need_s, owner_s;
+    for (int pass = 0; pass < 2; pass++) {
+        for (int i = 0; i < ctx->n_need; i++)
+            if ((owner[i] == rank) == (pass == 0)) {
+                need_s.push_back(ctx->h_need[i]);
+                owner_s.push_back(owner[i]);
+                if (pass == 1 && owner[i] < 32) ctx->peer_mask |= 1u << owner[i];
+            }
+        if (pass == 0) ctx->n_need_local = (int)need_s.size();
+    }
+    // per-k neighbour order: neighbours whose gauge is local first
+    const int nn = ctx->nn;
+    std::vector<uint8_t> border((size_t)ctx->nk * nn), nloc(ctx->nk);
+    for (int k = 0; k < ctx->nk; k++) {
+        int nl = 0;
+        for (int pass = 0; pass < 2; pass++)
+            for (int b = 0, at = nl; b < nn; b++) {
+                const int kp = ctx->h_kpb[(size_t)k * nn + b];
+                const bool local = kp >= bounds[rank] && kp < bounds[rank + 1];
+                if (local == (pass == 0)) {
+                    border[(size_t)k * nn + (pass == 0 ? nl++ : at++)] = (uint8_t)b;
+                }
+            }
+        nloc[k] = (uint8_t)nl;
+    }
     WB_CUDA(ctx, cudaMalloc((void**)&ctx->d_peerU, sizeof(void*) * world));
     WB_CUDA(ctx, cudaMalloc(&ctx->d_need_owner, sizeof(int32_t) * ctx->n_need));
+    WB_CUDA(ctx, cudaMalloc(&ctx->d_need_split, sizeof(int32_t) * ctx->n_need));
+    WB_CUDA(ctx, cudaMalloc(&ctx->d_owner_split, sizeof(int32_t) * ctx->n_need));
     WB_CUDA(ctx, cudaMemcpy((void*)ctx->d_peerU, U_ptrs, sizeof(void*) * world, cudaMemcpyHostToDevice));
     WB_CUDA(ctx, cudaMemcpy(ctx->d_need_owner, owner.data(), sizeof(int32_t) * ctx->n_need, cudaMemcpyHostToDevice));
+    WB_CUDA(ctx, cudaMemcpy(ctx->d_need_split, need_s.data(), sizeof(int32_t) * ctx->n_need, cudaMemcpyHostToDevice));
+    WB_CUDA(ctx, cudaMemcpy(ctx->d_owner_split, owner_s.data(), sizeof(int32_t) * ctx->n_need, cudaMemcpyHostToDevice));
+    if (nn > 0 && nn < 256) {
+        WB_CUDA(ctx, cudaMalloc(&ctx->d_border, border.size()));
+        WB_CUDA(ctx, cudaMalloc(&ctx->d_nloc, nloc.size()));
+        WB_CUDA(ctx, cudaMemcpy(ctx->d_border, border.data(), border.size(), cudaMemcpyHostToDevice));
+        WB_CUDA(ctx, cudaMemcpy(ctx->d_nloc, nloc.data(), nloc.size(), cudaMemcpyHostToDevice));
+        if (!ctx->halo_stream) {
+            int lo = 0, hi = 0;
+            cudaDeviceGetStreamPriorityRange(&lo, &hi);   // hi = numerically lowest = greatest priority
+            WB_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->halo_stream, cudaStreamNonBlocking, hi));
+            WB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_rows, cudaEventDisableTiming));
+            WB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_halo, cudaEventDisableTiming));
+        }
+        const char* e = getenv("WB200_HALO_SPLIT");
+        ctx->halo_split = !(e && e[0] == '0');
+    }
     ctx->peer_world = world;
-    ctx->peer_rank = 0;
-    while (ctx->peer_rank + 1 < world && ctx->k_begin >= bounds[ctx->peer_rank + 1]) ctx->peer_rank++;
-    ctx->peer_self = (cplx*)U_ptrs[ctx->peer_rank];
+    ctx->peer_rank = rank;
+    ctx->peer_self = (cplx*)U_ptrs[rank];
+    return WB200_OK;
+}
+
+// Point-to-point readiness flags.  flag_ptrs[q] is rank q's flag array (`world` 64-bit words, zeroed by the
+// caller before any rank evaluates), mapped into this process / device like the gauge arrays.  With flags in
+// place an evaluation no longer opens with a one-element all-reduce ("every rank has written its rows"): phase 1
+// stores this rank's evaluation counter into every peer's array and waits, on the stream that fetches the
+// halo, until the owners of the rows it reads have published the same counter.  Every rank must make the same
+// sequence of evaluations, and a collective (the all-reduce of the sums) must separate two evaluations — both
+// hold for every driver in this library.  Must follow wb200_set_peer_gauges; NULL removes the flags.
+extern "C" int wb200_set_peer_flags(wb200_ctx* ctx, int world, void* const* flag_ptrs) {
+    if (!ctx) return WB200_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    WB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->d_flag_ptrs) { cudaFree((void*)ctx->d_flag_ptrs); ctx->d_flag_ptrs = nullptr; }
+    ctx->my_flags = nullptr;
+    ctx->epoch = 0;
+    if (!flag_ptrs || world <= 0) return WB200_OK;
+    if (world != ctx->peer_world || world > 32) {
+        ctx->err = "wb200_set_peer_flags: call wb200_set_peer_gauges first, with the same world size (at most 32)";
+        return WB200_ERR_ARG;
+    }
+    WB_CUDA(ctx, cudaMalloc((void**)&ctx->d_flag_ptrs, sizeof(void*) * world));
+    WB_CUDA(ctx, cudaMemcpy((void*)ctx->d_flag_ptrs, flag_ptrs, sizeof(void*) * world, cudaMemcpyHostToDevice));
+    ctx->my_flags = (unsigned long long*)flag_ptrs[ctx->peer_rank];
     return WB200_OK;
 }
 

@@ -95,6 +95,21 @@ struct wb200_ctx {
     int peer_world = 0;
     int peer_rank = -1;
     cplx* peer_self = nullptr;        // this rank's full gauge array (U_ptrs[rank])
+    // halo split (set up with the peer gauges): need list reordered local rows first, per-k neighbour order
+    // with the local neighbours first, and the second stream the peer-memory half of the packing runs on
+    int32_t* d_need_split = nullptr;  // [n_need] local rows, then remote rows
+    int32_t* d_owner_split = nullptr; // [n_need]
+    int n_need_local = 0;
+    uint8_t* d_border = nullptr;      // [nk][nn] neighbour indices, local ones first
+    uint8_t* d_nloc = nullptr;        // [nk] number of local neighbours
+    int halo_split = 0;               // 1: phase 1 overlaps the halo packing with the local-neighbour rotation
+    cudaStream_t halo_stream = nullptr;
+    cudaEvent_t ev_rows = nullptr, ev_halo = nullptr;
+    // point-to-point "my rows are in place" flags in peer memory (wb200_set_peer_flags) instead of a collective
+    unsigned long long** d_flag_ptrs = nullptr;   // [world] device array: rank q's flag array (world words)
+    unsigned long long* my_flags = nullptr;       // flag_ptrs[rank]
+    unsigned long long epoch = 0;
+    unsigned peer_mask = 0;                       // ranks owning rows this slab reads
     wb200_allreduce_fn allreduce = nullptr;   // caller-supplied collective (sharded optimiser)
     void* allreduce_user = nullptr;
     int poison_next = 0;   // the next evaluation's sums are replaced by NaN before they are reduced (a
@@ -266,7 +281,10 @@ int wb_axpby(wb200_ctx* ctx, double alpha, const double* x, double beta, double*
 int wb_dmma_plan_create(wb200_ctx* ctx, const double* hM);   // may leave ctx->dmma == nullptr if not applicable
 void wb_dmma_plan_destroy(wb200_ctx* ctx);
 int wb_pack_dmma(wb200_ctx* ctx, const cplx* dU, int ja, int jb);     // pack need[ja:jb) of the gauge
-int wb_rotate_dmma(wb200_ctx* ctx, const cplx* dU, int ka, int kb);   // MU, dN, fro(=||MU||^2) of local k in [ka, kb)
+// MU, dN, fro(=||MU||^2) of local k in [ka, kb); phase 1 / 2: only the pairs whose neighbour is local / remote
+int wb_rotate_dmma(wb200_ctx* ctx, const cplx* dU, int ka, int kb, int phase = 0);
+bool wb_dmma_phases_supported(const wb200_ctx* ctx);
+int wb_pack_dmma_split(wb200_ctx* ctx, const cplx* dU, int ja, int jb, bool halo);
 
 bool wb_zgemm_dmma_applicable(const wb200_ctx* ctx, int nrow, int ncol);
 int wb_zgemm_dmma(wb200_ctx* ctx, int transA, const cplx* A, const cplx* B, cplx* C, int count);   // C = op(A) B, n x n

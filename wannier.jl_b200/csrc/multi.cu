@@ -57,6 +57,7 @@ struct wb200_multi {
     std::vector<int> devices, bounds;
     std::vector<wb200_ctx*> ctx;
     std::vector<cplx*> Ufull;            // per slab: [nk][nw][nb] on its device; the slab owns its rows
+    std::vector<void*> flags;            // per slab: readiness-flag words (distinct devices only)
     HostBarrier bar;
     int maxc = 0;
     double* h_x[2] = {nullptr, nullptr};   // pinned [parity][slab][maxc]: contributions
@@ -144,6 +145,10 @@ extern "C" void wb200_multi_destroy(wb200_multi* m) {
             cudaSetDevice(m->devices[r]);
             cudaFree(m->Ufull[r]);
         }
+        if (r < (int)m->flags.size() && m->flags[r]) {
+            cudaSetDevice(m->devices[r]);
+            cudaFree(m->flags[r]);
+        }
     }
     for (int p = 0; p < 2; p++) {
         if (m->h_x[p]) cudaFreeHost(m->h_x[p]);
@@ -203,11 +208,24 @@ extern "C" int wb200_multi_create(wb200_multi** out, const int* devices, int nde
         if (cudaMallocHost(&m->h_x[p], sizeof(double) * (size_t)ndev * m->maxc) != cudaSuccess ||
             cudaMallocHost(&m->h_r[p], sizeof(double) * (size_t)ndev * m->maxc) != cudaSuccess)
             return fail(WB200_ERR_CUDA, "wb200_multi_create: cudaMallocHost failed");
+    // point-to-point readiness flags replace the "rows are in place" reduction when every slab has its own
+    // device (two slabs of one device could share a hardware queue: a spinning wait in front of its signal)
+    bool distinct = ndev <= 32;
+    for (int r = 0; r < ndev; r++)
+        for (int q = 0; q < r; q++) distinct = distinct && devices[r] != devices[q];
+    { const char* e = getenv("WB200_PEER_FLAGS"); if (e && e[0] == '0') distinct = false; }
+    m->flags.assign(ndev, nullptr);
+    if (distinct && ndev > 1)
+        for (int r = 0; r < ndev; r++)
+            if (cudaSetDevice(devices[r]) != cudaSuccess || cudaMalloc(&m->flags[r], 8 * (size_t)ndev) != cudaSuccess ||
+                cudaMemset(m->flags[r], 0, 8 * (size_t)ndev) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess)
+                return fail(WB200_ERR_CUDA, "wb200_multi_create: cudaMalloc of the readiness flags failed");
     std::vector<const void*> ptrs(ndev);
     for (int r = 0; r < ndev; r++) ptrs[r] = m->Ufull[r];
     for (int r = 0; r < ndev; r++) {
         m->users[r] = {m, r};
         int s = wb200_set_peer_gauges(m->ctx[r], ndev, ptrs.data(), m->bounds.data());
+        if (s == WB200_OK && distinct && ndev > 1) s = wb200_set_peer_flags(m->ctx[r], ndev, m->flags.data());
         if (s == WB200_OK) s = wb200_set_allreduce(m->ctx[r], multi_allreduce, &m->users[r]);
         if (s != WB200_OK) return fail(s, "wb200_multi_create: " + m->ctx[r]->err);
     }

@@ -144,21 +144,13 @@ __global__ void tile_overlaps_kernel(int nb, int WM, int KC, int nch, const cplx
 }
 // B-operand image of U.  Chunk c = [wn][ks][j(3)][lane] double2; the 6 doubles of a lane are
 //   (Br, Bi-Br, Br+Bi) of nt = 0..1 with l = c*KC + ks*4 + lane%4, n = ct*NC + wn*16 + nt*8 + lane/4.
-__global__ void __launch_bounds__(256) pack_gauge_kernel(int nb, int nw, int WN, int KC, int nch, int nct,
-                                                         const int32_t* __restrict__ need,
-                                                         const int32_t* __restrict__ owner,
-                                                         const cplx* const* __restrict__ peerU,
-                                                         const cplx* __restrict__ U,
-                                                         double* __restrict__ Up) {
-    const long long kg = need ? need[blockIdx.x] : blockIdx.x;   // only the k-points this slab reads
-    // k-sharded runs: a row another rank owns is read straight from that rank's memory over NVLink
-    // (peer-mapped pointer) — the halo exchange is fused into the packing
-    if (peerU) U = peerU[owner[blockIdx.x]];
-    const int ct = blockIdx.y;
+__device__ __forceinline__ void pack_gauge_row(int nb, int nw, int WN, int KC, int nch, int nct, long long kg, int ct,
+                                               const cplx* __restrict__ U, double* __restrict__ Up) {
     const int KS = KC / 4;
     const int items = WN * KS * 32;              // per chunk
     const cplx* src = U + kg * (long long)nb * nw;
     double* dst0 = Up + ((kg * nct + ct) * nch) * (long long)(items * 6);
+#pragma unroll 2
     for (int oo = threadIdx.x; oo < items * nch; oo += blockDim.x) {
         const int c = oo / items, o = oo - c * items;
         const int lane = o & 31, ks = (o >> 5) % KS, wn = (o >> 5) / KS;
@@ -178,6 +170,33 @@ __global__ void __launch_bounds__(256) pack_gauge_kernel(int nb, int nw, int WN,
         for (int j = 0; j < 3; j++) d2[j * 32] = make_double2(q[2 * j], q[2 * j + 1]);
     }
 }
+__global__ void __launch_bounds__(256) pack_gauge_kernel(int nb, int nw, int WN, int KC, int nch, int nct,
+                                                         const int32_t* __restrict__ need,
+                                                         const int32_t* __restrict__ owner,
+                                                         const cplx* const* __restrict__ peerU,
+                                                         const cplx* __restrict__ U,
+                                                         double* __restrict__ Up) {
+    const long long kg = need ? need[blockIdx.x] : blockIdx.x;   // only the k-points this slab reads
+    // k-sharded runs: a row another rank owns is read straight from that rank's memory over NVLink
+    // (peer-mapped pointer) — the halo exchange is fused into the packing
+    if (peerU) U = peerU[owner[blockIdx.x]];
+    pack_gauge_row(nb, nw, WN, KC, nch, nct, kg, blockIdx.y, U, Up);
+}
+// The halo half of the packing (rows other ranks own) runs on a second stream UNDER the rotation of the pairs
+// whose neighbour is local, so it must leave the SMs to the rotation kernel (one 384-thread CTA owns a whole
+// SM's register file): a few fat CTAs walk the (row, column tile) items instead of one small CTA per item, which
+// the block scheduler would spread over every SM.  The link, not the SM count, bounds it: 32 CTAs x 1024
+// threads x 2 x 32 B keep ~2 MB in flight.
+__global__ void __launch_bounds__(1024) pack_gauge_halo_kernel(int nb, int nw, int WN, int KC, int nch, int nct, int nrows,
+                                                               const int32_t* __restrict__ need,
+                                                               const int32_t* __restrict__ owner,
+                                                               const cplx* const* __restrict__ peerU,
+                                                               double* __restrict__ Up) {
+    for (int item = blockIdx.x; item < nrows * nct; item += gridDim.x) {
+        const int row = item / nct, ct = item - row * nct;
+        pack_gauge_row(nb, nw, WN, KC, nch, nct, need[row], ct, peerU[owner[row]], Up);
+    }
+}
 
 // ---- the rotation kernel ---------------------------------------------------------------------
 template <int WM, int WN, int KC, int STAGES>
@@ -185,7 +204,8 @@ __global__ void __launch_bounds__(384, 1)
 rotate_dmma_kernel(int nb, int nw, int nn, int nch, int nct, int k_begin, int k_off,
                    const int32_t* __restrict__ kpb, const double* __restrict__ Mt,
                    const double* __restrict__ Up, const cplx* __restrict__ U,
-                   cplx* __restrict__ MU, cplx* __restrict__ dNp, double* __restrict__ frop) {
+                   cplx* __restrict__ MU, cplx* __restrict__ dNp, double* __restrict__ frop,
+                   const uint8_t* __restrict__ border, const uint8_t* __restrict__ nloc, int phase) {
     constexpr int KS = KC / 4;
     constexpr int NC = 16 * WN;
     constexpr int A_D2 = WM * KS * 6 * 32;   // double2 per A stage
@@ -198,6 +218,7 @@ rotate_dmma_kernel(int nb, int nw, int nn, int nch, int nct, int k_begin, int k_
     cplx* sB = sA + STAGES * A_D2;                                     // [STAGES][B_D2]
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(sB + STAGES * B_D2);
     // bars[0..STAGES) full, bars[STAGES..2 STAGES) empty
+    int* sPair = reinterpret_cast<int*>(bars + 2 * STAGES);   // [nn <= 255] pair index of the b-th neighbour this CTA rotates
 
 #ifdef WB_TIMING
     const long long t_cta0 = clock64();
@@ -206,14 +227,24 @@ rotate_dmma_kernel(int nb, int nw, int nn, int nch, int nct, int k_begin, int k_
     const uint32_t bar_base = smem_u32(bars), sA_base = smem_u32(sA), sB_base = smem_u32(sB);
     const int kl = blockIdx.x / nct + k_off, ct = blockIdx.x % nct;
     const int n0 = ct * NC;
-    const int total = nn * nch;  // chunks streamed by this CTA
+    // k-sharded runs split the neighbours of a k-point into those whose gauge this rank owns and those read
+    // from a peer: `border` lists the local ones first, phase 1 rotates the first nloc[kl] pairs (while the
+    // halo rows are still being fetched and packed on another stream), phase 2 the rest.  phase 0: all, in order.
+    int b_lo = 0, b_cnt = nn;
+    if (phase) {
+        const int nl = nloc[kl];
+        if (phase == 1) b_cnt = nl; else { b_lo = nl; b_cnt = nn - nl; }
+        if (b_cnt == 0) return;   // uniform over the CTA, before any barrier
+        border += (long long)kl * nn + b_lo;
+    }
+    const int total = b_cnt * nch;  // chunks streamed by this CTA
 
     // producer state (only meaningful in warp 8 lane 0)
     auto produce = [&](int i) {
         const int s = i % STAGES;
         const uint32_t round = (uint32_t)(i / STAGES);
-        const int b = i / nch, c = i - b * nch;
-        const long long pair = (long long)kl * nn + b;
+        const int bi = i / nch, c = i - bi * nch;
+        const long long pair = (long long)kl * nn + (phase ? (int)border[bi] : bi);
         const long long kp = kpb[pair];
         mbar_wait(bar_base + 8u * (STAGES + s), (round & 1u) ^ 1u);
         const uint32_t full = bar_base + 8u * s;
@@ -244,6 +275,7 @@ rotate_dmma_kernel(int nb, int nw, int nn, int nch, int nct, int k_begin, int k_
             for (int i = 0; i < npre; i++) produce(i);   // prime the ring while the CTA sets up
         }
     } else {
+        if (tid < b_cnt) sPair[tid] = kl * nn + (phase ? (int)border[tid] : tid);
         const cplx* Uk = U + (long long)(k_begin + kl) * nb * nw;
 #pragma unroll
         for (int e = 0; e < 16; e++) {
@@ -418,7 +450,7 @@ rotate_dmma_kernel(int nb, int nw, int nn, int nch, int nct, int k_begin, int k_
     // a pipe slot only every ~10 cycles.  Staggering the slices of the two warps of an SMSP, or
     // skewing the warps by whole chunks, was tried and is slower: the warps drift apart and stall on
     // the 5-stage ring.)
-    for (int b = 0; b < nn; b++) {
+    for (int b = 0; b < b_cnt; b++) {
         // first EPI_CHUNKS chunks of the pair carry the deferred epilogue of the previous pair
         if (b > 0) {
 #pragma unroll
@@ -433,7 +465,7 @@ rotate_dmma_kernel(int nb, int nw, int nn, int nch, int nct, int k_begin, int k_
 #pragma unroll 1
         for (int c = EPI_CHUNKS; c < nch; c++) chunk(c, false);
         WB_T0
-        epi_begin((long long)kl * nn + b);
+        epi_begin(sPair[b]);
         WB_T1(t_epi)
     }
     {   // the last pair has no successor to hide under
@@ -817,11 +849,11 @@ template <int WM, int WN, int KC, int STAGES>
 size_t smem_bytes() {
     constexpr int KS = KC / 4;
     return sizeof(cplx) * (8 * 16 * 32 + (size_t)STAGES * (WM * KS * 6 * 32 + WN * KS * 3 * 32)) +
-           sizeof(unsigned long long) * 2 * STAGES;
+           sizeof(unsigned long long) * 2 * STAGES + sizeof(int) * 256;
 }
 
 template <int WM, int WN, int KC, int STAGES>
-int launch_rotate(wb200_ctx* ctx, const cplx* dU, int ka, int kb, const RotateOverride* ov = nullptr) {
+int launch_rotate(wb200_ctx* ctx, const cplx* dU, int ka, int kb, const RotateOverride* ov = nullptr, int phase = 0) {
     DmmaPlan* p = ctx->dmma;
     auto kern = rotate_dmma_kernel<WM, WN, KC, STAGES>;
     static bool attr_done[16] = {false};
@@ -831,11 +863,12 @@ int launch_rotate(wb200_ctx* ctx, const cplx* dU, int ka, int kb, const RotateOv
     }
     if (ov)   // batched-GEMM use: one "pair" per matrix, neighbour table = identity
         kern<<<(kb - ka) * p->nct, 384, p->smem, ctx->stream>>>(ctx->nb, ctx->nw, 1, p->nch, p->nct, 0, ka, ov->iota,
-                                                              ov->At, ov->Bp, dU, ov->C, ov->dNp, ov->frop);
+                                                              ov->At, ov->Bp, dU, ov->C, ov->dNp, ov->frop, nullptr, nullptr, 0);
     else
         kern<<<(kb - ka) * p->nct, 384, p->smem, ctx->stream>>>(ctx->nb, ctx->nw, ctx->nn, p->nch, p->nct,
                                                               ctx->k_begin, ka, ctx->d_kpb, p->d_Mt, p->d_Up,
-                                                              dU, ctx->d_MU, p->d_dNp, p->d_frop);
+                                                              dU, ctx->d_MU, p->d_dNp, p->d_frop, ctx->d_border, ctx->d_nloc,
+                                                              phase);
     WB_LAUNCH_CHECK(ctx);
     return WB200_OK;
 }
@@ -850,7 +883,7 @@ int launch_rotate(wb200_ctx* ctx, const cplx* dU, int ka, int kb, const RotateOv
 
 int wb_dmma_plan_create(wb200_ctx* ctx, const double* /*hM*/) {
     const int nb = ctx->nb, nw = ctx->nw;
-    if (nb > 256 || (nb <= 32 && nw > 32)) return WB200_OK;  // CUDA-core path
+    if (nb > 256 || (nb <= 32 && nw > 32) || ctx->nn > 255) return WB200_OK;  // CUDA-core path
     DmmaPlan* p = new DmmaPlan();
     if (nb <= 32) {
         p->small = true; p->WM = 1; p->WN = 2; p->KC = 32; p->smem = 0;
@@ -913,7 +946,31 @@ int wb_pack_dmma(wb200_ctx* ctx, const cplx* dU, int ja, int jb) {
     return WB200_OK;
 }
 
-int wb_rotate_dmma(wb200_ctx* ctx, const cplx* dU, int ka, int kb) {
+// the halo split (api.cu) applies to the three CTA-per-(k, column tile) kernels
+bool wb_dmma_phases_supported(const wb200_ctx* ctx) { return ctx->dmma && !ctx->dmma->small; }
+
+// rows [ja, jb) of the split need list (local rows first, then the rows peers own).  halo = true: the fat-CTA
+// kernel on ctx->halo_stream (rows come from peer memory), otherwise the plain kernel on ctx->stream.
+int wb_pack_dmma_split(wb200_ctx* ctx, const cplx* dU, int ja, int jb, bool halo) {
+    DmmaPlan* p = ctx->dmma;
+    if (jb <= ja) return WB200_OK;
+    if (halo) {
+        const int items = (jb - ja) * p->nct;
+        const int grid = items < 32 ? items : 32;
+        pack_gauge_halo_kernel<<<grid, 1024, 0, ctx->halo_stream>>>(ctx->nb, ctx->nw, p->WN, p->KC, p->nch, p->nct, jb - ja,
+                                                                   ctx->d_need_split + ja, ctx->d_owner_split + ja,
+                                                                   ctx->d_peerU, p->d_Up);
+    } else {
+        dim3 g((unsigned)(jb - ja), (unsigned)p->nct);
+        ProfScope ps(ctx, 0);
+        pack_gauge_kernel<<<g, 256, 0, ctx->stream>>>(ctx->nb, ctx->nw, p->WN, p->KC, p->nch, p->nct, ctx->d_need_split + ja,
+                                                      ctx->d_owner_split + ja, ctx->d_peerU, dU, p->d_Up);
+    }
+    WB_LAUNCH_CHECK(ctx);
+    return WB200_OK;
+}
+
+int wb_rotate_dmma(wb200_ctx* ctx, const cplx* dU, int ka, int kb, int phase) {
     DmmaPlan* p = ctx->dmma;
     ctx->fro_src = nullptr;
     if (p->small) {
@@ -953,10 +1010,11 @@ int wb_rotate_dmma(wb200_ctx* ctx, const cplx* dU, int ka, int kb) {
     }
     {
         ProfScope ps(ctx, 1);
-        if (p->WM == 2) WB_TRY((launch_rotate<WB_CFG_64>(ctx, dU, ka, kb)));
-        else if (p->WM == 4) WB_TRY((launch_rotate<WB_CFG_128>(ctx, dU, ka, kb)));
-        else WB_TRY((launch_rotate<WB_CFG_256>(ctx, dU, ka, kb)));
+        if (p->WM == 2) WB_TRY((launch_rotate<WB_CFG_64>(ctx, dU, ka, kb, nullptr, phase)));
+        else if (p->WM == 4) WB_TRY((launch_rotate<WB_CFG_128>(ctx, dU, ka, kb, nullptr, phase)));
+        else WB_TRY((launch_rotate<WB_CFG_256>(ctx, dU, ka, kb, nullptr, phase)));
     }
+    if (phase == 1) return WB200_OK;   // the partials are combined once both phases have run
     ProfScope ps2(ctx, 2);
     combine_partials_kernel<<<(kb - ka) * ctx->nn, 128, 0, ctx->stream>>>(
         ctx->nw, p->WM, p->nct * 8, (long long)ka * ctx->nn, p->d_dNp, p->d_frop, ctx->d_dN, ctx->d_fro);

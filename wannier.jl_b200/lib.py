@@ -26,6 +26,7 @@ SYMBOLS = [
     "wb200_omega_local", "wb200_fg_rotate", "wb200_opt_rotate", "wb200_position_op", "wb200_berry_connection",
     "wb200_set_allreduce",
     "wb200_ipc_alloc", "wb200_ipc_open", "wb200_ipc_close", "wb200_ipc_free", "wb200_set_peer_gauges",
+    "wb200_set_peer_flags",
     "wb200_multi_create", "wb200_multi_destroy", "wb200_multi_last_error", "wb200_multi_ndev",
     "wb200_multi_slab_begin", "wb200_multi_launch_count", "wb200_multi_set_penalty", "wb200_multi_set_frozen",
     "wb200_multi_fg", "wb200_multi_spread", "wb200_multi_fg_xy", "wb200_multi_max_localize",
@@ -109,6 +110,7 @@ def load():
     lib.wb200_ipc_close.argtypes = [i32, vp]
     lib.wb200_ipc_free.argtypes = [i32, vp]
     lib.wb200_set_peer_gauges.argtypes = [vp, i32, pd, pd]
+    lib.wb200_set_peer_flags.argtypes = [vp, i32, pd]
     lib.wb200_multi_create.argtypes = [C.POINTER(vp), pd, i32, i32, i32, i32, i32, pd, pd, pd, pd, C.c_uint]
     lib.wb200_multi_destroy.argtypes = [vp]
     lib.wb200_multi_destroy.restype = None
@@ -268,6 +270,15 @@ class Context:
         p = np.asarray(ptrs, dtype=np.uint64)
         b = np.ascontiguousarray(bounds, dtype=np.int32)
         self._ck(self._lib.wb200_set_peer_gauges(self._h, len(p), _addr(p), _addr(b)))
+
+    def set_peer_flags(self, ptrs):
+        """ptrs[r]: device address of rank r's readiness-flag array (world uint64, zeroed) as mapped on this
+        device; None removes the flags.  Replaces the "rows are in place" all-reduce in front of an evaluation."""
+        if ptrs is None:
+            self._ck(self._lib.wb200_set_peer_flags(self._h, 0, None))
+            return
+        p = np.asarray(ptrs, dtype=np.uint64)
+        self._ck(self._lib.wb200_set_peer_flags(self._h, len(p), _addr(p)))
 
     def set_allreduce(self, fn):
         """fn(dptr: int, count: int, op: int (0 sum, 1 max), stream: int) all-reduces `count` doubles

@@ -100,6 +100,48 @@ class HaloPlan:
         flat.index_copy_(0, ri, recv)
 
 
+class SharedGauges:
+    """Peer-memory plumbing of a one-process-per-GPU run: every rank allocates the FULL gauge array (and a
+    small readiness-flag array) in CUDA-IPC shareable memory, the handles travel through torch.distributed,
+    every rank maps its peers' allocations and hands the pointer tables to its slab context
+    (wb200_set_peer_gauges / wb200_set_peer_flags).  `ptr` is this rank's array; `close()` unmaps and frees."""
+
+    def __init__(self, ctx, dist, device_index, rank, world, nk, nb, nw, bounds, flags=True):
+        from . import lib
+        self._lib, self.ctx, self.dist = lib, ctx, dist
+        self.device, self.rank, self.world = device_index, rank, world
+        self.ptr, handle = lib.ipc_alloc(device_index, 16 * nk * nb * nw)
+        self.flag_ptr, fhandle = lib.ipc_alloc(device_index, 8 * max(world, 32)) if flags else (None, None)
+        handles = [None] * world
+        dist.all_gather_object(handles, (handle, fhandle))
+        self.ptrs = [self.ptr if r == rank else lib.ipc_open(device_index, handles[r][0]) for r in range(world)]
+        ctx.set_peer_gauges(self.ptrs, bounds)
+        self.flag_ptrs = None
+        if flags:
+            import torch
+            torch.as_tensor(lib.DeviceArray(self.flag_ptr, (max(world, 32),), "<i8"),
+                            device=torch.device("cuda", device_index)).zero_()
+            torch.cuda.synchronize()
+            dist.barrier()                       # every flag array is zero before anyone can signal
+            self.flag_ptrs = [self.flag_ptr if r == rank else lib.ipc_open(device_index, handles[r][1])
+                              for r in range(world)]
+            ctx.set_peer_flags(self.flag_ptrs)
+
+    def close(self):
+        lib = self._lib
+        self.ctx.set_peer_flags(None)
+        self.ctx.set_peer_gauges(None, None)
+        for r in range(self.world):
+            if r != self.rank:
+                lib.ipc_close(self.device, self.ptrs[r])
+                if self.flag_ptrs:
+                    lib.ipc_close(self.device, self.flag_ptrs[r])
+        self.dist.barrier()
+        lib.ipc_free(self.device, self.ptr)
+        if self.flag_ptr:
+            lib.ipc_free(self.device, self.flag_ptr)
+
+
 def torch_allreduce(dist, device):
     """The callback wb200_set_allreduce wants, on top of torch.distributed (NCCL): wraps the raw
     device pointer as a tensor and reduces it in place on torch's current stream (the stream the
