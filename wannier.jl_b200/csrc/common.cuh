@@ -137,6 +137,8 @@ struct wb200_ctx {
     double* d_fro = nullptr; // [nk][nn]          ||N||_F^2 (or ||MU||_F^2)
     const double* fro_src = nullptr;  // where pair_reduce finds ||.||^2: nullptr = d_fro, else partials
     int fro_parts = 1;
+    const cplx* dn_src = nullptr;     // diag N left as partials by the rotation (summed by pair_reduce); nullptr = d_dN is final
+    int dn_parts = 1;
     double* d_part = nullptr;   // [nk][nsums]
     double* d_pmin = nullptr;   // [nk]
     double* d_sums = nullptr;   // [nsums]

@@ -194,6 +194,7 @@ int wb_rotate_generic(wb200_ctx* ctx, const cplx* dU, int ka, int kb) {
     a.alpha = 1.0; a.beta = 0.0; a.batch = pairs; a.transA = 0; a.transB = 0;
     ProfScope ps(ctx, 1);
     ctx->fro_src = nullptr;
+    ctx->dn_src = nullptr;
     WB_TRY(wb_zgemm(ctx, a));     // nb > 256 lands here: tensor pipe from the plain layout of M
     diag_kernel<<<pairs, 256, 0, ctx->stream>>>(nb, nw, dU, ctx->d_kself + p0, ctx->d_MU + p0 * nb * nw,
                                                  ctx->d_dN + p0 * nw, ctx->d_fro + p0);
@@ -237,7 +238,8 @@ int wb_form_N(wb200_ctx* ctx, const cplx* dU) {
 //   4nw: sum_b w_b ||N||_F^2       4nw+1: sum_b w_b sum_n |N_nn|^2
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) pair_reduce_kernel(int nw, int nn, int nk, int k_off,
-                                                          const cplx* __restrict__ dN,
+                                                          cplx* __restrict__ dN,
+                                                          const cplx* __restrict__ dNp, int ndn,
                                                           const double* __restrict__ fro, int nfro,
                                                           const double* __restrict__ bvec,
                                                           const double* __restrict__ wb,
@@ -249,7 +251,16 @@ __global__ void __launch_bounds__(128) pair_reduce_kernel(int nw, int nn, int nk
     extern __shared__ double sphi[];            // [nn][nw] phi, then [nn][nw] |N_nn|^2
     double* sa2 = sphi + nn * nw;
     for (int i = threadIdx.x; i < nn * nw; i += blockDim.x) {
-        const cplx z = dN[(long long)k * nn * nw + i];
+        cplx z;
+        if (dNp) {   // the tensor rotation leaves diag N as per-warp-row partials: sum them in fixed order, keep the result
+            const int b = i / nw, n = i - b * nw;
+            const cplx* pp = dNp + (((long long)k * nn + b) * ndn) * nw + n;
+            z = make_double2(0.0, 0.0);
+            for (int w = 0; w < ndn; w++) { z.x += pp[(long long)w * nw].x; z.y += pp[(long long)w * nw].y; }
+            dN[(long long)k * nn * nw + i] = z;
+        } else {
+            z = dN[(long long)k * nn * nw + i];
+        }
         sphi[i] = atan2(z.y, z.x);              // imaglog, src/utils/linalg.jl:15
         sa2[i] = z.x * z.x + z.y * z.y;
     }
@@ -341,7 +352,7 @@ int wb_pair_partial(wb200_ctx* ctx, int ka, int kb) {
             return WB200_ERR_ARG;
         }
     }
-    pair_reduce_kernel<<<kb - ka, 128, smem, ctx->stream>>>(ctx->nw, ctx->nn, ctx->nk, ka, ctx->d_dN,
+    pair_reduce_kernel<<<kb - ka, 128, smem, ctx->stream>>>(ctx->nw, ctx->nn, ctx->nk, ka, ctx->d_dN, ctx->dn_src, ctx->dn_parts,
                                                           ctx->fro_src ? ctx->fro_src : ctx->d_fro, ctx->fro_src ? ctx->fro_parts : 1,
                                                           ctx->d_bvec, ctx->d_wb,
                                                           ctx->d_part, ctx->d_pmin);

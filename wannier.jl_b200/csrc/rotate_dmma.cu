@@ -24,7 +24,7 @@
 //     warps 0-7 are consumers: warp tile 32 x 16 complex = 4 x 2 DMMA tiles x (P1, P2, P3).
 //   * U_k's column tile stays in shared memory (accumulator-fragment order) for the whole CTA, so
 //     the epilogue of every pair is registers + LDS only; per-warp partial diagonals go straight
-//     to global (summed in fixed order by combine_partials_kernel) — no CTA-wide barrier anywhere
+//     to global (summed in fixed order by pair_reduce_kernel) — no CTA-wide barrier anywhere
 //     in the main loop, and results are bitwise deterministic.
 #include "common.cuh"
 
@@ -818,29 +818,6 @@ rotate_small_ring_kernel(int nb, int nw, int nn, long long pair0, long long pair
     }
 }
 
-// dN[pair][n] = sum_wm dNp[pair][wm][n];  fro[pair] = sum frop[pair][:]   (fixed order)
-__global__ void __launch_bounds__(128) combine_partials_kernel(int nw, int WM, int nfro, long long pair_off,
-                                                               const cplx* __restrict__ dNp,
-                                                               const double* __restrict__ frop,
-                                                               cplx* __restrict__ dN,
-                                                               double* __restrict__ fro) {
-    const long long pair = blockIdx.x + pair_off;
-    for (int n = threadIdx.x; n < nw; n += blockDim.x) {
-        cplx s = make_double2(0.0, 0.0);
-        for (int w = 0; w < WM; w++) {
-            const cplx v = dNp[(pair * WM + w) * nw + n];
-            s.x += v.x;
-            s.y += v.y;
-        }
-        dN[pair * nw + n] = s;
-    }
-    if (threadIdx.x == 0) {
-        double f = 0.0;
-        for (int i = 0; i < nfro; i++) f += frop[pair * nfro + i];
-        fro[pair] = f;
-    }
-}
-
 struct RotateOverride {
     const int32_t* iota; const double* At; const double* Bp; cplx* C; cplx* dNp; double* frop;
 };
@@ -973,6 +950,7 @@ int wb_pack_dmma_split(wb200_ctx* ctx, const cplx* dU, int ja, int jb, bool halo
 int wb_rotate_dmma(wb200_ctx* ctx, const cplx* dU, int ka, int kb, int phase) {
     DmmaPlan* p = ctx->dmma;
     ctx->fro_src = nullptr;
+    ctx->dn_src = nullptr;
     if (p->small) {
         const long long p0 = (long long)ka * ctx->nn, p1 = (long long)kb * ctx->nn;
         {
@@ -1014,11 +992,9 @@ int wb_rotate_dmma(wb200_ctx* ctx, const cplx* dU, int ka, int kb, int phase) {
         else if (p->WM == 4) WB_TRY((launch_rotate<WB_CFG_128>(ctx, dU, ka, kb, nullptr, phase)));
         else WB_TRY((launch_rotate<WB_CFG_256>(ctx, dU, ka, kb, nullptr, phase)));
     }
-    if (phase == 1) return WB200_OK;   // the partials are combined once both phases have run
-    ProfScope ps2(ctx, 2);
-    combine_partials_kernel<<<(kb - ka) * ctx->nn, 128, 0, ctx->stream>>>(
-        ctx->nw, p->WM, p->nct * 8, (long long)ka * ctx->nn, p->d_dNp, p->d_frop, ctx->d_dN, ctx->d_fro);
-    WB_LAUNCH_CHECK(ctx);
+    // per-warp partial diagonals and norms are summed (fixed order) by pair_reduce_kernel itself
+    ctx->dn_src = p->d_dNp; ctx->dn_parts = p->WM;
+    ctx->fro_src = p->d_frop; ctx->fro_parts = p->nct * 8;
     return WB200_OK;
 }
 
