@@ -219,9 +219,10 @@ def main():
     ap.add_argument("--config", default="cfg4_nw128")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-peer-flags", action="store_true",
-                    help="N > 1, --halo peer: open every evaluation with a one-element all-reduce instead of the "
-                         "point-to-point readiness flags in peer memory")
+    ap.add_argument("--no-peer-comm", action="store_true",
+                    help="N > 1, --halo peer: the round-1 scheme — NCCL all-reduces (a one-element one in front of "
+                         "every evaluation, the sums) and peer rows packed straight from peer memory — instead of "
+                         "the library's own peer-memory flags / all-reduce / packed-halo pull")
     ap.add_argument("--halo", default="peer", choices=["peer", "nccl"],
                     help="N > 1: read neighbour gauges from peer memory inside the pack kernel (CUDA IPC "
                          "over NVLink) or exchange them with an NCCL all-to-all / send-recv first")
@@ -307,7 +308,7 @@ def main():
         # the other ranks map it and their pack kernels read the rows they need over NVLink
         try:
             shared = w.sharding.SharedGauges(ctx, dist, local_rank, rank, world, nk, nb, nw, bounds,
-                                             flags=not args.no_peer_flags)
+                                             comm=not args.no_peer_comm)
             Ushared = torch.as_tensor(w.lib.DeviceArray(shared.ptr, (nk, nw, nb)), device=dev)
             Ushared.fill_(complex(float("nan"), float("nan")))      # rows of other ranks are never valid here
             Ushared[k0:k1].copy_(dU[k0:k1])
@@ -323,7 +324,13 @@ def main():
         torch.cuda.synchronize()
         dist.barrier()
 
-    peer_flags = halo == "peer" and not args.no_peer_flags
+    peer_comm = halo == "peer" and not args.no_peer_comm
+
+    def reduce_sums():
+        if peer_comm:
+            ctx.peer_allreduce_dev(dsums.data_ptr(), ctx.nsums)     # one small kernel per rank over peer memory
+        else:
+            dist.all_reduce(dsums)
     breakdown = os.environ.get("WB_BENCH_BREAKDOWN") == "1" and world > 1
     bd_events = []
 
@@ -332,13 +339,13 @@ def main():
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
             ev[0].record(stream)
             if halo == "peer":
-                if not peer_flags:
+                if not peer_comm:
                     dist.all_reduce(ready)
             else:
                 plan.exchange(dU, dist)
             ev[1].record(stream)
             ctx.fg_phase1_dev(dU.data_ptr(), dsums.data_ptr()); ev[2].record(stream)
-            dist.all_reduce(dsums); ev[3].record(stream)
+            reduce_sums(); ev[3].record(stream)
             ctx.fg_phase2_dev(dsums.data_ptr(), dres.data_ptr(), dG.data_ptr()); ev[4].record(stream)
             bd_events.append(ev)
             return
@@ -350,12 +357,12 @@ def main():
             # reductions play that role), then phase 1 reads neighbour rows from peer memory inside
             # its pack kernel.  halo = nccl: explicit exchange of the neighbour rows first.
             if halo == "peer":
-                if not peer_flags:
-                    dist.all_reduce(ready)     # with flags phase 1 publishes / waits neighbour to neighbour itself
+                if not peer_comm:
+                    dist.all_reduce(ready)     # with comm buffers phase 1 publishes / waits neighbour to neighbour itself
             else:
                 plan.exchange(dU, dist)
             ctx.fg_phase1_dev(dU.data_ptr(), dsums.data_ptr())
-            dist.all_reduce(dsums)
+            reduce_sums()
             ctx.fg_phase2_dev(dsums.data_ptr(), dres.data_ptr(), dG.data_ptr())
 
     def barrier():
@@ -404,7 +411,7 @@ def main():
         hres = torch.empty(ctx.nres, dtype=torch.float64).pin_memory()
         hUn, hGn = hU.numpy(), hG.numpy()
 
-        if world > 1 and halo == "peer":
+        if world > 1 and halo == "peer" and not peer_comm:
             # the slab context itself takes host pointers: H2D of the slab's rows, "rows are in place"
             # reduction, phase 1 with peer-memory halo reads, all-reduce of the sums, phase 2 with the
             # gradient streamed back sub-slab by sub-slab behind grad_kernel (wb200_fg on a k-slab ctx)
@@ -501,7 +508,8 @@ def main():
             "config": dict(config, n_bvectors=nn, rotation_kernel=ctx.rotation_kernel,
                            parallelism=f"k-slab x{world}", halo=halo, halo_k_per_rank=plan.n_halo,
                            halo_overlap=(os.environ.get("WB200_HALO_SPLIT", "1") != "0") if halo == "peer" else None,
-                           ready_sync=("peer flags" if peer_flags else "all-reduce") if halo == "peer" else None,
+                           collectives=("peer memory (flags, packed-halo pull by copy engines, in-library all-reduce)" if peer_comm
+                                        else "NCCL all-reduce + pack from peer memory") if halo == "peer" else None,
                            omega_check=omega_val,
                            g_check=g_check),
             "e2e": e2e, "gpu_launches": int(launches), "clocks": cs.summary(), "roofline": roof}

@@ -188,20 +188,39 @@ int wb200_ipc_open(int device, const unsigned char handle[64], void** dptr);
 int wb200_ipc_close(int device, void* dptr);
 int wb200_ipc_free(int device, void* dptr);
 int wb200_set_peer_gauges(wb200_ctx* ctx, int world, const void* const* U_ptrs, const int32_t* bounds);
-/* Halo overlap.  Once peer gauges are set, phase 1 of the tensor path (32 < nb <= 256) splits the neighbours
- * of every k-point into those whose gauge the rank owns and those a peer owns: the peer rows are fetched
- * over NVLink and packed by a few fat CTAs on a second, high-priority stream WHILE the main stream packs the
- * local rows and rotates the local-neighbour pairs; the remote-neighbour pairs follow.  dU passed to
- * wb200_fg_phase1_dev must then be U_ptrs[rank].  WB200_HALO_SPLIT=0 (environment, read here) keeps the
- * one-pass packing.
- * wb200_set_peer_flags: point-to-point readiness flags instead of the "rows are in place" all-reduce in front
- * of an evaluation.  flag_ptrs[q] = rank q's flag array (`world` 64-bit words, zeroed by the caller before the
- * first evaluation), mapped like the gauge arrays.  Phase 1 then stores the rank's evaluation counter into
- * every peer's array (remote stores) and the halo stream waits for the counters of the ranks it reads from;
- * no collective precedes the rotation.  Every rank must make the same sequence of evaluations and a collective
- * (the all-reduce of the sums) must separate consecutive evaluations.  One slab per device only (a spinning
- * wait kernel must never share a hardware queue with the signal it waits for).  NULL removes the flags.   */
-int wb200_set_peer_flags(wb200_ctx* ctx, int world, void* const* flag_ptrs);
+/* Halo overlap.  Once peer gauges are set, phase 1 of the tensor path (32 < nb <= 256) can split the neighbours
+ * of every k-point into those whose gauge the rank owns and those a peer owns: the peer rows arrive on a
+ * second stream WHILE the main stream packs the local rows and rotates the local-neighbour pairs; the
+ * remote-neighbour pairs follow.  dU passed to wb200_fg_phase1_dev must be U_ptrs[rank].
+ * WB200_HALO_SPLIT=0 (environment, read here) keeps the one-pass packing.
+ * (The split needs the comm buffers and the peers' packed arrays below; without them phase 1 packs local and
+ * peer rows in one pass, reading the peer rows over NVLink inside the pack kernel.)                         */
+
+/* ---- the library's own collectives over peer memory (peer.cu), one slab per GPU ---------------------------
+ * wb200_peer_comm_bytes(nw): size of a rank's comm buffer (readiness flags + all-reduce slots).  Every rank
+ *   allocates one (wb200_ipc_alloc, or cudaMalloc with peer access in one process), ZEROES it, and all ranks
+ *   synchronise before the first evaluation.
+ * wb200_set_peer_comm(ctx, world, comm_ptrs): comm_ptrs[q] = rank q's buffer as mapped on this device; must
+ *   follow wb200_set_peer_gauges; NULL removes.  From then on
+ *     - an evaluation no longer opens with a one-element "rows are in place" all-reduce: phase 1 publishes the
+ *       rank's evaluation counter into its peers' buffers (remote stores) and waits for the owners of its halo;
+ *     - unless the caller registers its own wb200_set_allreduce callback, every all-reduce of the library
+ *       (spread sums, min |N_nn|, the optimiser's scalar products) is ONE small kernel per rank that pushes the
+ *       contribution into a slot of every peer's buffer, waits for the peers and sums the slots in rank order:
+ *       bitwise identical on every rank, no NCCL on the hot path.  wb200_peer_allreduce_dev exposes it
+ *       (op 0 sum, 1 max, 2 min; count <= 4 nw + 64) for callers that drive phase1 / phase2 themselves.
+ *   Every rank must make the same sequence of calls.  One slab per device only (a spinning wait kernel must
+ *   never share a hardware queue with the signal it waits for); bounded spins trap after ~20 s.
+ * wb200_packed_gauge / wb200_ipc_get_handle / wb200_set_peer_packed: the tensor path (32 < nb <= 256) keeps the
+ *   gauge as a packed B-operand image; with the peers' images mapped (Up_ptrs[q]) a slab packs only ITS rows and
+ *   pulls the packed rows of its halo from the owners with the copy engines on a second stream while the
+ *   local-neighbour pairs are being rotated (src/spread.jl:164-195 has no counterpart: single process).      */
+size_t wb200_peer_comm_bytes(int nw);
+int wb200_set_peer_comm(wb200_ctx* ctx, int world, void* const* comm_ptrs);
+int wb200_peer_allreduce_dev(wb200_ctx* ctx, double* dptr, int count, int op);
+int wb200_packed_gauge(wb200_ctx* ctx, void** dptr, size_t* bytes);
+int wb200_ipc_get_handle(int device, void* dptr, unsigned char handle[64]);
+int wb200_set_peer_packed(wb200_ctx* ctx, int world, void* const* Up_ptrs);
 
 /* ---- sharded optimiser: caller-supplied collective ------------------------------------------------
  * With one process per GPU the library does not own a communicator.  The host registers a callback

@@ -37,9 +37,11 @@ def _worker(rank, world, port, case, out):
         ctx = w.Context(nb, nw, nk, nn, st["kpb_k"][k0:k1], st["bvec"][k0:k1], st["wb"],
                         w.api.to_abi_M(M[k0:k1]), device=rank, k_begin=k0, nk=k1 - k0)
         ctx.set_stream(torch.cuda.current_stream().cuda_stream)
-        # every other case with point-to-point readiness flags, the rest with the one-element all-reduce
-        shared = w.sharding.SharedGauges(ctx, dist, rank, rank, world, nk, nb, nw, bounds, flags=(nb != 16))
-        ctx.set_allreduce(w.sharding.torch_allreduce(dist, dev))
+        # the library's own peer-memory collectives, except one case that keeps the caller-supplied NCCL all-reduce
+        comm = nb != 16
+        shared = w.sharding.SharedGauges(ctx, dist, rank, rank, world, nk, nb, nw, bounds, comm=comm)
+        if not comm:
+            ctx.set_allreduce(w.sharding.torch_allreduce(dist, dev))
         if len(case) > 3:      # disentangle: (X, Y) slab, frozen bands of the slab
             from oracle import spread_oracle as so
             frozen = w.synthetic.make_frozen(nk, nb, case[4])

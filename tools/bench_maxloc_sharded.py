@@ -37,9 +37,10 @@ ctx.set_stream(torch.cuda.current_stream().cuda_stream)
 Uslab0 = w.synthetic.make_gauge_torch(nk, nb, nw, dev)[k0:k1].cpu().numpy().copy()
 shared = None
 if world > 1:
-    shared = w.sharding.SharedGauges(ctx, dist, local, rank, world, nk, nb, nw, bounds,
-                                     flags=os.environ.get("WB200_PEER_FLAGS", "1") != "0")
-    ctx.set_allreduce(w.sharding.torch_allreduce(dist, dev))
+    comm = os.environ.get("WB200_PEER_COMM", "1") != "0"
+    shared = w.sharding.SharedGauges(ctx, dist, local, rank, world, nk, nb, nw, bounds, comm=comm)
+    if not comm:
+        ctx.set_allreduce(w.sharding.torch_allreduce(dist, dev))
 
 res = []
 for rep in range(2):          # the first call pays one-off allocations

@@ -20,7 +20,7 @@ extern "C" void wb200_destroy(wb200_ctx* ctx) {
     if (ctx->halo_stream) cudaStreamDestroy(ctx->halo_stream);
     if (ctx->ev_rows) cudaEventDestroy(ctx->ev_rows);
     if (ctx->ev_halo) cudaEventDestroy(ctx->ev_halo);
-    void* ptrs[] = {(void*)ctx->d_flag_ptrs, ctx->d_need_split, ctx->d_owner_split, ctx->d_border, ctx->d_nloc,
+    void* ptrs[] = {(void*)ctx->d_comm, ctx->d_need_split, ctx->d_owner_split, ctx->d_border, ctx->d_nloc,
                     (void*)ctx->d_peerU, ctx->d_need_owner, ctx->d_need, ctx->d_kpb, ctx->d_kself, ctx->d_bvec, ctx->d_wb, ctx->d_M, ctx->d_r0,
                     ctx->d_frozen, ctx->d_nfrozen, ctx->d_U, ctx->d_G, ctx->d_MU, ctx->d_N,
                     ctx->d_dN, ctx->d_fro, ctx->d_part, ctx->d_pmin, ctx->d_sums, ctx->d_res,
@@ -215,44 +215,6 @@ static int rotate(wb200_ctx* ctx, const cplx* dU) {
     return rotate_range(ctx, dU, 0, ctx->nk);
 }
 
-// ---- "my rows are in place" without a collective (wb200_set_peer_flags) ----
-namespace {
-// one thread per peer: publish this rank's epoch in the peer's flag array (a remote store over NVLink)
-__global__ void flag_signal_kernel(int world, int rank, unsigned long long* const* __restrict__ flags,
-                                   unsigned long long epoch) {
-    const int q = threadIdx.x;
-    if (q >= world || q == rank) return;
-    __threadfence_system();
-    *(volatile unsigned long long*)(flags[q] + rank) = epoch;
-}
-// one thread per peer this slab reads from: spin on the LOCAL flag word until that peer has published
-// `epoch`.  Bounded (~20 s): a peer that died must not hang the device.
-__global__ void flag_wait_kernel(int world, unsigned mask, const unsigned long long* my_flags, unsigned long long epoch) {
-    const int q = threadIdx.x;
-    if (q >= world || !((mask >> q) & 1u)) return;
-    const volatile unsigned long long* f = my_flags + q;
-    unsigned long long t0;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-    while (*f < epoch) {
-        unsigned long long t;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-        if (t - t0 > 20000000000ull) __trap();
-        __nanosleep(200);
-    }
-    __threadfence_system();
-}
-}  // namespace
-
-// publish (on ctx->stream, after whatever wrote the rows) and wait (on `on`) for the owners of the halo rows
-static int flags_signal_wait(wb200_ctx* ctx, cudaStream_t on) {
-    ctx->epoch++;
-    flag_signal_kernel<<<1, 32, 0, ctx->stream>>>(ctx->peer_world, ctx->peer_rank, ctx->d_flag_ptrs, ctx->epoch);
-    WB_LAUNCH_CHECK(ctx);
-    flag_wait_kernel<<<1, 32, 0, on>>>(ctx->peer_world, ctx->peer_mask, ctx->my_flags, ctx->epoch);
-    WB_LAUNCH_CHECK(ctx);
-    return WB200_OK;
-}
-
 extern "C" int wb200_fg_phase1_dev(wb200_ctx* ctx, const double* dU, double* dsums, int exact_split) {
     if (!ctx || !dU || !dsums) return WB200_ERR_ARG;
     cudaSetDevice(ctx->device);
@@ -262,30 +224,31 @@ extern "C" int wb200_fg_phase1_dev(wb200_ctx* ctx, const double* dU, double* dsu
         ctx->err = "wb200_fg_phase1_dev: with peer gauges set, dU must be this rank's shared gauge array (U_ptrs[rank])";
         return WB200_ERR_ARG;
     }
-    const bool split = ctx->halo_split && ctx->d_peerU && !exact_split && ctx->n_need_local < ctx->n_need &&
+    if (ctx->d_peerU && ctx->d_comm) ctx->epoch++;
+    // (the same on every rank: which flag a peer waits for depends on it)
+    const bool split = ctx->halo_split && ctx->d_peerU && ctx->d_comm && !ctx->h_peerUp.empty() && !exact_split &&
                        wb_dmma_phases_supported(ctx);
     if (split) {
-        // Rows peers own are fetched over NVLink and packed on a second stream while the main stream packs the
-        // local rows and rotates every pair whose neighbour is local; the remaining pairs follow once the
-        // halo has landed.  The U_k tiles of the epilogue are always local.
-        if (ctx->d_flag_ptrs) {
-            WB_CUDA(ctx, cudaEventRecord(ctx->ev_rows, ctx->stream));   // WAR on Up: the previous evaluation's rotation
-            WB_CUDA(ctx, cudaStreamWaitEvent(ctx->halo_stream, ctx->ev_rows, 0));
-            WB_TRY(flags_signal_wait(ctx, ctx->halo_stream));
-        } else {
-            WB_CUDA(ctx, cudaEventRecord(ctx->ev_rows, ctx->stream));
-            WB_CUDA(ctx, cudaStreamWaitEvent(ctx->halo_stream, ctx->ev_rows, 0));
-        }
-        WB_TRY(wb_pack_dmma_split(ctx, (const cplx*)dU, ctx->n_need_local, ctx->n_need, true));
+        // Halo overlap (peer.cu).  Every rank packs ITS rows and says so; the packed rows a slab needs from peers
+        // are pulled by the copy engines on a second stream while the main stream rotates every pair whose
+        // neighbour is local; the remaining pairs follow once the halo has landed.
+        WB_CUDA(ctx, cudaEventRecord(ctx->ev_rows, ctx->stream));   // WAR on the packed halo rows: the previous rotation
+        WB_CUDA(ctx, cudaStreamWaitEvent(ctx->halo_stream, ctx->ev_rows, 0));
+        WB_TRY(wb_pack_dmma_local(ctx, (const cplx*)dU));
+        WB_TRY(wb_peer_signal(ctx, 1, ctx->epoch));
+        WB_TRY(wb_peer_wait(ctx, 1, ctx->epoch, ctx->halo_stream));
+        WB_TRY(wb_peer_pull_packed(ctx));
         WB_CUDA(ctx, cudaEventRecord(ctx->ev_halo, ctx->halo_stream));
-        WB_TRY(wb_pack_dmma_split(ctx, (const cplx*)dU, 0, ctx->n_need_local, false));
         WB_TRY(wb_rotate_dmma(ctx, (const cplx*)dU, 0, ctx->nk, 1));
         WB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_halo, 0));
         WB_TRY(wb_rotate_dmma(ctx, (const cplx*)dU, 0, ctx->nk, 2));
         WB_TRY(wb_pair_reduce(ctx, dsums));
         return WB200_OK;
     }
-    if (ctx->d_peerU && ctx->d_flag_ptrs) WB_TRY(flags_signal_wait(ctx, ctx->stream));
+    if (ctx->d_peerU && ctx->d_comm) {   // "my rows are in place", neighbour to neighbour, instead of a collective
+        WB_TRY(wb_peer_signal(ctx, 0, ctx->epoch));
+        WB_TRY(wb_peer_wait(ctx, 0, ctx->epoch, ctx->stream));
+    }
     // with peer gauges the tensor path reads remote rows inside its pack kernel; every other
     // consumer (CUDA-core rotation, exact N) reads dU[k+b] directly, so fetch the halo rows first
     if (ctx->d_peerU && (!ctx->dmma || exact_split)) WB_TRY(wb_halo_fetch(ctx, (cplx*)dU));
@@ -331,7 +294,7 @@ int wb_fg_device(wb200_ctx* ctx, const cplx* dU, double* dres, cplx* dG, int exa
         if (dU != rows)
             WB_CUDA(ctx, cudaMemcpyAsync(rows, dU, sizeof(cplx) * mat * ctx->nk, cudaMemcpyDeviceToDevice,
                                          ctx->stream));
-        if (!ctx->d_flag_ptrs) {   // with peer flags phase 1 itself publishes and waits, neighbour to neighbour
+        if (!ctx->d_comm) {   // with peer comm buffers phase 1 itself publishes and waits, neighbour to neighbour
             WB_CUDA(ctx, cudaMemsetAsync(ctx->d_scal + 2, 0, sizeof(double), ctx->stream));
             WB_TRY(wb_allreduce(ctx, ctx->d_scal + 2, 1, 0));
         }
@@ -927,15 +890,18 @@ extern "C" int wb200_set_peer_gauges(wb200_ctx* ctx, int world, const void* cons
     WB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (ctx->halo_stream) WB_CUDA(ctx, cudaStreamSynchronize(ctx->halo_stream));
     void** owned[] = {(void**)&ctx->d_peerU, (void**)&ctx->d_need_owner, (void**)&ctx->d_need_split, (void**)&ctx->d_owner_split,
-                      (void**)&ctx->d_border, (void**)&ctx->d_nloc, (void**)&ctx->d_flag_ptrs};
+                      (void**)&ctx->d_border, (void**)&ctx->d_nloc, (void**)&ctx->d_comm};
     for (void** p : owned)
         if (*p) { cudaFree(*p); *p = nullptr; }
     ctx->peer_world = 0;
     ctx->peer_self = nullptr;
     ctx->peer_rank = -1;
-    ctx->my_flags = nullptr;
+    if (wb_allreduce_is_builtin(ctx)) { ctx->allreduce = nullptr; ctx->allreduce_user = nullptr; }
+    ctx->my_comm = nullptr;
     ctx->peer_mask = 0;
     ctx->halo_split = 0;
+    ctx->h_peerUp.clear();
+    ctx->halo_runs.clear();
     if (world <= 0 || !U_ptrs) return WB200_OK;   // back to purely local reads
     if (!bounds || bounds[0] != 0 || bounds[world] != ctx->nk_total) {
         ctx->err = "wb200_set_peer_gauges: bounds must run from 0 to nk_total";
@@ -959,6 +925,13 @@ extern "C" int wb200_set_peer_gauges(wb200_ctx* ctx, int world, const void* cons
                 if (pass == 1 && owner[i] < 32) ctx->peer_mask |= 1u << owner[i];
             }
         if (pass == 0) ctx->n_need_local = (int)need_s.size();
+    }
+    for (size_t i = ctx->n_need_local; i < need_s.size(); i++) {   // remote rows are sorted by k: runs with one owner
+        if (!ctx->halo_runs.empty() && ctx->halo_runs.back().owner == owner_s[i] &&
+            ctx->halo_runs.back().k0 + ctx->halo_runs.back().count == need_s[i])
+            ctx->halo_runs.back().count++;
+        else
+            ctx->halo_runs.push_back({owner_s[i], need_s[i], 1});
     }
     // per-k neighbour order: neighbours whose gauge is local first
     const int nn = ctx->nn;
@@ -1004,34 +977,10 @@ extern "C" int wb200_set_peer_gauges(wb200_ctx* ctx, int world, const void* cons
     return WB200_OK;
 }
 
-// Point-to-point readiness flags.  flag_ptrs[q] is rank q's flag array (`world` 64-bit words, zeroed by the
-// caller before any rank evaluates), mapped into this process / device like the gauge arrays.  With flags in
-// place an evaluation no longer opens with a one-element all-reduce ("every rank has written its rows"): phase 1
-// stores this rank's evaluation counter into every peer's array and waits, on the stream that fetches the
-// halo, until the owners of the rows it reads have published the same counter.  Every rank must make the same
-// sequence of evaluations, and a collective (the all-reduce of the sums) must separate two evaluations — both
-// hold for every driver in this library.  Must follow wb200_set_peer_gauges; NULL removes the flags.
-extern "C" int wb200_set_peer_flags(wb200_ctx* ctx, int world, void* const* flag_ptrs) {
-    if (!ctx) return WB200_ERR_ARG;
-    cudaSetDevice(ctx->device);
-    WB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    if (ctx->d_flag_ptrs) { cudaFree((void*)ctx->d_flag_ptrs); ctx->d_flag_ptrs = nullptr; }
-    ctx->my_flags = nullptr;
-    ctx->epoch = 0;
-    if (!flag_ptrs || world <= 0) return WB200_OK;
-    if (world != ctx->peer_world || world > 32) {
-        ctx->err = "wb200_set_peer_flags: call wb200_set_peer_gauges first, with the same world size (at most 32)";
-        return WB200_ERR_ARG;
-    }
-    WB_CUDA(ctx, cudaMalloc((void**)&ctx->d_flag_ptrs, sizeof(void*) * world));
-    WB_CUDA(ctx, cudaMemcpy((void*)ctx->d_flag_ptrs, flag_ptrs, sizeof(void*) * world, cudaMemcpyHostToDevice));
-    ctx->my_flags = (unsigned long long*)flag_ptrs[ctx->peer_rank];
-    return WB200_OK;
-}
-
 extern "C" int wb200_set_allreduce(wb200_ctx* ctx, wb200_allreduce_fn fn, void* user) {
     if (!ctx) return WB200_ERR_ARG;
     ctx->allreduce = fn;
     ctx->allreduce_user = user;
+    if (!fn) wb_allreduce_install_builtin(ctx);   // with comm buffers in place NULL means "the library's own"
     return WB200_OK;
 }

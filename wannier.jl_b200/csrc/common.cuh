@@ -105,11 +105,15 @@ struct wb200_ctx {
     int halo_split = 0;               // 1: phase 1 overlaps the halo packing with the local-neighbour rotation
     cudaStream_t halo_stream = nullptr;
     cudaEvent_t ev_rows = nullptr, ev_halo = nullptr;
-    // point-to-point "my rows are in place" flags in peer memory (wb200_set_peer_flags) instead of a collective
-    unsigned long long** d_flag_ptrs = nullptr;   // [world] device array: rank q's flag array (world words)
-    unsigned long long* my_flags = nullptr;       // flag_ptrs[rank]
-    unsigned long long epoch = 0;
+    // peer-memory comm buffers (wb200_set_peer_comm, peer.cu): readiness flags and all-reduce slots
+    unsigned long long** d_comm = nullptr;        // [world] device array: rank q's comm buffer
+    unsigned long long* my_comm = nullptr;        // comm_ptrs[rank]
+    int comm_maxc = 0;                            // doubles per all-reduce slot
+    unsigned long long epoch = 0, ar_epoch = 0;   // evaluation / all-reduce counters (identical on every rank)
     unsigned peer_mask = 0;                       // ranks owning rows this slab reads
+    std::vector<void*> h_peerUp;                  // packed-gauge arrays of the ranks (wb200_set_peer_packed)
+    struct HaloRun { int owner, k0, count; };
+    std::vector<HaloRun> halo_runs;               // contiguous runs of remote rows with one owner
     wb200_allreduce_fn allreduce = nullptr;   // caller-supplied collective (sharded optimiser)
     void* allreduce_user = nullptr;
     int poison_next = 0;   // the next evaluation's sums are replaced by NaN before they are reduced (a
@@ -225,6 +229,15 @@ struct ProfScope {
 // ---- api.cu ----
 int wb_allreduce(wb200_ctx* ctx, double* dptr, int count, int op);   // checked call of the registered collective
 
+// ---- peer.cu ----
+#define WB_COMM_MAXR 32
+int wb_peer_allreduce(wb200_ctx* ctx, double* dptr, int count, int op, int count2, int op2);
+bool wb_allreduce_is_builtin(const wb200_ctx* ctx);
+void wb_allreduce_install_builtin(wb200_ctx* ctx);
+int wb_peer_signal(wb200_ctx* ctx, int which, unsigned long long epoch);
+int wb_peer_wait(wb200_ctx* ctx, int which, unsigned long long epoch, cudaStream_t on);
+int wb_peer_pull_packed(wb200_ctx* ctx);
+
 // ---- kernels_generic.cu ----
 int wb_zgemm_batched(wb200_ctx* ctx, const ZgemmArgs& a);
 int wb_rotate_generic(wb200_ctx* ctx, const cplx* dU, int ka, int kb);  // MU, dN, fro(=||MU||^2) of local k in [ka, kb)
@@ -286,7 +299,8 @@ int wb_pack_dmma(wb200_ctx* ctx, const cplx* dU, int ja, int jb);     // pack ne
 // MU, dN, fro(=||MU||^2) of local k in [ka, kb); phase 1 / 2: only the pairs whose neighbour is local / remote
 int wb_rotate_dmma(wb200_ctx* ctx, const cplx* dU, int ka, int kb, int phase = 0);
 bool wb_dmma_phases_supported(const wb200_ctx* ctx);
-int wb_pack_dmma_split(wb200_ctx* ctx, const cplx* dU, int ja, int jb, bool halo);
+int wb_pack_dmma_local(wb200_ctx* ctx, const cplx* dU);   // the rows this rank owns (split need list)
+int wb_dmma_packed_info(wb200_ctx* ctx, void** dptr, size_t* bytes, size_t* row_bytes);
 
 bool wb_zgemm_dmma_applicable(const wb200_ctx* ctx, int nrow, int ncol);
 int wb_zgemm_dmma(wb200_ctx* ctx, int transA, const cplx* A, const cplx* B, cplx* C, int count);   // C = op(A) B, n x n

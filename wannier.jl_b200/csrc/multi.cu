@@ -57,7 +57,7 @@ struct wb200_multi {
     std::vector<int> devices, bounds;
     std::vector<wb200_ctx*> ctx;
     std::vector<cplx*> Ufull;            // per slab: [nk][nw][nb] on its device; the slab owns its rows
-    std::vector<void*> flags;            // per slab: readiness-flag words (distinct devices only)
+    std::vector<void*> flags;            // per slab: peer comm buffer (distinct devices only)
     HostBarrier bar;
     int maxc = 0;
     double* h_x[2] = {nullptr, nullptr};   // pinned [parity][slab][maxc]: contributions
@@ -208,25 +208,36 @@ extern "C" int wb200_multi_create(wb200_multi** out, const int* devices, int nde
         if (cudaMallocHost(&m->h_x[p], sizeof(double) * (size_t)ndev * m->maxc) != cudaSuccess ||
             cudaMallocHost(&m->h_r[p], sizeof(double) * (size_t)ndev * m->maxc) != cudaSuccess)
             return fail(WB200_ERR_CUDA, "wb200_multi_create: cudaMallocHost failed");
-    // point-to-point readiness flags replace the "rows are in place" reduction when every slab has its own
-    // device (two slabs of one device could share a hardware queue: a spinning wait in front of its signal)
-    bool distinct = ndev <= 32;
+    // One slab per device: the library's own peer-memory collectives (peer.cu) — readiness flags instead of a
+    // "rows are in place" reduction, packed halo rows pulled by the copy engines under the rotation, all-reduces as
+    // one small kernel per slab.  Two slabs of one device could share a hardware queue (a spinning wait in front
+    // of its signal), so repeated devices keep the host-side all-reduce at the barrier.
+    bool distinct = ndev <= WB_COMM_MAXR;
     for (int r = 0; r < ndev; r++)
         for (int q = 0; q < r; q++) distinct = distinct && devices[r] != devices[q];
-    { const char* e = getenv("WB200_PEER_FLAGS"); if (e && e[0] == '0') distinct = false; }
+    { const char* e = getenv("WB200_PEER_COMM"); if (e && e[0] == '0') distinct = false; }
+    const bool peer_comm = distinct && ndev > 1;
     m->flags.assign(ndev, nullptr);
-    if (distinct && ndev > 1)
+    const size_t comm_bytes = wb200_peer_comm_bytes(nw);
+    if (peer_comm)
         for (int r = 0; r < ndev; r++)
-            if (cudaSetDevice(devices[r]) != cudaSuccess || cudaMalloc(&m->flags[r], 8 * (size_t)ndev) != cudaSuccess ||
-                cudaMemset(m->flags[r], 0, 8 * (size_t)ndev) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess)
-                return fail(WB200_ERR_CUDA, "wb200_multi_create: cudaMalloc of the readiness flags failed");
+            if (cudaSetDevice(devices[r]) != cudaSuccess || cudaMalloc(&m->flags[r], comm_bytes) != cudaSuccess ||
+                cudaMemset(m->flags[r], 0, comm_bytes) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess)
+                return fail(WB200_ERR_CUDA, "wb200_multi_create: cudaMalloc of the comm buffers failed");
     std::vector<const void*> ptrs(ndev);
-    for (int r = 0; r < ndev; r++) ptrs[r] = m->Ufull[r];
+    std::vector<void*> packed(ndev, nullptr);
+    bool have_packed = peer_comm;
+    for (int r = 0; r < ndev; r++) {
+        ptrs[r] = m->Ufull[r];
+        size_t bytes = 0;
+        if (have_packed && wb200_packed_gauge(m->ctx[r], &packed[r], &bytes) != WB200_OK) have_packed = false;
+    }
     for (int r = 0; r < ndev; r++) {
         m->users[r] = {m, r};
         int s = wb200_set_peer_gauges(m->ctx[r], ndev, ptrs.data(), m->bounds.data());
-        if (s == WB200_OK && distinct && ndev > 1) s = wb200_set_peer_flags(m->ctx[r], ndev, m->flags.data());
-        if (s == WB200_OK) s = wb200_set_allreduce(m->ctx[r], multi_allreduce, &m->users[r]);
+        if (s == WB200_OK && peer_comm) s = wb200_set_peer_comm(m->ctx[r], ndev, m->flags.data());
+        if (s == WB200_OK && have_packed) s = wb200_set_peer_packed(m->ctx[r], ndev, packed.data());
+        if (s == WB200_OK && !peer_comm) s = wb200_set_allreduce(m->ctx[r], multi_allreduce, &m->users[r]);
         if (s != WB200_OK) return fail(s, "wb200_multi_create: " + m->ctx[r]->err);
     }
     *out = m;

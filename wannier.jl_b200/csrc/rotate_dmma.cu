@@ -182,22 +182,6 @@ __global__ void __launch_bounds__(256) pack_gauge_kernel(int nb, int nw, int WN,
     if (peerU) U = peerU[owner[blockIdx.x]];
     pack_gauge_row(nb, nw, WN, KC, nch, nct, kg, blockIdx.y, U, Up);
 }
-// The halo half of the packing (rows other ranks own) runs on a second stream UNDER the rotation of the pairs
-// whose neighbour is local, so it must leave the SMs to the rotation kernel (one 384-thread CTA owns a whole
-// SM's register file): a few fat CTAs walk the (row, column tile) items instead of one small CTA per item, which
-// the block scheduler would spread over every SM.  The link, not the SM count, bounds it: 32 CTAs x 1024
-// threads x 2 x 32 B keep ~2 MB in flight.
-__global__ void __launch_bounds__(1024) pack_gauge_halo_kernel(int nb, int nw, int WN, int KC, int nch, int nct, int nrows,
-                                                               const int32_t* __restrict__ need,
-                                                               const int32_t* __restrict__ owner,
-                                                               const cplx* const* __restrict__ peerU,
-                                                               double* __restrict__ Up) {
-    for (int item = blockIdx.x; item < nrows * nct; item += gridDim.x) {
-        const int row = item / nct, ct = item - row * nct;
-        pack_gauge_row(nb, nw, WN, KC, nch, nct, need[row], ct, peerU[owner[row]], Up);
-    }
-}
-
 // ---- the rotation kernel ---------------------------------------------------------------------
 template <int WM, int WN, int KC, int STAGES>
 __global__ void __launch_bounds__(384, 1)
@@ -926,24 +910,28 @@ int wb_pack_dmma(wb200_ctx* ctx, const cplx* dU, int ja, int jb) {
 // the halo split (api.cu) applies to the three CTA-per-(k, column tile) kernels
 bool wb_dmma_phases_supported(const wb200_ctx* ctx) { return ctx->dmma && !ctx->dmma->small; }
 
-// rows [ja, jb) of the split need list (local rows first, then the rows peers own).  halo = true: the fat-CTA
-// kernel on ctx->halo_stream (rows come from peer memory), otherwise the plain kernel on ctx->stream.
-int wb_pack_dmma_split(wb200_ctx* ctx, const cplx* dU, int ja, int jb, bool halo) {
+// the rows this rank owns (the first n_need_local entries of the split need list)
+int wb_pack_dmma_local(wb200_ctx* ctx, const cplx* dU) {
     DmmaPlan* p = ctx->dmma;
-    if (jb <= ja) return WB200_OK;
-    if (halo) {
-        const int items = (jb - ja) * p->nct;
-        const int grid = items < 32 ? items : 32;
-        pack_gauge_halo_kernel<<<grid, 1024, 0, ctx->halo_stream>>>(ctx->nb, ctx->nw, p->WN, p->KC, p->nch, p->nct, jb - ja,
-                                                                   ctx->d_need_split + ja, ctx->d_owner_split + ja,
-                                                                   ctx->d_peerU, p->d_Up);
-    } else {
-        dim3 g((unsigned)(jb - ja), (unsigned)p->nct);
-        ProfScope ps(ctx, 0);
-        pack_gauge_kernel<<<g, 256, 0, ctx->stream>>>(ctx->nb, ctx->nw, p->WN, p->KC, p->nch, p->nct, ctx->d_need_split + ja,
-                                                      ctx->d_owner_split + ja, ctx->d_peerU, dU, p->d_Up);
-    }
+    if (ctx->n_need_local <= 0) return WB200_OK;
+    dim3 g((unsigned)ctx->n_need_local, (unsigned)p->nct);
+    ProfScope ps(ctx, 0);
+    pack_gauge_kernel<<<g, 256, 0, ctx->stream>>>(ctx->nb, ctx->nw, p->WN, p->KC, p->nch, p->nct, ctx->d_need_split,
+                                                  ctx->d_owner_split, ctx->d_peerU, dU, p->d_Up);
     WB_LAUNCH_CHECK(ctx);
+    return WB200_OK;
+}
+
+// the packed-gauge image [nk_total][nct][nch][b_stage]: base pointer, size, bytes per k-point
+int wb_dmma_packed_info(wb200_ctx* ctx, void** dptr, size_t* bytes, size_t* row_bytes) {
+    DmmaPlan* p = ctx->dmma;
+    if (!p || p->small) {
+        ctx->err = "no packed gauge image for this shape (tensor path with 32 < nb <= 256 only)";
+        return WB200_ERR_ARG;
+    }
+    *row_bytes = sizeof(double) * (size_t)p->nct * p->nch * p->b_stage;
+    *bytes = *row_bytes * (size_t)ctx->nk_total;
+    *dptr = p->d_Up;
     return WB200_OK;
 }
 

@@ -169,8 +169,12 @@ int wb_cross_launch(wb200_ctx* ctx, const WbCrossArgs& p, size_t n) {
     cross_stage2<<<WB_CROSS_NOUT, RED_THREADS, 0, ctx->stream>>>(ctx->d_red, blocks, out);
     WB_LAUNCH_CHECK(ctx);
     if (ctx->allreduce) {   // k-sharded optimiser: the vectors are slab-local, the scalars global
-        WB_TRY(wb_allreduce(ctx, out, WB_CROSS_NOUT - 1, 0));
-        WB_TRY(wb_allreduce(ctx, out + WB_CROSS_NOUT - 1, 1, 1));
+        if (wb_allreduce_is_builtin(ctx)) {   // sums and the max in one peer-memory launch
+            WB_TRY(wb_peer_allreduce(ctx, out, WB_CROSS_NOUT - 1, 0, 1, 1));
+        } else {
+            WB_TRY(wb_allreduce(ctx, out, WB_CROSS_NOUT - 1, 0));
+            WB_TRY(wb_allreduce(ctx, out + WB_CROSS_NOUT - 1, 1, 1));
+        }
     }
     WB_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned + WB_PIN_CROSS, out, sizeof(double) * WB_CROSS_NOUT,
                                  cudaMemcpyDeviceToHost, ctx->stream));

@@ -26,7 +26,8 @@ SYMBOLS = [
     "wb200_omega_local", "wb200_fg_rotate", "wb200_opt_rotate", "wb200_position_op", "wb200_berry_connection",
     "wb200_set_allreduce",
     "wb200_ipc_alloc", "wb200_ipc_open", "wb200_ipc_close", "wb200_ipc_free", "wb200_set_peer_gauges",
-    "wb200_set_peer_flags",
+    "wb200_peer_comm_bytes", "wb200_set_peer_comm", "wb200_peer_allreduce_dev", "wb200_packed_gauge",
+    "wb200_ipc_get_handle", "wb200_set_peer_packed",
     "wb200_multi_create", "wb200_multi_destroy", "wb200_multi_last_error", "wb200_multi_ndev",
     "wb200_multi_slab_begin", "wb200_multi_launch_count", "wb200_multi_set_penalty", "wb200_multi_set_frozen",
     "wb200_multi_fg", "wb200_multi_spread", "wb200_multi_fg_xy", "wb200_multi_max_localize",
@@ -110,7 +111,13 @@ def load():
     lib.wb200_ipc_close.argtypes = [i32, vp]
     lib.wb200_ipc_free.argtypes = [i32, vp]
     lib.wb200_set_peer_gauges.argtypes = [vp, i32, pd, pd]
-    lib.wb200_set_peer_flags.argtypes = [vp, i32, pd]
+    lib.wb200_peer_comm_bytes.argtypes = [i32]
+    lib.wb200_peer_comm_bytes.restype = C.c_size_t
+    lib.wb200_set_peer_comm.argtypes = [vp, i32, pd]
+    lib.wb200_peer_allreduce_dev.argtypes = [vp, pd, i32, i32]
+    lib.wb200_packed_gauge.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
+    lib.wb200_ipc_get_handle.argtypes = [i32, vp, pd]
+    lib.wb200_set_peer_packed.argtypes = [vp, i32, pd]
     lib.wb200_multi_create.argtypes = [C.POINTER(vp), pd, i32, i32, i32, i32, i32, pd, pd, pd, pd, C.c_uint]
     lib.wb200_multi_destroy.argtypes = [vp]
     lib.wb200_multi_destroy.restype = None
@@ -271,21 +278,43 @@ class Context:
         b = np.ascontiguousarray(bounds, dtype=np.int32)
         self._ck(self._lib.wb200_set_peer_gauges(self._h, len(p), _addr(p), _addr(b)))
 
-    def set_peer_flags(self, ptrs):
-        """ptrs[r]: device address of rank r's readiness-flag array (world uint64, zeroed) as mapped on this
-        device; None removes the flags.  Replaces the "rows are in place" all-reduce in front of an evaluation."""
+    def set_peer_comm(self, ptrs):
+        """ptrs[r]: device address of rank r's comm buffer (peer_comm_bytes(nw) bytes, zeroed) as mapped on this
+        device; None removes.  Readiness flags replace the "rows are in place" all-reduce and, unless a callback
+        is registered with set_allreduce, the library's own peer-memory all-reduce serves every collective."""
         if ptrs is None:
-            self._ck(self._lib.wb200_set_peer_flags(self._h, 0, None))
+            self._ck(self._lib.wb200_set_peer_comm(self._h, 0, None))
+            self._comm = False
+            self._sharded = getattr(self, "_cb", None) is not None
             return
         p = np.asarray(ptrs, dtype=np.uint64)
-        self._ck(self._lib.wb200_set_peer_flags(self._h, len(p), _addr(p)))
+        self._ck(self._lib.wb200_set_peer_comm(self._h, len(p), _addr(p)))
+        self._comm = True
+        self._sharded = True
+
+    def set_peer_packed(self, ptrs):
+        """ptrs[r]: device address of rank r's packed-gauge image (packed_gauge()) as mapped here; None removes."""
+        if ptrs is None:
+            self._ck(self._lib.wb200_set_peer_packed(self._h, 0, None))
+            return
+        p = np.asarray(ptrs, dtype=np.uint64)
+        self._ck(self._lib.wb200_set_peer_packed(self._h, len(p), _addr(p)))
+
+    def packed_gauge(self):
+        """(device address, bytes) of this ctx's packed-gauge image; raises for shapes outside the tensor path."""
+        ptr, n = C.c_void_p(), C.c_size_t()
+        self._ck(self._lib.wb200_packed_gauge(self._h, C.byref(ptr), C.byref(n)))
+        return ptr.value, n.value
+
+    def peer_allreduce_dev(self, dptr, count, op=0):
+        self._ck(self._lib.wb200_peer_allreduce_dev(self._h, dptr, count, op))
 
     def set_allreduce(self, fn):
         """fn(dptr: int, count: int, op: int (0 sum, 1 max), stream: int) all-reduces `count` doubles
         in place over the ranks on `stream`; None unregisters.  The ctypes thunk is kept alive here."""
         if fn is None:
             self._cb = None
-            self._sharded = False
+            self._sharded = getattr(self, "_comm", False)    # the library's own peer-memory collective remains
             self._ck(self._lib.wb200_set_allreduce(self._h, None, None))
             return
         self._sharded = True
@@ -595,6 +624,20 @@ def ipc_alloc(device, nbytes):
     if st != 0:
         raise WB200Error(st, "wb200_ipc_alloc failed")
     return ptr.value, bytes(h)
+
+
+def ipc_get_handle(device, ptr):
+    """64-byte CUDA-IPC handle of an existing cudaMalloc allocation (its base address)"""
+    lib = load()
+    h = (C.c_ubyte * 64)()
+    st = lib.wb200_ipc_get_handle(device, ptr, C.addressof(h))
+    if st != 0:
+        raise WB200Error(st, "wb200_ipc_get_handle failed")
+    return bytes(h)
+
+
+def peer_comm_bytes(nw):
+    return int(load().wb200_peer_comm_bytes(nw))
 
 
 def ipc_open(device, handle):

@@ -101,45 +101,62 @@ class HaloPlan:
 
 
 class SharedGauges:
-    """Peer-memory plumbing of a one-process-per-GPU run: every rank allocates the FULL gauge array (and a
-    small readiness-flag array) in CUDA-IPC shareable memory, the handles travel through torch.distributed,
-    every rank maps its peers' allocations and hands the pointer tables to its slab context
-    (wb200_set_peer_gauges / wb200_set_peer_flags).  `ptr` is this rank's array; `close()` unmaps and frees."""
+    """Peer-memory plumbing of a one-process-per-GPU run: every rank allocates the FULL gauge array and a comm
+    buffer (readiness flags + all-reduce slots) in CUDA-IPC shareable memory and exports its context's packed
+    gauge image; the handles travel through torch.distributed once, every rank maps its peers' allocations and
+    hands the pointer tables to its slab context (wb200_set_peer_gauges / _comm / _packed).  After that the
+    evaluations and the optimiser need no torch.distributed / NCCL call at all.  `ptr` is this rank's gauge
+    array; `close()` unmaps and frees.  comm=False keeps the round-1 scheme (caller-supplied all-reduce)."""
 
-    def __init__(self, ctx, dist, device_index, rank, world, nk, nb, nw, bounds, flags=True):
+    def __init__(self, ctx, dist, device_index, rank, world, nk, nb, nw, bounds, comm=True):
+        import torch
         from . import lib
         self._lib, self.ctx, self.dist = lib, ctx, dist
         self.device, self.rank, self.world = device_index, rank, world
         self.ptr, handle = lib.ipc_alloc(device_index, 16 * nk * nb * nw)
-        self.flag_ptr, fhandle = lib.ipc_alloc(device_index, 8 * max(world, 32)) if flags else (None, None)
-        handles = [None] * world
-        dist.all_gather_object(handles, (handle, fhandle))
-        self.ptrs = [self.ptr if r == rank else lib.ipc_open(device_index, handles[r][0]) for r in range(world)]
-        ctx.set_peer_gauges(self.ptrs, bounds)
-        self.flag_ptrs = None
-        if flags:
-            import torch
-            torch.as_tensor(lib.DeviceArray(self.flag_ptr, (max(world, 32),), "<i8"),
+        self.comm_ptr, chandle, phandle = None, None, None
+        if comm:
+            nbytes = lib.peer_comm_bytes(nw)
+            self.comm_ptr, chandle = lib.ipc_alloc(device_index, nbytes)
+            torch.as_tensor(lib.DeviceArray(self.comm_ptr, (nbytes // 8,), "<i8"),
                             device=torch.device("cuda", device_index)).zero_()
             torch.cuda.synchronize()
-            dist.barrier()                       # every flag array is zero before anyone can signal
-            self.flag_ptrs = [self.flag_ptr if r == rank else lib.ipc_open(device_index, handles[r][1])
-                              for r in range(world)]
-            ctx.set_peer_flags(self.flag_ptrs)
+            try:
+                phandle = lib.ipc_get_handle(device_index, ctx.packed_gauge()[0])
+            except lib.WB200Error:
+                phandle = None                      # shape outside the tensor path: raw rows are pulled instead
+        handles = [None] * world
+        dist.all_gather_object(handles, (handle, chandle, phandle))     # also orders the zeroing before any signal
+        opened = lambda r, i: lib.ipc_open(device_index, handles[r][i])
+        self.ptrs = [self.ptr if r == rank else opened(r, 0) for r in range(world)]
+        ctx.set_peer_gauges(self.ptrs, bounds)
+        self.comm_ptrs = self.packed_ptrs = None
+        if comm:
+            self.comm_ptrs = [self.comm_ptr if r == rank else opened(r, 1) for r in range(world)]
+            ctx.set_peer_comm(self.comm_ptrs)
+            if all(h[2] is not None for h in handles):
+                self.packed_ptrs = [ctx.packed_gauge()[0] if r == rank else opened(r, 2) for r in range(world)]
+                ctx.set_peer_packed(self.packed_ptrs)
 
     def close(self):
+        import torch
         lib = self._lib
-        self.ctx.set_peer_flags(None)
+        torch.cuda.synchronize()
+        self.dist.barrier()                      # nobody still reads a peer's memory
+        self.ctx.set_peer_packed(None)
+        self.ctx.set_peer_comm(None)
         self.ctx.set_peer_gauges(None, None)
         for r in range(self.world):
             if r != self.rank:
                 lib.ipc_close(self.device, self.ptrs[r])
-                if self.flag_ptrs:
-                    lib.ipc_close(self.device, self.flag_ptrs[r])
+                if self.comm_ptrs:
+                    lib.ipc_close(self.device, self.comm_ptrs[r])
+                if self.packed_ptrs:
+                    lib.ipc_close(self.device, self.packed_ptrs[r])
         self.dist.barrier()
         lib.ipc_free(self.device, self.ptr)
-        if self.flag_ptr:
-            lib.ipc_free(self.device, self.flag_ptr)
+        if self.comm_ptr:
+            lib.ipc_free(self.device, self.comm_ptr)
 
 
 def torch_allreduce(dist, device):
