@@ -138,8 +138,11 @@ int wb200_disentangle(wb200_ctx* ctx, double* XY_inout, double f_tol, double g_t
  *         0, 0, omega_n[nw], r[nw][3]}
  *   dG    device, [nk][nw][nb] or NULL
  * `exact_split` != 0 forms the full N (second GEMM) so OmegaI/OmegaOD are exact for any U;
- * 0 uses ||N||_F = ||M U_{k+b}||_F, valid for square unitary U_k (max_localize); Omega, r, omega_n
- * and G never depend on this choice.                                                            */
+ * 0 uses ||N||_F = ||M U_{k+b}||_F, valid for square unitary U_k (max_localize) — and on the tensor path with
+ * n_bands == n_wann the gauge invariance of that norm, ||U_k^H M_kb U_{k+b}||_F = ||M_kb||_F, computed from
+ * M once at creation (the spread functional's Omega_I is gauge invariant for an isolated manifold;
+ * WB200_CONST_NORM=0 in the environment keeps the per-evaluation norm); Omega, r, omega_n and G never
+ * depend on this choice.                                                                          */
 int wb200_nsums(const wb200_ctx* ctx);
 int wb200_nres(const wb200_ctx* ctx);
 int wb200_fg_phase1_dev(wb200_ctx* ctx, const double* dU, double* dsums, int exact_split);

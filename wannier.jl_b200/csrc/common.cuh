@@ -174,6 +174,7 @@ struct wb200_ctx {
     unsigned long long graph_clock = 0;
     int use_graphs = 1;        // WB200_GRAPH=0 disables
     unsigned zd_attr_mask = 0; // zgemm_dmma.cu: shared-memory attribute set for these instantiations
+    int rot_attr_done = 0;     // rotate_dmma.cu: the same for the rotation kernel of this ctx's shape
 
     DmmaPlan* dmma = nullptr;  // tensor-path state (nullptr: CUDA-core rotation)
     int rotation_kernel = 0;
@@ -301,9 +302,6 @@ int wb_rotate_dmma(wb200_ctx* ctx, const cplx* dU, int ka, int kb, int phase = 0
 bool wb_dmma_phases_supported(const wb200_ctx* ctx);
 int wb_pack_dmma_local(wb200_ctx* ctx, const cplx* dU);   // the rows this rank owns (split need list)
 int wb_dmma_packed_info(wb200_ctx* ctx, void** dptr, size_t* bytes, size_t* row_bytes);
-
-bool wb_zgemm_dmma_applicable(const wb200_ctx* ctx, int nrow, int ncol);
-int wb_zgemm_dmma(wb200_ctx* ctx, int transA, const cplx* A, const cplx* B, cplx* C, int count);   // C = op(A) B, n x n
 
 // ---- zgemm_dmma.cu: batched complex GEMM on the FP64 tensor pipe from plain column-major operands ----
 bool wb_zgemm_tensor_applicable(int m, int n, int k);

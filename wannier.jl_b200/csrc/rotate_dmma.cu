@@ -43,9 +43,7 @@ struct DmmaPlan {
     cplx* d_dNp = nullptr;        // [pairs][WM][nw]  per-warp-row partial diagonals
     double* d_frop = nullptr;     // [pairs][nct][8]
     size_t smem = 0;
-    // scratch of the batched-GEMM engine (wb_zgemm_dmma), sized on first use
-    double* g_At = nullptr; double* g_Bp = nullptr; cplx* g_dNp = nullptr; double* g_frop = nullptr;
-    int32_t* g_iota = nullptr; int g_count = 0;
+    double* d_froM = nullptr;     // [pairs] ||M_kb||_F^2 (nb == nw: the gauge-invariant norm of N_kb for unitary U)
 };
 
 namespace {
@@ -116,7 +114,7 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 // A-operand image of M.  Chunk c = [wm][ks][j(6)][lane] double2; the 12 doubles of a lane are
 //   (re, im, re+im) of mt = 0..3 with row = wm*32 + mt*8 + lane/4, col = c*KC + ks*4 + lane%4.
 __global__ void tile_overlaps_kernel(int nb, int WM, int KC, int nch, const cplx* __restrict__ M,
-                                     double* __restrict__ Mt, int conj_transpose = 0) {
+                                     double* __restrict__ Mt) {
     const long long pair = blockIdx.x;
     const int c = blockIdx.y;
     const int KS = KC / 4;
@@ -131,8 +129,7 @@ __global__ void tile_overlaps_kernel(int nb, int WM, int KC, int nch, const cplx
         for (int mt = 0; mt < 4; mt++) {
             const int row = wm * 32 + mt * 8 + (lane >> 2);
             cplx v = make_double2(0.0, 0.0);
-            if (row < nb && col < nb)   // conj_transpose: the A operand is src^H (Stiefel GEMMs X^H X, X^H G)
-                v = conj_transpose ? cconj(src[col + (long long)row * nb]) : src[row + (long long)col * nb];
+            if (row < nb && col < nb) v = src[row + (long long)col * nb];
             q[3 * mt] = v.x;
             q[3 * mt + 1] = v.y;
             q[3 * mt + 2] = v.x + v.y;
@@ -183,7 +180,9 @@ __global__ void __launch_bounds__(256) pack_gauge_kernel(int nb, int nw, int WN,
     pack_gauge_row(nb, nw, WN, KC, nch, nct, kg, blockIdx.y, U, Up);
 }
 // ---- the rotation kernel ---------------------------------------------------------------------
-template <int WM, int WN, int KC, int STAGES>
+// NORM = false: ||MU_kb||_F^2 is not accumulated (square gauges: the norm of N_kb is gauge invariant for unitary U and
+// was computed from M once; a third of the epilogue's CUDA-core FP64 work, which competes with the DMMAs for the pipe)
+template <int WM, int WN, int KC, int STAGES, bool NORM>
 __global__ void __launch_bounds__(384, 1)
 rotate_dmma_kernel(int nb, int nw, int nn, int nch, int nct, int k_begin, int k_off,
                    const int32_t* __restrict__ kpb, const double* __restrict__ Mt,
@@ -341,8 +340,10 @@ rotate_dmma_kernel(int nb, int nw, int nn, int nch, int nct, int k_begin, int k_
 #endif
 #ifndef WB_EPI_NOMATH
             cfma_conj(d[nt][j], uk[e * 32], xv);
-            f = fma(xv.x, xv.x, f);
-            f = fma(xv.y, xv.y, f);
+            if (NORM) {
+                f = fma(xv.x, xv.x, f);
+                f = fma(xv.y, xv.y, f);
+            }
 #endif
         }
     };
@@ -358,7 +359,7 @@ rotate_dmma_kernel(int nb, int nw, int nn, int nch, int nct, int k_begin, int k_
                     d[nt][j].y += __shfl_xor_sync(0xffffffffu, d[nt][j].y, o);
                 }
             }
-        f = warp_sum(f);
+        if (NORM) f = warp_sum(f);
         if (g == 0) {
 #pragma unroll
             for (int nt = 0; nt < 2; nt++)
@@ -368,7 +369,7 @@ rotate_dmma_kernel(int nb, int nw, int nn, int nch, int nct, int k_begin, int k_
                     if (n < nw) dNp[(epi_pair * WM + wm) * nw + n] = d[nt][j];
                 }
         }
-        if (lane == 0) frop[(epi_pair * nct + ct) * 8 + warp] = f;
+        if (NORM && lane == 0) frop[(epi_pair * nct + ct) * 8 + warp] = f;
     };
 
 #ifdef WB_TIMING
@@ -802,10 +803,6 @@ rotate_small_ring_kernel(int nb, int nw, int nn, long long pair0, long long pair
     }
 }
 
-struct RotateOverride {
-    const int32_t* iota; const double* At; const double* Bp; cplx* C; cplx* dNp; double* frop;
-};
-
 template <int WM, int WN, int KC, int STAGES>
 size_t smem_bytes() {
     constexpr int KS = KC / 4;
@@ -814,24 +811,37 @@ size_t smem_bytes() {
 }
 
 template <int WM, int WN, int KC, int STAGES>
-int launch_rotate(wb200_ctx* ctx, const cplx* dU, int ka, int kb, const RotateOverride* ov = nullptr, int phase = 0) {
+int launch_rotate(wb200_ctx* ctx, const cplx* dU, int ka, int kb, int phase, bool norm) {
     DmmaPlan* p = ctx->dmma;
-    auto kern = rotate_dmma_kernel<WM, WN, KC, STAGES>;
-    static bool attr_done[16] = {false};
-    if (!attr_done[ctx->device & 15]) {
-        WB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
-        attr_done[ctx->device & 15] = true;
+    if (!ctx->rot_attr_done) {   // once per ctx (contexts of different devices share the instantiations)
+        WB_CUDA(ctx, cudaFuncSetAttribute(rotate_dmma_kernel<WM, WN, KC, STAGES, true>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
+        WB_CUDA(ctx, cudaFuncSetAttribute(rotate_dmma_kernel<WM, WN, KC, STAGES, false>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
+        ctx->rot_attr_done = 1;
     }
-    if (ov)   // batched-GEMM use: one "pair" per matrix, neighbour table = identity
-        kern<<<(kb - ka) * p->nct, 384, p->smem, ctx->stream>>>(ctx->nb, ctx->nw, 1, p->nch, p->nct, 0, ka, ov->iota,
-                                                              ov->At, ov->Bp, dU, ov->C, ov->dNp, ov->frop, nullptr, nullptr, 0);
-    else
-        kern<<<(kb - ka) * p->nct, 384, p->smem, ctx->stream>>>(ctx->nb, ctx->nw, ctx->nn, p->nch, p->nct,
-                                                              ctx->k_begin, ka, ctx->d_kpb, p->d_Mt, p->d_Up,
-                                                              dU, ctx->d_MU, p->d_dNp, p->d_frop, ctx->d_border, ctx->d_nloc,
-                                                              phase);
+    auto kern = norm ? rotate_dmma_kernel<WM, WN, KC, STAGES, true> : rotate_dmma_kernel<WM, WN, KC, STAGES, false>;
+    kern<<<(kb - ka) * p->nct, 384, p->smem, ctx->stream>>>(ctx->nb, ctx->nw, ctx->nn, p->nch, p->nct, ctx->k_begin, ka,
+                                                          ctx->d_kpb, p->d_Mt, p->d_Up, dU, ctx->d_MU, p->d_dNp, p->d_frop,
+                                                          ctx->d_border, ctx->d_nloc, phase);
     WB_LAUNCH_CHECK(ctx);
     return WB200_OK;
+}
+
+// ||M_kb||_F^2 per pair, one CTA per pair (fixed-order tree)
+__global__ void __launch_bounds__(256) overlap_norm_kernel(int nb, const cplx* __restrict__ M, double* __restrict__ out) {
+    const cplx* m = M + (long long)blockIdx.x * nb * nb;
+    double s = 0.0;
+    for (int e = threadIdx.x; e < nb * nb; e += blockDim.x) s = fma(m[e].x, m[e].x, fma(m[e].y, m[e].y, s));
+    __shared__ double sh[8];
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; w++) t += sh[w];
+        out[blockIdx.x] = t;
+    }
 }
 
 }  // namespace
@@ -873,6 +883,14 @@ int wb_dmma_plan_create(wb200_ctx* ctx, const double* /*hM*/) {
     dim3 grid((unsigned)pairs, (unsigned)p->nch);
     tile_overlaps_kernel<<<grid, 128, 0, ctx->stream>>>(nb, p->WM, p->KC, p->nch, ctx->d_M, p->d_Mt);
     WB_LAUNCH_CHECK(ctx);
+    if (!p->small && nb == nw) {
+        const char* e = getenv("WB200_CONST_NORM");
+        if (!(e && e[0] == '0')) {
+            WB_CUDA(ctx, cudaMalloc(&p->d_froM, sizeof(double) * pairs));
+            overlap_norm_kernel<<<(unsigned)pairs, 256, 0, ctx->stream>>>(nb, ctx->d_M, p->d_froM);
+            WB_LAUNCH_CHECK(ctx);
+        }
+    }
     WB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     cudaFree(ctx->d_M);
     ctx->d_M = nullptr;
@@ -886,11 +904,7 @@ void wb_dmma_plan_destroy(wb200_ctx* ctx) {
     if (p->d_Up) cudaFree(p->d_Up);
     if (p->d_dNp) cudaFree(p->d_dNp);
     if (p->d_frop) cudaFree(p->d_frop);
-    if (p->g_At) cudaFree(p->g_At);
-    if (p->g_Bp) cudaFree(p->g_Bp);
-    if (p->g_dNp) cudaFree(p->g_dNp);
-    if (p->g_frop) cudaFree(p->g_frop);
-    if (p->g_iota) cudaFree(p->g_iota);
+    if (p->d_froM) cudaFree(p->d_froM);
     delete p;
     ctx->dmma = nullptr;
 }
@@ -976,13 +990,15 @@ int wb_rotate_dmma(wb200_ctx* ctx, const cplx* dU, int ka, int kb, int phase) {
     }
     {
         ProfScope ps(ctx, 1);
-        if (p->WM == 2) WB_TRY((launch_rotate<WB_CFG_64>(ctx, dU, ka, kb, nullptr, phase)));
-        else if (p->WM == 4) WB_TRY((launch_rotate<WB_CFG_128>(ctx, dU, ka, kb, nullptr, phase)));
-        else WB_TRY((launch_rotate<WB_CFG_256>(ctx, dU, ka, kb, nullptr, phase)));
+        const bool norm = p->d_froM == nullptr;
+        if (p->WM == 2) WB_TRY((launch_rotate<WB_CFG_64>(ctx, dU, ka, kb, phase, norm)));
+        else if (p->WM == 4) WB_TRY((launch_rotate<WB_CFG_128>(ctx, dU, ka, kb, phase, norm)));
+        else WB_TRY((launch_rotate<WB_CFG_256>(ctx, dU, ka, kb, phase, norm)));
     }
     // per-warp partial diagonals and norms are summed (fixed order) by pair_reduce_kernel itself
     ctx->dn_src = p->d_dNp; ctx->dn_parts = p->WM;
-    ctx->fro_src = p->d_frop; ctx->fro_parts = p->nct * 8;
+    if (p->d_froM) { ctx->fro_src = p->d_froM; ctx->fro_parts = 1; }
+    else { ctx->fro_src = p->d_frop; ctx->fro_parts = p->nct * 8; }
     return WB200_OK;
 }
 
@@ -991,52 +1007,3 @@ extern "C" int wb200_debug_set_timing_buffer(long long* dptr) {
     return cudaMemcpyToSymbol(wb_dbg, &dptr, sizeof(dptr)) == cudaSuccess ? 0 : -2;
 }
 #endif
-
-// ---------------------------------------------------------------------------------------------
-// Batched square complex GEMM on the tensor pipe:  C[i] = op(A[i]) * B[i],  op = identity or ^H,
-// for `count` contiguous n x n matrices with n = ctx->nb = ctx->nw (the Stiefel GEMMs of
-// max_localize at large n: X^H X, X T, X^H G, X S).  It is the rotation kernel with one "pair" per
-// matrix: A is tiled (optionally conjugate-transposed) and B packed into the operand images first.
-// ---------------------------------------------------------------------------------------------
-bool wb_zgemm_dmma_applicable(const wb200_ctx* ctx, int nrow, int ncol) {
-    return ctx->dmma && !ctx->dmma->small && nrow == ncol && nrow == ctx->nb && ctx->nb == ctx->nw;
-}
-
-__global__ void iota_kernel(int n, int32_t* out) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = i;
-}
-
-int wb_zgemm_dmma(wb200_ctx* ctx, int transA, const cplx* A, const cplx* B, cplx* C, int count) {
-    DmmaPlan* p = ctx->dmma;
-    const int n = ctx->nb;
-    if (count > p->g_count) {
-        if (p->g_At) cudaFree(p->g_At);
-        if (p->g_Bp) cudaFree(p->g_Bp);
-        if (p->g_dNp) cudaFree(p->g_dNp);
-        if (p->g_frop) cudaFree(p->g_frop);
-        if (p->g_iota) cudaFree(p->g_iota);
-        p->g_At = p->g_Bp = p->g_frop = nullptr; p->g_dNp = nullptr; p->g_iota = nullptr; p->g_count = 0;
-        WB_CUDA(ctx, cudaMalloc(&p->g_At, sizeof(double) * (size_t)count * p->nch * p->a_stage));
-        WB_CUDA(ctx, cudaMalloc(&p->g_Bp, sizeof(double) * (size_t)count * p->nct * p->nch * p->b_stage));
-        WB_CUDA(ctx, cudaMalloc(&p->g_dNp, sizeof(cplx) * (size_t)count * p->WM * n));
-        WB_CUDA(ctx, cudaMalloc(&p->g_frop, sizeof(double) * (size_t)count * p->nct * 8));
-        WB_CUDA(ctx, cudaMalloc(&p->g_iota, sizeof(int32_t) * count));
-        iota_kernel<<<(count + 255) / 256, 256, 0, ctx->stream>>>(count, p->g_iota);
-        WB_LAUNCH_CHECK(ctx);
-        p->g_count = count;
-    }
-    dim3 gt((unsigned)count, (unsigned)p->nch);
-    tile_overlaps_kernel<<<gt, 128, 0, ctx->stream>>>(n, p->WM, p->KC, p->nch, A, p->g_At, transA);
-    WB_LAUNCH_CHECK(ctx);
-    dim3 gp((unsigned)count, (unsigned)p->nct);
-    pack_gauge_kernel<<<gp, 256, 0, ctx->stream>>>(n, n, p->WN, p->KC, p->nch, p->nct, nullptr, nullptr, nullptr, B,
-                                                  p->g_Bp);
-    WB_LAUNCH_CHECK(ctx);
-    RotateOverride ov{p->g_iota, p->g_At, p->g_Bp, C, p->g_dNp, p->g_frop};
-    // the kernel's diag epilogue needs some n x n array per matrix for its U_k tile: B serves
-    if (p->WM == 2) WB_TRY((launch_rotate<WB_CFG_64>(ctx, B, 0, count, &ov)));
-    else if (p->WM == 4) WB_TRY((launch_rotate<WB_CFG_128>(ctx, B, 0, count, &ov)));
-    else WB_TRY((launch_rotate<WB_CFG_256>(ctx, B, 0, count, &ov)));
-    return WB200_OK;
-}
