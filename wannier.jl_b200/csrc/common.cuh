@@ -256,7 +256,10 @@ int wb_halo_fetch(wb200_ctx* ctx, cplx* dU);   // copy the remote rows of `need`
 int wb_project_tangent_dev(wb200_ctx* ctx, const cplx* dX, cplx* dG, int nrow, int ncol, int count);
 // tangent_step: X = X0 + a s with X0 on the manifold and s tangent at X0, hence X^H X = I + a^2 s^H s: every
 // singular value is >= 1, which the scaled Newton-Schulz iteration of the large-shape path exploits
-int wb_retract_dev(wb200_ctx* ctx, cplx* dX, int nrow, int ncol, int count, int* iters, bool tangent_step = false);
+struct WbTangentGram { const cplx* S; double alpha, fro_max; };   // S_k = s_k^H s_k of the search direction, max_k ||S_k||_F
+int wb_retract_dev(wb200_ctx* ctx, cplx* dX, int nrow, int ncol, int count, int* iters, bool tangent_step = false,
+                   const WbTangentGram* gram = nullptr);
+int wb_tangent_gram(wb200_ctx* ctx, const cplx* ds, int nrow, int ncol, int count, cplx* dS, double* fro_max, bool* ok);
 // st: distance in complex elements between the [X_k; Y_k] blocks of consecutive k (0: nw*nw + nb*nw, the
 // packed XY array; the MagModel array interleaves the up and down blocks, st = 2 (nw*nw + nb*nw))
 int wb_retract_xy(wb200_ctx* ctx, cplx* dXY, bool tangent_step = false, long long st = 0);

@@ -232,12 +232,36 @@ struct Problem {
     int n_fg = 0;
     const WbCustomProblem* custom = nullptr;   // mode 3
     Trace trace;
+    // mode 0, large n: S = s^H s of the current search direction (every trial point of the line search has
+    // X^H X = I + alpha^2 S, which saves the first GEMM and the first host round trip of each retraction)
+    cplx* dS = nullptr;
+    WbTangentGram gram{nullptr, 0.0, 0.0};
+    int prepare_direction(const cplx* s) {
+        gram.S = nullptr;
+        if (mode != 0) return WB200_OK;
+        if (!dS) {
+            if (wb_small_applicable(ctx->nb, ctx->nw) || (ctx->flags & WB200_FLAG_NO_TENSOR) ||
+                !wb_zgemm_tensor_applicable(ctx->nw, ctx->nw, ctx->nb)) return WB200_OK;
+            WB_CUDA(ctx, cudaMalloc(&dS, sizeof(cplx) * (size_t)ctx->nk * ctx->nw * ctx->nw));
+        }
+        bool ok = false;
+        double fro = 0.0;
+        WB_TRY(wb_tangent_gram(ctx, s, ctx->nb, ctx->nw, ctx->nk, dS, &fro, &ok));
+        if (ok) { gram.S = dS; gram.fro_max = fro; }
+        return WB200_OK;
+    }
+    ~Problem() { if (dS) cudaFree(dS); }
 
     // tangent_step: x = x0 + a s with x0 on the manifold and s tangent at x0 (every trial point of a line search)
-    int retract(cplx* x, bool tangent_step = false) {
+    // alpha > 0: x = x0 + alpha s with s the direction prepare_direction() saw
+    int retract(cplx* x, bool tangent_step = false, double alpha = 0.0) {
         if (mode == 3) return custom->retract(x, tangent_step);
         if (mode == 2) return wb_retract_dev(ctx, x, ctx->nw, ctx->nw, 1, nullptr, tangent_step);
-        if (mode == 0) return wb_retract_dev(ctx, x, ctx->nb, ctx->nw, ctx->nk, nullptr, tangent_step);
+        if (mode == 0) {
+            gram.alpha = alpha;
+            return wb_retract_dev(ctx, x, ctx->nb, ctx->nw, ctx->nk, nullptr, tangent_step,
+                                  (tangent_step && alpha > 0.0 && gram.S) ? &gram : nullptr);
+        }
         return wb_retract_xy(ctx, x, tangent_step);
     }
     int project(const cplx* x, cplx* g) {
@@ -443,6 +467,7 @@ static int lbfgs_run(wb200_ctx* ctx, int mode, const WbCustomProblem* custom, cp
             dphi0 = -gg;
             hist_reset = true;
         }
+        WB_TRY(P.prepare_direction((const cplx*)s));
         const double f_prev = f;
         double last_alpha = -1.0, last_f = 0.0;
         HagerZhang hz;
@@ -455,7 +480,7 @@ static int lbfgs_run(wb200_ctx* ctx, int mode, const WbCustomProblem* custom, cp
             }
             {
                 TraceScope ts_(P.trace, 0, ctx->stream);
-                int st = P.retract((cplx*)xn, true);
+                int st = P.retract((cplx*)xn, true, a);
                 if (st == WB200_ERR_NOCONV) ctx->poison_next = 1;   // this trial point is rejected on every rank
                 else WB_TRY(st);
             }
