@@ -594,8 +594,8 @@ constexpr uint32_t SR_SLOT_BYTES = SR_A_BYTES + 2 * SR_B_BYTES;   // 12288
 constexpr size_t SR_RING_BYTES = (size_t)4 * SR_SLOTS * SR_SLOT_BYTES;
 constexpr size_t SR_SMEM = SR_RING_BYTES + 8 * 2 * 4 * SR_SLOTS;
 
-// FULL: nb > 28 and nw > 24, nothing to skip: no predicates in the main loop
-template <bool FULL>
+// FULL: nb > 28 and nw > 24, nothing to skip: no predicates in the main loop.  NORM as in rotate_dmma_kernel.
+template <bool FULL, bool NORM>
 __global__ void __launch_bounds__(384, 1)
 rotate_small_ring_kernel(int nb, int nw, int nn, long long pair0, long long pair_end, int k_begin,
                          const int32_t* __restrict__ kpb, const double* __restrict__ Mt,
@@ -687,7 +687,7 @@ rotate_small_ring_kernel(int nb, int nw, int nn, long long pair0, long long pair
                 mbar_wait(full, (uint32_t)(u / SR_SLOTS) & 1u);
                 if (lane == 0) mbar_arrive(full + 8u);
             }
-            if (lane == 0) frop[(my0 + i) * 2 + half] = 0.0;
+            if (NORM && lane == 0) frop[(my0 + i) * 2 + half] = 0.0;
         }
         return;
     }
@@ -775,7 +775,7 @@ rotate_small_ring_kernel(int nb, int nw, int nn, long long pair0, long long pair
                         mu[m + (long long)n * nb] = x;
                         cfma_conj(d[nt][j], uk[(mt * 2 + nt) * 2 + j], x);
                     }
-                    f4[nt][j] = fma(x.x, x.x, fma(x.y, x.y, f4[nt][j]));
+                    if (NORM) f4[nt][j] = fma(x.x, x.x, fma(x.y, x.y, f4[nt][j]));
                 }
 #pragma unroll
         for (int nt = 0; nt < 2; nt++)
@@ -787,7 +787,8 @@ rotate_small_ring_kernel(int nb, int nw, int nn, long long pair0, long long pair
                     d[nt][j].y += __shfl_xor_sync(0xffffffffu, d[nt][j].y, o);
                 }
             }
-        const double f = warp_sum((f4[0][0] + f4[0][1]) + (f4[1][0] + f4[1][1]));
+        double f = 0.0;
+        if (NORM) f = warp_sum((f4[0][0] + f4[0][1]) + (f4[1][0] + f4[1][1]));
         if (g == 0) {
 #pragma unroll
             for (int nt = 0; nt < 2; nt++)
@@ -797,7 +798,7 @@ rotate_small_ring_kernel(int nb, int nw, int nn, long long pair0, long long pair
                     if (n < nw) dN[p * nw + n] = d[nt][j];
                 }
         }
-        if (lane == 0) frop[p * 2 + half] = f;
+        if (NORM && lane == 0) frop[p * 2 + half] = f;
         fresh = ++bi == nn;
         if (fresh) { bi = 0; kl++; }
     }
@@ -883,7 +884,7 @@ int wb_dmma_plan_create(wb200_ctx* ctx, const double* /*hM*/) {
     dim3 grid((unsigned)pairs, (unsigned)p->nch);
     tile_overlaps_kernel<<<grid, 128, 0, ctx->stream>>>(nb, p->WM, p->KC, p->nch, ctx->d_M, p->d_Mt);
     WB_LAUNCH_CHECK(ctx);
-    if (!p->small && nb == nw) {
+    if (nb == nw) {
         const char* e = getenv("WB200_CONST_NORM");
         if (!(e && e[0] == '0')) {
             WB_CUDA(ctx, cudaMalloc(&p->d_froM, sizeof(double) * pairs));
@@ -955,28 +956,26 @@ int wb_rotate_dmma(wb200_ctx* ctx, const cplx* dU, int ka, int kb, int phase) {
     ctx->dn_src = nullptr;
     if (p->small) {
         const long long p0 = (long long)ka * ctx->nn, p1 = (long long)kb * ctx->nn;
+        bool ring_used = false;
         {
             ProfScope ps(ctx, 1);
             if (p->small_ring && p1 - p0 >= p->small_ring_min) {
-                static bool attr_done[16] = {false};
-                if (!attr_done[ctx->device & 15]) {
-                    WB_CUDA(ctx, cudaFuncSetAttribute(rotate_small_ring_kernel<true>,
-                                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SR_SMEM));
-                    WB_CUDA(ctx, cudaFuncSetAttribute(rotate_small_ring_kernel<false>,
-                                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SR_SMEM));
-                    attr_done[ctx->device & 15] = true;
+                if (!ctx->rot_attr_done) {
+                    WB_CUDA(ctx, cudaFuncSetAttribute(rotate_small_ring_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SR_SMEM));
+                    WB_CUDA(ctx, cudaFuncSetAttribute(rotate_small_ring_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SR_SMEM));
+                    WB_CUDA(ctx, cudaFuncSetAttribute(rotate_small_ring_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SR_SMEM));
+                    WB_CUDA(ctx, cudaFuncSetAttribute(rotate_small_ring_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SR_SMEM));
+                    ctx->rot_attr_done = 1;
                 }
                 // persistent: one CTA per SM, each a contiguous range of pairs (4 in flight per CTA)
                 const long long want = (p1 - p0 + 3) / 4;
                 const int grid = (int)(want < p->num_sms ? want : p->num_sms);
-                if (ctx->nb > 28 && ctx->nw > 24)
-                    rotate_small_ring_kernel<true><<<grid, 384, SR_SMEM, ctx->stream>>>(
-                        ctx->nb, ctx->nw, ctx->nn, p0, p1, ctx->k_begin, ctx->d_kpb, p->d_Mt, p->d_Up, dU, ctx->d_MU,
-                        ctx->d_dN, p->d_frop);
-                else
-                    rotate_small_ring_kernel<false><<<grid, 384, SR_SMEM, ctx->stream>>>(
-                        ctx->nb, ctx->nw, ctx->nn, p0, p1, ctx->k_begin, ctx->d_kpb, p->d_Mt, p->d_Up, dU, ctx->d_MU,
-                        ctx->d_dN, p->d_frop);
+                const bool full = ctx->nb > 28 && ctx->nw > 24, norm = p->d_froM == nullptr;
+                auto kern = full ? (norm ? rotate_small_ring_kernel<true, true> : rotate_small_ring_kernel<true, false>)
+                                 : (norm ? rotate_small_ring_kernel<false, true> : rotate_small_ring_kernel<false, false>);
+                kern<<<grid, 384, SR_SMEM, ctx->stream>>>(ctx->nb, ctx->nw, ctx->nn, p0, p1, ctx->k_begin, ctx->d_kpb, p->d_Mt,
+                                                          p->d_Up, dU, ctx->d_MU, ctx->d_dN, p->d_frop);
+                ring_used = true;
             } else {
                 rotate_small_kernel<<<(unsigned)((p1 - p0 + 3) / 4), 256, 0, ctx->stream>>>(
                     ctx->nb, ctx->nw, ctx->nn, p0, p1, ctx->k_begin, ctx->d_kpb, p->d_Mt, p->d_Up, dU, ctx->d_MU,
@@ -984,8 +983,8 @@ int wb_rotate_dmma(wb200_ctx* ctx, const cplx* dU, int ka, int kb, int phase) {
             }
         }
         WB_LAUNCH_CHECK(ctx);
-        ctx->fro_src = p->d_frop;   // pair_reduce_kernel adds the two half-tile norms itself
-        ctx->fro_parts = 2;
+        if (ring_used && p->d_froM) { ctx->fro_src = p->d_froM; ctx->fro_parts = 1; }
+        else { ctx->fro_src = p->d_frop; ctx->fro_parts = 2; }   // pair_reduce_kernel adds the two half-tile norms itself
         return WB200_OK;
     }
     {
