@@ -96,3 +96,60 @@ def test_multi_create_errors(w, valence):
     st = dict(kpb_k=valence["kpb_k"], bvec=valence["bvec"], wb=valence["wb"])
     with pytest.raises(w.WB200Error):
         _multi(w, st, valence["M"], 4, [0, 99])          # no such device
+
+
+_PEER_SCRIPT = r"""
+import sys, numpy as np
+sys.path.insert(0, {root!r}); sys.path.insert(0, {root!r} + "/tests")
+import __graft_entry__ as ge
+w = ge.load_package()
+from oracle import spread_oracle as so
+for lat, grid, nb, nw, ndev in [("cubic", (4, 2, 2), 72, 72, 2), ("cubic", (3, 2, 2), 72, 40, 3), ("bcc", (4, 2, 2), 16, 16, 2)]:
+    st, M, U = w.synthetic.make_model_arrays(lat, grid, nb, nw, eps=0.02)
+    nk, nn = st["kpb_k"].shape
+    m = w.MultiContext(nb, nw, nk, nn, st["kpb_k"], st["bvec"], st["wb"], w.api.to_abi_M(M), devices=[0] * ndev)
+    G = np.empty((nk, nw, nb), dtype=np.complex128)
+    Ua = w.api.to_abi_U(U)
+    # page-locked host arrays: a copy to / from pageable memory blocks its host thread inside the driver, and with
+    # both slabs in ONE CUDA context that stalls the other slab's launches — which the blocked copy is waiting for
+    w.lib.host_register(Ua); w.lib.host_register(G)
+    for rep in range(3):                       # consecutive evaluations: flag epochs, both all-reduce parities
+        f = m.fg(Ua, G=G)
+    f_ref, G_ref = so.fg_maxloc(M, st["kpb_k"], st["bvec"], st["wb"], U)
+    assert abs(f - f_ref) < 1e-10 * abs(f_ref), (f, f_ref)
+    assert np.abs(G.transpose(0, 2, 1) - G_ref).max() < 1e-10 * np.abs(G_ref).max()
+    out5, om, r, mn = m.spread(Ua)                         # exact split: raw rows pulled, min over the slabs
+    ref = so.omega(M, st["kpb_k"], st["bvec"], st["wb"], U)
+    assert abs(out5[1] - ref["OmegaI"]) < 1e-10 * max(1.0, abs(ref["Omega"]))
+    if nb == nw:
+        U2 = w.api.to_abi_U(U)
+        w.lib.host_register(U2)
+        f2, it2, nfg2 = m.max_localize(U2, f_tol=1e-10, g_tol=1e-7, max_iter=5)
+        w.lib.host_unregister(U2)
+        ctx = w.Context(nb, nw, nk, nn, st["kpb_k"], st["bvec"], st["wb"], w.api.to_abi_M(M))
+        U1 = w.api.to_abi_U(U)
+        f1, it1, nfg1 = ctx.max_localize(U1, f_tol=1e-10, g_tol=1e-7, max_iter=5)
+        ctx.close()
+        assert (it1, nfg1) == (it2, nfg2) and abs(f1 - f2) < 1e-9 * abs(f1) and np.abs(U1 - U2).max() < 1e-8
+    w.lib.host_unregister(Ua); w.lib.host_unregister(G)
+    m.close()
+print("PEER-OK")
+"""
+
+
+def test_peer_memory_collectives_on_one_gpu():
+    """peer.cu (readiness flags, packed-halo pull by the copy engines, the in-library all-reduce kernel) between
+    slabs of ONE device, so that a one-GPU box exercises the code the multi-GPU runs use.  In a subprocess with a
+    short spin timeout: the kernels spin on flags, and between slabs of one device forward progress rests on their
+    streams landing in different hardware queues (hence the documented one-slab-per-device rule for production)."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    # WB200_PEER_PULL=kernel: copy engines run their queues in order, so on ONE device a pull parked behind its wait
+    # kernel would hold up the other slab's host copies (with one slab per device the engines are separate).
+    # eager module loading: with lazy loading the first launch of a kernel waits for the context to drain, i.e. for a
+    # spinning wait kernel of the OTHER slab of the same device, which waits for exactly that launch
+    env = dict(os.environ, WB200_PEER_COMM="force", WB200_SPIN_TIMEOUT_MS="5000", CUDA_DEVICE_MAX_CONNECTIONS="32",
+               CUDA_MODULE_LOADING="EAGER", WB200_PEER_PULL="kernel")
+    p = subprocess.run([sys.executable, "-c", _PEER_SCRIPT.format(root=root)], env=env, capture_output=True, text=True,
+                       timeout=300)
+    assert p.returncode == 0 and "PEER-OK" in p.stdout, p.stdout[-2000:] + p.stderr[-2000:]

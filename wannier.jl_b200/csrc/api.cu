@@ -397,6 +397,8 @@ static int upload_U(wb200_ctx* ctx, const double* U) {
 
 // Sub-slab plan of the pipelined host entry point: contiguous k sub-slabs and, for each, the
 // sub-slabs of U its pairs read (from kpb_k).  Built once per ctx.
+static int ensure_pipeline(wb200_ctx* ctx, const std::vector<int32_t>& kpb_host);
+int wb_ensure_pipeline(wb200_ctx* ctx) { return ensure_pipeline(ctx, ctx->h_kpb); }
 static int ensure_pipeline(wb200_ctx* ctx, const std::vector<int32_t>& kpb_host) {
     if (!ctx->sub_bounds.empty()) return WB200_OK;
     const int nk = ctx->nk;

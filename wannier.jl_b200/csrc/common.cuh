@@ -109,9 +109,11 @@ struct wb200_ctx {
     unsigned long long** d_comm = nullptr;        // [world] device array: rank q's comm buffer
     unsigned long long* my_comm = nullptr;        // comm_ptrs[rank]
     int comm_maxc = 0;                            // doubles per all-reduce slot
+    unsigned long long spin_timeout_ns = 20000000000ull;
     unsigned long long epoch = 0, ar_epoch = 0;   // evaluation / all-reduce counters (identical on every rank)
     unsigned peer_mask = 0;                       // ranks owning rows this slab reads
     std::vector<void*> h_peerUp;                  // packed-gauge arrays of the ranks (wb200_set_peer_packed)
+    int peer_pull_kernel = 0;                     // pull with a kernel instead of the copy engines (WB200_PEER_PULL=kernel)
     struct HaloRun { int owner, k0, count; };
     std::vector<HaloRun> halo_runs;               // contiguous runs of remote rows with one owner
     wb200_allreduce_fn allreduce = nullptr;   // caller-supplied collective (sharded optimiser)
@@ -229,6 +231,7 @@ struct ProfScope {
 
 // ---- api.cu ----
 int wb_allreduce(wb200_ctx* ctx, double* dptr, int count, int op);   // checked call of the registered collective
+int wb_ensure_pipeline(wb200_ctx* ctx);   // copy streams / events of the host-pointer entry points
 
 // ---- peer.cu ----
 #define WB_COMM_MAXR 32

@@ -215,7 +215,13 @@ extern "C" int wb200_multi_create(wb200_multi** out, const int* devices, int nde
     bool distinct = ndev <= WB_COMM_MAXR;
     for (int r = 0; r < ndev; r++)
         for (int q = 0; q < r; q++) distinct = distinct && devices[r] != devices[q];
-    { const char* e = getenv("WB200_PEER_COMM"); if (e && e[0] == '0') distinct = false; }
+    {   // WB200_PEER_COMM=0: host-side all-reduce everywhere; =force: peer-memory collectives even between slabs of one
+        // device (the test suite does this in a subprocess to cover peer.cu on a one-GPU box; forward progress then
+        // rests on the slabs' streams landing in different hardware queues)
+        const char* e = getenv("WB200_PEER_COMM");
+        if (e && e[0] == '0') distinct = false;
+        if (e && e[0] == 'f' && ndev <= WB_COMM_MAXR) distinct = true;
+    }
     const bool peer_comm = distinct && ndev > 1;
     m->flags.assign(ndev, nullptr);
     const size_t comm_bytes = wb200_peer_comm_bytes(nw);

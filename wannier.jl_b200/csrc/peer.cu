@@ -26,13 +26,14 @@ namespace {
 constexpr int MAXR = WB_COMM_MAXR;
 constexpr int OFF_READY = 0, OFF_PACKED = MAXR, OFF_ARFLAG = 2 * MAXR, OFF_SLOTS = 4 * MAXR;
 
-__device__ __forceinline__ void spin_until(const volatile unsigned long long* f, unsigned long long epoch) {
+__device__ __forceinline__ void spin_until(const volatile unsigned long long* f, unsigned long long epoch,
+                                           unsigned long long timeout_ns) {
     unsigned long long t0;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-    while (*f < epoch) {   // bounded (~20 s): a peer that died must not hang the device
+    while (*f < epoch) {   // bounded (20 s unless WB200_SPIN_TIMEOUT_MS says otherwise): a dead peer must not hang the device
         unsigned long long t;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-        if (t - t0 > 20000000000ull) __trap();
+        if (t - t0 > timeout_ns) __trap();
         __nanosleep(100);
     }
 }
@@ -47,10 +48,10 @@ __global__ void flag_signal_kernel(int world, int rank, unsigned long long* cons
 }
 // one thread per peer this slab reads from: spin on the LOCAL flag word until that peer has published `epoch`
 __global__ void flag_wait_kernel(int world, unsigned mask, const unsigned long long* mine, int off,
-                                 unsigned long long epoch) {
+                                 unsigned long long epoch, unsigned long long timeout_ns) {
     const int q = threadIdx.x;
     if (q >= world || !((mask >> q) & 1u)) return;
-    spin_until(mine + off + q, epoch);
+    spin_until(mine + off + q, epoch, timeout_ns);
     __threadfence_system();
 }
 
@@ -58,7 +59,8 @@ __global__ void flag_wait_kernel(int world, unsigned mask, const unsigned long l
 // the optimiser's "sums + max" pair).
 __global__ void __launch_bounds__(256) peer_allreduce_kernel(int world, int rank, unsigned long long* const* __restrict__ comm,
                                                              int maxc, unsigned long long epoch, double* __restrict__ x,
-                                                             int count, int op, int count2, int op2) {
+                                                             int count, int op, int count2, int op2,
+                                                             unsigned long long timeout_ns) {
     const int par = (int)(epoch & 1ull);
     const int n = count + count2;
     // 1. my contribution into slot [par][rank] of every rank's buffer (my own included)
@@ -73,7 +75,7 @@ __global__ void __launch_bounds__(256) peer_allreduce_kernel(int world, int rank
         *(volatile unsigned long long*)(comm[threadIdx.x] + OFF_ARFLAG + par * MAXR + rank) = epoch;
     }
     // 2. every contribution has landed in MY buffer
-    if (threadIdx.x < world) spin_until(comm[rank] + OFF_ARFLAG + par * MAXR + threadIdx.x, epoch);
+    if (threadIdx.x < world) spin_until(comm[rank] + OFF_ARFLAG + par * MAXR + threadIdx.x, epoch, timeout_ns);
     __syncthreads();
     __threadfence_system();
     // 3. reduce in rank order (identical on every rank)
@@ -87,6 +89,12 @@ __global__ void __launch_bounds__(256) peer_allreduce_kernel(int world, int rank
         }
         x[i] = acc;
     }
+}
+
+// the pull as a kernel (a few CTAs) instead of a copy-engine transfer, for slabs that share a device: copy engines
+// run their queues in order, so a pull parked behind its wait kernel would hold up the OTHER slab's host copies
+__global__ void __launch_bounds__(256) peer_copy_kernel(double2* __restrict__ dst, const double2* __restrict__ src, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
 }
 
 int builtin_allreduce(void* dptr, int count, int op, void* /*stream*/, void* user) {
@@ -106,7 +114,7 @@ int wb_peer_allreduce(wb200_ctx* ctx, double* dptr, int count, int op, int count
     }
     ctx->ar_epoch++;
     peer_allreduce_kernel<<<1, 256, 0, ctx->stream>>>(ctx->peer_world, ctx->peer_rank, ctx->d_comm, ctx->comm_maxc, ctx->ar_epoch,
-                                                      dptr, count, op, count2, op2);
+                                                      dptr, count, op, count2, op2, ctx->spin_timeout_ns);
     WB_LAUNCH_CHECK(ctx);
     return WB200_OK;
 }
@@ -124,7 +132,8 @@ int wb_peer_signal(wb200_ctx* ctx, int which, unsigned long long epoch) {
 }
 int wb_peer_wait(wb200_ctx* ctx, int which, unsigned long long epoch, cudaStream_t on) {
     if (!ctx->peer_mask) return WB200_OK;
-    flag_wait_kernel<<<1, 32, 0, on>>>(ctx->peer_world, ctx->peer_mask, ctx->my_comm, which ? OFF_PACKED : OFF_READY, epoch);
+    flag_wait_kernel<<<1, 32, 0, on>>>(ctx->peer_world, ctx->peer_mask, ctx->my_comm, which ? OFF_PACKED : OFF_READY, epoch,
+                                      ctx->spin_timeout_ns);
     WB_LAUNCH_CHECK(ctx);
     return WB200_OK;
 }
@@ -137,6 +146,13 @@ int wb_peer_pull_packed(wb200_ctx* ctx) {
     WB_TRY(wb_dmma_packed_info(ctx, &mine, &bytes, &row));
     for (const auto& r : ctx->halo_runs) {
         const size_t off = (size_t)r.k0 * row;
+        if (ctx->peer_pull_kernel) {
+            peer_copy_kernel<<<32, 256, 0, ctx->halo_stream>>>((double2*)((char*)mine + off),
+                                                               (const double2*)((const char*)ctx->h_peerUp[r.owner] + off),
+                                                               (size_t)r.count * row / 16);
+            WB_LAUNCH_CHECK(ctx);
+            continue;
+        }
         WB_CUDA(ctx, cudaMemcpyAsync((char*)mine + off, (const char*)ctx->h_peerUp[r.owner] + off, (size_t)r.count * row,
                                      cudaMemcpyDeviceToDevice, ctx->halo_stream));
     }
@@ -165,7 +181,11 @@ extern "C" int wb200_set_peer_comm(wb200_ctx* ctx, int world, void* const* comm_
     WB_CUDA(ctx, cudaMemcpy((void*)ctx->d_comm, comm_ptrs, sizeof(void*) * world, cudaMemcpyHostToDevice));
     ctx->my_comm = (unsigned long long*)comm_ptrs[ctx->peer_rank];
     ctx->comm_maxc = 4 * ctx->nw + 64;
+    { const char* e = getenv("WB200_SPIN_TIMEOUT_MS"); ctx->spin_timeout_ns = 1000000ull * (unsigned long long)(e && atoll(e) > 0 ? atoll(e) : 20000); }
     wb_allreduce_install_builtin(ctx);   // the library's own collective, unless the caller registered one
+    // streams and events of the host-pointer entry points now, not lazily in the middle of a collective evaluation:
+    // cudaStreamCreate can wait for the device to drain, and a peer's kernel may be spinning on this slab's next launch
+    if (ctx->nn > 0) WB_TRY(wb_ensure_pipeline(ctx));
     return WB200_OK;
 }
 
@@ -193,6 +213,7 @@ extern "C" int wb200_set_peer_packed(wb200_ctx* ctx, int world, void* const* Up_
         return WB200_ERR_ARG;
     }
     ctx->h_peerUp.assign(Up_ptrs, Up_ptrs + world);
+    { const char* e = getenv("WB200_PEER_PULL"); ctx->peer_pull_kernel = (e && e[0] == 'k') ? 1 : 0; }   // =kernel
     return WB200_OK;
 }
 
