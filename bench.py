@@ -219,6 +219,9 @@ def main():
     ap.add_argument("--config", default="cfg4_nw128")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--maxloc-iters", type=int, default=10,
+                    help="also time the device max_localize driver for this many iterations (0: skip); extra key "
+                         "`max_localize` in the JSON line, outside the timed region of `value`")
     ap.add_argument("--no-peer-comm", action="store_true",
                     help="N > 1, --halo peer: the round-1 scheme — NCCL all-reduces (a one-element one in front of "
                          "every evaluation, the sums) and peer rows packed straight from peer memory — instead of "
@@ -451,6 +454,31 @@ def main():
         if world > 1 and halo == "peer":
             ctx.set_allreduce(None)
 
+    # ---- the loop the evaluation sits in: device-resident max_localize (wb200_max_localize), a few iterations ----
+    maxloc = None
+    if args.maxloc_iters > 0 and nb == nw and (world == 1 or halo == "peer"):
+        hUm = torch.empty((nkl if world > 1 else nk, nw, nb), dtype=torch.complex128).pin_memory()
+        # (a sharded driver publishes every trial point in the rank's rows of the shared gauge array: keep the start)
+        U_start = dU[k0:k1].clone() if world > 1 else dU
+        if world > 1 and not peer_comm:
+            ctx.set_allreduce(w.sharding.torch_allreduce(dist, dev))
+        for rep in range(2):                                   # the first call pays lazy kernel loading and allocations
+            hUm.copy_(U_start)
+            barrier()
+            t0 = time.perf_counter()
+            f_ml, it_ml, nfg_ml = ctx.max_localize(hUm.numpy(), max_iter=args.maxloc_iters)
+            barrier()
+            dt_ml = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt_ml], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt_ml = t.item()
+            if not peer_comm:
+                ctx.set_allreduce(None)
+        maxloc = {"api": "wb200_max_localize (L-BFGS + HagerZhang + Stiefel retraction on the device, U in and out through "
+                         "pinned host memory)", "max_iter": args.maxloc_iters, "iterations": it_ml, "n_evaluations": nfg_ml,
+                  "seconds": dt_ml, "ms_per_evaluation": 1e3 * dt_ml / max(nfg_ml, 1), "f_start": omega_val, "f_end": f_ml}
+
     if breakdown:
         torch.cuda.synchronize()
         names = ["exchange", "phase1", "allreduce", "phase2"]
@@ -512,7 +540,8 @@ def main():
                                         else "NCCL all-reduce + pack from peer memory") if halo == "peer" else None,
                            omega_check=omega_val,
                            g_check=g_check),
-            "e2e": e2e, "gpu_launches": int(launches), "clocks": cs.summary(), "roofline": roof}
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": cs.summary(), "roofline": roof,
+            "max_localize": maxloc}
 
     ctx.close()
     del ctx, dG

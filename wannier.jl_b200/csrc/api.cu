@@ -224,6 +224,9 @@ extern "C" int wb200_fg_phase1_dev(wb200_ctx* ctx, const double* dU, double* dsu
         ctx->err = "wb200_fg_phase1_dev: with peer gauges set, dU must be this rank's shared gauge array (U_ptrs[rank])";
         return WB200_ERR_ARG;
     }
+    // exact_split = 0 equates ||N_kb||_F with ||M U_{k+b}||_F: true for square gauges (unitary U assumed), not for
+    // rectangular ones — their OmegaI / OmegaOD / OmegaD / OmegaTilde come out as NaN instead of plausible wrong numbers
+    ctx->split_valid = exact_split || ctx->nb == ctx->nw;
     if (ctx->d_peerU && ctx->d_comm) ctx->epoch++;
     // (the same on every rank: which flag a peer waits for depends on it)
     const bool split = ctx->halo_split && ctx->d_peerU && ctx->d_comm && !ctx->h_peerUp.empty() && !exact_split &&

@@ -177,6 +177,8 @@ struct wb200_ctx {
     int use_graphs = 1;        // WB200_GRAPH=0 disables
     unsigned zd_attr_mask = 0; // zgemm_dmma.cu: shared-memory attribute set for these instantiations
     int rot_attr_done = 0;     // rotate_dmma.cu: the same for the rotation kernel of this ctx's shape
+    unsigned attr_mask = 0;    // other kernels that need more than 48 KB of dynamic shared memory (bit per kernel)
+    int split_valid = 1;       // the last phase 1 produced a valid OmegaI / OmegaOD / OmegaD split
 
     DmmaPlan* dmma = nullptr;  // tensor-path state (nullptr: CUDA-core rotation)
     int rotation_kernel = 0;

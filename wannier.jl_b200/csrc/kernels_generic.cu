@@ -342,10 +342,9 @@ int wb_pair_partial(wb200_ctx* ctx, int ka, int kb) {
     ProfScope ps(ctx, 2);
     const size_t smem = sizeof(double) * 2 * (size_t)ctx->nn * ctx->nw;
     if (smem > 48 * 1024) {
-        static bool attr_done[16] = {false};
-        if (!attr_done[ctx->device & 15]) {
+        if (!(ctx->attr_mask & 1u)) {
             WB_CUDA(ctx, cudaFuncSetAttribute(pair_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            attr_done[ctx->device & 15] = true;
+            ctx->attr_mask |= 1u;
         }
         if (smem > 200 * 1024) {
             ctx->err = "pair_reduce: nn * nw too large for the shared-memory staging";
@@ -379,7 +378,7 @@ int wb_pair_reduce(wb200_ctx* ctx, double* dsums) {
 // ------------------------------------------------------------------------------------------
 __global__ void finalize_kernel(int nw, int nk_total, double wsum, const double* __restrict__ sums,
                                 int has_penalty, double lambda, const double* __restrict__ r0,
-                                double* __restrict__ res) {
+                                double* __restrict__ res, int split_valid) {
     const double inv = 1.0 / (double)nk_total;
     for (int n = threadIdx.x; n < nw; n += blockDim.x) {
         const double rx = -sums[3 * n + 0] * inv, ry = -sums[3 * n + 1] * inv,
@@ -406,11 +405,12 @@ __global__ void finalize_kernel(int nw, int nk_total, double wsum, const double*
         const double OI = ((double)nw * wsum * (double)nk_total - sumF) * inv;
         const double OOD = (sumF - sumD) * inv;
         const double Ot = Om - OI;
+        const double nan = __longlong_as_double(0x7ff8000000000000ll);
         res[0] = Om;
-        res[1] = OI;
-        res[2] = OOD;
-        res[3] = Ot - OOD;
-        res[4] = Ot;
+        res[1] = split_valid ? OI : nan;
+        res[2] = split_valid ? OOD : nan;
+        res[3] = split_valid ? Ot - OOD : nan;
+        res[4] = split_valid ? Ot : nan;
         res[5] = Om + Oc;
         res[6] = Oc;
         res[7] = 0.0;
@@ -419,7 +419,7 @@ __global__ void finalize_kernel(int nw, int nk_total, double wsum, const double*
 
 int wb_finalize(wb200_ctx* ctx, const double* dsums, double* dres) {
     finalize_kernel<<<1, 256, 0, ctx->stream>>>(ctx->nw, ctx->nk_total, ctx->wsum, dsums,
-                                                ctx->has_penalty, ctx->lambda, ctx->d_r0, dres);
+                                                ctx->has_penalty, ctx->lambda, ctx->d_r0, dres, ctx->split_valid);
     WB_LAUNCH_CHECK(ctx);
     return WB200_OK;
 }

@@ -410,11 +410,10 @@ __global__ void __launch_bounds__(128) gu_to_gxy_small_kernel(int nb, int nw, lo
 }
 
 static int xy_small_attr(wb200_ctx* ctx) {
-    static bool done[16] = {false};
-    if (!done[ctx->device & 15]) {
+    if (!(ctx->attr_mask & 8u)) {
         WB_CUDA(ctx, cudaFuncSetAttribute(xy_to_u_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         WB_CUDA(ctx, cudaFuncSetAttribute(gu_to_gxy_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        done[ctx->device & 15] = true;
+        ctx->attr_mask |= 8u;
     }
     return WB200_OK;
 }

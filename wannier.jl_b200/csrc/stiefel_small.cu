@@ -355,10 +355,9 @@ static bool use32(int nrow, int ncol) {
 int wb_retract_small(wb200_ctx* ctx, cplx* dX, int nrow, int ncol, int ld, long long stride, int count) {
     if (use32(nrow, ncol)) {
         const size_t smem32 = sizeof(cplx) * 4 * 2 * S32_MAT;
-        static bool attr32[16] = {false};
-        if (!attr32[ctx->device & 15]) {
+        if (!(ctx->attr_mask & 16u)) {
             WB_CUDA(ctx, cudaFuncSetAttribute(retract32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32));
-            attr32[ctx->device & 15] = true;
+            ctx->attr_mask |= 16u;
         }
         int* flag = reinterpret_cast<int*>(ctx->d_scal + 4);
         WB_CUDA(ctx, cudaMemsetAsync(flag, 0, sizeof(int), ctx->stream));
@@ -374,11 +373,10 @@ int wb_retract_small(wb200_ctx* ctx, cplx* dX, int nrow, int ncol, int ld, long 
         return WB200_OK;
     }
     const size_t smem = sizeof(cplx) * ((size_t)ncol * (nrow + 1) + (size_t)ncol * ncol);
-    static bool attr_done[16] = {false};
-    if (!attr_done[ctx->device & 15]) {
+    if (!(ctx->attr_mask & 2u)) {
         WB_CUDA(ctx, cudaFuncSetAttribute(retract_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)(sizeof(cplx) * (WB_SMALL_MAX * (WB_SMALL_MAX + 1) + WB_SMALL_MAX * WB_SMALL_MAX))));
-        attr_done[ctx->device & 15] = true;
+        ctx->attr_mask |= 2u;
     }
     int* flag = reinterpret_cast<int*>(ctx->d_scal + 4);
     WB_CUDA(ctx, cudaMemsetAsync(flag, 0, sizeof(int), ctx->stream));
@@ -398,21 +396,19 @@ int wb_project_small(wb200_ctx* ctx, const cplx* dX, cplx* dG, int nrow, int nco
                      int count) {
     if (use32(nrow, ncol)) {
         const size_t smem32 = sizeof(cplx) * 4 * 3 * S32_MAT;
-        static bool attr32[16] = {false};
-        if (!attr32[ctx->device & 15]) {
+        if (!(ctx->attr_mask & 32u)) {
             WB_CUDA(ctx, cudaFuncSetAttribute(project32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32));
-            attr32[ctx->device & 15] = true;
+            ctx->attr_mask |= 32u;
         }
         project32_kernel<<<(count + 3) / 4, 256, smem32, ctx->stream>>>(nrow, ncol, ld, stride, dX, dG, count);
         WB_LAUNCH_CHECK(ctx);
         return WB200_OK;
     }
     const size_t smem = sizeof(cplx) * (2 * (size_t)ncol * (nrow + 1) + (size_t)ncol * ncol);
-    static bool attr_done[16] = {false};
-    if (!attr_done[ctx->device & 15]) {
+    if (!(ctx->attr_mask & 4u)) {
         WB_CUDA(ctx, cudaFuncSetAttribute(project_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)(sizeof(cplx) * (2 * WB_SMALL_MAX * (WB_SMALL_MAX + 1) + WB_SMALL_MAX * WB_SMALL_MAX))));
-        attr_done[ctx->device & 15] = true;
+        ctx->attr_mask |= 4u;
     }
     project_small_kernel<<<count, WB_SMALL_THREADS, smem, ctx->stream>>>(nrow, ncol, ld, stride, dX, dG);
     WB_LAUNCH_CHECK(ctx);
