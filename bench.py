@@ -219,7 +219,7 @@ def main():
     ap.add_argument("--config", default="cfg4_nw128")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--maxloc-iters", type=int, default=10,
+    ap.add_argument("--maxloc-iters", type=int, default=20,
                     help="also time the device max_localize driver for this many iterations (0: skip); extra key "
                          "`max_localize` in the JSON line, outside the timed region of `value`")
     ap.add_argument("--no-peer-comm", action="store_true",
