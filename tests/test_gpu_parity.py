@@ -389,6 +389,46 @@ def test_unitary_shortcut_vs_exact_split(w):
     sp = so.omega(M, st["kpb_k"], st["bvec"], st["wb"], U)
     assert abs(a[1] - sp["OmegaI"]) < 1e-10 * sp["Omega"] and abs(a[2] - sp["OmegaOD"]) < 1e-10 * sp["Omega"]
     ctx.close()
+    # both epilogues of the shortcut (the gauge-invariant norm ||M_kb||_F computed once, and ||M U||_F per
+    # evaluation) give the same split; the small ring kernel likewise (nb = nw = 32, enough pairs for it)
+    import os
+    for lat, grid, n in [("bcc", (2, 2, 2), 64), ("cubic", (6, 6, 6), 32)]:
+        st, M, U = w.synthetic.make_model_arrays(lat, grid, n, n)
+        sp = so.omega(M, st["kpb_k"], st["bvec"], st["wb"], U)
+        for env in ("1", "0"):
+            os.environ["WB200_CONST_NORM"] = env
+            try:
+                ctx = make_ctx(w, st, M, n)
+            finally:
+                os.environ.pop("WB200_CONST_NORM", None)
+            ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+            dU = torch.from_numpy(w.api.to_abi_U(U)).cuda()
+            ctx.fg_dev(dU.data_ptr(), res[:ctx.nres].data_ptr(), None, exact_split=False)
+            a = res.cpu().numpy()
+            for i, key in enumerate(["Omega", "OmegaI", "OmegaOD", "OmegaD", "OmegaTilde"]):
+                assert abs(a[i] - sp[key]) < 1e-10 * abs(sp["Omega"]), (n, env, key)
+            ctx.close()
+
+
+def test_rectangular_shortcut_reports_no_split(w):
+    # exact_split = 0 equates ||N||_F with ||M U||_F, which only holds for square gauges: with nb > nw the spread
+    # and f are right and the OmegaI / OmegaOD / OmegaD / OmegaTilde slots are NaN, not plausible wrong numbers
+    import torch
+    st, M, U = w.synthetic.make_model_arrays("cubic", (3, 2, 2), 72, 40)
+    ctx = make_ctx(w, st, M, 40)
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    dU = torch.from_numpy(w.api.to_abi_U(U)).cuda()
+    res = torch.zeros(ctx.nres, dtype=torch.float64, device="cuda")
+    ctx.fg_dev(dU.data_ptr(), res.data_ptr(), None, exact_split=False)
+    a = res.cpu().numpy().copy()
+    sp = so.omega(M, st["kpb_k"], st["bvec"], st["wb"], U)
+    assert abs(a[0] - sp["Omega"]) < 1e-10 * abs(sp["Omega"]) and abs(a[5] - sp["Omega"]) < 1e-10 * abs(sp["Omega"])
+    assert np.isnan(a[1:5]).all()
+    ctx.fg_dev(dU.data_ptr(), res.data_ptr(), None, exact_split=True)
+    b = res.cpu().numpy()
+    for i, key in enumerate(["Omega", "OmegaI", "OmegaOD", "OmegaD", "OmegaTilde"]):
+        assert abs(b[i] - sp[key]) < 1e-10 * abs(sp["Omega"]), key
+    ctx.close()
 
 
 def test_k_slab_sharding_on_one_gpu(w):
