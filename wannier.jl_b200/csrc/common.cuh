@@ -69,6 +69,16 @@ struct ZgemmArgs {
 // ---------------------------------------------------------------------------------------------
 struct DmmaPlan;  // rotate_dmma.cu
 
+// Slabs of ONE process (wb200_multi_*, multi.cu): the host threads of the slabs can rendezvous and CUDA events order
+// streams across devices, so the peer-memory collectives need no spinning kernels there (a spinning kernel and the
+// runtime's lazy module loading / pageable copies of another host thread of the same process can wait for each other).
+struct WbInproc {
+    int n = 0;
+    std::vector<cudaEvent_t> ev_ready, ev_packed;   // [slab]: "gauge rows written" / "rows packed", recorded on the slab's stream
+    std::vector<cudaEvent_t> ev_ar[2];              // [parity][slab]: contribution pushed into every slab's slot
+    std::function<bool()> barrier;                  // host-thread rendezvous of the slabs; false: a slab failed
+};
+
 struct wb200_ctx {
     int device = 0;
     int num_sms = 148;
@@ -110,6 +120,7 @@ struct wb200_ctx {
     unsigned long long* my_comm = nullptr;        // comm_ptrs[rank]
     int comm_maxc = 0;                            // doubles per all-reduce slot
     unsigned long long spin_timeout_ns = 20000000000ull;
+    WbInproc* inproc = nullptr;                   // set by wb200_multi_create: events + host barrier instead of flags
     unsigned long long epoch = 0, ar_epoch = 0;   // evaluation / all-reduce counters (identical on every rank)
     unsigned peer_mask = 0;                       // ranks owning rows this slab reads
     std::vector<void*> h_peerUp;                  // packed-gauge arrays of the ranks (wb200_set_peer_packed)

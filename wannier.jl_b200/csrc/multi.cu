@@ -57,7 +57,8 @@ struct wb200_multi {
     std::vector<int> devices, bounds;
     std::vector<wb200_ctx*> ctx;
     std::vector<cplx*> Ufull;            // per slab: [nk][nw][nb] on its device; the slab owns its rows
-    std::vector<void*> flags;            // per slab: peer comm buffer (distinct devices only)
+    std::vector<void*> flags;            // per slab: peer comm buffer
+    WbInproc inproc;                     // events + host rendezvous of the slab threads
     HostBarrier bar;
     int maxc = 0;
     double* h_x[2] = {nullptr, nullptr};   // pinned [parity][slab][maxc]: contributions
@@ -149,6 +150,8 @@ extern "C" void wb200_multi_destroy(wb200_multi* m) {
             cudaSetDevice(m->devices[r]);
             cudaFree(m->flags[r]);
         }
+        for (auto* v : {&m->inproc.ev_ready, &m->inproc.ev_packed, &m->inproc.ev_ar[0], &m->inproc.ev_ar[1]})
+            if (r < (int)v->size() && (*v)[r]) { cudaSetDevice(m->devices[r]); cudaEventDestroy((*v)[r]); }
     }
     for (int p = 0; p < 2; p++) {
         if (m->h_x[p]) cudaFreeHost(m->h_x[p]);
@@ -208,19 +211,19 @@ extern "C" int wb200_multi_create(wb200_multi** out, const int* devices, int nde
         if (cudaMallocHost(&m->h_x[p], sizeof(double) * (size_t)ndev * m->maxc) != cudaSuccess ||
             cudaMallocHost(&m->h_r[p], sizeof(double) * (size_t)ndev * m->maxc) != cudaSuccess)
             return fail(WB200_ERR_CUDA, "wb200_multi_create: cudaMallocHost failed");
-    // One slab per device: the library's own peer-memory collectives (peer.cu) — readiness flags instead of a
-    // "rows are in place" reduction, packed halo rows pulled by the copy engines under the rotation, all-reduces as
-    // one small kernel per slab.  Two slabs of one device could share a hardware queue (a spinning wait in front
-    // of its signal), so repeated devices keep the host-side all-reduce at the barrier.
+    // The library's own peer-memory collectives (peer.cu): packed halo rows pulled by the copy engines under the
+    // rotation, all-reduces as a push into every slab's slot + a rank-order sum.  Between the slabs of ONE process the
+    // ordering comes from CUDA events and a host rendezvous of the slab threads (WbInproc) — no kernel ever spins, so
+    // repeated devices, pageable host arrays and lazily loaded kernels are all safe.
+    // WB200_PEER_COMM=0: round-1 scheme (host-side all-reduce at the barrier, peer rows packed straight from peer
+    // memory); =force: the spinning-flag protocol of the one-process-per-GPU mode (the test suite runs it in a
+    // subprocess to cover that code on a one-GPU box).
     bool distinct = ndev <= WB_COMM_MAXR;
-    for (int r = 0; r < ndev; r++)
-        for (int q = 0; q < r; q++) distinct = distinct && devices[r] != devices[q];
-    {   // WB200_PEER_COMM=0: host-side all-reduce everywhere; =force: peer-memory collectives even between slabs of one
-        // device (the test suite does this in a subprocess to cover peer.cu on a one-GPU box; forward progress then
-        // rests on the slabs' streams landing in different hardware queues)
+    bool spin_flags = false;
+    {
         const char* e = getenv("WB200_PEER_COMM");
         if (e && e[0] == '0') distinct = false;
-        if (e && e[0] == 'f' && ndev <= WB_COMM_MAXR) distinct = true;
+        if (e && e[0] == 'f') spin_flags = true;
     }
     const bool peer_comm = distinct && ndev > 1;
     m->flags.assign(ndev, nullptr);
@@ -230,6 +233,18 @@ extern "C" int wb200_multi_create(wb200_multi** out, const int* devices, int nde
             if (cudaSetDevice(devices[r]) != cudaSuccess || cudaMalloc(&m->flags[r], comm_bytes) != cudaSuccess ||
                 cudaMemset(m->flags[r], 0, comm_bytes) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess)
                 return fail(WB200_ERR_CUDA, "wb200_multi_create: cudaMalloc of the comm buffers failed");
+    if (peer_comm && !spin_flags) {
+        WbInproc& ip = m->inproc;
+        ip.n = ndev;
+        ip.barrier = [m]() { return m->bar.wait(); };
+        for (auto* v : {&ip.ev_ready, &ip.ev_packed, &ip.ev_ar[0], &ip.ev_ar[1]}) {
+            v->assign(ndev, nullptr);
+            for (int r = 0; r < ndev; r++)
+                if (cudaSetDevice(devices[r]) != cudaSuccess ||
+                    cudaEventCreateWithFlags(&(*v)[r], cudaEventDisableTiming) != cudaSuccess)
+                    return fail(WB200_ERR_CUDA, "wb200_multi_create: cudaEventCreate failed");
+        }
+    }
     std::vector<const void*> ptrs(ndev);
     std::vector<void*> packed(ndev, nullptr);
     bool have_packed = peer_comm;
@@ -241,6 +256,7 @@ extern "C" int wb200_multi_create(wb200_multi** out, const int* devices, int nde
     for (int r = 0; r < ndev; r++) {
         m->users[r] = {m, r};
         int s = wb200_set_peer_gauges(m->ctx[r], ndev, ptrs.data(), m->bounds.data());
+        if (s == WB200_OK && peer_comm && !spin_flags) m->ctx[r]->inproc = &m->inproc;
         if (s == WB200_OK && peer_comm) s = wb200_set_peer_comm(m->ctx[r], ndev, m->flags.data());
         if (s == WB200_OK && have_packed) s = wb200_set_peer_packed(m->ctx[r], ndev, packed.data());
         if (s == WB200_OK && !peer_comm) s = wb200_set_allreduce(m->ctx[r], multi_allreduce, &m->users[r]);

@@ -97,6 +97,38 @@ __global__ void __launch_bounds__(256) peer_copy_kernel(double2* __restrict__ ds
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
 }
 
+// the same all-reduce in two kernels with a stream dependency (CUDA events) between them instead of a spin — for the
+// slabs of one process
+__global__ void __launch_bounds__(256) peer_push_kernel(int world, int rank, unsigned long long* const* __restrict__ comm,
+                                                        int maxc, int par, const double* __restrict__ x, int n) {
+    for (int q = 0; q < world; q++) {
+        double* slot = reinterpret_cast<double*>(comm[q] + OFF_SLOTS) + ((size_t)par * MAXR + rank) * maxc;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) slot[i] = x[i];
+    }
+    __threadfence_system();
+}
+__global__ void __launch_bounds__(256) peer_sum_kernel(int world, const unsigned long long* __restrict__ mine, int maxc, int par,
+                                                       double* __restrict__ x, int count, int op, int count2, int op2) {
+    const double* slots = reinterpret_cast<const double*>(mine + OFF_SLOTS) + (size_t)par * MAXR * maxc;
+    for (int i = threadIdx.x; i < count + count2; i += blockDim.x) {
+        const int o = i < count ? op : op2;
+        double acc = __ldcg(slots + i);
+        for (int q = 1; q < world; q++) {
+            const double v = __ldcg(slots + (size_t)q * maxc + i);
+            acc = o == 0 ? acc + v : (o == 1 ? fmax(acc, v) : fmin(acc, v));
+        }
+        x[i] = acc;
+    }
+}
+
+int inproc_barrier(wb200_ctx* ctx) {
+    if (!ctx->inproc->barrier()) {
+        ctx->err = "all-reduce callback failed: another slab of this call reported an error";
+        return WB200_ERR_CUDA;
+    }
+    return WB200_OK;
+}
+
 int builtin_allreduce(void* dptr, int count, int op, void* /*stream*/, void* user) {
     return wb_peer_allreduce((wb200_ctx*)user, (double*)dptr, count, op, 0, 0) == WB200_OK ? 0 : 1;
 }
@@ -113,6 +145,21 @@ int wb_peer_allreduce(wb200_ctx* ctx, double* dptr, int count, int op, int count
         return WB200_ERR_ARG;
     }
     ctx->ar_epoch++;
+    if (ctx->inproc) {
+        // push my contribution into every slab's slot; once EVERY slab has recorded its push (host rendezvous of the
+        // slab threads — the streams are not drained), this stream waits for those events and sums in rank order
+        const int par = (int)(ctx->ar_epoch & 1ull);
+        peer_push_kernel<<<1, 256, 0, ctx->stream>>>(ctx->peer_world, ctx->peer_rank, ctx->d_comm, ctx->comm_maxc, par, dptr,
+                                                     count + count2);
+        WB_LAUNCH_CHECK(ctx);
+        WB_CUDA(ctx, cudaEventRecord(ctx->inproc->ev_ar[par][ctx->peer_rank], ctx->stream));
+        WB_TRY(inproc_barrier(ctx));
+        for (int q = 0; q < ctx->peer_world; q++)
+            if (q != ctx->peer_rank) WB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->inproc->ev_ar[par][q], 0));
+        peer_sum_kernel<<<1, 256, 0, ctx->stream>>>(ctx->peer_world, ctx->my_comm, ctx->comm_maxc, par, dptr, count, op, count2, op2);
+        WB_LAUNCH_CHECK(ctx);
+        return WB200_OK;
+    }
     peer_allreduce_kernel<<<1, 256, 0, ctx->stream>>>(ctx->peer_world, ctx->peer_rank, ctx->d_comm, ctx->comm_maxc, ctx->ar_epoch,
                                                       dptr, count, op, count2, op2, ctx->spin_timeout_ns);
     WB_LAUNCH_CHECK(ctx);
@@ -126,11 +173,23 @@ void wb_allreduce_install_builtin(wb200_ctx* ctx) {
 
 // publish flag word `which` (0 ready, 1 packed) on ctx->stream; wait for the owners of the halo rows on `on`
 int wb_peer_signal(wb200_ctx* ctx, int which, unsigned long long epoch) {
+    if (ctx->inproc) {
+        auto& ev = which ? ctx->inproc->ev_packed : ctx->inproc->ev_ready;
+        WB_CUDA(ctx, cudaEventRecord(ev[ctx->peer_rank], ctx->stream));
+        return WB200_OK;
+    }
     flag_signal_kernel<<<1, 32, 0, ctx->stream>>>(ctx->peer_world, ctx->peer_rank, ctx->d_comm, which ? OFF_PACKED : OFF_READY, epoch);
     WB_LAUNCH_CHECK(ctx);
     return WB200_OK;
 }
 int wb_peer_wait(wb200_ctx* ctx, int which, unsigned long long epoch, cudaStream_t on) {
+    if (ctx->inproc) {   // every slab has recorded its event of this evaluation once the slab threads have met
+        WB_TRY(inproc_barrier(ctx));
+        auto& ev = which ? ctx->inproc->ev_packed : ctx->inproc->ev_ready;
+        for (int q = 0; q < ctx->peer_world; q++)
+            if ((ctx->peer_mask >> q) & 1u) WB_CUDA(ctx, cudaStreamWaitEvent(on, ev[q], 0));
+        return WB200_OK;
+    }
     if (!ctx->peer_mask) return WB200_OK;
     flag_wait_kernel<<<1, 32, 0, on>>>(ctx->peer_world, ctx->peer_mask, ctx->my_comm, which ? OFF_PACKED : OFF_READY, epoch,
                                       ctx->spin_timeout_ns);
