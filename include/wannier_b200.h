@@ -349,6 +349,18 @@ int wb200_mag_disentangle(wb200_mag* m, double* XY_inout, double lambda, double 
 int wb200_host_register(void* ptr, size_t bytes);
 int wb200_host_unregister(void* ptr);
 
+/* ---- resource pools ---------------------------------------------------------------------------------------------
+ * The reference's one-shot calls (omega(bvectors, M, U), omega_grad(...), max_localize(model): src/spread.jl:370-381,
+ * 496-510, benchmark/bench_spread.jl, bench_grad.jl, bench_maxloc.jl) build a Cache per call; here that is a device
+ * context per call.  The library therefore keeps the device buffers, page-locked host buffers and streams of
+ * destroyed contexts (per device, blocks of at most 64 MB, at most 1 GB) and hands them out again, so that a one-shot
+ * call costs its arithmetic and copies, not ~60 driver allocations.  WB200_POOL=0 disables this.
+ *   wb200_trim_pools   gives everything kept back to the driver.
+ *   wb200_pool_stats   bytes kept on `device` (device < 0: page-locked host bytes); hits / misses (nullable) count
+ *                      device allocations served from / not served from the kept blocks since the process started. */
+void wb200_trim_pools(void);
+long long wb200_pool_stats(int device, long long* hits, long long* misses);
+
 /* ---- measurement helpers (bench.py) -------------------------------------------------------------
  * wb200_profile: when enabled, every launch of the four kernel classes below is bracketed by CUDA
  * events on the ctx's stream; wb200_profile_read synchronises, returns the summed milliseconds and

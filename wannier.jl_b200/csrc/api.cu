@@ -7,6 +7,26 @@
 
 static thread_local std::string g_create_error;
 
+// WB200_TRACE_CREATE: wall-clock attribution of context creation / destruction (stderr)
+namespace {
+struct CreateTrace {
+    bool on = getenv("WB200_TRACE_CREATE") != nullptr;
+    double t0 = 0.0;
+    const char* what;
+    static double now() {
+        timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts);
+        return ts.tv_sec + 1e-9 * ts.tv_nsec;
+    }
+    explicit CreateTrace(const char* w) : what(w) { if (on) t0 = now(); }
+    void mark(const char* phase) {
+        if (!on) return;
+        const double t = now();
+        fprintf(stderr, "[wb200] %s: %-28s %8.3f ms\n", what, phase, 1e3 * (t - t0));
+        t0 = t;
+    }
+};
+}  // namespace
+
 extern "C" const char* wb200_version(void) { return "wannier_b200 0.1 (sm_100a)"; }
 
 extern "C" const char* wb200_last_error(const wb200_ctx* ctx) {
@@ -15,9 +35,15 @@ extern "C" const char* wb200_last_error(const wb200_ctx* ctx) {
 
 extern "C" void wb200_destroy(wb200_ctx* ctx) {
     if (!ctx) return;
+    CreateTrace tr("destroy");
     cudaSetDevice(ctx->device);
+    // the buffers go back to the caching allocator (mempool.cu), which — unlike cudaFree — does not wait for work in
+    // flight: drain the device once, here
+    cudaDeviceSynchronize();
+    tr.mark("device sync");
     wb_dmma_plan_destroy(ctx);
-    if (ctx->halo_stream) cudaStreamDestroy(ctx->halo_stream);
+    tr.mark("tensor plan");
+    if (ctx->halo_stream) cudaStreamDestroy(ctx->halo_stream);   // high priority: not pooled
     if (ctx->ev_rows) cudaEventDestroy(ctx->ev_rows);
     if (ctx->ev_halo) cudaEventDestroy(ctx->ev_halo);
     void* ptrs[] = {(void*)ctx->d_comm, ctx->d_need_split, ctx->d_owner_split, ctx->d_border, ctx->d_nloc,
@@ -26,17 +52,21 @@ extern "C" void wb200_destroy(wb200_ctx* ctx) {
                     ctx->d_dN, ctx->d_fro, ctx->d_part, ctx->d_pmin, ctx->d_sums, ctx->d_res,
                     ctx->d_min, ctx->d_scal, ctx->d_red, ctx->d_zpart, ctx->d_tmp1, ctx->d_tmp2, ctx->d_XY, ctx->d_GXY};
     for (void* p : ptrs)
-        if (p) cudaFree(p);
+        if (p) wb_dev_free_drained(p);
+    tr.mark("buffers");
     for (auto& g : ctx->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
     for (auto& v : ctx->prof_events)
         for (auto& pr : v) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
-    if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    tr.mark("graphs, events");
+    if (ctx->h_pinned) wb_pinned_free(ctx->h_pinned);
+    tr.mark("cudaFreeHost");
     for (auto e : ctx->ev_up) cudaEventDestroy(e);
     for (auto e : ctx->ev_grad) cudaEventDestroy(e);
-    if (ctx->h2d_stream) cudaStreamDestroy(ctx->h2d_stream);
-    if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
-    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    if (ctx->h2d_stream) wb_stream_release(ctx->h2d_stream);
+    if (ctx->d2h_stream) wb_stream_release(ctx->d2h_stream);
+    if (ctx->own_stream) wb_stream_release(ctx->own_stream);
     delete ctx;
+    tr.mark("streams");
 }
 
 #define CREATE_FAIL(code, msg)        \
@@ -56,6 +86,7 @@ extern "C" int wb200_create(wb200_ctx** out, int device, int nb, int nw, int nk_
                             int nk, int nn, const int32_t* kpb_k, const double* bvec_cart,
                             const double* bweights, const double* M, unsigned flags) {
     wb200_ctx* ctx = nullptr;
+    CreateTrace tr("create");
     if (!out) CREATE_FAIL(WB200_ERR_ARG, "wb200_create: out is NULL");
     *out = nullptr;
     if (nb <= 0 || nw <= 0 || nw > nb || nk_total <= 0 || nn <= 0 || nk <= 0 || k_begin < 0 ||
@@ -71,44 +102,52 @@ extern "C" int wb200_create(wb200_ctx** out, int device, int nb, int nw, int nk_
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev)
         CREATE_FAIL(WB200_ERR_NODEVICE, "wb200_create: no CUDA device " + std::to_string(device) +
                                             " (this library has no CPU fallback)");
-    cudaDeviceProp prop;
-    CREATE_CUDA(cudaGetDeviceProperties(&prop, device));
-    if (prop.major != 10)
-        CREATE_FAIL(WB200_ERR_NODEVICE, std::string("wb200_create: device is ") + prop.name +
-                                            " (sm_" + std::to_string(prop.major) + std::to_string(prop.minor) +
-                                            "); this library is built for sm_100a only");
+    int cc_major = 0, cc_minor = 0, num_sms = 0;
+    if (wb_device_info(device, &cc_major, &cc_minor, &num_sms) != WB200_OK)
+        CREATE_FAIL(WB200_ERR_CUDA, "wb200_create: cudaDeviceGetAttribute failed for device " + std::to_string(device));
+    if (cc_major != 10)
+        CREATE_FAIL(WB200_ERR_NODEVICE, std::string("wb200_create: device ") + std::to_string(device) +
+                                            " is sm_" + std::to_string(cc_major) + std::to_string(cc_minor) +
+                                            "; this library is built for sm_100a only");
     CREATE_CUDA(cudaSetDevice(device));
+    tr.mark("checks, device properties");
 
     ctx = new wb200_ctx();
     ctx->device = device;
-    ctx->num_sms = prop.multiProcessorCount;
+    ctx->num_sms = num_sms;
     { const char* e = getenv("WB200_GRAPH"); ctx->use_graphs = !(e && e[0] == '0'); }
     ctx->nb = nb; ctx->nw = nw; ctx->nk_total = nk_total; ctx->k_begin = k_begin; ctx->nk = nk;
     ctx->nn = nn; ctx->flags = flags;
-    CREATE_CUDA(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+    CREATE_CUDA(wb_stream_acquire(&ctx->own_stream));
     ctx->stream = ctx->own_stream;
+    tr.mark("stream");
 
     const size_t pairs = (size_t)nk * nn;
     const size_t mat = (size_t)nb * nw;
-    CREATE_CUDA(cudaMalloc(&ctx->d_kpb, sizeof(int32_t) * pairs));
-    CREATE_CUDA(cudaMalloc(&ctx->d_kself, sizeof(int32_t) * pairs));
-    CREATE_CUDA(cudaMalloc(&ctx->d_bvec, sizeof(double) * pairs * 3));
-    CREATE_CUDA(cudaMalloc(&ctx->d_wb, sizeof(double) * nn));
-    CREATE_CUDA(cudaMalloc(&ctx->d_M, sizeof(cplx) * pairs * nb * nb));
-    CREATE_CUDA(cudaMalloc(&ctx->d_r0, sizeof(double) * 3 * nw));
-    CREATE_CUDA(cudaMalloc(&ctx->d_U, sizeof(cplx) * (size_t)nk_total * mat));
-    CREATE_CUDA(cudaMalloc(&ctx->d_G, sizeof(cplx) * (size_t)nk * mat));
-    CREATE_CUDA(cudaMalloc(&ctx->d_MU, sizeof(cplx) * pairs * mat));
-    CREATE_CUDA(cudaMalloc(&ctx->d_dN, sizeof(cplx) * pairs * nw));
-    CREATE_CUDA(cudaMalloc(&ctx->d_fro, sizeof(double) * pairs));
-    CREATE_CUDA(cudaMalloc(&ctx->d_part, sizeof(double) * (size_t)nk * ctx->nsums()));
-    CREATE_CUDA(cudaMalloc(&ctx->d_pmin, sizeof(double) * nk));
-    CREATE_CUDA(cudaMalloc(&ctx->d_sums, sizeof(double) * ctx->nsums()));
-    CREATE_CUDA(cudaMalloc(&ctx->d_res, sizeof(double) * ctx->nres()));
-    CREATE_CUDA(cudaMalloc(&ctx->d_min, sizeof(double)));
-    CREATE_CUDA(cudaMalloc(&ctx->d_scal, sizeof(double) * 2048));
-    CREATE_CUDA(cudaMallocHost(&ctx->h_pinned, sizeof(double) * (ctx->nres() + 64)));
-    CREATE_CUDA(cudaMemset(ctx->d_r0, 0, sizeof(double) * 3 * nw));
+    CREATE_CUDA(wb_dev_alloc(&ctx->d_kpb, sizeof(int32_t) * pairs));
+    CREATE_CUDA(wb_dev_alloc(&ctx->d_kself, sizeof(int32_t) * pairs));
+    CREATE_CUDA(wb_dev_alloc(&ctx->d_bvec, sizeof(double) * pairs * 3));
+    CREATE_CUDA(wb_dev_alloc(&ctx->d_wb, sizeof(double) * nn));
+    CREATE_CUDA(wb_dev_alloc(&ctx->d_M, sizeof(cplx) * pairs * nb * nb));
+    CREATE_CUDA(wb_dev_alloc(&ctx->d_r0, sizeof(double) * 3 * nw));
+    CREATE_CUDA(wb_dev_alloc(&ctx->d_U, sizeof(cplx) * (size_t)nk_total * mat));
+    CREATE_CUDA(wb_dev_alloc(&ctx->d_G, sizeof(cplx) * (size_t)nk * mat));
+    CREATE_CUDA(wb_dev_alloc(&ctx->d_MU, sizeof(cplx) * pairs * mat));
+    CREATE_CUDA(wb_dev_alloc(&ctx->d_dN, sizeof(cplx) * pairs * nw));
+    CREATE_CUDA(wb_dev_alloc(&ctx->d_fro, sizeof(double) * pairs));
+    CREATE_CUDA(wb_dev_alloc(&ctx->d_part, sizeof(double) * (size_t)nk * ctx->nsums()));
+    CREATE_CUDA(wb_dev_alloc(&ctx->d_pmin, sizeof(double) * nk));
+    CREATE_CUDA(wb_dev_alloc(&ctx->d_sums, sizeof(double) * ctx->nsums()));
+    CREATE_CUDA(wb_dev_alloc(&ctx->d_res, sizeof(double) * ctx->nres()));
+    CREATE_CUDA(wb_dev_alloc(&ctx->d_min, sizeof(double)));
+    CREATE_CUDA(wb_dev_alloc(&ctx->d_scal, sizeof(double) * 2048));
+    tr.mark("cudaMalloc x17");
+    CREATE_CUDA(wb_pinned_alloc(&ctx->h_pinned, sizeof(double) * (ctx->nres() + 64)));
+    tr.mark("cudaMallocHost");
+    // every upload below is ordered on the ctx's own stream in front of the re-tiling kernels; one wait at the end.
+    // (Pageable sources are staged by the driver before cudaMemcpyAsync returns, so the host vectors may go out of scope.)
+    cudaStream_t cs = ctx->stream;
+    CREATE_CUDA(cudaMemsetAsync(ctx->d_r0, 0, sizeof(double) * 3 * nw, cs));
 
     std::vector<int32_t> kself(pairs);
     for (size_t p = 0; p < pairs; p++) kself[p] = k_begin + (int32_t)(p / nn);
@@ -120,18 +159,24 @@ extern "C" int wb200_create(wb200_ctx** out, int device, int nb, int nw, int nk_
         for (int k = 0; k < nk_total; k++) if (mark[k]) need.push_back(k);
         ctx->n_need = (int)need.size();
         ctx->h_need = need;
-        CREATE_CUDA(cudaMalloc(&ctx->d_need, sizeof(int32_t) * need.size()));
-        CREATE_CUDA(cudaMemcpy(ctx->d_need, need.data(), sizeof(int32_t) * need.size(), cudaMemcpyHostToDevice));
+        CREATE_CUDA(wb_dev_alloc(&ctx->d_need, sizeof(int32_t) * need.size()));
+        CREATE_CUDA(cudaMemcpyAsync(ctx->d_need, need.data(), sizeof(int32_t) * need.size(), cudaMemcpyHostToDevice, cs));
     }
-    CREATE_CUDA(cudaMemcpy(ctx->d_kpb, kpb_k, sizeof(int32_t) * pairs, cudaMemcpyHostToDevice));
-    CREATE_CUDA(cudaMemcpy(ctx->d_kself, kself.data(), sizeof(int32_t) * pairs, cudaMemcpyHostToDevice));
-    CREATE_CUDA(cudaMemcpy(ctx->d_bvec, bvec_cart, sizeof(double) * pairs * 3, cudaMemcpyHostToDevice));
-    CREATE_CUDA(cudaMemcpy(ctx->d_wb, bweights, sizeof(double) * nn, cudaMemcpyHostToDevice));
-    CREATE_CUDA(cudaMemcpy(ctx->d_M, M, sizeof(cplx) * pairs * nb * nb, cudaMemcpyDefault));  // host or device
-    // M may be a device pointer: a device-to-device cudaMemcpy returns before the copy has run and
-    // is ordered only on the legacy default stream, while everything below runs on the ctx's own
-    // non-blocking stream.  Drain the device once (one-off cost at creation).
-    CREATE_CUDA(cudaDeviceSynchronize());
+    CREATE_CUDA(cudaMemcpyAsync(ctx->d_kpb, kpb_k, sizeof(int32_t) * pairs, cudaMemcpyHostToDevice, cs));
+    CREATE_CUDA(cudaMemcpyAsync(ctx->d_kself, kself.data(), sizeof(int32_t) * pairs, cudaMemcpyHostToDevice, cs));
+    CREATE_CUDA(cudaMemcpyAsync(ctx->d_bvec, bvec_cart, sizeof(double) * pairs * 3, cudaMemcpyHostToDevice, cs));
+    CREATE_CUDA(cudaMemcpyAsync(ctx->d_wb, bweights, sizeof(double) * nn, cudaMemcpyHostToDevice, cs));
+    {
+        // M may be a device pointer whose producer ran on another stream (torch's, the legacy default stream): nothing
+        // orders that work in front of the ctx's own non-blocking stream, so drain the device first in that case only
+        cudaPointerAttributes pa{};
+        const bool on_device = cudaPointerGetAttributes(&pa, M) == cudaSuccess &&
+                               (pa.type == cudaMemoryTypeDevice || pa.type == cudaMemoryTypeManaged);
+        cudaGetLastError();
+        if (on_device) CREATE_CUDA(cudaDeviceSynchronize());
+    }
+    CREATE_CUDA(cudaMemcpyAsync(ctx->d_M, M, sizeof(cplx) * pairs * nb * nb, cudaMemcpyDefault, cs));  // host or device
+    tr.mark("uploads (enqueued)");
     ctx->h_wb.assign(bweights, bweights + nn);
     ctx->h_kpb.assign(kpb_k, kpb_k + pairs);
     ctx->wsum = 0.0;
@@ -144,7 +189,13 @@ extern "C" int wb200_create(wb200_ctx** out, int device, int nb, int nw, int nk_
     if ((flags & WB200_FLAG_FORCE_TENSOR) && !ctx->dmma)
         CREATE_FAIL(WB200_ERR_ARG, "wb200_create: WB200_FLAG_FORCE_TENSOR but the DMMA rotation kernel does not support this shape");
     ctx->rotation_kernel = ctx->dmma ? 1 : 0;
-    CREATE_CUDA(cudaDeviceSynchronize());
+    CREATE_CUDA(cudaStreamSynchronize(cs));   // the caller's arrays (and the host vectors above) are no longer read
+    if (ctx->release_M_after_create) {        // the tensor path never reads the plain layout again
+        wb_dev_free_drained(ctx->d_M);        // (only this stream ever touched it)
+        ctx->d_M = nullptr;
+        ctx->release_M_after_create = 0;
+    }
+    tr.mark("tensor plan (tile M) + wait");
     *out = ctx;
     return WB200_OK;
 }
@@ -182,13 +233,13 @@ extern "C" int wb200_set_frozen(wb200_ctx* ctx, const uint8_t* frozen) {
     if (!ctx) return WB200_ERR_ARG;
     cudaSetDevice(ctx->device);
     if (!frozen) {
-        if (ctx->d_frozen) { cudaFree(ctx->d_frozen); ctx->d_frozen = nullptr; }
-        if (ctx->d_nfrozen) { cudaFree(ctx->d_nfrozen); ctx->d_nfrozen = nullptr; }
+        if (ctx->d_frozen) { wb_dev_free(ctx->d_frozen); ctx->d_frozen = nullptr; }
+        if (ctx->d_nfrozen) { wb_dev_free(ctx->d_nfrozen); ctx->d_nfrozen = nullptr; }
         return WB200_OK;
     }
     const size_t n = (size_t)ctx->nk * ctx->nb;
-    if (!ctx->d_frozen) WB_CUDA(ctx, cudaMalloc(&ctx->d_frozen, n));
-    if (!ctx->d_nfrozen) WB_CUDA(ctx, cudaMalloc(&ctx->d_nfrozen, sizeof(int32_t) * ctx->nk));
+    if (!ctx->d_frozen) WB_CUDA(ctx, wb_dev_alloc(&ctx->d_frozen, n));
+    if (!ctx->d_nfrozen) WB_CUDA(ctx, wb_dev_alloc(&ctx->d_nfrozen, sizeof(int32_t) * ctx->nk));
     std::vector<int32_t> nf(ctx->nk, 0);
     for (int k = 0; k < ctx->nk; k++)
         for (int m = 0; m < ctx->nb; m++) nf[k] += frozen[(size_t)k * ctx->nb + m] ? 1 : 0;
@@ -423,8 +474,8 @@ static int ensure_pipeline(wb200_ctx* ctx, const std::vector<int32_t>& kpb_host)
         }
         for (int j = 0; j < S; j++) if (mark[j]) ctx->sub_deps[i].push_back(j);
     }
-    WB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking));
-    WB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
+    WB_CUDA(ctx, wb_stream_acquire(&ctx->h2d_stream));
+    WB_CUDA(ctx, wb_stream_acquire(&ctx->d2h_stream));
     ctx->ev_up.resize(S);
     ctx->ev_grad.resize(S);
     for (int i = 0; i < S; i++) {
@@ -596,8 +647,8 @@ extern "C" int wb200_rotate_overlaps(wb200_ctx* ctx, const double* U, double* N,
 
 static int ensure_xy(wb200_ctx* ctx) {
     const size_t st = (size_t)ctx->nw * ctx->nw + (size_t)ctx->nb * ctx->nw;
-    if (!ctx->d_XY) WB_CUDA(ctx, cudaMalloc(&ctx->d_XY, sizeof(cplx) * st * ctx->nk));
-    if (!ctx->d_GXY) WB_CUDA(ctx, cudaMalloc(&ctx->d_GXY, sizeof(cplx) * st * ctx->nk));
+    if (!ctx->d_XY) WB_CUDA(ctx, wb_dev_alloc(&ctx->d_XY, sizeof(cplx) * st * ctx->nk));
+    if (!ctx->d_GXY) WB_CUDA(ctx, wb_dev_alloc(&ctx->d_GXY, sizeof(cplx) * st * ctx->nk));
     return WB200_OK;
 }
 
@@ -641,8 +692,8 @@ extern "C" int wb200_project_tangent(wb200_ctx* ctx, const double* X, double* G,
     cudaSetDevice(ctx->device);
     const size_t e = (size_t)nrow * ncol * count;
     cplx *dX = nullptr, *dG = nullptr;
-    WB_CUDA(ctx, cudaMalloc(&dX, sizeof(cplx) * e));
-    if (cudaMalloc(&dG, sizeof(cplx) * e) != cudaSuccess) { cudaFree(dX); ctx->err = "cudaMalloc"; return WB200_ERR_CUDA; }
+    WB_CUDA(ctx, wb_dev_alloc(&dX, sizeof(cplx) * e));
+    if (wb_dev_alloc(&dG, sizeof(cplx) * e) != cudaSuccess) { wb_dev_free(dX); ctx->err = "cudaMalloc"; return WB200_ERR_CUDA; }
     int s = WB200_OK;
     if (cudaMemcpyAsync(dX, X, sizeof(cplx) * e, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess ||
         cudaMemcpyAsync(dG, G, sizeof(cplx) * e, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) {
@@ -653,7 +704,7 @@ extern "C" int wb200_project_tangent(wb200_ctx* ctx, const double* X, double* G,
                           cudaStreamSynchronize(ctx->stream) != cudaSuccess)) {
         ctx->err = "D2H copy failed"; s = WB200_ERR_CUDA;
     }
-    cudaFree(dX); cudaFree(dG);
+    wb_dev_free(dX); wb_dev_free(dG);
     return s;
 }
 
@@ -662,7 +713,7 @@ extern "C" int wb200_retract(wb200_ctx* ctx, double* X, int nrow, int ncol, int 
     cudaSetDevice(ctx->device);
     const size_t e = (size_t)nrow * ncol * count;
     cplx* dX = nullptr;
-    WB_CUDA(ctx, cudaMalloc(&dX, sizeof(cplx) * e));
+    WB_CUDA(ctx, wb_dev_alloc(&dX, sizeof(cplx) * e));
     int s = WB200_OK;
     if (cudaMemcpyAsync(dX, X, sizeof(cplx) * e, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) {
         ctx->err = "H2D copy failed"; s = WB200_ERR_CUDA;
@@ -672,7 +723,7 @@ extern "C" int wb200_retract(wb200_ctx* ctx, double* X, int nrow, int ncol, int 
                           cudaStreamSynchronize(ctx->stream) != cudaSuccess)) {
         ctx->err = "D2H copy failed"; s = WB200_ERR_CUDA;
     }
-    cudaFree(dX);
+    wb_dev_free(dX);
     return s;
 }
 
@@ -687,7 +738,7 @@ extern "C" int wb200_max_localize(wb200_ctx* ctx, double* U, double f_tol, doubl
     }
     const size_t e = (size_t)ctx->nk * ctx->nb * ctx->nw;
     cplx* dx = nullptr;
-    WB_CUDA(ctx, cudaMalloc(&dx, sizeof(cplx) * e));
+    WB_CUDA(ctx, wb_dev_alloc(&dx, sizeof(cplx) * e));
     int s = WB200_OK;
     if (cudaMemcpyAsync(dx, U, sizeof(cplx) * e, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) {
         ctx->err = "H2D copy failed"; s = WB200_ERR_CUDA;
@@ -697,7 +748,7 @@ extern "C" int wb200_max_localize(wb200_ctx* ctx, double* U, double f_tol, doubl
                           cudaStreamSynchronize(ctx->stream) != cudaSuccess)) {
         ctx->err = "D2H copy failed"; s = WB200_ERR_CUDA;
     }
-    cudaFree(dx);
+    wb_dev_free(dx);
     return s;
 }
 
@@ -712,7 +763,7 @@ extern "C" int wb200_opt_rotate(wb200_ctx* ctx, double* W, double f_tol, double 
     }
     const size_t e = (size_t)ctx->nw * ctx->nw;
     cplx* dx = nullptr;
-    WB_CUDA(ctx, cudaMalloc(&dx, sizeof(cplx) * e));
+    WB_CUDA(ctx, wb_dev_alloc(&dx, sizeof(cplx) * e));
     int s = WB200_OK;
     if (cudaMemcpyAsync(dx, W, sizeof(cplx) * e, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) {
         ctx->err = "H2D copy failed"; s = WB200_ERR_CUDA;
@@ -722,7 +773,7 @@ extern "C" int wb200_opt_rotate(wb200_ctx* ctx, double* W, double f_tol, double 
                           cudaStreamSynchronize(ctx->stream) != cudaSuccess)) {
         ctx->err = "D2H copy failed"; s = WB200_ERR_CUDA;
     }
-    cudaFree(dx);
+    wb_dev_free(dx);
     return s;
 }
 
@@ -735,7 +786,7 @@ extern "C" int wb200_disentangle(wb200_ctx* ctx, double* XY, double f_tol, doubl
     if (!(ctx->allreduce && ctx->peer_self)) WB_TRY(require_single_slab(ctx, "wb200_disentangle"));
     const size_t e = (size_t)ctx->nk * ((size_t)ctx->nw * ctx->nw + (size_t)ctx->nb * ctx->nw);
     cplx* dx = nullptr;
-    WB_CUDA(ctx, cudaMalloc(&dx, sizeof(cplx) * e));
+    WB_CUDA(ctx, wb_dev_alloc(&dx, sizeof(cplx) * e));
     int s = WB200_OK;
     if (cudaMemcpyAsync(dx, XY, sizeof(cplx) * e, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) {
         ctx->err = "H2D copy failed"; s = WB200_ERR_CUDA;
@@ -745,7 +796,7 @@ extern "C" int wb200_disentangle(wb200_ctx* ctx, double* XY, double f_tol, doubl
                           cudaStreamSynchronize(ctx->stream) != cudaSuccess)) {
         ctx->err = "D2H copy failed"; s = WB200_ERR_CUDA;
     }
-    cudaFree(dx);
+    wb_dev_free(dx);
     return s;
 }
 
@@ -835,7 +886,7 @@ extern "C" int wb200_probe_fp64_peak(int device, double* dmma_tflops, double* df
     if (cudaGetDeviceProperties(&p, device) != cudaSuccess) return WB200_ERR_CUDA;
     const int sms = p.multiProcessorCount;
     double* out = nullptr;
-    if (cudaMalloc(&out, sizeof(double) * sms * 2 * 256) != cudaSuccess) return WB200_ERR_CUDA;
+    if (wb_dev_alloc(&out, sizeof(double) * sms * 2 * 256) != cudaSuccess) return WB200_ERR_CUDA;
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     double best_mma = 0.0, best_fma = 0.0;
@@ -854,7 +905,7 @@ extern "C" int wb200_probe_fp64_peak(int device, double* dmma_tflops, double* df
         if (tf > best_fma) best_fma = tf;
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1);
-    cudaFree(out);
+    wb_dev_free(out);
     if (cudaGetLastError() != cudaSuccess) return WB200_ERR_CUDA;
     if (dmma_tflops) *dmma_tflops = best_mma;
     if (dfma_tflops) *dfma_tflops = best_fma;
@@ -867,6 +918,8 @@ extern "C" int wb200_probe_fp64_peak(int device, double* dmma_tflops, double* df
 extern "C" int wb200_ipc_alloc(int device, size_t bytes, void** dptr, unsigned char handle[64]) {
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
     if (!dptr || !handle || cudaSetDevice(device) != cudaSuccess) return WB200_ERR_ARG;
+    // (memory exported to other processes never goes through the caching allocator: a recycled block could still
+    // be mapped by a peer)
     if (cudaMalloc(dptr, bytes) != cudaSuccess) return WB200_ERR_CUDA;
     cudaIpcMemHandle_t h;
     if (cudaIpcGetMemHandle(&h, *dptr) != cudaSuccess) { cudaFree(*dptr); *dptr = nullptr; return WB200_ERR_CUDA; }
@@ -897,7 +950,7 @@ extern "C" int wb200_set_peer_gauges(wb200_ctx* ctx, int world, const void* cons
     void** owned[] = {(void**)&ctx->d_peerU, (void**)&ctx->d_need_owner, (void**)&ctx->d_need_split, (void**)&ctx->d_owner_split,
                       (void**)&ctx->d_border, (void**)&ctx->d_nloc, (void**)&ctx->d_comm};
     for (void** p : owned)
-        if (*p) { cudaFree(*p); *p = nullptr; }
+        if (*p) { wb_dev_free(*p); *p = nullptr; }
     ctx->peer_world = 0;
     ctx->peer_self = nullptr;
     ctx->peer_rank = -1;
@@ -953,17 +1006,17 @@ extern "C" int wb200_set_peer_gauges(wb200_ctx* ctx, int world, const void* cons
             }
         nloc[k] = (uint8_t)nl;
     }
-    WB_CUDA(ctx, cudaMalloc((void**)&ctx->d_peerU, sizeof(void*) * world));
-    WB_CUDA(ctx, cudaMalloc(&ctx->d_need_owner, sizeof(int32_t) * ctx->n_need));
-    WB_CUDA(ctx, cudaMalloc(&ctx->d_need_split, sizeof(int32_t) * ctx->n_need));
-    WB_CUDA(ctx, cudaMalloc(&ctx->d_owner_split, sizeof(int32_t) * ctx->n_need));
+    WB_CUDA(ctx, wb_dev_alloc((void**)&ctx->d_peerU, sizeof(void*) * world));
+    WB_CUDA(ctx, wb_dev_alloc(&ctx->d_need_owner, sizeof(int32_t) * ctx->n_need));
+    WB_CUDA(ctx, wb_dev_alloc(&ctx->d_need_split, sizeof(int32_t) * ctx->n_need));
+    WB_CUDA(ctx, wb_dev_alloc(&ctx->d_owner_split, sizeof(int32_t) * ctx->n_need));
     WB_CUDA(ctx, cudaMemcpy((void*)ctx->d_peerU, U_ptrs, sizeof(void*) * world, cudaMemcpyHostToDevice));
     WB_CUDA(ctx, cudaMemcpy(ctx->d_need_owner, owner.data(), sizeof(int32_t) * ctx->n_need, cudaMemcpyHostToDevice));
     WB_CUDA(ctx, cudaMemcpy(ctx->d_need_split, need_s.data(), sizeof(int32_t) * ctx->n_need, cudaMemcpyHostToDevice));
     WB_CUDA(ctx, cudaMemcpy(ctx->d_owner_split, owner_s.data(), sizeof(int32_t) * ctx->n_need, cudaMemcpyHostToDevice));
     if (nn > 0 && nn < 256) {
-        WB_CUDA(ctx, cudaMalloc(&ctx->d_border, border.size()));
-        WB_CUDA(ctx, cudaMalloc(&ctx->d_nloc, nloc.size()));
+        WB_CUDA(ctx, wb_dev_alloc(&ctx->d_border, border.size()));
+        WB_CUDA(ctx, wb_dev_alloc(&ctx->d_nloc, nloc.size()));
         WB_CUDA(ctx, cudaMemcpy(ctx->d_border, border.data(), border.size(), cudaMemcpyHostToDevice));
         WB_CUDA(ctx, cudaMemcpy(ctx->d_nloc, nloc.data(), nloc.size(), cudaMemcpyHostToDevice));
         if (!ctx->halo_stream) {

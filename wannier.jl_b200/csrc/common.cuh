@@ -129,11 +129,14 @@ struct wb200_ctx {
     std::vector<HaloRun> halo_runs;               // contiguous runs of remote rows with one owner
     wb200_allreduce_fn allreduce = nullptr;   // caller-supplied collective (sharded optimiser)
     void* allreduce_user = nullptr;
+    int retract_deferred = 0;  // optimiser, single slab: the small retraction does not wait for its convergence flag ...
+    int retract_pending = 0;   // ... which is read after the evaluation's wait (stiefel_small.cu)
     int poison_next = 0;   // the next evaluation's sums are replaced by NaN before they are reduced (a
                            // rank-local failure, e.g. of a retraction, must be seen by every rank)
     double* d_bvec = nullptr;    // [nk][nn][3]
     double* d_wb = nullptr;      // [nn]
     cplx* d_M = nullptr;         // [nk][nn][nb*nb] col-major (generic path / exact N)
+    int release_M_after_create = 0;   // the tensor plan has re-tiled M: wb200_create releases d_M after its final wait
     double wsum = 0.0;           // sum_b w_b
     std::vector<double> h_wb;
     std::vector<int32_t> h_kpb;  // host copy of kpb_k (sub-slab dependency plan)
@@ -242,6 +245,18 @@ struct ProfScope {
     ~ProfScope() { if (stop) cudaEventRecord(stop, c->stream); }
 };
 
+// ---- mempool.cu: process-wide caching of device / page-locked buffers and streams ----
+cudaError_t wb_dev_alloc_raw(void** p, size_t bytes);          // on the current device
+template <class T> inline cudaError_t wb_dev_alloc(T** p, size_t bytes) { return wb_dev_alloc_raw((void**)p, bytes); }
+void wb_dev_free(void* p);                                     // drains the block's device first, like cudaFree
+void wb_dev_free_drained(void* p);                             // the caller has drained the device
+cudaError_t wb_pinned_alloc_raw(void** p, size_t bytes);
+template <class T> inline cudaError_t wb_pinned_alloc(T** p, size_t bytes) { return wb_pinned_alloc_raw((void**)p, bytes); }
+void wb_pinned_free(void* p);
+cudaError_t wb_stream_acquire(cudaStream_t* s);                // non-blocking stream of the current device
+void wb_stream_release(cudaStream_t s);                        // idle streams only
+int wb_device_info(int device, int* major, int* minor, int* num_sms);
+
 // ---- api.cu ----
 int wb_allreduce(wb200_ctx* ctx, double* dptr, int count, int op);   // checked call of the registered collective
 int wb_ensure_pipeline(wb200_ctx* ctx);   // copy streams / events of the host-pointer entry points
@@ -286,6 +301,7 @@ int wb_gu_to_gxy(wb200_ctx* ctx, const cplx* dXY, const cplx* dGU, cplx* dGXY, l
 // ---- stiefel_small.cu ----
 bool wb_small_applicable(int nrow, int ncol);
 int wb_retract_small(wb200_ctx* ctx, cplx* dX, int nrow, int ncol, int ld, long long stride, int count);
+bool wb_retract_pending_failed(wb200_ctx* ctx);
 int wb_project_small(wb200_ctx* ctx, const cplx* dX, cplx* dG, int nrow, int ncol, int ld, long long stride,
                      int count);
 

@@ -169,9 +169,9 @@ __global__ void __launch_bounds__(256) fro_kernel(int len, const cplx* __restric
 
 int wb_ensure_zpart(wb200_ctx* ctx, size_t elems) {
     if (elems <= ctx->zpart_elems) return WB200_OK;
-    if (ctx->d_zpart) cudaFree(ctx->d_zpart);
+    if (ctx->d_zpart) wb_dev_free(ctx->d_zpart);
     ctx->d_zpart = nullptr; ctx->zpart_elems = 0;
-    WB_CUDA(ctx, cudaMalloc(&ctx->d_zpart, sizeof(double) * elems));
+    WB_CUDA(ctx, wb_dev_alloc(&ctx->d_zpart, sizeof(double) * elems));
     ctx->zpart_elems = elems;
     return WB200_OK;
 }
@@ -204,7 +204,7 @@ int wb_rotate_generic(wb200_ctx* ctx, const cplx* dU, int ka, int kb) {
 
 int wb_ensure_N(wb200_ctx* ctx) {
     if (ctx->d_N) return WB200_OK;
-    WB_CUDA(ctx, cudaMalloc(&ctx->d_N, sizeof(cplx) * (size_t)ctx->nk * ctx->nn * ctx->nw * ctx->nw));
+    WB_CUDA(ctx, wb_dev_alloc(&ctx->d_N, sizeof(cplx) * (size_t)ctx->nk * ctx->nn * ctx->nw * ctx->nw));
     return WB200_OK;
 }
 
@@ -510,15 +510,15 @@ int wb_halo_fetch(wb200_ctx* ctx, cplx* dU) {
 
 int wb_ensure_tmp(wb200_ctx* ctx, size_t e1, size_t e2) {
     if (e1 > ctx->tmp1_elems) {
-        if (ctx->d_tmp1) cudaFree(ctx->d_tmp1);
+        if (ctx->d_tmp1) wb_dev_free(ctx->d_tmp1);
         ctx->d_tmp1 = nullptr; ctx->tmp1_elems = 0;
-        WB_CUDA(ctx, cudaMalloc(&ctx->d_tmp1, sizeof(cplx) * e1));
+        WB_CUDA(ctx, wb_dev_alloc(&ctx->d_tmp1, sizeof(cplx) * e1));
         ctx->tmp1_elems = e1;
     }
     if (e2 > ctx->tmp2_elems) {
-        if (ctx->d_tmp2) cudaFree(ctx->d_tmp2);
+        if (ctx->d_tmp2) wb_dev_free(ctx->d_tmp2);
         ctx->d_tmp2 = nullptr; ctx->tmp2_elems = 0;
-        WB_CUDA(ctx, cudaMalloc(&ctx->d_tmp2, sizeof(cplx) * e2));
+        WB_CUDA(ctx, wb_dev_alloc(&ctx->d_tmp2, sizeof(cplx) * e2));
         ctx->tmp2_elems = e2;
     }
     return WB200_OK;

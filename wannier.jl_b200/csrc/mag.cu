@@ -246,7 +246,7 @@ extern "C" void wb200_mag_destroy(wb200_mag* m) {
     if (!m) return;
     if (m->up) cudaSetDevice(m->up->device);
     void* ptrs[] = {m->d_Mud, m->d_T, m->d_S, m->d_dpart, m->d_d, m->d_Mw, m->d_XY, m->d_GXY, m->d_out};
-    for (void* p : ptrs) if (p) cudaFree(p);
+    for (void* p : ptrs) if (p) wb_dev_free(p);
     delete m;
 }
 
@@ -270,12 +270,12 @@ extern "C" int wb200_mag_create(wb200_mag** out, wb200_ctx* up, wb200_ctx* dn, c
     m->up = up; m->dn = dn; m->nb = up->nb; m->nw = up->nw; m->nk = up->nk;
     const size_t mat = (size_t)m->nb * m->nw;
     const int nchunks = (m->nk + 63) / 64;
-    cudaError_t e = cudaMalloc(&m->d_Mud, sizeof(cplx) * (size_t)m->nk * m->nb * m->nb);
-    if (e == cudaSuccess) e = cudaMalloc(&m->d_T, sizeof(cplx) * (size_t)m->nk * mat);
-    if (e == cudaSuccess) e = cudaMalloc(&m->d_S, sizeof(cplx) * (size_t)m->nk * mat);
-    if (e == cudaSuccess) e = cudaMalloc(&m->d_dpart, sizeof(cplx) * (size_t)(m->nk + nchunks) * m->nw);
-    if (e == cudaSuccess) e = cudaMalloc(&m->d_d, sizeof(cplx) * m->nw);
-    if (e == cudaSuccess) e = cudaMalloc(&m->d_out, sizeof(double) * 4);
+    cudaError_t e = wb_dev_alloc(&m->d_Mud, sizeof(cplx) * (size_t)m->nk * m->nb * m->nb);
+    if (e == cudaSuccess) e = wb_dev_alloc(&m->d_T, sizeof(cplx) * (size_t)m->nk * mat);
+    if (e == cudaSuccess) e = wb_dev_alloc(&m->d_S, sizeof(cplx) * (size_t)m->nk * mat);
+    if (e == cudaSuccess) e = wb_dev_alloc(&m->d_dpart, sizeof(cplx) * (size_t)(m->nk + nchunks) * m->nw);
+    if (e == cudaSuccess) e = wb_dev_alloc(&m->d_d, sizeof(cplx) * m->nw);
+    if (e == cudaSuccess) e = wb_dev_alloc(&m->d_out, sizeof(double) * 4);
     if (e == cudaSuccess) e = cudaMemcpy(m->d_Mud, Mud, sizeof(cplx) * (size_t)m->nk * m->nb * m->nb, cudaMemcpyDefault);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
@@ -311,7 +311,7 @@ extern "C" int wb200_mag_overlap(wb200_mag* m, const double* Uup, const double* 
     WB_TRY(mag_upload_gauges(m, Uup, Udn));
     WB_TRY(mag_coupling(m, m->up->d_U, m->dn->d_U, false, false, nullptr, nullptr, 0.0, nullptr));
     if (Mw2) {
-        if (!m->d_Mw) MAG_CUDA(m, cudaMalloc(&m->d_Mw, sizeof(cplx) * (size_t)nk * nw * nw + sizeof(double) * nw * nw));
+        if (!m->d_Mw) MAG_CUDA(m, wb_dev_alloc(&m->d_Mw, sizeof(cplx) * (size_t)nk * nw * nw + sizeof(double) * nw * nw));
         ZgemmArgs a{};   // Mw_k = Uup_k^H T_k
         a.m = nw; a.n = nw; a.k = nb;
         a.A = m->up->d_U; a.strideA = (long long)nb * nw; a.lda = nb; a.transA = 1;
@@ -347,8 +347,8 @@ extern "C" int wb200_mag_omega_updn_grad(wb200_mag* m, const double* Uup, const 
 
 static int mag_ensure_xy(wb200_mag* m) {
     const size_t bytes = sizeof(cplx) * 2 * m->n_inner() * m->nk;
-    if (!m->d_XY) MAG_CUDA(m, cudaMalloc(&m->d_XY, bytes));
-    if (!m->d_GXY) MAG_CUDA(m, cudaMalloc(&m->d_GXY, bytes));
+    if (!m->d_XY) MAG_CUDA(m, wb_dev_alloc(&m->d_XY, bytes));
+    if (!m->d_GXY) MAG_CUDA(m, wb_dev_alloc(&m->d_GXY, bytes));
     return WB200_OK;
 }
 

@@ -144,18 +144,18 @@ extern "C" void wb200_multi_destroy(wb200_multi* m) {
         if (m->ctx[r]) wb200_destroy(m->ctx[r]);
         if (r < (int)m->Ufull.size() && m->Ufull[r]) {
             cudaSetDevice(m->devices[r]);
-            cudaFree(m->Ufull[r]);
+            wb_dev_free(m->Ufull[r]);
         }
         if (r < (int)m->flags.size() && m->flags[r]) {
             cudaSetDevice(m->devices[r]);
-            cudaFree(m->flags[r]);
+            wb_dev_free(m->flags[r]);
         }
         for (auto* v : {&m->inproc.ev_ready, &m->inproc.ev_packed, &m->inproc.ev_ar[0], &m->inproc.ev_ar[1]})
             if (r < (int)v->size() && (*v)[r]) { cudaSetDevice(m->devices[r]); cudaEventDestroy((*v)[r]); }
     }
     for (int p = 0; p < 2; p++) {
-        if (m->h_x[p]) cudaFreeHost(m->h_x[p]);
-        if (m->h_r[p]) cudaFreeHost(m->h_r[p]);
+        if (m->h_x[p]) wb_pinned_free(m->h_x[p]);
+        if (m->h_r[p]) wb_pinned_free(m->h_r[p]);
     }
     delete m;
 }
@@ -190,7 +190,7 @@ extern "C" int wb200_multi_create(wb200_multi** out, const int* devices, int nde
         const int s = wb200_create(&m->ctx[r], devices[r], nb, nw, nk, k0, k1 - k0, nn, kpb_k + (size_t)k0 * nn,
                                    bvec_cart + (size_t)k0 * nn * 3, bweights, M + 2 * (size_t)k0 * nn * nb * nb, flags);
         if (s != WB200_OK) return fail(s, std::string("wb200_multi_create: slab ") + std::to_string(r) + ": " + wb200_last_error(nullptr));
-        if (cudaSetDevice(devices[r]) != cudaSuccess || cudaMalloc(&m->Ufull[r], sizeof(cplx) * mat * nk) != cudaSuccess)
+        if (cudaSetDevice(devices[r]) != cudaSuccess || wb_dev_alloc(&m->Ufull[r], sizeof(cplx) * mat * nk) != cudaSuccess)
             return fail(WB200_ERR_CUDA, "wb200_multi_create: cudaMalloc of the gauge array failed");
     }
     // peer access between the distinct devices (the pack kernels read neighbour gauges from their owners)
@@ -208,8 +208,8 @@ extern "C" int wb200_multi_create(wb200_multi** out, const int* devices, int nde
             cudaGetLastError();
         }
     for (int p = 0; p < 2; p++)
-        if (cudaMallocHost(&m->h_x[p], sizeof(double) * (size_t)ndev * m->maxc) != cudaSuccess ||
-            cudaMallocHost(&m->h_r[p], sizeof(double) * (size_t)ndev * m->maxc) != cudaSuccess)
+        if (wb_pinned_alloc(&m->h_x[p], sizeof(double) * (size_t)ndev * m->maxc) != cudaSuccess ||
+            wb_pinned_alloc(&m->h_r[p], sizeof(double) * (size_t)ndev * m->maxc) != cudaSuccess)
             return fail(WB200_ERR_CUDA, "wb200_multi_create: cudaMallocHost failed");
     // The library's own peer-memory collectives (peer.cu): packed halo rows pulled by the copy engines under the
     // rotation, all-reduces as a push into every slab's slot + a rank-order sum.  Between the slabs of ONE process the
@@ -230,7 +230,7 @@ extern "C" int wb200_multi_create(wb200_multi** out, const int* devices, int nde
     const size_t comm_bytes = wb200_peer_comm_bytes(nw);
     if (peer_comm)
         for (int r = 0; r < ndev; r++)
-            if (cudaSetDevice(devices[r]) != cudaSuccess || cudaMalloc(&m->flags[r], comm_bytes) != cudaSuccess ||
+            if (cudaSetDevice(devices[r]) != cudaSuccess || wb_dev_alloc(&m->flags[r], comm_bytes) != cudaSuccess ||
                 cudaMemset(m->flags[r], 0, comm_bytes) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess)
                 return fail(WB200_ERR_CUDA, "wb200_multi_create: cudaMalloc of the comm buffers failed");
     if (peer_comm && !spin_flags) {

@@ -242,7 +242,7 @@ struct Problem {
         if (!dS) {
             if (wb_small_applicable(ctx->nb, ctx->nw) || (ctx->flags & WB200_FLAG_NO_TENSOR) ||
                 !wb_zgemm_tensor_applicable(ctx->nw, ctx->nw, ctx->nb)) return WB200_OK;
-            WB_CUDA(ctx, cudaMalloc(&dS, sizeof(cplx) * (size_t)ctx->nk * ctx->nw * ctx->nw));
+            WB_CUDA(ctx, wb_dev_alloc(&dS, sizeof(cplx) * (size_t)ctx->nk * ctx->nw * ctx->nw));
         }
         bool ok = false;
         double fro = 0.0;
@@ -250,7 +250,7 @@ struct Problem {
         if (ok) { gram.S = dS; gram.fro_max = fro; }
         return WB200_OK;
     }
-    ~Problem() { if (dS) cudaFree(dS); }
+    ~Problem() { if (dS) wb_dev_free(dS); }
 
     // tangent_step: x = x0 + a s with x0 on the manifold and s tangent at x0 (every trial point of a line search)
     // alpha > 0: x = x0 + alpha s with s the direction prepare_direction() saw
@@ -306,6 +306,10 @@ struct Problem {
         WB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         *f = ctx->h_pinned[16];
         if (d) *gd = ctx->h_pinned[WB_PIN_CROSS];
+        if (wb_retract_pending_failed(ctx)) {   // the deferred check of the retraction in front of this evaluation:
+            *f = NAN;                           // a point that is not on the manifold is a rejected trial point
+            if (d) *gd = NAN;
+        }
         if (mode == 2 && !ctx->allreduce && ctx->h_pinned[17] < 1e-10) {   // opt_rotate.jl:60-62
             ctx->err = "N^kb too small! (|N_nn| < 1e-10)";
             return WB200_ERR_SINGULAR;
@@ -332,6 +336,14 @@ static int lbfgs_run(wb200_ctx* ctx, int mode, const WbCustomProblem* custom, cp
                      int max_iter, int history, double* f_final, int* iters_out, int* n_fg_out) {
     Problem P{ctx, mode, 0};
     P.custom = custom;
+    // single slab: the convergence flag of a small-shape retraction is read after the evaluation's wait (one host round
+    // trip per trial point); k-sharded runs keep the immediate check, every rank must poison the same evaluation
+    struct Deferred {
+        wb200_ctx* c;
+        ~Deferred() { c->retract_deferred = 0; c->retract_pending = 0; }
+    } deferred_guard{ctx};
+    ctx->retract_deferred = (mode != 3 && !ctx->allreduce) ? 1 : 0;
+    ctx->retract_pending = 0;
     const size_t ncplx = (mode == 3) ? custom->ncplx : (mode == 2) ? (size_t)ctx->nw * ctx->nw
                          : (mode == 0) ? (size_t)ctx->nk * ctx->nb * ctx->nw
                                        : (size_t)ctx->nk * ((size_t)ctx->nw * ctx->nw + (size_t)ctx->nb * ctx->nw);
@@ -344,8 +356,8 @@ static int lbfgs_run(wb200_ctx* ctx, int mode, const WbCustomProblem* custom, cp
     const int nfixed = 4;
     const int nvec = nfixed + 2 * m;
     double* pool = nullptr;
-    WB_CUDA(ctx, cudaMalloc(&pool, sizeof(double) * n * nvec));
-    struct Free { double* p; ~Free() { cudaFree(p); } } guard{pool};
+    WB_CUDA(ctx, wb_dev_alloc(&pool, sizeof(double) * n * nvec));
+    struct Free { double* p; ~Free() { wb_dev_free(p); } } guard{pool};
     auto vec = [&](int i) { return pool + (size_t)i * n; };
     // x lives in the caller's array or in a spare (pointer swaps instead of copies)
     double *x = (double*)dx, *g = vec(0), *s = vec(1), *xn = vec(2), *gn = vec(3);

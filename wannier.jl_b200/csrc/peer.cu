@@ -226,7 +226,7 @@ extern "C" int wb200_set_peer_comm(wb200_ctx* ctx, int world, void* const* comm_
     if (!ctx) return WB200_ERR_ARG;
     cudaSetDevice(ctx->device);
     WB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    if (ctx->d_comm) { cudaFree((void*)ctx->d_comm); ctx->d_comm = nullptr; }
+    if (ctx->d_comm) { wb_dev_free((void*)ctx->d_comm); ctx->d_comm = nullptr; }
     if (wb_allreduce_is_builtin(ctx)) { ctx->allreduce = nullptr; ctx->allreduce_user = nullptr; }
     ctx->my_comm = nullptr;
     ctx->epoch = 0;
@@ -236,7 +236,7 @@ extern "C" int wb200_set_peer_comm(wb200_ctx* ctx, int world, void* const* comm_
         ctx->err = "wb200_set_peer_comm: call wb200_set_peer_gauges first, with the same world size (at most 32)";
         return WB200_ERR_ARG;
     }
-    WB_CUDA(ctx, cudaMalloc((void**)&ctx->d_comm, sizeof(void*) * world));
+    WB_CUDA(ctx, wb_dev_alloc((void**)&ctx->d_comm, sizeof(void*) * world));
     WB_CUDA(ctx, cudaMemcpy((void*)ctx->d_comm, comm_ptrs, sizeof(void*) * world, cudaMemcpyHostToDevice));
     ctx->my_comm = (unsigned long long*)comm_ptrs[ctx->peer_rank];
     ctx->comm_maxc = 4 * ctx->nw + 64;

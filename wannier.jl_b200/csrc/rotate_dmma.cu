@@ -875,10 +875,10 @@ int wb_dmma_plan_create(wb200_ctx* ctx, const double* /*hM*/) {
     p->b_stage = (size_t)p->WN * (p->KC / 4) * 32 * 6;
     ctx->dmma = p;
     const size_t pairs = (size_t)ctx->nk * ctx->nn;
-    WB_CUDA(ctx, cudaMalloc(&p->d_Mt, sizeof(double) * pairs * p->nch * p->a_stage));
-    WB_CUDA(ctx, cudaMalloc(&p->d_Up, sizeof(double) * (size_t)ctx->nk_total * p->nct * p->nch * p->b_stage));
-    if (!p->small) WB_CUDA(ctx, cudaMalloc(&p->d_dNp, sizeof(cplx) * pairs * p->WM * nw));
-    WB_CUDA(ctx, cudaMalloc(&p->d_frop, sizeof(double) * pairs * (p->small ? 2 : p->nct * 8)));
+    WB_CUDA(ctx, wb_dev_alloc(&p->d_Mt, sizeof(double) * pairs * p->nch * p->a_stage));
+    WB_CUDA(ctx, wb_dev_alloc(&p->d_Up, sizeof(double) * (size_t)ctx->nk_total * p->nct * p->nch * p->b_stage));
+    if (!p->small) WB_CUDA(ctx, wb_dev_alloc(&p->d_dNp, sizeof(cplx) * pairs * p->WM * nw));
+    WB_CUDA(ctx, wb_dev_alloc(&p->d_frop, sizeof(double) * pairs * (p->small ? 2 : p->nct * 8)));
     // re-lay-out M (already uploaded to d_M) into the A-operand image; d_M is then released:
     // the tensor path never reads the plain layout again.
     dim3 grid((unsigned)pairs, (unsigned)p->nch);
@@ -887,25 +887,26 @@ int wb_dmma_plan_create(wb200_ctx* ctx, const double* /*hM*/) {
     if (nb == nw) {
         const char* e = getenv("WB200_CONST_NORM");
         if (!(e && e[0] == '0')) {
-            WB_CUDA(ctx, cudaMalloc(&p->d_froM, sizeof(double) * pairs));
+            WB_CUDA(ctx, wb_dev_alloc(&p->d_froM, sizeof(double) * pairs));
             overlap_norm_kernel<<<(unsigned)pairs, 256, 0, ctx->stream>>>(nb, ctx->d_M, p->d_froM);
             WB_LAUNCH_CHECK(ctx);
         }
     }
-    WB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    cudaFree(ctx->d_M);
-    ctx->d_M = nullptr;
+    // d_M is released when the tiling kernels have run: enqueue nothing after them that reads it, and let the
+    // end-of-create wait cover the release (the block goes back to the pool only then: see wb200_create)
+    ctx->release_M_after_create = 1;
     return WB200_OK;
 }
 
 void wb_dmma_plan_destroy(wb200_ctx* ctx) {
     DmmaPlan* p = ctx->dmma;
     if (!p) return;
-    if (p->d_Mt) cudaFree(p->d_Mt);
-    if (p->d_Up) cudaFree(p->d_Up);
-    if (p->d_dNp) cudaFree(p->d_dNp);
-    if (p->d_frop) cudaFree(p->d_frop);
-    if (p->d_froM) cudaFree(p->d_froM);
+    // (wb200_destroy has drained the device)
+    if (p->d_Mt) wb_dev_free_drained(p->d_Mt);
+    if (p->d_Up) wb_dev_free_drained(p->d_Up);
+    if (p->d_dNp) wb_dev_free_drained(p->d_dNp);
+    if (p->d_frop) wb_dev_free_drained(p->d_frop);
+    if (p->d_froM) wb_dev_free_drained(p->d_froM);
     delete p;
     ctx->dmma = nullptr;
 }

@@ -171,7 +171,7 @@ int wb_u_to_xy_dev(wb200_ctx* ctx, const cplx* dU, cplx* dXY) {
 
 static int setup_host(wb200_ctx* ctx, const double* U, double* XY, double* U_out) {
     const size_t mat = (size_t)ctx->nb * ctx->nw, st = (size_t)ctx->nw * ctx->nw + mat;
-    if (!ctx->d_XY) WB_CUDA(ctx, cudaMalloc(&ctx->d_XY, sizeof(cplx) * st * ctx->nk));
+    if (!ctx->d_XY) WB_CUDA(ctx, wb_dev_alloc(&ctx->d_XY, sizeof(cplx) * st * ctx->nk));
     WB_CUDA(ctx, cudaMemcpyAsync(ctx->d_U, U, sizeof(cplx) * mat * ctx->nk, cudaMemcpyHostToDevice, ctx->stream));
     WB_TRY(wb_u_to_xy_dev(ctx, ctx->d_U, ctx->d_XY));
     if (XY)
@@ -202,23 +202,22 @@ extern "C" int wb200_create_stiefel(wb200_ctx** out, int device, int nb, int nw,
     if (!out) return WB200_ERR_ARG;
     *out = nullptr;
     if (nb <= 0 || nw <= 0 || nw > nb || nk <= 0) return WB200_ERR_ARG;
-    int ndev = 0;
-    cudaDeviceProp prop;
+    int ndev = 0, cc_major = 0, cc_minor = 0, num_sms = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev ||
-        cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major != 10)
+        wb_device_info(device, &cc_major, &cc_minor, &num_sms) != WB200_OK || cc_major != 10)
         return WB200_ERR_NODEVICE;
     if (cudaSetDevice(device) != cudaSuccess) return WB200_ERR_CUDA;
     wb200_ctx* ctx = new wb200_ctx();
     ctx->device = device;
-    ctx->num_sms = prop.multiProcessorCount;
+    ctx->num_sms = num_sms;
     ctx->use_graphs = 0;
     ctx->nb = nb; ctx->nw = nw; ctx->nk_total = nk; ctx->k_begin = 0; ctx->nk = nk; ctx->nn = 0;
-    cudaError_t e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
+    cudaError_t e = wb_stream_acquire(&ctx->own_stream);
     ctx->stream = ctx->own_stream;
-    if (e == cudaSuccess) e = cudaMalloc(&ctx->d_U, sizeof(cplx) * (size_t)nk * nb * nw);
-    if (e == cudaSuccess) e = cudaMalloc(&ctx->d_scal, sizeof(double) * 2048);
-    if (e == cudaSuccess) e = cudaMalloc(&ctx->d_res, sizeof(double) * ctx->nres());
-    if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_pinned, sizeof(double) * (ctx->nres() + 64));
+    if (e == cudaSuccess) e = wb_dev_alloc(&ctx->d_U, sizeof(cplx) * (size_t)nk * nb * nw);
+    if (e == cudaSuccess) e = wb_dev_alloc(&ctx->d_scal, sizeof(double) * 2048);
+    if (e == cudaSuccess) e = wb_dev_alloc(&ctx->d_res, sizeof(double) * ctx->nres());
+    if (e == cudaSuccess) e = wb_pinned_alloc(&ctx->h_pinned, sizeof(double) * (ctx->nres() + 64));
     if (e != cudaSuccess) { wb200_destroy(ctx); return WB200_ERR_CUDA; }
     *out = ctx;
     return WB200_OK;

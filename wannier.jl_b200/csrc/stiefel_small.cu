@@ -352,6 +352,28 @@ static bool use32(int nrow, int ncol) {
     return !off && nrow <= 32 && ncol <= 32;
 }
 
+// "did every matrix converge?" comes back in h_pinned[8].  Normally the caller waits for it here.  The optimiser
+// (ctx->retract_deferred, single-slab runs) does not: the evaluation that follows is enqueued right behind the
+// retraction and the flag is read after THAT wait (wb_retract_pending_failed) — one host round trip per trial point
+// instead of two; the flag accumulates over the retractions of one trial point (X and Y factors).
+static int retract_flag_check(wb200_ctx* ctx, int* flag) {
+    int* hflag = reinterpret_cast<int*>(ctx->h_pinned + 8);
+    WB_CUDA(ctx, cudaMemcpyAsync(hflag, flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    if (ctx->retract_deferred) { ctx->retract_pending = 1; return WB200_OK; }
+    WB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (*hflag) {
+        ctx->err = "retract: Newton-Schulz polar iteration did not converge (singular or NaN input?)";
+        return WB200_ERR_NOCONV;
+    }
+    return WB200_OK;
+}
+// after a wait on ctx->stream: did a deferred retraction fail?  Clears the pending state.
+bool wb_retract_pending_failed(wb200_ctx* ctx) {
+    if (!ctx->retract_pending) return false;
+    ctx->retract_pending = 0;
+    return *reinterpret_cast<int*>(ctx->h_pinned + 8) != 0;
+}
+
 int wb_retract_small(wb200_ctx* ctx, cplx* dX, int nrow, int ncol, int ld, long long stride, int count) {
     if (use32(nrow, ncol)) {
         const size_t smem32 = sizeof(cplx) * 4 * 2 * S32_MAT;
@@ -360,17 +382,10 @@ int wb_retract_small(wb200_ctx* ctx, cplx* dX, int nrow, int ncol, int ld, long 
             ctx->attr_mask |= 16u;
         }
         int* flag = reinterpret_cast<int*>(ctx->d_scal + 4);
-        WB_CUDA(ctx, cudaMemsetAsync(flag, 0, sizeof(int), ctx->stream));
+        if (!ctx->retract_pending) WB_CUDA(ctx, cudaMemsetAsync(flag, 0, sizeof(int), ctx->stream));
         retract32_kernel<<<(count + 3) / 4, 256, smem32, ctx->stream>>>(nrow, ncol, ld, stride, dX, count, 100, 2e-8, flag);
         WB_LAUNCH_CHECK(ctx);
-        int* hflag = reinterpret_cast<int*>(ctx->h_pinned + 8);
-        WB_CUDA(ctx, cudaMemcpyAsync(hflag, flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-        WB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        if (*hflag) {
-            ctx->err = "retract: Newton-Schulz polar iteration did not converge (singular or NaN input?)";
-            return WB200_ERR_NOCONV;
-        }
-        return WB200_OK;
+        return retract_flag_check(ctx, flag);
     }
     const size_t smem = sizeof(cplx) * ((size_t)ncol * (nrow + 1) + (size_t)ncol * ncol);
     if (!(ctx->attr_mask & 2u)) {
@@ -379,17 +394,10 @@ int wb_retract_small(wb200_ctx* ctx, cplx* dX, int nrow, int ncol, int ld, long 
         ctx->attr_mask |= 2u;
     }
     int* flag = reinterpret_cast<int*>(ctx->d_scal + 4);
-    WB_CUDA(ctx, cudaMemsetAsync(flag, 0, sizeof(int), ctx->stream));
+    if (!ctx->retract_pending) WB_CUDA(ctx, cudaMemsetAsync(flag, 0, sizeof(int), ctx->stream));
     retract_small_kernel<<<count, WB_SMALL_THREADS, smem, ctx->stream>>>(nrow, ncol, ld, stride, dX, 100, 2e-8, flag);
     WB_LAUNCH_CHECK(ctx);
-    int* hflag = reinterpret_cast<int*>(ctx->h_pinned + 8);
-    WB_CUDA(ctx, cudaMemcpyAsync(hflag, flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    WB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    if (*hflag) {
-        ctx->err = "retract: Newton-Schulz polar iteration did not converge (singular or NaN input?)";
-        return WB200_ERR_NOCONV;
-    }
-    return WB200_OK;
+    return retract_flag_check(ctx, flag);
 }
 
 int wb_project_small(wb200_ctx* ctx, const cplx* dX, cplx* dG, int nrow, int ncol, int ld, long long stride,

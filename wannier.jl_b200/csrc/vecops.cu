@@ -140,7 +140,7 @@ int wb_cross_launch(wb200_ctx* ctx, const WbCrossArgs& p, size_t n) {
     const int blocks = (int)(want < (size_t)RED_MAX_BLOCKS ? (want ? want : 1) : RED_MAX_BLOCKS);
     if (!ctx->d_red) {
         const size_t bytes = sizeof(double) * WB_CROSS_NOUT * (RED_MAX_BLOCKS + 1);
-        WB_CUDA(ctx, cudaMalloc(&ctx->d_red, bytes));
+        WB_CUDA(ctx, wb_dev_alloc(&ctx->d_red, bytes));
         WB_CUDA(ctx, cudaMemsetAsync(ctx->d_red, 0, bytes, ctx->stream));   // slots a small instantiation never writes
     }
     double* out = ctx->d_red + (size_t)WB_CROSS_NOUT * RED_MAX_BLOCKS;

@@ -22,7 +22,7 @@ SYMBOLS = [
     "wb200_fg_xy", "wb200_project_tangent", "wb200_retract", "wb200_max_localize",
     "wb200_disentangle", "wb200_nsums", "wb200_nres", "wb200_fg_phase1_dev", "wb200_fg_phase2_dev",
     "wb200_fg_dev", "wb200_min_abs_diag", "wb200_project_tangent_dev", "wb200_retract_dev",
-    "wb200_profile", "wb200_profile_read", "wb200_probe_fp64_peak",
+    "wb200_profile", "wb200_profile_read", "wb200_probe_fp64_peak", "wb200_trim_pools", "wb200_pool_stats",
     "wb200_omega_local", "wb200_fg_rotate", "wb200_opt_rotate", "wb200_position_op", "wb200_berry_connection",
     "wb200_set_allreduce",
     "wb200_ipc_alloc", "wb200_ipc_open", "wb200_ipc_close", "wb200_ipc_free", "wb200_set_peer_gauges",
@@ -158,9 +158,14 @@ def load():
     lib.wb200_profile.argtypes = [vp, i32]
     lib.wb200_profile_read.argtypes = [vp, pd, pd]
     lib.wb200_probe_fp64_peak.argtypes = [i32, pd, pd]
+    lib.wb200_trim_pools.argtypes = []
+    lib.wb200_trim_pools.restype = None
+    lib.wb200_pool_stats.argtypes = [i32, pd, pd]
+    lib.wb200_pool_stats.restype = C.c_longlong
     for name in SYMBOLS:
         f = getattr(lib, name)
-        if name not in ("wb200_destroy", "wb200_last_error", "wb200_version", "wb200_launch_count",
+        if name not in ("wb200_destroy", "wb200_last_error", "wb200_version", "wb200_launch_count", "wb200_trim_pools",
+                        "wb200_pool_stats",
                         "wb200_multi_destroy", "wb200_multi_last_error", "wb200_multi_launch_count",
                         "wb200_mag_destroy", "wb200_mag_last_error", "wb200_io_last_error"):
             f.restype = i32
@@ -613,6 +618,18 @@ def probe_fp64_peak(device=0):
     if st != 0:
         raise WB200Error(st, "wb200_probe_fp64_peak failed")
     return a.value, b.value
+
+
+def trim_pools():
+    """Give the device / page-locked buffers and streams kept from destroyed contexts back to the driver."""
+    load().wb200_trim_pools()
+
+
+def pool_stats(device=0):
+    """(bytes kept on `device` (< 0: page-locked host bytes), hits, misses) of the caching allocator."""
+    h, m = C.c_longlong(0), C.c_longlong(0)
+    kept = load().wb200_pool_stats(device, C.addressof(h), C.addressof(m))
+    return kept, h.value, m.value
 
 
 def ipc_alloc(device, nbytes):
