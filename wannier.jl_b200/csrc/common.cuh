@@ -131,6 +131,7 @@ struct wb200_ctx {
     void* allreduce_user = nullptr;
     int retract_deferred = 0;  // optimiser, single slab: the small retraction does not wait for its convergence flag ...
     int retract_pending = 0;   // ... which is read after the evaluation's wait (stiefel_small.cu)
+    int publish_eval = 0;      // the next wb_cross_launch also publishes f, min |N_nn| and the retraction flag (vecops.cu)
     int poison_next = 0;   // the next evaluation's sums are replaced by NaN before they are reduced (a
                            // rank-local failure, e.g. of a retraction, must be seen by every rank)
     double* d_bvec = nullptr;    // [nk][nn][3]

@@ -288,10 +288,19 @@ struct Problem {
             WB_TRY(wb_gu_to_gxy(ctx, x, ctx->d_G, g));
         }
         }
-        WB_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned + 16, ctx->d_res + 5, sizeof(double),
-                                     cudaMemcpyDeviceToHost, ctx->stream));
-        WB_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned + 17, ctx->d_min, sizeof(double),
-                                     cudaMemcpyDeviceToHost, ctx->stream));
+        // f, min |N_nn| and the deferred retraction flag reach the host with the inner product's results (zero-copy
+        // stores of the last kernel, vecops.cu) when this evaluation has one and the run is a single slab; by copies
+        // otherwise
+        const bool published = d && !ctx->allreduce;
+        if (!published) {
+            WB_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned + 16, ctx->d_res + 5, sizeof(double),
+                                         cudaMemcpyDeviceToHost, ctx->stream));
+            WB_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned + 17, ctx->d_min, sizeof(double),
+                                         cudaMemcpyDeviceToHost, ctx->stream));
+            if (ctx->retract_pending)
+                WB_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned + 8, ctx->d_scal + 4, sizeof(int),
+                                             cudaMemcpyDeviceToHost, ctx->stream));
+        }
         {
             TraceScope ts_(trace, 2, ctx->stream);
             WB_TRY(project(x, g));
@@ -301,7 +310,10 @@ struct Problem {
             WbCrossArgs c{};
             c.a[0] = (const double*)g; c.na = 1;
             c.b[0] = d; c.nb = 1;
-            WB_TRY(wb_cross_launch(ctx, c, n));
+            ctx->publish_eval = published ? 1 : 0;
+            const int st_ = wb_cross_launch(ctx, c, n);
+            ctx->publish_eval = 0;
+            WB_TRY(st_);
         }
         WB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         *f = ctx->h_pinned[16];

@@ -358,8 +358,8 @@ static bool use32(int nrow, int ncol) {
 // instead of two; the flag accumulates over the retractions of one trial point (X and Y factors).
 static int retract_flag_check(wb200_ctx* ctx, int* flag) {
     int* hflag = reinterpret_cast<int*>(ctx->h_pinned + 8);
+    if (ctx->retract_deferred) { ctx->retract_pending = 1; return WB200_OK; }   // delivered with the evaluation's results
     WB_CUDA(ctx, cudaMemcpyAsync(hflag, flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    if (ctx->retract_deferred) { ctx->retract_pending = 1; return WB200_OK; }
     WB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (*hflag) {
         ctx->err = "retract: Newton-Schulz polar iteration did not converge (singular or NaN input?)";

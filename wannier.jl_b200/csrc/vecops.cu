@@ -19,10 +19,34 @@ namespace {
 constexpr int RED_THREADS = 256;
 constexpr int RED_MAX_BLOCKS = 148 * 8;
 
-// NA x NB inner products in one pass; A_IN_B: a[i] is b[i] (read once)
+// What the host reads after an evaluation of the optimiser, written straight into page-locked host memory by the
+// last kernel of the chain (zero-copy stores) instead of four 8-byte device-to-host copies behind it: each copy is a
+// node of its own in the stream and costs more than the kernels of a 64-k-point problem (profiles/r4_summary.md).
+struct WbPublish {
+    double* hout;          // h_pinned + WB_PIN_CROSS (nullptr: nothing is published)
+    const double* f;       // d_res + 5   -> h_pinned[16]
+    const double* dmin;    // d_min       -> h_pinned[17]
+    const int* flag;       // retraction flag -> h_pinned[8] (as int)
+    double* hbase;         // h_pinned
+};
+
+__device__ __forceinline__ void publish_result(const WbPublish& pub, int slot, double r) {
+    if (!pub.hout) return;
+    pub.hout[slot] = r;
+    if (slot == 0) {
+        if (pub.f) pub.hbase[16] = *pub.f;
+        if (pub.dmin) pub.hbase[17] = *pub.dmin;
+        if (pub.flag) *reinterpret_cast<int*>(pub.hbase + 8) = *pub.flag;
+    }
+}
+
+// NA x NB inner products in one pass; A_IN_B: a[i] is b[i] (read once).  Launched with ONE block (short vectors: the
+// reference's own problem sizes) the block's result is the final one: it is written to `final_out` and published,
+// and the second stage is not launched.
 template <int NA, int NB, bool A_IN_B>
 __global__ void __launch_bounds__(RED_THREADS) cross_stage1(WbCrossArgs p, size_t n2,
-                                                            double* __restrict__ partial) {
+                                                            double* __restrict__ partial,
+                                                            double* __restrict__ final_out, WbPublish pub) {
     constexpr int NOUT = NA * NB + 1;
     double acc[NA][NB];
     double mx = 0.0;
@@ -62,13 +86,18 @@ __global__ void __launch_bounds__(RED_THREADS) cross_stage1(WbCrossArgs p, size_
         for (int w = 0; w < RED_THREADS / 32; w++) t = (q == NOUT - 1) ? fmax(t, sh[w][q]) : t + sh[w][q];
         // results in the fixed layout [na][WB_CROSS_NB] + max, whatever NB is
         const int slot = (q == NOUT - 1) ? WB_CROSS_NOUT - 1 : (q / NB) * WB_CROSS_NB + (q % NB);
-        partial[(size_t)slot * gridDim.x + blockIdx.x] = t;
+        if (final_out) {
+            final_out[slot] = t;
+            publish_result(pub, slot, t);
+        } else {
+            partial[(size_t)slot * gridDim.x + blockIdx.x] = t;
+        }
     }
 }
 
 // one CTA per output: sums (or maximises) the block partials of that output in a fixed order
 __global__ void __launch_bounds__(RED_THREADS) cross_stage2(const double* __restrict__ partial, int blocks,
-                                                            double* __restrict__ out) {
+                                                            double* __restrict__ out, WbPublish pub) {
     const int q = blockIdx.x;
     const bool is_max = q == WB_CROSS_NOUT - 1;
     const double* src = partial + (size_t)q * blocks;
@@ -86,6 +115,7 @@ __global__ void __launch_bounds__(RED_THREADS) cross_stage2(const double* __rest
         double r = 0.0;
         for (int w = 0; w < RED_THREADS / 32; w++) r = is_max ? fmax(r, sh[w]) : r + sh[w];
         out[q] = r;
+        publish_result(pub, q, r);
     }
 }
 
@@ -137,37 +167,56 @@ int wb_cross_launch(wb200_ctx* ctx, const WbCrossArgs& p, size_t n) {
     }
     const size_t n2 = n / 2;
     const size_t want = (n2 + RED_THREADS - 1) / RED_THREADS;
-    const int blocks = (int)(want < (size_t)RED_MAX_BLOCKS ? (want ? want : 1) : RED_MAX_BLOCKS);
+    // up to 16 elements per thread: one block, one launch (a 64-k-point, 4-band vector has 1024 elements)
+    const bool one_block = n2 <= (size_t)16 * RED_THREADS;
+    const int blocks = one_block ? 1 : (int)(want < (size_t)RED_MAX_BLOCKS ? want : RED_MAX_BLOCKS);
     if (!ctx->d_red) {
         const size_t bytes = sizeof(double) * WB_CROSS_NOUT * (RED_MAX_BLOCKS + 1);
         WB_CUDA(ctx, wb_dev_alloc(&ctx->d_red, bytes));
         WB_CUDA(ctx, cudaMemsetAsync(ctx->d_red, 0, bytes, ctx->stream));   // slots a small instantiation never writes
     }
     double* out = ctx->d_red + (size_t)WB_CROSS_NOUT * RED_MAX_BLOCKS;
+    // single slab: the results (and, for the optimiser's evaluations, f / min |N_nn| / the retraction flag) go to the
+    // page-locked scratch by zero-copy stores; k-sharded runs reduce them first and copy
+    WbPublish pub{nullptr, nullptr, nullptr, nullptr, ctx->h_pinned};
+    if (!ctx->allreduce) {
+        pub.hout = ctx->h_pinned + WB_PIN_CROSS;
+        if (ctx->publish_eval) {
+            pub.f = ctx->d_res + 5;
+            pub.dmin = ctx->d_min;
+            if (ctx->retract_pending) pub.flag = reinterpret_cast<const int*>(ctx->d_scal + 4);
+        }
+    }
+    double* fin = one_block ? out : nullptr;
     // the shapes the optimiser uses get exact-size instantiations (no predicates, fewer registers);
     // anything else is padded to 3 x 7 with repeats of the first vector (extra products are ignored)
     WbCrossArgs a = p;
     if (p.na == 1 && p.nb == 1 && !p.a_in_b) {
-        cross_stage1<1, 1, false><<<blocks, RED_THREADS, 0, ctx->stream>>>(a, n2, ctx->d_red);
+        cross_stage1<1, 1, false><<<blocks, RED_THREADS, 0, ctx->stream>>>(a, n2, ctx->d_red, fin, pub);
     } else if (p.na == 1 && p.nb == 1) {
-        cross_stage1<1, 1, true><<<blocks, RED_THREADS, 0, ctx->stream>>>(a, n2, ctx->d_red);
+        cross_stage1<1, 1, true><<<blocks, RED_THREADS, 0, ctx->stream>>>(a, n2, ctx->d_red, fin, pub);
     } else if (p.na == 1 && p.nb == 3 && p.a_in_b) {
-        cross_stage1<1, 3, true><<<blocks, RED_THREADS, 0, ctx->stream>>>(a, n2, ctx->d_red);
+        cross_stage1<1, 3, true><<<blocks, RED_THREADS, 0, ctx->stream>>>(a, n2, ctx->d_red, fin, pub);
     } else if (p.na == 3 && p.nb == 7 && p.a_in_b) {
-        cross_stage1<3, 7, true><<<blocks, RED_THREADS, 0, ctx->stream>>>(a, n2, ctx->d_red);
+        cross_stage1<3, 7, true><<<blocks, RED_THREADS, 0, ctx->stream>>>(a, n2, ctx->d_red, fin, pub);
     } else {
-        for (int i = p.na; i < WB_CROSS_NA; i++) a.a[i] = p.a[0];
+        for (int i = p.na; i < WB_CROSS_NA; i++) a.a[i] = p.b[0];
         for (int j = p.nb; j < WB_CROSS_NB; j++) a.b[j] = p.b[0];
         if (p.a_in_b) {
             // the prefix property is lost by the padding unless a is read separately
             for (int i = 0; i < p.na; i++) a.a[i] = p.b[i];
             for (int i = p.na; i < WB_CROSS_NA; i++) a.a[i] = p.b[0];
+        } else {
+            for (int i = p.na; i < WB_CROSS_NA; i++) a.a[i] = p.a[0];
         }
-        cross_stage1<WB_CROSS_NA, WB_CROSS_NB, false><<<blocks, RED_THREADS, 0, ctx->stream>>>(a, n2, ctx->d_red);
+        cross_stage1<WB_CROSS_NA, WB_CROSS_NB, false><<<blocks, RED_THREADS, 0, ctx->stream>>>(a, n2, ctx->d_red, fin, pub);
     }
     WB_LAUNCH_CHECK(ctx);
-    cross_stage2<<<WB_CROSS_NOUT, RED_THREADS, 0, ctx->stream>>>(ctx->d_red, blocks, out);
-    WB_LAUNCH_CHECK(ctx);
+    if (!one_block) {
+        cross_stage2<<<WB_CROSS_NOUT, RED_THREADS, 0, ctx->stream>>>(ctx->d_red, blocks, out, pub);
+        WB_LAUNCH_CHECK(ctx);
+    }
+    if (pub.hout) return WB200_OK;
     if (ctx->allreduce) {   // k-sharded optimiser: the vectors are slab-local, the scalars global
         if (wb_allreduce_is_builtin(ctx)) {   // sums and the max in one peer-memory launch
             WB_TRY(wb_peer_allreduce(ctx, out, WB_CROSS_NOUT - 1, 0, 1, 1));
