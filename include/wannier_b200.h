@@ -46,6 +46,8 @@ enum wb200_status {
 #define WB200_FLAG_DEFAULT 0u
 #define WB200_FLAG_NO_TENSOR 1u   /* force the CUDA-core FP64 rotation kernel even where DMMA applies */
 #define WB200_FLAG_FORCE_TENSOR 2u /* fail instead of falling back when the DMMA kernel cannot be used */
+#define WB200_FLAG_NO_FUSED_TRIAL 4u /* optimiser drivers: never use the one-launch trial-point kernel for tiny shapes
+                                        (n_bands <= 16, tiny.cu); the general kernels run instead (tests compare the two) */
 
 /* ---- context --------------------------------------------------------------------------------
  * Replaces `Cache(model)` (src/spread.jl:139-162) + the stencil fields read by the hot loops

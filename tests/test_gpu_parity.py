@@ -285,6 +285,55 @@ def test_disentangle_driver(w, silicon):
     assert np.abs(w2[silicon["frozen"]] - 1).max() < 1e-10
 
 
+@pytest.mark.parametrize("lat,grid,nb,nw,nfroz", [
+    ("fcc", (4, 4, 4), 4, 4, 0),       # the Si2_valence shape of benchmark/bench_maxloc.jl
+    ("bcc", (3, 3, 3), 16, 16, 0),     # largest square shape the fused kernel takes, 12 neighbours
+    ("cubic", (3, 2, 2), 7, 7, 0),     # odd sizes
+    ("fcc", (4, 4, 4), 12, 8, 4),      # the Si2 shape of benchmark/bench_disentangle.jl: (X, Y) chain, frozen bands
+    ("tetragonal", (5, 5, 1), 16, 5, 3),   # self-neighbours with G != 0, few Wannier functions
+    ("cubic", (2, 2, 2), 9, 9, 9),     # every band frozen at every k (the n_froz == n_wann branch, disentangle.jl:390)
+])
+def test_tiny_trial_kernel_matches_general_path(w, lat, grid, nb, nw, nfroz):
+    """tiny.cu (one cooperative launch per trial point, n_bands <= 16) against the chain of general kernels
+    (WB200_FLAG_NO_FUSED_TRIAL): the same L-BFGS / HagerZhang run must take the same iterations and evaluations and
+    arrive at the same point; with and without the centre penalty; each also checked against the oracle's spread."""
+    st, M, U = w.synthetic.make_model_arrays(lat, grid, nb, nw)
+    nk = len(U)
+    rng = np.random.default_rng(11)
+    r0 = rng.standard_normal((nw, 3))
+    for penalty in (None, (r0, 0.3)):
+        out = []
+        for flags in (w.lib.FLAG_DEFAULT, w.lib.FLAG_NO_FUSED_TRIAL):
+            ctx = make_ctx(w, st, M, nw, flags=flags)
+            if penalty:
+                ctx.set_penalty(penalty[0], penalty[1])
+            if nfroz:
+                frozen = w.synthetic.make_frozen(nk, nb, nfroz)
+                ctx.set_frozen(frozen)
+                X, Y = so.U_to_X_Y(U, frozen)
+                x = np.ascontiguousarray(so.X_Y_to_XY(X, Y))
+                f, it, nfg = ctx.disentangle(x, 1e-7, 1e-5, 6, 3)
+                Xd, Yd = so.XY_to_X_Y(x, nb, nw)
+                Ud = so.X_Y_to_U(Xd, Yd)
+                assert np.abs((np.abs(Ud) ** 2).sum(axis=2)[frozen] - 1).max() < 1e-10
+            else:
+                x = w.api.to_abi_U(U).copy()
+                f, it, nfg = ctx.max_localize(x, 1e-7, 1e-5, 6, 3)
+                Ud = w.api.from_abi_U(x)
+            launches = ctx.launch_count
+            ctx.close()
+            sp = so.omega(M, st["kpb_k"], st["bvec"], st["wb"], Ud)
+            fo = sp["Omega"] + (penalty[1] * ((sp["r"] - penalty[0]) ** 2).sum() if penalty else 0.0)
+            assert abs(fo - f) < 1e-9 * max(1.0, abs(f))
+            assert np.abs(np.conj(Ud.transpose(0, 2, 1)) @ Ud - np.eye(nw)).max() < 1e-11
+            out.append((f, it, nfg, x, launches))
+        (f1, it1, n1, x1, l1), (f2, it2, n2, x2, l2) = out
+        assert (it1, n1) == (it2, n2)
+        assert abs(f1 - f2) < 1e-9 * max(1.0, abs(f2))
+        assert np.abs(x1 - x2).max() < 1e-7
+        assert l1 < l2 / 2          # the fused path really ran: one launch per trial point instead of ~13
+
+
 # ---------------------------------------------------------------------------------------------
 # synthetic shapes: both rotation kernels against the oracle, padding and edge cases
 # ---------------------------------------------------------------------------------------------

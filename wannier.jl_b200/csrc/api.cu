@@ -50,11 +50,13 @@ extern "C" void wb200_destroy(wb200_ctx* ctx) {
                     (void*)ctx->d_peerU, ctx->d_need_owner, ctx->d_need, ctx->d_kpb, ctx->d_kself, ctx->d_bvec, ctx->d_wb, ctx->d_M, ctx->d_r0,
                     ctx->d_frozen, ctx->d_nfrozen, ctx->d_U, ctx->d_G, ctx->d_MU, ctx->d_N,
                     ctx->d_dN, ctx->d_fro, ctx->d_part, ctx->d_pmin, ctx->d_sums, ctx->d_res,
-                    ctx->d_min, ctx->d_scal, ctx->d_red, ctx->d_zpart, ctx->d_tmp1, ctx->d_tmp2, ctx->d_XY, ctx->d_GXY};
+                    ctx->d_min, ctx->d_scal, ctx->d_red, ctx->d_zpart, ctx->d_tmp1, ctx->d_tmp2, ctx->d_XY, ctx->d_GXY,
+                    ctx->d_tiny};
     for (void* p : ptrs)
         if (p) wb_dev_free_drained(p);
     tr.mark("buffers");
     for (auto& g : ctx->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+    for (auto& g : ctx->tgraphs) if (g.exec) cudaGraphExecDestroy(g.exec);
     for (auto& v : ctx->prof_events)
         for (auto& pr : v) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     tr.mark("graphs, events");
@@ -182,6 +184,7 @@ extern "C" int wb200_create(wb200_ctx** out, int device, int nb, int nw, int nk_
     ctx->wsum = 0.0;
     for (int b = 0; b < nn; b++) ctx->wsum += bweights[b];
 
+    ctx->tiny_ok = (!(flags & WB200_FLAG_NO_FUSED_TRIAL) && wb_tiny_shape(nb, nw, nk_total, nk, nn)) ? 1 : 0;
     if (!(flags & WB200_FLAG_NO_TENSOR)) {
         int s = wb_dmma_plan_create(ctx, M);
         if (s != WB200_OK) CREATE_FAIL(s, "wb200_create: tensor plan: " + ctx->err);

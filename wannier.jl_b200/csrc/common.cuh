@@ -188,6 +188,18 @@ struct wb200_ctx {
         cudaGraphExec_t exec = nullptr; long long nlaunch = 0; unsigned long long stamp = 0; int seen = 0;
     };
     EvalGraph graphs[6];
+    // the optimiser's whole trial point (step, retraction, evaluation, projection, inner product) for small problems
+    struct TrialGraph {
+        const void *x = nullptr, *s = nullptr, *xn = nullptr, *gn = nullptr;
+        int mode = 0, has_penalty = 0; double lambda = 0.0; const void* frozen = nullptr;
+        cudaGraphExec_t exec = nullptr; long long nlaunch = 0; unsigned long long stamp = 0; int seen = 0;
+    };
+    TrialGraph tgraphs[4];
+    // tiny.cu: the whole trial point in one cooperative launch (n_bands <= 16, one CTA per k-point)
+    int tiny_ok = 0;           // shape served (decided at creation: the plain overlaps d_M are kept then)
+    int tiny_blocks = 0;       // co-resident CTAs of the fused kernel on this device (0: not queried yet)
+    double* d_tiny = nullptr;  // [nk] per-k inner products, then the retraction flag word
+    int tiny_epoch = 0;
     unsigned long long graph_clock = 0;
     int use_graphs = 1;        // WB200_GRAPH=0 disables
     unsigned zd_attr_mask = 0; // zgemm_dmma.cu: shared-memory attribute set for these instantiations
@@ -306,6 +318,11 @@ bool wb_retract_pending_failed(wb200_ctx* ctx);
 int wb_project_small(wb200_ctx* ctx, const cplx* dX, cplx* dG, int nrow, int ncol, int ld, long long stride,
                      int count);
 
+// ---- tiny.cu ----
+bool wb_tiny_shape(int nb, int nw, int nk_total, int nk, int nn);
+bool wb_tiny_usable(wb200_ctx* ctx, int mode);
+int wb_tiny_trial(wb200_ctx* ctx, int mode, const cplx* x, const cplx* s, double alpha, cplx* xn, cplx* gn);
+
 // ---- vecops.cu ----
 #define WB_CROSS_NA 3
 #define WB_CROSS_NB 7
@@ -322,6 +339,8 @@ struct WbLinArgs {
     double c[WB_CROSS_NB];
     int nv;
     double beta;
+    const double* cdev;   // optional: c[cdev_idx] is read from device memory (a captured graph's step length)
+    int cdev_idx;
 };
 int wb_cross_launch(wb200_ctx* ctx, const WbCrossArgs& p, size_t n);   // results in h_pinned after a sync
 int wb_lincomb(wb200_ctx* ctx, const WbLinArgs& p, double* out, size_t n);   // out = beta out + sum c_j v_j

@@ -39,7 +39,7 @@ namespace {
 // WB200_TRACE: wall-clock share of each phase of the driver (the stream is drained at the end of every scope,
 // so this mode is for attribution only, not for timing the driver)
 struct Trace {
-    bool on = getenv("WB200_TRACE") != nullptr;
+    bool on = getenv("WB200_TRACE") != nullptr && strcmp(getenv("WB200_TRACE"), "coarse") != 0;
     double t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long n[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     static double now() {
@@ -52,6 +52,18 @@ struct Trace {
                                        "direction (lincomb)", "project s", "trial point (lincomb)", "secant + Gram refresh"};
         for (int i = 0; i < 8; i++)
             if (n[i]) fprintf(stderr, "[wb200] %-34s %6ld calls %9.3f ms total %8.3f ms each\n", names[i], n[i], 1e3 * t[i], 1e3 * t[i] / n[i]);
+    }
+};
+// WB200_TRACE=coarse: host wall clock of the three parts of an iteration as they are (no added waits)
+struct Coarse {
+    bool on = getenv("WB200_TRACE") && !strcmp(getenv("WB200_TRACE"), "coarse");
+    double t[4] = {0, 0, 0, 0}; long n[4] = {0, 0, 0, 0};
+    void add(int i, double t0) { if (on) { t[i] += Trace::now() - t0; n[i]++; } }
+    void report() const {
+        if (!on) return;
+        static const char* names[4] = {"direction + project + dphi0 (1 wait)", "trial point (1 wait)", "secant + Gram refresh (1 wait)", "whole run"};
+        for (int i = 0; i < 4; i++)
+            if (n[i]) fprintf(stderr, "[wb200] %-40s %6ld x %9.3f us\n", names[i], n[i], 1e6 * t[i] / n[i]);
     }
 };
 struct TraceScope {
@@ -271,8 +283,8 @@ struct Problem {
         return wb_project_xy(ctx, x, g);
     }
     // launches f and the PROJECTED gradient at x, and (optionally) <g, d> in the same submission;
-    // one synchronisation returns f, min |N_nn| and the inner product
-    int fg(const cplx* x, double* f, cplx* g, const double* d, double* gd) {
+    // one synchronisation (fg_finish) returns f, min |N_nn| and the inner product
+    int fg_enqueue(const cplx* x, cplx* g, const double* d) {
         n_fg++;
         {
         TraceScope ts_(trace, 1, ctx->stream);
@@ -315,6 +327,9 @@ struct Problem {
             ctx->publish_eval = 0;
             WB_TRY(st_);
         }
+        return WB200_OK;
+    }
+    int fg_finish(double* f, const double* d, double* gd) {
         WB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         *f = ctx->h_pinned[16];
         if (d) *gd = ctx->h_pinned[WB_PIN_CROSS];
@@ -327,6 +342,109 @@ struct Problem {
             return WB200_ERR_SINGULAR;
         }
         return WB200_OK;
+    }
+    int fg(const cplx* x, double* f, cplx* g, const double* d, double* gd) {
+        WB_TRY(fg_enqueue(x, g, d));
+        return fg_finish(f, d, gd);
+    }
+
+    // ---- one trial point of the line search: xn = retract(x + a s), gn = the projected gradient there,
+    //      phi = f(xn), dphi = <gn, s> ----
+    // Small problems (the reference's own benchmark sizes) are pure launch latency: ~12 dependent kernels of a few
+    // microseconds each.  On a single slab with the fused small-shape retraction the whole chain — step length
+    // included, which a 8-byte copy node brings from page-locked memory — is captured ONCE per (x, s, xn, gn)
+    // buffer combination into a CUDA graph and replayed: one submission and one wait per trial point.
+    bool trial_graphs_usable() const {
+        return ctx->use_graphs && !trace.on && !ctx->profiling && !ctx->allreduce && ctx->retract_deferred && mode != 3 &&
+               ctx->stream != nullptr && !gram.S && wb_small_applicable(ctx->nb, ctx->nw);
+    }
+    int trial_enqueue(const double* x, const double* s, double* xn, double* gn, double a, bool alpha_from_device) {
+        WbLinArgs l{};
+        l.v[0] = x; l.c[0] = 1.0; l.v[1] = s; l.c[1] = a; l.nv = 2;
+        if (alpha_from_device) {
+            WB_CUDA(ctx, cudaMemcpyAsync(ctx->d_scal + 16, ctx->h_pinned + 20, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+            l.cdev = ctx->d_scal + 16; l.cdev_idx = 1;
+        }
+        {
+            TraceScope ts_(trace, 6, ctx->stream);
+            WB_TRY(wb_lincomb(ctx, l, xn, n));
+        }
+        {
+            TraceScope ts_(trace, 0, ctx->stream);
+            int st = retract((cplx*)xn, true, a);
+            if (st == WB200_ERR_NOCONV) ctx->poison_next = 1;   // this trial point is rejected on every rank
+            else WB_TRY(st);
+        }
+        return fg_enqueue((const cplx*)xn, (cplx*)gn, s);
+    }
+    // tiny problems: the whole trial point is one cooperative launch (tiny.cu)
+    bool tiny_usable() { return !trace.on && mode != 3 && wb_tiny_usable(ctx, mode); }
+    int trial(const double* x, const double* s, double* xn, double* gn, double a, double* phi, double* dphi) {
+        if (tiny_usable()) {
+            n_fg++;
+            WB_TRY(wb_tiny_trial(ctx, mode, (const cplx*)x, (const cplx*)s, a, (cplx*)xn, (cplx*)gn));
+            const int st_ = fg_finish(phi, s, dphi);
+#ifdef WB_TINY_TIMING
+            fprintf(stderr, "[tiny] a=%g ns:", a);
+            for (int i = 0; i < 7; i++) fprintf(stderr, " %6.0f", ctx->h_pinned[48 + i]);
+            fprintf(stderr, "\n");
+#endif
+            return st_;
+        }
+        if (!trial_graphs_usable()) {
+            WB_TRY(trial_enqueue(x, s, xn, gn, a, false));
+            return fg_finish(phi, s, dphi);
+        }
+        wb200_ctx::TrialGraph* slot = nullptr;
+        for (auto& g : ctx->tgraphs)
+            if (g.seen && g.x == x && g.s == s && g.xn == xn && g.gn == gn && g.mode == mode && g.has_penalty == ctx->has_penalty &&
+                g.lambda == ctx->lambda && g.frozen == ctx->d_frozen) { slot = &g; break; }
+        ctx->h_pinned[20] = a;
+        if (slot && slot->exec) {
+            n_fg++;
+            ctx->retract_pending = 1;           // the graph contains a deferred retraction; its flag is published
+            WB_CUDA(ctx, cudaGraphLaunch(slot->exec, ctx->stream));
+            ctx->launches += slot->nlaunch;
+            slot->stamp = ++ctx->graph_clock;
+            return fg_finish(phi, s, dphi);
+        }
+        if (!slot) {   // first sighting: run plainly (lazy allocations, function attributes), remember the key
+            slot = &ctx->tgraphs[0];
+            for (auto& g : ctx->tgraphs) if (g.stamp < slot->stamp) slot = &g;
+            if (slot->exec) { cudaGraphExecDestroy(slot->exec); slot->exec = nullptr; }
+            *slot = wb200_ctx::TrialGraph{};
+            slot->x = x; slot->s = s; slot->xn = xn; slot->gn = gn; slot->mode = mode; slot->has_penalty = ctx->has_penalty;
+            slot->lambda = ctx->lambda; slot->frozen = ctx->d_frozen; slot->seen = 1; slot->stamp = ++ctx->graph_clock;
+            WB_TRY(trial_enqueue(x, s, xn, gn, a, true));
+            return fg_finish(phi, s, dphi);
+        }
+        // second sighting: capture, instantiate, launch
+        const int saved_graphs = ctx->use_graphs;
+        const int saved_nfg = n_fg;
+        const long long l0 = ctx->launches;
+        ctx->use_graphs = 0;                    // the evaluation inside is captured as plain launches
+        cudaGraph_t graph = nullptr;
+        cudaError_t ce = cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed);
+        int st = WB200_OK;
+        if (ce == cudaSuccess) {
+            st = trial_enqueue(x, s, xn, gn, a, true);
+            ce = cudaStreamEndCapture(ctx->stream, &graph);
+        }
+        ctx->use_graphs = saved_graphs;
+        n_fg = saved_nfg;
+        ctx->retract_pending = 0;
+        if (ce == cudaSuccess && st == WB200_OK && graph &&
+            cudaGraphInstantiate(&slot->exec, graph, 0) == cudaSuccess) {
+            slot->nlaunch = ctx->launches - l0;
+            ctx->launches = l0;
+        } else {
+            slot->exec = nullptr;
+            cudaGetLastError();
+            ctx->use_graphs = 0;                // graphs are not usable here: plain launches from now on
+        }
+        if (graph) cudaGraphDestroy(graph);
+        if (st != WB200_OK) return st;
+        return trial(x, s, xn, gn, a, phi, dphi);   // replays the new graph (or runs plainly if it could not be built)
     }
 };
 
@@ -348,6 +466,8 @@ static int lbfgs_run(wb200_ctx* ctx, int mode, const WbCustomProblem* custom, cp
                      int max_iter, int history, double* f_final, int* iters_out, int* n_fg_out) {
     Problem P{ctx, mode, 0};
     P.custom = custom;
+    Coarse coarse;
+    const double t_run0 = Trace::now();
     // single slab: the convergence flag of a small-shape retraction is read after the evaluation's wait (one host round
     // trip per trial point); k-sharded runs keep the immediate check, every rank must poison the same evaluation
     struct Deferred {
@@ -410,14 +530,20 @@ static int lbfgs_run(wb200_ctx* ctx, int mode, const WbCustomProblem* custom, cp
     };
 
     // ---- initial_state: retract!, value_gradient!!, project_tangent! ----
-    {
-        TraceScope ts_(P.trace, 0, ctx->stream);
-        int st = P.retract(dx);
-        if (st == WB200_ERR_NOCONV && ctx->allreduce) ctx->poison_next = 1;   // peers must see the failure too
-        else WB_TRY(st);
-    }
     double f = 0.0;
-    WB_TRY(P.fg(dx, &f, (cplx*)g, nullptr, nullptr));
+    if (P.tiny_usable()) {   // retraction, evaluation and projection in one launch
+        P.n_fg++;
+        WB_TRY(wb_tiny_trial(ctx, mode, dx, nullptr, 0.0, dx, (cplx*)g));
+        WB_TRY(P.fg_finish(&f, nullptr, nullptr));
+    } else {
+        {
+            TraceScope ts_(P.trace, 0, ctx->stream);
+            int st = P.retract(dx);
+            if (st == WB200_ERR_NOCONV && ctx->allreduce) ctx->poison_next = 1;   // peers must see the failure too
+            else WB_TRY(st);
+        }
+        WB_TRY(P.fg(dx, &f, (cplx*)g, nullptr, nullptr));
+    }
     if (!std::isfinite(f)) {
         ctx->err = "initial point: spread is not finite (retraction failed or singular overlaps)";
         return WB200_ERR_NOCONV;
@@ -429,6 +555,7 @@ static int lbfgs_run(wb200_ctx* ctx, int mode, const WbCustomProblem* custom, cp
     bool hist_reset = false;
     while (!converged && it < max_iter) {
         it++;
+        const double t_dir0 = Trace::now();
         // ---- update_state!: two-loop recursion on the coefficients of q = sum_id c[id] v_id ----
         std::vector<double> c(nid, 0.0);
         c[0] = 1.0;
@@ -492,24 +619,15 @@ static int lbfgs_run(wb200_ctx* ctx, int mode, const WbCustomProblem* custom, cp
             hist_reset = true;
         }
         WB_TRY(P.prepare_direction((const cplx*)s));
+        coarse.add(0, t_dir0);
         const double f_prev = f;
         double last_alpha = -1.0, last_f = 0.0;
         HagerZhang hz;
         hz.phidphi = [&](double a, double& phi, double& dphi) -> int {
-            WbLinArgs l{};
-            l.v[0] = x; l.c[0] = 1.0; l.v[1] = s; l.c[1] = a; l.nv = 2;
-            {
-                TraceScope ts_(P.trace, 6, ctx->stream);
-                WB_TRY(wb_lincomb(ctx, l, xn, n));
-            }
-            {
-                TraceScope ts_(P.trace, 0, ctx->stream);
-                int st = P.retract((cplx*)xn, true, a);
-                if (st == WB200_ERR_NOCONV) ctx->poison_next = 1;   // this trial point is rejected on every rank
-                else WB_TRY(st);
-            }
             double fv = 0.0, dv = 0.0;
-            WB_TRY(P.fg((cplx*)xn, &fv, (cplx*)gn, s, &dv));
+            const double t_tr0 = Trace::now();
+            WB_TRY(P.trial(x, s, xn, gn, a, &fv, &dv));
+            coarse.add(1, t_tr0);
             phi = fv; dphi = dv;
             last_alpha = a; last_f = fv;
             return WB200_OK;
@@ -541,6 +659,7 @@ static int lbfgs_run(wb200_ctx* ctx, int mode, const WbCustomProblem* custom, cp
         if (free_slots.empty()) { sl = slots.front(); slots.pop_front(); }
         else { sl = free_slots.back(); free_slots.pop_back(); }
         TraceScope ts_secant(P.trace, 7, ctx->stream);
+        const double t_sec0 = Trace::now();
         WB_TRY(wb_secant(ctx, alpha, s, gn, g, DX(sl), DG(sl), n));
         std::swap(x, xn);   // x <- accepted point, g <- its projected gradient (the old ones become the trial buffers)
         std::swap(g, gn);
@@ -552,6 +671,7 @@ static int lbfgs_run(wb200_ctx* ctx, int mode, const WbCustomProblem* custom, cp
             for (size_t i = 0; i + 1 < slots.size(); i++) ids.push_back(idG(slots[i]));
             WB_TRY(refresh(ids, 3, &gmax));
         }
+        coarse.add(2, t_sec0);
         const double sy = GM[(size_t)idX(sl) * nid + idG(sl)];
         if (sy == 0.0 || !std::isfinite(1.0 / sy)) {   // isinf(rho): pseudo_iteration = 0, history dropped
             while (!slots.empty()) { free_slots.push_back(slots.front()); slots.pop_front(); }
@@ -567,6 +687,8 @@ static int lbfgs_run(wb200_ctx* ctx, int mode, const WbCustomProblem* custom, cp
         WB_CUDA(ctx, cudaMemcpyAsync(dx, x, sizeof(double) * n, cudaMemcpyDeviceToDevice, ctx->stream));
     WB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     P.trace.report();
+    coarse.add(3, t_run0);
+    coarse.report();
     if (f_final) *f_final = f;
     if (iters_out) *iters_out = it;
     if (n_fg_out) *n_fg_out = P.n_fg;

@@ -894,7 +894,8 @@ int wb_dmma_plan_create(wb200_ctx* ctx, const double* /*hM*/) {
     }
     // d_M is released when the tiling kernels have run: enqueue nothing after them that reads it, and let the
     // end-of-create wait cover the release (the block goes back to the pool only then: see wb200_create)
-    ctx->release_M_after_create = 1;
+    // (tiny shapes keep it: the fused trial-point kernel of tiny.cu reads the plain layout)
+    ctx->release_M_after_create = ctx->tiny_ok ? 0 : 1;
     return WB200_OK;
 }
 

@@ -120,6 +120,7 @@ __global__ void __launch_bounds__(RED_THREADS) cross_stage2(const double* __rest
 }
 
 __global__ void __launch_bounds__(256) lincomb_kernel(WbLinArgs p, double2* out, size_t n2) {
+    if (p.cdev) p.c[p.cdev_idx] = *p.cdev;
     for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < n2;
          e += (size_t)gridDim.x * blockDim.x) {
         double2 r = make_double2(0.0, 0.0);

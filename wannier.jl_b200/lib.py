@@ -43,6 +43,7 @@ SYMBOLS = [
 FLAG_DEFAULT = 0
 FLAG_NO_TENSOR = 1
 FLAG_FORCE_TENSOR = 2
+FLAG_NO_FUSED_TRIAL = 4
 
 
 class WB200Error(RuntimeError):
