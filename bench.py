@@ -219,6 +219,8 @@ def main():
     ap.add_argument("--config", default="cfg4_nw128")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-reference-suite", action="store_true",
+                    help="skip the extra `reference_suite` key (the reference's own small benchmarks, one-shot calls)")
     ap.add_argument("--maxloc-iters", type=int, default=20,
                     help="also time the device max_localize driver for this many iterations (0: skip); extra key "
                          "`max_localize` in the JSON line, outside the timed region of `value`")
@@ -549,6 +551,15 @@ def main():
     if not args.no_cpu_baseline and world == 1:
         cb, _, _ = cpu_port_figure(w, st, nb, nw, 3, 1, dev, seconds_budget=25.0)
         line["cpu_baseline"] = cb
+    if world == 1 and not args.no_reference_suite:
+        # the reference's OWN benchmark suite (benchmark/bench_*.jl on Si2 / Si2_valence) as one-shot public calls,
+        # next to the CPU port on one thread; a few seconds, outside every timed region above
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import bench_reference_suite
+            line["reference_suite"] = bench_reference_suite.run(cpu=not args.no_cpu_baseline, min_s=0.15)
+        except Exception as e:          # never lose the headline line over the side table
+            line["reference_suite"] = {"error": repr(e)}
     print(json.dumps(line), file=json_out, flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -46,6 +46,8 @@ enum wb200_status {
 #define WB200_FLAG_DEFAULT 0u
 #define WB200_FLAG_NO_TENSOR 1u   /* force the CUDA-core FP64 rotation kernel even where DMMA applies */
 #define WB200_FLAG_FORCE_TENSOR 2u /* fail instead of falling back when the DMMA kernel cannot be used */
+#define WB200_FLAG_M_ROW_MAJOR 8u  /* wb200_create: every M_kb is given row-major (C order, M[k][b][m][l] — what numpy
+                                      holds); it is transposed on the device instead of by the caller */
 #define WB200_FLAG_NO_FUSED_TRIAL 4u /* optimiser drivers: never use the one-launch trial-point kernel for tiny shapes
                                         (n_bands <= 16, tiny.cu); the general kernels run instead (tests compare the two) */
 

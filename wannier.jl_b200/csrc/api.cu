@@ -84,6 +84,13 @@ extern "C" void wb200_destroy(wb200_ctx* ctx) {
             CREATE_FAIL(WB200_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
     } while (0)
 
+// out[pair] = in[pair]^T (nb x nb complex): WB200_FLAG_M_ROW_MAJOR
+__global__ void __launch_bounds__(256) transpose_overlaps_kernel(int nb, const cplx* __restrict__ in, cplx* __restrict__ out) {
+    const cplx* a = in + (long long)blockIdx.x * nb * nb;
+    cplx* b = out + (long long)blockIdx.x * nb * nb;
+    for (int e = threadIdx.x; e < nb * nb; e += blockDim.x) b[e] = a[(e % nb) * nb + e / nb];
+}
+
 extern "C" int wb200_create(wb200_ctx** out, int device, int nb, int nw, int nk_total, int k_begin,
                             int nk, int nn, const int32_t* kpb_k, const double* bvec_cart,
                             const double* bweights, const double* M, unsigned flags) {
@@ -178,6 +185,15 @@ extern "C" int wb200_create(wb200_ctx** out, int device, int nb, int nw, int nk_
         if (on_device) CREATE_CUDA(cudaDeviceSynchronize());
     }
     CREATE_CUDA(cudaMemcpyAsync(ctx->d_M, M, sizeof(cplx) * pairs * nb * nb, cudaMemcpyDefault, cs));  // host or device
+    cplx* m_as_given = nullptr;
+    if (flags & WB200_FLAG_M_ROW_MAJOR) {   // C-order matrices: transpose here, not in the caller's interpreter
+        cplx* t = nullptr;
+        CREATE_CUDA(wb_dev_alloc(&t, sizeof(cplx) * pairs * nb * nb));
+        transpose_overlaps_kernel<<<(unsigned)pairs, 256, 0, cs>>>(nb, ctx->d_M, t);
+        ctx->launches++;
+        m_as_given = ctx->d_M;
+        ctx->d_M = t;
+    }
     tr.mark("uploads (enqueued)");
     ctx->h_wb.assign(bweights, bweights + nn);
     ctx->h_kpb.assign(kpb_k, kpb_k + pairs);
@@ -193,6 +209,7 @@ extern "C" int wb200_create(wb200_ctx** out, int device, int nb, int nw, int nk_
         CREATE_FAIL(WB200_ERR_ARG, "wb200_create: WB200_FLAG_FORCE_TENSOR but the DMMA rotation kernel does not support this shape");
     ctx->rotation_kernel = ctx->dmma ? 1 : 0;
     CREATE_CUDA(cudaStreamSynchronize(cs));   // the caller's arrays (and the host vectors above) are no longer read
+    if (m_as_given) wb_dev_free_drained(m_as_given);
     if (ctx->release_M_after_create) {        // the tensor path never reads the plain layout again
         wb_dev_free_drained(ctx->d_M);        // (only this stream ever touched it)
         ctx->d_M = nullptr;

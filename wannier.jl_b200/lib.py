@@ -44,6 +44,7 @@ FLAG_DEFAULT = 0
 FLAG_NO_TENSOR = 1
 FLAG_FORCE_TENSOR = 2
 FLAG_NO_FUSED_TRIAL = 4
+FLAG_M_ROW_MAJOR = 8
 
 
 class WB200Error(RuntimeError):
