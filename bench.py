@@ -553,12 +553,18 @@ def main():
         line["cpu_baseline"] = cb
     if world == 1 and not args.no_reference_suite:
         # the reference's OWN benchmark suite (benchmark/bench_*.jl on Si2 / Si2_valence) as one-shot public calls,
-        # next to the CPU port on one thread; a few seconds, outside every timed region above
+        # next to the CPU port on one thread; a few seconds, outside every timed region above, in a process of its
+        # own so that nothing that happens there can cost the headline line
+        import subprocess, tempfile
         try:
-            sys.path.insert(0, os.path.join(ROOT, "tools"))
-            import bench_reference_suite
-            line["reference_suite"] = bench_reference_suite.run(cpu=not args.no_cpu_baseline, min_s=0.15)
-        except Exception as e:          # never lose the headline line over the side table
+            with tempfile.TemporaryDirectory() as td:
+                dst = os.path.join(td, "suite.json")
+                cmd = [sys.executable, os.path.join(ROOT, "tools", "bench_reference_suite.py"), dst, "--quick"]
+                if args.no_cpu_baseline:
+                    cmd.append("--no-cpu")
+                subprocess.run(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=240, check=True)
+                line["reference_suite"] = json.load(open(dst))
+        except Exception as e:
             line["reference_suite"] = {"error": repr(e)}
     print(json.dumps(line), file=json_out, flush=True)
     if world > 1:

@@ -58,6 +58,15 @@ end
 pin!(A::Array) = (ccall((:wb200_host_register, LIB), Cint, (Ptr{Cvoid}, Csize_t), A, sizeof(A)); A)
 unpin!(A::Array) = (ccall((:wb200_host_unregister, LIB), Cint, (Ptr{Cvoid},), A); A)
 
+"""
+The one-shot calls (`omega(stencil, M, U)`, `omega_grad(...)`, `max_localize(model)`: a `Cache` per call in the
+reference, src/spread.jl:378, 497; a device context per call here) are cheap because the library keeps the device /
+page-locked blocks and streams of destroyed contexts.  `trim_pools()` hands them back to the driver (e.g. before
+CUDA.jl needs the memory); `pool_bytes(device)` reports what is kept.
+"""
+trim_pools() = ccall((:wb200_trim_pools, LIB), Cvoid, ())
+pool_bytes(device::Integer=0) = ccall((:wb200_pool_stats, LIB), Clonglong, (Cint, Ptr{Clonglong}, Ptr{Clonglong}), device, C_NULL, C_NULL)
+
 # ------------------------------------------------------------------------------------------------------
 # device contexts: replace `Cache(model)` (src/spread.jl:127-162)
 # ------------------------------------------------------------------------------------------------------

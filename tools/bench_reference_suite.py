@@ -9,7 +9,7 @@ reference's benchmark setting, benchmark/runbenchmarks.jl:5) as the baseline.
 Datasets: tests/golden/silicon_12to8.npz (= Si2: 12 bands -> 8 WFs, 4x4x4 k, 8 b, frozen window) and
 tests/golden/valence_silicon.npz (= Si2_valence: 4 WFs), both made from the reference's fixture files.
 
-    python tools/bench_reference_suite.py [out.json] [--no-cpu]"""
+    python tools/bench_reference_suite.py [out.json] [--no-cpu] [--quick]"""
 import json, os, sys, time
 import numpy as np
 
@@ -123,7 +123,7 @@ def run(cpu=True, min_s=0.25):
 
 
 if __name__ == "__main__":
-    out = run(cpu="--no-cpu" not in sys.argv)
+    out = run(cpu="--no-cpu" not in sys.argv, min_s=0.12 if "--quick" in sys.argv else 0.25)
     for k, v in out.items():
         print(k, json.dumps(v, default=float), flush=True)
     dst = next((a for a in sys.argv[1:] if not a.startswith("--")), os.path.join(ROOT, "gpurun_out", "ref_suite.json"))
