@@ -531,6 +531,50 @@ def test_error_behaviour(w, valence):
     ctx.close()
 
 
+def test_caching_allocator_and_one_shot_contexts(w, valence):
+    """mempool.cu: a context per call (what the reference's one-shot API does with its Cache, spread.jl:378, 497) must
+    not cost driver allocations the second time, must give the same answers from recycled blocks, and the kept blocks
+    must go back to the driver on request."""
+    import os
+    if os.environ.get("WB200_POOL") == "0":
+        pytest.skip("caching allocator disabled by WB200_POOL=0")
+    st = fixture_stencil(valence)
+    Uc = w.api.to_abi_U(valence["U"])
+    ref = None
+    w.lib.trim_pools()
+    assert w.lib.pool_stats(0)[0] == 0 and w.lib.pool_stats(-1)[0] == 0
+    for rep in range(4):
+        _, h0, m0 = w.lib.pool_stats(0)
+        ctx = make_ctx(w, st, valence["M"], 4)
+        G = np.empty_like(Uc)
+        f = ctx.fg(Uc, G=G)
+        out5 = ctx.spread(Uc)[0]
+        ctx.close()
+        kept, h1, m1 = w.lib.pool_stats(0)
+        assert kept > 0 and w.lib.pool_stats(-1)[0] > 0
+        if rep == 0:
+            ref = (f, G.copy(), np.array(out5))
+            assert m1 > m0                       # first context: everything from the driver
+        else:
+            assert m1 == m0 and h1 > h0          # later contexts: nothing from the driver
+            assert f == ref[0] and np.array_equal(G, ref[1]) and np.array_equal(np.array(out5), ref[2])   # bitwise
+    kept_before = w.lib.pool_stats(0)[0]
+    for rep in range(20):                        # no growth: the same blocks go round
+        make_ctx(w, st, valence["M"], 4).close()
+    assert w.lib.pool_stats(0)[0] == kept_before
+    w.lib.trim_pools()
+    assert w.lib.pool_stats(0)[0] == 0 and w.lib.pool_stats(-1)[0] == 0
+    ctx = make_ctx(w, st, valence["M"], 4)       # and the library still works from the driver again
+    assert ctx.fg(Uc) == ref[0]
+    ctx.close()
+    # numpy-order overlaps transposed on the device (WB200_FLAG_M_ROW_MAJOR) = the caller transposing them
+    nk, nn, nb, _ = valence["M"].shape
+    ctx = w.Context(nb, 4, nk, nn, st["kpb_k"], st["bvec"], st["wb"], np.ascontiguousarray(valence["M"]),
+                    flags=w.lib.FLAG_M_ROW_MAJOR)
+    assert ctx.fg(Uc) == ref[0]
+    ctx.close()
+
+
 def test_multi_wave_determinism_and_parity(w):
     """864 CTAs of the DMMA kernel (about 6 waves on 148 SMs): results must be bitwise identical
     from call to call and match the oracle.  Guards the shared-memory ring of the rotation kernel
