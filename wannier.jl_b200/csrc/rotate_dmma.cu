@@ -692,6 +692,10 @@ rotate_small_ring_kernel(int nb, int nw, int nn, long long pair0, long long pair
         return;
     }
     cplx uk[16];   // U_k values of this thread's 16 outputs
+#ifdef WB_TIMING
+    long long r_wait = 0, r_mma = 0, r_epi = 0;
+    const long long r_start = clock64();
+#endif
     long long p = my0 + q0(wp);
     long long kl = p / nn;
     int bi = (int)(p - kl * nn);
@@ -717,7 +721,14 @@ rotate_small_ring_kernel(int nb, int nw, int nn, long long pair0, long long pair
             if (!FULL && c >= nch_act) break;
             const int s = u % SR_SLOTS;
             const uint32_t full = bar_base + 16u * (wp * SR_SLOTS + s);
+#ifdef WB_TIMING
+            const long long tw0 = clock64();
+#endif
             mbar_wait(full, (uint32_t)(u / SR_SLOTS) & 1u);
+#ifdef WB_TIMING
+            const long long tw1 = clock64();
+            r_wait += tw1 - tw0;
+#endif
             const cplx* Ap = reinterpret_cast<const cplx*>(smem_raw + (size_t)(wp * SR_SLOTS + s) * SR_SLOT_BYTES) + lane;
             const cplx* Bp = Ap + (SR_A_BYTES + half * SR_B_BYTES) / 16;
 #pragma unroll
@@ -752,7 +763,13 @@ rotate_small_ring_kernel(int nb, int nw, int nn, long long pair0, long long pair
             __syncwarp();
             if (lane == 0) mbar_arrive(full + 8u);
             u++;
+#ifdef WB_TIMING
+            r_mma += clock64() - tw1;
+#endif
         }
+#ifdef WB_TIMING
+        const long long te0 = clock64();
+#endif
         // epilogue: MU, diag(U_k^H MU) (complete: the warp holds all rows), ||MU||_F^2 of this half.
         // (Deferring it into the next pair's k-steps, as rotate_dmma_kernel does, was measured slower
         // here: 0.246 vs 0.196 ms at nb = 32, 12^3 k — eight k-steps cannot hide eight slices.)
@@ -801,7 +818,16 @@ rotate_small_ring_kernel(int nb, int nw, int nn, long long pair0, long long pair
         if (NORM && lane == 0) frop[p * 2 + half] = f;
         fresh = ++bi == nn;
         if (fresh) { bi = 0; kl++; }
+#ifdef WB_TIMING
+        r_epi += clock64() - te0;
+#endif
     }
+#ifdef WB_TIMING
+    if (lane == 0 && wb_dbg) {
+        long long* dd = wb_dbg + ((long long)blockIdx.x * 8 + warp) * 8;
+        dd[0] = clock64() - r_start; dd[1] = r_wait; dd[2] = r_mma; dd[3] = r_epi; dd[4] = q0(wp + 1) - q0(wp);
+    }
+#endif
 }
 
 template <int WM, int WN, int KC, int STAGES>
