@@ -292,6 +292,7 @@ def test_disentangle_driver(w, silicon):
     ("fcc", (4, 4, 4), 12, 8, 4),      # the Si2 shape of benchmark/bench_disentangle.jl: (X, Y) chain, frozen bands
     ("tetragonal", (5, 5, 1), 16, 5, 3),   # self-neighbours with G != 0, few Wannier functions
     ("cubic", (2, 2, 2), 9, 9, 9),     # every band frozen at every k (the n_froz == n_wann branch, disentangle.jl:390)
+    ("cubic", (12, 12, 10), 8, 8, 0),  # 1 440 k-points
 ])
 def test_tiny_trial_kernel_matches_general_path(w, lat, grid, nb, nw, nfroz):
     """tiny.cu (one cooperative launch per trial point, n_bands <= 16) against the chain of general kernels
@@ -301,9 +302,14 @@ def test_tiny_trial_kernel_matches_general_path(w, lat, grid, nb, nw, nfroz):
     nk = len(U)
     rng = np.random.default_rng(11)
     r0 = rng.standard_normal((nw, 3))
+    import os
     for penalty in (None, (r0, 0.3)):
         out = []
-        for flags in (w.lib.FLAG_DEFAULT, w.lib.FLAG_NO_FUSED_TRIAL):
+        # fused kernel with one k-point per CTA, the general kernels, the fused kernel with (at least) three k-points per CTA
+        for flags, kper in ((w.lib.FLAG_DEFAULT, None), (w.lib.FLAG_NO_FUSED_TRIAL, None), (w.lib.FLAG_DEFAULT, "3")):
+            os.environ.pop("WB200_TINY_KPER", None)
+            if kper:
+                os.environ["WB200_TINY_KPER"] = kper
             ctx = make_ctx(w, st, M, nw, flags=flags)
             if penalty:
                 ctx.set_penalty(penalty[0], penalty[1])
@@ -322,16 +328,22 @@ def test_tiny_trial_kernel_matches_general_path(w, lat, grid, nb, nw, nfroz):
                 Ud = w.api.from_abi_U(x)
             launches = ctx.launch_count
             ctx.close()
+            os.environ.pop("WB200_TINY_KPER", None)
             sp = so.omega(M, st["kpb_k"], st["bvec"], st["wb"], Ud)
             fo = sp["Omega"] + (penalty[1] * ((sp["r"] - penalty[0]) ** 2).sum() if penalty else 0.0)
             assert abs(fo - f) < 1e-9 * max(1.0, abs(f))
             assert np.abs(np.conj(Ud.transpose(0, 2, 1)) @ Ud - np.eye(nw)).max() < 1e-11
             out.append((f, it, nfg, x, launches))
-        (f1, it1, n1, x1, l1), (f2, it2, n2, x2, l2) = out
-        assert (it1, n1) == (it2, n2)
+        (f1, it1, n1, x1, l1), (f2, it2, n2, x2, l2), (f3, it3, n3, x3, l3) = out
+        assert (it1, n1) == (it2, n2) == (it3, n3)
         assert abs(f1 - f2) < 1e-9 * max(1.0, abs(f2))
         assert np.abs(x1 - x2).max() < 1e-7
-        assert l1 < l2 / 2          # the fused path really ran: one launch per trial point instead of ~13
+        assert l1 < l2 / 2               # the fused path really ran: one launch per trial point instead of ~13
+        # one or several k-points per CTA: the same arithmetic in the same order (three slots of the 16 x 16, 12-neighbour
+        # shape do not fit into shared memory: that context falls back to the general kernels)
+        assert l3 in (l1, l2)
+        ref = (f1, x1) if l3 == l1 else (f2, x2)
+        assert f3 == ref[0] and np.array_equal(x3, ref[1])
 
 
 # ---------------------------------------------------------------------------------------------

@@ -197,7 +197,8 @@ struct wb200_ctx {
     TrialGraph tgraphs[4];
     // tiny.cu: the whole trial point in one cooperative launch (n_bands <= 16, one CTA per k-point)
     int tiny_ok = 0;           // shape served (decided at creation: the plain overlaps d_M are kept then)
-    int tiny_blocks = 0;       // co-resident CTAs of the fused kernel on this device (0: not queried yet)
+    int tiny_blocks = 0;       // grid of the fused kernel (0: not planned yet); the whole grid must be co-resident
+    int tiny_kper = 1;         // k-points per CTA
     double* d_tiny = nullptr;  // [nk] per-k inner products, then the retraction flag word
     int tiny_epoch = 0;
     unsigned long long graph_clock = 0;

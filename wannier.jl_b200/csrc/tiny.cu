@@ -1,13 +1,14 @@
 // tiny.cu — one trial point of the optimiser's line search in ONE cooperative launch, for the problem sizes the
 // reference's own benchmark suite runs (benchmark/bench_maxloc.jl: Si2_valence, 4 WFs, 64 k-points;
-// bench_disentangle.jl: Si2, 12 bands -> 8 WFs): n_bands <= 16 and as many k-points as CTAs fit on the device.
+// bench_disentangle.jl: Si2, 12 bands -> 8 WFs): n_bands <= 16 and as many k-points as fit into the shared memory of
+// a co-resident grid (a CTA owns one or several k-points: e.g. 8 WFs on a 12 x 12 x 12 grid).
 //
 // At those sizes one evaluation is ~0.3-2 MFLOP: the arithmetic of a whole trial point
 //     xn = retract(x + a s);  f, G = spread and gradient at xn;  gn = project(G, xn);  dphi = <gn, s>
 // (max_localize.jl:13-23 / disentangle.jl:586-614 behind Optim's retract! / project_tangent!, call sites
 // max_localize.jl:62-63, disentangle.jl:687-690) is a few microseconds, but as the chain of general kernels it is
 // 13 dependent launches of 3-28 us each (profiles/r4_summary.md: 72 us per trial point even as a CUDA graph).
-// Here CTA k owns k-point k for the whole trial point and keeps everything of it in shared memory — the factors
+// Here a CTA owns its k-points for the whole trial point and keeps everything of them in shared memory — the factors
 // (X_k, Y_k) or U_k, the nn rotated overlaps MU_kb, diag N_kb, the gradient — and the grid meets three times
 // (cooperative groups grid sync): after the retraction (neighbours read U_{k+b}), after the per-k partial sums (every
 // CTA then forms the centres r itself, in the same fixed order, so all agree bitwise), and before CTA 0 adds up the
@@ -34,6 +35,7 @@ namespace cg = cooperative_groups;
 
 struct TinyArgs {
     int mode, nb, nw, nk, nn;
+    int kper;                      // k-points per CTA (CTA c owns k = c, c + gridDim.x, ...)
     const int32_t* kpb;
     const double* bvec;
     const double* wb;
@@ -168,33 +170,39 @@ __device__ void tiny_project(const cplx* X, cplx* G, cplx* S, cplx* T, int nrow,
 
 __global__ void __launch_bounds__(WB_TINY_THREADS) tiny_trial_kernel(TinyArgs a) {
     cg::grid_group grid = cg::this_grid();
-    const int nb = a.nb, nw = a.nw, nn = a.nn, nk = a.nk;
-    const int k = blockIdx.x, tid = threadIdx.x;
+    const int nb = a.nb, nw = a.nw, nn = a.nn, nk = a.nk, kper = a.kper;
+    const int tid = threadIdx.x;
     const int mat = nb * nw, nxx = nw * nw;
     const int vlen = a.mode == 1 ? nxx + mat : mat;      // complex elements of the optimisation variable per k-point
     const int nsums = 4 * nw + 2;
 
+    // shared memory: `kper` slots of per-k state that lives through the whole trial point (the CTA owns the k-points
+    // blockIdx.x, blockIdx.x + gridDim.x, ...), then scratch that every slot re-uses
     extern __shared__ __align__(16) unsigned char tiny_smem[];
-    cplx* sU = reinterpret_cast<cplx*>(tiny_smem);   // [mat]   U_k
-    cplx* sX = sU + mat;                             // [nxx]   X_k (mode 1)
-    cplx* sY = sX + nxx;                             // [mat]   Y_k (mode 1)
-    cplx* sP = sY + mat;                             // [nxx]   scratch
+    const int state_c = 2 * mat + nxx + nn * mat + nn * nw;
+    cplx* st0 = reinterpret_cast<cplx*>(tiny_smem);
+    cplx* sP = st0 + (size_t)kper * state_c;         // [nxx]   scratch
     cplx* sT = sP + nxx;                             // [mat]   scratch
     cplx* sG = sT + mat;                             // [mat]   G_k
     cplx* sGX = sG + mat;                            // [nxx]
     cplx* sMk = sGX + nxx;                           // [nn][nb*nb] M_kb staging
     cplx* sUp = sMk + nn * nb * nb;                  // [nn][mat]   U_{k+b} staging (later: G_Y)
-    cplx* sMU = sUp + nn * mat;                      // [nn][mat]
-    cplx* sZ = sMU + nn * mat;                       // [nn][nw] diag N_kb, later the gradient coefficients
-    double* sphi = reinterpret_cast<double*>(sZ + nn * nw);   // [nn][nw]
-    double* sa2 = sphi + nn * nw;                    // [nn][nw]
-    double* ssum = sa2 + nn * nw;                    // [nsums]
+    double* dst0 = reinterpret_cast<double*>(sUp + nn * mat);
+    double* ssum = dst0 + (size_t)kper * 2 * nn * nw;   // [nsums]
     double* sfro = ssum + nsums;                     // [nn]
     double* red = sfro + nn;                         // [8]
     __shared__ int s_ok;
+#define SLOT_POINTERS(slot)                                                                   \
+    cplx* sU = st0 + (size_t)(slot) * state_c;            /* [mat]  U_k               */      \
+    cplx* sX = sU + mat;                                  /* [nxx]  X_k (mode 1)      */      \
+    cplx* sY = sX + nxx;                                  /* [mat]  Y_k (mode 1)      */      \
+    cplx* sMU = sY + mat;                                 /* [nn][mat]                */      \
+    cplx* sZ = sMU + nn * mat;                            /* [nn][nw] diag N_kb, later the gradient coefficients */ \
+    double* sphi = dst0 + (size_t)(slot) * 2 * nn * nw;   /* [nn][nw]                 */      \
+    double* sa2 = sphi + nn * nw;                         /* [nn][nw]                 */
 #ifdef WB_TINY_TIMING
     unsigned long long tt[8];
-#define TT(i) do { if (k == 0 && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt[i])); } while (0)
+#define TT(i) do { if (blockIdx.x == 0 && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt[i])); } while (0)
 #else
 #define TT(i)
 #endif
@@ -202,36 +210,42 @@ __global__ void __launch_bounds__(WB_TINY_THREADS) tiny_trial_kernel(TinyArgs a)
 
     // ---- phase 1: trial point and its retraction -------------------------------------------------------------
     const double alpha = a.s ? (a.alpha_dev ? *a.alpha_dev : a.alpha) : 0.0;
-    const cplx* xk = a.x + (long long)k * vlen;
-    const cplx* sk = a.s ? a.s + (long long)k * vlen : nullptr;
-    cplx* xnk = a.xn + (long long)k * vlen;
     bool ok = true;
-    if (a.mode == 1) {
-        for (int e = tid; e < vlen; e += WB_TINY_THREADS) {
-            cplx v = xk[e];
-            if (sk) { const cplx d = sk[e]; v.x = fma(alpha, d.x, v.x); v.y = fma(alpha, d.y, v.y); }
-            if (e < nxx) sX[e] = v; else sY[e - nxx] = v;
+    for (int slot = 0, k = blockIdx.x; slot < kper && k < nk; slot++, k += gridDim.x) {
+        cplx* sU = st0 + (size_t)slot * state_c;
+        cplx* sX = sU + mat;
+        cplx* sY = sX + nxx;
+        const cplx* xk = a.x + (long long)k * vlen;
+        const cplx* sk = a.s ? a.s + (long long)k * vlen : nullptr;
+        cplx* xnk = a.xn + (long long)k * vlen;
+        if (a.mode == 1) {
+            for (int e = tid; e < vlen; e += WB_TINY_THREADS) {
+                cplx v = xk[e];
+                if (sk) { const cplx d = sk[e]; v.x = fma(alpha, d.x, v.x); v.y = fma(alpha, d.y, v.y); }
+                if (e < nxx) sX[e] = v; else sY[e - nxx] = v;
+            }
+            __syncthreads();
+            ok = tiny_polar(sX, sP, sT, nw, nw, red) && ok;
+            ok = tiny_polar(sY, sP, sT, nb, nw, red) && ok;
+            for (int e = tid; e < vlen; e += WB_TINY_THREADS) xnk[e] = e < nxx ? sX[e] : sY[e - nxx];
+            for (int e = tid; e < mat; e += WB_TINY_THREADS) {   // U = Y X
+                const int m = e % nb, n = e / nb;
+                cplx acc = make_double2(0.0, 0.0);
+                for (int l = 0; l < nw; l++) cfma(acc, sY[l * nb + m], sX[n * nw + l]);
+                sU[e] = acc;
+                a.U[(long long)k * mat + e] = acc;
+            }
+        } else {
+            for (int e = tid; e < mat; e += WB_TINY_THREADS) {
+                cplx v = xk[e];
+                if (sk) { const cplx d = sk[e]; v.x = fma(alpha, d.x, v.x); v.y = fma(alpha, d.y, v.y); }
+                sU[e] = v;
+            }
+            __syncthreads();
+            ok = tiny_polar(sU, sP, sT, nb, nw, red) && ok;
+            for (int e = tid; e < mat; e += WB_TINY_THREADS) xnk[e] = sU[e];   // mode 0: a.U == a.xn
         }
         __syncthreads();
-        ok = tiny_polar(sX, sP, sT, nw, nw, red);
-        ok = tiny_polar(sY, sP, sT, nb, nw, red) && ok;
-        for (int e = tid; e < vlen; e += WB_TINY_THREADS) xnk[e] = e < nxx ? sX[e] : sY[e - nxx];
-        for (int e = tid; e < mat; e += WB_TINY_THREADS) {   // U = Y X
-            const int m = e % nb, n = e / nb;
-            cplx acc = make_double2(0.0, 0.0);
-            for (int l = 0; l < nw; l++) cfma(acc, sY[l * nb + m], sX[n * nw + l]);
-            sU[e] = acc;
-            a.U[(long long)k * mat + e] = acc;
-        }
-    } else {
-        for (int e = tid; e < mat; e += WB_TINY_THREADS) {
-            cplx v = xk[e];
-            if (sk) { const cplx d = sk[e]; v.x = fma(alpha, d.x, v.x); v.y = fma(alpha, d.y, v.y); }
-            sU[e] = v;
-        }
-        __syncthreads();
-        ok = tiny_polar(sU, sP, sT, nb, nw, red);
-        for (int e = tid; e < mat; e += WB_TINY_THREADS) xnk[e] = sU[e];   // mode 0: a.U == a.xn
     }
     if (!ok && tid == 0) atomicMax(a.flag, a.epoch);
     TT(1);
@@ -240,39 +254,44 @@ __global__ void __launch_bounds__(WB_TINY_THREADS) tiny_trial_kernel(TinyArgs a)
     TT(2);
 
     // ---- phase 2: MU_kb = M_kb U_{k+b}, diag N_kb, per-k partial sums -----------------------------------------
-    // all nn neighbours at once: one exposure of the load latency, one atan2 per thread
-    for (int e = tid; e < nn * nb * nb; e += WB_TINY_THREADS) sMk[e] = a.M[(long long)k * nn * nb * nb + e];
-    for (int e = tid; e < nn * mat; e += WB_TINY_THREADS) {
-        const int b = e / mat;
-        sUp[e] = a.U[(long long)a.kpb[(long long)k * nn + b] * mat + (e - b * mat)];
-    }
-    __syncthreads();
-    for (int e = tid; e < nn * mat; e += WB_TINY_THREADS) {
-        const int b = e / mat, r = e - b * mat, m = r % nb, n = r / nb;
-        const cplx* Mb = sMk + b * nb * nb;
-        const cplx* Ub = sUp + b * mat;
-        cplx acc = make_double2(0.0, 0.0);
-        for (int l = 0; l < nb; l++) cfma(acc, Mb[l * nb + m], Ub[n * nb + l]);
-        sMU[e] = acc;
-    }
-    __syncthreads();
-    for (int b = tid >> 5; b < nn; b += WB_TINY_THREADS / 32) {   // ||MU_kb||_F^2: a warp per pair, fixed order
-        double f2 = 0.0;
-        for (int e = tid & 31; e < mat; e += 32) { const cplx v = sMU[b * mat + e]; f2 = fma(v.x, v.x, fma(v.y, v.y, f2)); }
-        f2 = warp_sum(f2);
-        if ((tid & 31) == 0) sfro[b] = f2;
-    }
-    for (int e = tid; e < nn * nw; e += WB_TINY_THREADS) {
-        const int b = e / nw, n = e - b * nw;
-        const cplx* mu = sMU + b * mat + n * nb;
-        cplx d = make_double2(0.0, 0.0);
-        for (int m = 0; m < nb; m++) cfma_conj(d, sU[n * nb + m], mu[m]);
-        sZ[e] = d;
-        sphi[e] = atan2(d.y, d.x);             // imaglog, src/utils/linalg.jl:15
-        sa2[e] = d.x * d.x + d.y * d.y;
-    }
-    __syncthreads();
-    {
+    for (int slot = 0, k = blockIdx.x; slot < kper && k < nk; slot++, k += gridDim.x) {
+        cplx* sU = st0 + (size_t)slot * state_c;
+        cplx* sMU = sU + 2 * mat + nxx;
+        cplx* sZ = sMU + nn * mat;
+        double* sphi = dst0 + (size_t)slot * 2 * nn * nw;
+        double* sa2 = sphi + nn * nw;
+        // all nn neighbours at once: one exposure of the load latency, one atan2 per thread
+        for (int e = tid; e < nn * nb * nb; e += WB_TINY_THREADS) sMk[e] = a.M[(long long)k * nn * nb * nb + e];
+        for (int e = tid; e < nn * mat; e += WB_TINY_THREADS) {
+            const int b = e / mat;
+            sUp[e] = a.U[(long long)a.kpb[(long long)k * nn + b] * mat + (e - b * mat)];
+        }
+        __syncthreads();
+        for (int e = tid; e < nn * mat; e += WB_TINY_THREADS) {
+            const int b = e / mat, r = e - b * mat, m = r % nb, n = r / nb;
+            const cplx* Mb = sMk + b * nb * nb;
+            const cplx* Ub = sUp + b * mat;
+            cplx acc = make_double2(0.0, 0.0);
+            for (int l = 0; l < nb; l++) cfma(acc, Mb[l * nb + m], Ub[n * nb + l]);
+            sMU[e] = acc;
+        }
+        __syncthreads();
+        for (int b = tid >> 5; b < nn; b += WB_TINY_THREADS / 32) {   // ||MU_kb||_F^2: a warp per pair, fixed order
+            double f2 = 0.0;
+            for (int e = tid & 31; e < mat; e += 32) { const cplx v = sMU[b * mat + e]; f2 = fma(v.x, v.x, fma(v.y, v.y, f2)); }
+            f2 = warp_sum(f2);
+            if ((tid & 31) == 0) sfro[b] = f2;
+        }
+        for (int e = tid; e < nn * nw; e += WB_TINY_THREADS) {
+            const int b = e / nw, n = e - b * nw;
+            const cplx* mu = sMU + b * mat + n * nb;
+            cplx d = make_double2(0.0, 0.0);
+            for (int m = 0; m < nb; m++) cfma_conj(d, sU[n * nb + m], mu[m]);
+            sZ[e] = d;
+            sphi[e] = atan2(d.y, d.x);             // imaglog, src/utils/linalg.jl:15
+            sa2[e] = d.x * d.x + d.y * d.y;
+        }
+        __syncthreads();
         double sd = 0.0, mn = 1e300;
         for (int n = tid; n < nw; n += WB_TINY_THREADS) {
             double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
@@ -305,6 +324,7 @@ __global__ void __launch_bounds__(WB_TINY_THREADS) tiny_trial_kernel(TinyArgs a)
             a.part[(long long)(4 * nw + 1) * nk + k] = sd;
             a.pmin[k] = sqrt(m);
         }
+        __syncthreads();
     }
     TT(3);
     __threadfence();
@@ -322,7 +342,7 @@ __global__ void __launch_bounds__(WB_TINY_THREADS) tiny_trial_kernel(TinyArgs a)
     }
     __syncthreads();
     const double inv = 1.0 / (double)nk;
-    if (k == 0) {   // finalize_kernel
+    if (blockIdx.x == 0) {   // finalize_kernel
         for (int n = tid; n < nw; n += WB_TINY_THREADS) {
             const double rx = -ssum[3 * n + 0] * inv, ry = -ssum[3 * n + 1] * inv, rz = -ssum[3 * n + 2] * inv;
             a.res[8 + n] = ssum[3 * nw + n] * inv - (rx * rx + ry * ry + rz * rz);
@@ -357,76 +377,84 @@ __global__ void __launch_bounds__(WB_TINY_THREADS) tiny_trial_kernel(TinyArgs a)
             a.res[7] = 0.0;
         }
     }
-    // gradient coefficients (grad_kernel): c = 4 w_b / nk * (t - conj z), t = -i q / z, q = imaglog z + b . r~
-    for (int e = tid; e < nn * nw; e += WB_TINY_THREADS) {
-        const int b = e / nw, n = e % nw;
-        const cplx z = sZ[e];
-        double rx = -ssum[3 * n + 0] * inv, ry = -ssum[3 * n + 1] * inv, rz = -ssum[3 * n + 2] * inv;
-        if (a.has_penalty) {   // spread.jl:227
-            rx -= a.lambda * (rx - a.r0[3 * n + 0]);
-            ry -= a.lambda * (ry - a.r0[3 * n + 1]);
-            rz -= a.lambda * (rz - a.r0[3 * n + 2]);
-        }
-        const double* bv = a.bvec + ((long long)k * nn + b) * 3;
-        const double q = sphi[e] + (rx * bv[0] + ry * bv[1] + rz * bv[2]);
-        const double sq = q / sa2[e];
-        const double f = 4.0 * a.wb[b] * inv;
-        sZ[e] = make_double2(f * (-sq * z.y - z.x), f * (-sq * z.x + z.y));
-    }
-    __syncthreads();
-    for (int e = tid; e < mat; e += WB_TINY_THREADS) {
-        const int n = e / nb;
-        cplx acc = make_double2(0.0, 0.0);
-        for (int b = 0; b < nn; b++) cfma(acc, sMU[b * mat + e], sZ[b * nw + n]);
-        sG[e] = acc;
-    }
-    __syncthreads();
-    cplx* gk = a.gn + (long long)k * vlen;
-    double dot = 0.0;
-    if (a.mode == 1) {
-        // G_X = Y^H G_U, G_Y = G_U X^H with the frozen masks (disentangle.jl:481-501)
-        for (int e = tid; e < nxx; e += WB_TINY_THREADS) {
-            const int i = e % nw, n = e / nw;
-            cplx acc = make_double2(0.0, 0.0);
-            for (int m = 0; m < nb; m++) cfma_conj(acc, sY[i * nb + m], sG[n * nb + m]);
-            sGX[e] = acc;
-        }
-        const int nf = a.frozen ? a.nfrozen[k] : 0;
-        for (int e = tid; e < mat; e += WB_TINY_THREADS) {
-            const int m = e % nb, l = e / nb;
-            cplx acc = make_double2(0.0, 0.0);
-            if (!(a.frozen && (a.frozen[(long long)k * nb + m] || l < nf)))
-                for (int n = 0; n < nw; n++) cfma(acc, sG[n * nb + m], cconj(sX[n * nw + l]));
-            sUp[e] = acc;   // G_Y (the U_{k+b} staging buffer is free now)
+    for (int slot = 0, k = blockIdx.x; slot < kper && k < nk; slot++, k += gridDim.x) {
+        SLOT_POINTERS(slot)
+        const cplx* sk = a.s ? a.s + (long long)k * vlen : nullptr;
+        // gradient coefficients (grad_kernel): c = 4 w_b / nk * (t - conj z), t = -i q / z, q = imaglog z + b . r~
+        for (int e = tid; e < nn * nw; e += WB_TINY_THREADS) {
+            const int b = e / nw, n = e % nw;
+            const cplx z = sZ[e];
+            double rx = -ssum[3 * n + 0] * inv, ry = -ssum[3 * n + 1] * inv, rz = -ssum[3 * n + 2] * inv;
+            if (a.has_penalty) {   // spread.jl:227
+                rx -= a.lambda * (rx - a.r0[3 * n + 0]);
+                ry -= a.lambda * (ry - a.r0[3 * n + 1]);
+                rz -= a.lambda * (rz - a.r0[3 * n + 2]);
+            }
+            const double* bv = a.bvec + ((long long)k * nn + b) * 3;
+            const double q = sphi[e] + (rx * bv[0] + ry * bv[1] + rz * bv[2]);
+            const double sq = q / sa2[e];
+            const double f = 4.0 * a.wb[b] * inv;
+            sZ[e] = make_double2(f * (-sq * z.y - z.x), f * (-sq * z.x + z.y));
         }
         __syncthreads();
-        tiny_project(sX, sGX, sP, sT, nw, nw);
-        tiny_project(sY, sUp, sP, sT, nb, nw);
-        for (int e = tid; e < vlen; e += WB_TINY_THREADS) {
-            const cplx g = e < nxx ? sGX[e] : sUp[e - nxx];
-            gk[e] = g;
-            if (sk) { const cplx d = sk[e]; dot = fma(g.x, d.x, fma(g.y, d.y, dot)); }
-        }
-    } else {
-        tiny_project(sU, sG, sP, sT, nb, nw);
         for (int e = tid; e < mat; e += WB_TINY_THREADS) {
-            const cplx g = sG[e];
-            gk[e] = g;
-            if (sk) { const cplx d = sk[e]; dot = fma(g.x, d.x, fma(g.y, d.y, dot)); }
+            const int n = e / nb;
+            cplx acc = make_double2(0.0, 0.0);
+            for (int b = 0; b < nn; b++) cfma(acc, sMU[b * mat + e], sZ[b * nw + n]);
+            sG[e] = acc;
         }
+        __syncthreads();
+        cplx* gk = a.gn + (long long)k * vlen;
+        double dot = 0.0;
+        if (a.mode == 1) {
+            // G_X = Y^H G_U, G_Y = G_U X^H with the frozen masks (disentangle.jl:481-501)
+            for (int e = tid; e < nxx; e += WB_TINY_THREADS) {
+                const int i = e % nw, n = e / nw;
+                cplx acc = make_double2(0.0, 0.0);
+                for (int m = 0; m < nb; m++) cfma_conj(acc, sY[i * nb + m], sG[n * nb + m]);
+                sGX[e] = acc;
+            }
+            const int nf = a.frozen ? a.nfrozen[k] : 0;
+            for (int e = tid; e < mat; e += WB_TINY_THREADS) {
+                const int m = e % nb, l = e / nb;
+                cplx acc = make_double2(0.0, 0.0);
+                if (!(a.frozen && (a.frozen[(long long)k * nb + m] || l < nf)))
+                    for (int n = 0; n < nw; n++) cfma(acc, sG[n * nb + m], cconj(sX[n * nw + l]));
+                sUp[e] = acc;   // G_Y (the U_{k+b} staging buffer is free now)
+            }
+            __syncthreads();
+            tiny_project(sX, sGX, sP, sT, nw, nw);
+            tiny_project(sY, sUp, sP, sT, nb, nw);
+            for (int e = tid; e < vlen; e += WB_TINY_THREADS) {
+                const cplx g = e < nxx ? sGX[e] : sUp[e - nxx];
+                gk[e] = g;
+                if (sk) { const cplx d = sk[e]; dot = fma(g.x, d.x, fma(g.y, d.y, dot)); }
+            }
+        } else {
+            tiny_project(sU, sG, sP, sT, nb, nw);
+            for (int e = tid; e < mat; e += WB_TINY_THREADS) {
+                const cplx g = sG[e];
+                gk[e] = g;
+                if (sk) { const cplx d = sk[e]; dot = fma(g.x, d.x, fma(g.y, d.y, dot)); }
+            }
+        }
+        dot = tiny_block_sum(dot, red);
+        if (tid == 0) a.dpart[k] = dot;
+        __syncthreads();
     }
-    dot = tiny_block_sum(dot, red);
-    if (tid == 0) a.dpart[k] = dot;
     TT(5);
     __threadfence();
     grid.sync();
     TT(6);
 
     // ---- phase 4: CTA 0 publishes ----------------------------------------------------------------------------
-    if (k == 0) {
-        double d = 0.0, mn = 1e300;
-        for (int q = tid; q < nk; q += WB_TINY_THREADS) { d += a.dpart[q]; mn = fmin(mn, a.pmin[q]); }
-        d = tiny_block_sum(d, red);
+    if (blockIdx.x == 0) {
+        double d0 = 0.0, d1 = 0.0, mn = 1e300;
+        for (int q = tid; q < nk; q += 2 * WB_TINY_THREADS) {
+            d0 += a.dpart[q]; mn = fmin(mn, a.pmin[q]);
+            if (q + WB_TINY_THREADS < nk) { d1 += a.dpart[q + WB_TINY_THREADS]; mn = fmin(mn, a.pmin[q + WB_TINY_THREADS]); }
+        }
+        const double d = tiny_block_sum(d0 + d1, red);
         mn = warp_min(mn);
         __syncthreads();
         if ((tid & 31) == 0) red[tid >> 5] = mn;
@@ -446,13 +474,15 @@ __global__ void __launch_bounds__(WB_TINY_THREADS) tiny_trial_kernel(TinyArgs a)
 #endif
         }
     }
+#undef SLOT_POINTERS
 }
 
-size_t tiny_smem_bytes(int nb, int nw, int nn) {
+size_t tiny_smem_bytes(int nb, int nw, int nn, int kper) {
     const size_t mat = (size_t)nb * nw, nxx = (size_t)nw * nw;
-    const size_t cplx_elems = mat * 5 + nxx * 3 + (size_t)nn * nb * nb + 2 * (size_t)nn * mat + (size_t)nn * nw;
-    const size_t dbl = 2 * (size_t)nn * nw + (4 * (size_t)nw + 2) + nn + 8;
-    return cplx_elems * sizeof(cplx) + dbl * sizeof(double);
+    const size_t state_c = 2 * mat + nxx + (size_t)nn * mat + (size_t)nn * nw;
+    const size_t scratch_c = 2 * nxx + 2 * mat + (size_t)nn * nb * nb + (size_t)nn * mat;
+    const size_t dbl = (size_t)kper * 2 * nn * nw + (4 * (size_t)nw + 2) + nn + 8;
+    return ((size_t)kper * state_c + scratch_c) * sizeof(cplx) + dbl * sizeof(double);
 }
 
 }  // namespace
@@ -460,30 +490,39 @@ size_t tiny_smem_bytes(int nb, int nw, int nn) {
 // Is this context's shape served by the fused kernel?  (decided once, at creation: the plain overlaps must be kept)
 bool wb_tiny_shape(int nb, int nw, int nk_total, int nk, int nn) {
     static const bool off = [] { const char* e = getenv("WB200_TINY"); return e && e[0] == '0'; }();
-    return !off && nb <= WB_TINY_MAXB && nw <= nb && nn <= 32 && nk == nk_total && nk <= 1024;
+    return !off && nb <= WB_TINY_MAXB && nw <= nb && nn <= 32 && nk == nk_total && nk <= 148 * 64;
 }
 
 // mode 0: U on (Stiefel nb x nw)^nk with nb == nw handled as one factor; mode 1: (X, Y).  s may be nullptr.
 bool wb_tiny_usable(wb200_ctx* ctx, int mode) {
     if (!ctx->tiny_ok || ctx->allreduce || ctx->peer_self || ctx->profiling || !ctx->d_M) return false;
     if (mode != 0 && mode != 1) return false;
-    if (ctx->tiny_blocks == 0) {   // co-residency of nk CTAs (cooperative launch): once per ctx
-        const size_t smem = tiny_smem_bytes(ctx->nb, ctx->nw, ctx->nn);
-        if (smem > 200 * 1024 ||
-            cudaFuncSetAttribute(tiny_trial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
-            cudaGetLastError();
-            ctx->tiny_ok = 0;
-            return false;
-        }
-        int per_sm = 0, coop = 0;
+    if (ctx->tiny_blocks == 0) {   // grid and k-points per CTA such that the whole grid is co-resident: once per ctx
+        int coop = 0;
         cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device);
-        if (!coop || cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tiny_trial_kernel, WB_TINY_THREADS, smem) != cudaSuccess) {
+        if (!coop || cudaFuncSetAttribute(tiny_trial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) {
             cudaGetLastError();
             ctx->tiny_ok = 0;
             return false;
         }
-        ctx->tiny_blocks = per_sm * ctx->num_sms;
-        if (ctx->tiny_blocks < ctx->nk) { ctx->tiny_ok = 0; return false; }
+        int kmin = 1;
+        if (const char* e = getenv("WB200_TINY_KPER")) kmin = atoi(e) > 1 ? atoi(e) : 1;   // tests: force several k-points per CTA
+        ctx->tiny_ok = 0;
+        for (int kper = kmin; kper <= 64; kper++) {
+            const size_t smem = tiny_smem_bytes(ctx->nb, ctx->nw, ctx->nn, kper);
+            if (smem > 200 * 1024) break;
+            int per_sm = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tiny_trial_kernel, WB_TINY_THREADS, smem) != cudaSuccess) {
+                cudaGetLastError();
+                break;
+            }
+            const int grid = (ctx->nk + kper - 1) / kper;
+            if (per_sm * ctx->num_sms >= grid) {
+                ctx->tiny_ok = 1; ctx->tiny_blocks = grid; ctx->tiny_kper = kper;
+                break;
+            }
+        }
+        if (!ctx->tiny_ok) return false;
     }
     return true;
 }
@@ -500,7 +539,7 @@ int wb_tiny_trial(wb200_ctx* ctx, int mode, const cplx* x, const cplx* s, double
     }
     if (mode == 1 && !ctx->d_U) { ctx->err = "wb_tiny_trial: no gauge buffer"; return WB200_ERR_ARG; }
     TinyArgs a{};
-    a.mode = mode; a.nb = nb; a.nw = nw; a.nk = nk; a.nn = nn;
+    a.mode = mode; a.nb = nb; a.nw = nw; a.nk = nk; a.nn = nn; a.kper = ctx->tiny_kper;
     a.kpb = ctx->d_kpb; a.bvec = ctx->d_bvec; a.wb = ctx->d_wb; a.M = ctx->d_M;
     a.frozen = mode == 1 ? ctx->d_frozen : nullptr; a.nfrozen = ctx->d_nfrozen;
     a.has_penalty = ctx->has_penalty; a.lambda = ctx->lambda; a.r0 = ctx->d_r0; a.wsum = ctx->wsum;
@@ -514,8 +553,9 @@ int wb_tiny_trial(wb200_ctx* ctx, int mode, const cplx* x, const cplx* s, double
     a.epoch = ++ctx->tiny_epoch;
     a.hpin = ctx->h_pinned;
     void* args[] = {&a};
-    const size_t smem = tiny_smem_bytes(nb, nw, nn);
-    WB_CUDA(ctx, cudaLaunchCooperativeKernel((void*)tiny_trial_kernel, dim3(nk), dim3(WB_TINY_THREADS), args, smem, ctx->stream));
+    const size_t smem = tiny_smem_bytes(nb, nw, nn, ctx->tiny_kper);
+    WB_CUDA(ctx, cudaLaunchCooperativeKernel((void*)tiny_trial_kernel, dim3(ctx->tiny_blocks), dim3(WB_TINY_THREADS), args, smem,
+                                             ctx->stream));
     WB_LAUNCH_CHECK(ctx);
     ctx->retract_pending = 1;   // h_pinned[8] carries the flag of this launch
     return WB200_OK;
