@@ -49,7 +49,7 @@ enum wb200_status {
 #define WB200_FLAG_M_ROW_MAJOR 8u  /* wb200_create: every M_kb is given row-major (C order, M[k][b][m][l] — what numpy
                                       holds); it is transposed on the device instead of by the caller */
 #define WB200_FLAG_NO_FUSED_TRIAL 4u /* optimiser drivers: never use the one-launch trial-point kernel for tiny shapes
-                                        (n_bands <= 16, tiny.cu); the general kernels run instead (tests compare the two) */
+                                        (n_bands <= 32 and little arithmetic, tiny.cu); the general kernels run instead (tests compare the two) */
 
 /* ---- context --------------------------------------------------------------------------------
  * Replaces `Cache(model)` (src/spread.jl:139-162) + the stencil fields read by the hot loops

@@ -292,10 +292,12 @@ def test_disentangle_driver(w, silicon):
     ("fcc", (4, 4, 4), 12, 8, 4),      # the Si2 shape of benchmark/bench_disentangle.jl: (X, Y) chain, frozen bands
     ("tetragonal", (5, 5, 1), 16, 5, 3),   # self-neighbours with G != 0, few Wannier functions
     ("cubic", (2, 2, 2), 9, 9, 9),     # every band frozen at every k (the n_froz == n_wann branch, disentangle.jl:390)
-    ("cubic", (12, 12, 10), 8, 8, 0),  # 1 440 k-points
+    ("cubic", (6, 6, 6), 8, 8, 0),     # 216 k-points: more CTAs than SMs
+    ("fcc", (5, 5, 5), 18, 9, 5),      # the band counts of BASELINE config 2 (Cu-like), n_bands > 16
+    ("fcc", (4, 4, 4), 20, 12, 6),
 ])
 def test_tiny_trial_kernel_matches_general_path(w, lat, grid, nb, nw, nfroz):
-    """tiny.cu (one cooperative launch per trial point, n_bands <= 16) against the chain of general kernels
+    """tiny.cu (one cooperative launch per trial point, small n_bands and little arithmetic) against the chain of general kernels
     (WB200_FLAG_NO_FUSED_TRIAL): the same L-BFGS / HagerZhang run must take the same iterations and evaluations and
     arrive at the same point; with and without the centre penalty; each also checked against the oracle's spread."""
     st, M, U = w.synthetic.make_model_arrays(lat, grid, nb, nw)
@@ -339,8 +341,8 @@ def test_tiny_trial_kernel_matches_general_path(w, lat, grid, nb, nw, nfroz):
         assert abs(f1 - f2) < 1e-9 * max(1.0, abs(f2))
         assert np.abs(x1 - x2).max() < 1e-7
         assert l1 < l2 / 2               # the fused path really ran: one launch per trial point instead of ~13
-        # one or several k-points per CTA: the same arithmetic in the same order (three slots of the 16 x 16, 12-neighbour
-        # shape do not fit into shared memory: that context falls back to the general kernels)
+        # one or several k-points per CTA: the same arithmetic in the same order (where three slots do not fit into
+        # shared memory — the 16 x 16, 12-neighbour shape — that context falls back to the general kernels)
         assert l3 in (l1, l2)
         ref = (f1, x1) if l3 == l1 else (f2, x2)
         assert f3 == ref[0] and np.array_equal(x3, ref[1])

@@ -199,6 +199,7 @@ struct wb200_ctx {
     int tiny_ok = 0;           // shape served (decided at creation: the plain overlaps d_M are kept then)
     int tiny_blocks = 0;       // grid of the fused kernel (0: not planned yet); the whole grid must be co-resident
     int tiny_kper = 1;         // k-points per CTA
+    int tiny_mu_global = 0;    // the rotated overlaps of a k-point wait for the gradient in d_MU instead of shared memory
     double* d_tiny = nullptr;  // [nk] per-k inner products, then the retraction flag word
     int tiny_epoch = 0;
     unsigned long long graph_clock = 0;

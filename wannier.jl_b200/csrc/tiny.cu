@@ -1,7 +1,9 @@
 // tiny.cu — one trial point of the optimiser's line search in ONE cooperative launch, for the problem sizes the
 // reference's own benchmark suite runs (benchmark/bench_maxloc.jl: Si2_valence, 4 WFs, 64 k-points;
-// bench_disentangle.jl: Si2, 12 bands -> 8 WFs): n_bands <= 16 and as many k-points as fit into the shared memory of
-// a co-resident grid (a CTA owns one or several k-points: e.g. 8 WFs on a 12 x 12 x 12 grid).
+// bench_disentangle.jl: Si2, 12 bands -> 8 WFs) and their neighbourhood: n_bands <= 32 as far as shared memory
+// allows, one CTA per k-point, at most two CTAs per SM (<= 296 k-points on a B200) — where it measures 1.1-1.5 x
+// faster than the chain of general kernels; beyond that the general kernels run (tools/debug_tiny_crossover.py).
+// (The kernel itself handles several k-points per CTA in slots of shared memory; the plan does not use that.)
 //
 // At those sizes one evaluation is ~0.3-2 MFLOP: the arithmetic of a whole trial point
 //     xn = retract(x + a s);  f, G = spread and gradient at xn;  gn = project(G, xn);  dphi = <gn, s>
@@ -30,12 +32,14 @@
 #include <cooperative_groups.h>
 namespace cg = cooperative_groups;
 
-#define WB_TINY_MAXB 16
+#define WB_TINY_MAXB 32
 #define WB_TINY_THREADS 128
 
 struct TinyArgs {
     int mode, nb, nw, nk, nn;
     int kper;                      // k-points per CTA (CTA c owns k = c, c + gridDim.x, ...)
+    int mu_global;                 // the rotated overlaps MU_kb wait for phase 3 in global memory (L2), not in the slots
+    cplx* MUg;                     // [pairs][nb*nw] (ctx->d_MU)
     const int32_t* kpb;
     const double* bvec;
     const double* wb;
@@ -179,7 +183,8 @@ __global__ void __launch_bounds__(WB_TINY_THREADS) tiny_trial_kernel(TinyArgs a)
     // shared memory: `kper` slots of per-k state that lives through the whole trial point (the CTA owns the k-points
     // blockIdx.x, blockIdx.x + gridDim.x, ...), then scratch that every slot re-uses
     extern __shared__ __align__(16) unsigned char tiny_smem[];
-    const int state_c = 2 * mat + nxx + nn * mat + nn * nw;
+    // slot: U_k, X_k, Y_k, diag N_kb [nn][nw] (+ MU_kb [nn][mat] unless they wait in global memory)
+    const int state_c = 2 * mat + nxx + nn * nw + (a.mu_global ? 0 : nn * mat);
     cplx* st0 = reinterpret_cast<cplx*>(tiny_smem);
     cplx* sP = st0 + (size_t)kper * state_c;         // [nxx]   scratch
     cplx* sT = sP + nxx;                             // [mat]   scratch
@@ -187,7 +192,8 @@ __global__ void __launch_bounds__(WB_TINY_THREADS) tiny_trial_kernel(TinyArgs a)
     cplx* sGX = sG + mat;                            // [nxx]
     cplx* sMk = sGX + nxx;                           // [nn][nb*nb] M_kb staging
     cplx* sUp = sMk + nn * nb * nb;                  // [nn][mat]   U_{k+b} staging (later: G_Y)
-    double* dst0 = reinterpret_cast<double*>(sUp + nn * mat);
+    cplx* sMUscr = sUp + nn * mat;                   // [nn][mat]   MU_kb of the current k-point when they live in global memory
+    double* dst0 = reinterpret_cast<double*>(sMUscr + (a.mu_global ? nn * mat : 0));
     double* ssum = dst0 + (size_t)kper * 2 * nn * nw;   // [nsums]
     double* sfro = ssum + nsums;                     // [nn]
     double* red = sfro + nn;                         // [8]
@@ -196,8 +202,8 @@ __global__ void __launch_bounds__(WB_TINY_THREADS) tiny_trial_kernel(TinyArgs a)
     cplx* sU = st0 + (size_t)(slot) * state_c;            /* [mat]  U_k               */      \
     cplx* sX = sU + mat;                                  /* [nxx]  X_k (mode 1)      */      \
     cplx* sY = sX + nxx;                                  /* [mat]  Y_k (mode 1)      */      \
-    cplx* sMU = sY + mat;                                 /* [nn][mat]                */      \
-    cplx* sZ = sMU + nn * mat;                            /* [nn][nw] diag N_kb, later the gradient coefficients */ \
+    cplx* sZ = sY + mat;                                  /* [nn][nw] diag N_kb, later the gradient coefficients */ \
+    cplx* sMU = a.mu_global ? sMUscr : sZ + nn * nw;      /* [nn][mat]                */      \
     double* sphi = dst0 + (size_t)(slot) * 2 * nn * nw;   /* [nn][nw]                 */      \
     double* sa2 = sphi + nn * nw;                         /* [nn][nw]                 */
 #ifdef WB_TINY_TIMING
@@ -256,8 +262,8 @@ __global__ void __launch_bounds__(WB_TINY_THREADS) tiny_trial_kernel(TinyArgs a)
     // ---- phase 2: MU_kb = M_kb U_{k+b}, diag N_kb, per-k partial sums -----------------------------------------
     for (int slot = 0, k = blockIdx.x; slot < kper && k < nk; slot++, k += gridDim.x) {
         cplx* sU = st0 + (size_t)slot * state_c;
-        cplx* sMU = sU + 2 * mat + nxx;
-        cplx* sZ = sMU + nn * mat;
+        cplx* sZ = sU + 2 * mat + nxx;
+        cplx* sMU = a.mu_global ? sMUscr : sZ + nn * nw;
         double* sphi = dst0 + (size_t)slot * 2 * nn * nw;
         double* sa2 = sphi + nn * nw;
         // all nn neighbours at once: one exposure of the load latency, one atan2 per thread
@@ -274,6 +280,7 @@ __global__ void __launch_bounds__(WB_TINY_THREADS) tiny_trial_kernel(TinyArgs a)
             cplx acc = make_double2(0.0, 0.0);
             for (int l = 0; l < nb; l++) cfma(acc, Mb[l * nb + m], Ub[n * nb + l]);
             sMU[e] = acc;
+            if (a.mu_global) a.MUg[(long long)k * nn * mat + e] = acc;
         }
         __syncthreads();
         for (int b = tid >> 5; b < nn; b += WB_TINY_THREADS / 32) {   // ||MU_kb||_F^2: a warp per pair, fixed order
@@ -380,6 +387,8 @@ __global__ void __launch_bounds__(WB_TINY_THREADS) tiny_trial_kernel(TinyArgs a)
     for (int slot = 0, k = blockIdx.x; slot < kper && k < nk; slot++, k += gridDim.x) {
         SLOT_POINTERS(slot)
         const cplx* sk = a.s ? a.s + (long long)k * vlen : nullptr;
+        if (a.mu_global)   // (written by this CTA in phase 2: L2, or still L1)
+            for (int e = tid; e < nn * mat; e += WB_TINY_THREADS) sMU[e] = a.MUg[(long long)k * nn * mat + e];
         // gradient coefficients (grad_kernel): c = 4 w_b / nk * (t - conj z), t = -i q / z, q = imaglog z + b . r~
         for (int e = tid; e < nn * nw; e += WB_TINY_THREADS) {
             const int b = e / nw, n = e % nw;
@@ -477,10 +486,10 @@ __global__ void __launch_bounds__(WB_TINY_THREADS) tiny_trial_kernel(TinyArgs a)
 #undef SLOT_POINTERS
 }
 
-size_t tiny_smem_bytes(int nb, int nw, int nn, int kper) {
+size_t tiny_smem_bytes(int nb, int nw, int nn, int kper, bool mu_global) {
     const size_t mat = (size_t)nb * nw, nxx = (size_t)nw * nw;
-    const size_t state_c = 2 * mat + nxx + (size_t)nn * mat + (size_t)nn * nw;
-    const size_t scratch_c = 2 * nxx + 2 * mat + (size_t)nn * nb * nb + (size_t)nn * mat;
+    const size_t state_c = 2 * mat + nxx + (size_t)nn * nw + (mu_global ? 0 : (size_t)nn * mat);
+    const size_t scratch_c = 2 * nxx + 2 * mat + (size_t)nn * nb * nb + (size_t)nn * mat + (mu_global ? (size_t)nn * mat : 0);
     const size_t dbl = (size_t)kper * 2 * nn * nw + (4 * (size_t)nw + 2) + nn + 8;
     return ((size_t)kper * state_c + scratch_c) * sizeof(cplx) + dbl * sizeof(double);
 }
@@ -490,7 +499,10 @@ size_t tiny_smem_bytes(int nb, int nw, int nn, int kper) {
 // Is this context's shape served by the fused kernel?  (decided once, at creation: the plain overlaps must be kept)
 bool wb_tiny_shape(int nb, int nw, int nk_total, int nk, int nn) {
     static const bool off = [] { const char* e = getenv("WB200_TINY"); return e && e[0] == '0'; }();
-    return !off && nb <= WB_TINY_MAXB && nw <= nb && nn <= 32 && nk == nk_total && nk <= 148 * 64;
+    // CUDA-core FP64 on 128 threads per k-point: worth it while the arithmetic of an evaluation stays a few
+    // microseconds (32 M complex multiply-adds ~ 10 us on 148 SMs); beyond that the DMMA kernels win
+    const double cmacs = (double)nk * nn * nb * nb * nw;
+    return !off && nb <= WB_TINY_MAXB && nw <= nb && nn <= 32 && nk == nk_total && nk <= 148 * 64 && cmacs <= 32e6;
 }
 
 // mode 0: U on (Stiefel nb x nw)^nk with nb == nw handled as one factor; mode 1: (X, Y).  s may be nullptr.
@@ -505,23 +517,31 @@ bool wb_tiny_usable(wb200_ctx* ctx, int mode) {
             ctx->tiny_ok = 0;
             return false;
         }
-        int kmin = 1;
-        if (const char* e = getenv("WB200_TINY_KPER")) kmin = atoi(e) > 1 ? atoi(e) : 1;   // tests: force several k-points per CTA
+        // Measured (tools/debug_tiny_crossover.py, profiles/r4_summary.md): the fused kernel beats the chain of general
+        // kernels by 1.1-1.5 x while there are at most ~2 CTAs per SM with one k-point each (64 and 216 k-points, n_bands
+        // 4-20) and loses beyond (512 k-points: 0.84-0.92 x, 729: 0.81 x — every CTA re-adds the partial sums of all k,
+        // and the latency-bound per-k chains no longer have an SM to themselves).  So: one k-point per CTA, at most two
+        // CTAs per SM; WB200_TINY_KPER (tests) forces several k-points per CTA regardless.
+        int kmin = 1, kmax = 1;
+        if (const char* e = getenv("WB200_TINY_KPER")) { kmin = atoi(e) > 1 ? atoi(e) : 1; kmax = 64; }
+        if (kmax == 1 && ctx->nk > 2 * ctx->num_sms) { ctx->tiny_ok = 0; return false; }
         ctx->tiny_ok = 0;
-        for (int kper = kmin; kper <= 64; kper++) {
-            const size_t smem = tiny_smem_bytes(ctx->nb, ctx->nw, ctx->nn, kper);
-            if (smem > 200 * 1024) break;
-            int per_sm = 0;
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tiny_trial_kernel, WB_TINY_THREADS, smem) != cudaSuccess) {
-                cudaGetLastError();
-                break;
+        // first choice: the rotated overlaps of a k-point stay in its slot; second: they wait in global memory (L2)
+        for (int mug = 0; mug < 2 && !ctx->tiny_ok; mug++)
+            for (int kper = kmin; kper <= kmax; kper++) {
+                const size_t smem = tiny_smem_bytes(ctx->nb, ctx->nw, ctx->nn, kper, mug != 0);
+                if (smem > 200 * 1024) break;
+                int per_sm = 0;
+                if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tiny_trial_kernel, WB_TINY_THREADS, smem) != cudaSuccess) {
+                    cudaGetLastError();
+                    break;
+                }
+                const int grid = (ctx->nk + kper - 1) / kper;
+                if (per_sm * ctx->num_sms >= grid) {
+                    ctx->tiny_ok = 1; ctx->tiny_blocks = grid; ctx->tiny_kper = kper; ctx->tiny_mu_global = mug;
+                    break;
+                }
             }
-            const int grid = (ctx->nk + kper - 1) / kper;
-            if (per_sm * ctx->num_sms >= grid) {
-                ctx->tiny_ok = 1; ctx->tiny_blocks = grid; ctx->tiny_kper = kper;
-                break;
-            }
-        }
         if (!ctx->tiny_ok) return false;
     }
     return true;
@@ -540,6 +560,7 @@ int wb_tiny_trial(wb200_ctx* ctx, int mode, const cplx* x, const cplx* s, double
     if (mode == 1 && !ctx->d_U) { ctx->err = "wb_tiny_trial: no gauge buffer"; return WB200_ERR_ARG; }
     TinyArgs a{};
     a.mode = mode; a.nb = nb; a.nw = nw; a.nk = nk; a.nn = nn; a.kper = ctx->tiny_kper;
+    a.mu_global = ctx->tiny_mu_global; a.MUg = ctx->d_MU;
     a.kpb = ctx->d_kpb; a.bvec = ctx->d_bvec; a.wb = ctx->d_wb; a.M = ctx->d_M;
     a.frozen = mode == 1 ? ctx->d_frozen : nullptr; a.nfrozen = ctx->d_nfrozen;
     a.has_penalty = ctx->has_penalty; a.lambda = ctx->lambda; a.r0 = ctx->d_r0; a.wsum = ctx->wsum;
@@ -553,7 +574,7 @@ int wb_tiny_trial(wb200_ctx* ctx, int mode, const cplx* x, const cplx* s, double
     a.epoch = ++ctx->tiny_epoch;
     a.hpin = ctx->h_pinned;
     void* args[] = {&a};
-    const size_t smem = tiny_smem_bytes(nb, nw, nn, ctx->tiny_kper);
+    const size_t smem = tiny_smem_bytes(nb, nw, nn, ctx->tiny_kper, ctx->tiny_mu_global != 0);
     WB_CUDA(ctx, cudaLaunchCooperativeKernel((void*)tiny_trial_kernel, dim3(ctx->tiny_blocks), dim3(WB_TINY_THREADS), args, smem,
                                              ctx->stream));
     WB_LAUNCH_CHECK(ctx);
