@@ -172,7 +172,20 @@ def test_synthetic_xy_chain_and_disentangle(w, lat, grid, nb, nw, nfroz):
     ctx.close()
 
 
-def test_stiefel_project_and_retract(w, valence, silicon):
+@pytest.mark.parametrize("dmma", [None, "0", "1"])
+def test_stiefel_project_and_retract(w, valence, silicon, dmma):
+    # n <= 32: tensor-pipe or CUDA-core kernels, chosen by the amount of work; WB200_STIEFEL_DMMA = 0 / 1 forces one
+    import os
+    os.environ.pop("WB200_STIEFEL_DMMA", None)
+    if dmma is not None:
+        os.environ["WB200_STIEFEL_DMMA"] = dmma
+    try:
+        _stiefel_project_and_retract(w, valence, silicon)
+    finally:
+        os.environ.pop("WB200_STIEFEL_DMMA", None)
+
+
+def _stiefel_project_and_retract(w, valence, silicon):
     ctx = make_ctx(w, fixture_stencil(valence), valence["M"], 4)
     rng = np.random.default_rng(7)
     # shapes above 64 run on the plain-layout tensor GEMM (zgemm_dmma.cu): ragged m / n / k, one and
@@ -180,7 +193,7 @@ def test_stiefel_project_and_retract(w, valence, silicon):
     for (nrow, ncol, count) in ((4, 4, 64), (12, 8, 17), (128, 128, 3), (40, 24, 5), (32, 32, 9), (31, 17, 6),
                                (9, 9, 5), (18, 9, 7), (1, 1, 3), (33, 32, 2), (72, 40, 5), (100, 100, 7),
                                (130, 70, 3), (257, 129, 2), (65, 65, 11), (200, 33, 4), (256, 256, 2),
-                               (96, 64, 301)):
+                               (96, 64, 301), (32, 32, 200), (24, 20, 600)):
         X = so.stiefel_retract(rng.standard_normal((count, nrow, ncol)) + 1j * rng.standard_normal((count, nrow, ncol)))
         G = rng.standard_normal(X.shape) + 1j * rng.standard_normal(X.shape)
         Gc = w.api.to_abi_U(G)
@@ -287,14 +300,13 @@ def test_disentangle_driver(w, silicon):
 
 @pytest.mark.parametrize("lat,grid,nb,nw,nfroz", [
     ("fcc", (4, 4, 4), 4, 4, 0),       # the Si2_valence shape of benchmark/bench_maxloc.jl
-    ("bcc", (3, 3, 3), 16, 16, 0),     # largest square shape the fused kernel takes, 12 neighbours
+    ("bcc", (3, 3, 3), 11, 11, 0),     # 12 neighbours
     ("cubic", (3, 2, 2), 7, 7, 0),     # odd sizes
     ("fcc", (4, 4, 4), 12, 8, 4),      # the Si2 shape of benchmark/bench_disentangle.jl: (X, Y) chain, frozen bands
-    ("tetragonal", (5, 5, 1), 16, 5, 3),   # self-neighbours with G != 0, few Wannier functions
+    ("tetragonal", (5, 5, 1), 16, 5, 3),   # self-neighbours with G != 0, few Wannier functions, 16 bands
     ("cubic", (2, 2, 2), 9, 9, 9),     # every band frozen at every k (the n_froz == n_wann branch, disentangle.jl:390)
     ("cubic", (6, 6, 6), 8, 8, 0),     # 216 k-points: more CTAs than SMs
     ("fcc", (5, 5, 5), 18, 9, 5),      # the band counts of BASELINE config 2 (Cu-like), n_bands > 16
-    ("fcc", (4, 4, 4), 20, 12, 6),
 ])
 def test_tiny_trial_kernel_matches_general_path(w, lat, grid, nb, nw, nfroz):
     """tiny.cu (one cooperative launch per trial point, small n_bands and little arithmetic) against the chain of general kernels
@@ -341,8 +353,8 @@ def test_tiny_trial_kernel_matches_general_path(w, lat, grid, nb, nw, nfroz):
         assert abs(f1 - f2) < 1e-9 * max(1.0, abs(f2))
         assert np.abs(x1 - x2).max() < 1e-7
         assert l1 < l2 / 2               # the fused path really ran: one launch per trial point instead of ~13
-        # one or several k-points per CTA: the same arithmetic in the same order (where three slots do not fit into
-        # shared memory — the 16 x 16, 12-neighbour shape — that context falls back to the general kernels)
+        # one or several k-points per CTA: the same arithmetic in the same order (a context whose three slots do not
+        # fit into shared memory falls back to the general kernels)
         assert l3 in (l1, l2)
         ref = (f1, x1) if l3 == l1 else (f2, x2)
         assert f3 == ref[0] and np.array_equal(x3, ref[1])

@@ -347,9 +347,19 @@ __global__ void __launch_bounds__(256, 1) project32_kernel(int nrow, int ncol, i
 
 bool wb_small_applicable(int nrow, int ncol) { return nrow <= WB_SMALL_MAX && ncol <= WB_SMALL_MAX; }
 
-static bool use32(int nrow, int ncol) {
-    static const bool off = [] { const char* e = getenv("WB200_STIEFEL_DMMA"); return e && e[0] == '0'; }();
-    return !off && nrow <= 32 && ncol <= 32;
+// DMMA (four matrices per CTA, 32 x 32 padded tiles) or CUDA cores (one CTA per matrix)?  The tensor kernels have a
+// latency floor of ~28 us per launch whatever the size (profiles/r4e_launches_valence_maxloc.csv: a 32 x 32 tile
+// iterating on 4 x 4 matrices) and win only when there is work to fill them: 1 728 matrices of 32 x 32 take 107 us
+// against 306 us on the CUDA cores, but with WB200_STIEFEL_DMMA=0 the optimiser was 6-25 % faster per evaluation at
+// every shape of tools/debug_tiny_crossover.py with n <= 24 and up to 729 matrices.  Threshold between those
+// measurements: count * nrow * ncol^2 > 5e6 complex multiply-adds per product.  WB200_STIEFEL_DMMA = 0 / 1 forces.
+static bool use32(int nrow, int ncol, int count) {
+    if (nrow > 32 || ncol > 32) return false;
+    if (const char* e = getenv("WB200_STIEFEL_DMMA")) {
+        if (e[0] == '0') return false;
+        if (e[0] == '1') return true;
+    }
+    return (double)count * nrow * ncol * ncol > 5e6;
 }
 
 // "did every matrix converge?" comes back in h_pinned[8].  Normally the caller waits for it here.  The optimiser
@@ -375,7 +385,7 @@ bool wb_retract_pending_failed(wb200_ctx* ctx) {
 }
 
 int wb_retract_small(wb200_ctx* ctx, cplx* dX, int nrow, int ncol, int ld, long long stride, int count) {
-    if (use32(nrow, ncol)) {
+    if (use32(nrow, ncol, count)) {
         const size_t smem32 = sizeof(cplx) * 4 * 2 * S32_MAT;
         if (!(ctx->attr_mask & 16u)) {
             WB_CUDA(ctx, cudaFuncSetAttribute(retract32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32));
@@ -402,7 +412,7 @@ int wb_retract_small(wb200_ctx* ctx, cplx* dX, int nrow, int ncol, int ld, long 
 
 int wb_project_small(wb200_ctx* ctx, const cplx* dX, cplx* dG, int nrow, int ncol, int ld, long long stride,
                      int count) {
-    if (use32(nrow, ncol)) {
+    if (use32(nrow, ncol, count)) {
         const size_t smem32 = sizeof(cplx) * 4 * 3 * S32_MAT;
         if (!(ctx->attr_mask & 32u)) {
             WB_CUDA(ctx, cudaFuncSetAttribute(project32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32));

@@ -499,10 +499,11 @@ size_t tiny_smem_bytes(int nb, int nw, int nn, int kper, bool mu_global) {
 // Is this context's shape served by the fused kernel?  (decided once, at creation: the plain overlaps must be kept)
 bool wb_tiny_shape(int nb, int nw, int nk_total, int nk, int nn) {
     static const bool off = [] { const char* e = getenv("WB200_TINY"); return e && e[0] == '0'; }();
-    // CUDA-core FP64 on 128 threads per k-point: worth it while the arithmetic of an evaluation stays a few
-    // microseconds (32 M complex multiply-adds ~ 10 us on 148 SMs); beyond that the DMMA kernels win
-    const double cmacs = (double)nk * nn * nb * nb * nw;
-    return !off && nb <= WB_TINY_MAXB && nw <= nb && nn <= 32 && nk == nk_total && nk <= 148 * 64 && cmacs <= 32e6;
+    // CUDA-core FP64 on 128 threads per k-point: measured against the general kernels (profiles/r4s_tiny_crossover.txt)
+    // it wins by 1.15-1.34 x up to nn nb^2 nw = 14 k complex multiply-adds per k-point (4 x 4 ... 12 x 12), by 1.18 x at
+    // 23 k (18 -> 9), and loses 2 % at 33 k (16 x 16): the line is drawn at 24 k
+    const double cmacs_per_k = (double)nn * nb * nb * nw;
+    return !off && nb <= WB_TINY_MAXB && nw <= nb && nn <= 32 && nk == nk_total && cmacs_per_k <= 24e3;
 }
 
 // mode 0: U on (Stiefel nb x nw)^nk with nb == nw handled as one factor; mode 1: (X, Y).  s may be nullptr.
