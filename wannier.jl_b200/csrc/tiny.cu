@@ -32,7 +32,8 @@
 #include <cooperative_groups.h>
 namespace cg = cooperative_groups;
 
-#define WB_TINY_MAXB 32
+#define WB_TINY_MAXB 32   /* bands */
+#define WB_TINY_MAXW 16   /* Wannier functions: the polar iteration keeps ncol^2 / 128 elements per thread in registers */
 #define WB_TINY_THREADS 128
 
 struct TinyArgs {
@@ -91,10 +92,10 @@ __device__ bool tiny_polar(cplx* A, cplx* P, cplx* T, int nrow, int ncol, double
     cplx* nxt = T;
     for (int it = 0; it < 100 && !converged; it++) {
         // P = cur^H cur (each thread keeps its elements in registers until they are scaled), ||P - I||_F, ||P||_F
-        cplx pv[(WB_TINY_MAXB * WB_TINY_MAXB + WB_TINY_THREADS - 1) / WB_TINY_THREADS];
+        cplx pv[(WB_TINY_MAXW * WB_TINY_MAXW + WB_TINY_THREADS - 1) / WB_TINY_THREADS];
         double e2 = 0.0, f2 = 0.0;
 #pragma unroll
-        for (int q = 0; q < (WB_TINY_MAXB * WB_TINY_MAXB + WB_TINY_THREADS - 1) / WB_TINY_THREADS; q++) {
+        for (int q = 0; q < (WB_TINY_MAXW * WB_TINY_MAXW + WB_TINY_THREADS - 1) / WB_TINY_THREADS; q++) {
             const int e = tid + q * WB_TINY_THREADS;
             if (e < ncol * ncol) {
                 const int i = e % ncol, j = e / ncol;
@@ -118,7 +119,7 @@ __device__ bool tiny_polar(cplx* A, cplx* P, cplx* T, int nrow, int ncol, double
         const double sc = (it == 0 && err >= 1.9) ? rsqrt(fro) : 1.0;
         const double s3 = 0.5 * sc * sc * sc;
 #pragma unroll
-        for (int q = 0; q < (WB_TINY_MAXB * WB_TINY_MAXB + WB_TINY_THREADS - 1) / WB_TINY_THREADS; q++) {
+        for (int q = 0; q < (WB_TINY_MAXW * WB_TINY_MAXW + WB_TINY_THREADS - 1) / WB_TINY_THREADS; q++) {
             const int e = tid + q * WB_TINY_THREADS;
             if (e < ncol * ncol) {
                 const int i = e % ncol, j = e / ncol;
@@ -503,7 +504,7 @@ bool wb_tiny_shape(int nb, int nw, int nk_total, int nk, int nn) {
     // it wins by 1.15-1.34 x up to nn nb^2 nw = 14 k complex multiply-adds per k-point (4 x 4 ... 12 x 12), by 1.18 x at
     // 23 k (18 -> 9), and loses 2 % at 33 k (16 x 16): the line is drawn at 24 k
     const double cmacs_per_k = (double)nn * nb * nb * nw;
-    return !off && nb <= WB_TINY_MAXB && nw <= nb && nn <= 32 && nk == nk_total && cmacs_per_k <= 24e3;
+    return !off && nb <= WB_TINY_MAXB && nw <= WB_TINY_MAXW && nw <= nb && nn <= 32 && nk == nk_total && cmacs_per_k <= 24e3;
 }
 
 // mode 0: U on (Stiefel nb x nw)^nk with nb == nw handled as one factor; mode 1: (X, Y).  s may be nullptr.
