@@ -168,7 +168,10 @@ struct wb200_ctx {
     double* d_scal = nullptr;   // [2048] scratch scalars (errors, flags)
     double* d_red = nullptr;    // block partials + results of the fused inner-product kernel (lazy)
     double* d_zpart = nullptr; size_t zpart_elems = 0;   // per-warp norm partials of the tensor GEMM epilogues (lazy)
-    double* h_pinned = nullptr; // pinned host scratch (nres + 64 doubles)
+    // pinned host scratch (nres + 64 doubles).  Slots: [0, nres] results of the host entry points (res, then min |N_nn|);
+    // inside the optimiser [8] retraction flag (int), [16] f, [17] min |N_nn|, [20] step length read by a captured
+    // trial-point graph, [WB_PIN_CROSS, +22) inner products, [48, 55) phase times of tiny.cu (-DWB_TINY_TIMING builds)
+    double* h_pinned = nullptr;
     // generic scratch for stiefel / xy (lazy, sized on demand)
     cplx* d_tmp1 = nullptr; size_t tmp1_elems = 0;
     cplx* d_tmp2 = nullptr; size_t tmp2_elems = 0;

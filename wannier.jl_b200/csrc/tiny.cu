@@ -54,7 +54,6 @@ struct TinyArgs {
     int split_valid;
     const cplx* x;                 // base point
     const cplx* s;                 // direction (nullptr: evaluate at retract(x))
-    const double* alpha_dev;       // step length in device memory (nullptr: `alpha`)
     double alpha;
     cplx* xn;                      // trial point (may alias x when s == nullptr)
     cplx* gn;                      // projected gradient at xn
@@ -82,10 +81,12 @@ __device__ __forceinline__ double tiny_block_sum(double v, double* sh) {
     return t;
 }
 
+// (The helpers are __noinline__: the kernel runs once per launch on cold instruction caches, and with three inlined
+// copies of each iteration it measured 8 % slower end to end.)
 // A (nrow x ncol, column-major, ld = nrow, shared memory) <- its polar factor; P: ncol x ncol scratch, T: nrow x ncol
 // scratch.  The iteration of retract_small_kernel: stop when ||A^H A - I||_F < tol was measured BEFORE the last update
 // (which takes err to ~err^2); first pass scaled by ||A^H A||_F^(-1/2) when sigma_max^2 may exceed 3.
-__device__ bool tiny_polar(cplx* A, cplx* P, cplx* T, int nrow, int ncol, double* red) {
+__device__ __noinline__ bool tiny_polar(cplx* A, cplx* P, cplx* T, int nrow, int ncol, double* red) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     bool converged = false;
     cplx* cur = A;
@@ -143,8 +144,64 @@ __device__ bool tiny_polar(cplx* A, cplx* P, cplx* T, int nrow, int ncol, double
     return converged;
 }
 
+// The same iteration run by ONE warp (barriers become __syncwarp, reductions shuffles) for matrices of at most 128
+// elements with ncol <= 8: at those sizes a block-wide step is all barrier latency, and the two factors of the (X, Y)
+// parametrisation can iterate side by side on two warps.  P and T are private to the calling warp.
+__device__ __forceinline__ bool tiny_polar_fits_warp(int nrow, int ncol) { return nrow * ncol <= 128 && ncol <= 8; }
+__device__ __noinline__ bool tiny_polar_warp(cplx* A, cplx* P, cplx* T, int nrow, int ncol) {
+    const int lane = threadIdx.x & 31;
+    bool converged = false;
+    cplx* cur = A;
+    cplx* nxt = T;
+    for (int it = 0; it < 100 && !converged; it++) {
+        cplx pv[2];
+        double e2 = 0.0, f2 = 0.0;
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+            const int e = lane + 32 * q;
+            if (e < ncol * ncol) {
+                const int i = e % ncol, j = e / ncol;
+                cplx acc = make_double2(0.0, 0.0);
+                for (int m = 0; m < nrow; m++) cfma_conj(acc, cur[i * nrow + m], cur[j * nrow + m]);
+                pv[q] = acc;
+                const double dx = acc.x - (i == j ? 1.0 : 0.0);
+                e2 += dx * dx + acc.y * acc.y;
+                f2 += acc.x * acc.x + acc.y * acc.y;
+            }
+        }
+        const double err = sqrt(warp_sum(e2));
+        const double fro = sqrt(warp_sum(f2));
+        if (!(err == err)) break;   // NaN input
+        converged = err < 2e-8;
+        const double sc = (it == 0 && err >= 1.9) ? rsqrt(fro) : 1.0;
+        const double s3 = 0.5 * sc * sc * sc;
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+            const int e = lane + 32 * q;
+            if (e < ncol * ncol) {
+                const int i = e % ncol, j = e / ncol;
+                P[e] = make_double2((i == j ? 1.5 * sc : 0.0) - s3 * pv[q].x, -s3 * pv[q].y);
+            }
+        }
+        __syncwarp();
+        for (int e = lane; e < nrow * ncol; e += 32) {
+            const int m = e % nrow, n = e / nrow;
+            cplx acc = make_double2(0.0, 0.0);
+            for (int l = 0; l < ncol; l++) cfma(acc, cur[l * nrow + m], P[n * ncol + l]);
+            nxt[e] = acc;
+        }
+        __syncwarp();
+        cplx* t = cur; cur = nxt; nxt = t;
+    }
+    if (cur != A) {
+        for (int e = lane; e < nrow * ncol; e += 32) A[e] = cur[e];
+        __syncwarp();
+    }
+    return converged;
+}
+
 // G (nrow x ncol, shared) <- G - X (X^H G + G^H X)/2; S: ncol x ncol scratch, T: nrow x ncol scratch
-__device__ void tiny_project(const cplx* X, cplx* G, cplx* S, cplx* T, int nrow, int ncol) {
+__device__ __noinline__ void tiny_project(const cplx* X, cplx* G, cplx* S, cplx* T, int nrow, int ncol) {
     const int tid = threadIdx.x;
     for (int e = tid; e < ncol * ncol; e += WB_TINY_THREADS) {
         const int i = e % ncol, j = e / ncol;
@@ -198,7 +255,9 @@ __global__ void __launch_bounds__(WB_TINY_THREADS) tiny_trial_kernel(TinyArgs a)
     double* ssum = dst0 + (size_t)kper * 2 * nn * nw;   // [nsums]
     double* sfro = ssum + nsums;                     // [nn]
     double* red = sfro + nn;                         // [8]
-    __shared__ int s_ok;
+    __shared__ int s_ok, s_fail;
+    if (tid == 0) s_fail = 0;
+    __syncthreads();
 #define SLOT_POINTERS(slot)                                                                   \
     cplx* sU = st0 + (size_t)(slot) * state_c;            /* [mat]  U_k               */      \
     cplx* sX = sU + mat;                                  /* [nxx]  X_k (mode 1)      */      \
@@ -216,7 +275,7 @@ __global__ void __launch_bounds__(WB_TINY_THREADS) tiny_trial_kernel(TinyArgs a)
     TT(0);
 
     // ---- phase 1: trial point and its retraction -------------------------------------------------------------
-    const double alpha = a.s ? (a.alpha_dev ? *a.alpha_dev : a.alpha) : 0.0;
+    const double alpha = a.s ? a.alpha : 0.0;
     bool ok = true;
     for (int slot = 0, k = blockIdx.x; slot < kper && k < nk; slot++, k += gridDim.x) {
         cplx* sU = st0 + (size_t)slot * state_c;
@@ -232,8 +291,14 @@ __global__ void __launch_bounds__(WB_TINY_THREADS) tiny_trial_kernel(TinyArgs a)
                 if (e < nxx) sX[e] = v; else sY[e - nxx] = v;
             }
             __syncthreads();
-            ok = tiny_polar(sX, sP, sT, nw, nw, red) && ok;
-            ok = tiny_polar(sY, sP, sT, nb, nw, red) && ok;
+            if (tiny_polar_fits_warp(nb, nw)) {   // both factors side by side: warp 0 iterates on X_k, warp 1 on Y_k
+                if (tid < 32) { if (!tiny_polar_warp(sX, sP, sGX, nw, nw)) s_fail = 1; }
+                else if (tid < 64) { if (!tiny_polar_warp(sY, sG, sT, nb, nw)) s_fail = 1; }
+                __syncthreads();
+            } else {
+                ok = tiny_polar(sX, sP, sT, nw, nw, red) && ok;
+                ok = tiny_polar(sY, sP, sT, nb, nw, red) && ok;
+            }
             for (int e = tid; e < vlen; e += WB_TINY_THREADS) xnk[e] = e < nxx ? sX[e] : sY[e - nxx];
             for (int e = tid; e < mat; e += WB_TINY_THREADS) {   // U = Y X
                 const int m = e % nb, n = e / nb;
@@ -249,12 +314,17 @@ __global__ void __launch_bounds__(WB_TINY_THREADS) tiny_trial_kernel(TinyArgs a)
                 sU[e] = v;
             }
             __syncthreads();
-            ok = tiny_polar(sU, sP, sT, nb, nw, red) && ok;
+            if (tiny_polar_fits_warp(nb, nw)) {
+                if (tid < 32) { if (!tiny_polar_warp(sU, sP, sT, nb, nw)) s_fail = 1; }
+                __syncthreads();
+            } else {
+                ok = tiny_polar(sU, sP, sT, nb, nw, red) && ok;
+            }
             for (int e = tid; e < mat; e += WB_TINY_THREADS) xnk[e] = sU[e];   // mode 0: a.U == a.xn
         }
         __syncthreads();
     }
-    if (!ok && tid == 0) atomicMax(a.flag, a.epoch);
+    if ((!ok || s_fail) && tid == 0) atomicMax(a.flag, a.epoch);
     TT(1);
     __threadfence();
     grid.sync();
@@ -568,7 +638,7 @@ int wb_tiny_trial(wb200_ctx* ctx, int mode, const cplx* x, const cplx* s, double
     a.has_penalty = ctx->has_penalty; a.lambda = ctx->lambda; a.r0 = ctx->d_r0; a.wsum = ctx->wsum;
     ctx->split_valid = nb == nw;
     a.split_valid = ctx->split_valid;
-    a.x = x; a.s = s; a.alpha_dev = nullptr; a.alpha = alpha; a.xn = xn; a.gn = gn;
+    a.x = x; a.s = s; a.alpha = alpha; a.xn = xn; a.gn = gn;
     a.U = mode == 1 ? ctx->d_U : xn;
     a.part = ctx->d_part; a.pmin = ctx->d_pmin; a.dpart = ctx->d_tiny;
     a.res = ctx->d_res; a.dmin = ctx->d_min;
