@@ -305,7 +305,8 @@ def test_disentangle_driver(w, silicon):
     ("fcc", (4, 4, 4), 12, 8, 4),      # the Si2 shape of benchmark/bench_disentangle.jl: (X, Y) chain, frozen bands
     ("tetragonal", (5, 5, 1), 16, 5, 3),   # self-neighbours with G != 0, few Wannier functions, 16 bands
     ("cubic", (2, 2, 2), 9, 9, 9),     # every band frozen at every k (the n_froz == n_wann branch, disentangle.jl:390)
-    ("cubic", (6, 6, 6), 8, 8, 0),     # 216 k-points: more CTAs than SMs
+    ("cubic", (6, 6, 6), 8, 8, 0),     # 216 k-points: more CTAs than SMs, the global sums formed once (two-level)
+    ("cubic", (10, 8, 8), 6, 6, 0),    # 640 k-points: two k-points per CTA by the plan itself
     ("fcc", (5, 5, 5), 18, 9, 5),      # the band counts of BASELINE config 2 (Cu-like), n_bands > 16
 ])
 def test_tiny_trial_kernel_matches_general_path(w, lat, grid, nb, nw, nfroz):

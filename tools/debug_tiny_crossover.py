@@ -8,7 +8,10 @@ w = ge.load_package()
 shapes = [("fcc", (4, 4, 4), 4, 4, 0), ("fcc", (4, 4, 4), 8, 8, 0), ("fcc", (4, 4, 4), 12, 8, 4), ("fcc", (4, 4, 4), 12, 12, 0),
           ("fcc", (4, 4, 4), 16, 16, 0), ("bcc", (4, 4, 4), 16, 16, 0), ("fcc", (6, 6, 6), 8, 8, 0), ("fcc", (8, 8, 8), 8, 8, 0),
           ("fcc", (6, 6, 6), 12, 12, 0), ("fcc", (8, 8, 8), 12, 8, 4), ("fcc", (6, 6, 6), 18, 9, 5), ("fcc", (9, 9, 9), 18, 9, 5),
-          ("fcc", (4, 4, 4), 24, 24, 0), ("fcc", (4, 4, 4), 20, 12, 6)]
+          ("fcc", (4, 4, 4), 24, 24, 0), ("fcc", (4, 4, 4), 20, 12, 6), ("fcc", (10, 10, 10), 12, 8, 4),
+          ("cubic", (12, 12, 10), 8, 8, 0), ("fcc", (12, 12, 12), 6, 6, 0), ("fcc", (10, 10, 10), 4, 4, 0)]
+if os.environ.get("WB_LADDER") == "big":
+    shapes = shapes[-6:]
 from oracle import spread_oracle as so      # start point of the (X, Y) runs only
 for lat, grid, nb, nw, nfroz in shapes:
     st, M, U = w.synthetic.make_model_arrays(lat, grid, nb, nw)

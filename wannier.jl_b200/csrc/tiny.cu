@@ -1,9 +1,9 @@
 // tiny.cu — one trial point of the optimiser's line search in ONE cooperative launch, for the problem sizes the
 // reference's own benchmark suite runs (benchmark/bench_maxloc.jl: Si2_valence, 4 WFs, 64 k-points;
-// bench_disentangle.jl: Si2, 12 bands -> 8 WFs) and their neighbourhood: n_bands <= 32 as far as shared memory
-// allows, one CTA per k-point, at most two CTAs per SM (<= 296 k-points on a B200) — where it measures 1.1-1.5 x
-// faster than the chain of general kernels; beyond that the general kernels run (tools/debug_tiny_crossover.py).
-// (The kernel itself handles several k-points per CTA in slots of shared memory; the plan does not use that.)
+// bench_disentangle.jl: Si2, 12 bands -> 8 WFs) and their neighbourhood: at most 24 k complex multiply-adds per
+// k-point (4 x 4 ... 12 x 12, 18 -> 9), one CTA per k-point while the grid is co-resident (592 k-points on a B200) and
+// up to four k-points per CTA, in slots of shared memory, beyond (8 WFs on a 12 x 12 x 10 grid) — where it measures
+// 1.1-1.8 x faster than the chain of general kernels (tools/debug_tiny_crossover.py, profiles/r4y_tiny_crossover.txt).
 //
 // At those sizes one evaluation is ~0.3-2 MFLOP: the arithmetic of a whole trial point
 //     xn = retract(x + a s);  f, G = spread and gradient at xn;  gn = project(G, xn);  dphi = <gn, s>
@@ -39,6 +39,8 @@ namespace cg = cooperative_groups;
 struct TinyArgs {
     int mode, nb, nw, nk, nn;
     int kper;                      // k-points per CTA (CTA c owns k = c, c + gridDim.x, ...)
+    int two_level;                 // the global sums are formed once (CTA j adds column j) instead of in every CTA
+    double* gsums;                 // [nsums] (ctx->d_sums)
     int mu_global;                 // the rotated overlaps MU_kb wait for phase 3 in global memory (L2), not in the slots
     cplx* MUg;                     // [pairs][nb*nw] (ctx->d_MU)
     const int32_t* kpb;
@@ -410,13 +412,28 @@ __global__ void __launch_bounds__(WB_TINY_THREADS) tiny_trial_kernel(TinyArgs a)
     TT(4);
 
     // ---- phase 3: global sums (every CTA, same order), spread scalars, gradient of k, projection, <gn_k, s_k> --
-    for (int j = tid; j < nsums; j += WB_TINY_THREADS) {   // four interleaved partial sums: the loads pipeline
-        double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
-        const double* p = a.part + (long long)j * nk;
-        int q = 0;
-        for (; q + 3 < nk; q += 4) { t0 += p[q]; t1 += p[q + 1]; t2 += p[q + 2]; t3 += p[q + 3]; }
-        for (; q < nk; q++) t0 += p[q];
-        ssum[j] = (t0 + t1) + (t2 + t3);
+    if (a.two_level) {
+        // many k-points: re-adding all partial sums in every CTA is O(nk^2) loads.  CTA j < nsums adds column j (all
+        // its threads, fixed order), one more grid sync, then everybody reads the nsums results.
+        for (int j = blockIdx.x; j < nsums; j += gridDim.x) {
+            const double* p = a.part + (long long)j * nk;
+            double t = 0.0;
+            for (int q = tid; q < nk; q += WB_TINY_THREADS) t += p[q];
+            t = tiny_block_sum(t, red);
+            if (tid == 0) a.gsums[j] = t;
+        }
+        __threadfence();
+        grid.sync();
+        for (int j = tid; j < nsums; j += WB_TINY_THREADS) ssum[j] = a.gsums[j];
+    } else {
+        for (int j = tid; j < nsums; j += WB_TINY_THREADS) {   // four interleaved partial sums: the loads pipeline
+            double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
+            const double* p = a.part + (long long)j * nk;
+            int q = 0;
+            for (; q + 3 < nk; q += 4) { t0 += p[q]; t1 += p[q + 1]; t2 += p[q + 2]; t3 += p[q + 3]; }
+            for (; q < nk; q++) t0 += p[q];
+            ssum[j] = (t0 + t1) + (t2 + t3);
+        }
     }
     __syncthreads();
     const double inv = 1.0 / (double)nk;
@@ -589,14 +606,12 @@ bool wb_tiny_usable(wb200_ctx* ctx, int mode) {
             ctx->tiny_ok = 0;
             return false;
         }
-        // Measured (tools/debug_tiny_crossover.py, profiles/r4_summary.md): the fused kernel beats the chain of general
-        // kernels by 1.1-1.5 x while there are at most ~2 CTAs per SM with one k-point each (64 and 216 k-points, n_bands
-        // 4-20) and loses beyond (512 k-points: 0.84-0.92 x, 729: 0.81 x — every CTA re-adds the partial sums of all k,
-        // and the latency-bound per-k chains no longer have an SM to themselves).  So: one k-point per CTA, at most two
-        // CTAs per SM; WB200_TINY_KPER (tests) forces several k-points per CTA regardless.
-        int kmin = 1, kmax = 1;
+        // One k-point per CTA while the grid is co-resident (register-limited to 4 CTAs of 128 threads per SM: 592
+        // k-points on a B200), then two, three, ... k-points per CTA in slots of shared memory (WB200_TINY_KPER forces a
+        // minimum, WB200_TINY_MAX_KPER caps it; measured crossover: tools/debug_tiny_crossover.py, profiles/r4_summary.md).
+        int kmin = 1, kmax = 4;
         if (const char* e = getenv("WB200_TINY_KPER")) { kmin = atoi(e) > 1 ? atoi(e) : 1; kmax = 64; }
-        if (kmax == 1 && ctx->nk > 2 * ctx->num_sms) { ctx->tiny_ok = 0; return false; }
+        if (const char* e = getenv("WB200_TINY_MAX_KPER")) kmax = atoi(e) > 0 ? atoi(e) : kmax;
         ctx->tiny_ok = 0;
         // first choice: the rotated overlaps of a k-point stay in its slot; second: they wait in global memory (L2)
         for (int mug = 0; mug < 2 && !ctx->tiny_ok; mug++)
@@ -609,6 +624,9 @@ bool wb_tiny_usable(wb200_ctx* ctx, int mode) {
                     break;
                 }
                 const int grid = (ctx->nk + kper - 1) / kper;
+                // work per CTA: measured wins up to 23 k complex multiply-adds (18 -> 9, one k-point per CTA) and at
+                // 18 k (12 -> 8, two per CTA), a loss at 117 k (18 -> 9, five per CTA): the line is drawn at 40 k
+                if (kper > 1 && (double)kper * ctx->nn * ctx->nb * ctx->nb * ctx->nw > 40e3) break;
                 if (per_sm * ctx->num_sms >= grid) {
                     ctx->tiny_ok = 1; ctx->tiny_blocks = grid; ctx->tiny_kper = kper; ctx->tiny_mu_global = mug;
                     break;
@@ -633,6 +651,7 @@ int wb_tiny_trial(wb200_ctx* ctx, int mode, const cplx* x, const cplx* s, double
     TinyArgs a{};
     a.mode = mode; a.nb = nb; a.nw = nw; a.nk = nk; a.nn = nn; a.kper = ctx->tiny_kper;
     a.mu_global = ctx->tiny_mu_global; a.MUg = ctx->d_MU;
+    a.two_level = ctx->nk > ctx->num_sms ? 1 : 0; a.gsums = ctx->d_sums;   // (by nk, not by the grid: the result does not depend on k-points per CTA)
     a.kpb = ctx->d_kpb; a.bvec = ctx->d_bvec; a.wb = ctx->d_wb; a.M = ctx->d_M;
     a.frozen = mode == 1 ? ctx->d_frozen : nullptr; a.nfrozen = ctx->d_nfrozen;
     a.has_penalty = ctx->has_penalty; a.lambda = ctx->lambda; a.r0 = ctx->d_r0; a.wsum = ctx->wsum;
