@@ -51,7 +51,7 @@ extern "C" void wb200_destroy(wb200_ctx* ctx) {
                     ctx->d_frozen, ctx->d_nfrozen, ctx->d_U, ctx->d_G, ctx->d_MU, ctx->d_N,
                     ctx->d_dN, ctx->d_fro, ctx->d_part, ctx->d_pmin, ctx->d_sums, ctx->d_res,
                     ctx->d_min, ctx->d_scal, ctx->d_red, ctx->d_zpart, ctx->d_tmp1, ctx->d_tmp2, ctx->d_XY, ctx->d_GXY,
-                    ctx->d_tiny};
+                    ctx->d_tiny, ctx->d_M_given};
     for (void* p : ptrs)
         if (p) wb_dev_free_drained(p);
     tr.mark("buffers");
@@ -185,14 +185,12 @@ extern "C" int wb200_create(wb200_ctx** out, int device, int nb, int nw, int nk_
         if (on_device) CREATE_CUDA(cudaDeviceSynchronize());
     }
     CREATE_CUDA(cudaMemcpyAsync(ctx->d_M, M, sizeof(cplx) * pairs * nb * nb, cudaMemcpyDefault, cs));  // host or device
-    cplx* m_as_given = nullptr;
     if (flags & WB200_FLAG_M_ROW_MAJOR) {   // C-order matrices: transpose here, not in the caller's interpreter
-        cplx* t = nullptr;
-        CREATE_CUDA(wb_dev_alloc(&t, sizeof(cplx) * pairs * nb * nb));
-        transpose_overlaps_kernel<<<(unsigned)pairs, 256, 0, cs>>>(nb, ctx->d_M, t);
+        ctx->d_M_given = ctx->d_M;          // (owned by the ctx until the final wait below, so that every exit path frees it)
+        ctx->d_M = nullptr;
+        CREATE_CUDA(wb_dev_alloc(&ctx->d_M, sizeof(cplx) * pairs * nb * nb));
+        transpose_overlaps_kernel<<<(unsigned)pairs, 256, 0, cs>>>(nb, ctx->d_M_given, ctx->d_M);
         ctx->launches++;
-        m_as_given = ctx->d_M;
-        ctx->d_M = t;
     }
     tr.mark("uploads (enqueued)");
     ctx->h_wb.assign(bweights, bweights + nn);
@@ -209,7 +207,7 @@ extern "C" int wb200_create(wb200_ctx** out, int device, int nb, int nw, int nk_
         CREATE_FAIL(WB200_ERR_ARG, "wb200_create: WB200_FLAG_FORCE_TENSOR but the DMMA rotation kernel does not support this shape");
     ctx->rotation_kernel = ctx->dmma ? 1 : 0;
     CREATE_CUDA(cudaStreamSynchronize(cs));   // the caller's arrays (and the host vectors above) are no longer read
-    if (m_as_given) wb_dev_free_drained(m_as_given);
+    if (ctx->d_M_given) { wb_dev_free_drained(ctx->d_M_given); ctx->d_M_given = nullptr; }
     if (ctx->release_M_after_create) {        // the tensor path never reads the plain layout again
         wb_dev_free_drained(ctx->d_M);        // (only this stream ever touched it)
         ctx->d_M = nullptr;

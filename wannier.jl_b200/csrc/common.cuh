@@ -137,6 +137,7 @@ struct wb200_ctx {
     double* d_bvec = nullptr;    // [nk][nn][3]
     double* d_wb = nullptr;      // [nn]
     cplx* d_M = nullptr;         // [nk][nn][nb*nb] col-major (generic path / exact N)
+    cplx* d_M_given = nullptr;   // WB200_FLAG_M_ROW_MAJOR: the overlaps as uploaded, until wb200_create has transposed them
     int release_M_after_create = 0;   // the tensor plan has re-tiled M: wb200_create releases d_M after its final wait
     double wsum = 0.0;           // sum_b w_b
     std::vector<double> h_wb;
