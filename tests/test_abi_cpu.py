@@ -26,6 +26,17 @@ def test_library_exports_every_declared_symbol(w):
     assert b"sm_100a" in w.lib.load().wb200_version()
 
 
+def test_flag_constants_match_the_header(w):
+    """the ctypes side must pass the bit values include/wannier_b200.h defines"""
+    hdr = open(os.path.join(ROOT, "include", "wannier_b200.h")).read()
+    flags = dict(re.findall(r"#define\s+WB200_FLAG_([A-Z_]+)\s+(\d+)u", hdr))
+    assert set(flags) >= {"DEFAULT", "NO_TENSOR", "FORCE_TENSOR", "NO_FUSED_TRIAL", "M_ROW_MAJOR"}
+    for name, val in flags.items():
+        assert getattr(w.lib, "FLAG_" + name) == int(val), name
+    vals = [int(v) for k, v in flags.items() if k != "DEFAULT"]
+    assert len(set(vals)) == len(vals) and all(v & (v - 1) == 0 for v in vals)      # distinct single bits
+
+
 def test_no_cpu_fallback_create_fails_without_device(w):
     import torch
     if torch.cuda.is_available():
