@@ -88,12 +88,11 @@ for name in ([c for c in _all if c in _sel.split(",")] if _sel else _all):
                     N, _ = ctx.rotate_overlaps(hU)
                     r["rotate_overlaps_host_ms"] = timed(lambda: ctx.rotate_overlaps(hU), lambda: None, min_s=0.2, nmin=3)
             if nb > nw:    # (X, Y) chain and the device disentangle driver
-                from oracle import spread_oracle as so      # host setup of the start point only
                 frozen = w.synthetic.make_frozen(nk, nb, 5)
                 ctx.set_frozen(frozen)
                 U = np.ascontiguousarray(dU.cpu().numpy().transpose(0, 2, 1))
-                X, Y = so.U_to_X_Y(U, frozen)
-                XY = np.ascontiguousarray(so.X_Y_to_XY(X, Y))
+                X, Y = w.api.U_to_X_Y(U, frozen)          # the product's own setup step (wb200_u_to_xy)
+                XY = np.ascontiguousarray(w.api.X_Y_to_XY(X, Y))
                 Gxy = np.empty_like(XY)
                 r["fg_xy_host_ms"] = timed(lambda: ctx.fg_xy(XY, G=Gxy), lambda: None, min_s=0.2, nmin=3)
                 for rep in range(2):               # first call: lazy kernel loading, one-off allocations

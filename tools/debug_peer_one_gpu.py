@@ -3,7 +3,6 @@ import sys, os, numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import __graft_entry__ as ge
 w = ge.load_package()
-from oracle import spread_oracle as so
 case = sys.argv[1]
 lat, grid, nb, nw, ndev = {"big": ("cubic", (4, 2, 2), 72, 72, 2), "small": ("bcc", (4, 2, 2), 16, 16, 2)}[case]
 st, M, U = w.synthetic.make_model_arrays(lat, grid, nb, nw, eps=0.02)

@@ -12,7 +12,6 @@ shapes = [("fcc", (4, 4, 4), 4, 4, 0), ("fcc", (4, 4, 4), 8, 8, 0), ("fcc", (4, 
           ("cubic", (12, 12, 10), 8, 8, 0), ("fcc", (12, 12, 12), 6, 6, 0), ("fcc", (10, 10, 10), 4, 4, 0)]
 if os.environ.get("WB_LADDER") == "big":
     shapes = shapes[-6:]
-from oracle import spread_oracle as so      # start point of the (X, Y) runs only
 for lat, grid, nb, nw, nfroz in shapes:
     st, M, U = w.synthetic.make_model_arrays(lat, grid, nb, nw)
     nk, nn = st["kpb_k"].shape
@@ -22,8 +21,8 @@ for lat, grid, nb, nw, nfroz in shapes:
         if nfroz:
             frozen = w.synthetic.make_frozen(nk, nb, nfroz)
             ctx.set_frozen(frozen)
-            X, Y = so.U_to_X_Y(U, frozen)
-            x0 = np.ascontiguousarray(so.X_Y_to_XY(X, Y))
+            X, Y = w.api.U_to_X_Y(U, frozen)          # the product's own setup step (wb200_u_to_xy)
+            x0 = np.ascontiguousarray(w.api.X_Y_to_XY(X, Y))
             run = lambda x: ctx.disentangle(x, 1e-7, 1e-5, 15, 3)
         else:
             x0 = w.api.to_abi_U(U).copy()
